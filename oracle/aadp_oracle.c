@@ -1,0 +1,462 @@
+/* oracle/aadp_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See aadp_oracle.h.
+ *
+ * Plain-C restatement of the reference DP path. All four reference fills (fwd/rev x
+ * global/local, dpmatrix.h:356-1030) are one routine here, written in "flow" coordinates:
+ * a flow cell (a,b) is matrix cell (a,b) for the forward fill and (q1-a, t1-b) for the
+ * reverse fill, so the anchor is always flow (0,0), the final cell is flow (q1,t1) and every
+ * scan runs over ascending flow index -- which is ascending k in the forward fill
+ * (dpmatrix.h:459,471) and descending k in the reverse fill (dpmatrix.h:798,810).
+ *
+ * Float arithmetic keeps the reference's operation order  s = D; s -= gap; s += sim
+ * (dpmatrix.h:460-462); compile with -ffp-contract=off (oracle/Makefile).
+ */
+#include "aadp_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_NULL (-1) /* DPCell::null, dpmatrix.cpp:15 */
+
+/* ---------------------------------------------------------------- evaluator (aasubalib.h) */
+
+static int del_free(int at) { /* aasubalib.h:39-42: case local, semi_local, local_global */
+  return at == ORC_LOCAL || at == ORC_SEMI_LOCAL || at == ORC_LOCAL_GLOBAL;
+}
+static int ins_free(int at) { /* aasubalib.h:65-68: case local, semi_local, global_local */
+  return at == ORC_LOCAL || at == ORC_SEMI_LOCAL || at == ORC_GLOBAL_LOCAL;
+}
+
+static float affine(const orc_scoring* sc, int len) { /* aasubalib.h:37-38 */
+  return sc->gi + sc->ge * (float)(len - 1);
+}
+
+/* aasubalib.h:27-51. t_pos1 < t_pos2 are matrix columns; column 0 is Head, sz2-1 is Tail. */
+float orc_deletion(const orc_scoring* sc, int sz2, int t_pos1, int t_pos2) {
+  int len = t_pos2 - t_pos1 - 1;
+  if (len < 1) return 0.f;
+  if (del_free(sc->align_type) && (t_pos1 == 0 || t_pos2 == sz2 - 1)) return 0.f;
+  return affine(sc, len);
+}
+
+/* aasubalib.h:53-77 */
+float orc_insertion(const orc_scoring* sc, int sz1, int q_pos1, int q_pos2) {
+  int len = q_pos2 - q_pos1 - 1;
+  if (len < 1) return 0.f;
+  if (ins_free(sc->align_type) && (q_pos1 == 0 || q_pos2 == sz1 - 1)) return 0.f;
+  return affine(sc, len);
+}
+
+/* simmatrix.h:52-72 + aasubalib.h:17-25: borders 0, interior = substitution score */
+static void build_sim(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                      float* sim) {
+  int sz1 = Lq + 2, sz2 = Lt + 2;
+  memset(sim, 0, sizeof(float) * (size_t)sz1 * sz2);
+  for (int i = 1; i <= Lq; ++i)
+    for (int j = 1; j <= Lt; ++j)
+      sim[(size_t)i * sz2 + j] = sc->sub[(int)q[i - 1] * sc->A + (int)t[j - 1]];
+}
+
+/* ---------------------------------------------------------------- flow-coordinate helpers */
+
+typedef struct {
+  int rev, q1, t1, sz1, sz2, local;
+  const orc_scoring* sc;
+  const float* sim;
+  float* D;
+  int *pq, *pt;
+} flow_t;
+
+static size_t at(const flow_t* f, int a, int b) {
+  int i = f->rev ? f->q1 - a : a, j = f->rev ? f->t1 - b : b;
+  return (size_t)i * f->sz2 + j;
+}
+static int rowof(const flow_t* f, int a) { return f->rev ? f->q1 - a : a; }
+static int colof(const flow_t* f, int b) { return f->rev ? f->t1 - b : b; }
+
+/* gap between flow columns b0 < b1 (deletion) / flow rows a0 < a1 (insertion) */
+static float gdel(const flow_t* f, int b0, int b1) {
+  int x = colof(f, b0), y = colof(f, b1);
+  return orc_deletion(f->sc, f->sz2, x < y ? x : y, x < y ? y : x);
+}
+static float gins(const flow_t* f, int a0, int a1) {
+  int x = rowof(f, a0), y = rowof(f, a1);
+  return orc_insertion(f->sc, f->sz1, x < y ? x : y, x < y ? y : x);
+}
+static float clampl(const flow_t* f, float s) { /* dpmatrix.h:580 etc.: s = max(0.f,s) */
+  return (f->local && s < 0.f) ? 0.f : s;
+}
+static void set_tb(const flow_t* f, int a, int b, int pa, int pb, float s) { /* dpmatrix.cpp:27-32 */
+  size_t o = at(f, a, b);
+  f->D[o] = s;
+  f->pq[o] = rowof(f, pa);
+  f->pt[o] = colof(f, pb);
+}
+
+static int flow_init(flow_t* f, const uint8_t* q, int Lq, const uint8_t* t, int Lt,
+                     const orc_scoring* sc, int direction, float* score, int* prev_q, int* prev_t,
+                     float* sim) {
+  f->rev = (direction == ORC_REV);
+  f->sz1 = Lq + 2;
+  f->sz2 = Lt + 2;
+  f->q1 = f->sz1 - 1;
+  f->t1 = f->sz2 - 1;
+  f->local = (sc->align_type == ORC_LOCAL); /* dpmatrix.h:155 */
+  f->sc = sc;
+  f->sim = sim;
+  f->D = score;
+  f->pq = prev_q;
+  f->pt = prev_t;
+  build_sim(q, Lq, t, Lt, sc, sim);
+  size_t n = (size_t)f->sz1 * f->sz2;
+  for (size_t o = 0; o < n; ++o) { /* DPCell::DPCell, dpmatrix.cpp:17-25 */
+    score[o] = 0.f;
+    prev_q[o] = ORC_NULL;
+    prev_t[o] = ORC_NULL;
+  }
+  return 0;
+}
+
+/* Special cases #1/#2 (dpmatrix.h:374-390, 712-728): one sequence is empty. Not clamped in
+ * the local variants either (dpmatrix.h:557-573). Returns 1 if handled. */
+static int degenerate(flow_t* f) {
+  float s;
+  if (f->q1 == 1) {
+    s = f->D[at(f, 0, 0)];
+    s -= gdel(f, 0, f->t1);
+    s += f->sim[at(f, f->q1, f->t1)];
+    set_tb(f, f->q1, f->t1, 0, 0, s);
+    return 1;
+  }
+  if (f->t1 == 1) {
+    s = f->D[at(f, 0, 0)];
+    s -= gins(f, 0, f->q1);
+    s += f->sim[at(f, f->q1, f->t1)];
+    set_tb(f, f->q1, f->t1, 0, 0, s);
+    return 1;
+  }
+  return 0;
+}
+
+/* boundary row/column of the flow (dpmatrix.h:408-426, 746-764, 579-599, 920-940) */
+static void boundary(flow_t* f) {
+  float s0 = f->D[at(f, 0, 0)], s;
+  s = s0 + f->sim[at(f, 1, 1)];
+  set_tb(f, 1, 1, 0, 0, clampl(f, s));
+  for (int b = 2; b < f->t1; ++b) {
+    s = s0;
+    s -= gdel(f, 0, b);
+    s += f->sim[at(f, 1, b)];
+    set_tb(f, 1, b, 0, 0, clampl(f, s));
+  }
+  for (int a = 2; a < f->q1; ++a) {
+    s = s0;
+    s -= gins(f, 0, a);
+    s += f->sim[at(f, a, 1)];
+    set_tb(f, a, 1, 0, 0, clampl(f, s));
+  }
+}
+
+/* final cell (dpmatrix.h:504-534, 844-874, 654-687, 995-1028) */
+static void final_cell(flow_t* f, int repro_rev_bug) {
+  int q1 = f->q1, t1 = f->t1;
+  float simf = f->sim[at(f, q1, t1)], s;
+  int oa = q1 - 1, ob = t1 - 1, from_col = 0;
+  float os = clampl(f, f->D[at(f, oa, ob)] + simf);
+  for (int k = 1; k < t1; ++k) {
+    s = f->D[at(f, q1 - 1, k)];
+    s -= gdel(f, k, t1);
+    s += simf;
+    s = clampl(f, s);
+    if (s > os) { oa = q1 - 1; ob = k; os = s; }
+  }
+  for (int k = 1; k < q1; ++k) {
+    s = f->D[at(f, k, t1 - 1)];
+    s -= gins(f, k, q1);
+    s += simf;
+    s = clampl(f, s);
+    if (s > os) { oa = k; ob = t1 - 1; os = s; from_col = 1; }
+  }
+  set_tb(f, q1, t1, oa, ob, os);
+  /* dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 (a matrix column) for the
+   * left-column candidates instead of t0_p1. The local variant is correct (dpmatrix.h:1022). */
+  if (f->rev && !f->local && repro_rev_bug && from_col) f->pt[at(f, q1, t1)] = t1 - 1;
+}
+
+/* ---------------------------------------------------------------- literal O(n^3) fill */
+
+int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+             int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
+             float* sim_out) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  size_t n = (size_t)(Lq + 2) * (Lt + 2);
+  float* sim = sim_out ? sim_out : (float*)malloc(sizeof(float) * n);
+  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
+  /* dpmatrix.h:306-307: both corner scores are zeroed; bounds check :360 */
+  if (f.q1 <= 0 || f.t1 <= 0) { if (!sim_out) free(sim); return 1; }
+  if (!degenerate(&f)) {
+    boundary(&f);
+    for (int a = 2; a < f.q1; ++a) {
+      for (int b = 2; b < f.t1; ++b) {
+        float simc = sim[at(&f, a, b)], s;
+        int oa = a - 1, ob = b - 1;
+        float os = clampl(&f, score[at(&f, oa, ob)] + simc); /* match, :453-456 */
+        for (int k = 1; k < b - 1; ++k) {                     /* deletions, :459-468 */
+          s = score[at(&f, a - 1, k)];
+          s -= gdel(&f, k, b);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = a - 1; ob = k; os = s; }
+        }
+        for (int k = 1; k < a - 1; ++k) {                     /* insertions, :471-480 */
+          s = score[at(&f, k, b - 1)];
+          s -= gins(&f, k, a);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = k; ob = b - 1; os = s; }
+        }
+        set_tb(&f, a, b, oa, ob, os);
+      }
+    }
+    final_cell(&f, repro_rev_bug);
+  }
+  if (!sim_out) free(sim);
+  return 0;
+}
+
+/* ---------------------------------------------------------------- exact O(n^2) fill */
+
+int orc_fill_fast(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                  int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  size_t n = (size_t)(Lq + 2) * (Lt + 2);
+  float* sim = (float*)malloc(sizeof(float) * n);
+  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
+  if (f.q1 <= 0 || f.t1 <= 0) { free(sim); return 1; }
+  if (!degenerate(&f)) {
+    boundary(&f);
+    /* colorg[b] = flow row k (<= a-2) maximising D[k][b] - w(a-k-1), smallest k on ties */
+    int* colorg = (int*)malloc(sizeof(int) * (size_t)(f.t1 + 1));
+    for (int b = 0; b <= f.t1; ++b) colorg[b] = 0;
+    for (int a = 2; a < f.q1; ++a) {
+      int roworg = 0; /* flow column k (<= b-2) maximising D[a-1][k] - w(b-k-1) */
+      for (int b = 2; b < f.t1; ++b) {
+        float simc = sim[at(&f, a, b)], s;
+        int oa = a - 1, ob = b - 1;
+        float os = clampl(&f, score[at(&f, oa, ob)] + simc);
+        if (b >= 3) { /* row running maximum: extend the old origin or open at b-2 */
+          int kn = b - 2;
+          if (roworg == 0) roworg = kn;
+          else {
+            float ext = score[at(&f, a - 1, roworg)] - gdel(&f, roworg, b);
+            float opn = score[at(&f, a - 1, kn)] - gdel(&f, kn, b);
+            if (opn > ext) roworg = kn; /* ties keep the smaller k, as the ascending strict-> scan */
+          }
+          s = score[at(&f, a - 1, roworg)];
+          s -= gdel(&f, roworg, b);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = a - 1; ob = roworg; os = s; }
+        }
+        if (a >= 3) { /* column running maximum for column b-1 */
+          int kn = a - 2, ko = colorg[b - 1];
+          if (ko == 0) ko = kn;
+          else {
+            float ext = score[at(&f, ko, b - 1)] - gins(&f, ko, a);
+            float opn = score[at(&f, kn, b - 1)] - gins(&f, kn, a);
+            if (opn > ext) ko = kn;
+          }
+          colorg[b - 1] = ko;
+          s = score[at(&f, ko, b - 1)];
+          s -= gins(&f, ko, a);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = ko; ob = b - 1; os = s; }
+        }
+        set_tb(&f, a, b, oa, ob, os);
+      }
+    }
+    free(colorg);
+    final_cell(&f, repro_rev_bug);
+  }
+  free(sim);
+  return 0;
+}
+
+/* ---------------------------------------------------------------- optimal tracebacks */
+
+/* optimal.h:47-124 */
+int orc_optimal_fwd(const float* score, const int* prev_q, const int* prev_t, int sz1, int sz2,
+                    int is_local, int* pairs, int max_pairs, int* npairs, float* ali_score) {
+  /* the list is built back-to-front with prepend(); collect reversed, then flip */
+  int n = 0, ql = sz1 - 1, tl = sz2 - 1, rc = 0;
+  int cap = sz1 + sz2 + 4;
+  int* tmp = (int*)malloc(sizeof(int) * 2 * (size_t)cap);
+#define PUSHF(a, b) do { if (n < cap) { tmp[2 * n] = (a); tmp[2 * n + 1] = (b); } ++n; } while (0)
+  if (!is_local) {
+    *ali_score = score[(size_t)ql * sz2 + tl];
+    PUSHF(ql, tl);
+    while (ql > 0) { /* optimal.h:66-71 */
+      size_t o = (size_t)ql * sz2 + tl;
+      int nq = prev_q[o], nt = prev_t[o];
+      ql = nq; tl = nt;
+      PUSHF(ql, tl);
+      if (ql < 0 || tl < 0 || n > cap) break;
+    }
+    if (ql != 0 || tl != 0) rc = 3; /* optimal.h:74 */
+  } else {
+    PUSHF(ql, tl);
+    /* find_max, optimal.h:106-124: seed at (sz1-2,sz2-2), row-major scan, strict < */
+    int mq = sz1 - 2, mt = sz2 - 2;
+    float s = score[(size_t)mq * sz2 + mt];
+    for (int i = 0; i < sz1 - 1; ++i)
+      for (int j = 0; j < sz2 - 1; ++j)
+        if (s < score[(size_t)i * sz2 + j]) { mq = i; mt = j; s = score[(size_t)i * sz2 + j]; }
+    ql = mq; tl = mt;
+    *ali_score = s;
+    PUSHF(ql, tl);
+    while (ql > 0) { /* optimal.h:96-102 */
+      size_t o = (size_t)ql * sz2 + tl;
+      int nq = prev_q[o], nt = prev_t[o];
+      ql = nq; tl = nt;
+      if (ql < 0 || tl < 0) break;
+      if (score[(size_t)ql * sz2 + tl] <= 0.f) break;
+      PUSHF(ql, tl);
+    }
+    if (ql != 0 && tl != 0) PUSHF(0, 0); /* optimal.h:104 */
+  }
+#undef PUSHF
+  int m = n < cap ? n : cap;
+  for (int k = 0; k < m && k < max_pairs; ++k) {
+    pairs[2 * k] = tmp[2 * (m - 1 - k)];
+    pairs[2 * k + 1] = tmp[2 * (m - 1 - k) + 1];
+  }
+  *npairs = m;
+  free(tmp);
+  return rc;
+}
+
+/* optimal_rev.h:47-131 */
+int orc_optimal_rev(const float* score, const int* prev_q, const int* prev_t, int sz1, int sz2,
+                    int is_local, int* pairs, int max_pairs, int* npairs, float* ali_score) {
+  int n = 0, ql = sz1 - 1, tl = sz2 - 1, qf = 0, tf = 0, rc = 0;
+#define PUSHR(a, b) do { if (n < max_pairs) { pairs[2 * n] = (a); pairs[2 * n + 1] = (b); } ++n; } while (0)
+  if (!is_local) {
+    *ali_score = score[0];
+    PUSHR(0, 0);
+    int guard = 0;
+    while (qf < ql) { /* optimal_rev.h:68-73 */
+      size_t o = (size_t)qf * sz2 + tf;
+      int nq = prev_q[o], nt = prev_t[o];
+      qf = nq; tf = nt;
+      PUSHR(qf, tf);
+      if (qf < 0 || tf < 0 || ++guard > ql + tl + 4) { rc = 3; break; }
+    }
+    if (qf != ql || tf != tl) rc = 3; /* optimal_rev.h:76 */
+  } else {
+    float s = score[0]; /* find_max, optimal_rev.h:114-131 */
+    int mq = 0, mt = 0;
+    for (int i = sz1 - 1; i > 0; --i)
+      for (int j = sz2 - 1; j > 0; --j)
+        if (s < score[(size_t)i * sz2 + j]) { mq = i; mt = j; s = score[(size_t)i * sz2 + j]; }
+    PUSHR(0, 0);
+    qf = mq; tf = mt;
+    *ali_score = s;
+    PUSHR(qf, tf);
+    while (qf < ql) { /* optimal_rev.h:102-108 */
+      size_t o = (size_t)qf * sz2 + tf;
+      int nq = prev_q[o], nt = prev_t[o];
+      qf = nq; tf = nt;
+      if (qf < 0 || tf < 0) break;
+      if (score[(size_t)qf * sz2 + tf] <= 0.f) break;
+      PUSHR(qf, tf);
+    }
+    if (qf != ql && tf != tl) PUSHR(ql, tl); /* optimal_rev.h:110 */
+  }
+#undef PUSHR
+  *npairs = n;
+  return rc;
+}
+
+/* ---------------------------------------------------------------- near-optimal cell set */
+
+float orc_threshold(float opt, float delta_ratio) { /* cw.h:86-88 */
+  float thr = (1.f - delta_ratio) * opt;
+  float alt = opt - 0.1f;
+  return thr < alt ? thr : alt;
+}
+
+long orc_nearopt_mask(const float* F, const float* R, const float* sim, int sz1, int sz2,
+                      float thr, uint8_t* mask) {
+  long cnt = 0;
+  memset(mask, 0, (size_t)sz1 * sz2);
+  for (int i = 1; i < sz1 - 1; ++i)
+    for (int j = 1; j < sz2 - 1; ++j) {
+      size_t o = (size_t)i * sz2 + j;
+      float v = F[o] + R[o];
+      v -= sim[o];
+      if (v > thr) { mask[o] = 1; ++cnt; }
+    }
+  return cnt;
+}
+
+/* ucw.h:88-191 as a cell-marking recursion. */
+typedef struct {
+  const orc_scoring* sc;
+  const float *F, *sim;
+  int sz1, sz2;
+  float thr;
+  long count, limit;
+  uint8_t* mark;
+} ucw_t;
+
+static void ucw_branch(ucw_t* u, int q0, int t0, float curr) {
+  if (u->count < 0) return;
+  int sz2 = u->sz2;
+  if (q0 == 1 || t0 == 1) { /* base case, ucw.h:94-101 */
+    u->mark[(size_t)q0 * sz2 + t0] = 1;
+    u->mark[0] = 1;
+    if (++u->count > u->limit) u->count = -1;
+    return;
+  }
+  float r = curr + u->sim[(size_t)q0 * sz2 + t0]; /* ucw.h:141 */
+  float f = u->F[(size_t)(q0 - 1) * sz2 + (t0 - 1)];
+  int any = 0;
+  if (f + r > u->thr) { /* ucw.h:144-150 */
+    any = 1;
+    ucw_branch(u, q0 - 1, t0 - 1, r);
+  }
+  for (int i = t0 - 2; i > 0; --i) { /* ucw.h:154-165 */
+    f = u->F[(size_t)(q0 - 1) * sz2 + i];
+    float g = orc_deletion(u->sc, u->sz2, i, t0);
+    if (f + r - g > u->thr) {
+      any = 1;
+      ucw_branch(u, q0 - 1, i, r - g);
+    }
+  }
+  for (int j = q0 - 2; j > 0; --j) { /* ucw.h:169-180 */
+    f = u->F[(size_t)j * sz2 + (t0 - 1)];
+    float g = orc_insertion(u->sc, u->sz1, j, q0);
+    if (f + r - g > u->thr) {
+      any = 1;
+      ucw_branch(u, j, t0 - 1, r - g);
+    }
+  }
+  if (any) u->mark[(size_t)q0 * sz2 + t0] = 1;
+  /* any == 0 is the opt_path fallback (ucw.h:182-189); it cannot happen in exact arithmetic
+   * because the optimal predecessor of a cell that passed always passes; flagged to the caller. */
+  else if (u->count >= 0) u->count = -2;
+}
+
+long orc_ucw_cells(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                   const float* F, const float* sim, float thr, long max_alignments,
+                   uint8_t* cell_union) {
+  (void)q; (void)t;
+  ucw_t u;
+  u.sc = sc; u.F = F; u.sim = sim; u.sz1 = Lq + 2; u.sz2 = Lt + 2; u.thr = thr;
+  u.count = 0; u.limit = max_alignments; u.mark = cell_union;
+  memset(cell_union, 0, (size_t)u.sz1 * u.sz2);
+  ucw_branch(&u, u.sz1 - 1, u.sz2 - 1, 0.f);
+  return u.count;
+}

@@ -1,0 +1,85 @@
+/* oracle/aadp_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of the reference's DP hot path (christang/alignment-algos):
+ * the general-gap matrix fill of dpmatrix.h driven by AASubstitutionEval (aasubalib.h),
+ * the optimal tracebacks of optimal.h / optimal_rev.h and the near-optimal cell set the
+ * enumerators of ucw.h / cw.h consume.
+ *
+ * PARITY PIN: every function here is checked against the real reference compiled from
+ * /root/reference (oracle/_ref/libaadp_ref.so, built by oracle/Makefile) in
+ * tests/test_oracle_vs_reference.py, and against the committed golden vectors in
+ * tests/golden/ (generated from the real reference by oracle/gen_golden.py). The reference
+ * ships no tests or golden vectors of its own.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this library.
+ */
+#ifndef AADP_ORACLE_H
+#define AADP_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* alib.h:20-26 */
+enum { ORC_GLOBAL_LOCAL = 0, ORC_GLOBAL = 1, ORC_LOCAL_GLOBAL = 2, ORC_LOCAL = 3, ORC_SEMI_LOCAL = 4 };
+/* dpmatrix.h:23-26 */
+enum { ORC_FWD = 1, ORC_REV = 2 };
+
+typedef struct {
+  int A;            /* alphabet size; residue codes are 0..A-1 */
+  const float* sub; /* A x A row-major substitution scores: sub[q_code*A + t_code] */
+  float gi, ge;     /* gap(len) = gi + ge*(len-1), aasubalib.h:37-38 */
+  int align_type;   /* alib.h:20-26 */
+} orc_scoring;
+
+/* Sequences are residue codes WITHOUT sentinels; matrices are (Lq+2) x (Lt+2) row-major with
+ * index 0 = Head '^' and last = Tail '$' exactly as the reference (sequence.cpp:15-16).      */
+
+/* Literal O(Lq*Lt*(Lq+Lt)) restatement of build_{forw,rev}[_local]_dpm_nonlinear_gaps.
+ * repro_rev_bug != 0 reproduces dpmatrix.h:868 (opt_j = t1_m1) in the global reverse fill.
+ * sim_out may be NULL. Returns 0, or 1 for "Illegal bounds building DPM" (dpmatrix.h:360).  */
+int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+             int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
+             float* sim_out);
+
+/* Exact O(Lq*Lt) restatement (running maxima with origin tracking).
+ * Candidates are re-evaluated as (D[origin] - w(len)) + sim like dpmatrix.h:460-462, so
+ * it is bit-identical to orc_fill whenever all scores/penalties lie on one dyadic grid.    */
+int orc_fill_fast(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                  int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t);
+
+/* optimal.h:47-124 on a forward matrix. pairs = 2 ints per aligned pair, front to back.
+ * Returns 0, or 3 for "Illegal alignment start pair" (optimal.h:74).                        */
+int orc_optimal_fwd(const float* score, const int* prev_q, const int* prev_t, int sz1, int sz2,
+                    int is_local, int* pairs, int max_pairs, int* npairs, float* ali_score);
+
+/* optimal_rev.h:47-131 on a reverse matrix. */
+int orc_optimal_rev(const float* score, const int* prev_q, const int* prev_t, int sz1, int sz2,
+                    int is_local, int* pairs, int max_pairs, int* npairs, float* ali_score);
+
+/* cw.h:86-88 == ucw.h:81-83 == kscw.h:124-126 */
+float orc_threshold(float opt_score, float delta_ratio);
+
+/* Near-optimal cell set {interior (i,j): F + R - sim > thr}.
+ * mask is sz1*sz2 bytes (0/1). Returns the number of set cells.                             */
+long orc_nearopt_mask(const float* F, const float* R, const float* sim, int sz1, int sz2,
+                      float thr, uint8_t* mask);
+
+/* Waterman branching of ucw.h:88-191 restated as a cell-marking recursion: marks every cell
+ * that lies on any alignment UnconstrainedNearOptimal::enumerate would emit (before sortSet),
+ * and counts the alignments. Stops with -1 if more than max_alignments would be produced
+ * (the reference switches to opt_path at user_limit=100000, ucw.h:72,115-126).             */
+long orc_ucw_cells(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                   const float* F, const float* sim, float thr, long max_alignments,
+                   uint8_t* cell_union);
+
+/* aasubalib.h:27-77 restated (positions are matrix indices incl. sentinels). */
+float orc_deletion(const orc_scoring* sc, int sz2, int t_pos1, int t_pos2);
+float orc_insertion(const orc_scoring* sc, int sz1, int q_pos1, int q_pos2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,222 @@
+"""ctypes bindings for the TEST oracles (oracle/liboracle.so and oracle/_ref/libaadp_ref.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.  The product package
+(alignment_algos_b200) never does.
+
+`Oracle`  -> the plain-C restatement (oracle/aadp_oracle.c), available everywhere.
+`Reference` -> the real reference compiled from /root/reference (oracle/ref_harness.cpp);
+              present wherever oracle/_ref/libaadp_ref.so was built (it ships to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_ORACLE = os.path.join(HERE, "liboracle.so")
+LIB_REF = os.path.join(HERE, "_ref", "libaadp_ref.so")
+
+GLOBAL_LOCAL, GLOBAL, LOCAL_GLOBAL, LOCAL, SEMI_LOCAL = 0, 1, 2, 3, 4  # alib.h:20-26
+FWD, REV = 1, 2  # dpmatrix.h:23-26
+
+
+def build(force=False):
+    """Compile liboracle.so (always) and _ref/libaadp_ref.so (when /root/reference exists)."""
+    if force or not os.path.exists(LIB_ORACLE) or (
+        os.path.getmtime(LIB_ORACLE) < os.path.getmtime(os.path.join(HERE, "aadp_oracle.c"))
+    ):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference") and (
+        force or not os.path.exists(LIB_REF)
+        or os.path.getmtime(LIB_REF) < os.path.getmtime(os.path.join(HERE, "ref_harness.cpp"))
+    ):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+
+
+class _Scoring(C.Structure):
+    _fields_ = [("A", C.c_int), ("sub", C.POINTER(C.c_float)), ("gi", C.c_float),
+                ("ge", C.c_float), ("align_type", C.c_int)]
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class Oracle:
+    """The C restatement. Sequences are uint8 code arrays without sentinels."""
+
+    def __init__(self, sub, gi, ge, align_type):
+        build()
+        self.lib = C.CDLL(LIB_ORACLE)
+        self.sub = np.ascontiguousarray(sub, dtype=np.float32)
+        self.A = self.sub.shape[0]
+        self.sc = _Scoring(self.A, _p(self.sub, C.c_float), gi, ge, align_type)
+        self.align_type = align_type
+        self.lib.orc_threshold.restype = C.c_float
+        self.lib.orc_threshold.argtypes = [C.c_float, C.c_float]
+        self.lib.orc_nearopt_mask.restype = C.c_long
+        self.lib.orc_ucw_cells.restype = C.c_long
+
+    def fill(self, q, t, direction=FWD, repro_rev_bug=True, fast=False, want_sim=False):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        if fast:
+            rc = self.lib.orc_fill_fast(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t),
+                                        C.byref(self.sc), direction, int(repro_rev_bug),
+                                        _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int))
+            sim = None
+        else:
+            sim = np.zeros((sz1, sz2), np.float32)
+            rc = self.lib.orc_fill(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t),
+                                   C.byref(self.sc), direction, int(repro_rev_bug),
+                                   _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int),
+                                   _p(sim, C.c_float))
+        if rc:
+            raise RuntimeError("Illegal bounds building DPM")
+        return (score, pq, pt, sim) if want_sim else (score, pq, pt)
+
+    def sim(self, q, t):
+        q = np.asarray(q, dtype=np.int64)
+        t = np.asarray(t, dtype=np.int64)
+        s = np.zeros((len(q) + 2, len(t) + 2), np.float32)
+        if len(q) and len(t):
+            s[1:-1, 1:-1] = self.sub[q[:, None], t[None, :]]
+        return s
+
+    def optimal(self, score, pq, pt, direction=FWD):
+        sz1, sz2 = score.shape
+        cap = sz1 + sz2 + 8
+        pairs = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        s = C.c_float(0)
+        fn = self.lib.orc_optimal_fwd if direction == FWD else self.lib.orc_optimal_rev
+        rc = fn(_p(np.ascontiguousarray(score), C.c_float), _p(np.ascontiguousarray(pq), C.c_int),
+                _p(np.ascontiguousarray(pt), C.c_int), sz1, sz2, int(self.align_type == LOCAL),
+                _p(pairs, C.c_int), cap, C.byref(n), C.byref(s))
+        return rc, pairs[: min(n.value, cap)].copy(), s.value
+
+    def threshold(self, opt, delta_ratio):
+        return self.lib.orc_threshold(C.c_float(opt), C.c_float(delta_ratio))
+
+    def nearopt_mask(self, F, R, sim, thr):
+        sz1, sz2 = F.shape
+        mask = np.zeros((sz1, sz2), np.uint8)
+        n = self.lib.orc_nearopt_mask(_p(np.ascontiguousarray(F), C.c_float),
+                                      _p(np.ascontiguousarray(R), C.c_float),
+                                      _p(np.ascontiguousarray(sim), C.c_float), sz1, sz2,
+                                      C.c_float(thr), _p(mask, C.c_uint8))
+        return mask, n
+
+    def ucw_cells(self, q, t, F, sim, thr, max_alignments=2_000_000):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        mark = np.zeros(F.shape, np.uint8)
+        n = self.lib.orc_ucw_cells(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t),
+                                   C.byref(self.sc), _p(np.ascontiguousarray(F), C.c_float),
+                                   _p(np.ascontiguousarray(sim), C.c_float), C.c_float(thr),
+                                   C.c_long(max_alignments), _p(mark, C.c_uint8))
+        return mark, n
+
+
+def write_matrix_file(path, alphabet, sub):
+    """Write a substitution matrix in the format submatrix.cpp:16-54 parses."""
+    with open(path, "w") as f:
+        f.write("# written by oracle/pyoracle.py\n")
+        f.write("   " + "  ".join(alphabet) + "\n")
+        for i, a in enumerate(alphabet):
+            f.write(a + " " + " ".join(repr(float(x)) if float(x) != int(x) else str(int(x))
+                                       for x in sub[i]) + "\n")
+
+
+class Reference:
+    """The real reference (libaadp_ref.so). Sequences are letter strings (no sentinels)."""
+
+    def __init__(self, alphabet, sub, gi, ge, align_type):
+        build()
+        if not os.path.exists(LIB_REF):
+            raise FileNotFoundError(LIB_REF)
+        self.lib = C.CDLL(LIB_REF)
+        self.lib.ref_last_error.restype = C.c_char_p
+        self.lib.ref_time_fills.restype = C.c_double
+        self.alphabet = alphabet
+        self.gi, self.ge, self.align_type = float(gi), float(ge), int(align_type)
+        fd, self.matrix_file = tempfile.mkstemp(prefix="aadp_sub_", suffix=".txt")
+        os.close(fd)
+        write_matrix_file(self.matrix_file, alphabet, np.asarray(sub))
+
+    def __del__(self):
+        try:
+            os.unlink(self.matrix_file)
+        except Exception:
+            pass
+
+    def letters(self, codes):
+        return "".join(self.alphabet[int(c)] for c in codes).encode()
+
+    def _args(self, q, t):
+        return (self.letters(q), self.letters(t), self.matrix_file.encode(), C.c_float(self.gi),
+                C.c_float(self.ge), self.align_type)
+
+    def fill(self, q, t, direction=FWD):
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        sim = np.zeros((sz1, sz2), np.float32)
+        rc = self.lib.ref_fill(*self._args(q, t), direction, _p(score, C.c_float),
+                               _p(pq, C.c_int), _p(pt, C.c_int), _p(sim, C.c_float))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return score, pq, pt, sim
+
+    def optimal(self, q, t, direction=FWD):
+        cap = len(q) + len(t) + 16
+        pairs = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        s = C.c_float(0)
+        if direction == FWD:
+            ident = C.c_float(0)
+            rc = self.lib.ref_optimal(*self._args(q, t), _p(pairs, C.c_int), cap, C.byref(n),
+                                      C.byref(s), C.byref(ident))
+        else:
+            rc = self.lib.ref_optimal_rev(*self._args(q, t), _p(pairs, C.c_int), cap, C.byref(n),
+                                          C.byref(s))
+        return rc, pairs[: min(n.value, cap)].copy(), s.value
+
+    def nearopt(self, q, t, delta_ratio, number_suboptimal=0, which=0, flags=None, max_scores=4096):
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        union = np.zeros((sz1, sz2), np.uint8)
+        n = C.c_int(0)
+        scores = np.zeros(max_scores, np.float32)
+        thr = C.c_float(0)
+        rc = self.lib.ref_nearopt(*self._args(q, t), C.c_float(delta_ratio), number_suboptimal,
+                                  which, flags.encode() if flags else None, _p(union, C.c_uint8),
+                                  C.byref(n), _p(scores, C.c_float), max_scores, C.byref(thr))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return union, n.value, scores[: min(n.value, max_scores)].copy(), thr.value
+
+    def time_fills(self, seqs, pair_q, pair_t, what=3, nthreads=1):
+        """Time the reference DPMatrix constructor over pairs. Returns (seconds, cells, checksum)."""
+        arena = b"".join(self.letters(s) for s in seqs)
+        lens = np.array([len(s) for s in seqs], np.int32)
+        off = np.zeros(len(seqs), np.int64)
+        off[1:] = np.cumsum(lens)[:-1]
+        pq = np.ascontiguousarray(pair_q, np.int32)
+        pt = np.ascontiguousarray(pair_t, np.int32)
+        cells = C.c_double(0)
+        chk = C.c_double(0)
+        sec = self.lib.ref_time_fills(arena, _p(off, C.c_longlong), _p(lens, C.c_int),
+                                      _p(pq, C.c_int), _p(pt, C.c_int), len(pq),
+                                      self.matrix_file.encode(), C.c_float(self.gi),
+                                      C.c_float(self.ge), self.align_type, what, nthreads,
+                                      C.byref(cells), C.byref(chk))
+        return sec, cells.value, chk.value

@@ -1,0 +1,356 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin C-ABI harness around the UNMODIFIED reference implementation. It #includes the
+// reference's own headers from /root/reference (never copied into this repo) and is linked
+// against the reference's own translation units (see oracle/Makefile). The result,
+// oracle/_ref/libaadp_ref.so, is the ground truth that
+//   * pins the C restatement in oracle/aadp_oracle.c,
+//   * generates the golden fixtures under tests/golden/ (oracle/gen_golden.py),
+//   * serves as the "reference" CPU baseline of bench.py (--impl reference / cpu_baseline).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+//
+// What is exercised (reference file:line):
+//   DPMatrix ctor + build()            dpmatrix.h:147-165, 291-317
+//   forward / reverse / local fills    dpmatrix.h:356-536, 538-689, 691-877, 879-1030
+//   SimilarityMatrix                   simmatrix.h:40-73
+//   AASubstitutionEval                 aasubalib.h:8-87
+//   BlosumMatrix file parser           submatrix.cpp:16-54
+//   Optimal::enumerate                 optimal.h:47-124
+//   UnconstrainedNearOptimal           ucw.h:63-236
+//   ConstrainedNearOptimal             cw.h:67-284
+// Optimal_Rev is abstract in the reference (optimal_rev.h:29-30 does not override
+// enumerator.h:23-24), so its loop (optimal_rev.h:47-78 / 80-112) is driven here over the
+// reference's own rev DPMatrix by following prev_* exactly as that loop does.
+//
+// Built WITHOUT -ffast-math (IEEE), unlike the reference makefile:6.
+
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+#include <chrono>
+#include <atomic>
+
+#include "aa_seq.h"
+#include "aasubalib.h"
+#include "alib.h"
+#include "alignment.h"
+#include "cw.h"
+#include "dpmatrix.h"
+#include "noalib.h"
+#include "optimal.h"
+#include "sflags.h"
+#include "submatrix.h"
+#include "ucw.h"
+
+typedef AASubstitutionEval<AASequence, AASequence> AAEval;
+typedef DPMatrix<AASequence, AASequence, AAEval> AADPM;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct NullBuf : std::streambuf {
+  int overflow(int c) { return c; }
+};
+NullBuf g_nullbuf;
+
+// dpmatrix.h:696 and cw.h:90 write to cerr on every call; silence them for the
+// lifetime of the library (restored never: this is a test-only shared object).
+struct CerrSilencer {
+  CerrSilencer() { std::cerr.rdbuf(&g_nullbuf); }
+};
+CerrSilencer g_silencer;
+
+void make_seq(AASequence& s, const char* letters) {
+  // fastaio.h:126,137 builds sequences as '^' + residues + '$'; FastaRead itself duplicates
+  // the last line at EOF, so sequences are appended directly.
+  std::string x("^");
+  x += letters;
+  x += "$";
+  s.append(x);
+}
+
+AliParams make_params(float gi, float ge, int align_type) {
+  AliParams p;
+  p.align_type = static_cast<align_t>(align_type);
+  p.gap_init_penalty = gi;
+  p.gap_extn_penalty = ge;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// Fill one matrix with the reference. direction: 1 = fwd, 2 = rev (dpmatrix.h:23-26).
+// Outputs are row-major sz1 x sz2 with sz1 = strlen(q)+2, sz2 = strlen(t)+2. Any may be NULL.
+int ref_fill(const char* q, const char* t, const char* matrix_file, float gi, float ge,
+             int align_type, int direction, float* score, int* prev_q, int* prev_t,
+             float* sim) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, static_cast<direction_t>(direction), ap.align_type);
+    int sz1 = dpm.getQuerySize(), sz2 = dpm.getTemplateSize();
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) {
+        const DPCell* c = dpm.getCell(i, j);
+        size_t o = (size_t)i * sz2 + j;
+        if (score) score[o] = c->score;
+        if (prev_q) prev_q[o] = c->prev_query_idx;
+        if (prev_t) prev_t[o] = c->prev_template_idx;
+        if (sim) sim[o] = dpm.getSim(i, j);
+      }
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+// Optimal alignment through the reference's own Optimal enumerator (optimal.h:47-124) on a
+// forward matrix. pairs receives (q,t) index pairs, 2 ints each.
+int ref_optimal(const char* q, const char* t, const char* matrix_file, float gi, float ge,
+                int align_type, int* pairs, int max_pairs, int* npairs, float* score,
+                float* identity) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, fwd, ap.align_type);
+    Optimal<AASequence, AASequence, AAEval> opt(ap.align_type);
+    AlignmentSet<AASequence, AASequence, AAEval> as(dpm, opt);
+    int n = 0;
+    for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = as[0].begin();
+         it != as[0].end(); ++it) {
+      if (n < max_pairs) {
+        pairs[2 * n] = it->query_idx();
+        pairs[2 * n + 1] = it->template_idx();
+      }
+      ++n;
+    }
+    *npairs = n;
+    if (score) *score = as[0].score;
+    if (identity) *identity = as[0].identity;
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+// Reverse optimal alignment: the loop of optimal_rev.h:47-78 (global) / 80-112 (local) driven
+// over the reference's own reverse DPMatrix (the class itself cannot be instantiated).
+int ref_optimal_rev(const char* q, const char* t, const char* matrix_file, float gi, float ge,
+                    int align_type, int* pairs, int max_pairs, int* npairs, float* score) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, rev, ap.align_type);
+    int q_last = dpm.getQuerySize() - 1, t_last = dpm.getTemplateSize() - 1;
+    int n = 0;
+    int qf = 0, tf = 0;
+#define PUSH(a, b)                 \
+  do {                             \
+    if (n < max_pairs) {           \
+      pairs[2 * n] = (a);          \
+      pairs[2 * n + 1] = (b);      \
+    }                              \
+    ++n;                           \
+  } while (0)
+    if (ap.align_type != local) {
+      if (score) *score = dpm.getCell(0, 0)->score;
+      PUSH(0, 0);
+      int guard = 0;
+      while (qf < q_last) {
+        const DPCell* c = dpm.getCell(qf, tf);
+        qf = c->prev_query_idx;
+        tf = c->prev_template_idx;
+        PUSH(qf, tf);
+        if (qf < 0 || tf < 0 || ++guard > q_last + t_last + 4) {
+          // the :868 bug can send the walk to a cell that was never filled (tb -1,-1)
+          *npairs = n;
+          g_err = "Illegal alignment start pair";
+          return 3;
+        }
+      }
+      *npairs = n;
+      if (qf != q_last || tf != t_last) {
+        g_err = "Illegal alignment start pair";
+        return 3;
+      }
+    } else {
+      float s = dpm.getCell(0, 0)->score;  // optimal_rev.h:114-131 find_max
+      int mq = 0, mt = 0;
+      for (int i = dpm.getQuerySize() - 1; i > 0; --i)
+        for (int j = dpm.getTemplateSize() - 1; j > 0; --j)
+          if (s < dpm.getCell(i, j)->score) {
+            mq = i;
+            mt = j;
+            s = dpm.getCell(i, j)->score;
+          }
+      PUSH(0, 0);
+      qf = mq;
+      tf = mt;
+      if (score) *score = s;
+      PUSH(qf, tf);
+      while (qf < q_last) {
+        const DPCell* c = dpm.getCell(qf, tf);
+        qf = c->prev_query_idx;
+        tf = c->prev_template_idx;
+        if (qf < 0 || tf < 0) break;
+        if (dpm.getCell(qf, tf)->score <= 0.f) break;
+        PUSH(qf, tf);
+      }
+      if (qf != q_last && tf != t_last) PUSH(q_last, t_last);
+      *npairs = n;
+    }
+#undef PUSH
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+// Near-optimal enumeration with the reference's own enumerators.
+//   which = 0: UnconstrainedNearOptimal (ucw.h), 1: ConstrainedNearOptimal (cw.h) with the
+//   SuboptFlags given in `flags` (one char '0'/'1' per template position incl. sentinels,
+//   NULL = all true; built as nalign.cpp:84 does, not with aa_ali.cpp:86's swapped arguments).
+// cell_union (sz1*sz2 bytes, may be NULL) gets 1 for every (q,t) on any enumerated alignment
+// *before* sortSet truncates (number_suboptimal is forced huge for the union, then the
+// caller's value is applied to the returned score list).
+int ref_nearopt(const char* q, const char* t, const char* matrix_file, float gi, float ge,
+                int align_type, float delta_ratio, int number_suboptimal, int which,
+                const char* flags, unsigned char* cell_union, int* n_alignments,
+                float* scores, int max_scores, float* threshold) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, fwd, ap.align_type);
+    NOaliParams np;
+    np.delta_ratio = delta_ratio;
+    np.number_suboptimal = 0x3fffffff / 32;  // estimateSize()*20 must not overflow (ucw.h:75)
+    Optimal<AASequence, AASequence, AAEval> opt(ap.align_type);
+    AlignmentSet<AASequence, AASequence, AAEval> as(dpm, opt);
+    as.clear();
+    int sz1 = dpm.getQuerySize(), sz2 = dpm.getTemplateSize();
+    if (which == 0) {
+      UnconstrainedNearOptimal<AASequence, AASequence, AAEval> u(np);
+      u.enumerate(dpm, as);
+    } else {
+      SuboptFlags sf(true, (size_t)sz2);
+      if (flags)
+        for (int j = 0; j < sz2; ++j) sf.Set(j, flags[j] != '0');
+      ConstrainedNearOptimal<AASequence, AASequence, AAEval> c(np, sf);
+      c.enumerate(dpm, as);
+    }
+    if (cell_union) {
+      memset(cell_union, 0, (size_t)sz1 * sz2);
+      for (size_t k = 0; k < as.size(); ++k)
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = as[k].begin();
+             it != as[k].end(); ++it)
+          cell_union[(size_t)it->query_idx() * sz2 + it->template_idx()] = 1;
+    }
+    *n_alignments = (int)as.size();
+    as.sortSet(number_suboptimal > 0 ? number_suboptimal : (int)as.size());
+    for (int k = 0; k < (int)as.size() && k < max_scores; ++k) scores[k] = as[k].score;
+    if (threshold) {
+      float o = dpm.getCell(sz1 - 1, sz2 - 1)->score;
+      float thr = (1.f - np.delta_ratio) * o;  // cw.h:86-88, ucw.h:81-83
+      thr = std::min(thr, o - 0.1f);
+      *threshold = thr;
+    }
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (std::bad_alloc&) {
+    g_err = "bad_alloc";
+    return 4;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+// CPU baseline timing: runs the reference's DPMatrix constructor (fill only, as BASELINE.md §3
+// states) over `npairs` pairs given as offsets into one residue arena, on `nthreads` host threads
+// (one worker per thread over a shared atomic cursor; the fill is single-threaded and shares no
+// mutable state). what: 1 = fwd only, 3 = fwd + rev (two constructions).
+// Returns wall seconds; *cells gets sum(Lq*Lt) over the pairs (per direction).
+double ref_time_fills(const char* arena, const long long* off, const int* len, const int* pair_q,
+                      const int* pair_t, int npairs, const char* matrix_file, float gi, float ge,
+                      int align_type, int what, int nthreads, double* cells, double* checksum) {
+  AliParams ap = make_params(gi, ge, align_type);
+  BlosumMatrix bm(matrix_file);
+  AAEval ev(ap, bm);
+  std::atomic<int> cursor(0);
+  std::vector<double> sums(nthreads, 0.0);
+  double ncell = 0;
+  for (int p = 0; p < npairs; ++p) ncell += (double)len[pair_q[p]] * len[pair_t[p]];
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int w = 0; w < nthreads; ++w)
+    th.emplace_back([&, w]() {
+      double acc = 0;
+      for (;;) {
+        int p = cursor.fetch_add(1);
+        if (p >= npairs) break;
+        std::string a(arena + off[pair_q[p]], len[pair_q[p]]);
+        std::string b(arena + off[pair_t[p]], len[pair_t[p]]);
+        AASequence qs, ts;
+        make_seq(qs, a.c_str());
+        make_seq(ts, b.c_str());
+        {
+          AADPM f(qs, ts, ev, fwd, ap.align_type);
+          acc += f.getCell(f.getQuerySize() - 1, f.getTemplateSize() - 1)->score;
+        }
+        if (what & 2) {
+          AADPM r(qs, ts, ev, rev, ap.align_type);
+          acc += r.getCell(0, 0)->score;
+        }
+      }
+      sums[w] = acc;
+    });
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  if (cells) *cells = ncell;
+  if (checksum) {
+    double c = 0;
+    for (double s : sums) c += s;
+    *checksum = c;
+  }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
