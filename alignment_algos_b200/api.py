@@ -1,0 +1,180 @@
+"""Thin Python view of the C ABI (include/aadp.h), used by the tests and by bench.py.
+
+The product's host side is C++ (include/hmap2/*.h mirrors the reference's template API);
+this module only marshals numpy / torch buffers into the same C entry points.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib
+
+GLOBAL_LOCAL, GLOBAL, LOCAL_GLOBAL, LOCAL, SEMI_LOCAL = 0, 1, 2, 3, 4  # alib.h:20-26
+FWD, REV, BOTH = 1, 2, 3                                               # dpmatrix.h:23-26
+REPRO_REV_BUG = 1
+W_FWD, W_REV, W_TB, W_SCORES, W_MASK = 1, 2, 4, 8, 16
+
+
+class AadpError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + stream.  Mirrors the life of a reference DPMatrix/Evaluator pair."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.h = self.L.aadp_create(device)
+        if not self.h:
+            raise AadpError(self.L.aadp_last_error().decode())
+        self.align_type = None
+        self.flags = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.aadp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise AadpError(self.L.aadp_last_error().decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.aadp_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.L.aadp_synchronize(self.h))
+
+    def set_scoring(self, sub, gi, ge, align_type, flags=REPRO_REV_BUG):
+        sub = np.ascontiguousarray(sub, dtype=np.float32)
+        assert sub.ndim == 2 and sub.shape[0] == sub.shape[1]
+        self._ck(self.L.aadp_set_scoring(self.h, _ptr(sub), sub.shape[0], gi, ge, align_type, flags))
+        self.align_type, self.flags = align_type, flags
+
+    # ---- single pair (DPMatrix constructor replacement) ----
+    def fill_pair(self, q, t, direction=FWD, delta_ratio=-1.0, want_tb=True, want_scores=True):
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        sz = (len(q) + 2, len(t) + 2)
+        out = {}
+
+        def mk(name, dt, cond):
+            out[name] = np.zeros(sz, dt) if cond else None
+            return _ptr(out[name])
+
+        f, r = bool(direction & 1), bool(direction & 2)
+        args = [mk("score_fwd", np.float32, f and want_scores), mk("prevq_fwd", np.int32, f and want_tb),
+                mk("prevt_fwd", np.int32, f and want_tb), mk("score_rev", np.float32, r and want_scores),
+                mk("prevq_rev", np.int32, r and want_tb), mk("prevt_rev", np.int32, r and want_tb)]
+        want_mask = delta_ratio >= 0 and direction == BOTH
+        args.append(mk("nearopt", np.uint8, want_mask))
+        thr = C.c_float(0)
+        self._ck(self.L.aadp_fill_pair(self.h, _ptr(q), len(q), _ptr(t), len(t), direction, delta_ratio,
+                                       *args, C.cast(C.byref(thr), C.c_void_p) if want_mask else None))
+        out["threshold"] = thr.value if want_mask else None
+        return out
+
+    # ---- batches ----
+    @staticmethod
+    def pack(seqs):
+        lens = np.array([len(s) for s in seqs], np.int64)
+        off = np.zeros(len(seqs) + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        res = np.concatenate([np.asarray(s, np.uint8) for s in seqs]) if len(seqs) else np.zeros(0, np.uint8)
+        return np.ascontiguousarray(res, np.uint8), off
+
+    def fill_batch(self, residues, seq_off, pair_q, pair_t, what, delta_ratio=0.01):
+        pair_q = np.ascontiguousarray(pair_q, np.int32)
+        pair_t = np.ascontiguousarray(pair_t, np.int32)
+        n = len(pair_q)
+        fs = np.zeros(n, np.float32) if what & W_FWD else None
+        rs = np.zeros(n, np.float32) if what & W_REV else None
+        th = np.zeros(n, np.float32) if what & W_MASK else None
+        cn = np.zeros(n, np.int64) if what & W_MASK else None
+        self._ck(self.L.aadp_fill_batch(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(pair_q),
+                                        _ptr(pair_t), n, what, delta_ratio, _ptr(fs), _ptr(rs), _ptr(th), _ptr(cn)))
+        return {"fwd_score": fs, "rev_score": rs, "threshold": th, "nearopt_count": cn}
+
+    def upload_batch(self, residues, seq_off, pair_q, pair_t, what):
+        pair_q = np.ascontiguousarray(pair_q, np.int32)
+        pair_t = np.ascontiguousarray(pair_t, np.int32)
+        self._ck(self.L.aadp_upload_batch(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(pair_q),
+                                          _ptr(pair_t), len(pair_q), what))
+
+    def run_batch(self, what, delta_ratio=0.01, d_fwd=None, d_rev=None, d_thr=None, d_cnt=None):
+        """d_* are raw device pointers (ints) or None."""
+        self._ck(self.L.aadp_run_batch(self.h, what, delta_ratio, d_fwd, d_rev, d_thr, d_cnt))
+
+    def resident_bytes(self, which):
+        return self.L.aadp_batch_resident_bytes(self.h, which)
+
+    def last_launch_count(self):
+        return self.L.aadp_last_launch_count(self.h)
+
+    def last_cell_updates(self):
+        return self.L.aadp_last_cell_updates(self.h)
+
+    def set_profiling(self, on):
+        self._ck(self.L.aadp_set_profiling(self.h, int(bool(on))))
+
+    def profile(self):
+        """[(kernel name, ms, cell updates)] of the last run (needs set_profiling(True))."""
+        out = []
+        buf = C.create_string_buffer(96)
+        for i in range(self.L.aadp_profile_count(self.h)):
+            ms, cells = C.c_float(0), C.c_double(0)
+            self._ck(self.L.aadp_profile_get(self.h, i, C.cast(buf, C.c_void_p), 96,
+                                             C.cast(C.byref(ms), C.c_void_p), C.cast(C.byref(cells), C.c_void_p)))
+            out.append((buf.value.decode(), ms.value, cells.value))
+        return out
+
+    def fetch_pair(self, p, Lq, Lt, fwd=True, rev=False, tb=True, scores=True, mask=False):
+        sz = (Lq + 2, Lt + 2)
+        out = {}
+
+        def mk(name, dt, cond):
+            out[name] = np.zeros(sz, dt) if cond else None
+            return _ptr(out[name])
+
+        args = [mk("score_fwd", np.float32, fwd and scores), mk("prevq_fwd", np.int32, fwd and tb),
+                mk("prevt_fwd", np.int32, fwd and tb), mk("score_rev", np.float32, rev and scores),
+                mk("prevq_rev", np.int32, rev and tb), mk("prevt_rev", np.int32, rev and tb),
+                mk("nearopt", np.uint8, mask)]
+        self._ck(self.L.aadp_batch_fetch_pair(self.h, p, *args))
+        return out
+
+    def optimal(self, p, direction, Lq, Lt):
+        cap = Lq + Lt + 8
+        pairs = np.zeros((cap, 2), np.int32)
+        n = C.c_int32(0)
+        s = C.c_float(0)
+        rc = self.L.aadp_batch_optimal(self.h, p, direction, _ptr(pairs), cap, C.cast(C.byref(n), C.c_void_p),
+                                       C.cast(C.byref(s), C.c_void_p))
+        if rc not in (0, 3):
+            raise AadpError(self.L.aadp_last_error().decode())
+        return rc, pairs[: min(n.value, cap)].copy(), s.value
+
+    def fetch_tb(self, p, direction, Lq, Lt):
+        nbytes = max(int(Lq * self.L.aadp_tb_row_bytes(Lt)), 1)
+        tb = np.zeros(nbytes, np.uint8)
+        fin = np.zeros(4, np.int32)
+        self._ck(self.L.aadp_batch_fetch_tb(self.h, p, direction, _ptr(tb), nbytes, _ptr(fin)))
+        return tb, fin
+
+    def decode_cell(self, tb, fin, Lq, Lt, direction, i, j):
+        pq, pt = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.aadp_decode_cell(_ptr(tb), Lq, Lt, direction, self.align_type, self.flags, _ptr(fin), i, j,
+                                         C.cast(C.byref(pq), C.c_void_p), C.cast(C.byref(pt), C.c_void_p)))
+        return pq.value, pt.value

@@ -1,0 +1,729 @@
+// aadp_api.cu -- C ABI (include/aadp.h) + host orchestration of the sm_100a fill kernels.
+// The product path: there is no CPU fallback anywhere in this file; every compute entry point
+// fails with an error message when no CUDA device / kernel image is available.
+#include "../../include/aadp.h"
+#include "aadp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace aadp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;        \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      g_err = std::string("cudaMalloc failed for ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e);
+      p = nullptr;
+      return 1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Batch {
+  int64_t nseq = 0, npairs = 0;
+  std::vector<int64_t> seq_off;
+  std::vector<int32_t> pair_q, pair_t;
+  std::vector<int64_t> tb_off, sc_off, mask_off;  // per pair, +1 total at the end
+  std::vector<int32_t> order[2];                  // bucket 0: K=8, bucket 1: K=16
+  double bucket_cells[2] = {0, 0};
+  int max_Lq = 0, max_Lt = 0;
+  int st_mode = 1;  // 1 = int16 score storage possible, 2 = int32
+  double cells = 0;
+  uint32_t uploaded_what = 0;
+  uint32_t ran_what = 0;
+};
+
+}  // namespace
+
+struct aadp_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  bool have_scoring = false;
+  Scoring sc{};
+  int align_type = AADP_GLOBAL;
+  uint32_t flags = 0;
+  std::vector<int8_t> sub8_h;
+  int max_abs_sub = 0;
+  DevBuf sub8, residues, seq_off, pair_q, pair_t, order[2], tb_off, sc_off, mask_off;
+  DevBuf tb[2], scb[2], mask, fin_score[2], fin_kind[2], fin_k[2], counter, bbuf, thr, count, fscore[2];
+  DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
+  Batch b;
+  int64_t launches = 0;
+  int bb_rows = 0;
+  // optional per-launch timing
+  bool profiling = false;
+  struct Prof { std::string name; cudaEvent_t e0, e1; double cells; };
+  std::vector<Prof> prof;       // launches of the last run
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_used++];
+  }
+  void prof_begin(const char* name, double cells) {
+    if (!profiling) return;
+    Prof p{name, next_event(), next_event(), cells};
+    cudaEventRecord(p.e0, stream);
+    prof.push_back(p);
+  }
+  void prof_end() {
+    if (!profiling) return;
+    cudaEventRecord(prof.back().e1, stream);
+  }
+};
+
+namespace {
+
+template <int K, int TBM, int STM>
+int launch_fill_t(aadp_ctx* c, FillParams& P) {
+  auto kern = fill_kernel<K, TBM, STM>;
+  const int A = P.sc.A;
+  const size_t smem = (size_t)((A * A + 15) / 16 * 16) + (size_t)kWarpsPerCta * A * 32 * K;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
+  if (occ < 1) return fail("fill kernel does not fit on an SM");
+  int grid = c->num_sms * occ;
+  const int need = (P.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  // multi-stripe pairs need a boundary buffer slot per resident warp
+  if (c->b.max_Lt > 32 * K) {
+    c->bb_rows = c->b.max_Lq + 2;
+    if (c->bbuf.reserve((size_t)c->num_sms * occ * kWarpsPerCta * c->bb_rows * sizeof(int4))) return 1;
+    P.bbuf = c->bbuf.as<int4>();
+    P.bb_rows = c->bb_rows;
+  }
+  char nm[64];
+  snprintf(nm, sizeof nm, "fill_kernel<K=%d,TB=%d,ST=%d>%s", K, TBM, STM, P.rev ? "rev" : "fwd");
+  c->prof_begin(nm, P.cells_hint);
+  kern<<<grid, kWarpsPerCta * 32, smem, c->stream>>>(P);
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+template <int K>
+int launch_fill_k(aadp_ctx* c, FillParams& P, int tbm, int stm) {
+  if (tbm == 0) {
+    if (stm == 0) return launch_fill_t<K, 0, 0>(c, P);
+    if (stm == 1) return launch_fill_t<K, 0, 1>(c, P);
+    return launch_fill_t<K, 0, 2>(c, P);
+  }
+  if (stm == 0) return launch_fill_t<K, 1, 0>(c, P);
+  if (stm == 1) return launch_fill_t<K, 1, 1>(c, P);
+  return launch_fill_t<K, 1, 2>(c, P);
+}
+
+__global__ void scores_to_float_kernel(const int32_t* fin, float* out, int64_t n, int scale_log2) {
+  const float inv = 1.f / (float)(1 << scale_log2);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)fin[i] * inv;
+}
+
+int check_ctx(aadp_ctx* c, bool need_scoring) {
+  if (!c) return fail("null context");
+  if (need_scoring && !c->have_scoring) return fail("aadp_set_scoring has not been called");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int build_batch_meta(aadp_ctx* c, uint32_t what) {
+  Batch& b = c->b;
+  const int64_t np = b.npairs;
+  b.tb_off.assign(np + 1, 0);
+  b.sc_off.assign(np + 1, 0);
+  b.mask_off.assign(np + 1, 0);
+  b.order[0].clear();
+  b.order[1].clear();
+  b.max_Lq = b.max_Lt = 0;
+  b.cells = 0;
+  b.bucket_cells[0] = b.bucket_cells[1] = 0;
+  std::vector<int64_t> cells(np);
+  int64_t bound = 0;
+  for (int64_t p = 0; p < np; ++p) {
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    if (qs < 0 || qs >= b.nseq || ts < 0 || ts >= b.nseq) return fail("pair index out of range");
+    const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
+    if (Lq < 0 || Lt < 0 || Lq > (1 << 24) || Lt > (1 << 24)) return fail("bad sequence length");
+    b.max_Lq = std::max<int>(b.max_Lq, (int)Lq);
+    b.max_Lt = std::max<int>(b.max_Lt, (int)Lt);
+    b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? Lq * tb_row_bytes((int)Lt) : 0);
+    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? Lq * sc_row_elems((int)Lt) : 0);
+    b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? Lq * mask_row_words((int)Lt) : 0);
+    cells[p] = Lq * Lt;
+    b.cells += (double)cells[p];
+    b.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
+    b.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cells[p];
+    // |score| bound in integer units: matches + one end gap on each side
+    const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
+    bound = std::max(bound, bd);
+  }
+  b.st_mode = bound < 30000 ? 1 : 2;
+  if (bound >= (1 << 24)) return fail("scores exceed the exactly-representable float range (2^24 units)");
+  for (int k = 0; k < 2; ++k)
+    std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
+  return 0;
+}
+
+template <class T>
+int upload_vec(DevBuf& d, const std::vector<T>& v, cudaStream_t s) {
+  if (d.reserve(std::max<size_t>(v.size() * sizeof(T), 16))) return 1;
+  if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what) {
+  Batch& b = c->b;
+  const int tbm = (what & AADP_W_TB) ? 1 : 0;
+  const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
+  const int64_t np = b.npairs;
+  if (c->fin_score[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
+  if (c->fin_kind[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
+  if (c->fin_k[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
+  if (tbm && c->tb[dir].reserve(std::max<size_t>((size_t)b.tb_off[np], 16))) return 1;
+  if (stm && c->scb[dir].reserve(std::max<size_t>((size_t)b.sc_off[np] * (stm == 1 ? 2 : 4), 16))) return 1;
+  if (c->counter.reserve(64)) return 1;
+  for (int k = 0; k < 2; ++k) {
+    if (b.order[k].empty()) continue;
+    FillParams P{};
+    P.sc = c->sc;
+    P.sub8 = c->sub8.as<int8_t>();
+    P.residues = c->residues.as<uint8_t>();
+    P.seq_off = c->seq_off.as<int64_t>();
+    P.pair_q = c->pair_q.as<int32_t>();
+    P.pair_t = c->pair_t.as<int32_t>();
+    P.order = c->order[k].as<int32_t>();
+    P.n_items = (int)b.order[k].size();
+    P.rev = dir;
+    P.counter = c->counter.as<unsigned int>() + (dir * 2 + k);
+    P.tb = tbm ? c->tb[dir].as<uint8_t>() : nullptr;
+    P.tb_off = c->tb_off.as<int64_t>();
+    P.sc_blob = stm ? c->scb[dir].p : nullptr;
+    P.sc_off = c->sc_off.as<int64_t>();
+    P.fin_score = c->fin_score[dir].as<int32_t>();
+    P.fin_kind = c->fin_kind[dir].as<int32_t>();
+    P.fin_k = c->fin_k[dir].as<int32_t>();
+    P.bbuf = nullptr;
+    P.bb_rows = 0;
+    P.cells_hint = b.bucket_cells[k];
+    int rc = (k == 0) ? launch_fill_k<8>(c, P, tbm, stm) : launch_fill_k<16>(c, P, tbm, stm);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, int32_t* h_pt) {
+  if (!h_score && !h_pq && !h_pt) return 0;
+  Batch& b = c->b;
+  const int qs = b.pair_q[p], ts = b.pair_t[p];
+  const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  const int64_t n = (int64_t)(Lq + 2) * (Lt + 2);
+  const bool have_tb = (b.ran_what & AADP_W_TB) != 0;
+  const bool have_sc = (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) != 0;
+  if (h_score && !have_sc) return fail("score matrices were not kept (run with AADP_W_SCORES)");
+  if ((h_pq || h_pt) && !have_tb) return fail("traceback was not kept (run with AADP_W_TB)");
+  if ((h_pq || h_pt) && c->sc.local && !have_sc) return fail("local tracebacks need AADP_W_SCORES");
+  int32_t fin[3];
+  CK(cudaMemcpyAsync(&fin[0], c->fin_score[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&fin[1], c->fin_kind[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&fin[2], c->fin_k[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  DenseParams D{};
+  D.sc = c->sc;
+  D.Lq = Lq;
+  D.Lt = Lt;
+  D.rev = dir;
+  D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
+  D.st_mode = have_sc ? b.st_mode : 0;
+  D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
+  D.sc_off = b.sc_off[p];
+  D.tb = have_tb ? c->tb[dir].as<uint8_t>() + b.tb_off[p] : nullptr;
+  D.fin_score = fin[0];
+  D.fin_kind = fin[1];
+  D.fin_k = fin[2];
+  if (h_score) { if (c->scratch_a.reserve(n * 4)) return 1; D.score = c->scratch_a.as<float>(); }
+  if (h_pq || h_pt) {
+    if (c->scratch_b.reserve(n * 4) || c->scratch_c.reserve(n * 4)) return 1;
+    D.prev_q = c->scratch_b.as<int32_t>();
+    D.prev_t = c->scratch_c.as<int32_t>();
+  }
+  const int threads = 256;
+  const int grid = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 8);
+  dense_kernel<<<grid, threads, 0, c->stream>>>(D);
+  CK(cudaGetLastError());
+  c->launches++;
+  if (h_score) CK(cudaMemcpyAsync(h_score, D.score, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_pq) CK(cudaMemcpyAsync(h_pq, D.prev_q, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (h_pt) CK(cudaMemcpyAsync(h_pt, D.prev_t, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
+  if (!h_mask) return 0;
+  Batch& b = c->b;
+  if (!(b.ran_what & AADP_W_MASK)) return fail("near-optimal mask was not computed (run with AADP_W_MASK)");
+  const int qs = b.pair_q[p], ts = b.pair_t[p];
+  const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  const int sz2 = Lt + 2;
+  const int64_t mws = mask_row_words(Lt);
+  std::vector<uint32_t> bits((size_t)std::max<int64_t>(Lq * mws, 1));
+  if (Lq * mws > 0) {
+    CK(cudaMemcpyAsync(bits.data(), c->mask.as<uint32_t>() + b.mask_off[p], (size_t)(Lq * mws) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  memset(h_mask, 0, (size_t)(Lq + 2) * sz2);
+  for (int i = 1; i <= Lq; ++i)
+    for (int j = 1; j <= Lt; ++j)
+      h_mask[(size_t)i * sz2 + j] = (bits[(size_t)(i - 1) * mws + ((j - 1) >> 5)] >> ((j - 1) & 31)) & 1u;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* aadp_last_error(void) { return g_err.c_str(); }
+const char* aadp_version(void) { return "aadp 0.1 (sm_100a)"; }
+
+aadp_ctx* aadp_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_err = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+            "); this library has no CPU fallback";
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { g_err = "device index out of range"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return nullptr; }
+  if (prop.major != 10) {
+    g_err = "this build contains sm_100a kernels only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return nullptr;
+  }
+  aadp_ctx* c = new aadp_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed";
+    delete c;
+    return nullptr;
+  }
+  c->stream = c->own_stream;
+  return c;
+}
+
+void aadp_destroy(aadp_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  DevBuf* all[] = {&c->sub8, &c->residues, &c->seq_off, &c->pair_q, &c->pair_t, &c->order[0], &c->order[1], &c->tb_off,
+                   &c->sc_off, &c->mask_off, &c->tb[0], &c->tb[1], &c->scb[0], &c->scb[1], &c->mask, &c->fin_score[0],
+                   &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
+                   &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d};
+  for (DevBuf* d : all) d->release();
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int aadp_set_stream(aadp_ctx* c, void* s) {
+  if (!c) return fail("null context");
+  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  return 0;
+}
+
+int aadp_synchronize(aadp_ctx* c) {
+  if (check_ctx(c, false)) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, int align_type, uint32_t flags) {
+  if (check_ctx(c, false)) return 1;
+  if (!sub || A < 1 || A > 64) return fail("alphabet size must be 1..64");
+  if (align_type < 0 || align_type > 4) return fail("Illegal gap style");  // aasubalib.h:49
+  if (!(gi >= 0.f) || !(ge >= 0.f)) return fail("gap penalties must be non-negative");
+  // find the dyadic grid: smallest s with everything integral in units of 2^-s
+  int s = -1;
+  for (int t = 0; t <= 8 && s < 0; ++t) {
+    const float m = (float)(1 << t);
+    bool ok = (gi * m == rintf(gi * m)) && (ge * m == rintf(ge * m));
+    for (int i = 0; i < A * A && ok; ++i) ok = (sub[i] * m == rintf(sub[i] * m));
+    if (ok) s = t;
+  }
+  if (s < 0)
+    return fail("scores/penalties do not share a dyadic grid (2^-8); the exact integer path cannot represent them");
+  const float m = (float)(1 << s);
+  c->sub8_h.resize((size_t)A * A);
+  int mx = 0;
+  for (int i = 0; i < A * A; ++i) {
+    const float v = sub[i] * m;
+    if (fabsf(v) > 127.f) return fail("substitution scores exceed the int8 profile range after scaling");
+    c->sub8_h[i] = (int8_t)(int)v;
+    mx = std::max(mx, std::abs((int)v));
+  }
+  if (gi * m > 1e6f || ge * m > 1e5f) return fail("gap penalties too large");
+  c->max_abs_sub = mx;
+  c->sc.A = A;
+  c->sc.gi = (int)(gi * m);
+  c->sc.ge = (int)(ge * m);
+  c->sc.delfree = (align_type == AADP_LOCAL || align_type == AADP_SEMI_LOCAL || align_type == AADP_LOCAL_GLOBAL);
+  c->sc.insfree = (align_type == AADP_LOCAL || align_type == AADP_SEMI_LOCAL || align_type == AADP_GLOBAL_LOCAL);
+  c->sc.local = (align_type == AADP_LOCAL);
+  c->sc.scale_log2 = s;
+  c->align_type = align_type;
+  c->flags = flags;
+  if (c->sub8.reserve((size_t)A * A)) return 1;
+  CK(cudaMemcpyAsync(c->sub8.p, c->sub8_h.data(), (size_t)A * A, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->have_scoring = true;
+  return 0;
+}
+
+int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                      const int32_t* pair_t, int64_t npairs, uint32_t what) {
+  if (check_ctx(c, true)) return 1;
+  if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
+  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
+    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  Batch& b = c->b;
+  b.nseq = nseq;
+  b.npairs = npairs;
+  b.seq_off.assign(seq_off, seq_off + nseq + 1);
+  b.pair_q.assign(pair_q, pair_q + npairs);
+  b.pair_t.assign(pair_t, pair_t + npairs);
+  const int64_t nres = seq_off[nseq];
+  for (int64_t i = 0; i < nres; ++i)
+    if (residues[i] >= c->sc.A) return fail("residue code outside the substitution alphabet");  // submatrix.h:36-38 is UB here
+  if (build_batch_meta(c, what)) return 1;
+  b.uploaded_what = what;
+  b.ran_what = 0;
+  if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
+  if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
+  if (upload_vec(c->seq_off, b.seq_off, c->stream)) return 1;
+  if (upload_vec(c->pair_q, b.pair_q, c->stream)) return 1;
+  if (upload_vec(c->pair_t, b.pair_t, c->stream)) return 1;
+  if (upload_vec(c->order[0], b.order[0], c->stream)) return 1;
+  if (upload_vec(c->order[1], b.order[1], c->stream)) return 1;
+  if (upload_vec(c->tb_off, b.tb_off, c->stream)) return 1;
+  if (upload_vec(c->sc_off, b.sc_off, c->stream)) return 1;
+  if (upload_vec(c->mask_off, b.mask_off, c->stream)) return 1;
+  CK(cudaStreamSynchronize(c->stream));  // host vectors may be reused by the caller
+  return 0;
+}
+
+int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
+                   float* d_threshold, int64_t* d_nearopt_count) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if ((what & ~b.uploaded_what) & (AADP_W_TB | AADP_W_SCORES | AADP_W_MASK))
+    return fail("aadp_run_batch asks for products the batch was not uploaded for");
+  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
+    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
+  c->launches = 0;
+  c->prof.clear();
+  c->ev_used = 0;
+  const int64_t np = b.npairs;
+  if (np == 0) { b.ran_what = what; return 0; }
+  if (c->counter.reserve(64)) return 1;
+  CK(cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
+  const int threads = 256;
+  const int g1 = (int)std::min<int64_t>((np + threads - 1) / threads, 148 * 8);
+  if (what & AADP_W_FWD) {
+    if (run_direction(c, 0, what)) return 1;
+    if (d_fwd_score) {
+      scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[0].as<int32_t>(), d_fwd_score, np, c->sc.scale_log2);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  if (what & AADP_W_REV) {
+    if (run_direction(c, 1, what)) return 1;
+    if (d_rev_score) {
+      scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[1].as<int32_t>(), d_rev_score, np, c->sc.scale_log2);
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  if (what & AADP_W_MASK) {
+    if (c->mask.reserve(std::max<size_t>((size_t)b.mask_off[np] * 4, 16))) return 1;
+    MaskParams M{};
+    M.sc = c->sc;
+    M.sub8 = c->sub8.as<int8_t>();
+    M.residues = c->residues.as<uint8_t>();
+    M.seq_off = c->seq_off.as<int64_t>();
+    M.pair_q = c->pair_q.as<int32_t>();
+    M.pair_t = c->pair_t.as<int32_t>();
+    M.n_pairs = (int)np;
+    M.st_mode = b.st_mode;
+    M.scF = c->scb[0].p;
+    M.scR = c->scb[1].p;
+    M.sc_off = c->sc_off.as<int64_t>();
+    M.fin_fwd = c->fin_score[0].as<int32_t>();
+    M.delta_ratio = delta_ratio;
+    M.mask = c->mask.as<uint32_t>();
+    M.mask_off = c->mask_off.as<int64_t>();
+    M.threshold = d_threshold;
+    M.count = reinterpret_cast<long long*>(d_nearopt_count);
+    c->prof_begin("mask_kernel", 0);
+    mask_kernel<<<(int)np, 256, 0, c->stream>>>(M);
+    c->prof_end();
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  b.ran_what = what;
+  return 0;
+}
+
+int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                    const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
+                    float* rev_score, float* threshold, int64_t* nearopt_count) {
+  if (aadp_upload_batch(c, residues, seq_off, nseq, pair_q, pair_t, npairs, what)) return 1;
+  const size_t nb = std::max<size_t>((size_t)npairs * 4, 16);
+  float *df = nullptr, *dr = nullptr, *dt = nullptr;
+  int64_t* dc = nullptr;
+  if (fwd_score) { if (c->fscore[0].reserve(nb)) return 1; df = c->fscore[0].as<float>(); }
+  if (rev_score) { if (c->fscore[1].reserve(nb)) return 1; dr = c->fscore[1].as<float>(); }
+  if (threshold) { if (c->thr.reserve(nb)) return 1; dt = c->thr.as<float>(); }
+  if (nearopt_count) { if (c->count.reserve(nb * 2)) return 1; dc = c->count.as<int64_t>(); }
+  if (aadp_run_batch(c, what, delta_ratio, df, dr, dt, dc)) return 1;
+  if (npairs) {
+    if (fwd_score && (what & AADP_W_FWD)) CK(cudaMemcpyAsync(fwd_score, df, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rev_score && (what & AADP_W_REV)) CK(cudaMemcpyAsync(rev_score, dr, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (threshold && (what & AADP_W_MASK)) CK(cudaMemcpyAsync(threshold, dt, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (nearopt_count && (what & AADP_W_MASK)) CK(cudaMemcpyAsync(nearopt_count, dc, npairs * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int64_t aadp_batch_resident_bytes(aadp_ctx* c, uint32_t which) {
+  if (!c) return 0;
+  const Batch& b = c->b;
+  if (b.tb_off.empty()) return 0;
+  const int ndir = ((b.ran_what & AADP_W_FWD) ? 1 : 0) + ((b.ran_what & AADP_W_REV) ? 1 : 0);
+  if (which == AADP_W_TB) return (b.ran_what & AADP_W_TB) ? b.tb_off[b.npairs] * ndir : 0;
+  if (which == AADP_W_SCORES) return (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) ? b.sc_off[b.npairs] * (b.st_mode == 1 ? 2 : 4) * ndir : 0;
+  if (which == AADP_W_MASK) return (b.ran_what & AADP_W_MASK) ? b.mask_off[b.npairs] * 4 : 0;
+  return 0;
+}
+
+int64_t aadp_last_launch_count(aadp_ctx* c) { return c ? c->launches : 0; }
+
+int aadp_set_profiling(aadp_ctx* c, int on) {
+  if (!c) return fail("null context");
+  c->profiling = on != 0;
+  return 0;
+}
+
+int aadp_profile_count(aadp_ctx* c) { return c ? (int)c->prof.size() : 0; }
+
+int aadp_profile_get(aadp_ctx* c, int idx, char* name, int name_cap, float* ms, double* cells) {
+  if (check_ctx(c, false)) return 1;
+  if (idx < 0 || idx >= (int)c->prof.size()) return fail("profile index out of range");
+  const aadp_ctx::Prof& p = c->prof[idx];
+  CK(cudaEventSynchronize(p.e1));
+  float t = 0.f;
+  CK(cudaEventElapsedTime(&t, p.e0, p.e1));
+  if (ms) *ms = t;
+  if (cells) *cells = p.cells;
+  if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  return 0;
+}
+
+double aadp_last_cell_updates(aadp_ctx* c) {
+  if (!c) return 0;
+  const int ndir = ((c->b.ran_what & AADP_W_FWD) ? 1 : 0) + ((c->b.ran_what & AADP_W_REV) ? 1 : 0);
+  return c->b.cells * ndir;
+}
+
+int aadp_batch_fetch_pair(aadp_ctx* c, int64_t p, float* score_fwd, int32_t* prevq_fwd, int32_t* prevt_fwd,
+                          float* score_rev, int32_t* prevq_rev, int32_t* prevt_rev, uint8_t* nearopt) {
+  if (check_ctx(c, true)) return 1;
+  if (p < 0 || p >= c->b.npairs) return fail("pair index out of range");
+  if ((score_fwd || prevq_fwd || prevt_fwd) && !(c->b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
+  if ((score_rev || prevq_rev || prevt_rev) && !(c->b.ran_what & AADP_W_REV)) return fail("reverse fill was not run");
+  if (dense_pair(c, p, 0, score_fwd, prevq_fwd, prevt_fwd)) return 1;
+  if (dense_pair(c, p, 1, score_rev, prevq_rev, prevt_rev)) return 1;
+  if (dense_mask(c, p, nearopt)) return 1;
+  return 0;
+}
+
+int aadp_fill_pair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, int Lt, int direction, float delta_ratio,
+                   float* score_fwd, int32_t* prevq_fwd, int32_t* prevt_fwd, float* score_rev, int32_t* prevq_rev,
+                   int32_t* prevt_rev, uint8_t* nearopt, float* threshold) {
+  if (check_ctx(c, true)) return 1;
+  if (Lq < 0 || Lt < 0) return fail("Illegal bounds building DPM");  // dpmatrix.h:360-361
+  if (direction < 1 || direction > 3) return fail("bad direction");
+  std::vector<uint8_t> res((size_t)Lq + Lt + 1);
+  if (Lq) memcpy(res.data(), q, Lq);
+  if (Lt) memcpy(res.data() + Lq, t, Lt);
+  const int64_t off[3] = {0, Lq, (int64_t)Lq + Lt};
+  const int32_t pq = 0, pt = 1;
+  uint32_t what = (direction & 1 ? AADP_W_FWD : 0) | (direction & 2 ? AADP_W_REV : 0);
+  if (prevq_fwd || prevt_fwd || prevq_rev || prevt_rev) what |= AADP_W_TB;
+  if (score_fwd || score_rev || c->sc.local) what |= AADP_W_SCORES;
+  const bool want_mask = (nearopt || threshold) && delta_ratio >= 0.f;
+  if (want_mask) {
+    if (direction != 3) return fail("the near-optimal cell set needs direction 3 (fwd+rev)");
+    what |= AADP_W_MASK;
+  }
+  float* dthr = nullptr;
+  if (want_mask) { if (c->thr.reserve(16)) return 1; dthr = c->thr.as<float>(); }
+  if (aadp_upload_batch(c, res.data(), off, 2, &pq, &pt, 1, what)) return 1;
+  if (aadp_run_batch(c, what, delta_ratio, nullptr, nullptr, dthr, nullptr)) return 1;
+  if (aadp_batch_fetch_pair(c, 0, (direction & 1) ? score_fwd : nullptr, (direction & 1) ? prevq_fwd : nullptr,
+                            (direction & 1) ? prevt_fwd : nullptr, (direction & 2) ? score_rev : nullptr,
+                            (direction & 2) ? prevq_rev : nullptr, (direction & 2) ? prevt_rev : nullptr,
+                            want_mask ? nearopt : nullptr))
+    return 1;
+  if (threshold && want_mask) {
+    CK(cudaMemcpyAsync(threshold, dthr, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int64_t aadp_tb_row_bytes(int Lt) { return tb_row_bytes(Lt); }
+
+int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int64_t tb_bytes, int32_t* final_rec) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (p < 0 || p >= b.npairs) return fail("pair index out of range");
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  const int dir = direction - 1;
+  if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
+  if (tb) {
+    if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
+    const int64_t need = b.tb_off[p + 1] - b.tb_off[p];
+    if (tb_bytes < need) return fail("traceback buffer too small");
+    if (need) CK(cudaMemcpyAsync(tb, c->tb[dir].as<uint8_t>() + b.tb_off[p], need, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (final_rec) {
+    CK(cudaMemcpyAsync(&final_rec[0], c->fin_score[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&final_rec[1], c->fin_kind[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&final_rec[2], c->fin_k[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
+    final_rec[3] = c->sc.scale_log2;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align_type, uint32_t flags,
+                     const int32_t* final_rec, int i, int j, int32_t* prev_q, int32_t* prev_t) {
+  if (!tb || !prev_q || !prev_t) return fail("null argument");
+  const int rev = (direction == AADP_REV);
+  const int a = rev ? Lq + 1 - i : i, b = rev ? Lt + 1 - j : j;
+  int pa = -1, pb = -1;
+  bool is_final = false;
+  if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) decode_prev(tb, Lt, a, b, &pa, &pb);
+  else if (a == Lq + 1 && b == Lt + 1) {
+    if (!final_rec) return fail("final_rec needed for the final cell");
+    decode_final(tb, Lq, Lt, final_rec[1], final_rec[2], &pa, &pb);
+    is_final = true;
+  }
+  if (pa < 0) { *prev_q = -1; *prev_t = -1; return 0; }
+  *prev_q = rev ? Lq + 1 - pa : pa;
+  *prev_t = rev ? Lt + 1 - pb : pb;
+  if (is_final && rev && align_type != AADP_LOCAL && (flags & AADP_REPRO_REV_BUG) && final_rec[1] == 2 && Lq > 0 && Lt > 0)
+    *prev_t = Lt;  // dpmatrix.h:868
+  return 0;
+}
+
+int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, int32_t max_pairs, int32_t* npairs,
+                       float* score) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (p < 0 || p >= b.npairs) return fail("pair index out of range");
+  if (c->sc.local) return fail("aadp_batch_optimal: local tracebacks go through aadp_batch_fetch_pair (they need find_max)");
+  const int qs = b.pair_q[p], ts = b.pair_t[p];
+  const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  std::vector<uint8_t> tb((size_t)std::max<int64_t>(b.tb_off[p + 1] - b.tb_off[p], 1));
+  int32_t fin[4];
+  if (aadp_batch_fetch_tb(c, p, direction, tb.data(), (int64_t)tb.size(), fin)) return 1;
+  if (score) *score = (float)fin[0] / (float)(1 << fin[3]);
+  // optimal.h:57-74 / optimal_rev.h:57-76: follow prev_* from the final cell to the anchor
+  const int rev = (direction == AADP_REV);
+  int i = rev ? 0 : Lq + 1, j = rev ? 0 : Lt + 1;
+  const int ei = rev ? Lq + 1 : 0, ej = rev ? Lt + 1 : 0;
+  std::vector<int32_t> path;
+  path.push_back(i);
+  path.push_back(j);
+  int guard = 0;
+  while (rev ? (i < ei) : (i > 0)) {
+    int32_t pi, pj;
+    if (aadp_decode_cell(tb.data(), Lq, Lt, direction, c->align_type, c->flags, fin, i, j, &pi, &pj)) return 1;
+    i = pi;
+    j = pj;
+    path.push_back(i);
+    path.push_back(j);
+    if (i < 0 || j < 0 || ++guard > Lq + Lt + 4) break;
+  }
+  const int n = (int)path.size() / 2;
+  if (npairs) *npairs = n;
+  for (int k = 0; k < n && k < max_pairs; ++k) {
+    const int src = rev ? k : n - 1 - k;  // forward alignments are built with prepend()
+    pairs[2 * k] = path[2 * src];
+    pairs[2 * k + 1] = path[2 * src + 1];
+  }
+  if (i != ei || j != ej) {
+    g_err = "Illegal alignment start pair";  // optimal.h:74
+    return 3;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,522 @@
+// aadp_kernels.cuh -- hand-written sm_100a kernels for the affine-gap DP fill of
+// christang/alignment-algos (dpmatrix.h:356-1030 driven by AASubstitutionEval, aasubalib.h:8-87).
+//
+// Recurrence.  The reference scans, for every interior cell (i,j), the whole previous row and the
+// whole previous column (dpmatrix.h:459-480).  For the affine gap cost gi+ge*(len-1) that is the
+// three-state recurrence, written here in FLOW coordinates (flow = matrix
+// coordinates for the forward fill, mirrored coordinates for the reverse fill):
+//     M(i,j) = sim(i,j) + X(i-1,j-1)                       X = max3(M,E,F), ties M > E > F
+//     E(i,j) = max(E(i,j-1) - ge, M(i,j-1) - gi)           ties keep the extension (smaller k)
+//     F(i,j) = max(F(i-1,j) - ge, M(i-1,j) - gi)           ties keep the extension (smaller k)
+// which reproduces the reference's strict-'>' scan order match -> deletions(k asc) -> insertions
+// (k asc) (dpmatrix.h:463,475) exactly when all scores are integers in the chosen units.
+// M is the reference's DPCell::score.  E and F never chain into each other (a predecessor moves
+// one index by exactly 1, dpmatrix.h:453-480).
+//
+// Mapping (one warp per pair, "striped + skewed"): lane l owns K consecutive template columns and
+// processes row i = step - l + 1, so the E chain crosses lanes with three __shfl_up_sync per step
+// and everything else stays in registers.  Substitution scores come from a per-pair int8
+// template profile staged in shared memory (prof[a][column] = sub[a][t_column]); the row's query
+// residue selects the profile row, one 8/16-byte conflict-free LDS per lane per step.
+//
+// Packed traceback (4 bit/cell, "planes"): for flow cell (i,j)
+//     plane0 selE  = [E > M]          plane1 selF  = [F > max(M,E)]
+//     plane2 eopen = [M(i,j-1)-gi > E(i,j-1)-ge]     plane3 fopen = [M(i-1,j)-gi > F(i-1,j)-ge]
+// stored per row as 32-bit words covering 8 columns: byte p = plane p, bit (7-c) = column 8g+c+1.
+// The absolute predecessor the reference stores in DPCell (dpmatrix.h:28-37) is recovered by
+// walking eopen / fopen bits (see decode_prev below).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aadp {
+
+constexpr int kNeg32 = -(1 << 30);    // "-infinity" for E/F seeds (int32 path)
+constexpr int kFloor32 = -(1 << 29);  // clamp floor of M (never reached by real scores)
+constexpr int kWarpsPerCta = 4;
+
+__host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+// packed-traceback row stride in bytes: one 32-bit word per 8 columns, rows padded to 16 B
+__host__ __device__ inline int64_t tb_row_bytes(int Lt) { return round_up64(4 * (int64_t)((Lt + 7) / 8), 16); }
+// score-matrix row stride in elements (rows hold columns 1..Lt, padded to 16 elements)
+__host__ __device__ inline int64_t sc_row_elems(int Lt) { return round_up64(Lt, 16); }
+
+struct Scoring {
+  int A;        // alphabet size
+  int gi, ge;   // gap penalties in integer units (scaled by 2^scale_log2)
+  int delfree;  // aasubalib.h:39-42: free end gaps in the template (local, semi_local, local_global)
+  int insfree;  // aasubalib.h:65-68: free end gaps in the query (local, semi_local, global_local)
+  int local;    // align_type == local (dpmatrix.h:155): clamp at 0
+  int scale_log2;
+};
+
+struct FillParams {
+  Scoring sc;
+  const int8_t* sub8;        // A*A scaled substitution scores
+  const uint8_t* residues;   // sequence arena
+  const int64_t* seq_off;    // nseq+1
+  const int32_t* pair_q;     // npairs
+  const int32_t* pair_t;
+  const int32_t* order;      // work list (pair ids) for this launch
+  int n_items;
+  int rev;                   // 0 = forward flow, 1 = reverse flow
+  unsigned int* counter;     // dynamic work counter (zeroed before launch)
+  uint8_t* tb;               // packed traceback blob of this direction (or null)
+  const int64_t* tb_off;     // per pair byte offset
+  void* sc_blob;             // score blob of this direction (int16 or int32 elements)
+  const int64_t* sc_off;     // per pair element offset
+  int32_t* fin_score;        // per pair: final-cell score (integer units)
+  int32_t* fin_kind;         // 0 = diagonal, 1 = row (deletion), 2 = column (insertion)
+  int32_t* fin_k;            // kind 1: flow column k of the predecessor; kind 2: -1 (resolved by decode)
+  int4* bbuf;                // stripe boundary buffer: [warp slot][bb_rows]
+  int bb_rows;
+  double cells_hint;         // host-side bookkeeping only (cell updates of this launch)
+};
+
+// gap(len) in integer units; 0 for len < 1 (aasubalib.h:33-38)
+__host__ __device__ inline int gap_w(int gi, int ge, int len) { return len < 1 ? 0 : gi + ge * (len - 1); }
+
+// prmt.b32 with the full 4-bit selector nibbles (bit 3 = replicate the sign of the selected byte).
+// __byte_perm() masks the selector to 3 bits, so the PTX instruction is issued directly.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+__device__ __forceinline__ int sext8(uint32_t w, int c) {
+  // byte c of w -> int32: byte 0 = the byte, bytes 1..3 = its sign
+  const uint32_t sel = (uint32_t)c | ((uint32_t)(c | 8) << 4) | ((uint32_t)(c | 8) << 8) | ((uint32_t)(c | 8) << 12);
+  return (int)prmt(w, 0u, sel);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp fills one pair in one direction.  K = columns per lane (8 or 16).
+// TBM: write packed traceback.  STM: 0 = no score matrix, 1 = int16, 2 = int32.
+// ------------------------------------------------------------------------------------------------
+template <int K, int TBM, int STM>
+__device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, int8_t* prof,
+                                               const int8_t* s_sub, int4* bb, int lane) {
+  constexpr int W = 32 * K;
+  const Scoring& S = P.sc;
+  const int gi = S.gi, ge = S.ge;
+  const int floorM = S.local ? 0 : kFloor32;
+
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
+  const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
+  const uint8_t* qseq = P.residues + qo;
+  const uint8_t* tseq = P.residues + to;
+  const int rev = P.rev;
+
+  // Special cases #1/#2 (dpmatrix.h:374-390, 712-728): an empty sequence forces one gap.
+  if (Lq == 0 || Lt == 0) {
+    if (lane == 0) {
+      int s;
+      if (Lq == 0) s = -(S.delfree ? 0 : gap_w(gi, ge, Lt));
+      else s = -(S.insfree ? 0 : gap_w(gi, ge, Lq));
+      P.fin_score[pair] = s;
+      P.fin_kind[pair] = 0;
+      P.fin_k[pair] = 0;
+    }
+    return;
+  }
+
+  const int64_t tbs = tb_row_bytes(Lt);
+  const int64_t scs = sc_row_elems(Lt);
+  uint8_t* tbp = TBM ? P.tb + P.tb_off[pair] : nullptr;
+
+  const int nstripes = (Lt + W - 1) / W;
+  // running row-part of the final cell: best M(Lq,k) - pen(Lt-k) over k < Lt, smallest k on ties
+  int rb_val = kNeg32, rb_k = 0;
+  int diag_val = kNeg32, col_val = kNeg32;
+
+  for (int st = 0; st < nstripes; ++st) {
+    const int jbase = st * W + lane * K;  // flow column of register c is jbase + c + 1
+    const int cols_here = min(W, Lt - st * W);
+    const int n_act = (cols_here + K - 1) / K;
+
+    // ---- template profile for this stripe: prof[a*W + lane*K + c] = sub8[a][t_(jbase+c+1)]
+    {
+      uint32_t tc[K / 4];
+#pragma unroll
+      for (int w = 0; w < K / 4; ++w) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          int j = jbase + w * 4 + b + 1;
+          uint32_t code = 0;
+          if (j <= Lt) code = rev ? tseq[Lt - j] : tseq[j - 1];
+          x |= code << (8 * b);
+        }
+        tc[w] = x;
+      }
+      __syncwarp();  // previous users of prof are done
+      for (int a = 0; a < S.A; ++a) {
+        const int8_t* row = s_sub + a * S.A;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(prof + a * W + lane * K);
+#pragma unroll
+        for (int w = 0; w < K / 4; ++w) {
+          uint32_t x = tc[w], o = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) o |= (uint32_t)(uint8_t)row[(x >> (8 * b)) & 0xff] << (8 * b);
+          dst[w] = o;
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- state for virtual row 0
+    int Xp[K], Fs[K], Mg[K], nge[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      int j = jbase + c + 1;
+      Xp[c] = -(S.delfree ? 0 : gap_w(gi, ge, j));  // X(0,j): dpmatrix.h:412-418
+      Fs[c] = kNeg32;
+      Mg[c] = kNeg32;
+      nge[c] = (S.insfree && j == Lt) ? 0 : -ge;  // zero-penalty F chain in the last column
+    }
+    int xl_hold;  // X(i-1, jbase): diagonal input of the lane's first column
+    {
+      int jl = jbase;  // column to the left of the lane's first column
+      xl_hold = (jl == 0) ? 0 : -(S.delfree ? 0 : gap_w(gi, ge, jl));
+    }
+    int x_pub = 0, e_pub = kNeg32, mg_pub = kNeg32;
+    int a_nxt = 0;
+    if (lane == 0) a_nxt = rev ? qseq[Lq - 1] : qseq[0];
+
+    const int nsteps = Lq + n_act - 1;
+    for (int s = 0; s < nsteps; ++s) {
+      int xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
+      int e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
+      int mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
+      const int i = s - lane + 1;
+      const int a_cur = a_nxt;
+      {
+        int inx = i + 1;
+        if (inx >= 1 && inx <= Lq) a_nxt = rev ? qseq[Lq - inx] : qseq[inx - 1];
+      }
+      if (lane == 0) {
+        if (st == 0) {
+          xn = -(S.insfree ? 0 : gap_w(gi, ge, i));  // X(i,0): dpmatrix.h:420-426
+          e_in = kNeg32;
+          mg_in = kNeg32;
+        } else if (i <= Lq) {
+          int4 b = bb[i];
+          xn = b.x;
+          e_in = b.y;
+          mg_in = b.z;
+        }
+      }
+      const bool active = (i >= 1) && (i <= Lq) && (lane < n_act);
+      if (active) {
+        uint32_t pw[K / 4];
+        if (K == 16) {
+          uint4 v = *reinterpret_cast<const uint4*>(prof + a_cur * W + lane * K);
+          pw[0] = v.x; pw[1] = v.y; pw[K / 4 - 2] = v.z; pw[K / 4 - 1] = v.w;
+        } else {
+          uint2 v = *reinterpret_cast<const uint2*>(prof + a_cur * W + lane * K);
+          pw[0] = v.x; pw[1] = v.y;
+        }
+        int Xd = xl_hold, E = e_in, Mgl = mg_in;
+        uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        uint32_t tbw[K / 8];
+        int mrow[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const int sim = sext8(pw[c >> 2], c & 3);
+          const int M = __viaddmax_s32(sim, Xd, floorM);
+          Xd = Xp[c];
+          int F, X;
+          if (TBM) {
+            const int Eext = E - ge;
+            const int Fext = Fs[c] + nge[c];
+            const int dE = Eext - Mgl;  // < 0  <=> the open candidate wins strictly
+            E = max(Eext, Mgl);
+            const int dF = Fext - Mg[c];
+            F = max(Fext, Mg[c]);
+            const int dS1 = M - E;  // < 0 <=> E > M
+            const int t = max(M, E);
+            const int dS2 = t - F;  // < 0 <=> F > max(M,E)
+            X = max(t, F);
+            acc0 = __funnelshift_l((uint32_t)dS1, acc0, 1);
+            acc1 = __funnelshift_l((uint32_t)dS2, acc1, 1);
+            acc2 = __funnelshift_l((uint32_t)dE, acc2, 1);
+            acc3 = __funnelshift_l((uint32_t)dF, acc3, 1);
+            if ((c & 7) == 7)
+              tbw[c >> 3] = __byte_perm(__byte_perm(acc0, acc1, 0x0040), __byte_perm(acc2, acc3, 0x0040), 0x5410);
+          } else {
+            E = __viaddmax_s32(E, -ge, Mgl);
+            F = __viaddmax_s32(Fs[c], nge[c], Mg[c]);
+            X = __vimax3_s32(M, E, F);
+          }
+          Mgl = M - gi;
+          Xp[c] = X;
+          Fs[c] = F;
+          Mg[c] = Mgl;
+          if (STM) mrow[c] = M;
+        }
+        xl_hold = xn;
+        x_pub = Xp[K - 1];
+        e_pub = E;
+        mg_pub = Mgl;
+        if (TBM) {
+          uint8_t* dst = tbp + (int64_t)(i - 1) * tbs + (int64_t)(st * W + lane * K) / 2;
+          if (K == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(tbw[0], tbw[K / 8 - 1]);
+          else *reinterpret_cast<uint32_t*>(dst) = tbw[0];
+        }
+        if (STM == 1) {
+          int16_t* dst = reinterpret_cast<int16_t*>(P.sc_blob) + P.sc_off[pair] + (int64_t)(i - 1) * scs + st * W + lane * K;
+          uint32_t pk[K / 2];
+#pragma unroll
+          for (int c = 0; c < K / 2; ++c) pk[c] = __byte_perm((uint32_t)mrow[2 * c], (uint32_t)mrow[2 * c + 1], 0x5410);
+#pragma unroll
+          for (int c = 0; c < K / 8; ++c)
+            reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        } else if (STM == 2) {
+          int32_t* dst = reinterpret_cast<int32_t*>(P.sc_blob) + P.sc_off[pair] + (int64_t)(i - 1) * scs + st * W + lane * K;
+#pragma unroll
+          for (int c = 0; c < K / 4; ++c)
+            reinterpret_cast<int4*>(dst)[c] = make_int4(mrow[4 * c], mrow[4 * c + 1], mrow[4 * c + 2], mrow[4 * c + 3]);
+        }
+        if (st + 1 < nstripes && lane == 31) bb[i] = make_int4(x_pub, e_pub, mg_pub, 0);
+      }
+    }
+
+    // ---- after the last row: contributions of this stripe's columns to the final cell
+    // (dpmatrix.h:504-534).  Mg[c] + gi = M(Lq, j).
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      int j = jbase + c + 1;
+      int m = Mg[c] + gi;
+      if (j < Lt) {
+        int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt - j));
+        if (v > rb_val) { rb_val = v; rb_k = j; }
+      } else if (j == Lt) {
+        diag_val = m;
+        col_val = (Lq >= 2) ? Fs[c] + (S.insfree ? gi : 0) : kNeg32;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- final cell: match, then bottom-row candidates (k ascending), then right-column
+  // candidates, strict '>' (dpmatrix.h:504-534 / 844-874)
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    int v2 = __shfl_xor_sync(0xffffffffu, rb_val, o);
+    int k2 = __shfl_xor_sync(0xffffffffu, rb_k, o);
+    if (v2 > rb_val || (v2 == rb_val && k2 < rb_k)) { rb_val = v2; rb_k = k2; }
+    diag_val = max(diag_val, __shfl_xor_sync(0xffffffffu, diag_val, o));
+    col_val = max(col_val, __shfl_xor_sync(0xffffffffu, col_val, o));
+  }
+  if (lane == 0) {
+    int best = diag_val, kind = 0, k = Lt;
+    if (S.local) best = max(best, 0);
+    if (Lt >= 2 && rb_val > best) { best = rb_val; kind = 1; k = rb_k; }
+    if (col_val > best) { best = col_val; kind = 2; k = -1; }
+    P.fin_score[pair] = best;
+    P.fin_kind[pair] = kind;
+    P.fin_k[pair] = k;
+  }
+}
+
+template <int K, int TBM, int STM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int W = 32 * K;
+  const int A = P.sc.A;
+  int8_t* s_sub = reinterpret_cast<int8_t*>(smem);
+  const int sub_bytes = (A * A + 15) / 16 * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + warp * A * W);
+  for (int x = threadIdx.x; x < A * A; x += blockDim.x) s_sub[x] = P.sub8[x];
+  __syncthreads();
+  const int slot = blockIdx.x * kWarpsPerCta + warp;
+  int4* bb = P.bbuf ? P.bbuf + (int64_t)slot * P.bb_rows : nullptr;
+  for (;;) {
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(P.counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= (unsigned int)P.n_items) break;
+    fill_pair_warp<K, TBM, STM>(P, P.order[item], prof, s_sub, bb, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed-traceback decode (shared by host and device).
+// tb: packed traceback of one pair in FLOW coordinates. Returns the flow predecessor of flow
+// cell (a,b), 1 <= a <= Lq, 1 <= b <= Lt.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int tb_plane(const uint8_t* tb, int64_t tbs, int a, int b, int plane) {
+  const uint8_t byte = tb[(int64_t)(a - 1) * tbs + 4 * ((b - 1) >> 3) + plane];
+  return (byte >> (7 - ((b - 1) & 7))) & 1;
+}
+
+__host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int a, int b, int* pa, int* pb) {
+  if (a == 1 || b == 1) { *pa = 0; *pb = 0; return; }  // dpmatrix.h:408-426: boundary cells point at the anchor
+  const int64_t tbs = tb_row_bytes(Lt);
+  const int r = a - 1, c = b - 1;
+  if (tb_plane(tb, tbs, r, c, 1)) {  // F won: walk up column c while the gap was extended
+    int rr = r;
+    while (rr > 1 && !tb_plane(tb, tbs, rr, c, 3)) --rr;
+    *pa = rr - 1; *pb = c;
+  } else if (tb_plane(tb, tbs, r, c, 0)) {  // E won: walk left along row r
+    int cc = c;
+    while (cc > 1 && !tb_plane(tb, tbs, r, cc, 2)) --cc;
+    *pa = r; *pb = cc - 1;
+  } else {
+    *pa = r; *pb = c;
+  }
+}
+
+// Predecessor of the final flow cell (Lq+1, Lt+1) from the per-pair record.
+__host__ __device__ inline void decode_final(const uint8_t* tb, int Lq, int Lt, int kind, int k, int* pa, int* pb) {
+  if (Lq == 0 || Lt == 0) { *pa = 0; *pb = 0; return; }
+  if (kind == 0) { *pa = Lq; *pb = Lt; }
+  else if (kind == 1) { *pa = Lq; *pb = k; }
+  else {
+    const int64_t tbs = tb_row_bytes(Lt);
+    int rr = Lq;
+    while (rr > 1 && !tb_plane(tb, tbs, rr, Lt, 3)) --rr;
+    *pa = rr - 1; *pb = Lt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Near-optimal cell set (consumed by ucw.h:141-180): one block per pair.
+// mask bit (j-1) of row (i-1) is set iff F(i,j) + R(i,j) - sim(i,j) > thr, thr = cw.h:86-88.
+// ------------------------------------------------------------------------------------------------
+struct MaskParams {
+  Scoring sc;
+  const int8_t* sub8;
+  const uint8_t* residues;
+  const int64_t* seq_off;
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  int n_pairs;
+  int st_mode;               // 1 = int16 scores, 2 = int32
+  const void* scF; const void* scR;
+  const int64_t* sc_off;
+  const int32_t* fin_fwd;    // forward final score (integer units)
+  float delta_ratio;
+  uint32_t* mask;            // bit blob
+  const int64_t* mask_off;   // per pair word offset
+  float* threshold;          // per pair (may be null)
+  long long* count;          // per pair (may be null)
+};
+
+__host__ __device__ inline int64_t mask_row_words(int Lt) { return (Lt + 31) / 32; }
+
+__device__ __forceinline__ float nearopt_threshold(float opt, float delta_ratio) {
+  float thr = __fmul_rn(1.f - delta_ratio, opt);  // (1.f - delta_ratio) * opt, cw.h:86-87
+  float alt = __fsub_rn(opt, 0.1f);               // cw.h:88
+  return fminf(thr, alt);
+}
+
+__global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
+  const int pair = blockIdx.x;
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
+  const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
+  const float inv = 1.f / (float)(1 << P.sc.scale_log2);
+  const float opt = (float)P.fin_fwd[pair] * inv;
+  const float thr = nearopt_threshold(opt, P.delta_ratio);
+  if (threadIdx.x == 0 && P.threshold) P.threshold[pair] = thr;
+  if (Lq == 0 || Lt == 0) { if (threadIdx.x == 0 && P.count) P.count[pair] = 0; return; }
+  const int64_t scs = sc_row_elems(Lt), mws = mask_row_words(Lt);
+  const int64_t so = P.sc_off[pair];
+  uint32_t* mk = P.mask + P.mask_off[pair];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int A = P.sc.A;
+  long long cnt = 0;
+  for (int i = 1 + warp; i <= Lq; i += nw) {
+    const int qa = P.residues[qo + i - 1];
+    for (int j0 = 0; j0 < Lt; j0 += 32) {
+      const int j = j0 + lane + 1;
+      bool on = false;
+      if (j <= Lt) {
+        int f, r;
+        const int64_t fo = so + (int64_t)(i - 1) * scs + (j - 1);
+        const int64_t ro = so + (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
+        if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[fo]; r = ((const int16_t*)P.scR)[ro]; }
+        else { f = ((const int32_t*)P.scF)[fo]; r = ((const int32_t*)P.scR)[ro]; }
+        const int sm = P.sub8[qa * A + P.residues[to + j - 1]];
+        float v = __fadd_rn((float)f * inv, (float)r * inv);
+        v = __fsub_rn(v, (float)sm * inv);
+        on = v > thr;
+      }
+      const uint32_t bits = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) { mk[(int64_t)(i - 1) * mws + (j0 >> 5)] = bits; cnt += __popc(bits); }
+    }
+  }
+  if (P.count) {
+    __shared__ long long s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (lane == 0 && cnt) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) P.count[pair] = s_cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense, reference-shaped expansion of one pair (DPCell::score / prev_*; dpmatrix.h:28-37).
+// ------------------------------------------------------------------------------------------------
+struct DenseParams {
+  Scoring sc;
+  int Lq, Lt, rev, repro_rev_bug;
+  int st_mode;
+  const void* sc_blob; int64_t sc_off;
+  const uint8_t* tb;  // packed traceback of this pair/direction (or null)
+  int fin_score, fin_kind, fin_k;
+  float* score;       // (Lq+2)*(Lt+2) or null
+  int32_t* prev_q;    // or null
+  int32_t* prev_t;
+};
+
+__global__ void dense_kernel(const DenseParams P) {
+  const int sz1 = P.Lq + 2, sz2 = P.Lt + 2;
+  const int64_t n = (int64_t)sz1 * sz2;
+  const float inv = 1.f / (float)(1 << P.sc.scale_log2);
+  const int64_t scs = sc_row_elems(P.Lt);
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(o / sz2), j = (int)(o % sz2);
+    // flow coordinates
+    const int a = P.rev ? P.Lq + 1 - i : i, b = P.rev ? P.Lt + 1 - j : j;
+    float s = 0.f;
+    int pa = -1, pb = -1;  // flow predecessor; -1 = DPCell::null
+    const bool interior = a >= 1 && a <= P.Lq && b >= 1 && b <= P.Lt;
+    int si = 0;
+    if (interior) {
+      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1)];
+      else if (P.st_mode == 2) si = ((const int32_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1)];
+      s = (float)si * inv;
+      if (P.tb) {
+        decode_prev(P.tb, P.Lt, a, b, &pa, &pb);
+        // local fills: a cell clamped to 0 keeps the match predecessor (dpmatrix.h:616-646)
+        if (P.sc.local && si == 0 && a > 1 && b > 1) { pa = a - 1; pb = b - 1; }
+      }
+    } else if (a == P.Lq + 1 && b == P.Lt + 1) {
+      s = (float)P.fin_score * inv;
+      if (P.Lq == 0 || P.Lt == 0) { pa = 0; pb = 0; }
+      else if (P.tb) decode_final(P.tb, P.Lq, P.Lt, P.fin_kind, P.fin_k, &pa, &pb);
+      else if (P.fin_kind == 0) { pa = P.Lq; pb = P.Lt; }
+      else if (P.fin_kind == 1) { pa = P.Lq; pb = P.fin_k; }
+    }
+    if (P.score) P.score[o] = s;
+    if (P.prev_q) {
+      int pi = -1, pj = -1;
+      if (pa >= 0) {
+        pi = P.rev ? P.Lq + 1 - pa : pa;
+        pj = P.rev ? P.Lt + 1 - pb : pb;
+        // dpmatrix.h:868: the global reverse fill stores opt_j = t1_m1 for left-column candidates
+        if (P.rev && !P.sc.local && P.repro_rev_bug && !interior && P.fin_kind == 2 && P.Lq > 0 && P.Lt > 0) pj = P.Lt;
+      }
+      P.prev_q[o] = pi;
+      P.prev_t[o] = pj;
+    }
+  }
+}
+
+}  // namespace aadp

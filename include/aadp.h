@@ -1,0 +1,143 @@
+/* include/aadp.h -- C ABI of the B200-native DP-fill library (libaadp.so).
+ *
+ * Drop-in boundary for ONE path of christang/alignment-algos: the dynamic-programming matrix
+ * fill of dpmatrix.{h,cpp} (forward + reverse, global + local), the optimal tracebacks of
+ * optimal.h / optimal_rev.h and the near-optimal cell set the enumerators of ucw.h / cw.h
+ * consume.  The reference has no FFI of its own (it is one C++ template library); the entry
+ * points below are what its DPMatrix<S1,S2,Etype>::build() (dpmatrix.h:291-317) binds to when
+ * the fill is moved to the GPU -- see INTEGRATION.md for the C++ side of the binding
+ * (include/hmap2/dpmatrix.h is that binding, source compatible with the reference class).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - sequences are residue CODES 0..A-1 without the '^'/'$' sentinels the reference adds
+ *     (sequence.cpp:15-16); every matrix-shaped output is (Lq+2) x (Lt+2) row-major, index 0 =
+ *     Head, last = Tail, exactly the reference's DPCell matrix (dpmatrix.h:250-259);
+ *   - every function returns 0 on success, nonzero on error; aadp_last_error() returns a
+ *     thread-local message (the C++ wrapper rethrows it as std::string like dpmatrix.h:361);
+ *   - a context owns one device + one stream and is not shared between threads;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails loudly.
+ */
+#ifndef AADP_H
+#define AADP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aadp_ctx aadp_ctx;
+
+/* alib.h:20-26 (align_t) */
+#define AADP_GLOBAL_LOCAL 0
+#define AADP_GLOBAL 1
+#define AADP_LOCAL_GLOBAL 2
+#define AADP_LOCAL 3
+#define AADP_SEMI_LOCAL 4
+
+/* dpmatrix.h:23-26 (direction_t); 3 = both */
+#define AADP_FWD 1
+#define AADP_REV 2
+
+/* aadp_set_scoring flags */
+#define AADP_REPRO_REV_BUG 1u /* reproduce dpmatrix.h:868 (opt_j = t1_m1) -- the reference's behaviour */
+
+/* `what` bits of the batch calls */
+#define AADP_W_FWD 1u    /* forward fill (build_forw[_local]_dpm_nonlinear_gaps, dpmatrix.h:356,538) */
+#define AADP_W_REV 2u    /* reverse fill (build_rev[_local]_dpm_nonlinear_gaps, dpmatrix.h:691,879) */
+#define AADP_W_TB 4u     /* keep bit-packed traceback (4 bit/cell) for every filled direction */
+#define AADP_W_SCORES 8u /* keep the score matrices (needed by AADP_W_MASK and by local tracebacks) */
+#define AADP_W_MASK 16u  /* near-optimal cell set {F+R-sim > thr} (ucw.h:141-180), needs FWD|REV */
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+aadp_ctx* aadp_create(int device); /* NULL on failure (see aadp_last_error) */
+void aadp_destroy(aadp_ctx* ctx);
+const char* aadp_last_error(void);
+const char* aadp_version(void);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's
+ * current stream, so that the caller's events bracket the kernels. NULL = the context's own.  */
+int aadp_set_stream(aadp_ctx* ctx, void* cuda_stream);
+int aadp_synchronize(aadp_ctx* ctx);
+
+/* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)
+ * sub is A x A row-major, sub[q_code*A + t_code] == SubstitutionMatrix::score (submatrix.h:36-38).
+ * gap(len) = gi + ge*(len-1) (aasubalib.h:37-38) with the per-align_type free end gaps of
+ * aasubalib.h:27-77.  All of sub, gi, ge must lie on one dyadic grid (multiples of 2^-s, s<=8;
+ * integer matrices trivially do): that is the class for which results are bit-exact.          */
+int aadp_set_scoring(aadp_ctx* ctx, const float* sub, int A, float gi, float ge, int align_type,
+                     uint32_t flags);
+
+/* ---- single pair, dense reference-shaped outputs: replaces the DPMatrix constructor
+ * (dpmatrix.h:147-165) + build() (dpmatrix.h:291-317).  direction: AADP_FWD, AADP_REV or 3.
+ * Outputs (host pointers, any may be NULL), all (Lq+2)*(Lt+2):
+ *   score_*          DPCell::score            prevq_* / prevt_*   DPCell::prev_query_idx / prev_template_idx
+ *   nearopt          1 byte per cell, 1 where F+R-sim > threshold (needs direction 3, delta_ratio >= 0)
+ *   threshold        min((1-delta_ratio)*opt, opt-0.1f)  (cw.h:86-88)                           */
+int aadp_fill_pair(aadp_ctx* ctx, const uint8_t* q, int Lq, const uint8_t* t, int Lt,
+                   int direction, float delta_ratio, float* score_fwd, int32_t* prevq_fwd,
+                   int32_t* prevt_fwd, float* score_rev, int32_t* prevq_rev, int32_t* prevt_rev,
+                   uint8_t* nearopt, float* threshold);
+
+/* ---- batch of pairs, HOST buffers (the end-to-end call) ------------------------------------
+ * residues: all sequences back to back; sequence s is residues[seq_off[s] .. seq_off[s+1]).
+ * pair p aligns query pair_q[p] against template pair_t[p].
+ * Per-pair host outputs (any may be NULL): fwd_score[p] = D[last][last].score of the forward
+ * matrix, rev_score[p] = D[0][0].score of the reverse matrix, threshold[p], nearopt_count[p].
+ * Traceback / score matrices / masks stay RESIDENT in HBM inside the context (they are tens of
+ * GB for 100k pairs); fetch what is needed with aadp_batch_fetch_*.                           */
+int aadp_fill_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,
+                    const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what,
+                    float delta_ratio, float* fwd_score, float* rev_score, float* threshold,
+                    int64_t* nearopt_count);
+
+/* Same work with inputs ALREADY RESIDENT in device memory and per-pair outputs left in device
+ * memory (d_* are device pointers; may be NULL like above). Asynchronous on the context stream. */
+int aadp_upload_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,
+                      const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what);
+int aadp_run_batch(aadp_ctx* ctx, uint32_t what, float delta_ratio, float* d_fwd_score,
+                   float* d_rev_score, float* d_threshold, int64_t* d_nearopt_count);
+
+/* Bytes of HBM the resident batch products occupy (0 if none). which: AADP_W_TB / _SCORES / _MASK */
+int64_t aadp_batch_resident_bytes(aadp_ctx* ctx, uint32_t which);
+/* Number of kernels launched by the last batch/pair call (for bench.py's gpu_launches). */
+int64_t aadp_last_launch_count(aadp_ctx* ctx);
+/* Cell updates (sum of Lq*Lt per filled direction) of the last batch call. */
+double aadp_last_cell_updates(aadp_ctx* ctx);
+
+/* Per-launch device timing (CUDA events on the context stream around every kernel of the batch
+ * calls). Off by default. aadp_profile_get returns the idx-th launch of the last run: kernel
+ * name, milliseconds and the cell updates that launch processed (0 for helper kernels).       */
+int aadp_set_profiling(aadp_ctx* ctx, int on);
+int aadp_profile_count(aadp_ctx* ctx);
+int aadp_profile_get(aadp_ctx* ctx, int idx, char* name, int name_cap, float* ms, double* cells);
+
+/* Dense, reference-shaped view of pair p of the resident batch (same outputs as aadp_fill_pair;
+ * requires the batch to have been run with the corresponding AADP_W_* bits).                    */
+int aadp_batch_fetch_pair(aadp_ctx* ctx, int64_t p, float* score_fwd, int32_t* prevq_fwd,
+                          int32_t* prevt_fwd, float* score_rev, int32_t* prevq_rev,
+                          int32_t* prevt_rev, uint8_t* nearopt);
+
+/* Optimal alignment of pair p traced on the GPU from the packed traceback: replaces
+ * Optimal::enumerate (optimal.h:47-75) for direction AADP_FWD and Optimal_Rev::enumerate
+ * (optimal_rev.h:47-78) for AADP_REV. pairs receives 2 ints (query_idx, template_idx) per
+ * aligned pair in alignment order, including (0,0) and (last,last). Returns 3 with
+ * "Illegal alignment start pair" when the reference would throw (optimal.h:74).                 */
+int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, int32_t max_pairs,
+                       int32_t* npairs, float* score);
+
+/* ---- packed traceback format helpers (host side, no GPU needed) ---------------------------
+ * Row stride in bytes of the packed traceback of a pair with template length Lt.               */
+int64_t aadp_tb_row_bytes(int Lt);
+/* Decode one cell of a packed traceback fetched with aadp_batch_fetch_tb. (i,j) and the result
+ * are reference matrix coordinates; direction selects the fwd or rev conventions.              */
+int aadp_batch_fetch_tb(aadp_ctx* ctx, int64_t p, int direction, uint8_t* tb, int64_t tb_bytes,
+                        int32_t* final_rec /* [4]: score units, kind, k, scale_log2 */);
+int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align_type,
+                     uint32_t flags, const int32_t* final_rec, int i, int j, int32_t* prev_q,
+                     int32_t* prev_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AADP_H */

@@ -1,0 +1,180 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the oracle on the same seeded inputs and against the golden vectors of the real reference.
+Bit-exact bar: scores, traceback pointers and near-optimal cell sets for integer scoring."""
+import numpy as np
+import pytest
+
+from util import po, MODES, MODE_NAMES, golden_cases, golden_case, rand_pair, assert_matrix_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import alignment_algos_b200 as a
+    c = a.Context(0)
+    yield c
+    c.close()
+
+
+def _check_pair(ctx, O, q, t, tag, mask_dr=None):
+    import alignment_algos_b200 as a
+    out = ctx.fill_pair(q, t, a.BOTH, delta_ratio=(mask_dr if mask_dr is not None else -1.0))
+    for d, nm in ((po.FWD, "fwd"), (po.REV, "rev")):
+        s, pq, pt = O.fill(q, t, d, True, fast=True)
+        assert_matrix_equal(tag + " score_" + nm, out["score_" + nm], s)
+        assert_matrix_equal(tag + " prevq_" + nm, out["prevq_" + nm], pq)
+        assert_matrix_equal(tag + " prevt_" + nm, out["prevt_" + nm], pt)
+    if mask_dr is not None:
+        F = O.fill(q, t, po.FWD, True, fast=True)[0]
+        R = O.fill(q, t, po.REV, True, fast=True)[0]
+        thr = O.threshold(float(F[-1, -1]), mask_dr)
+        mask, _ = O.nearopt_mask(F, R, O.sim(q, t), thr)
+        assert out["threshold"] == thr
+        assert_matrix_equal(tag + " nearopt", out["nearopt"], mask)
+
+
+def test_golden_vectors_of_the_reference(ctx, golden):
+    import alignment_algos_b200 as a
+    sub = golden["sub"]
+    for name in golden_cases(golden):
+        q, t, gi, ge, at = golden_case(golden, name)
+        ctx.set_scoring(sub, gi, ge, at)
+        out = ctx.fill_pair(q, t, a.BOTH)
+        for nm in ("fwd", "rev"):
+            assert_matrix_equal(name + " score_" + nm, out["score_" + nm], golden[name + "." + nm + ".score"])
+            assert_matrix_equal(name + " pq_" + nm, out["prevq_" + nm], golden[name + "." + nm + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + " pt_" + nm, out["prevt_" + nm], golden[name + "." + nm + ".pt"].astype(np.int32))
+
+
+def test_golden_ucw_union_equals_gpu_mask(ctx, golden):
+    import alignment_algos_b200 as a
+    sub = golden["sub"]
+    n = 0
+    for name in golden_cases(golden):
+        for dr in (5, 20):
+            key = "%s.ucw%02d" % (name, dr)
+            if key + ".union" not in golden:
+                continue
+            q, t, gi, ge, at = golden_case(golden, name)
+            ctx.set_scoring(sub, gi, ge, at)
+            out = ctx.fill_pair(q, t, a.BOTH, delta_ratio=dr / 100.0)
+            shape = (len(q) + 2, len(t) + 2)
+            union = np.unpackbits(golden[key + ".union"])[: shape[0] * shape[1]].reshape(shape)
+            interior = np.zeros_like(union)
+            interior[1:-1, 1:-1] = union[1:-1, 1:-1]
+            assert out["threshold"] == golden[key + ".thr"][0]
+            assert_matrix_equal(key, out["nearopt"], interior)
+            n += 1
+    assert n >= 8
+
+
+@pytest.mark.parametrize("at", MODES, ids=[MODE_NAMES[m] for m in MODES])
+def test_random_pairs_all_modes(ctx, blosum, at):
+    _, M = blosum
+    rng = np.random.default_rng(100 + at)
+    for gi, ge in [(12, 1), (3, 1), (10.5, 0.25), (1, 0)]:
+        ctx.set_scoring(M, gi, ge, at)
+        O = po.Oracle(M, gi, ge, at)
+        for _ in range(5):
+            q, t = rand_pair(rng, int(rng.integers(0, 70)), int(rng.integers(0, 70)), 24)
+            _check_pair(ctx, O, q, t, "at%d gi%s ge%s %dx%d" % (at, gi, ge, len(q), len(t)),
+                        mask_dr=(0.1 if at != po.LOCAL and len(q) and len(t) else None))
+
+
+@pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL, po.LOCAL, po.GLOBAL_LOCAL],
+                         ids=["global", "semi_local", "local", "global_local"])
+def test_edge_lengths(ctx, blosum, at):
+    # ragged / boundary sizes: empty, 1, lane-chunk edges (8,16), bucket edge (256/257), stripe edge (512/513)
+    _, M = blosum
+    ctx.set_scoring(M, 12, 1, at)
+    O = po.Oracle(M, 12, 1, at)
+    rng = np.random.default_rng(5)
+    for Lq, Lt in [(0, 0), (0, 5), (5, 0), (1, 1), (1, 9), (9, 1), (2, 2), (3, 8), (8, 9), (17, 16), (5, 255),
+                   (5, 256), (6, 257), (40, 300), (7, 512), (7, 513), (33, 1100), (300, 40)]:
+        q, t = rand_pair(rng, Lq, Lt)
+        _check_pair(ctx, O, q, t, "at%d %dx%d" % (at, Lq, Lt))
+
+
+def test_config1_size_250(ctx, blosum):
+    # BASELINE.json configs[0]: one pair of ~250-residue proteins, optimal + near-optimal cell set
+    import alignment_algos_b200 as a
+    alpha20, M20 = a.blosum62()
+    from alignment_algos_b200 import synth
+    seqs, pq, pt = synth.config("c1")
+    for at in (po.SEMI_LOCAL, po.GLOBAL):
+        ctx.set_scoring(M20, 12, 1, at)
+        O = po.Oracle(M20, 12, 1, at)
+        _check_pair(ctx, O, seqs[0], seqs[1], "c1 at%d" % at, mask_dr=0.01)
+
+
+def test_batch_matches_oracle_and_properties(ctx):
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha20, M20 = a.blosum62()
+    seqs, pq, pt = synth.pair_workload(77, 600, 20, 330)
+    res, off = a.Context.pack(seqs)
+    for at in (po.SEMI_LOCAL, po.GLOBAL):
+        ctx.set_scoring(M20, 12, 1, at)
+        O = po.Oracle(M20, 12, 1, at)
+        what = a.W_FWD | a.W_REV | a.W_TB | a.W_SCORES | a.W_MASK
+        out = ctx.fill_batch(res, off, pq, pt, what, 0.01)
+        # property over the whole batch: F(end) == R(0,0)
+        assert_matrix_equal("fwd==rev optimum", out["fwd_score"], out["rev_score"])
+        assert ctx.last_launch_count() >= 3
+        rng = np.random.default_rng(3)
+        for p in rng.choice(len(pq), 24, replace=False):
+            q, t = seqs[pq[p]], seqs[pt[p]]
+            F, fq, ft = O.fill(q, t, po.FWD, True, fast=True)
+            R, rq, rt = O.fill(q, t, po.REV, True, fast=True)
+            assert out["fwd_score"][p] == F[-1, -1] and out["rev_score"][p] == R[0, 0]
+            thr = O.threshold(float(F[-1, -1]), 0.01)
+            mask, cnt = O.nearopt_mask(F, R, O.sim(q, t), thr)
+            assert out["threshold"][p] == thr and out["nearopt_count"][p] == cnt
+            got = ctx.fetch_pair(int(p), len(q), len(t), fwd=True, rev=True, mask=True)
+            assert_matrix_equal("F", got["score_fwd"], F)
+            assert_matrix_equal("R", got["score_rev"], R)
+            assert_matrix_equal("fq", got["prevq_fwd"], fq)
+            assert_matrix_equal("ft", got["prevt_fwd"], ft)
+            assert_matrix_equal("rq", got["prevq_rev"], rq)
+            assert_matrix_equal("rt", got["prevt_rev"], rt)
+            assert_matrix_equal("mask", got["nearopt"], mask)
+            # optimal alignment through the packed traceback (optimal.h:47-75)
+            rc, pairs, sc = ctx.optimal(int(p), a.FWD, len(q), len(t))
+            orc, opairs, osc = O.optimal(F, fq, ft, po.FWD)
+            assert rc == orc == 0 and sc == osc
+            assert_matrix_equal("optimal fwd", pairs, opairs)
+            rc, pairs, sc = ctx.optimal(int(p), a.REV, len(q), len(t))
+            orc, opairs, osc = O.optimal(R, rq, rt, po.REV)
+            assert (rc != 0) == (orc != 0)
+            if rc == 0:
+                assert_matrix_equal("optimal rev", pairs, opairs)
+
+
+def test_score_only_batch_equals_full_batch(ctx):
+    # the score-only kernels (DPX viaddmax/vimax3 path) and the traceback kernels agree
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha20, M20 = a.blosum62()
+    seqs, pq, pt = synth.pair_workload(78, 3000, 100, 500)
+    res, off = a.Context.pack(seqs)
+    ctx.set_scoring(M20, 12, 1, po.SEMI_LOCAL)
+    s0 = ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV)
+    s1 = ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB)
+    assert_matrix_equal("fwd", s0["fwd_score"], s1["fwd_score"])
+    assert_matrix_equal("rev", s0["rev_score"], s1["rev_score"])
+    assert_matrix_equal("fwd==rev", s0["fwd_score"], s0["rev_score"])
+    O = po.Oracle(M20, 12, 1, po.SEMI_LOCAL)
+    for p in (0, 17, 2999):
+        F = O.fill(seqs[pq[p]], seqs[pt[p]], po.FWD, True, fast=True)[0]
+        assert s0["fwd_score"][p] == F[-1, -1]
+
+
+def test_errors_are_loud(ctx, blosum):
+    import alignment_algos_b200 as a
+    _, M = blosum
+    with pytest.raises(a.AadpError):
+        ctx.set_scoring(M, 4.73, 0.34, po.SEMI_LOCAL)  # not on a dyadic grid: float path is out of scope
+    ctx.set_scoring(M, 12, 1, po.GLOBAL)
+    with pytest.raises(a.AadpError):
+        ctx.fill_pair(np.array([30], np.uint8), np.array([1], np.uint8))  # code outside the alphabet

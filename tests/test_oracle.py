@@ -1,0 +1,119 @@
+"""CPU tests: pin the C restatement (oracle/aadp_oracle.c) against the real reference and the
+committed golden vectors, and check the domain properties the GPU tests rely on."""
+import numpy as np
+import pytest
+
+from util import po, HAVE_REF, MODES, golden_cases, golden_case, rand_pair, assert_matrix_equal
+
+
+def test_oracle_matches_golden(golden):
+    sub = golden["sub"]
+    for name in golden_cases(golden):
+        q, t, gi, ge, at = golden_case(golden, name)
+        O = po.Oracle(sub, gi, ge, at)
+        for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+            for fast in (False, True):
+                s, pq, pt = O.fill(q, t, d, True, fast)
+                assert_matrix_equal(name + tag + ".score", s, golden[name + "." + tag + ".score"])
+                assert_matrix_equal(name + tag + ".pq", pq, golden[name + "." + tag + ".pq"].astype(np.int32))
+                assert_matrix_equal(name + tag + ".pt", pt, golden[name + "." + tag + ".pt"].astype(np.int32))
+            rc, pairs, sc = O.optimal(s, pq, pt, d)
+            want_rc = int(golden[name + "." + tag + ".opt_rc"][0])
+            assert (rc != 0) == (want_rc != 0), name + tag
+            if rc == 0:
+                assert_matrix_equal(name + tag + ".opt", pairs, golden[name + "." + tag + ".opt_pairs"].astype(np.int32))
+                assert sc == golden[name + "." + tag + ".opt_score"][0]
+
+
+def test_revbug_case_b5(golden):
+    # global rev cell (0,0) gets traceback (5,4) where (5,1) would be right
+    name = "b5_revbug"
+    q, t, gi, ge, at = golden_case(golden, name)
+    assert golden[name + ".rev.pq"][0, 0] == 5 and golden[name + ".rev.pt"][0, 0] == 4
+    O = po.Oracle(golden["sub"], gi, ge, at)
+    _, pq, pt = O.fill(q, t, po.REV, True)
+    assert (pq[0, 0], pt[0, 0]) == (5, 4)
+    _, pq, pt = O.fill(q, t, po.REV, False)
+    assert (pq[0, 0], pt[0, 0]) == (5, 1)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_matches_reference_random(blosum):
+    alpha, M = blosum
+    rng = np.random.default_rng(7)
+    cells = 0
+    for gi, ge in [(12, 1), (3, 1), (2, 2), (10.5, 0.25), (1, 0)]:
+        for at in MODES:
+            O = po.Oracle(M, gi, ge, at)
+            R = po.Reference(alpha, M, gi, ge, at)
+            for trial in range(6):
+                Lq, Lt = int(rng.integers(0, 36)), int(rng.integers(0, 36))
+                q, t = rand_pair(rng, Lq, Lt, 24)
+                for d in (po.FWD, po.REV):
+                    rs, rq, rt, rsim = R.fill(q, t, d)
+                    for fast in (False, True):
+                        s, pq, pt = O.fill(q, t, d, True, fast)
+                        assert_matrix_equal("score", s, rs)
+                        assert_matrix_equal("pq", pq, rq)
+                        assert_matrix_equal("pt", pt, rt)
+                        cells += s.size
+                    if at == po.LOCAL and (Lq == 0 or Lt == 0):
+                        continue  # optimal.h:100 reads getCell(-1,-1) here: undefined behaviour in the reference
+                    rc, pairs, sc = O.optimal(s, pq, pt, d)
+                    rrc, rpairs, rsc = R.optimal(q, t, d)
+                    assert (rc != 0) == (rrc != 0)
+                    if rc == 0:
+                        assert_matrix_equal("optimal", pairs, rpairs)
+                        assert sc == rsc
+    assert cells > 100000
+
+
+def test_fwd_end_equals_rev_start(blosum):
+    # F[last][last] == R[0][0] for every non-local mode (both are the optimum)
+    _, M = blosum
+    rng = np.random.default_rng(11)
+    for at in MODES:
+        O = po.Oracle(M, 12, 1, at)
+        for _ in range(5):
+            q, t = rand_pair(rng, int(rng.integers(1, 60)), int(rng.integers(1, 60)))
+            F = O.fill(q, t, po.FWD, fast=True)[0]
+            R = O.fill(q, t, po.REV, fast=True)[0]
+            if at != po.LOCAL:
+                assert F[-1, -1] == R[0, 0]
+
+
+def test_ucw_union_equals_mask_golden(golden):
+    # union of cells over all UCW alignments == {F+R-sim > thr}
+    sub = golden["sub"]
+    n_checked = 0
+    for name in golden_cases(golden):
+        for dr in (5, 20):
+            key = "%s.ucw%02d" % (name, dr)
+            if key + ".union" not in golden:
+                continue
+            q, t, gi, ge, at = golden_case(golden, name)
+            O = po.Oracle(sub, gi, ge, at)
+            F = golden[name + ".fwd.score"]
+            R = golden[name + ".rev.score"]
+            sim = O.sim(q, t)
+            thr = O.threshold(float(F[-1, -1]), dr / 100.0)
+            assert thr == golden[key + ".thr"][0]
+            mask, cnt = O.nearopt_mask(F, R, sim, thr)
+            union = np.unpackbits(golden[key + ".union"])[: F.size].reshape(F.shape)
+            interior = np.zeros_like(union)
+            interior[1:-1, 1:-1] = union[1:-1, 1:-1]
+            assert_matrix_equal(key + " mask vs reference UCW union", mask, interior)
+            # the restated branching agrees with the reference enumerator on cells and count
+            mark, n = O.ucw_cells(q, t, F, sim, thr)
+            assert n == int(golden[key + ".n"][0])
+            assert_matrix_equal(key + " restated UCW", mark, union)
+            n_checked += 1
+    assert n_checked >= 8
+
+
+def test_threshold_formula():
+    O = po.Oracle(np.zeros((2, 2), np.float32), 1, 1, po.GLOBAL)
+    for opt, dr in [(100.0, 0.01), (5.0, 0.01), (-20.0, 0.2), (0.0, 0.5), (483.0, 0.2)]:
+        want = np.float32(min(np.float32(np.float32(1.0) - np.float32(dr)) * np.float32(opt),
+                              np.float32(opt) - np.float32(0.1)))
+        assert O.threshold(opt, dr) == want
