@@ -124,7 +124,7 @@ template <int K, int TBM, int STM>
 int launch_fill_t(aadp_ctx* c, FillParams& P) {
   auto kern = fill_kernel<K, TBM, STM>;
   const int A = P.sc.A;
-  const size_t smem = (size_t)((A * A + 15) / 16 * 16) + (size_t)kWarpsPerCta * A * 32 * K;
+  const size_t smem = (size_t)((A * A + 15) / 16 * 16) + (size_t)kWarpsPerCta * (kQRing + A * 32 * K);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
@@ -379,7 +379,9 @@ void aadp_destroy(aadp_ctx* c) {
 
 int aadp_set_stream(aadp_ctx* c, void* s) {
   if (!c) return fail("null context");
-  c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+  // NULL is a valid handle: the legacy default stream (what torch.cuda.current_stream() is
+  // unless the caller switched streams).  aadp_create() starts on a private non-blocking stream.
+  c->stream = reinterpret_cast<cudaStream_t>(s);
   return 0;
 }
 
@@ -474,8 +476,6 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
     return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
   if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
   c->launches = 0;
-  c->prof.clear();
-  c->ev_used = 0;
   const int64_t np = b.npairs;
   if (np == 0) { b.ran_what = what; return 0; }
   if (c->counter.reserve(64)) return 1;
@@ -566,6 +566,8 @@ int64_t aadp_last_launch_count(aadp_ctx* c) { return c ? c->launches : 0; }
 int aadp_set_profiling(aadp_ctx* c, int on) {
   if (!c) return fail("null context");
   c->profiling = on != 0;
+  c->prof.clear();  // (re)arming resets the log; runs append to it
+  c->ev_used = 0;
   return 0;
 }
 

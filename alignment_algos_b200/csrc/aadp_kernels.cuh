@@ -34,6 +34,7 @@ namespace aadp {
 constexpr int kNeg32 = -(1 << 30);    // "-infinity" for E/F seeds (int32 path)
 constexpr int kFloor32 = -(1 << 29);  // clamp floor of M (never reached by real scores)
 constexpr int kWarpsPerCta = 4;
+constexpr int kQRing = 1024;           // per-warp query staging ring (bytes)
 
 __host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 // packed-traceback row stride in bytes: one 32-bit word per 8 columns, rows padded to 16 B
@@ -95,7 +96,7 @@ __device__ __forceinline__ int sext8(uint32_t w, int c) {
 // TBM: write packed traceback.  STM: 0 = no score matrix, 1 = int16, 2 = int32.
 // ------------------------------------------------------------------------------------------------
 template <int K, int TBM, int STM>
-__device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, int8_t* prof,
+__device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, int8_t* prof, uint8_t* qring,
                                                const int8_t* s_sub, int4* bb, int lane) {
   constexpr int W = 32 * K;
   const Scoring& S = P.sc;
@@ -124,7 +125,8 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
 
   const int64_t tbs = tb_row_bytes(Lt);
   const int64_t scs = sc_row_elems(Lt);
-  uint8_t* tbp = TBM ? P.tb + P.tb_off[pair] : nullptr;
+  uint8_t* const tbp = TBM ? P.tb + P.tb_off[pair] : nullptr;
+  const int64_t sco = STM ? P.sc_off[pair] : 0;  // hoisted: a per-step global load here stalls every row
 
   const int nstripes = (Lt + W - 1) / W;
   // running row-part of the final cell: best M(Lq,k) - pen(Lt-k) over k < Lt, smallest k on ties
@@ -182,11 +184,32 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
       xl_hold = (jl == 0) ? 0 : -(S.delfree ? 0 : gap_w(gi, ge, jl));
     }
     int x_pub = 0, e_pub = kNeg32, mg_pub = kNeg32;
+    // Query residues are staged in a kQRing-byte shared-memory ring, kQRing/2 rows at a time:
+    // lanes are skewed by one row, so at step s rows s-30..s+2 are live; block b (rows
+    // b*H+1..b*H+H, H = kQRing/2) is loaded at step (b-1)*H+32, after lane 31 has left block b-2.
+    constexpr int H = kQRing / 2;
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kQRing / 32; ++u) {
+      int r = u * 32 + lane;  // 0-based flow row
+      if (r < Lq && r < kQRing) qring[r] = rev ? qseq[Lq - 1 - r] : qseq[r];
+    }
+    __syncwarp();
     int a_nxt = 0;
-    if (lane == 0) a_nxt = rev ? qseq[Lq - 1] : qseq[0];
+    if (lane == 0) a_nxt = qring[0];
 
     const int nsteps = Lq + n_act - 1;
     for (int s = 0; s < nsteps; ++s) {
+      if (s >= H + 32 && ((s - 32) & (H - 1)) == 0) {  // refill: block b = (s-32)/H + 1
+        const int r0 = ((s - 32) / H + 1) * H;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < H / 32; ++u) {
+          int r = r0 + u * 32 + lane;
+          if (r < Lq) qring[r & (kQRing - 1)] = rev ? qseq[Lq - 1 - r] : qseq[r];
+        }
+        __syncwarp();
+      }
       int xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
       int e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
       int mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
@@ -194,7 +217,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
       const int a_cur = a_nxt;
       {
         int inx = i + 1;
-        if (inx >= 1 && inx <= Lq) a_nxt = rev ? qseq[Lq - inx] : qseq[inx - 1];
+        if (inx >= 1 && inx <= Lq) a_nxt = qring[(inx - 1) & (kQRing - 1)];
       }
       if (lane == 0) {
         if (st == 0) {
@@ -266,7 +289,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
           else *reinterpret_cast<uint32_t*>(dst) = tbw[0];
         }
         if (STM == 1) {
-          int16_t* dst = reinterpret_cast<int16_t*>(P.sc_blob) + P.sc_off[pair] + (int64_t)(i - 1) * scs + st * W + lane * K;
+          int16_t* dst = reinterpret_cast<int16_t*>(P.sc_blob) + sco + (int64_t)(i - 1) * scs + st * W + lane * K;
           uint32_t pk[K / 2];
 #pragma unroll
           for (int c = 0; c < K / 2; ++c) pk[c] = __byte_perm((uint32_t)mrow[2 * c], (uint32_t)mrow[2 * c + 1], 0x5410);
@@ -274,7 +297,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
           for (int c = 0; c < K / 8; ++c)
             reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         } else if (STM == 2) {
-          int32_t* dst = reinterpret_cast<int32_t*>(P.sc_blob) + P.sc_off[pair] + (int64_t)(i - 1) * scs + st * W + lane * K;
+          int32_t* dst = reinterpret_cast<int32_t*>(P.sc_blob) + sco + (int64_t)(i - 1) * scs + st * W + lane * K;
 #pragma unroll
           for (int c = 0; c < K / 4; ++c)
             reinterpret_cast<int4*>(dst)[c] = make_int4(mrow[4 * c], mrow[4 * c + 1], mrow[4 * c + 2], mrow[4 * c + 3]);
@@ -329,7 +352,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParam
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);
   const int sub_bytes = (A * A + 15) / 16 * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + warp * A * W);
+  uint8_t* qring = smem + sub_bytes + warp * kQRing;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kWarpsPerCta * kQRing + warp * A * W);
   for (int x = threadIdx.x; x < A * A; x += blockDim.x) s_sub[x] = P.sub8[x];
   __syncthreads();
   const int slot = blockIdx.x * kWarpsPerCta + warp;
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParam
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_items) break;
-    fill_pair_warp<K, TBM, STM>(P, P.order[item], prof, s_sub, bb, lane);
+    fill_pair_warp<K, TBM, STM>(P, P.order[item], prof, qring, s_sub, bb, lane);
   }
 }
 

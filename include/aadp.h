@@ -56,7 +56,8 @@ void aadp_destroy(aadp_ctx* ctx);
 const char* aadp_last_error(void);
 const char* aadp_version(void);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's
- * current stream, so that the caller's events bracket the kernels. NULL = the context's own.  */
+ * current stream, so that the caller's events bracket the kernels. NULL is the legacy default
+ * stream; until this is called the context uses a private non-blocking stream.               */
 int aadp_set_stream(aadp_ctx* ctx, void* cuda_stream);
 int aadp_synchronize(aadp_ctx* ctx);
 
@@ -106,8 +107,9 @@ int64_t aadp_last_launch_count(aadp_ctx* ctx);
 double aadp_last_cell_updates(aadp_ctx* ctx);
 
 /* Per-launch device timing (CUDA events on the context stream around every kernel of the batch
- * calls). Off by default. aadp_profile_get returns the idx-th launch of the last run: kernel
- * name, milliseconds and the cell updates that launch processed (0 for helper kernels).       */
+ * calls). Off by default; aadp_set_profiling(ctx,1) clears the log and every following run appends
+ * to it. aadp_profile_get returns the idx-th logged launch: kernel name, milliseconds and the
+ * cell updates that launch processed (0 for helper kernels).                                  */
 int aadp_set_profiling(aadp_ctx* ctx, int on);
 int aadp_profile_count(aadp_ctx* ctx);
 int aadp_profile_get(aadp_ctx* ctx, int idx, char* name, int name_cap, float* ms, double* cells);
