@@ -54,6 +54,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.aadp_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, key, value):
+        self._ck(self.L.aadp_set_option(self.h, key.encode(), int(value)))
+
     def synchronize(self):
         self._ck(self.L.aadp_synchronize(self.h))
 
@@ -169,7 +172,7 @@ class Context:
     def fetch_tb(self, p, direction, Lq, Lt):
         nbytes = max(int(Lq * self.L.aadp_tb_row_bytes(Lt)), 1)
         tb = np.zeros(nbytes, np.uint8)
-        fin = np.zeros(4, np.int32)
+        fin = np.zeros(5, np.int32)
         self._ck(self.L.aadp_batch_fetch_tb(self.h, p, direction, _ptr(tb), nbytes, _ptr(fin)))
         return tb, fin
 

@@ -3,6 +3,7 @@
 // fails with an error message when no CUDA device / kernel image is available.
 #include "../../include/aadp.h"
 #include "aadp_kernels.cuh"
+#include "aadp_packed.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -72,6 +73,13 @@ struct Batch {
   double bucket_cells[2] = {0, 0};
   int max_Lq = 0, max_Lt = 0;
   int st_mode = 1;  // 1 = int16 score storage possible, 2 = int32
+  // packed (int16x2) path
+  std::vector<uint8_t> fmt;       // per pair: 1 = packed kernels, 0 = int32 kernels
+  std::vector<int32_t> tasks;     // n_tasks * 64 pair ids
+  std::vector<int32_t> aoff;      // per sequence byte offset into the aligned arenas
+  std::vector<uint8_t> arena_f, arena_r;
+  double packed_cells = 0;
+  int64_t n_tasks = 0;
   double cells = 0;
   uint32_t uploaded_what = 0;
   uint32_t ran_what = 0;
@@ -93,6 +101,8 @@ struct aadp_ctx {
   DevBuf sub8, residues, seq_off, pair_q, pair_t, order[2], tb_off, sc_off, mask_off;
   DevBuf tb[2], scb[2], mask, fin_score[2], fin_kind[2], fin_k[2], counter, bbuf, thr, count, fscore[2];
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
+  DevBuf fmt, tasks, aoff, arena_f, arena_r;
+  bool allow_packed = true;
   Batch b;
   int64_t launches = 0;
   int bb_rows = 0;
@@ -162,6 +172,43 @@ int launch_fill_k(aadp_ctx* c, FillParams& P, int tbm, int stm) {
   return launch_fill_t<K, 1, 2>(c, P);
 }
 
+template <int TBM, int FST, int MSK>
+int launch_packed_t(aadp_ctx* c, PackedParams& P) {
+  auto kern = packed_kernel<TBM, FST, MSK>;
+  const int A = P.sc.A;
+  const size_t smem = (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + 2 * A * 512);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
+  if (occ < 1) return fail("packed kernel does not fit on an SM");
+  int grid = c->num_sms * occ;
+  const int need = (P.n_tasks + kPackedWarps - 1) / kPackedWarps;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  char nm[64];
+  snprintf(nm, sizeof nm, "packed_kernel<TB=%d,FST=%d,MSK=%d>%s", TBM, FST, MSK, P.rev ? "rev" : "fwd");
+  c->prof_begin(nm, P.cells_hint);
+  kern<<<grid, kPackedWarps * 32, smem, c->stream>>>(P);
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int launch_packed(aadp_ctx* c, PackedParams& P, int tbm, int fst, int msk) {
+  const int key = tbm * 4 + fst * 2 + msk;
+  switch (key) {
+    case 0: return launch_packed_t<0, 0, 0>(c, P);
+    case 1: return launch_packed_t<0, 0, 1>(c, P);
+    case 2: return launch_packed_t<0, 1, 0>(c, P);
+    case 3: return launch_packed_t<0, 1, 1>(c, P);
+    case 4: return launch_packed_t<1, 0, 0>(c, P);
+    case 5: return launch_packed_t<1, 0, 1>(c, P);
+    case 6: return launch_packed_t<1, 1, 0>(c, P);
+    default: return launch_packed_t<1, 1, 1>(c, P);
+  }
+}
+
 __global__ void scores_to_float_kernel(const int32_t* fin, float* out, int64_t n, int scale_log2) {
   const float inv = 1.f / (float)(1 << scale_log2);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -176,6 +223,90 @@ int check_ctx(aadp_ctx* c, bool need_scoring) {
   return 0;
 }
 
+// Couple pairs of equal lane width and similar query length (they share a segment, one per register
+// half), then bin-pack the couples into 32-lane tasks of similar duration.
+void build_tasks(aadp_ctx* c) {
+  Batch& b = c->b;
+  b.tasks.clear();
+  b.n_tasks = 0;
+  struct Item { int32_t p; int n; int Lq; };
+  std::vector<Item> items;
+  for (int64_t p = 0; p < b.npairs; ++p) {
+    if (!b.fmt[p]) continue;
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+    items.push_back({(int32_t)p, (Lt + 15) / 16, Lq});
+  }
+  if (items.empty()) return;
+  std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+    if (x.n != y.n) return x.n > y.n;
+    if (x.Lq != y.Lq) return x.Lq > y.Lq;
+    return x.p < y.p;
+  });
+  struct Couple { int32_t a, b; int n; int Lq; };
+  std::vector<Couple> couples;
+  for (size_t i = 0; i < items.size();) {
+    if (i + 1 < items.size() && items[i + 1].n == items[i].n) {
+      couples.push_back({items[i].p, items[i + 1].p, items[i].n, items[i].Lq});  // a has the longer query
+      i += 2;
+    } else {
+      couples.push_back({items[i].p, -1, items[i].n, items[i].Lq});
+      i += 1;
+    }
+  }
+  std::stable_sort(couples.begin(), couples.end(), [](const Couple& x, const Couple& y) { return x.Lq > y.Lq; });
+  struct Open { int64_t task; int used; };
+  std::vector<Open> open;
+  auto new_task = [&]() {
+    b.tasks.resize(b.tasks.size() + 64, -1);
+    return b.n_tasks++;
+  };
+  for (const Couple& cp : couples) {
+    int best = -1;
+    for (size_t k = 0; k < open.size(); ++k)
+      if (32 - open[k].used >= cp.n && (best < 0 || open[k].used > open[best].used)) best = (int)k;
+    if (best < 0) {
+      if (open.size() >= 48) open.erase(open.begin());  // oldest open task: its query lengths are the least similar
+      open.push_back({new_task(), 0});
+      best = (int)open.size() - 1;
+    }
+    Open& o = open[best];
+    for (int l = 0; l < cp.n; ++l) {
+      b.tasks[o.task * 64 + o.used + l] = cp.a;
+      b.tasks[o.task * 64 + 32 + o.used + l] = cp.b;
+    }
+    o.used += cp.n;
+    if (o.used == 32) open.erase(open.begin() + best);
+  }
+}
+
+// 4-byte aligned copies of the sequences: forward order and reversed (the reverse fill reads its
+// flow order front to back). Zero padding behind the last sequence absorbs read-ahead.
+void build_arenas(aadp_ctx* c, const uint8_t* residues) {
+  Batch& b = c->b;
+  b.aoff.assign(b.nseq + 1, 0);
+  int64_t cur = 0, maxL = 0;
+  for (int64_t s = 0; s < b.nseq; ++s) {
+    b.aoff[s] = (int32_t)cur;
+    const int64_t L = b.seq_off[s + 1] - b.seq_off[s];
+    maxL = std::max(maxL, L);
+    cur += (L + 3) / 4 * 4;
+  }
+  const int64_t total = cur + maxL + 64;
+  b.arena_f.assign((size_t)total, 0);
+  b.arena_r.assign((size_t)total, 0);
+  for (int64_t s = 0; s < b.nseq; ++s) {
+    const int64_t L = b.seq_off[s + 1] - b.seq_off[s];
+    const uint8_t* src = residues + b.seq_off[s];
+    uint8_t* df = b.arena_f.data() + b.aoff[s];
+    uint8_t* dr = b.arena_r.data() + b.aoff[s];
+    for (int64_t i = 0; i < L; ++i) {
+      df[i] = src[i];
+      dr[i] = src[L - 1 - i];
+    }
+  }
+}
+
 int build_batch_meta(aadp_ctx* c, uint32_t what) {
   Batch& b = c->b;
   const int64_t np = b.npairs;
@@ -187,6 +318,8 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   b.max_Lq = b.max_Lt = 0;
   b.cells = 0;
   b.bucket_cells[0] = b.bucket_cells[1] = 0;
+  b.fmt.assign(np, 0);
+  b.packed_cells = 0;
   std::vector<int64_t> cells(np);
   int64_t bound = 0;
   for (int64_t p = 0; p < np; ++p) {
@@ -197,18 +330,31 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
     b.max_Lq = std::max<int>(b.max_Lq, (int)Lq);
     b.max_Lt = std::max<int>(b.max_Lt, (int)Lt);
     b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? Lq * tb_row_bytes((int)Lt) : 0);
-    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? Lq * sc_row_elems((int)Lt) : 0);
     b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? Lq * mask_row_words((int)Lt) : 0);
     cells[p] = Lq * Lt;
     b.cells += (double)cells[p];
-    b.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
-    b.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cells[p];
     // |score| bound in integer units: matches + one end gap on each side
     const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
-    bound = std::max(bound, bd);
+    const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
+                           c->sc.ge <= 512 && c->sc.gi <= 2048;
+    b.fmt[p] = packed_ok ? 1 : 0;
+    if (packed_ok) {
+      b.packed_cells += (double)cells[p];
+    } else {
+      b.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
+      b.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cells[p];
+      bound = std::max(bound, bd);
+    }
   }
+  build_tasks(c);
   b.st_mode = bound < 30000 ? 1 : 2;
   if (bound >= (1 << 24)) return fail("scores exceed the exactly-representable float range (2^24 units)");
+  for (int64_t p = 0; p < np; ++p) {  // score offsets in int16 units
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
+    const int64_t units = (b.fmt[p] || b.st_mode == 1) ? 1 : 2;
+    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? Lq * sc_row_elems((int)Lt) * units : 0);
+  }
   for (int k = 0; k < 2; ++k)
     std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
   return 0;
@@ -221,17 +367,53 @@ int upload_vec(DevBuf& d, const std::vector<T>& v, cudaStream_t s) {
   return 0;
 }
 
-int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what) {
+int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float delta_ratio, float* d_threshold,
+                  int64_t* d_count) {
   Batch& b = c->b;
   const int tbm = (what & AADP_W_TB) ? 1 : 0;
   const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
   const int64_t np = b.npairs;
+  const bool have_v1 = !b.order[0].empty() || !b.order[1].empty();
+  // the packed reverse pass fuses the mask and needs no reverse score matrix of its own
+  const bool need_blob = (what & AADP_W_SCORES) || ((what & AADP_W_MASK) && (dir == 0 || have_v1));
   if (c->fin_score[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
   if (c->fin_kind[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
   if (c->fin_k[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
   if (tbm && c->tb[dir].reserve(std::max<size_t>((size_t)b.tb_off[np], 16))) return 1;
-  if (stm && c->scb[dir].reserve(std::max<size_t>((size_t)b.sc_off[np] * (stm == 1 ? 2 : 4), 16))) return 1;
+  if (need_blob && c->scb[dir].reserve(std::max<size_t>((size_t)b.sc_off[np] * 2, 16))) return 1;
   if (c->counter.reserve(64)) return 1;
+  if (b.n_tasks) {
+    PackedParams Q{};
+    Q.sc = c->sc;
+    Q.sub8 = c->sub8.as<int8_t>();
+    Q.arena = dir ? c->arena_r.as<uint8_t>() : c->arena_f.as<uint8_t>();
+    Q.aoff = c->aoff.as<int32_t>();
+    Q.seq_off = c->seq_off.as<int64_t>();
+    Q.pair_q = c->pair_q.as<int32_t>();
+    Q.pair_t = c->pair_t.as<int32_t>();
+    Q.tasks = c->tasks.as<int32_t>();
+    Q.n_tasks = (int)b.n_tasks;
+    Q.rev = dir;
+    Q.counter = c->counter.as<unsigned int>() + (4 + dir);
+    Q.tb = tbm ? c->tb[dir].as<uint8_t>() : nullptr;
+    Q.tb_off = c->tb_off.as<int64_t>();
+    const int msk = (dir == 1 && (what & AADP_W_MASK)) ? 1 : 0;
+    const int fst = (dir == 0) ? ((what & (AADP_W_SCORES | AADP_W_MASK)) ? 1 : 0) : ((what & AADP_W_SCORES) ? 1 : 0);
+    Q.sc_out = fst ? c->scb[dir].as<int16_t>() : nullptr;
+    Q.scF = msk ? c->scb[0].as<int16_t>() : nullptr;
+    Q.sc_off = c->sc_off.as<int64_t>();
+    Q.mask = msk ? c->mask.as<uint32_t>() : nullptr;
+    Q.mask_off = c->mask_off.as<int64_t>();
+    Q.fin_fwd = c->fin_score[0].as<int32_t>();
+    Q.delta_ratio = delta_ratio;
+    Q.threshold = msk ? d_threshold : nullptr;
+    Q.count = msk ? reinterpret_cast<long long*>(d_count) : nullptr;
+    Q.fin_score = c->fin_score[dir].as<int32_t>();
+    Q.fin_kind = c->fin_kind[dir].as<int32_t>();
+    Q.fin_k = c->fin_k[dir].as<int32_t>();
+    Q.cells_hint = b.packed_cells;
+    if (launch_packed(c, Q, tbm, fst, msk)) return 1;
+  }
   for (int k = 0; k < 2; ++k) {
     if (b.order[k].empty()) continue;
     FillParams P{};
@@ -283,8 +465,12 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   D.Lt = Lt;
   D.rev = dir;
   D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
-  D.st_mode = have_sc ? b.st_mode : 0;
+  const bool packed = b.fmt[p] != 0;
+  D.sig = (packed && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;
+  D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
   D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
+  if (h_score && packed && dir == 1 && !(b.ran_what & AADP_W_SCORES))
+    return fail("reverse score matrices were not kept (run with AADP_W_SCORES)");
   D.sc_off = b.sc_off[p];
   D.tb = have_tb ? c->tb[dir].as<uint8_t>() + b.tb_off[p] : nullptr;
   D.fin_score = fin[0];
@@ -322,9 +508,22 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
     CK(cudaStreamSynchronize(c->stream));
   }
   memset(h_mask, 0, (size_t)(Lq + 2) * sz2);
-  for (int i = 1; i <= Lq; ++i)
-    for (int j = 1; j <= Lt; ++j)
-      h_mask[(size_t)i * sz2 + j] = (bits[(size_t)(i - 1) * mws + ((j - 1) >> 5)] >> ((j - 1) & 31)) & 1u;
+  if (!b.fmt[p]) {
+    for (int i = 1; i <= Lq; ++i)
+      for (int j = 1; j <= Lt; ++j)
+        h_mask[(size_t)i * sz2 + j] = (bits[(size_t)(i - 1) * mws + ((j - 1) >> 5)] >> ((j - 1) & 31)) & 1u;
+  } else {
+    // packed reverse pass: reverse-flow coordinates, 2 bytes per 16-column lane slot,
+    // byte (c&1), bit 7-(c>>1)
+    const uint8_t* by = reinterpret_cast<const uint8_t*>(bits.data());
+    for (int i = 1; i <= Lq; ++i)
+      for (int j = 1; j <= Lt; ++j) {
+        const int a = Lq + 1 - i, bb = Lt + 1 - j;
+        const int slot = (bb - 1) >> 4, cc = (bb - 1) & 15;
+        const uint8_t v = by[(size_t)(a - 1) * mws * 4 + slot * 2 + (cc & 1)];
+        h_mask[(size_t)i * sz2 + j] = (v >> (7 - (cc >> 1))) & 1u;
+      }
+  }
   return 0;
 }
 
@@ -370,7 +569,8 @@ void aadp_destroy(aadp_ctx* c) {
   DevBuf* all[] = {&c->sub8, &c->residues, &c->seq_off, &c->pair_q, &c->pair_t, &c->order[0], &c->order[1], &c->tb_off,
                    &c->sc_off, &c->mask_off, &c->tb[0], &c->tb[1], &c->scb[0], &c->scb[1], &c->mask, &c->fin_score[0],
                    &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
-                   &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d};
+                   &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d,
+                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r};
   for (DevBuf* d : all) d->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -383,6 +583,12 @@ int aadp_set_stream(aadp_ctx* c, void* s) {
   // unless the caller switched streams).  aadp_create() starts on a private non-blocking stream.
   c->stream = reinterpret_cast<cudaStream_t>(s);
   return 0;
+}
+
+int aadp_set_option(aadp_ctx* c, const char* key, int value) {
+  if (!c || !key) return fail("null argument");
+  if (!strcmp(key, "packed")) { c->allow_packed = value != 0; return 0; }
+  return fail(std::string("unknown option ") + key);
 }
 
 int aadp_synchronize(aadp_ctx* c) {
@@ -452,6 +658,17 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   if (build_batch_meta(c, what)) return 1;
   b.uploaded_what = what;
   b.ran_what = 0;
+  if (b.n_tasks) {
+    int64_t tot = 0;
+    for (int64_t s2 = 0; s2 < nseq; ++s2) tot += (seq_off[s2 + 1] - seq_off[s2] + 3) / 4 * 4;
+    if (tot > 0x7fff0000LL) return fail("sequence arena too large for the packed path");
+    build_arenas(c, residues);
+    if (upload_vec(c->arena_f, b.arena_f, c->stream)) return 1;
+    if (upload_vec(c->arena_r, b.arena_r, c->stream)) return 1;
+    if (upload_vec(c->aoff, b.aoff, c->stream)) return 1;
+    if (upload_vec(c->tasks, b.tasks, c->stream)) return 1;
+  }
+  if (upload_vec(c->fmt, b.fmt, c->stream)) return 1;
   if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
   if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
   if (upload_vec(c->seq_off, b.seq_off, c->stream)) return 1;
@@ -482,8 +699,9 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
   CK(cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
   const int threads = 256;
   const int g1 = (int)std::min<int64_t>((np + threads - 1) / threads, 148 * 8);
+  if ((what & AADP_W_MASK) && c->mask.reserve(std::max<size_t>((size_t)b.mask_off[np] * 4, 16))) return 1;
   if (what & AADP_W_FWD) {
-    if (run_direction(c, 0, what)) return 1;
+    if (run_direction(c, 0, what, delta_ratio, d_threshold, d_nearopt_count)) return 1;
     if (d_fwd_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[0].as<int32_t>(), d_fwd_score, np, c->sc.scale_log2);
       CK(cudaGetLastError());
@@ -491,16 +709,16 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
     }
   }
   if (what & AADP_W_REV) {
-    if (run_direction(c, 1, what)) return 1;
+    if (run_direction(c, 1, what, delta_ratio, d_threshold, d_nearopt_count)) return 1;
     if (d_rev_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[1].as<int32_t>(), d_rev_score, np, c->sc.scale_log2);
       CK(cudaGetLastError());
       c->launches++;
     }
   }
-  if (what & AADP_W_MASK) {
-    if (c->mask.reserve(std::max<size_t>((size_t)b.mask_off[np] * 4, 16))) return 1;
+  if ((what & AADP_W_MASK) && (!b.order[0].empty() || !b.order[1].empty())) {
     MaskParams M{};
+    M.fmt = c->fmt.as<uint8_t>();
     M.sc = c->sc;
     M.sub8 = c->sub8.as<int8_t>();
     M.residues = c->residues.as<uint8_t>();
@@ -556,7 +774,7 @@ int64_t aadp_batch_resident_bytes(aadp_ctx* c, uint32_t which) {
   if (b.tb_off.empty()) return 0;
   const int ndir = ((b.ran_what & AADP_W_FWD) ? 1 : 0) + ((b.ran_what & AADP_W_REV) ? 1 : 0);
   if (which == AADP_W_TB) return (b.ran_what & AADP_W_TB) ? b.tb_off[b.npairs] * ndir : 0;
-  if (which == AADP_W_SCORES) return (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) ? b.sc_off[b.npairs] * (b.st_mode == 1 ? 2 : 4) * ndir : 0;
+  if (which == AADP_W_SCORES) return (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) ? b.sc_off[b.npairs] * 2 * ndir : 0;
   if (which == AADP_W_MASK) return (b.ran_what & AADP_W_MASK) ? b.mask_off[b.npairs] * 4 : 0;
   return 0;
 }
@@ -659,6 +877,11 @@ int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int6
     CK(cudaMemcpyAsync(&final_rec[1], c->fin_kind[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&final_rec[2], c->fin_k[dir].as<int32_t>() + p, 4, cudaMemcpyDeviceToHost, c->stream));
     final_rec[3] = c->sc.scale_log2;
+    {
+      const int ts = b.pair_t[p];
+      const int Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+      final_rec[4] = (b.fmt[p] && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;  // leading pad columns of the layout
+    }
   }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -671,10 +894,11 @@ int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align
   const int a = rev ? Lq + 1 - i : i, b = rev ? Lt + 1 - j : j;
   int pa = -1, pb = -1;
   bool is_final = false;
-  if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) decode_prev(tb, Lt, a, b, &pa, &pb);
+  const int sig = final_rec ? final_rec[4] : 0;
+  if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) decode_prev(tb, Lt, sig, a, b, &pa, &pb);
   else if (a == Lq + 1 && b == Lt + 1) {
     if (!final_rec) return fail("final_rec needed for the final cell");
-    decode_final(tb, Lq, Lt, final_rec[1], final_rec[2], &pa, &pb);
+    decode_final(tb, Lq, Lt, sig, final_rec[1], final_rec[2], &pa, &pb);
     is_final = true;
   }
   if (pa < 0) { *prev_q = -1; *prev_t = -1; return 0; }
@@ -694,7 +918,7 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
   const int qs = b.pair_q[p], ts = b.pair_t[p];
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
   std::vector<uint8_t> tb((size_t)std::max<int64_t>(b.tb_off[p + 1] - b.tb_off[p], 1));
-  int32_t fin[4];
+  int32_t fin[5];
   if (aadp_batch_fetch_tb(c, p, direction, tb.data(), (int64_t)tb.size(), fin)) return 1;
   if (score) *score = (float)fin[0] / (float)(1 << fin[3]);
   // optimal.h:57-74 / optimal_rev.h:57-76: follow prev_* from the final cell to the anchor

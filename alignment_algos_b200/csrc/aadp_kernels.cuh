@@ -65,7 +65,7 @@ struct FillParams {
   uint8_t* tb;               // packed traceback blob of this direction (or null)
   const int64_t* tb_off;     // per pair byte offset
   void* sc_blob;             // score blob of this direction (int16 or int32 elements)
-  const int64_t* sc_off;     // per pair element offset
+  const int64_t* sc_off;     // per pair offset in int16 units (int32 pairs use two units per element)
   int32_t* fin_score;        // per pair: final-cell score (integer units)
   int32_t* fin_kind;         // 0 = diagonal, 1 = row (deletion), 2 = column (insertion)
   int32_t* fin_k;            // kind 1: flow column k of the predecessor; kind 2: -1 (resolved by decode)
@@ -297,7 +297,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
           for (int c = 0; c < K / 8; ++c)
             reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         } else if (STM == 2) {
-          int32_t* dst = reinterpret_cast<int32_t*>(P.sc_blob) + sco + (int64_t)(i - 1) * scs + st * W + lane * K;
+          int32_t* dst = reinterpret_cast<int32_t*>(reinterpret_cast<int16_t*>(P.sc_blob) + sco) + (int64_t)(i - 1) * scs + st * W + lane * K;
 #pragma unroll
           for (int c = 0; c < K / 4; ++c)
             reinterpret_cast<int4*>(dst)[c] = make_int4(mrow[4 * c], mrow[4 * c + 1], mrow[4 * c + 2], mrow[4 * c + 3]);
@@ -372,22 +372,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParam
 // tb: packed traceback of one pair in FLOW coordinates. Returns the flow predecessor of flow
 // cell (a,b), 1 <= a <= Lq, 1 <= b <= Lt.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline int tb_plane(const uint8_t* tb, int64_t tbs, int a, int b, int plane) {
-  const uint8_t byte = tb[(int64_t)(a - 1) * tbs + 4 * ((b - 1) >> 3) + plane];
-  return (byte >> (7 - ((b - 1) & 7))) & 1;
+// `sig` = number of leading pad columns of the stored layout (0 for the int32 kernels and for the
+// packed reverse pass, 16*ceil(Lt/16)-Lt for the right-aligned packed forward pass).
+__host__ __device__ inline int tb_plane(const uint8_t* tb, int64_t tbs, int sig, int a, int b, int plane) {
+  const int pos = b - 1 + sig;
+  const uint8_t byte = tb[(int64_t)(a - 1) * tbs + 4 * (pos >> 3) + plane];
+  return (byte >> (7 - (pos & 7))) & 1;
 }
 
-__host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int a, int b, int* pa, int* pb) {
+__host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int sig, int a, int b, int* pa, int* pb) {
   if (a == 1 || b == 1) { *pa = 0; *pb = 0; return; }  // dpmatrix.h:408-426: boundary cells point at the anchor
   const int64_t tbs = tb_row_bytes(Lt);
   const int r = a - 1, c = b - 1;
-  if (tb_plane(tb, tbs, r, c, 1)) {  // F won: walk up column c while the gap was extended
+  if (tb_plane(tb, tbs, sig, r, c, 1)) {  // F won: walk up column c while the gap was extended
     int rr = r;
-    while (rr > 1 && !tb_plane(tb, tbs, rr, c, 3)) --rr;
+    while (rr > 1 && !tb_plane(tb, tbs, sig, rr, c, 3)) --rr;
     *pa = rr - 1; *pb = c;
-  } else if (tb_plane(tb, tbs, r, c, 0)) {  // E won: walk left along row r
+  } else if (tb_plane(tb, tbs, sig, r, c, 0)) {  // E won: walk left along row r
     int cc = c;
-    while (cc > 1 && !tb_plane(tb, tbs, r, cc, 2)) --cc;
+    while (cc > 1 && !tb_plane(tb, tbs, sig, r, cc, 2)) --cc;
     *pa = r; *pb = cc - 1;
   } else {
     *pa = r; *pb = c;
@@ -395,14 +398,14 @@ __host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int a, in
 }
 
 // Predecessor of the final flow cell (Lq+1, Lt+1) from the per-pair record.
-__host__ __device__ inline void decode_final(const uint8_t* tb, int Lq, int Lt, int kind, int k, int* pa, int* pb) {
+__host__ __device__ inline void decode_final(const uint8_t* tb, int Lq, int Lt, int sig, int kind, int k, int* pa, int* pb) {
   if (Lq == 0 || Lt == 0) { *pa = 0; *pb = 0; return; }
   if (kind == 0) { *pa = Lq; *pb = Lt; }
   else if (kind == 1) { *pa = Lq; *pb = k; }
   else {
     const int64_t tbs = tb_row_bytes(Lt);
     int rr = Lq;
-    while (rr > 1 && !tb_plane(tb, tbs, rr, Lt, 3)) --rr;
+    while (rr > 1 && !tb_plane(tb, tbs, sig, rr, Lt, 3)) --rr;
     *pa = rr - 1; *pb = Lt;
   }
 }
@@ -428,6 +431,7 @@ struct MaskParams {
   const int64_t* mask_off;   // per pair word offset
   float* threshold;          // per pair (may be null)
   long long* count;          // per pair (may be null)
+  const uint8_t* fmt;        // per pair: 1 = handled by the packed kernels (skipped here)
 };
 
 __host__ __device__ inline int64_t mask_row_words(int Lt) { return (Lt + 31) / 32; }
@@ -440,6 +444,7 @@ __device__ __forceinline__ float nearopt_threshold(float opt, float delta_ratio)
 
 __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
   const int pair = blockIdx.x;
+  if (P.fmt[pair]) return;
   const int qs = P.pair_q[pair], ts = P.pair_t[pair];
   const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
   const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
@@ -461,10 +466,10 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
       bool on = false;
       if (j <= Lt) {
         int f, r;
-        const int64_t fo = so + (int64_t)(i - 1) * scs + (j - 1);
-        const int64_t ro = so + (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
-        if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[fo]; r = ((const int16_t*)P.scR)[ro]; }
-        else { f = ((const int32_t*)P.scF)[fo]; r = ((const int32_t*)P.scR)[ro]; }
+        const int64_t fo = (int64_t)(i - 1) * scs + (j - 1);
+        const int64_t ro = (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
+        if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[so + fo]; r = ((const int16_t*)P.scR)[so + ro]; }
+        else { f = ((const int32_t*)((const int16_t*)P.scF + so))[fo]; r = ((const int32_t*)((const int16_t*)P.scR + so))[ro]; }
         const int sm = P.sub8[qa * A + P.residues[to + j - 1]];
         float v = __fadd_rn((float)f * inv, (float)r * inv);
         v = __fsub_rn(v, (float)sm * inv);
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
 struct DenseParams {
   Scoring sc;
   int Lq, Lt, rev, repro_rev_bug;
+  int sig;  // leading pad columns of the stored layout
   int st_mode;
   const void* sc_blob; int64_t sc_off;
   const uint8_t* tb;  // packed traceback of this pair/direction (or null)
@@ -513,18 +519,18 @@ __global__ void dense_kernel(const DenseParams P) {
     const bool interior = a >= 1 && a <= P.Lq && b >= 1 && b <= P.Lt;
     int si = 0;
     if (interior) {
-      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1)];
-      else if (P.st_mode == 2) si = ((const int32_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1)];
+      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1 + P.sig)];
+      else if (P.st_mode == 2) si = ((const int32_t*)((const int16_t*)P.sc_blob + P.sc_off))[(int64_t)(a - 1) * scs + (b - 1 + P.sig)];
       s = (float)si * inv;
       if (P.tb) {
-        decode_prev(P.tb, P.Lt, a, b, &pa, &pb);
+        decode_prev(P.tb, P.Lt, P.sig, a, b, &pa, &pb);
         // local fills: a cell clamped to 0 keeps the match predecessor (dpmatrix.h:616-646)
         if (P.sc.local && si == 0 && a > 1 && b > 1) { pa = a - 1; pb = b - 1; }
       }
     } else if (a == P.Lq + 1 && b == P.Lt + 1) {
       s = (float)P.fin_score * inv;
       if (P.Lq == 0 || P.Lt == 0) { pa = 0; pb = 0; }
-      else if (P.tb) decode_final(P.tb, P.Lq, P.Lt, P.fin_kind, P.fin_k, &pa, &pb);
+      else if (P.tb) decode_final(P.tb, P.Lq, P.Lt, P.sig, P.fin_kind, P.fin_k, &pa, &pb);
       else if (P.fin_kind == 0) { pa = P.Lq; pb = P.Lt; }
       else if (P.fin_kind == 1) { pa = P.Lq; pb = P.fin_k; }
     }

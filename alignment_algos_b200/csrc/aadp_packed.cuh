@@ -1,0 +1,484 @@
+// aadp_packed.cuh -- the fast path: packed int16x2 ("two pairs per register") segmented systolic
+// fill kernel for sm_100a, built on the DPX instructions VIADDMNMX.S16x2 / VIMNMX.S16x2 /
+// VIADD.16x2 and on PRMT sign-replication for the traceback bit gather.
+//
+// Same recurrence and tie rules as aadp_kernels.cuh (dpmatrix.h:356-1030).
+// What changes is the mapping:
+//   * every 32-bit register holds the same DP quantity of TWO independent pairs (a "couple":
+//     pair A in the low half, pair B in the high half), so one instruction updates two cells;
+//   * a warp is split into contiguous lane SEGMENTS; a segment of n = ceil(Lt/16) lanes owns one
+//     couple, lane `off` of a segment owns 16 consecutive template columns and runs `off` rows
+//     behind lane 0 (skewed systolic array).  Short templates therefore use few lanes and several
+//     couples share a warp ("task"); the host bin-packs couples of similar query length into tasks;
+//   * the forward pass is RIGHT-aligned (the last template column is always register 15 of the
+//     segment's last lane, pad columns come first and reproduce the boundary column through the F
+//     recurrence), the reverse pass is LEFT-aligned in its own flow.  Both therefore cut the
+//     template into the SAME 16-column chunks, so the reverse pass reads the forward scores with
+//     aligned 16-byte loads and emits the near-optimal cell set F+R-sim > thr (ucw.h:141-180,
+//     cw.h:86-88) on the fly -- the forward+reverse fusion of BASELINE.json's north_star.
+//
+// Layouts (shared with the int32 kernels; `sig` = number of leading pad columns of the direction):
+//   traceback  row a-1, 8-byte lane slots, two 32-bit words per slot (8 columns each), byte p =
+//              plane p, bit 7-(c&7) = register c; register c of slot k is flow column 16k+c+1-sig
+//   scores     int16, row stride 16n, element index (flow column - 1 + sig)
+//   mask       reverse-flow coordinates, 2 bytes per lane slot: byte (c&1), bit 7-(c>>1)
+#pragma once
+#include "aadp_kernels.cuh"
+
+namespace aadp {
+
+constexpr int kNeg16 = -24000;    // "-infinity" seed of E/F chains (only ever meets boundary-sized values)
+constexpr int kFloor16 = -16000;  // clamp floor of M / slack
+constexpr int kPackedBound = 8000;  // |score| bound (integer units) a pair must satisfy to use this kernel
+constexpr int kPackedWarps = 2;   // warps per CTA
+
+struct PackedParams {
+  Scoring sc;
+  const int8_t* sub8;        // A*A scaled substitution scores
+  const uint8_t* arena;      // 4-byte aligned sequence arena in the FLOW order of this direction
+  const int32_t* aoff;       // per sequence: byte offset into arena
+  const int64_t* seq_off;    // nseq+1 (lengths)
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  const int32_t* tasks;      // n_tasks * 64: pair id (or -1) of lane l, half h at [task*64 + h*32 + l]
+  int n_tasks;
+  int rev;
+  unsigned int* counter;
+  uint8_t* tb;               // packed traceback blob of this direction
+  const int64_t* tb_off;
+  int16_t* sc_out;           // score blob of this direction (written when FST)
+  const int16_t* scF;        // forward score blob (read when MSK)
+  const int64_t* sc_off;
+  uint32_t* mask;            // near-optimal bit blob (written when MSK)
+  const int64_t* mask_off;
+  const int32_t* fin_fwd;    // forward final scores, integer units (MSK)
+  float delta_ratio;
+  float* threshold;          // per pair, may be null (MSK)
+  long long* count;          // per pair, may be null (MSK)
+  int32_t* fin_score;
+  int32_t* fin_kind;
+  int32_t* fin_k;
+  double cells_hint;
+};
+
+__device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
+__device__ __forceinline__ int half16(uint32_t v, int h) { return h ? hi16(v) : lo16(v); }
+// acc | (t & pat)
+__device__ __forceinline__ uint32_t or_and(uint32_t acc, uint32_t t, uint32_t pat) { return acc | (t & pat); }
+
+// Per-lane, per-half final-row summary (what the final cell needs from this lane's 16 columns).
+struct RowSum {
+  int rb_val, rb_k;  // best bottom-row candidate M(Lq,k) - pen(Lt-k), k < Lt (smallest k on ties)
+  int diag, col;     // M(Lq,Lt) and the right-column candidate (lane owning column Lt only)
+};
+
+template <int TBM, int FST, int MSK>
+__device__ __forceinline__ void packed_task(const PackedParams& P, int task, int8_t* prof, int4* red,
+                                            const int8_t* s_sub, int lane) {
+  const Scoring& S = P.sc;
+  const int gi = S.gi, ge = S.ge, A = S.A;
+  const int W = 512;  // profile row stride: 32 lanes * 16 columns
+  int8_t* profA = prof;
+  int8_t* profB = prof + A * W;
+
+  // ---- who am I: pair ids of both halves, segment geometry
+  const int pid[2] = {P.tasks[task * 64 + lane], P.tasks[task * 64 + 32 + lane]};
+  const int prev_pid = __shfl_up_sync(0xffffffffu, pid[0], 1);
+  const bool seg_start = (lane == 0) || (prev_pid != pid[0]);
+  const unsigned starts = __ballot_sync(0xffffffffu, seg_start);
+  const int seg_lane0 = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+  const int off = lane - seg_lane0;
+
+  int Lq[2] = {0, 0}, Lt[2] = {0, 0}, sig[2] = {0, 0};
+  const uint8_t* qp[2] = {P.arena, P.arena};
+  const uint8_t* tp[2] = {P.arena, P.arena};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (pid[h] >= 0) {
+      const int qs = P.pair_q[pid[h]], ts = P.pair_t[pid[h]];
+      Lq[h] = (int)(P.seq_off[qs + 1] - P.seq_off[qs]);
+      Lt[h] = (int)(P.seq_off[ts + 1] - P.seq_off[ts]);
+      qp[h] = P.arena + P.aoff[qs];
+      tp[h] = P.arena + P.aoff[ts];
+      const int n = (Lt[h] + 15) >> 4;
+      sig[h] = P.rev ? 0 : 16 * n - Lt[h];  // forward pass is right-aligned
+    }
+  }
+  const int nl = (Lt[0] + 15) >> 4;  // lanes of this segment (both halves have the same n)
+  const int Lqmax = max(Lq[0], Lq[1]);
+  int nsteps = (pid[0] >= 0 || pid[1] >= 0) ? Lqmax + nl - 1 : 0;
+  nsteps = __reduce_max_sync(0xffffffffu, nsteps);
+
+  // ---- template profiles: prof[a*512 + lane*16 + c] = sub8[a][t_(column of register c)], pads = -128
+  {
+    uint32_t tc[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = off * 16 + w * 4 + b + 1 - sig[h];
+          uint32_t code = (uint32_t)A;  // pad column -> extra table column holding -128
+          if (pid[h] >= 0 && j >= 1 && j <= Lt[h]) code = tp[h][j - 1];
+          x |= code << (8 * b);
+        }
+        tc[h][w] = x;
+      }
+    __syncwarp();
+    for (int a = 0; a < A; ++a) {
+      const int8_t* row = s_sub + a * (A + 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t x = tc[h][w];
+          uint32_t v = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) v |= (uint32_t)(uint8_t)row[(x >> (8 * b)) & 0xff] << (8 * b);
+          ow[w] = v;
+        }
+        *reinterpret_cast<uint4*>((h ? profB : profA) + a * W + lane * 16) = o;
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- state for virtual row 0 (packed: A low, B high)
+  uint32_t Xp[16], Fs[16], Mg[16], nge[16];
+  uint32_t xl_hold;
+  {
+    int xh[2];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      int x[2], f[2], m[2], g[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = off * 16 + c + 1 - sig[h];
+        if (j < 0) { x[h] = kFloor16; f[h] = kNeg16; m[h] = kNeg16; g[h] = -ge; }
+        else if (j == 0) {  // the boundary column lives in a pad register: X(i,0) comes from its F chain
+          x[h] = 0;
+          f[h] = S.insfree ? 0 : kNeg16;
+          m[h] = S.insfree ? kNeg16 : -gi;
+          g[h] = S.insfree ? 0 : -ge;
+        } else {
+          x[h] = -(S.delfree ? 0 : gap_w(gi, ge, j));  // X(0,j): dpmatrix.h:412-418
+          f[h] = kNeg16;
+          m[h] = kNeg16;
+          g[h] = (S.insfree && j == Lt[h]) ? 0 : -ge;  // zero-penalty F chain in the last column
+        }
+      }
+      Xp[c] = pk2(x[0], x[1]);
+      Fs[c] = pk2(f[0], f[1]);
+      Mg[c] = pk2(m[0], m[1]);
+      nge[c] = pk2(g[0], g[1]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int jl = off * 16 - sig[h];  // column left of register 0
+      xh[h] = jl < 0 ? kFloor16 : (jl == 0 ? 0 : -(S.delfree ? 0 : gap_w(gi, ge, jl)));
+    }
+    xl_hold = pk2(xh[0], xh[1]);
+  }
+  // injection at the segment's first lane: X(i,0) when register 0 is column 1, "-inf" when it is a pad
+  const uint32_t inj_b_mask = (seg_start ? ((sig[0] == 0 ? 0x0000ffffu : 0u) | (sig[1] == 0 ? 0xffff0000u : 0u)) : 0u);
+  const uint32_t inj_mask = seg_start ? 0xffffffffu : 0u;
+  const uint32_t NEG2 = pk2(kNeg16, kNeg16);
+  const uint32_t FLOOR2 = pk2(kFloor16, kFloor16);
+  const uint32_t NGE2 = pk2(-ge, -ge);
+  const uint32_t NGI2 = pk2(-gi, -gi);
+
+  // ---- per-half output cursors
+  uint8_t* tbp[2] = {nullptr, nullptr};
+  int16_t* scp[2] = {nullptr, nullptr};
+  const int16_t* fp[2] = {nullptr, nullptr};
+  uint8_t* mkp[2] = {nullptr, nullptr};
+  int64_t tbs[2] = {0, 0}, scs[2] = {0, 0}, mks[2] = {0, 0};
+  uint32_t THR2 = 0;
+  float thr_f[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (pid[h] < 0) continue;
+    tbs[h] = tb_row_bytes(Lt[h]);
+    scs[h] = sc_row_elems(Lt[h]);
+    mks[h] = mask_row_words(Lt[h]) * 4;
+    if (TBM) tbp[h] = P.tb + P.tb_off[pid[h]] + off * 8;
+    if (FST) scp[h] = P.sc_out + P.sc_off[pid[h]] + off * 16;
+    if (MSK) {
+      // forward row (Lq - a) chunk (n-1-off): same 16 columns as this lane, in opposite order
+      fp[h] = P.scF + P.sc_off[pid[h]] + (int64_t)(Lq[h] - 1) * scs[h] + (nl - 1 - off) * 16;
+      mkp[h] = reinterpret_cast<uint8_t*>(P.mask + P.mask_off[pid[h]]) + off * 2;
+      const float inv = 1.f / (float)(1 << S.scale_log2);
+      const float opt = (float)P.fin_fwd[pid[h]] * inv;
+      thr_f[h] = nearopt_threshold(opt, P.delta_ratio);
+    }
+  }
+  if (MSK) {
+    int ti[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float t = floorf(thr_f[h] * (float)(1 << S.scale_log2));  // slack (integer) > thr  <=>  slack > floor(thr)
+      ti[h] = (int)fminf(fmaxf(t, (float)kFloor16), 16000.f);
+    }
+    THR2 = pk2(ti[0], ti[1]);
+  }
+
+  // ---- query residues: one 32-bit word (4 rows) at a time, fetched one word ahead
+  uint32_t qw[2] = {0, 0}, qwn[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) qwn[h] = *reinterpret_cast<const uint32_t*>(qp[h]);
+
+  uint32_t x_pub = 0, e_pub = NEG2, mg_pub = NEG2;
+  uint32_t fl[2][8];  // forward scores of the NEXT row (MSK), 16 int16 per half
+  if (MSK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (pid[h] >= 0 && Lq[h] >= 1) {
+        const uint4 a = reinterpret_cast<const uint4*>(fp[h])[0], b = reinterpret_cast<const uint4*>(fp[h])[1];
+        fl[h][0] = a.x; fl[h][1] = a.y; fl[h][2] = a.z; fl[h][3] = a.w;
+        fl[h][4] = b.x; fl[h][5] = b.y; fl[h][6] = b.z; fl[h][7] = b.w;
+      } else {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) fl[h][w] = 0;
+      }
+    }
+  }
+  // valid (non-pad) registers in the layout of accM: A bytes 0/1 (even/odd c), B bytes 2/3
+  uint32_t VM = 0;
+  if (MSK) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int j = off * 16 + c + 1 - sig[h];
+        if (pid[h] >= 0 && j >= 1 && j <= Lt[h]) VM |= 1u << (8 * (2 * h + (c & 1)) + 7 - (c >> 1));
+      }
+  }
+  long long cnt[2] = {0, 0};
+  RowSum capB = {kNeg32, 0, kNeg32, kNeg32};
+  bool have_capB = false;
+
+  // final-row summary of half h from the live state
+  auto row_summary = [&](int h) -> RowSum {
+    RowSum r = {kNeg32, 0, kNeg32, kNeg32};
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int j = off * 16 + c + 1 - sig[h];
+      const int m = half16(Mg[c], h) + gi;  // M(Lq, j)
+      if (j >= 1 && j < Lt[h]) {
+        const int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt[h] - j));
+        if (v > r.rb_val) { r.rb_val = v; r.rb_k = j; }
+      } else if (j == Lt[h]) {
+        r.diag = m;
+        r.col = (Lq[h] >= 2) ? half16(Fs[c], h) + (S.insfree ? gi : 0) : kNeg32;
+      }
+    }
+    return r;
+  };
+
+  for (int s = 0; s < nsteps; ++s) {
+    uint32_t xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
+    uint32_t e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
+    uint32_t mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
+    const int i = s - off + 1;
+    {
+      // X(i,0), dpmatrix.h:420-426; only the segment's first lane uses it
+      const int b = (i <= 0) ? 0 : -(S.insfree ? 0 : gi + ge * (i - 1));
+      const uint32_t b2 = pk2(b, b);
+      const uint32_t inj = (b2 & inj_b_mask) | (FLOOR2 & ~inj_b_mask);
+      xn = (xn & ~inj_mask) | (inj & inj_mask);
+      e_in = (e_in & ~inj_mask) | (NEG2 & inj_mask);
+      mg_in = (mg_in & ~inj_mask) | (NEG2 & inj_mask);
+    }
+    const bool act0 = pid[0] >= 0 && i >= 1 && i <= Lq[0];
+    const bool act1 = pid[1] >= 0 && i >= 1 && i <= Lq[1];
+    if (act0 || act1) {
+      if (((i - 1) & 3) == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          qw[h] = qwn[h];
+          qwn[h] = *reinterpret_cast<const uint32_t*>(qp[h] + (i - 1) + 4);
+        }
+      }
+      const int sh = 8 * ((i - 1) & 3);
+      const int qa0 = (qw[0] >> sh) & 0xff, qa1 = (qw[1] >> sh) & 0xff;
+      const uint4 pa = *reinterpret_cast<const uint4*>(profA + qa0 * W + lane * 16);
+      const uint4 pb = *reinterpret_cast<const uint4*>(profB + qa1 * W + lane * 16);
+      const uint32_t pwA[4] = {pa.x, pa.y, pa.z, pa.w};
+      const uint32_t pwB[4] = {pb.x, pb.y, pb.z, pb.w};
+      uint32_t fcur[2][8];
+      if (MSK) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) fcur[h][w] = fl[h][w];
+          const bool more = h ? (act1 && i < Lq[1]) : (act0 && i < Lq[0]);
+          if (more) {  // prefetch the forward scores of the next flow row (one row up in the forward matrix)
+            const int16_t* src = fp[h] - (int64_t)i * scs[h];
+            const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
+            fl[h][0] = a.x; fl[h][1] = a.y; fl[h][2] = a.z; fl[h][3] = a.w;
+            fl[h][4] = b.x; fl[h][5] = b.y; fl[h][6] = b.z; fl[h][7] = b.w;
+          }
+        }
+      }
+
+      uint32_t Xd = xl_hold, E = e_in, Mgl = mg_in;
+      uint32_t acc01 = 0, acc23 = 0, accM = 0;
+      uint32_t tbA[2], tbB[2], oA[8], oB[8];
+      uint32_t Mprev = 0, d5prev = 0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int k = c & 3;
+        const uint32_t ssel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
+        const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
+        const uint32_t M = __viaddmax_s16x2(simp, Xd, FLOOR2);
+        uint32_t d5 = 0;
+        if (MSK) {
+          // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1); element 15-c of the forward chunk
+          const int e = 15 - c;
+          const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
+          const uint32_t slack = __viaddmax_s16x2(fv, Xd, FLOOR2);
+          d5 = __vsub2(THR2, slack);  // sign set <=> slack > thr
+        }
+        Xd = Xp[c];
+        uint32_t F, X;
+        if (TBM) {
+          const uint32_t Eext = __vadd2(E, NGE2);
+          const uint32_t Fext = __vadd2(Fs[c], nge[c]);
+          const uint32_t dE = __vsub2(Eext, Mgl);  // sign set <=> the open candidate wins strictly
+          E = __vmaxs2(Eext, Mgl);
+          const uint32_t dF = __vsub2(Fext, Mg[c]);
+          F = __vmaxs2(Fext, Mg[c]);
+          const uint32_t dS1 = __vsub2(M, E);  // sign set <=> E > M
+          const uint32_t t = __vmaxs2(M, E);
+          const uint32_t dS2 = __vsub2(t, F);  // sign set <=> F > max(M,E)
+          X = __vmaxs2(t, F);
+          const uint32_t pat = 0x01010101u << (7 - (c & 7));
+          acc01 = or_and(acc01, prmt(dS1, dS2, 0xFBD9u), pat);
+          acc23 = or_and(acc23, prmt(dE, dF, 0xFBD9u), pat);
+          if ((c & 7) == 7) {
+            tbA[c >> 3] = prmt(acc01, acc23, 0x5410u);
+            tbB[c >> 3] = prmt(acc01, acc23, 0x7632u);
+            acc01 = 0;
+            acc23 = 0;
+          }
+        } else {
+          E = __viaddmax_s16x2(E, NGE2, Mgl);
+          F = __viaddmax_s16x2(Fs[c], nge[c], Mg[c]);
+          X = __vimax3_s16x2(M, E, F);
+        }
+        Mgl = __vadd2(M, NGI2);
+        Xp[c] = X;
+        Fs[c] = F;
+        Mg[c] = Mgl;
+        if (FST) {
+          if (c & 1) {
+            oA[c >> 1] = prmt(Mprev, M, 0x5410u);
+            oB[c >> 1] = prmt(Mprev, M, 0x7632u);
+          } else Mprev = M;
+        }
+        if (MSK) {
+          if (c & 1) accM = or_and(accM, prmt(d5prev, d5, 0xFBD9u), 0x01010101u << (7 - (c >> 1)));
+          else d5prev = d5;
+        }
+      }
+      if (MSK) accM &= VM;
+      xl_hold = xn;
+      x_pub = Xp[15];
+      e_pub = E;
+      mg_pub = Mgl;
+      if (act0) {
+        if (TBM) *reinterpret_cast<uint2*>(tbp[0] + (int64_t)(i - 1) * tbs[0]) = make_uint2(tbA[0], tbA[1]);
+        if (FST) {
+          uint4* d = reinterpret_cast<uint4*>(scp[0] + (int64_t)(i - 1) * scs[0]);
+          d[0] = make_uint4(oA[0], oA[1], oA[2], oA[3]);
+          d[1] = make_uint4(oA[4], oA[5], oA[6], oA[7]);
+        }
+        if (MSK) {
+          *reinterpret_cast<uint16_t*>(mkp[0] + (int64_t)(i - 1) * mks[0]) = (uint16_t)(accM & 0xffffu);
+          cnt[0] += __popc(accM & 0xffffu);
+        }
+      }
+      if (act1) {
+        if (TBM) *reinterpret_cast<uint2*>(tbp[1] + (int64_t)(i - 1) * tbs[1]) = make_uint2(tbB[0], tbB[1]);
+        if (FST) {
+          uint4* d = reinterpret_cast<uint4*>(scp[1] + (int64_t)(i - 1) * scs[1]);
+          d[0] = make_uint4(oB[0], oB[1], oB[2], oB[3]);
+          d[1] = make_uint4(oB[4], oB[5], oB[6], oB[7]);
+        }
+        if (MSK) {
+          *reinterpret_cast<uint16_t*>(mkp[1] + (int64_t)(i - 1) * mks[1]) = (uint16_t)(accM >> 16);
+          cnt[1] += __popc(accM >> 16);
+        }
+        // the shorter query of the couple ends first: keep its final row before later rows overwrite it
+        if (i == Lq[1] && Lq[1] < Lq[0]) { capB = row_summary(1); have_capB = true; }
+      }
+    }
+  }
+
+  // ---- final cells (dpmatrix.h:504-534 / 844-874): match, bottom row (k ascending), right column
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    RowSum r = (h == 1 && have_capB) ? capB : row_summary(h);
+    __syncwarp();
+    red[lane] = make_int4(r.rb_val, r.rb_k, r.diag, r.col);
+    __syncwarp();
+    if (seg_start && pid[h] >= 0) {
+      int rb = kNeg32, rk = 0, dg = kNeg32, cl = kNeg32;
+      for (int l = 0; l < nl; ++l) {
+        const int4 v = red[lane + l];
+        if (v.x > rb) { rb = v.x; rk = v.y; }  // lanes ascend in column order: '>' keeps the smallest k
+        dg = max(dg, v.z);
+        cl = max(cl, v.w);
+      }
+      int best = dg, kind = 0, k = Lt[h];
+      if (Lt[h] >= 2 && rb > best) { best = rb; kind = 1; k = rk; }
+      if (cl > best) { best = cl; kind = 2; k = -1; }
+      P.fin_score[pid[h]] = best;
+      P.fin_kind[pid[h]] = kind;
+      P.fin_k[pid[h]] = k;
+      if (MSK && P.threshold) P.threshold[pid[h]] = thr_f[h];
+    }
+    if (MSK && P.count) {
+      __syncwarp();
+      reinterpret_cast<long long*>(red)[lane] = cnt[h];
+      __syncwarp();
+      if (seg_start && pid[h] >= 0) {
+        long long t = 0;
+        for (int l = 0; l < nl; ++l) t += reinterpret_cast<long long*>(red)[lane + l];
+        P.count[pid[h]] = t;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int TBM, int FST, int MSK>
+__global__ void __launch_bounds__(kPackedWarps * 32) packed_kernel(const PackedParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int A = P.sc.A;
+  int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
+  const int sub_bytes = (A * (A + 1) + 15) / 16 * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * 32 * sizeof(int4)) + warp * 2 * A * 512;
+  for (int x = threadIdx.x; x < A * (A + 1); x += blockDim.x) {
+    const int a = x / (A + 1), b = x % (A + 1);
+    s_sub[x] = (b < A) ? P.sub8[a * A + b] : (int8_t)-128;
+  }
+  __syncthreads();
+  for (;;) {
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(P.counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= (unsigned int)P.n_tasks) break;
+    packed_task<TBM, FST, MSK>(P, (int)item, prof, red, s_sub, lane);
+  }
+}
+
+}  // namespace aadp

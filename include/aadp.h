@@ -60,6 +60,9 @@ const char* aadp_version(void);
  * stream; until this is called the context uses a private non-blocking stream.               */
 int aadp_set_stream(aadp_ctx* ctx, void* cuda_stream);
 int aadp_synchronize(aadp_ctx* ctx);
+/* Tuning / test switches. "packed" (default 1): use the packed int16x2 kernels for every pair that
+ * qualifies (non-local, Lt <= 512, |score| bound < 8000 units); 0 forces the int32 kernels.     */
+int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
 
 /* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)
  * sub is A x A row-major, sub[q_code*A + t_code] == SubstitutionMatrix::score (submatrix.h:36-38).
@@ -134,7 +137,7 @@ int64_t aadp_tb_row_bytes(int Lt);
 /* Decode one cell of a packed traceback fetched with aadp_batch_fetch_tb. (i,j) and the result
  * are reference matrix coordinates; direction selects the fwd or rev conventions.              */
 int aadp_batch_fetch_tb(aadp_ctx* ctx, int64_t p, int direction, uint8_t* tb, int64_t tb_bytes,
-                        int32_t* final_rec /* [4]: score units, kind, k, scale_log2 */);
+                        int32_t* final_rec /* [5]: score units, kind, k, scale_log2, leading pad columns */);
 int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align_type,
                      uint32_t flags, const int32_t* final_rec, int i, int j, int32_t* prev_q,
                      int32_t* prev_t);

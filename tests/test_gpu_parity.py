@@ -9,10 +9,13 @@ from util import po, MODES, MODE_NAMES, golden_cases, golden_case, rand_pair, as
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["packed", "int32"])
+def ctx(request):
+    # every parity test runs twice: through the packed int16x2 kernels (where a pair qualifies)
+    # and with the int32 kernels forced
     import alignment_algos_b200 as a
     c = a.Context(0)
+    c.set_option("packed", 1 if request.param == "packed" else 0)
     yield c
     c.close()
 
