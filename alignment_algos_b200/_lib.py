@@ -51,6 +51,8 @@ def lib():
     L.aadp_batch_optimal.argtypes = [vp, i64, C.c_int, vp, i32, vp, vp]
     L.aadp_tb_row_bytes.restype = i64
     L.aadp_tb_row_bytes.argtypes = [C.c_int]
+    L.aadp_batch_tb_bytes.restype = i64
+    L.aadp_batch_tb_bytes.argtypes = [vp, i64]
     L.aadp_batch_fetch_tb.argtypes = [vp, i64, C.c_int, vp, i64, vp]
     L.aadp_decode_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, vp, vp]
     _lib = L
@@ -62,6 +64,6 @@ EXPORTS = [
     "aadp_synchronize", "aadp_set_option", "aadp_set_scoring", "aadp_fill_pair", "aadp_fill_batch",
     "aadp_upload_batch", "aadp_run_batch", "aadp_batch_resident_bytes", "aadp_last_launch_count",
     "aadp_last_cell_updates", "aadp_set_profiling", "aadp_profile_count", "aadp_profile_get",
-    "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes",
+    "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes", "aadp_batch_tb_bytes",
     "aadp_batch_fetch_tb", "aadp_decode_cell",
 ]

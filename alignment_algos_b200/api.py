@@ -170,9 +170,9 @@ class Context:
         return rc, pairs[: min(n.value, cap)].copy(), s.value
 
     def fetch_tb(self, p, direction, Lq, Lt):
-        nbytes = max(int(Lq * self.L.aadp_tb_row_bytes(Lt)), 1)
+        nbytes = max(int(self.L.aadp_batch_tb_bytes(self.h, p)), 1)
         tb = np.zeros(nbytes, np.uint8)
-        fin = np.zeros(5, np.int32)
+        fin = np.zeros(6, np.int32)
         self._ck(self.L.aadp_batch_fetch_tb(self.h, p, direction, _ptr(tb), nbytes, _ptr(fin)))
         return tb, fin
 

@@ -176,7 +176,7 @@ template <int TBM, int FST, int MSK>
 int launch_packed_t(aadp_ctx* c, PackedParams& P) {
   auto kern = packed_kernel<TBM, FST, MSK>;
   const int A = P.sc.A;
-  const size_t smem = (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + 2 * A * 512);
+  const size_t smem = (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + kPackedStage + 2 * A * 512);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
@@ -290,9 +290,9 @@ void build_arenas(aadp_ctx* c, const uint8_t* residues) {
     b.aoff[s] = (int32_t)cur;
     const int64_t L = b.seq_off[s + 1] - b.seq_off[s];
     maxL = std::max(maxL, L);
-    cur += (L + 3) / 4 * 4;
+    cur += (L + 15) / 16 * 16;
   }
-  const int64_t total = cur + maxL + 64;
+  const int64_t total = cur + maxL + 128;
   b.arena_f.assign((size_t)total, 0);
   b.arena_r.assign((size_t)total, 0);
   for (int64_t s = 0; s < b.nseq; ++s) {
@@ -329,8 +329,6 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
     if (Lq < 0 || Lt < 0 || Lq > (1 << 24) || Lt > (1 << 24)) return fail("bad sequence length");
     b.max_Lq = std::max<int>(b.max_Lq, (int)Lq);
     b.max_Lt = std::max<int>(b.max_Lt, (int)Lt);
-    b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? Lq * tb_row_bytes((int)Lt) : 0);
-    b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? Lq * mask_row_words((int)Lt) : 0);
     cells[p] = Lq * Lt;
     b.cells += (double)cells[p];
     // |score| bound in integer units: matches + one end gap on each side
@@ -349,11 +347,14 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   build_tasks(c);
   b.st_mode = bound < 30000 ? 1 : 2;
   if (bound >= (1 << 24)) return fail("scores exceed the exactly-representable float range (2^24 units)");
-  for (int64_t p = 0; p < np; ++p) {  // score offsets in int16 units
+  for (int64_t p = 0; p < np; ++p) {  // product offsets (scores in int16 units; 16-byte aligned per pair)
     const int qs = b.pair_q[p], ts = b.pair_t[p];
     const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
+    const Layout L = make_layout((int)Lq, (int)Lt, b.fmt[p], 0);
     const int64_t units = (b.fmt[p] || b.st_mode == 1) ? 1 : 2;
-    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? Lq * sc_row_elems((int)Lt) * units : 0);
+    b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? round_up64(layout_tb_bytes(L), 16) : 0);
+    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? round_up64(layout_sc_elems(L) * units, 8) : 0);
+    b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? round_up64(layout_mask_words(L), 4) : 0);
   }
   for (int k = 0; k < 2; ++k)
     std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
@@ -466,7 +467,7 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   D.rev = dir;
   D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
   const bool packed = b.fmt[p] != 0;
-  D.sig = (packed && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;
+  D.lay = make_layout(Lq, Lt, packed, dir);
   D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
   D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
   if (h_score && packed && dir == 1 && !(b.ran_what & AADP_W_SCORES))
@@ -502,9 +503,11 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
   const int sz2 = Lt + 2;
   const int64_t mws = mask_row_words(Lt);
-  std::vector<uint32_t> bits((size_t)std::max<int64_t>(Lq * mws, 1));
-  if (Lq * mws > 0) {
-    CK(cudaMemcpyAsync(bits.data(), c->mask.as<uint32_t>() + b.mask_off[p], (size_t)(Lq * mws) * 4, cudaMemcpyDeviceToHost, c->stream));
+  const Layout L = make_layout(Lq, Lt, b.fmt[p], 1);
+  const int64_t nwords = layout_mask_words(L);
+  std::vector<uint32_t> bits((size_t)std::max<int64_t>(nwords, 1));
+  if (nwords > 0) {
+    CK(cudaMemcpyAsync(bits.data(), c->mask.as<uint32_t>() + b.mask_off[p], (size_t)nwords * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   memset(h_mask, 0, (size_t)(Lq + 2) * sz2);
@@ -513,14 +516,14 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
       for (int j = 1; j <= Lt; ++j)
         h_mask[(size_t)i * sz2 + j] = (bits[(size_t)(i - 1) * mws + ((j - 1) >> 5)] >> ((j - 1) & 31)) & 1u;
   } else {
-    // packed reverse pass: reverse-flow coordinates, 2 bytes per 16-column lane slot,
+    // packed reverse pass: reverse-flow coordinates, diagonal-major, 2 bytes per 16-column slot:
     // byte (c&1), bit 7-(c>>1)
     const uint8_t* by = reinterpret_cast<const uint8_t*>(bits.data());
     for (int i = 1; i <= Lq; ++i)
       for (int j = 1; j <= Lt; ++j) {
         const int a = Lq + 1 - i, bb = Lt + 1 - j;
         const int slot = (bb - 1) >> 4, cc = (bb - 1) & 15;
-        const uint8_t v = by[(size_t)(a - 1) * mws * 4 + slot * 2 + (cc & 1)];
+        const uint8_t v = by[((size_t)(a - 1 + slot) * L.n + slot) * 2 + (cc & 1)];
         h_mask[(size_t)i * sz2 + j] = (v >> (7 - (cc >> 1))) & 1u;
       }
   }
@@ -660,7 +663,7 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   b.ran_what = 0;
   if (b.n_tasks) {
     int64_t tot = 0;
-    for (int64_t s2 = 0; s2 < nseq; ++s2) tot += (seq_off[s2 + 1] - seq_off[s2] + 3) / 4 * 4;
+    for (int64_t s2 = 0; s2 < nseq; ++s2) tot += (seq_off[s2 + 1] - seq_off[s2] + 15) / 16 * 16;
     if (tot > 0x7fff0000LL) return fail("sequence arena too large for the packed path");
     build_arenas(c, residues);
     if (upload_vec(c->arena_f, b.arena_f, c->stream)) return 1;
@@ -859,6 +862,11 @@ int aadp_fill_pair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, int 
 
 int64_t aadp_tb_row_bytes(int Lt) { return tb_row_bytes(Lt); }
 
+int64_t aadp_batch_tb_bytes(aadp_ctx* c, int64_t p) {
+  if (!c || p < 0 || p >= c->b.npairs || c->b.tb_off.empty()) return 0;
+  return c->b.tb_off[p + 1] - c->b.tb_off[p];
+}
+
 int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int64_t tb_bytes, int32_t* final_rec) {
   if (check_ctx(c, true)) return 1;
   Batch& b = c->b;
@@ -881,6 +889,7 @@ int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int6
       const int ts = b.pair_t[p];
       const int Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
       final_rec[4] = (b.fmt[p] && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;  // leading pad columns of the layout
+      final_rec[5] = b.fmt[p] ? 1 : 0;                                          // 1 = diagonal-major
     }
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -894,11 +903,12 @@ int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align
   const int a = rev ? Lq + 1 - i : i, b = rev ? Lt + 1 - j : j;
   int pa = -1, pb = -1;
   bool is_final = false;
-  const int sig = final_rec ? final_rec[4] : 0;
-  if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) decode_prev(tb, Lt, sig, a, b, &pa, &pb);
+  Layout L = make_layout(Lq, Lt, final_rec ? final_rec[5] : 0, rev);
+  if (final_rec) L.sig = final_rec[4];
+  if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) decode_prev(tb, L, a, b, &pa, &pb);
   else if (a == Lq + 1 && b == Lt + 1) {
     if (!final_rec) return fail("final_rec needed for the final cell");
-    decode_final(tb, Lq, Lt, sig, final_rec[1], final_rec[2], &pa, &pb);
+    decode_final(tb, L, final_rec[1], final_rec[2], &pa, &pb);
     is_final = true;
   }
   if (pa < 0) { *prev_q = -1; *prev_t = -1; return 0; }
@@ -918,7 +928,7 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
   const int qs = b.pair_q[p], ts = b.pair_t[p];
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
   std::vector<uint8_t> tb((size_t)std::max<int64_t>(b.tb_off[p + 1] - b.tb_off[p], 1));
-  int32_t fin[5];
+  int32_t fin[6];
   if (aadp_batch_fetch_tb(c, p, direction, tb.data(), (int64_t)tb.size(), fin)) return 1;
   if (score) *score = (float)fin[0] / (float)(1 << fin[3]);
   // optimal.h:57-74 / optimal_rev.h:57-76: follow prev_* from the final cell to the anchor

@@ -372,25 +372,68 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParam
 // tb: packed traceback of one pair in FLOW coordinates. Returns the flow predecessor of flow
 // cell (a,b), 1 <= a <= Lq, 1 <= b <= Lt.
 // ------------------------------------------------------------------------------------------------
-// `sig` = number of leading pad columns of the stored layout (0 for the int32 kernels and for the
-// packed reverse pass, 16*ceil(Lt/16)-Lt for the right-aligned packed forward pass).
-__host__ __device__ inline int tb_plane(const uint8_t* tb, int64_t tbs, int sig, int a, int b, int plane) {
-  const int pos = b - 1 + sig;
-  const uint8_t byte = tb[(int64_t)(a - 1) * tbs + 4 * (pos >> 3) + plane];
-  return (byte >> (7 - (pos & 7))) & 1;
+// Storage layout of one pair's products in one direction.
+//   sig  = number of leading pad columns (0 for the int32 kernels and the packed reverse pass,
+//          16*ceil(Lt/16)-Lt for the right-aligned packed forward pass);
+//   skew = 0: row-major (int32 kernels).  1: diagonal-major (packed kernels): the 16-column chunk
+//          k of flow row a lives in "skew row" (a-1)+k, so everything a warp produces in one step
+//          is contiguous in memory (the lanes of a segment are skewed by one row per lane).
+struct Layout {
+  int Lq, Lt, n;  // n = ceil(Lt/16) chunks
+  int sig, skew;
+};
+__host__ __device__ inline Layout make_layout(int Lq, int Lt, int packed, int rev) {
+  Layout L;
+  L.Lq = Lq; L.Lt = Lt; L.n = (Lt + 15) >> 4;
+  L.skew = packed ? 1 : 0;
+  L.sig = (packed && !rev) ? 16 * L.n - Lt : 0;
+  return L;
+}
+// bytes of packed traceback / int16 units of scores / 32-bit words of mask one pair occupies
+__host__ __device__ inline int64_t layout_tb_bytes(const Layout& L) {
+  return L.skew ? (int64_t)(L.Lq + L.n - 1) * L.n * 8 : (int64_t)L.Lq * tb_row_bytes(L.Lt);
+}
+__host__ __device__ inline int64_t layout_sc_elems(const Layout& L) {
+  return L.skew ? (int64_t)(L.Lq + L.n - 1) * L.n * 16 : (int64_t)L.Lq * sc_row_elems(L.Lt);
+}
+__host__ __device__ inline int64_t layout_mask_words(const Layout& L) {
+  return L.skew ? ((int64_t)(L.Lq + L.n - 1) * L.n * 2 + 3) / 4 : (int64_t)L.Lq * ((L.Lt + 31) / 32);
+}
+// byte offset of the traceback byte holding plane `plane` of flow cell (a,b); *bit = bit index in it
+__host__ __device__ inline int64_t layout_tb_byte(const Layout& L, int a, int b, int plane, int* bit) {
+  const int pos = b - 1 + L.sig;
+  *bit = 7 - (pos & 7);
+  if (L.skew) {
+    const int k = pos >> 4;
+    return ((int64_t)(a - 1 + k) * L.n + k) * 8 + 4 * ((pos >> 3) & 1) + plane;
+  }
+  return (int64_t)(a - 1) * tb_row_bytes(L.Lt) + 4 * (pos >> 3) + plane;
+}
+// element index (int16 or int32 units) of the score of flow cell (a,b)
+__host__ __device__ inline int64_t layout_sc_index(const Layout& L, int a, int b) {
+  const int pos = b - 1 + L.sig;
+  if (L.skew) {
+    const int k = pos >> 4, e = pos & 15;
+    return (((int64_t)(a - 1 + k) * 2 + (e >> 3)) * L.n + k) * 8 + (e & 7);
+  }
+  return (int64_t)(a - 1) * sc_row_elems(L.Lt) + pos;
+}
+__host__ __device__ inline int tb_plane(const uint8_t* tb, const Layout& L, int a, int b, int plane) {
+  int bit;
+  const uint8_t byte = tb[layout_tb_byte(L, a, b, plane, &bit)];
+  return (byte >> bit) & 1;
 }
 
-__host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int sig, int a, int b, int* pa, int* pb) {
+__host__ __device__ inline void decode_prev(const uint8_t* tb, const Layout& L, int a, int b, int* pa, int* pb) {
   if (a == 1 || b == 1) { *pa = 0; *pb = 0; return; }  // dpmatrix.h:408-426: boundary cells point at the anchor
-  const int64_t tbs = tb_row_bytes(Lt);
   const int r = a - 1, c = b - 1;
-  if (tb_plane(tb, tbs, sig, r, c, 1)) {  // F won: walk up column c while the gap was extended
+  if (tb_plane(tb, L, r, c, 1)) {  // F won: walk up column c while the gap was extended
     int rr = r;
-    while (rr > 1 && !tb_plane(tb, tbs, sig, rr, c, 3)) --rr;
+    while (rr > 1 && !tb_plane(tb, L, rr, c, 3)) --rr;
     *pa = rr - 1; *pb = c;
-  } else if (tb_plane(tb, tbs, sig, r, c, 0)) {  // E won: walk left along row r
+  } else if (tb_plane(tb, L, r, c, 0)) {  // E won: walk left along row r
     int cc = c;
-    while (cc > 1 && !tb_plane(tb, tbs, sig, r, cc, 2)) --cc;
+    while (cc > 1 && !tb_plane(tb, L, r, cc, 2)) --cc;
     *pa = r; *pb = cc - 1;
   } else {
     *pa = r; *pb = c;
@@ -398,14 +441,14 @@ __host__ __device__ inline void decode_prev(const uint8_t* tb, int Lt, int sig, 
 }
 
 // Predecessor of the final flow cell (Lq+1, Lt+1) from the per-pair record.
-__host__ __device__ inline void decode_final(const uint8_t* tb, int Lq, int Lt, int sig, int kind, int k, int* pa, int* pb) {
+__host__ __device__ inline void decode_final(const uint8_t* tb, const Layout& L, int kind, int k, int* pa, int* pb) {
+  const int Lq = L.Lq, Lt = L.Lt;
   if (Lq == 0 || Lt == 0) { *pa = 0; *pb = 0; return; }
   if (kind == 0) { *pa = Lq; *pb = Lt; }
   else if (kind == 1) { *pa = Lq; *pb = k; }
   else {
-    const int64_t tbs = tb_row_bytes(Lt);
     int rr = Lq;
-    while (rr > 1 && !tb_plane(tb, tbs, sig, rr, Lt, 3)) --rr;
+    while (rr > 1 && !tb_plane(tb, L, rr, Lt, 3)) --rr;
     *pa = rr - 1; *pb = Lt;
   }
 }
@@ -495,7 +538,7 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
 struct DenseParams {
   Scoring sc;
   int Lq, Lt, rev, repro_rev_bug;
-  int sig;  // leading pad columns of the stored layout
+  Layout lay;
   int st_mode;
   const void* sc_blob; int64_t sc_off;
   const uint8_t* tb;  // packed traceback of this pair/direction (or null)
@@ -509,7 +552,6 @@ __global__ void dense_kernel(const DenseParams P) {
   const int sz1 = P.Lq + 2, sz2 = P.Lt + 2;
   const int64_t n = (int64_t)sz1 * sz2;
   const float inv = 1.f / (float)(1 << P.sc.scale_log2);
-  const int64_t scs = sc_row_elems(P.Lt);
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(o / sz2), j = (int)(o % sz2);
     // flow coordinates
@@ -519,18 +561,18 @@ __global__ void dense_kernel(const DenseParams P) {
     const bool interior = a >= 1 && a <= P.Lq && b >= 1 && b <= P.Lt;
     int si = 0;
     if (interior) {
-      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + (int64_t)(a - 1) * scs + (b - 1 + P.sig)];
-      else if (P.st_mode == 2) si = ((const int32_t*)((const int16_t*)P.sc_blob + P.sc_off))[(int64_t)(a - 1) * scs + (b - 1 + P.sig)];
+      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + layout_sc_index(P.lay, a, b)];
+      else if (P.st_mode == 2) si = ((const int32_t*)((const int16_t*)P.sc_blob + P.sc_off))[layout_sc_index(P.lay, a, b)];
       s = (float)si * inv;
       if (P.tb) {
-        decode_prev(P.tb, P.Lt, P.sig, a, b, &pa, &pb);
+        decode_prev(P.tb, P.lay, a, b, &pa, &pb);
         // local fills: a cell clamped to 0 keeps the match predecessor (dpmatrix.h:616-646)
         if (P.sc.local && si == 0 && a > 1 && b > 1) { pa = a - 1; pb = b - 1; }
       }
     } else if (a == P.Lq + 1 && b == P.Lt + 1) {
       s = (float)P.fin_score * inv;
       if (P.Lq == 0 || P.Lt == 0) { pa = 0; pb = 0; }
-      else if (P.tb) decode_final(P.tb, P.Lq, P.Lt, P.sig, P.fin_kind, P.fin_k, &pa, &pb);
+      else if (P.tb) decode_final(P.tb, P.lay, P.fin_kind, P.fin_k, &pa, &pb);
       else if (P.fin_kind == 0) { pa = P.Lq; pb = P.Lt; }
       else if (P.fin_kind == 1) { pa = P.Lq; pb = P.fin_k; }
     }

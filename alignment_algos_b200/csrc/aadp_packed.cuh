@@ -17,11 +17,15 @@
 //     aligned 16-byte loads and emits the near-optimal cell set F+R-sim > thr (ucw.h:141-180,
 //     cw.h:86-88) on the fly -- the forward+reverse fusion of BASELINE.json's north_star.
 //
-// Layouts (shared with the int32 kernels; `sig` = number of leading pad columns of the direction):
-//   traceback  row a-1, 8-byte lane slots, two 32-bit words per slot (8 columns each), byte p =
-//              plane p, bit 7-(c&7) = register c; register c of slot k is flow column 16k+c+1-sig
-//   scores     int16, row stride 16n, element index (flow column - 1 + sig)
-//   mask       reverse-flow coordinates, 2 bytes per lane slot: byte (c&1), bit 7-(c>>1)
+// Layouts (struct Layout in aadp_kernels.cuh; `sig` = number of leading pad columns): DIAGONAL-MAJOR.
+// Lane `off` of a segment works on flow row a = step-off+1, so chunk k of row a is produced at step
+// r = (a-1)+k.  Everything is stored by "skew row" r, which makes every store of a step contiguous
+// across the lanes of a segment (fully coalesced), and -- because the reverse pass is skewed the
+// opposite way -- makes the reverse pass read ONE contiguous skew row of forward scores per step:
+//   traceback  [r][slot k] 8 bytes: two 32-bit words (8 columns each), byte p = plane p,
+//              bit 7-(c&7) = register c; register c of slot k is flow column 16k+c+1-sig
+//   scores     int16 [r][c>>3][slot k][c&7]   (two 16-byte halves per slot, each half contiguous over k)
+//   mask       reverse-flow coordinates [r][slot k] 2 bytes: byte (c&1), bit 7-(c>>1)
 #pragma once
 #include "aadp_kernels.cuh"
 
@@ -31,6 +35,7 @@ constexpr int kNeg16 = -24000;    // "-infinity" seed of E/F chains (only ever m
 constexpr int kFloor16 = -16000;  // clamp floor of M / slack
 constexpr int kPackedBound = 8000;  // |score| bound (integer units) a pair must satisfy to use this kernel
 constexpr int kPackedWarps = 2;   // warps per CTA
+constexpr int kPackedStage = 2048 + 6144;  // per-warp cp.async staging: query rings + forward-score chunks
 
 struct PackedParams {
   Scoring sc;
@@ -65,6 +70,17 @@ __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo &
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
 __device__ __forceinline__ int half16(uint32_t v, int h) { return h ? hi16(v) : lo16(v); }
+// Asynchronous global->shared staging (LDGSTS): the prefetched bytes never occupy a register, so no
+// instruction waits on them until cp_async_wait() one or more rows later.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int cond) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 16; }"
+               :: "r"(sa), "l"(gsrc), "r"(cond) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 // acc | (t & pat)
 __device__ __forceinline__ uint32_t or_and(uint32_t acc, uint32_t t, uint32_t pat) { return acc | (t & pat); }
 
@@ -76,7 +92,7 @@ struct RowSum {
 
 template <int TBM, int FST, int MSK>
 __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int8_t* prof, int4* red,
-                                            const int8_t* s_sub, int lane) {
+                                            uint8_t* stage, const int8_t* s_sub, int lane) {
   const Scoring& S = P.sc;
   const int gi = S.gi, ge = S.ge, A = S.A;
   const int W = 512;  // profile row stride: 32 lanes * 16 columns
@@ -193,26 +209,23 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   const uint32_t NGE2 = pk2(-ge, -ge);
   const uint32_t NGI2 = pk2(-gi, -gi);
 
-  // ---- per-half output cursors
+  // ---- per-half output bases (diagonal-major: the address of a step is base + step * stride)
   uint8_t* tbp[2] = {nullptr, nullptr};
   int16_t* scp[2] = {nullptr, nullptr};
   const int16_t* fp[2] = {nullptr, nullptr};
   uint8_t* mkp[2] = {nullptr, nullptr};
-  int64_t tbs[2] = {0, 0}, scs[2] = {0, 0}, mks[2] = {0, 0};
   uint32_t THR2 = 0;
   float thr_f[2] = {0.f, 0.f};
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if (pid[h] < 0) continue;
-    tbs[h] = tb_row_bytes(Lt[h]);
-    scs[h] = sc_row_elems(Lt[h]);
-    mks[h] = mask_row_words(Lt[h]) * 4;
-    if (TBM) tbp[h] = P.tb + P.tb_off[pid[h]] + off * 8;
-    if (FST) scp[h] = P.sc_out + P.sc_off[pid[h]] + off * 16;
+    if (TBM) tbp[h] = P.tb + P.tb_off[pid[h]] + off * 8;                 // + step * nl*8
+    if (FST) scp[h] = P.sc_out + P.sc_off[pid[h]] + off * 8;             // + step * nl*16 (+ nl*8 for the upper half)
     if (MSK) {
-      // forward row (Lq - a) chunk (n-1-off): same 16 columns as this lane, in opposite order
-      fp[h] = P.scF + P.sc_off[pid[h]] + (int64_t)(Lq[h] - 1) * scs[h] + (nl - 1 - off) * 16;
-      mkp[h] = reinterpret_cast<uint8_t*>(P.mask + P.mask_off[pid[h]]) + off * 2;
+      // forward chunk (nl-1-off) of forward row Lq+1-a sits in forward skew row Lq+nl-2-step: the same
+      // skew row for every lane of the segment
+      fp[h] = P.scF + P.sc_off[pid[h]] + (int64_t)(Lq[h] + nl - 2) * nl * 16 + (nl - 1 - off) * 8;  // - step * nl*16
+      mkp[h] = reinterpret_cast<uint8_t*>(P.mask + P.mask_off[pid[h]]) + off * 2;  // + step * nl*2
       const float inv = 1.f / (float)(1 << S.scale_log2);
       const float opt = (float)P.fin_fwd[pid[h]] * inv;
       thr_f[h] = nearopt_threshold(opt, P.delta_ratio);
@@ -228,26 +241,33 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     THR2 = pk2(ti[0], ti[1]);
   }
 
-  // ---- query residues: one 32-bit word (4 rows) at a time, fetched one word ahead
-  uint32_t qw[2] = {0, 0}, qwn[2];
+  // ---- query residues: each lane stages its own rows in a private 32-byte ring per half
+  // (two 16-row blocks), refilled with cp.async one block (16 rows) ahead of use.
+  uint8_t* qst[2] = {stage + lane * 64, stage + lane * 64 + 32};
+  // forward-score chunks (MSK): private triple buffer (3 x 32 bytes per half), requested two rows ahead
+  uint8_t* fst[2] = {stage + 2048 + lane * 192, stage + 2048 + lane * 192 + 96};
 #pragma unroll
-  for (int h = 0; h < 2; ++h) qwn[h] = *reinterpret_cast<const uint32_t*>(qp[h]);
+  for (int h = 0; h < 2; ++h) {
+    cp_async16(qst[h], qp[h], 1);
+    cp_async16(qst[h] + 16, qp[h] + 16, 1);
+  }
 
   uint32_t x_pub = 0, e_pub = NEG2, mg_pub = NEG2;
-  uint32_t fl[2][8];  // forward scores of the NEXT row (MSK), 16 int16 per half
   if (MSK) {
+    // rows 1 and 2 of this lane (steps off and off+1) -> buffers 1 and 2
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (pid[h] >= 0 && Lq[h] >= 1) {
-        const uint4 a = reinterpret_cast<const uint4*>(fp[h])[0], b = reinterpret_cast<const uint4*>(fp[h])[1];
-        fl[h][0] = a.x; fl[h][1] = a.y; fl[h][2] = a.z; fl[h][3] = a.w;
-        fl[h][4] = b.x; fl[h][5] = b.y; fl[h][6] = b.z; fl[h][7] = b.w;
-      } else {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) fl[h][w] = 0;
+      for (int r = 1; r <= 2; ++r) {
+        const int ok = pid[h] >= 0 && Lq[h] >= r;
+        const int16_t* src = fp[h] - (int64_t)(off + r - 1) * nl * 16;
+        cp_async16(fst[h] + 32 * (r % 3), src, ok);
+        cp_async16(fst[h] + 32 * (r % 3) + 16, src + nl * 8, ok);
       }
     }
   }
+  cp_async_commit();
+  int qa_n0 = 0, qa_n1 = 0;  // query residues of the NEXT row (read one row ahead to shorten the LDS chain)
   // valid (non-pad) registers in the layout of accM: A bytes 0/1 (even/odd c), B bytes 2/3
   uint32_t VM = 0;
   if (MSK) {
@@ -298,75 +318,91 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     const bool act0 = pid[0] >= 0 && i >= 1 && i <= Lq[0];
     const bool act1 = pid[1] >= 0 && i >= 1 && i <= Lq[1];
     if (act0 || act1) {
-      if (((i - 1) & 3) == 0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          qw[h] = qwn[h];
-          qwn[h] = *reinterpret_cast<const uint32_t*>(qp[h] + (i - 1) + 4);
-        }
-      }
-      const int sh = 8 * ((i - 1) & 3);
-      const int qa0 = (qw[0] >> sh) & 0xff, qa1 = (qw[1] >> sh) & 0xff;
+      const int r0 = i - 1;
+      // One cp.async group is committed per row.  Query blocks are requested 16 rows ahead and forward
+      // scores 2 rows ahead, so only the most recent group(s) may still be in flight.
+      if (i == 1) {
+        cp_async_wait_all();
+        qa_n0 = qst[0][0];
+        qa_n1 = qst[1][0];
+      } else if (MSK) cp_async_wait_group<1>();
+      else cp_async_wait_group<8>();
+      const int qa0 = qa_n0, qa1 = qa_n1;
       const uint4 pa = *reinterpret_cast<const uint4*>(profA + qa0 * W + lane * 16);
       const uint4 pb = *reinterpret_cast<const uint4*>(profB + qa1 * W + lane * 16);
+      qa_n0 = qst[0][i & 31];
+      qa_n1 = qst[1][i & 31];
       const uint32_t pwA[4] = {pa.x, pa.y, pa.z, pa.w};
       const uint32_t pwB[4] = {pb.x, pb.y, pb.z, pb.w};
       uint32_t fcur[2][8];
       if (MSK) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          const uint4* src = reinterpret_cast<const uint4*>(fst[h] + 32 * (i % 3));
+          const uint4 a = src[0], b = src[1];
+          fcur[h][0] = a.x; fcur[h][1] = a.y; fcur[h][2] = a.z; fcur[h][3] = a.w;
+          fcur[h][4] = b.x; fcur[h][5] = b.y; fcur[h][6] = b.z; fcur[h][7] = b.w;
+        }
+      }
+      {
+        // stage ahead: the next 16-row query block (once per 16 rows) and the forward scores of row i+2
+        const int blk = (r0 >> 4) + 2;  // blocks 0 and 1 were requested up front
+        const int newblk = ((r0 & 15) == 0) && r0 > 0;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) fcur[h][w] = fl[h][w];
-          const bool more = h ? (act1 && i < Lq[1]) : (act0 && i < Lq[0]);
-          if (more) {  // prefetch the forward scores of the next flow row (one row up in the forward matrix)
-            const int16_t* src = fp[h] - (int64_t)i * scs[h];
-            const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
-            fl[h][0] = a.x; fl[h][1] = a.y; fl[h][2] = a.z; fl[h][3] = a.w;
-            fl[h][4] = b.x; fl[h][5] = b.y; fl[h][6] = b.z; fl[h][7] = b.w;
+        for (int h = 0; h < 2; ++h) {
+          cp_async16(qst[h] + 16 * ((blk - 1) & 1), qp[h] + 16 * (blk - 1), newblk);
+          if (MSK) {
+            const int more = pid[h] >= 0 && (i + 2) <= Lq[h];
+            const int16_t* src = fp[h] - (int64_t)(s + 2) * nl * 16;
+            cp_async16(fst[h] + 32 * ((i + 2) % 3), src, more);
+            cp_async16(fst[h] + 32 * ((i + 2) % 3) + 16, src + nl * 8, more);
           }
         }
+        cp_async_commit();
       }
 
       uint32_t Xd = xl_hold, E = e_in, Mgl = mg_in;
-      uint32_t acc01 = 0, acc23 = 0, accM = 0;
-      uint32_t tbA[2], tbB[2], oA[8], oB[8];
-      uint32_t Mprev = 0, d5prev = 0;
+      uint32_t accM = 0;
+      uint32_t tbA[2] = {0, 0}, tbB[2] = {0, 0}, oA[8], oB[8];
+      uint32_t Mprev = 0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int k = c & 3;
         const uint32_t ssel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
         const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
         const uint32_t M = __viaddmax_s16x2(simp, Xd, FLOOR2);
-        uint32_t d5 = 0;
         if (MSK) {
           // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1); element 15-c of the forward chunk
           const int e = 15 - c;
           const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
           const uint32_t slack = __viaddmax_s16x2(fv, Xd, FLOOR2);
-          d5 = __vsub2(THR2, slack);  // sign set <=> slack > thr
+          bool ph, pl;  // thr >= slack
+          (void)__vibmax_s16x2(THR2, slack, &ph, &pl);
+          const uint32_t bit = 1u << (8 * (c & 1) + 7 - (c >> 1));
+          if (!pl) accM |= bit;
+          if (!ph) accM |= bit << 16;
         }
         Xd = Xp[c];
         uint32_t F, X;
         if (TBM) {
+          // VIMNMX.S16x2 returns the maximum and, per half, the predicate (a >= b): one instruction gives
+          // both the value and the traceback bit; ties keep the first operand (extension / M / max(M,E)).
           const uint32_t Eext = __vadd2(E, NGE2);
           const uint32_t Fext = __vadd2(Fs[c], nge[c]);
-          const uint32_t dE = __vsub2(Eext, Mgl);  // sign set <=> the open candidate wins strictly
-          E = __vmaxs2(Eext, Mgl);
-          const uint32_t dF = __vsub2(Fext, Mg[c]);
-          F = __vmaxs2(Fext, Mg[c]);
-          const uint32_t dS1 = __vsub2(M, E);  // sign set <=> E > M
-          const uint32_t t = __vmaxs2(M, E);
-          const uint32_t dS2 = __vsub2(t, F);  // sign set <=> F > max(M,E)
-          X = __vmaxs2(t, F);
-          const uint32_t pat = 0x01010101u << (7 - (c & 7));
-          acc01 = or_and(acc01, prmt(dS1, dS2, 0xFBD9u), pat);
-          acc23 = or_and(acc23, prmt(dE, dF, 0xFBD9u), pat);
-          if ((c & 7) == 7) {
-            tbA[c >> 3] = prmt(acc01, acc23, 0x5410u);
-            tbB[c >> 3] = prmt(acc01, acc23, 0x7632u);
-            acc01 = 0;
-            acc23 = 0;
-          }
+          bool eh, el, fh, fl_, sh1, sl1, sh2, sl2;
+          E = __vibmax_s16x2(Eext, Mgl, &eh, &el);          // !p <=> the open candidate wins strictly
+          F = __vibmax_s16x2(Fext, Mg[c], &fh, &fl_);
+          const uint32_t t = __vibmax_s16x2(M, E, &sh1, &sl1);  // !p <=> E > M
+          X = __vibmax_s16x2(t, F, &sh2, &sl2);              // !p <=> F > max(M,E)
+          const int w = c >> 3, b0 = 7 - (c & 7);
+          if (!sl1) tbA[w] |= 1u << b0;
+          if (!sl2) tbA[w] |= 1u << (8 + b0);
+          if (!el) tbA[w] |= 1u << (16 + b0);
+          if (!fl_) tbA[w] |= 1u << (24 + b0);
+          if (!sh1) tbB[w] |= 1u << b0;
+          if (!sh2) tbB[w] |= 1u << (8 + b0);
+          if (!eh) tbB[w] |= 1u << (16 + b0);
+          if (!fh) tbB[w] |= 1u << (24 + b0);
         } else {
           E = __viaddmax_s16x2(E, NGE2, Mgl);
           F = __viaddmax_s16x2(Fs[c], nge[c], Mg[c]);
@@ -382,10 +418,6 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             oB[c >> 1] = prmt(Mprev, M, 0x7632u);
           } else Mprev = M;
         }
-        if (MSK) {
-          if (c & 1) accM = or_and(accM, prmt(d5prev, d5, 0xFBD9u), 0x01010101u << (7 - (c >> 1)));
-          else d5prev = d5;
-        }
       }
       if (MSK) accM &= VM;
       xl_hold = xn;
@@ -393,26 +425,26 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       e_pub = E;
       mg_pub = Mgl;
       if (act0) {
-        if (TBM) *reinterpret_cast<uint2*>(tbp[0] + (int64_t)(i - 1) * tbs[0]) = make_uint2(tbA[0], tbA[1]);
+        if (TBM) *reinterpret_cast<uint2*>(tbp[0] + (int64_t)s * nl * 8) = make_uint2(tbA[0], tbA[1]);
         if (FST) {
-          uint4* d = reinterpret_cast<uint4*>(scp[0] + (int64_t)(i - 1) * scs[0]);
-          d[0] = make_uint4(oA[0], oA[1], oA[2], oA[3]);
-          d[1] = make_uint4(oA[4], oA[5], oA[6], oA[7]);
+          int16_t* d = scp[0] + (int64_t)s * nl * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(oA[0], oA[1], oA[2], oA[3]);
+          *reinterpret_cast<uint4*>(d + nl * 8) = make_uint4(oA[4], oA[5], oA[6], oA[7]);
         }
         if (MSK) {
-          *reinterpret_cast<uint16_t*>(mkp[0] + (int64_t)(i - 1) * mks[0]) = (uint16_t)(accM & 0xffffu);
+          *reinterpret_cast<uint16_t*>(mkp[0] + (int64_t)s * nl * 2) = (uint16_t)(accM & 0xffffu);
           cnt[0] += __popc(accM & 0xffffu);
         }
       }
       if (act1) {
-        if (TBM) *reinterpret_cast<uint2*>(tbp[1] + (int64_t)(i - 1) * tbs[1]) = make_uint2(tbB[0], tbB[1]);
+        if (TBM) *reinterpret_cast<uint2*>(tbp[1] + (int64_t)s * nl * 8) = make_uint2(tbB[0], tbB[1]);
         if (FST) {
-          uint4* d = reinterpret_cast<uint4*>(scp[1] + (int64_t)(i - 1) * scs[1]);
-          d[0] = make_uint4(oB[0], oB[1], oB[2], oB[3]);
-          d[1] = make_uint4(oB[4], oB[5], oB[6], oB[7]);
+          int16_t* d = scp[1] + (int64_t)s * nl * 16;
+          *reinterpret_cast<uint4*>(d) = make_uint4(oB[0], oB[1], oB[2], oB[3]);
+          *reinterpret_cast<uint4*>(d + nl * 8) = make_uint4(oB[4], oB[5], oB[6], oB[7]);
         }
         if (MSK) {
-          *reinterpret_cast<uint16_t*>(mkp[1] + (int64_t)(i - 1) * mks[1]) = (uint16_t)(accM >> 16);
+          *reinterpret_cast<uint16_t*>(mkp[1] + (int64_t)s * nl * 2) = (uint16_t)(accM >> 16);
           cnt[1] += __popc(accM >> 16);
         }
         // the shorter query of the couple ends first: keep its final row before later rows overwrite it
@@ -466,7 +498,8 @@ __global__ void __launch_bounds__(kPackedWarps * 32) packed_kernel(const PackedP
   const int sub_bytes = (A * (A + 1) + 15) / 16 * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * 32 * sizeof(int4)) + warp * 2 * A * 512;
+  uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kPackedStage;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kPackedStage)) + warp * 2 * A * 512;
   for (int x = threadIdx.x; x < A * (A + 1); x += blockDim.x) {
     const int a = x / (A + 1), b = x % (A + 1);
     s_sub[x] = (b < A) ? P.sub8[a * A + b] : (int8_t)-128;
@@ -477,7 +510,7 @@ __global__ void __launch_bounds__(kPackedWarps * 32) packed_kernel(const PackedP
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_tasks) break;
-    packed_task<TBM, FST, MSK>(P, (int)item, prof, red, s_sub, lane);
+    packed_task<TBM, FST, MSK>(P, (int)item, prof, red, stage, s_sub, lane);
   }
 }
 
