@@ -77,7 +77,6 @@ struct Batch {
   std::vector<uint8_t> fmt;       // per pair: 1 = packed kernels, 0 = int32 kernels
   std::vector<int32_t> tasks;     // n_tasks * 64 pair ids
   std::vector<int32_t> aoff;      // per sequence byte offset into the aligned arenas
-  std::vector<uint8_t> arena_f, arena_r;
   double packed_cells = 0;
   int64_t n_tasks = 0;
   double cells = 0;
@@ -101,8 +100,12 @@ struct aadp_ctx {
   DevBuf sub8, residues, seq_off, pair_q, pair_t, order[2], tb_off, sc_off, mask_off;
   DevBuf tb[2], scb[2], mask, fin_score[2], fin_kind[2], fin_k[2], counter, bbuf, thr, count, fscore[2];
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
-  DevBuf fmt, tasks, aoff, arena_f, arena_r;
+  DevBuf fmt, tasks, aoff, arena_f, arena_r, badflag;
   bool allow_packed = true;
+  // pinned host staging for metadata uploads (bump-allocated per upload)
+  uint8_t* pin = nullptr;
+  size_t pin_cap = 0, pin_used = 0;
+  int* pin_flag = nullptr;
   Batch b;
   int64_t launches = 0;
   int bb_rows = 0;
@@ -172,11 +175,29 @@ int launch_fill_k(aadp_ctx* c, FillParams& P, int tbm, int stm) {
   return launch_fill_t<K, 1, 2>(c, P);
 }
 
+// Builds the 16-byte aligned forward and reversed sequence arenas on the device and validates the
+// residue codes (submatrix.h:36-38 is undefined behaviour for letters outside the matrix).
+__global__ void arena_kernel(const uint8_t* __restrict__ res, const int64_t* __restrict__ seq_off,
+                             const int32_t* __restrict__ aoff, int64_t nseq, int A, uint8_t* __restrict__ af,
+                             uint8_t* __restrict__ ar, int* __restrict__ bad) {
+  for (int64_t sq = blockIdx.x; sq < nseq; sq += gridDim.x) {
+    const int64_t o = seq_off[sq];
+    const int L = (int)(seq_off[sq + 1] - o);
+    const int64_t d = aoff[sq];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+      const uint8_t v = res[o + i];
+      if (v >= A) *bad = 1;
+      af[d + i] = v;
+      ar[d + L - 1 - i] = v;
+    }
+  }
+}
+
 template <int TBM, int FST, int MSK>
 int launch_packed_t(aadp_ctx* c, PackedParams& P) {
   auto kern = packed_kernel<TBM, FST, MSK>;
   const int A = P.sc.A;
-  const size_t smem = (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + kPackedStage + 2 * A * 512);
+  const size_t smem = packed_smem_bytes(A, MSK);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
@@ -280,33 +301,6 @@ void build_tasks(aadp_ctx* c) {
   }
 }
 
-// 4-byte aligned copies of the sequences: forward order and reversed (the reverse fill reads its
-// flow order front to back). Zero padding behind the last sequence absorbs read-ahead.
-void build_arenas(aadp_ctx* c, const uint8_t* residues) {
-  Batch& b = c->b;
-  b.aoff.assign(b.nseq + 1, 0);
-  int64_t cur = 0, maxL = 0;
-  for (int64_t s = 0; s < b.nseq; ++s) {
-    b.aoff[s] = (int32_t)cur;
-    const int64_t L = b.seq_off[s + 1] - b.seq_off[s];
-    maxL = std::max(maxL, L);
-    cur += (L + 15) / 16 * 16;
-  }
-  const int64_t total = cur + maxL + 128;
-  b.arena_f.assign((size_t)total, 0);
-  b.arena_r.assign((size_t)total, 0);
-  for (int64_t s = 0; s < b.nseq; ++s) {
-    const int64_t L = b.seq_off[s + 1] - b.seq_off[s];
-    const uint8_t* src = residues + b.seq_off[s];
-    uint8_t* df = b.arena_f.data() + b.aoff[s];
-    uint8_t* dr = b.arena_r.data() + b.aoff[s];
-    for (int64_t i = 0; i < L; ++i) {
-      df[i] = src[i];
-      dr[i] = src[L - 1 - i];
-    }
-  }
-}
-
 int build_batch_meta(aadp_ctx* c, uint32_t what) {
   Batch& b = c->b;
   const int64_t np = b.npairs;
@@ -361,10 +355,29 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   return 0;
 }
 
+int pin_reserve(aadp_ctx* c, size_t bytes) {
+  c->pin_used = 0;
+  if (bytes <= c->pin_cap) return 0;
+  if (c->pin) cudaFreeHost(c->pin);
+  c->pin = nullptr;
+  c->pin_cap = 0;
+  const size_t want = bytes + bytes / 4 + 4096;
+  if (cudaHostAlloc((void**)&c->pin, want, cudaHostAllocDefault) != cudaSuccess) return fail("cudaHostAlloc failed");
+  c->pin_cap = want;
+  return 0;
+}
+
+// copy a host vector into the pinned pool and start its (truly asynchronous) upload
 template <class T>
-int upload_vec(DevBuf& d, const std::vector<T>& v, cudaStream_t s) {
-  if (d.reserve(std::max<size_t>(v.size() * sizeof(T), 16))) return 1;
-  if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v) {
+  const size_t bytes = v.size() * sizeof(T);
+  if (d.reserve(std::max<size_t>(bytes, 16))) return 1;
+  if (!bytes) return 0;
+  const size_t at = (c->pin_used + 63) / 64 * 64;
+  if (at + bytes > c->pin_cap) return fail("internal: pinned staging pool too small");
+  memcpy(c->pin + at, v.data(), bytes);
+  c->pin_used = at + bytes;
+  CK(cudaMemcpyAsync(d.p, c->pin + at, bytes, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
 
@@ -573,8 +586,10 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->sc_off, &c->mask_off, &c->tb[0], &c->tb[1], &c->scb[0], &c->scb[1], &c->mask, &c->fin_score[0],
                    &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
                    &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d,
-                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r};
+                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag};
   for (DevBuf* d : all) d->release();
+  if (c->pin) cudaFreeHost(c->pin);
+  if (c->pin_flag) cudaFreeHost(c->pin_flag);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -656,33 +671,51 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   b.pair_q.assign(pair_q, pair_q + npairs);
   b.pair_t.assign(pair_t, pair_t + npairs);
   const int64_t nres = seq_off[nseq];
-  for (int64_t i = 0; i < nres; ++i)
-    if (residues[i] >= c->sc.A) return fail("residue code outside the substitution alphabet");  // submatrix.h:36-38 is UB here
+  // aligned arena offsets (16-byte aligned sequences, zero padding absorbs read-ahead)
+  b.aoff.assign(nseq + 1, 0);
+  int64_t cur = 0, maxL = 0;
+  for (int64_t s2 = 0; s2 < nseq; ++s2) {
+    const int64_t L = seq_off[s2 + 1] - seq_off[s2];
+    if (L < 0) return fail("sequence offsets must be non-decreasing");
+    if (cur > 0x7fff0000LL) return fail("sequence arena too large");
+    b.aoff[s2] = (int32_t)cur;
+    maxL = std::max(maxL, L);
+    cur += (L + 15) / 16 * 16;
+  }
+  const size_t arena_bytes = (size_t)(cur + maxL + 128);
+  // 1. start the big transfer and the device-side arena build / validation first ...
+  if (!c->pin_flag && cudaHostAlloc((void**)&c->pin_flag, 64, cudaHostAllocDefault) != cudaSuccess) return fail("cudaHostAlloc failed");
+  if (pin_reserve(c, (size_t)(nseq + 1) * 12 + (size_t)npairs * (8 + 1 + 4 + 24 + 64 * 4 / 2 + 64) + 65536)) return 1;
+  if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
+  if (c->arena_f.reserve(arena_bytes) || c->arena_r.reserve(arena_bytes) || c->badflag.reserve(16)) return 1;
+  if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
+  if (upload_vec(c, c->seq_off, b.seq_off)) return 1;
+  if (upload_vec(c, c->aoff, b.aoff)) return 1;
+  CK(cudaMemsetAsync(c->arena_f.p, 0, arena_bytes, c->stream));
+  CK(cudaMemsetAsync(c->arena_r.p, 0, arena_bytes, c->stream));
+  CK(cudaMemsetAsync(c->badflag.p, 0, 16, c->stream));
+  if (nseq) {
+    const int grid = (int)std::min<int64_t>(nseq, 148 * 32);
+    arena_kernel<<<grid, 128, 0, c->stream>>>(c->residues.as<uint8_t>(), c->seq_off.as<int64_t>(), c->aoff.as<int32_t>(), nseq,
+                                             c->sc.A, c->arena_f.as<uint8_t>(), c->arena_r.as<uint8_t>(), c->badflag.as<int>());
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  // 2. ... and build the schedule on the host while they run
   if (build_batch_meta(c, what)) return 1;
   b.uploaded_what = what;
   b.ran_what = 0;
-  if (b.n_tasks) {
-    int64_t tot = 0;
-    for (int64_t s2 = 0; s2 < nseq; ++s2) tot += (seq_off[s2 + 1] - seq_off[s2] + 15) / 16 * 16;
-    if (tot > 0x7fff0000LL) return fail("sequence arena too large for the packed path");
-    build_arenas(c, residues);
-    if (upload_vec(c->arena_f, b.arena_f, c->stream)) return 1;
-    if (upload_vec(c->arena_r, b.arena_r, c->stream)) return 1;
-    if (upload_vec(c->aoff, b.aoff, c->stream)) return 1;
-    if (upload_vec(c->tasks, b.tasks, c->stream)) return 1;
-  }
-  if (upload_vec(c->fmt, b.fmt, c->stream)) return 1;
-  if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
-  if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
-  if (upload_vec(c->seq_off, b.seq_off, c->stream)) return 1;
-  if (upload_vec(c->pair_q, b.pair_q, c->stream)) return 1;
-  if (upload_vec(c->pair_t, b.pair_t, c->stream)) return 1;
-  if (upload_vec(c->order[0], b.order[0], c->stream)) return 1;
-  if (upload_vec(c->order[1], b.order[1], c->stream)) return 1;
-  if (upload_vec(c->tb_off, b.tb_off, c->stream)) return 1;
-  if (upload_vec(c->sc_off, b.sc_off, c->stream)) return 1;
-  if (upload_vec(c->mask_off, b.mask_off, c->stream)) return 1;
-  CK(cudaStreamSynchronize(c->stream));  // host vectors may be reused by the caller
+  if (upload_vec(c, c->tasks, b.tasks)) return 1;
+  if (upload_vec(c, c->fmt, b.fmt)) return 1;
+  if (upload_vec(c, c->pair_q, b.pair_q)) return 1;
+  if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
+  if (upload_vec(c, c->order[0], b.order[0])) return 1;
+  if (upload_vec(c, c->order[1], b.order[1])) return 1;
+  if (upload_vec(c, c->tb_off, b.tb_off)) return 1;
+  if (upload_vec(c, c->sc_off, b.sc_off)) return 1;
+  if (upload_vec(c, c->mask_off, b.mask_off)) return 1;
+  CK(cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers; the validation flag is back
+  if (*c->pin_flag) return fail("residue code outside the substitution alphabet");
   return 0;
 }
 

@@ -34,8 +34,12 @@ namespace aadp {
 constexpr int kNeg16 = -24000;    // "-infinity" seed of E/F chains (only ever meets boundary-sized values)
 constexpr int kFloor16 = -16000;  // clamp floor of M / slack
 constexpr int kPackedBound = 8000;  // |score| bound (integer units) a pair must satisfy to use this kernel
-constexpr int kPackedWarps = 2;   // warps per CTA
-constexpr int kPackedStage = 2048 + 6144;  // per-warp cp.async staging: query rings + forward-score chunks
+constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
+// per-warp cp.async staging: query rings (2 KB) + forward-score chunks (6 KB, reverse+mask pass only)
+__host__ __device__ constexpr int packed_stage_bytes(int msk) { return msk ? 2048 + 6144 : 2048; }
+__host__ __device__ inline size_t packed_smem_bytes(int A, int msk) {
+  return (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + packed_stage_bytes(msk) + 2 * A * 512);
+}
 
 struct PackedParams {
   Scoring sc;
@@ -491,15 +495,16 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 }
 
 template <int TBM, int FST, int MSK>
-__global__ void __launch_bounds__(kPackedWarps * 32) packed_kernel(const PackedParams P) {
+__global__ void __launch_bounds__(kPackedWarps * 32, MSK ? 8 : 9) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
   const int sub_bytes = (A * (A + 1) + 15) / 16 * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
-  uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kPackedStage;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kPackedStage)) + warp * 2 * A * 512;
+  constexpr int kStage = packed_stage_bytes(MSK);
+  uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kStage;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kStage)) + warp * 2 * A * 512;
   for (int x = threadIdx.x; x < A * (A + 1); x += blockDim.x) {
     const int a = x / (A + 1), b = x % (A + 1);
     s_sub[x] = (b < A) ? P.sub8[a * A + b] : (int8_t)-128;
