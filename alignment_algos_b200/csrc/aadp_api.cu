@@ -328,7 +328,7 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
     // |score| bound in integer units: matches + one end gap on each side
     const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
     const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
-                           c->sc.ge <= 512 && c->sc.gi <= 2048;
+                           c->sc.ge <= 400 && c->sc.gi <= 2048;
     b.fmt[p] = packed_ok ? 1 : 0;
     if (packed_ok) {
       b.packed_cells += (double)cells[p];
@@ -481,6 +481,7 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
   const bool packed = b.fmt[p] != 0;
   D.lay = make_layout(Lq, Lt, packed, dir);
+  D.bias = packed ? kBias16 : 0;
   D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
   D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
   if (h_score && packed && dir == 1 && !(b.ran_what & AADP_W_SCORES))

@@ -539,6 +539,7 @@ struct DenseParams {
   Scoring sc;
   int Lq, Lt, rev, repro_rev_bug;
   Layout lay;
+  int bias;  // packed kernels store biased scores
   int st_mode;
   const void* sc_blob; int64_t sc_off;
   const uint8_t* tb;  // packed traceback of this pair/direction (or null)
@@ -561,7 +562,7 @@ __global__ void dense_kernel(const DenseParams P) {
     const bool interior = a >= 1 && a <= P.Lq && b >= 1 && b <= P.Lt;
     int si = 0;
     if (interior) {
-      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + layout_sc_index(P.lay, a, b)];
+      if (P.st_mode == 1) si = ((const int16_t*)P.sc_blob)[P.sc_off + layout_sc_index(P.lay, a, b)] - P.bias;
       else if (P.st_mode == 2) si = ((const int32_t*)((const int16_t*)P.sc_blob + P.sc_off))[layout_sc_index(P.lay, a, b)];
       s = (float)si * inv;
       if (P.tb) {

@@ -28,12 +28,21 @@
 //   mask       reverse-flow coordinates [r][slot k] 2 bytes: byte (c&1), bit 7-(c>>1)
 #pragma once
 #include "aadp_kernels.cuh"
+#include <cuda_fp16.h>
 
 namespace aadp {
 
-constexpr int kNeg16 = -24000;    // "-infinity" seed of E/F chains (only ever meets boundary-sized values)
-constexpr int kFloor16 = -16000;  // clamp floor of M / slack
-constexpr int kPackedBound = 8000;  // |score| bound (integer units) a pair must satisfy to use this kernel
+// BIASED DOMAIN.  Every DP value v is held as v + kBias16 in an unsigned 16-bit half with
+//   1024 <= v + kBias16 < 0x7C00.
+// Two things follow.  (1) The halves are positive, normal fp16 bit patterns whose fp16 order equals
+// their integer order, so HSET2.GT (one instruction on the fp16 pipe, no predicates) yields a
+// 0xFFFF/0 mask per half for the traceback decisions.  (2) Adding a packed non-positive constant is
+// a plain 32-bit add (the low half always carries into the high half, which the constant
+// pre-compensates), so those adds can issue on the FMA pipe (IMAD.IADD) instead of the ALU pipe.
+constexpr int kBias16 = 21500;
+constexpr int kNeg16 = -20000;    // "-infinity" seed of E/F chains (only ever extended once)
+constexpr int kFloor16 = -13000;  // clamp floor of M / slack
+constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must satisfy to use this kernel
 constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
 // per-warp cp.async staging: query rings (2 KB) + forward-score chunks (6 KB, reverse+mask pass only)
 __host__ __device__ constexpr int packed_stage_bytes(int msk) { return msk ? 2048 + 6144 : 2048; }
@@ -71,9 +80,31 @@ struct PackedParams {
 };
 
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+// biased pack
+__device__ __forceinline__ uint32_t pkb(int lo, int hi) { return pk2(lo + kBias16, hi + kBias16); }
+// 32-bit addend that subtracts dlo from the low half and dhi from the high half (dlo,dhi >= 0) of a
+// biased pair: the low half borrows nothing (values >= 1024 > d), i.e. adding 65536-dlo always carries
+// into the high half, so the high constant is reduced by that carry.
+__device__ __forceinline__ uint32_t pkdec(int dlo, int dhi) {
+  const uint32_t lo = (uint32_t)(-dlo) & 0xffffu;
+  const uint32_t carry = dlo != 0 ? 1u : 0u;
+  return lo | (((uint32_t)(-dhi) - carry) << 16);
+}
+// packed add of a pkdec() constant: a single 32-bit integer add, written as a multiply-add so that it
+// issues on the FMA pipe (IMAD) and leaves the ALU pipe to the DPX min/max instructions
+__device__ __forceinline__ uint32_t addc(uint32_t x, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(x), "r"(c));
+  return d;
+}
+// 0xFFFF per half where a > b (biased halves are ordered like positive fp16 numbers): HSET2.GT
+__device__ __forceinline__ uint32_t gt_mask(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+}
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
 __device__ __forceinline__ int half16(uint32_t v, int h) { return h ? hi16(v) : lo16(v); }
+__device__ __forceinline__ int unb16(uint32_t v, int h) { return (int)((v >> (16 * h)) & 0xffffu) - kBias16; }
 // Asynchronous global->shared staging (LDGSTS): the prefetched bytes never occupy a register, so no
 // instruction waits on them until cp_async_wait() one or more rows later.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int cond) {
@@ -193,25 +224,26 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           g[h] = (S.insfree && j == Lt[h]) ? 0 : -ge;  // zero-penalty F chain in the last column
         }
       }
-      Xp[c] = pk2(x[0], x[1]);
-      Fs[c] = pk2(f[0], f[1]);
-      Mg[c] = pk2(m[0], m[1]);
-      nge[c] = pk2(g[0], g[1]);
+      Xp[c] = pkb(x[0], x[1]);
+      Fs[c] = pkb(f[0], f[1]);
+      Mg[c] = pkb(m[0], m[1]);
+      nge[c] = pkdec(-g[0], -g[1]);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int jl = off * 16 - sig[h];  // column left of register 0
       xh[h] = jl < 0 ? kFloor16 : (jl == 0 ? 0 : -(S.delfree ? 0 : gap_w(gi, ge, jl)));
     }
-    xl_hold = pk2(xh[0], xh[1]);
+    xl_hold = pkb(xh[0], xh[1]);
   }
   // injection at the segment's first lane: X(i,0) when register 0 is column 1, "-inf" when it is a pad
   const uint32_t inj_b_mask = (seg_start ? ((sig[0] == 0 ? 0x0000ffffu : 0u) | (sig[1] == 0 ? 0xffff0000u : 0u)) : 0u);
   const uint32_t inj_mask = seg_start ? 0xffffffffu : 0u;
-  const uint32_t NEG2 = pk2(kNeg16, kNeg16);
-  const uint32_t FLOOR2 = pk2(kFloor16, kFloor16);
-  const uint32_t NGE2 = pk2(-ge, -ge);
-  const uint32_t NGI2 = pk2(-gi, -gi);
+  const uint32_t NEG2 = pkb(kNeg16, kNeg16);
+  const uint32_t FLOOR2 = pkb(kFloor16, kFloor16);
+  const uint32_t NGE2 = pkdec(ge, ge);
+  const uint32_t NGI2 = pkdec(gi, gi);
+  const uint32_t NBIAS2 = pk2(-kBias16, -kBias16);
 
   // ---- per-half output bases (diagonal-major: the address of a step is base + step * stride)
   uint8_t* tbp[2] = {nullptr, nullptr};
@@ -240,9 +272,9 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float t = floorf(thr_f[h] * (float)(1 << S.scale_log2));  // slack (integer) > thr  <=>  slack > floor(thr)
-      ti[h] = (int)fminf(fmaxf(t, (float)kFloor16), 16000.f);
+      ti[h] = (int)fminf(fmaxf(t, (float)kFloor16), (float)kPackedBound);
     }
-    THR2 = pk2(ti[0], ti[1]);
+    THR2 = pkb(ti[0], ti[1]);
   }
 
   // ---- query residues: each lane stages its own rows in a private 32-byte ring per half
@@ -256,7 +288,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     cp_async16(qst[h] + 16, qp[h] + 16, 1);
   }
 
-  uint32_t x_pub = 0, e_pub = NEG2, mg_pub = NEG2;
+  uint32_t x_pub = FLOOR2, e_pub = NEG2, mg_pub = NEG2;
   if (MSK) {
     // rows 1 and 2 of this lane (steps off and off+1) -> buffers 1 and 2
 #pragma unroll
@@ -293,13 +325,13 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const int j = off * 16 + c + 1 - sig[h];
-      const int m = half16(Mg[c], h) + gi;  // M(Lq, j)
+      const int m = unb16(Mg[c], h) + gi;  // M(Lq, j)
       if (j >= 1 && j < Lt[h]) {
         const int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt[h] - j));
         if (v > r.rb_val) { r.rb_val = v; r.rb_k = j; }
       } else if (j == Lt[h]) {
         r.diag = m;
-        r.col = (Lq[h] >= 2) ? half16(Fs[c], h) + (S.insfree ? gi : 0) : kNeg32;
+        r.col = (Lq[h] >= 2) ? unb16(Fs[c], h) + (S.insfree ? gi : 0) : kNeg32;
       }
     }
     return r;
@@ -313,7 +345,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     {
       // X(i,0), dpmatrix.h:420-426; only the segment's first lane uses it
       const int b = (i <= 0) ? 0 : -(S.insfree ? 0 : gi + ge * (i - 1));
-      const uint32_t b2 = pk2(b, b);
+      const uint32_t b2 = pkb(b, b);
       const uint32_t inj = (b2 & inj_b_mask) | (FLOOR2 & ~inj_b_mask);
       xn = (xn & ~inj_mask) | (inj & inj_mask);
       e_in = (e_in & ~inj_mask) | (NEG2 & inj_mask);
@@ -366,8 +398,8 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       }
 
       uint32_t Xd = xl_hold, E = e_in, Mgl = mg_in;
-      uint32_t accM = 0;
-      uint32_t tbA[2] = {0, 0}, tbB[2] = {0, 0}, oA[8], oB[8];
+      uint32_t accM = 0, accS1 = 0, accS2 = 0, accE = 0, accF = 0;  // flags: pair A in bits 0..15, pair B in 16..31
+      uint32_t oA[8], oB[8];
       uint32_t Mprev = 0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -376,43 +408,33 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
         const uint32_t M = __viaddmax_s16x2(simp, Xd, FLOOR2);
         if (MSK) {
-          // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1); element 15-c of the forward chunk
+          // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
+          // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
           const int e = 15 - c;
           const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
-          const uint32_t slack = __viaddmax_s16x2(fv, Xd, FLOOR2);
-          bool ph, pl;  // thr >= slack
-          (void)__vibmax_s16x2(THR2, slack, &ph, &pl);
-          const uint32_t bit = 1u << (8 * (c & 1) + 7 - (c >> 1));
-          if (!pl) accM |= bit;
-          if (!ph) accM |= bit << 16;
+          const uint32_t slack = __viaddmax_s16x2(fv, __vadd2(Xd, NBIAS2), FLOOR2);  // Xd may be below the bias: true packed add
+          accM |= gt_mask(slack, THR2) & (0x00010001u << (8 * (c & 1) + 7 - (c >> 1)));
         }
         Xd = Xp[c];
         uint32_t F, X;
         if (TBM) {
-          // VIMNMX.S16x2 returns the maximum and, per half, the predicate (a >= b): one instruction gives
-          // both the value and the traceback bit; ties keep the first operand (extension / M / max(M,E)).
-          const uint32_t Eext = __vadd2(E, NGE2);
-          const uint32_t Fext = __vadd2(Fs[c], nge[c]);
-          bool eh, el, fh, fl_, sh1, sl1, sh2, sl2;
-          E = __vibmax_s16x2(Eext, Mgl, &eh, &el);          // !p <=> the open candidate wins strictly
-          F = __vibmax_s16x2(Fext, Mg[c], &fh, &fl_);
-          const uint32_t t = __vibmax_s16x2(M, E, &sh1, &sl1);  // !p <=> E > M
-          X = __vibmax_s16x2(t, F, &sh2, &sl2);              // !p <=> F > max(M,E)
-          const int w = c >> 3, b0 = 7 - (c & 7);
-          if (!sl1) tbA[w] |= 1u << b0;
-          if (!sl2) tbA[w] |= 1u << (8 + b0);
-          if (!el) tbA[w] |= 1u << (16 + b0);
-          if (!fl_) tbA[w] |= 1u << (24 + b0);
-          if (!sh1) tbB[w] |= 1u << b0;
-          if (!sh2) tbB[w] |= 1u << (8 + b0);
-          if (!eh) tbB[w] |= 1u << (16 + b0);
-          if (!fh) tbB[w] |= 1u << (24 + b0);
+          const uint32_t pat = 0x00010001u << (8 * (c >> 3) + 7 - (c & 7));
+          const uint32_t Eext = addc(E, NGE2);
+          const uint32_t Fext = addc(Fs[c], nge[c]);
+          accE |= gt_mask(Mgl, Eext) & pat;     // the open candidate wins strictly
+          E = __vmaxs2(Eext, Mgl);
+          accF |= gt_mask(Mg[c], Fext) & pat;
+          F = __vmaxs2(Fext, Mg[c]);
+          accS1 |= gt_mask(E, M) & pat;         // E > M
+          const uint32_t t = __vmaxs2(M, E);
+          accS2 |= gt_mask(F, t) & pat;         // F > max(M,E)
+          X = __vmaxs2(t, F);
         } else {
-          E = __viaddmax_s16x2(E, NGE2, Mgl);
-          F = __viaddmax_s16x2(Fs[c], nge[c], Mg[c]);
+          E = __viaddmax_s16x2(E, pk2(-ge, -ge), Mgl);
+          F = __vmaxs2(addc(Fs[c], nge[c]), Mg[c]);
           X = __vimax3_s16x2(M, E, F);
         }
-        Mgl = __vadd2(M, NGI2);
+        Mgl = addc(M, NGI2);
         Xp[c] = X;
         Fs[c] = F;
         Mg[c] = Mgl;
@@ -422,6 +444,16 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             oB[c >> 1] = prmt(Mprev, M, 0x7632u);
           } else Mprev = M;
         }
+      }
+      uint32_t tbA[2], tbB[2];
+      if (TBM) {
+        // flag words -> traceback words: byte p of word w = plane p of cells 8w..8w+7
+        const uint32_t s01a = prmt(accS1, accS2, 0x5140u), s23a = prmt(accE, accF, 0x5140u);  // bytes 0,1 of each (pair A)
+        const uint32_t s01b = prmt(accS1, accS2, 0x7362u), s23b = prmt(accE, accF, 0x7362u);  // bytes 2,3 of each (pair B)
+        tbA[0] = prmt(s01a, s23a, 0x5410u);
+        tbA[1] = prmt(s01a, s23a, 0x7632u);
+        tbB[0] = prmt(s01b, s23b, 0x5410u);
+        tbB[1] = prmt(s01b, s23b, 0x7632u);
       }
       if (MSK) accM &= VM;
       xl_hold = xn;
