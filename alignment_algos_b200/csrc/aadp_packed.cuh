@@ -97,9 +97,14 @@ __device__ __forceinline__ uint32_t addc(uint32_t x, uint32_t c) {
   asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(x), "r"(c));
   return d;
 }
-// 0xFFFF per half where a > b (biased halves are ordered like positive fp16 numbers): HSET2.GT
-__device__ __forceinline__ uint32_t gt_mask(uint32_t a, uint32_t b) {
-  return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+// fp16x2 difference a - b of two biased pairs (HADD2 with a negated operand, on the fp16/FMA-lite pipe):
+// only its SIGN bits (bit 15 / bit 31) are used -- set exactly where a < b, because the biased halves
+// are positive fp16 bit patterns ordered like the integers and an fp16 difference never rounds across 0.
+// Measured on B200 (profiles/microbench/pipes.cu): HSET2, PRMT and VIADDMNMX are half-rate on the ALU
+// pipe the VIMNMX chain lives on, HADD2 / VIADD.16x2 run on a different pipe.
+__device__ __forceinline__ uint32_t lt_sign(uint32_t a, uint32_t b) {
+  const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&d);
 }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return ((int)v) >> 16; }
@@ -398,9 +403,9 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       }
 
       uint32_t Xd = xl_hold, E = e_in, Mgl = mg_in;
-      uint32_t accM = 0, accS1 = 0, accS2 = 0, accE = 0, accF = 0;  // flags: pair A in bits 0..15, pair B in 16..31
-      uint32_t oA[8], oB[8];
-      uint32_t Mprev = 0;
+      uint32_t accM = 0, acc01 = 0, acc23 = 0;
+      uint32_t tbA[2], tbB[2], oA[8], oB[8];
+      uint32_t Mprev = 0, d5prev = 0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int k = c & 3;
@@ -413,22 +418,34 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           const int e = 15 - c;
           const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
           const uint32_t slack = __viaddmax_s16x2(fv, __vadd2(Xd, NBIAS2), FLOOR2);  // Xd may be below the bias: true packed add
-          accM |= gt_mask(slack, THR2) & (0x00010001u << (8 * (c & 1) + 7 - (c >> 1)));
+          const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
+          // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
+          if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
+          else d5prev = d5;
         }
         Xd = Xp[c];
         uint32_t F, X;
         if (TBM) {
-          const uint32_t pat = 0x00010001u << (8 * (c >> 3) + 7 - (c & 7));
           const uint32_t Eext = addc(E, NGE2);
           const uint32_t Fext = addc(Fs[c], nge[c]);
-          accE |= gt_mask(Mgl, Eext) & pat;     // the open candidate wins strictly
+          const uint32_t dE = lt_sign(Eext, Mgl);   // the open candidate wins strictly
           E = __vmaxs2(Eext, Mgl);
-          accF |= gt_mask(Mg[c], Fext) & pat;
+          const uint32_t dF = lt_sign(Fext, Mg[c]);
           F = __vmaxs2(Fext, Mg[c]);
-          accS1 |= gt_mask(E, M) & pat;         // E > M
+          const uint32_t dS1 = lt_sign(M, E);       // E > M
           const uint32_t t = __vmaxs2(M, E);
-          accS2 |= gt_mask(F, t) & pat;         // F > max(M,E)
+          const uint32_t dS2 = lt_sign(t, F);       // F > max(M,E)
           X = __vmaxs2(t, F);
+          // PRMT with sign replication turns four sign bits into four 0xFF/0x00 bytes [A.x, A.y, B.x, B.y]
+          const uint32_t pat = 0x01010101u << (7 - (c & 7));
+          acc01 |= prmt(dS1, dS2, 0xFBD9u) & pat;
+          acc23 |= prmt(dE, dF, 0xFBD9u) & pat;
+          if ((c & 7) == 7) {
+            tbA[c >> 3] = prmt(acc01, acc23, 0x5410u);  // planes selE, selF, eopen, fopen of pair A
+            tbB[c >> 3] = prmt(acc01, acc23, 0x7632u);
+            acc01 = 0;
+            acc23 = 0;
+          }
         } else {
           E = __viaddmax_s16x2(E, pk2(-ge, -ge), Mgl);
           F = __vmaxs2(addc(Fs[c], nge[c]), Mg[c]);
@@ -444,16 +461,6 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             oB[c >> 1] = prmt(Mprev, M, 0x7632u);
           } else Mprev = M;
         }
-      }
-      uint32_t tbA[2], tbB[2];
-      if (TBM) {
-        // flag words -> traceback words: byte p of word w = plane p of cells 8w..8w+7
-        const uint32_t s01a = prmt(accS1, accS2, 0x5140u), s23a = prmt(accE, accF, 0x5140u);  // bytes 0,1 of each (pair A)
-        const uint32_t s01b = prmt(accS1, accS2, 0x7362u), s23b = prmt(accE, accF, 0x7362u);  // bytes 2,3 of each (pair B)
-        tbA[0] = prmt(s01a, s23a, 0x5410u);
-        tbA[1] = prmt(s01a, s23a, 0x7632u);
-        tbB[0] = prmt(s01b, s23b, 0x5410u);
-        tbB[1] = prmt(s01b, s23b, 0x7632u);
       }
       if (MSK) accM &= VM;
       xl_hold = xn;
