@@ -411,13 +411,15 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         const int k = c & 3;
         const uint32_t ssel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
         const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
-        const uint32_t M = __viaddmax_s16x2(simp, Xd, FLOOR2);
+        // plain packed add (VIADD.16x2, off the ALU pipe): no clamp is needed -- real cells stay far above the
+        // floor and pad columns only drift down by ge per row (bounded by the host-side score bound)
+        const uint32_t M = __vadd2(simp, Xd);
         if (MSK) {
           // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
           // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
           const int e = 15 - c;
           const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
-          const uint32_t slack = __viaddmax_s16x2(fv, __vadd2(Xd, NBIAS2), FLOOR2);  // Xd may be below the bias: true packed add
+          const uint32_t slack = __vadd2(fv, __vadd2(Xd, NBIAS2));  // Xd may be below the bias: true packed adds
           const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
           // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
           if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
