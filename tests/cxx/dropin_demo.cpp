@@ -1,0 +1,90 @@
+// tests/cxx/dropin_demo.cpp -- one source, two builds:
+//   dropin_demo : compiled against include/hmap2/ (this repo; the fill runs on the GPU via libaadp.so)
+//   ref_demo    : compiled against /root/reference (the unmodified reference headers + sources, CPU)
+// It follows the reference driver aa_ali.cpp:63-90 (sequences -> BlosumMatrix -> AASubstitutionEval ->
+// DPMatrix -> Optimal -> AlignmentSet) and dumps every DPCell plus the optimal alignment, so the
+// two builds can be compared byte for byte (tests/test_cxx_dropin.py).
+//
+//   usage: demo <matrix file> <align_type 0..4> <gi> <ge> <query letters> <template letters>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "aa_seq.h"
+#include "aasubalib.h"
+#include "alib.h"
+#include "alignment.h"
+#include "dpmatrix.h"
+#include "optimal.h"
+#include "submatrix.h"
+#ifdef AADP_HMAP2_DPMATRIX_H
+#include "optimal_rev.h"  // abstract (un-instantiable) in the reference: optimal_rev.h:29-30
+#endif
+
+typedef AASubstitutionEval<AASequence, AASequence> AAEval;
+typedef DPMatrix<AASequence, AASequence, AAEval> Matrix;
+
+static void dump(const char* tag, const Matrix& m) {
+  for (int i = 0; i < m.getQuerySize(); ++i)
+    for (int j = 0; j < m.getTemplateSize(); ++j) {
+      const DPCell* c = m.getCell(i, j);
+      std::printf("%s %d %d %.6g %d %d %.6g\n", tag, i, j, c->score, c->prev_query_idx, c->prev_template_idx, m.getSim(i, j));
+    }
+}
+
+int main(int argc, char** argv) {
+  if (argc != 7) {
+    std::fprintf(stderr, "usage: %s matrix align_type gi ge query template\n", argv[0]);
+    return 2;
+  }
+  try {
+    AliParams params;
+    params.submatrix_fn = argv[1];
+    params.align_type = static_cast<align_t>(std::atoi(argv[2]));
+    params.gap_init_penalty = (float)std::atof(argv[3]);
+    params.gap_extn_penalty = (float)std::atof(argv[4]);
+    AASequence query, templ;
+    query.append(std::string("^") + argv[5] + "$");
+    templ.append(std::string("^") + argv[6] + "$");
+    BlosumMatrix blosum(params.submatrix_fn.c_str());
+    AAEval eval(params, blosum);
+
+    Matrix forward(query, templ, eval, fwd, params.align_type);
+    dump("F", forward);
+    Matrix reverse(query, templ, eval, rev, params.align_type);
+    dump("R", reverse);
+
+    Optimal<AASequence, AASequence, AAEval> opt(params.align_type);
+    AlignmentSet<AASequence, AASequence, AAEval> alignments(forward, opt);
+    std::printf("OPT score %.6g identity %.6g pairs", alignments[0].score, alignments[0].identity);
+    for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = alignments[0].begin();
+         it != alignments[0].end(); ++it)
+      std::printf(" %d:%d", it->query_idx(), it->template_idx());
+    std::printf("\n");
+#ifdef AADP_HMAP2_DPMATRIX_H
+    // extras of this build: reverse traceback and the near-optimal cell set
+    try {
+      Optimal_Rev<AASequence, AASequence, AAEval> ropt(params.align_type);
+      AlignmentSet<AASequence, AASequence, AAEval> ra(reverse, ropt);
+      std::printf("#REV score %.6g pairs", ra[0].score);
+      for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = ra[0].begin(); it != ra[0].end(); ++it)
+        std::printf(" %d:%d", it->query_idx(), it->template_idx());
+      std::printf("\n");
+    } catch (std::string& e) {
+      std::printf("#REV error %s\n", e.c_str());
+    }
+    if (params.align_type != local) {
+      float thr = 0.f;
+      const std::vector<unsigned char>& cells = forward.nearOptimalCells(0.05f, &thr);
+      long n = 0;
+      for (size_t k = 0; k < cells.size(); ++k) n += cells[k];
+      std::printf("#NEAROPT delta 0.05 threshold %.6g cells %ld\n", thr, n);
+    }
+#endif
+  } catch (std::string& e) {
+    std::printf("ERROR %s\n", e.c_str());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,94 @@
+"""The C++ drop-in boundary: one demo source (tests/cxx/dropin_demo.cpp, shaped like the reference
+driver aa_ali.cpp:63-90) is compiled against this repo's include/hmap2 headers (GPU fill) and against
+the unmodified reference headers (CPU).  Their DPCell dumps and optimal alignments must be identical."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, po, MODES, MODE_NAMES
+
+CXX = os.path.join(ROOT, "tests", "cxx")
+DEMO = os.path.join(CXX, "dropin_demo")
+REF_DEMO = os.path.join(CXX, "ref_demo")
+MATRIX = os.path.join(ROOT, "alignment_algos_b200", "data", "BLOSUM62")
+ALPHA = "ARNDCQEGHILKMFPSTWYVBZX*"
+
+
+def _letters(codes):
+    return "".join(ALPHA[c] for c in codes)
+
+
+def _run(binary, at, gi, ge, q, t):
+    out = subprocess.run([binary, MATRIX, str(at), str(gi), str(ge), _letters(q), _letters(t)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return out.stdout.splitlines()
+
+
+def _expected_lines(O, q, t, sub):
+    """What the demo must print, from the oracle."""
+    lines = []
+    sim = O.sim(q, t)
+    res = {}
+    for d, tag in ((po.FWD, "F"), (po.REV, "R")):
+        s, pq, pt = O.fill(q, t, d, True, fast=True)
+        res[tag] = (s, pq, pt)
+        for i in range(s.shape[0]):
+            for j in range(s.shape[1]):
+                lines.append("%s %d %d %.6g %d %d %.6g" % (tag, i, j, s[i, j], pq[i, j], pt[i, j], sim[i, j]))
+    return lines, res
+
+
+def test_headers_compile_and_reference_demo_matches_oracle(blosum):
+    subprocess.check_call(["make", "-C", CXX, "all"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert os.path.exists(DEMO)
+    if not os.path.exists(REF_DEMO):
+        pytest.skip("reference demo not built")
+    _, M = blosum
+    rng = np.random.default_rng(21)
+    for at in (po.GLOBAL, po.SEMI_LOCAL, po.LOCAL):
+        q = rng.integers(0, 20, 23).astype(np.uint8)
+        t = rng.integers(0, 20, 31).astype(np.uint8)
+        O = po.Oracle(M, 12, 1, at)
+        want, _ = _expected_lines(O, q, t, M)
+        got = [l for l in _run(REF_DEMO, at, 12, 1, q, t) if l[:2] in ("F ", "R ")]
+        assert got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("at", MODES, ids=[MODE_NAMES[m] for m in MODES])
+def test_gpu_dropin_equals_reference_build(blosum, at):
+    _, M = blosum
+    rng = np.random.default_rng(40 + at)
+    for (gi, ge, Lq, Lt) in [(12, 1, 37, 52), (3, 1, 64, 20), (10.5, 0.25, 18, 18), (12, 1, 1, 9), (12, 1, 300, 270)]:
+        q = rng.integers(0, 20, Lq).astype(np.uint8)
+        t = rng.integers(0, 20, Lt).astype(np.uint8)
+        got = _run(DEMO, at, gi, ge, q, t)
+        core = [l for l in got if not l.startswith("#")]
+        O = po.Oracle(M, gi, ge, at)
+        want, res = _expected_lines(O, q, t, M)
+        assert core[:len(want)] == want
+        if os.path.exists(REF_DEMO) and Lq * Lt < 5000:
+            ref = [l for l in _run(REF_DEMO, at, gi, ge, q, t) if not l.startswith("#")]
+            assert core == ref, "GPU drop-in build and reference build print different results"
+        # optimal alignment line against the oracle traceback
+        F, fq, ft = res["F"]
+        rc, pairs, sc = O.optimal(F, fq, ft, po.FWD)
+        opt = [l for l in core if l.startswith("OPT ")]
+        assert len(opt) == 1
+        assert opt[0].split(" pairs ")[1].split() == ["%d:%d" % (a, b) for a, b in pairs]
+        # extras: reverse traceback and near-optimal cell count
+        R, rq, rt = res["R"]
+        rrc, rpairs, rsc = O.optimal(R, rq, rt, po.REV)
+        rev = [l for l in got if l.startswith("#REV")][0]
+        if rrc == 0:
+            assert rev.split(" pairs ")[1].split() == ["%d:%d" % (a, b) for a, b in rpairs]
+        else:
+            assert "Illegal alignment start pair" in rev
+        if at != po.LOCAL:
+            thr = O.threshold(float(F[-1, -1]), 0.05)
+            mask, cnt = O.nearopt_mask(F, R, O.sim(q, t), thr)
+            no = [l for l in got if l.startswith("#NEAROPT")][0].split()
+            assert int(no[-1]) == cnt and float(no[4]) == pytest.approx(thr, rel=1e-6)
