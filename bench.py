@@ -327,6 +327,14 @@ def main():
     dom_gcups = dom_cells / (dom_ms * 1e-3) / 1e9
     kernel_share = {k: v[0] / sum(x[0] for x in by.values()) for k, v in by.items()} if by else {}
 
+    # measured DRAM traffic of that kernel (one ncu --set full capture, profiles/), scaled to this launch
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom[0] in tj["kernels"]:
+            traffic = tj["kernels"][dom[0]]["bytes_per_cell_update"] * dom_cells
+    except Exception:
+        traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -342,7 +350,8 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches_step * args.steps),
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per cell update) x cell updates of this launch",
                      "bytes_per_cell_update": bytes_per_cu, "ms_per_launch": dom_ms},
         "issue_roofline": {"kernel": dom[0], "i_alg": i_alg, "lane_ops_per_s": lane_peak, "ceiling_gcups": lane_peak / i_alg / 1e9,
                            "achieved_gcups": dom_gcups, "frac": dom_gcups / (lane_peak / i_alg / 1e9), "sm_mhz": clk / 1e6},
