@@ -74,7 +74,8 @@ struct Batch {
   int max_Lq = 0, max_Lt = 0;
   int st_mode = 1;  // 1 = int16 score storage possible, 2 = int32
   // packed (int16x2) path
-  std::vector<uint8_t> fmt;       // per pair: 1 = packed kernels, 0 = int32 kernels
+  std::vector<uint8_t> fmt;       // per pair: 0 = int32 kernels, 1 = packed kernels, 2 = multi-CTA wavefront (long pair)
+  std::vector<int32_t> wave_pairs;
   std::vector<int32_t> tasks;     // n_tasks * 64 pair ids
   std::vector<int32_t> aoff;      // per sequence byte offset into the aligned arenas
   double packed_cells = 0;
@@ -102,6 +103,9 @@ struct aadp_ctx {
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
   DevBuf fmt, tasks, aoff, arena_f, arena_r, badflag;
   bool allow_packed = true;
+  bool allow_wave = true;
+  int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
+  DevBuf wave_bb, wave_ready, wave_part;
   // pinned host staging for metadata uploads (bump-allocated per upload)
   uint8_t* pin = nullptr;
   size_t pin_cap = 0, pin_used = 0;
@@ -230,6 +234,38 @@ int launch_packed(aadp_ctx* c, PackedParams& P, int tbm, int fst, int msk) {
   }
 }
 
+template <int TBM, int STM>
+int launch_wave_t(aadp_ctx* c, FillParams& Pf, FillParams& Pr, int ndirs, int nst) {
+  auto kern = wave_kernel<8, TBM, STM>;
+  const int A = Pf.sc.A;
+  size_t smem = (size_t)((A * A + 15) / 16 * 16) + kQRing + (size_t)A * 32 * 8;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  const int grid = ndirs * nst;
+  if (occ < 1 || grid > occ * c->num_sms) return fail("wavefront kernel: stripes of this pair cannot all be resident");
+  char nm[64];
+  snprintf(nm, sizeof nm, "wave_kernel<K=8,TB=%d,ST=%d>x%d", TBM, STM, ndirs);
+  c->prof_begin(nm, Pf.cells_hint * ndirs);
+  int nd = ndirs;
+  void* args[] = {(void*)&Pf, (void*)&Pr, (void*)&nd};
+  CK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(32), args, smem, c->stream));
+  c->prof_end();
+  c->launches++;
+  return 0;
+}
+
+int launch_wave(aadp_ctx* c, FillParams& Pf, FillParams& Pr, int ndirs, int nst, int tbm, int stm) {
+  if (tbm == 0) {
+    if (stm == 0) return launch_wave_t<0, 0>(c, Pf, Pr, ndirs, nst);
+    if (stm == 1) return launch_wave_t<0, 1>(c, Pf, Pr, ndirs, nst);
+    return launch_wave_t<0, 2>(c, Pf, Pr, ndirs, nst);
+  }
+  if (stm == 0) return launch_wave_t<1, 0>(c, Pf, Pr, ndirs, nst);
+  if (stm == 1) return launch_wave_t<1, 1>(c, Pf, Pr, ndirs, nst);
+  return launch_wave_t<1, 2>(c, Pf, Pr, ndirs, nst);
+}
+
 __global__ void scores_to_float_kernel(const int32_t* fin, float* out, int64_t n, int scale_log2) {
   const float inv = 1.f / (float)(1 << scale_log2);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -253,7 +289,7 @@ void build_tasks(aadp_ctx* c) {
   struct Item { int32_t p; int n; int Lq; };
   std::vector<Item> items;
   for (int64_t p = 0; p < b.npairs; ++p) {
-    if (!b.fmt[p]) continue;
+    if (b.fmt[p] != 1) continue;
     const int qs = b.pair_q[p], ts = b.pair_t[p];
     const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
     items.push_back({(int32_t)p, (Lt + 15) / 16, Lq});
@@ -313,6 +349,7 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   b.cells = 0;
   b.bucket_cells[0] = b.bucket_cells[1] = 0;
   b.fmt.assign(np, 0);
+  b.wave_pairs.clear();
   b.packed_cells = 0;
   std::vector<int64_t> cells(np);
   int64_t bound = 0;
@@ -329,9 +366,15 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
     const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
     const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
                            c->sc.ge <= 400 && c->sc.gi <= 2048;
-    b.fmt[p] = packed_ok ? 1 : 0;
+    // long pairs: one CTA per 256-column stripe, all stripes of both directions co-resident
+    const bool wave_ok = !packed_ok && c->allow_wave && Lq >= 1 && Lt > 512 && Lq * Lt >= (int64_t)c->wave_min_cells &&
+                         2 * ((Lt + 255) / 256) <= (int64_t)c->num_sms * 8;
+    b.fmt[p] = packed_ok ? 1 : (wave_ok ? 2 : 0);
     if (packed_ok) {
       b.packed_cells += (double)cells[p];
+    } else if (wave_ok) {
+      b.wave_pairs.push_back((int32_t)p);
+      bound = std::max(bound, bd);
     } else {
       b.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
       b.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cells[p];
@@ -344,8 +387,8 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   for (int64_t p = 0; p < np; ++p) {  // product offsets (scores in int16 units; 16-byte aligned per pair)
     const int qs = b.pair_q[p], ts = b.pair_t[p];
     const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
-    const Layout L = make_layout((int)Lq, (int)Lt, b.fmt[p], 0);
-    const int64_t units = (b.fmt[p] || b.st_mode == 1) ? 1 : 2;
+    const Layout L = make_layout((int)Lq, (int)Lt, b.fmt[p] == 1, 0);
+    const int64_t units = (b.fmt[p] == 1 || b.st_mode == 1) ? 1 : 2;
     b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? round_up64(layout_tb_bytes(L), 16) : 0);
     b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? round_up64(layout_sc_elems(L) * units, 8) : 0);
     b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? round_up64(layout_mask_words(L), 4) : 0);
@@ -387,7 +430,7 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
   const int tbm = (what & AADP_W_TB) ? 1 : 0;
   const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
   const int64_t np = b.npairs;
-  const bool have_v1 = !b.order[0].empty() || !b.order[1].empty();
+  const bool have_v1 = !b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty();
   // the packed reverse pass fuses the mask and needs no reverse score matrix of its own
   const bool need_blob = (what & AADP_W_SCORES) || ((what & AADP_W_MASK) && (dir == 0 || have_v1));
   if (c->fin_score[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
@@ -457,6 +500,57 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
   return 0;
 }
 
+// Long pairs: one cooperative launch per pair, covering both directions when both are requested.
+int run_wave_pairs(aadp_ctx* c, uint32_t what) {
+  Batch& b = c->b;
+  if (b.wave_pairs.empty()) return 0;
+  const int tbm = (what & AADP_W_TB) ? 1 : 0;
+  const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
+  for (int32_t p : b.wave_pairs) {
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+    const int nst = (Lt + 255) / 256;
+    const int bb_rows = Lq + 2;
+    int dirs[2], nd = 0;
+    if (what & AADP_W_FWD) dirs[nd++] = 0;
+    if (what & AADP_W_REV) dirs[nd++] = 1;
+    if (c->wave_bb.reserve((size_t)nd * nst * bb_rows * sizeof(int4))) return 1;
+    if (c->wave_ready.reserve((size_t)nd * nst * sizeof(int) + 16)) return 1;
+    if (c->wave_part.reserve((size_t)nd * nst * sizeof(int4))) return 1;
+    CK(cudaMemsetAsync(c->wave_ready.p, 0, (size_t)nd * nst * sizeof(int), c->stream));
+    FillParams P[2];
+    for (int k = 0; k < nd; ++k) {
+      const int dir = dirs[k];
+      FillParams& Q = P[k];
+      Q = FillParams{};
+      Q.sc = c->sc;
+      Q.sub8 = c->sub8.as<int8_t>();
+      Q.residues = c->residues.as<uint8_t>();
+      Q.seq_off = c->seq_off.as<int64_t>();
+      Q.pair_q = c->pair_q.as<int32_t>();
+      Q.pair_t = c->pair_t.as<int32_t>();
+      Q.rev = dir;
+      Q.tb = tbm ? c->tb[dir].as<uint8_t>() : nullptr;
+      Q.tb_off = c->tb_off.as<int64_t>();
+      Q.sc_blob = stm ? c->scb[dir].p : nullptr;
+      Q.sc_off = c->sc_off.as<int64_t>();
+      Q.fin_score = c->fin_score[dir].as<int32_t>();
+      Q.fin_kind = c->fin_kind[dir].as<int32_t>();
+      Q.fin_k = c->fin_k[dir].as<int32_t>();
+      Q.bb_rows = bb_rows;
+      Q.cells_hint = (double)Lq * Lt;
+      Q.wave_pair = p;
+      Q.wave_nstripes = nst;
+      Q.wave_bb = c->wave_bb.as<int4>() + (size_t)k * nst * bb_rows;
+      Q.wave_ready = c->wave_ready.as<int>() + (size_t)k * nst;
+      Q.wave_part = c->wave_part.as<int4>() + (size_t)k * nst;
+    }
+    if (nd == 1) P[1] = P[0];
+    if (launch_wave(c, P[0], P[1], nd, nst, tbm, stm)) return 1;
+  }
+  return 0;
+}
+
 int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, int32_t* h_pt) {
   if (!h_score && !h_pq && !h_pt) return 0;
   Batch& b = c->b;
@@ -479,7 +573,7 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   D.Lt = Lt;
   D.rev = dir;
   D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
-  const bool packed = b.fmt[p] != 0;
+  const bool packed = b.fmt[p] == 1;
   D.lay = make_layout(Lq, Lt, packed, dir);
   D.bias = packed ? kBias16 : 0;
   D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
@@ -517,7 +611,7 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
   const int sz2 = Lt + 2;
   const int64_t mws = mask_row_words(Lt);
-  const Layout L = make_layout(Lq, Lt, b.fmt[p], 1);
+  const Layout L = make_layout(Lq, Lt, b.fmt[p] == 1, 1);
   const int64_t nwords = layout_mask_words(L);
   std::vector<uint32_t> bits((size_t)std::max<int64_t>(nwords, 1));
   if (nwords > 0) {
@@ -525,7 +619,7 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
     CK(cudaStreamSynchronize(c->stream));
   }
   memset(h_mask, 0, (size_t)(Lq + 2) * sz2);
-  if (!b.fmt[p]) {
+  if (b.fmt[p] != 1) {
     for (int i = 1; i <= Lq; ++i)
       for (int j = 1; j <= Lt; ++j)
         h_mask[(size_t)i * sz2 + j] = (bits[(size_t)(i - 1) * mws + ((j - 1) >> 5)] >> ((j - 1) & 31)) & 1u;
@@ -587,7 +681,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->sc_off, &c->mask_off, &c->tb[0], &c->tb[1], &c->scb[0], &c->scb[1], &c->mask, &c->fin_score[0],
                    &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
                    &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d,
-                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag};
+                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -607,6 +701,8 @@ int aadp_set_stream(aadp_ctx* c, void* s) {
 int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!c || !key) return fail("null argument");
   if (!strcmp(key, "packed")) { c->allow_packed = value != 0; return 0; }
+  if (!strcmp(key, "wave")) { c->allow_wave = value != 0; return 0; }
+  if (!strcmp(key, "wave_min_cells")) { c->wave_min_cells = value; return 0; }
   return fail(std::string("unknown option ") + key);
 }
 
@@ -753,9 +849,23 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
       c->launches++;
     }
   }
-  if ((what & AADP_W_MASK) && (!b.order[0].empty() || !b.order[1].empty())) {
+  if (run_wave_pairs(c, what)) return 1;
+  if (!b.wave_pairs.empty()) {  // their scalar outputs (the launches above came after the conversions)
+    if ((what & AADP_W_FWD) && d_fwd_score) {
+      scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[0].as<int32_t>(), d_fwd_score, np, c->sc.scale_log2);
+      c->launches++;
+    }
+    if ((what & AADP_W_REV) && d_rev_score) {
+      scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[1].as<int32_t>(), d_rev_score, np, c->sc.scale_log2);
+      c->launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  if ((what & AADP_W_MASK) && (!b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty())) {
     MaskParams M{};
     M.fmt = c->fmt.as<uint8_t>();
+    M.want_fmt = 0;
+    M.only_pair = -1;
     M.sc = c->sc;
     M.sub8 = c->sub8.as<int8_t>();
     M.residues = c->residues.as<uint8_t>();
@@ -773,11 +883,23 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
     M.mask_off = c->mask_off.as<int64_t>();
     M.threshold = d_threshold;
     M.count = reinterpret_cast<long long*>(d_nearopt_count);
-    c->prof_begin("mask_kernel", 0);
-    mask_kernel<<<(int)np, 256, 0, c->stream>>>(M);
-    c->prof_end();
-    CK(cudaGetLastError());
-    c->launches++;
+    if (!b.order[0].empty() || !b.order[1].empty()) {
+      c->prof_begin("mask_kernel", 0);
+      mask_kernel<<<(int)np, 256, 0, c->stream>>>(M);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+    for (int32_t p : b.wave_pairs) {  // long pairs: rows of one pair split over many blocks
+      M.want_fmt = 2;
+      M.only_pair = p;
+      if (d_nearopt_count) CK(cudaMemsetAsync(d_nearopt_count + p, 0, 8, c->stream));
+      c->prof_begin("mask_kernel(long pair)", 0);
+      mask_kernel<<<dim3(1, 592), 256, 0, c->stream>>>(M);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+    }
   }
   b.ran_what = what;
   return 0;
@@ -922,8 +1044,8 @@ int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int6
     {
       const int ts = b.pair_t[p];
       const int Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
-      final_rec[4] = (b.fmt[p] && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;  // leading pad columns of the layout
-      final_rec[5] = b.fmt[p] ? 1 : 0;                                          // 1 = diagonal-major
+      final_rec[4] = (b.fmt[p] == 1 && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;  // leading pad columns of the layout
+      final_rec[5] = b.fmt[p] == 1 ? 1 : 0;                                          // 1 = diagonal-major
     }
   }
   CK(cudaStreamSynchronize(c->stream));

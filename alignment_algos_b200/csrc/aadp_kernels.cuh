@@ -72,7 +72,22 @@ struct FillParams {
   int4* bbuf;                // stripe boundary buffer: [warp slot][bb_rows]
   int bb_rows;
   double cells_hint;         // host-side bookkeeping only (cell updates of this launch)
+  // ---- multi-CTA wavefront mode (one long pair, one CTA per 32*K-column stripe)
+  int wave_pair;             // pair id
+  int wave_nstripes;
+  int4* wave_bb;             // [stripe][bb_rows] boundary (X, E, M-gi) of the stripe's last column per row
+  int* wave_ready;           // [stripe] rows published so far (Lq+1 = stripe completely done)
+  int4* wave_part;           // [stripe] final-row partials (rb_val, rb_k, diag, col)
 };
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 // gap(len) in integer units; 0 for len < 1 (aasubalib.h:33-38)
 __host__ __device__ inline int gap_w(int gi, int ge, int len) { return len < 1 ? 0 : gi + ge * (len - 1); }
@@ -95,9 +110,12 @@ __device__ __forceinline__ int sext8(uint32_t w, int c) {
 // One warp fills one pair in one direction.  K = columns per lane (8 or 16).
 // TBM: write packed traceback.  STM: 0 = no score matrix, 1 = int16, 2 = int32.
 // ------------------------------------------------------------------------------------------------
-template <int K, int TBM, int STM>
+// WAVE = 1: this warp (one CTA) fills ONLY stripe `wave_st` of the pair; stripe st consumes the boundary
+// column of stripe st-1 from global memory 32 rows at a time, gated by release/acquire progress flags --
+// the CTAs of one launch form an anti-diagonal wavefront over the column stripes of one long pair.
+template <int K, int TBM, int STM, int WAVE>
 __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, int8_t* prof, uint8_t* qring,
-                                               const int8_t* s_sub, int4* bb, int lane) {
+                                               const int8_t* s_sub, int4* bb, int lane, int wave_st = 0) {
   constexpr int W = 32 * K;
   const Scoring& S = P.sc;
   const int gi = S.gi, ge = S.ge;
@@ -133,7 +151,11 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
   int rb_val = kNeg32, rb_k = 0;
   int diag_val = kNeg32, col_val = kNeg32;
 
-  for (int st = 0; st < nstripes; ++st) {
+  const int st_lo = WAVE ? wave_st : 0, st_hi = WAVE ? wave_st + 1 : nstripes;
+  for (int st = st_lo; st < st_hi; ++st) {
+    if (WAVE) bb = P.wave_bb + (int64_t)st * P.bb_rows;  // this stripe's output; input is one stripe below
+    const int4* bb_in = WAVE ? P.wave_bb + (int64_t)(st - 1) * P.bb_rows : bb;
+    int4 bblk = make_int4(0, kNeg32, kNeg32, 0);  // WAVE: row (block start + lane) of the input boundary
     const int jbase = st * W + lane * K;  // flow column of register c is jbase + c + 1
     const int cols_here = min(W, Lt - st * W);
     const int n_act = (cols_here + K - 1) / K;
@@ -219,12 +241,27 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
         int inx = i + 1;
         if (inx >= 1 && inx <= Lq) a_nxt = qring[(inx - 1) & (kQRing - 1)];
       }
+      if (WAVE && st > 0) {
+        const int i0 = s + 1;  // row lane 0 works on in this step
+        if (i0 <= Lq && ((i0 - 1) & 31) == 0) {
+          // a new 32-row block of the left neighbour's boundary: wait until it is published, then load it
+          const int need = min(i0 + 31, Lq);
+          if (lane == 0) while (ld_acquire(P.wave_ready + st - 1) < need) __nanosleep(64);
+          __syncwarp();
+          const int r = i0 + lane;
+          if (r <= Lq) bblk = bb_in[r];
+        }
+        const int src = (i0 - 1) & 31;
+        const int bx = __shfl_sync(0xffffffffu, bblk.x, src), be = __shfl_sync(0xffffffffu, bblk.y, src),
+                  bm = __shfl_sync(0xffffffffu, bblk.z, src);
+        if (lane == 0) { xn = bx; e_in = be; mg_in = bm; }
+      }
       if (lane == 0) {
         if (st == 0) {
           xn = -(S.insfree ? 0 : gap_w(gi, ge, i));  // X(i,0): dpmatrix.h:420-426
           e_in = kNeg32;
           mg_in = kNeg32;
-        } else if (i <= Lq) {
+        } else if (!WAVE && i <= Lq) {
           int4 b = bb[i];
           xn = b.x;
           e_in = b.y;
@@ -302,7 +339,13 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
           for (int c = 0; c < K / 4; ++c)
             reinterpret_cast<int4*>(dst)[c] = make_int4(mrow[4 * c], mrow[4 * c + 1], mrow[4 * c + 2], mrow[4 * c + 3]);
         }
-        if (st + 1 < nstripes && lane == 31) bb[i] = make_int4(x_pub, e_pub, mg_pub, 0);
+        if (st + 1 < nstripes && lane == 31) {
+          bb[i] = make_int4(x_pub, e_pub, mg_pub, 0);
+          if (WAVE && ((i & 31) == 0 || i == Lq)) {  // publish a finished 32-row block to the next stripe
+            __threadfence();
+            st_release(P.wave_ready + st, i);
+          }
+        }
       }
     }
 
@@ -332,6 +375,32 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
     if (v2 > rb_val || (v2 == rb_val && k2 < rb_k)) { rb_val = v2; rb_k = k2; }
     diag_val = max(diag_val, __shfl_xor_sync(0xffffffffu, diag_val, o));
     col_val = max(col_val, __shfl_xor_sync(0xffffffffu, col_val, o));
+  }
+  if (WAVE) {
+    // stripe partial -> global; completion is chained stripe by stripe so that the last stripe sees them all
+    if (lane == 0) {
+      P.wave_part[wave_st] = make_int4(rb_val, rb_k, diag_val, col_val);
+      if (wave_st > 0) while (ld_acquire(P.wave_ready + wave_st - 1) < Lq + 1) __nanosleep(64);
+      __threadfence();
+      st_release(P.wave_ready + wave_st, Lq + 1);
+    }
+    __syncwarp();
+    if (wave_st != nstripes - 1) return;
+    rb_val = kNeg32; rb_k = 0; diag_val = kNeg32; col_val = kNeg32;
+    for (int t = lane; t < nstripes; t += 32) {  // ascending stripes per lane: '>' keeps the smallest k
+      const int4 v = P.wave_part[t];
+      if (v.x > rb_val) { rb_val = v.x; rb_k = v.y; }
+      diag_val = max(diag_val, v.z);
+      col_val = max(col_val, v.w);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      int v2 = __shfl_xor_sync(0xffffffffu, rb_val, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, rb_k, o);
+      if (v2 > rb_val || (v2 == rb_val && k2 < rb_k)) { rb_val = v2; rb_k = k2; }
+      diag_val = max(diag_val, __shfl_xor_sync(0xffffffffu, diag_val, o));
+      col_val = max(col_val, __shfl_xor_sync(0xffffffffu, col_val, o));
+    }
   }
   if (lane == 0) {
     int best = diag_val, kind = 0, k = Lt;
@@ -363,8 +432,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) fill_kernel(const FillParam
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_items) break;
-    fill_pair_warp<K, TBM, STM>(P, P.order[item], prof, qring, s_sub, bb, lane);
+    fill_pair_warp<K, TBM, STM, 0>(P, P.order[item], prof, qring, s_sub, bb, lane);
   }
+}
+
+// One long pair, both directions in one launch: CTA b (one warp) fills stripe b % nstripes of direction
+// b / nstripes.  All CTAs must be co-resident (they wait on each other): launched cooperatively.
+template <int K, int TBM, int STM>
+__global__ void __launch_bounds__(32) wave_kernel(const FillParams Pf, const FillParams Pr, int ndirs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int W = 32 * K;
+  const int nst = Pf.wave_nstripes;
+  const int d = blockIdx.x / nst, st = blockIdx.x % nst;
+  if (d >= ndirs) return;
+  const FillParams& P = d ? Pr : Pf;
+  const int A = P.sc.A;
+  int8_t* s_sub = reinterpret_cast<int8_t*>(smem);
+  const int sub_bytes = (A * A + 15) / 16 * 16;
+  const int lane = threadIdx.x;
+  uint8_t* qring = smem + sub_bytes;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kQRing);
+  for (int x = threadIdx.x; x < A * A; x += blockDim.x) s_sub[x] = P.sub8[x];
+  __syncwarp();
+  fill_pair_warp<K, TBM, STM, 1>(P, P.wave_pair, prof, qring, s_sub, nullptr, lane, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,7 +564,9 @@ struct MaskParams {
   const int64_t* mask_off;   // per pair word offset
   float* threshold;          // per pair (may be null)
   long long* count;          // per pair (may be null)
-  const uint8_t* fmt;        // per pair: 1 = handled by the packed kernels (skipped here)
+  const uint8_t* fmt;        // per pair: 0 = int32 kernels, 1 = packed kernels, 2 = wavefront (long pair)
+  int want_fmt;              // which class this launch handles
+  int only_pair;             // >= 0: this launch covers one pair, rows split over blockIdx.y
 };
 
 __host__ __device__ inline int64_t mask_row_words(int Lt) { return (Lt + 31) / 32; }
@@ -486,23 +578,23 @@ __device__ __forceinline__ float nearopt_threshold(float opt, float delta_ratio)
 }
 
 __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
-  const int pair = blockIdx.x;
-  if (P.fmt[pair]) return;
+  const int pair = P.only_pair >= 0 ? P.only_pair : blockIdx.x;
+  if (P.fmt[pair] != P.want_fmt) return;
   const int qs = P.pair_q[pair], ts = P.pair_t[pair];
   const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
   const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
   const float inv = 1.f / (float)(1 << P.sc.scale_log2);
   const float opt = (float)P.fin_fwd[pair] * inv;
   const float thr = nearopt_threshold(opt, P.delta_ratio);
-  if (threadIdx.x == 0 && P.threshold) P.threshold[pair] = thr;
-  if (Lq == 0 || Lt == 0) { if (threadIdx.x == 0 && P.count) P.count[pair] = 0; return; }
+  if (threadIdx.x == 0 && blockIdx.y == 0 && P.threshold) P.threshold[pair] = thr;
+  if (Lq == 0 || Lt == 0) { if (threadIdx.x == 0 && blockIdx.y == 0 && P.count) P.count[pair] = 0; return; }
   const int64_t scs = sc_row_elems(Lt), mws = mask_row_words(Lt);
   const int64_t so = P.sc_off[pair];
   uint32_t* mk = P.mask + P.mask_off[pair];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int A = P.sc.A;
   long long cnt = 0;
-  for (int i = 1 + warp; i <= Lq; i += nw) {
+  for (int i = 1 + warp + nw * blockIdx.y; i <= Lq; i += nw * gridDim.y) {
     const int qa = P.residues[qo + i - 1];
     for (int j0 = 0; j0 < Lt; j0 += 32) {
       const int j = j0 + lane + 1;
@@ -528,7 +620,10 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
     __syncthreads();
     if (lane == 0 && cnt) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
     __syncthreads();
-    if (threadIdx.x == 0) P.count[pair] = s_cnt;
+    if (threadIdx.x == 0) {
+      if (gridDim.y == 1) P.count[pair] = s_cnt;
+      else atomicAdd((unsigned long long*)&P.count[pair], (unsigned long long)s_cnt);  // zeroed by the host
+    }
   }
 }
 

@@ -187,6 +187,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pairs", type=int, default=100_000, help="pairs per GPU (C3 = 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3 (default, the headline): 100k pairs fwd+rev+traceback+mask; c2: 10k pairs forward "
+                         "score-only; c5: one 30k x 30k pair fwd+rev+traceback+mask (multi-CTA wavefront)")
+    ap.add_argument("--long-len", type=int, default=30000)
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
@@ -225,10 +229,27 @@ def main():
         return float(t.item())
 
     # ---- workload (synthetic, seeded; every rank owns its own C3-sized shard: weak scaling)
-    seqs, pq, pt = make_workload(rank, args.pairs)
-    res, off = a.Context.pack(seqs)
     alpha, M = a.blosum62()
-    what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+    if args.workload == "c3":
+        seqs, pq, pt = make_workload(rank, args.pairs)
+        what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+        wl_desc = ("c3: %d synthetic protein pairs per GPU, L in [100,500], BLOSUM62 gi=12 ge=1 semi_local, "
+                   "fwd+rev fill + packed traceback + near-optimal cell set (delta=0.01)" % args.pairs)
+    elif args.workload == "c2":
+        from alignment_algos_b200 import synth
+        npairs = args.pairs if args.pairs != 100_000 else 10_000
+        seqs, pq, pt = synth.pair_workload(1002 + rank, npairs, 100, 500)
+        what = a.W_FWD
+        wl_desc = ("c2: %d synthetic protein pairs per GPU, L in [100,500], BLOSUM62 gi=12 ge=1 semi_local, "
+                   "forward score-only fill" % npairs)
+    else:
+        rng = np.random.default_rng(1005 + rank)
+        seqs = [rng.integers(0, 20, args.long_len).astype(np.uint8) for _ in range(2)]
+        pq, pt = np.array([0], np.int32), np.array([1], np.int32)
+        what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+        wl_desc = ("c5: one synthetic pair %d x %d, BLOSUM62 gi=12 ge=1 semi_local, fwd+rev fill + packed traceback "
+                   "+ near-optimal cell set, multi-CTA anti-diagonal wavefront" % (args.long_len, args.long_len))
+    res, off = a.Context.pack(seqs)
     # pinned host staging buffers (numpy views of torch pinned tensors) for the end-to-end leg
     def pinned(arr):
         t = torch.from_numpy(arr.copy()).pin_memory()
@@ -283,7 +304,8 @@ def main():
     ms_per_step = ms_total / args.steps
 
     # correctness guard inside the bench: the two directions must agree on every optimum
-    assert torch.equal(d_f, d_r), "forward and reverse optima differ"
+    if what & a.W_REV:
+        assert torch.equal(d_f, d_r), "forward and reverse optima differ"
 
     # ---- leg 2: end to end through the C ABI with host buffers
     for _ in range(2):
@@ -300,7 +322,8 @@ def main():
     e2e_value = total_cu * args.steps / (e2e_ms * 1e-3) / 1e9
     h2d = int(hb["res"].nbytes + hb["off"].nbytes + hb["pq"].nbytes + hb["pt"].nbytes + n * 4 + 3 * (n + 1) * 8)
     d2h = int(n * (4 + 4 + 4 + 8))
-    assert np.array_equal(out["fwd_score"], out["rev_score"])
+    if what & a.W_REV:
+        assert np.array_equal(out["fwd_score"], out["rev_score"])
     sampler.stop()
     clocks = sampler.summary(w0, w1)
 
@@ -339,8 +362,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "c3: %d synthetic protein pairs per GPU, L in [100,500], BLOSUM62 gi=12 ge=1 semi_local, "
-                               "fwd+rev fill + packed traceback + near-optimal cell set (delta=0.01)" % n,
+        "config": {"workload": wl_desc,
                    "pairs_per_gpu": n, "cache": "outputs (%.1f GB/step) exceed L2; no flush needed" % (
                        (ctx.resident_bytes(a.W_TB) + ctx.resident_bytes(a.W_SCORES) + ctx.resident_bytes(a.W_MASK)) / 1e9),
                    "sharding": "independent pair shards per rank, no collective on the data path"},
@@ -358,7 +380,9 @@ def main():
         "kernel_share": kernel_share,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = reference_timer(seqs, pq, pt, 15.0, os.cpu_count() or 1)
+        if args.workload == "c5":  # the reference cannot run 30k x 30k (21.6 GB of DPCell, O(n^3)): C3-shaped sample
+            seqs, pq, pt = make_workload(0, 2048)
+        cb = reference_timer(seqs, pq, pt, 15.0, os.cpu_count() or 1, 3 if (what & a.W_REV) else 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line), flush=True)

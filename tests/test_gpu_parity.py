@@ -181,3 +181,40 @@ def test_errors_are_loud(ctx, blosum):
     ctx.set_scoring(M, 12, 1, po.GLOBAL)
     with pytest.raises(a.AadpError):
         ctx.fill_pair(np.array([30], np.uint8), np.array([1], np.uint8))  # code outside the alphabet
+
+
+@pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL, po.LOCAL], ids=["global", "semi_local", "local"])
+def test_long_pair_multi_cta_wavefront(blosum, at):
+    # BASELINE.json configs[4] in miniature: one long pair filled by the multi-CTA wavefront kernel
+    # (one CTA per 256-column stripe, both directions in one cooperative launch)
+    import alignment_algos_b200 as a
+    _, M = blosum
+    c = a.Context(0)
+    c.set_option("wave_min_cells", 1)
+    c.set_scoring(M, 12, 1, at)
+    O = po.Oracle(M, 12, 1, at)
+    rng = np.random.default_rng(9)
+    try:
+        for Lq, Lt in [(40, 600), (700, 1300), (1500, 2100), (33, 513), (300, 4000)]:
+            q, t = rand_pair(rng, Lq, Lt)
+            _check_pair(c, O, q, t, "wave at%d %dx%d" % (at, Lq, Lt), mask_dr=(0.02 if at != po.LOCAL else None))
+            names = set()
+    finally:
+        c.close()
+
+
+def test_long_pair_uses_wave_kernel(blosum):
+    import alignment_algos_b200 as a
+    _, M = blosum
+    c = a.Context(0)
+    c.set_option("wave_min_cells", 1)
+    c.set_scoring(M, 12, 1, po.GLOBAL)
+    rng = np.random.default_rng(10)
+    q, t = rand_pair(rng, 900, 1800)
+    res, off = a.Context.pack([q, t])
+    c.set_profiling(True)
+    out = c.fill_batch(res, off, [0], [1], a.W_FWD | a.W_REV | a.W_TB)
+    names = [n for n, ms, cells in c.profile()]
+    c.close()
+    assert any(n.startswith("wave_kernel") for n in names), names
+    assert out["fwd_score"][0] == out["rev_score"][0]
