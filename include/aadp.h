@@ -123,7 +123,7 @@ int aadp_batch_fetch_pair(aadp_ctx* ctx, int64_t p, float* score_fwd, int32_t* p
                           int32_t* prevt_fwd, float* score_rev, int32_t* prevq_rev,
                           int32_t* prevt_rev, uint8_t* nearopt);
 
-/* Optimal alignment of pair p traced on the GPU from the packed traceback: replaces
+/* Optimal alignment of pair p, walked (on the host) over the packed traceback fetched from HBM: replaces
  * Optimal::enumerate (optimal.h:47-75) for direction AADP_FWD and Optimal_Rev::enumerate
  * (optimal_rev.h:47-78) for AADP_REV. pairs receives 2 ints (query_idx, template_idx) per
  * aligned pair in alignment order, including (0,0) and (last,last). Returns 3 with

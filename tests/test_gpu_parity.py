@@ -218,3 +218,87 @@ def test_long_pair_uses_wave_kernel(blosum):
     c.close()
     assert any(n.startswith("wave_kernel") for n in names), names
     assert out["fwd_score"][0] == out["rev_score"][0]
+
+
+def _rescore(O, q, t, pairs, sub, gi, ge, at):
+    """Score of an alignment given as (q,t) index pairs incl. (0,0) and (last,last), with the
+    evaluator's gap rules (aasubalib.h:27-77)."""
+    sz1, sz2 = len(q) + 2, len(t) + 2
+    delfree = at in (po.LOCAL, po.SEMI_LOCAL, po.LOCAL_GLOBAL)
+    insfree = at in (po.LOCAL, po.SEMI_LOCAL, po.GLOBAL_LOCAL)
+    s = 0.0
+    for (a0, b0), (a1, b1) in zip(pairs[:-1], pairs[1:]):
+        dl, il = b1 - b0 - 1, a1 - a0 - 1
+        assert a1 > a0 and b1 > b0 and (dl == 0 or il == 0), "not a valid alignment step"
+        if dl >= 1 and not (delfree and (b0 == 0 or b1 == sz2 - 1)):
+            s -= gi + ge * (dl - 1)
+        if il >= 1 and not (insfree and (a0 == 0 or a1 == sz1 - 1)):
+            s -= gi + ge * (il - 1)
+        if 1 <= a1 <= len(q) and 1 <= b1 <= len(t):
+            s += sub[q[a1 - 1], t[b1 - 1]]
+    return s
+
+
+def test_large_batch_size_independent_properties(ctx):
+    # at sizes the oracle cannot sweep: (1) F(end) == R(0,0) for every pair, (2) the optimal alignment
+    # decoded from the packed traceback is a valid alignment whose rescored value equals the fill's optimum,
+    # in both directions, (3) every cell of that alignment is in the near-optimal set
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha20, M20 = a.blosum62()
+    seqs, pq, pt = synth.pair_workload(4242, 12000, 100, 500)
+    res, off = a.Context.pack(seqs)
+    for at in (po.SEMI_LOCAL, po.GLOBAL):
+        ctx.set_scoring(M20, 12, 1, at)
+        out = ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB | a.W_MASK, 0.01)
+        assert_matrix_equal("fwd==rev optimum", out["fwd_score"], out["rev_score"])
+        assert (out["nearopt_count"] >= 1).all()
+        rng = np.random.default_rng(at)
+        for p in rng.choice(len(pq), 40, replace=False):
+            q, t = seqs[pq[p]], seqs[pt[p]]
+            rc, pairs, sc = ctx.optimal(int(p), a.FWD, len(q), len(t))
+            assert rc == 0 and sc == out["fwd_score"][p]
+            assert tuple(pairs[0]) == (0, 0) and tuple(pairs[-1]) == (len(q) + 1, len(t) + 1)
+            assert _rescore(None, q, t, [tuple(x) for x in pairs], M20, 12, 1, at) == sc
+            got = ctx.fetch_pair(int(p), len(q), len(t), fwd=False, rev=False, tb=False, scores=False, mask=True)
+            for (i, j) in pairs[1:-1]:
+                assert got["nearopt"][i, j] == 1, "optimal cell missing from the near-optimal set"
+            rc, rpairs, rsc = ctx.optimal(int(p), a.REV, len(q), len(t))
+            if rc == 0:
+                rp = [tuple(int(v) for v in x) for x in rpairs]
+                # dpmatrix.h:868 (reproduced) can make the FIRST reverse step jump in both indices; that walk is
+                # the reference's behaviour but not an alignment. Every other reverse walk must rescore exactly.
+                first_ok = (rp[1][0] - rp[0][0] == 1) or (rp[1][1] - rp[0][1] == 1)
+                if first_ok:
+                    assert _rescore(None, q, t, rp, M20, 12, 1, at) == rsc
+                else:
+                    assert rp[1][1] == len(t), "only the :868 pattern may produce such a step"
+
+
+@pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL], ids=["global", "semi_local"])
+def test_extreme_scores_near_the_packed_bound(ctx, blosum, at):
+    # identical poly-W sequences (largest positive scores the packed int16 path accepts), all-mismatch
+    # pairs (most negative), and mixtures; lengths at the packed limits
+    alpha, M = blosum
+    W, C, G = alpha.index("W"), alpha.index("C"), alpha.index("G")
+    ctx.set_scoring(M, 12, 1, at)
+    O = po.Oracle(M, 12, 1, at)
+    rng = np.random.default_rng(3)
+    cases = [(np.full(500, W), np.full(500, W)), (np.full(512, W), np.full(512, W)), (np.full(500, W), np.full(500, G)),
+             (np.full(300, C), np.full(511, W)), (np.full(40, W), np.full(512, G)),
+             (np.r_[np.full(200, W), rng.integers(0, 20, 100)], np.r_[rng.integers(0, 20, 150), np.full(300, W)])]
+    for q, t in cases:
+        _check_pair(ctx, O, q.astype(np.uint8), t.astype(np.uint8), "extreme at%d %dx%d" % (at, len(q), len(t)), mask_dr=0.01)
+
+
+def test_half_unit_scoring_and_large_gaps(ctx, blosum):
+    # dyadic (non-integer) grids and gap penalties near the packed path's limits
+    _, M = blosum
+    rng = np.random.default_rng(8)
+    for gi, ge, at in [(10.5, 0.25, po.SEMI_LOCAL), (0.5, 0.5, po.GLOBAL), (40, 3, po.GLOBAL), (100, 0, po.SEMI_LOCAL),
+                       (300, 10, po.GLOBAL_LOCAL)]:
+        ctx.set_scoring(M, gi, ge, at)
+        O = po.Oracle(M, gi, ge, at)
+        for Lq, Lt in [(90, 130), (257, 31)]:
+            q, t = rand_pair(rng, Lq, Lt)
+            _check_pair(ctx, O, q, t, "gi%s ge%s at%d" % (gi, ge, at), mask_dr=0.05)
