@@ -42,6 +42,10 @@ def lib():
     L.aadp_batch_resident_bytes.argtypes = [vp, u32]
     L.aadp_last_launch_count.restype = i64
     L.aadp_last_launch_count.argtypes = [vp]
+    L.aadp_last_h2d_bytes.restype = i64
+    L.aadp_last_h2d_bytes.argtypes = [vp]
+    L.aadp_last_d2h_bytes.restype = i64
+    L.aadp_last_d2h_bytes.argtypes = [vp]
     L.aadp_last_cell_updates.restype = C.c_double
     L.aadp_last_cell_updates.argtypes = [vp]
     L.aadp_set_profiling.argtypes = [vp, C.c_int]
@@ -63,7 +67,7 @@ EXPORTS = [
     "aadp_create", "aadp_destroy", "aadp_last_error", "aadp_version", "aadp_set_stream",
     "aadp_synchronize", "aadp_set_option", "aadp_set_scoring", "aadp_fill_pair", "aadp_fill_batch",
     "aadp_upload_batch", "aadp_run_batch", "aadp_batch_resident_bytes", "aadp_last_launch_count",
-    "aadp_last_cell_updates", "aadp_set_profiling", "aadp_profile_count", "aadp_profile_get",
+    "aadp_last_h2d_bytes", "aadp_last_d2h_bytes", "aadp_last_cell_updates", "aadp_set_profiling", "aadp_profile_count", "aadp_profile_get",
     "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes", "aadp_batch_tb_bytes",
     "aadp_batch_fetch_tb", "aadp_decode_cell",
 ]

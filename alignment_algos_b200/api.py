@@ -126,6 +126,9 @@ class Context:
     def last_launch_count(self):
         return self.L.aadp_last_launch_count(self.h)
 
+    def last_transfer_bytes(self):
+        return self.L.aadp_last_h2d_bytes(self.h), self.L.aadp_last_d2h_bytes(self.h)
+
     def last_cell_updates(self):
         return self.L.aadp_last_cell_updates(self.h)
 

@@ -6,6 +6,7 @@
 #include "aadp_packed.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -112,6 +113,7 @@ struct aadp_ctx {
   int* pin_flag = nullptr;
   Batch b;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last upload / fill call
   int bb_rows = 0;
   // optional per-launch timing
   bool profiling = false;
@@ -295,13 +297,30 @@ void build_tasks(aadp_ctx* c) {
     items.push_back({(int32_t)p, (Lt + 15) / 16, Lq});
   }
   if (items.empty()) return;
-  std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+  // order by (lane width desc, query length desc, pair id): a counting sort when the key space is small
+  // (the usual case: Lq up to a few thousand), std::sort otherwise
+  int maxLq = 0;
+  for (const Item& it : items) maxLq = std::max(maxLq, it.Lq);
+  auto cmp = [](const Item& x, const Item& y) {
     if (x.n != y.n) return x.n > y.n;
     if (x.Lq != y.Lq) return x.Lq > y.Lq;
     return x.p < y.p;
-  });
+  };
+  if ((int64_t)33 * (maxLq + 1) <= (int64_t)4 * (int64_t)items.size() + 65536) {
+    const int64_t nb = (int64_t)33 * (maxLq + 1);
+    std::vector<int32_t> cnt((size_t)nb + 1, 0);
+    auto key = [&](const Item& it) { return (int64_t)(32 - it.n) * (maxLq + 1) + (maxLq - it.Lq); };
+    for (const Item& it : items) cnt[(size_t)key(it) + 1]++;
+    for (int64_t k = 0; k < nb; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
+    std::vector<Item> sorted(items.size());
+    for (const Item& it : items) sorted[(size_t)cnt[(size_t)key(it)]++] = it;  // stable: pair ids stay ascending
+    items.swap(sorted);
+  } else {
+    std::sort(items.begin(), items.end(), cmp);
+  }
   struct Couple { int32_t a, b; int n; int Lq; };
   std::vector<Couple> couples;
+  couples.reserve(items.size() / 2 + 64);
   for (size_t i = 0; i < items.size();) {
     if (i + 1 < items.size() && items[i + 1].n == items[i].n) {
       couples.push_back({items[i].p, items[i + 1].p, items[i].n, items[i].Lq});  // a has the longer query
@@ -311,7 +330,18 @@ void build_tasks(aadp_ctx* c) {
       i += 1;
     }
   }
-  std::stable_sort(couples.begin(), couples.end(), [](const Couple& x, const Couple& y) { return x.Lq > y.Lq; });
+  // stable order by query length, longest first (longest tasks are scheduled first)
+  if ((int64_t)maxLq + 1 <= (int64_t)4 * (int64_t)couples.size() + 65536) {
+    std::vector<int32_t> cnt((size_t)maxLq + 2, 0);
+    for (const Couple& cp : couples) cnt[(size_t)(maxLq - cp.Lq) + 1]++;
+    for (int k = 0; k <= maxLq; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
+    std::vector<Couple> sorted(couples.size());
+    for (const Couple& cp : couples) sorted[(size_t)cnt[(size_t)(maxLq - cp.Lq)]++] = cp;
+    couples.swap(sorted);
+  } else {
+    std::stable_sort(couples.begin(), couples.end(), [](const Couple& x, const Couple& y) { return x.Lq > y.Lq; });
+  }
+  b.tasks.reserve(couples.size() * 64 / 2 + 4096);
   struct Open { int64_t task; int used; };
   std::vector<Open> open;
   auto new_task = [&]() {
@@ -420,6 +450,7 @@ int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v) {
   if (at + bytes > c->pin_cap) return fail("internal: pinned staging pool too small");
   memcpy(c->pin + at, v.data(), bytes);
   c->pin_used = at + bytes;
+  c->h2d_bytes += (int64_t)bytes;
   CK(cudaMemcpyAsync(d.p, c->pin + at, bytes, cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
@@ -761,6 +792,7 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
   if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
     return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  const auto t_begin = std::chrono::steady_clock::now();
   Batch& b = c->b;
   b.nseq = nseq;
   b.npairs = npairs;
@@ -785,6 +817,8 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   if (pin_reserve(c, (size_t)(nseq + 1) * 12 + (size_t)npairs * (8 + 1 + 4 + 24 + 64 * 4 / 2 + 64) + 65536)) return 1;
   if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
   if (c->arena_f.reserve(arena_bytes) || c->arena_r.reserve(arena_bytes) || c->badflag.reserve(16)) return 1;
+  c->h2d_bytes = nres;
+  c->d2h_bytes = 4;
   if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
   if (upload_vec(c, c->seq_off, b.seq_off)) return 1;
   if (upload_vec(c, c->aoff, b.aoff)) return 1;
@@ -799,7 +833,9 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   }
   CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
   // 2. ... and build the schedule on the host while they run
+  const auto t_meta0 = std::chrono::steady_clock::now();
   if (build_batch_meta(c, what)) return 1;
+  const auto t_meta1 = std::chrono::steady_clock::now();
   b.uploaded_what = what;
   b.ran_what = 0;
   if (upload_vec(c, c->tasks, b.tasks)) return 1;
@@ -811,7 +847,16 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   if (upload_vec(c, c->tb_off, b.tb_off)) return 1;
   if (upload_vec(c, c->sc_off, b.sc_off)) return 1;
   if (upload_vec(c, c->mask_off, b.mask_off)) return 1;
+  const auto t_up = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers; the validation flag is back
+  if (getenv("AADP_TIMING")) {
+    const auto t_end = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[aadp] upload: pre %.2f ms, schedule %.2f ms, stage+enqueue %.2f ms, drain %.2f ms (tasks %lld)\n",
+            ms(t_begin, t_meta0), ms(t_meta0, t_meta1), ms(t_meta1, t_up), ms(t_up, t_end), (long long)b.n_tasks);
+  }
   if (*c->pin_flag) return fail("residue code outside the substitution alphabet");
   return 0;
 }
@@ -918,10 +963,10 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
   if (nearopt_count) { if (c->count.reserve(nb * 2)) return 1; dc = c->count.as<int64_t>(); }
   if (aadp_run_batch(c, what, delta_ratio, df, dr, dt, dc)) return 1;
   if (npairs) {
-    if (fwd_score && (what & AADP_W_FWD)) CK(cudaMemcpyAsync(fwd_score, df, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (rev_score && (what & AADP_W_REV)) CK(cudaMemcpyAsync(rev_score, dr, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (threshold && (what & AADP_W_MASK)) CK(cudaMemcpyAsync(threshold, dt, npairs * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (nearopt_count && (what & AADP_W_MASK)) CK(cudaMemcpyAsync(nearopt_count, dc, npairs * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (fwd_score && (what & AADP_W_FWD)) { CK(cudaMemcpyAsync(fwd_score, df, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
+    if (rev_score && (what & AADP_W_REV)) { CK(cudaMemcpyAsync(rev_score, dr, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
+    if (threshold && (what & AADP_W_MASK)) { CK(cudaMemcpyAsync(threshold, dt, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
+    if (nearopt_count && (what & AADP_W_MASK)) { CK(cudaMemcpyAsync(nearopt_count, dc, npairs * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 8; }
   }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -939,6 +984,8 @@ int64_t aadp_batch_resident_bytes(aadp_ctx* c, uint32_t which) {
 }
 
 int64_t aadp_last_launch_count(aadp_ctx* c) { return c ? c->launches : 0; }
+int64_t aadp_last_h2d_bytes(aadp_ctx* c) { return c ? c->h2d_bytes : 0; }
+int64_t aadp_last_d2h_bytes(aadp_ctx* c) { return c ? c->d2h_bytes : 0; }
 
 int aadp_set_profiling(aadp_ctx* c, int on) {
   if (!c) return fail("null context");

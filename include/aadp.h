@@ -106,6 +106,9 @@ int aadp_run_batch(aadp_ctx* ctx, uint32_t what, float delta_ratio, float* d_fwd
 int64_t aadp_batch_resident_bytes(aadp_ctx* ctx, uint32_t which);
 /* Number of kernels launched by the last batch/pair call (for bench.py's gpu_launches). */
 int64_t aadp_last_launch_count(aadp_ctx* ctx);
+/* Bytes copied host->device / device->host by the last aadp_fill_batch / aadp_upload_batch call. */
+int64_t aadp_last_h2d_bytes(aadp_ctx* ctx);
+int64_t aadp_last_d2h_bytes(aadp_ctx* ctx);
 /* Cell updates (sum of Lq*Lt per filled direction) of the last batch call. */
 double aadp_last_cell_updates(aadp_ctx* ctx);
 
