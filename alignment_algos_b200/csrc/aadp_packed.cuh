@@ -402,30 +402,40 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         cp_async_commit();
       }
 
-      uint32_t Xd = xl_hold, E = e_in, Mgl = mg_in;
+      uint32_t E = e_in, Mgl = mg_in;
       uint32_t accM = 0, acc01 = 0, acc23 = 0;
       uint32_t tbA[2], tbB[2], oA[8], oB[8];
-      uint32_t Mprev = 0, d5prev = 0;
+      // ---- phase 1: every M of the row (independent adds), and the near-optimal test of the reverse pass.
+      // Doing this first frees the previous row's X registers, so phase 2 updates the state in place.
+      uint32_t Mv[16];
+      {
+        uint32_t Xd = xl_hold, d5prev = 0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int k = c & 3;
+          const uint32_t ssel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
+          const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
+          // plain packed add (VIADD.16x2, off the ALU pipe): no clamp is needed -- real cells stay far above the
+          // floor and pad columns only drift down by ge per row (bounded by the host-side score bound)
+          Mv[c] = __vadd2(simp, Xd);
+          if (MSK) {
+            // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
+            // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
+            const int e = 15 - c;
+            const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
+            const uint32_t slack = __vadd2(fv, __vadd2(Xd, NBIAS2));  // Xd may be below the bias: true packed adds
+            const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
+            // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
+            if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
+            else d5prev = d5;
+          }
+          Xd = Xp[c];
+        }
+      }
+      // ---- phase 2: E chain, F, X, traceback bits
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        const int k = c & 3;
-        const uint32_t ssel = (uint32_t)k | ((uint32_t)(k | 8) << 4) | ((uint32_t)(4 + k) << 8) | ((uint32_t)((4 + k) | 8) << 12);
-        const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
-        // plain packed add (VIADD.16x2, off the ALU pipe): no clamp is needed -- real cells stay far above the
-        // floor and pad columns only drift down by ge per row (bounded by the host-side score bound)
-        const uint32_t M = __vadd2(simp, Xd);
-        if (MSK) {
-          // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
-          // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
-          const int e = 15 - c;
-          const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
-          const uint32_t slack = __vadd2(fv, __vadd2(Xd, NBIAS2));  // Xd may be below the bias: true packed adds
-          const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
-          // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
-          if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
-          else d5prev = d5;
-        }
-        Xd = Xp[c];
+        const uint32_t M = Mv[c];
         uint32_t F, X;
         if (TBM) {
           const uint32_t Eext = addc(E, NGE2);
@@ -457,11 +467,9 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         Xp[c] = X;
         Fs[c] = F;
         Mg[c] = Mgl;
-        if (FST) {
-          if (c & 1) {
-            oA[c >> 1] = prmt(Mprev, M, 0x5410u);
-            oB[c >> 1] = prmt(Mprev, M, 0x7632u);
-          } else Mprev = M;
+        if (FST && (c & 1)) {
+          oA[c >> 1] = prmt(Mv[c - 1], M, 0x5410u);
+          oB[c >> 1] = prmt(Mv[c - 1], M, 0x7632u);
         }
       }
       if (MSK) accM &= VM;
