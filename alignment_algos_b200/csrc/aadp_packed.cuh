@@ -248,7 +248,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   const uint32_t FLOOR2 = pkb(kFloor16, kFloor16);
   const uint32_t NGE2 = pkdec(ge, ge);
   const uint32_t NGI2 = pkdec(gi, gi);
-  const uint32_t NBIAS2 = pk2(-kBias16, -kBias16);
+  const uint32_t NBIASC = pkdec(kBias16, kBias16);
 
   // ---- per-half output bases (diagonal-major: the address of a step is base + step * stride)
   uint8_t* tbp[2] = {nullptr, nullptr};
@@ -423,7 +423,10 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
             const int e = 15 - c;
             const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
-            const uint32_t slack = __vadd2(fv, __vadd2(Xd, NBIAS2));  // Xd may be below the bias: true packed adds
+            // both halves are positive 16-bit numbers whose sum stays below 65536, so fv + Xd is a plain 32-bit
+            // add without a carry between the halves; removing one bias uses the carry-compensated constant
+            // (the low sum of a real cell is >= bias, so the borrow pattern is fixed).  One IADD3.
+            const uint32_t slack = fv + Xd + NBIASC;
             const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
             // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
             if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
