@@ -12,6 +12,10 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 using namespace aadp;
@@ -77,13 +81,35 @@ struct Batch {
   // packed (int16x2) path
   std::vector<uint8_t> fmt;       // per pair: 0 = int32 kernels, 1 = packed kernels, 2 = multi-CTA wavefront (long pair)
   std::vector<int32_t> wave_pairs;
-  std::vector<int32_t> tasks;     // n_tasks * 64 pair ids
   std::vector<int32_t> aoff;      // per sequence byte offset into the aligned arenas
   double packed_cells = 0;
   int64_t n_tasks = 0;
   double cells = 0;
   uint32_t uploaded_what = 0;
   uint32_t ran_what = 0;
+};
+
+struct HostPool {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv, done;
+  std::function<void(int)>* fn = nullptr;
+  uint64_t gen = 0;
+  int active = 0, pending = 0;
+  bool stop = false;
+  void start(int n);
+  void run(int T, std::function<void(int)> f);
+  ~HostPool();
+};
+
+// per-host-thread scratch of the scheduler, kept between batches (fresh allocations page-fault, and page
+// faults of concurrent threads serialise on the process' address-space lock)
+struct SchedItem { int32_t p; int n; int Lq; };
+struct SchedCouple { int32_t a, b; int n; int Lq; };
+struct SchedScratch {
+  std::vector<SchedItem> items, items2;
+  std::vector<SchedCouple> couples, couples2;
+  std::vector<int32_t> cnt, tasks, order[2], wave;
 };
 
 }  // namespace
@@ -105,6 +131,10 @@ struct aadp_ctx {
   DevBuf fmt, tasks, aoff, arena_f, arena_r, badflag;
   bool allow_packed = true;
   bool allow_wave = true;
+  int host_threads = 0;  // 0 = min(hardware threads, 8)
+  HostPool pool;
+  std::vector<SchedScratch> sched;
+  std::vector<int32_t> Lq32, Lt32;
   int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
   DevBuf wave_bb, wave_ready, wave_part;
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -282,19 +312,71 @@ int check_ctx(aadp_ctx* c, bool need_scoring) {
   return 0;
 }
 
+// Persistent host worker pool (the schedule of a batch is built on several host threads; spawning
+// threads per call costs more than the work itself).  run(T, f) executes f(t) for t in [0,T): the
+// caller is thread 0, workers take 1..T-1.
+void HostPool::start(int n) {
+  while ((int)workers.size() < n) {
+    const int id = (int)workers.size() + 1;
+    workers.emplace_back([this, id]() {
+      uint64_t seen = 0;
+      for (;;) {
+        std::function<void(int)>* f = nullptr;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&]() { return stop || gen != seen; });
+          if (stop) return;
+          seen = gen;
+          if (id < active) f = fn;
+        }
+        if (f) {
+          (*f)(id);
+          std::unique_lock<std::mutex> lk(mu);
+          if (--pending == 0) done.notify_one();
+        }
+      }
+    });
+  }
+}
+void HostPool::run(int T, std::function<void(int)> f) {
+  if (T <= 1) { f(0); return; }
+  start(T - 1);
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    fn = &f;
+    active = T;
+    pending = T - 1;
+    ++gen;
+  }
+  cv.notify_all();
+  f(0);
+  std::unique_lock<std::mutex> lk(mu);
+  done.wait(lk, [&]() { return pending == 0; });
+  fn = nullptr;
+}
+HostPool::~HostPool() {
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    stop = true;
+  }
+  cv.notify_all();
+  for (std::thread& t : workers) t.join();
+}
+
 // Couple pairs of equal lane width and similar query length (they share a segment, one per register
-// half), then bin-pack the couples into 32-lane tasks of similar duration.
-void build_tasks(aadp_ctx* c) {
-  Batch& b = c->b;
-  b.tasks.clear();
-  b.n_tasks = 0;
-  struct Item { int32_t p; int n; int Lq; };
-  std::vector<Item> items;
-  for (int64_t p = 0; p < b.npairs; ++p) {
+// half), then bin-pack the couples into 32-lane tasks of similar duration.  Works on the packed pairs of
+// the id range [lo,hi) only, so that several host threads can schedule disjoint ranges independently;
+// S.tasks receives 64 pair ids per task, longest tasks first.
+void build_tasks_range(const Batch& b, const int32_t* Lq32, const int32_t* Lt32, int64_t lo, int64_t hi, SchedScratch& S) {
+  typedef SchedItem Item;
+  typedef SchedCouple Couple;
+  std::vector<int32_t>& out = S.tasks;
+  out.clear();
+  std::vector<Item>& items = S.items;
+  items.clear();
+  for (int64_t p = lo; p < hi; ++p) {
     if (b.fmt[p] != 1) continue;
-    const int qs = b.pair_q[p], ts = b.pair_t[p];
-    const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
-    items.push_back({(int32_t)p, (Lt + 15) / 16, Lq});
+    items.push_back({(int32_t)p, (Lt32[p] + 15) / 16, Lq32[p]});
   }
   if (items.empty()) return;
   // order by (lane width desc, query length desc, pair id): a counting sort when the key space is small
@@ -306,21 +388,22 @@ void build_tasks(aadp_ctx* c) {
     if (x.Lq != y.Lq) return x.Lq > y.Lq;
     return x.p < y.p;
   };
+  std::vector<int32_t>& cnt = S.cnt;
   if ((int64_t)33 * (maxLq + 1) <= (int64_t)4 * (int64_t)items.size() + 65536) {
     const int64_t nb = (int64_t)33 * (maxLq + 1);
-    std::vector<int32_t> cnt((size_t)nb + 1, 0);
+    cnt.assign((size_t)nb + 1, 0);
     auto key = [&](const Item& it) { return (int64_t)(32 - it.n) * (maxLq + 1) + (maxLq - it.Lq); };
     for (const Item& it : items) cnt[(size_t)key(it) + 1]++;
     for (int64_t k = 0; k < nb; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
-    std::vector<Item> sorted(items.size());
+    std::vector<Item>& sorted = S.items2;
+    sorted.resize(items.size());
     for (const Item& it : items) sorted[(size_t)cnt[(size_t)key(it)]++] = it;  // stable: pair ids stay ascending
     items.swap(sorted);
   } else {
     std::sort(items.begin(), items.end(), cmp);
   }
-  struct Couple { int32_t a, b; int n; int Lq; };
-  std::vector<Couple> couples;
-  couples.reserve(items.size() / 2 + 64);
+  std::vector<Couple>& couples = S.couples;
+  couples.clear();
   for (size_t i = 0; i < items.size();) {
     if (i + 1 < items.size() && items[i + 1].n == items[i].n) {
       couples.push_back({items[i].p, items[i + 1].p, items[i].n, items[i].Lq});  // a has the longer query
@@ -332,99 +415,201 @@ void build_tasks(aadp_ctx* c) {
   }
   // stable order by query length, longest first (longest tasks are scheduled first)
   if ((int64_t)maxLq + 1 <= (int64_t)4 * (int64_t)couples.size() + 65536) {
-    std::vector<int32_t> cnt((size_t)maxLq + 2, 0);
+    cnt.assign((size_t)maxLq + 2, 0);
     for (const Couple& cp : couples) cnt[(size_t)(maxLq - cp.Lq) + 1]++;
     for (int k = 0; k <= maxLq; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
-    std::vector<Couple> sorted(couples.size());
+    std::vector<Couple>& sorted = S.couples2;
+    sorted.resize(couples.size());
     for (const Couple& cp : couples) sorted[(size_t)cnt[(size_t)(maxLq - cp.Lq)]++] = cp;
     couples.swap(sorted);
   } else {
     std::stable_sort(couples.begin(), couples.end(), [](const Couple& x, const Couple& y) { return x.Lq > y.Lq; });
   }
-  b.tasks.reserve(couples.size() * 64 / 2 + 4096);
   struct Open { int64_t task; int used; };
-  std::vector<Open> open;
-  auto new_task = [&]() {
-    b.tasks.resize(b.tasks.size() + 64, -1);
-    return b.n_tasks++;
-  };
+  Open open[49];
+  int n_open = 0;
+  int64_t n_tasks = 0;
   for (const Couple& cp : couples) {
     int best = -1;
-    for (size_t k = 0; k < open.size(); ++k)
-      if (32 - open[k].used >= cp.n && (best < 0 || open[k].used > open[best].used)) best = (int)k;
+    for (int k = 0; k < n_open; ++k)
+      if (32 - open[k].used >= cp.n && (best < 0 || open[k].used > open[best].used)) best = k;
     if (best < 0) {
-      if (open.size() >= 48) open.erase(open.begin());  // oldest open task: its query lengths are the least similar
-      open.push_back({new_task(), 0});
-      best = (int)open.size() - 1;
+      if (n_open >= 48) {  // drop the oldest open task: its query lengths are the least similar
+        for (int k = 1; k < n_open; ++k) open[k - 1] = open[k];
+        --n_open;
+      }
+      out.resize(out.size() + 64, -1);
+      open[n_open] = {n_tasks++, 0};
+      best = n_open++;
     }
     Open& o = open[best];
+    int32_t* dst = &out[(size_t)o.task * 64 + o.used];
     for (int l = 0; l < cp.n; ++l) {
-      b.tasks[o.task * 64 + o.used + l] = cp.a;
-      b.tasks[o.task * 64 + 32 + o.used + l] = cp.b;
+      dst[l] = cp.a;
+      dst[32 + l] = cp.b;
     }
     o.used += cp.n;
-    if (o.used == 32) open.erase(open.begin() + best);
+    if (o.used == 32) {
+      for (int k = best + 1; k < n_open; ++k) open[k - 1] = open[k];
+      --n_open;
+    }
   }
 }
 
-int build_batch_meta(aadp_ctx* c, uint32_t what) {
+// Classifies every pair (packed / int32 / wavefront), sizes its resident products and builds the packed
+// task list.  All O(npairs) passes run on `host_threads` threads over disjoint pair ranges; the per-range
+// task lists (each longest first) are interleaved round-robin so the global order stays longest first.
+// The interleaved task list is assembled directly in the pinned staging pool (*tasks_pinned).
+int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
   Batch& b = c->b;
   const int64_t np = b.npairs;
-  b.tb_off.assign(np + 1, 0);
-  b.sc_off.assign(np + 1, 0);
-  b.mask_off.assign(np + 1, 0);
+  b.tb_off.resize(np + 1);
+  b.sc_off.resize(np + 1);
+  b.mask_off.resize(np + 1);
+  b.tb_off[0] = b.sc_off[0] = b.mask_off[0] = 0;
   b.order[0].clear();
   b.order[1].clear();
   b.max_Lq = b.max_Lt = 0;
   b.cells = 0;
   b.bucket_cells[0] = b.bucket_cells[1] = 0;
-  b.fmt.assign(np, 0);
+  b.fmt.resize(np);
   b.wave_pairs.clear();
   b.packed_cells = 0;
-  std::vector<int64_t> cells(np);
-  int64_t bound = 0;
-  for (int64_t p = 0; p < np; ++p) {
-    const int qs = b.pair_q[p], ts = b.pair_t[p];
-    if (qs < 0 || qs >= b.nseq || ts < 0 || ts >= b.nseq) return fail("pair index out of range");
-    const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
-    if (Lq < 0 || Lt < 0 || Lq > (1 << 24) || Lt > (1 << 24)) return fail("bad sequence length");
-    b.max_Lq = std::max<int>(b.max_Lq, (int)Lq);
-    b.max_Lt = std::max<int>(b.max_Lt, (int)Lt);
-    cells[p] = Lq * Lt;
-    b.cells += (double)cells[p];
-    // |score| bound in integer units: matches + one end gap on each side
-    const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
-    const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
-                           c->sc.ge <= 400 && c->sc.gi <= 2048;
-    // long pairs: one CTA per 256-column stripe, all stripes of both directions co-resident
-    const bool wave_ok = !packed_ok && c->allow_wave && Lq >= 1 && Lt > 512 && Lq * Lt >= (int64_t)c->wave_min_cells &&
-                         2 * ((Lt + 255) / 256) <= (int64_t)c->num_sms * 8;
-    b.fmt[p] = packed_ok ? 1 : (wave_ok ? 2 : 0);
-    if (packed_ok) {
-      b.packed_cells += (double)cells[p];
-    } else if (wave_ok) {
-      b.wave_pairs.push_back((int32_t)p);
-      bound = std::max(bound, bd);
-    } else {
-      b.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
-      b.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cells[p];
-      bound = std::max(bound, bd);
+  b.n_tasks = 0;
+  *tasks_pinned = nullptr;
+  int T = c->host_threads;
+  if (T <= 0) T = (int)std::min<unsigned>(std::max<unsigned>(std::thread::hardware_concurrency(), 1u), 8u);
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(T, np / 4096));
+  if ((int)c->sched.size() < T) c->sched.resize((size_t)T);
+  c->Lq32.resize((size_t)np);
+  c->Lt32.resize((size_t)np);
+  int32_t* const Lq32 = c->Lq32.data();
+  int32_t* const Lt32 = c->Lt32.data();
+  struct Part {
+    int err = 0, max_Lq = 0, max_Lt = 0;
+    int64_t bound = 0, sum[3] = {0, 0, 0};
+    double cells = 0, packed_cells = 0, bucket_cells[2] = {0, 0};
+  };
+  std::vector<Part> part((size_t)T);
+  auto range = [&](int t, int64_t* lo, int64_t* hi) { *lo = np * t / T; *hi = np * (t + 1) / T; };
+  // ---- pass 1: lengths, class, score bound
+  c->pool.run(T, [&](int t) {
+    Part P;
+    SchedScratch& S = c->sched[(size_t)t];
+    S.order[0].clear();
+    S.order[1].clear();
+    S.wave.clear();
+    int64_t lo, hi;
+    range(t, &lo, &hi);
+    for (int64_t p = lo; p < hi; ++p) {
+      const int qs = b.pair_q[p], ts = b.pair_t[p];
+      if (qs < 0 || qs >= b.nseq || ts < 0 || ts >= b.nseq) { P.err = 1; break; }
+      const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
+      if (Lq < 0 || Lt < 0 || Lq > (1 << 24) || Lt > (1 << 24)) { P.err = 2; break; }
+      Lq32[p] = (int32_t)Lq;
+      Lt32[p] = (int32_t)Lt;
+      P.max_Lq = std::max<int>(P.max_Lq, (int)Lq);
+      P.max_Lt = std::max<int>(P.max_Lt, (int)Lt);
+      const int64_t cl = Lq * Lt;
+      P.cells += (double)cl;
+      // |score| bound in integer units: matches + one end gap on each side
+      const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
+      const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
+                             c->sc.ge <= 400 && c->sc.gi <= 2048;
+      // long pairs: one CTA per 256-column stripe, all stripes of both directions co-resident
+      const bool wave_ok = !packed_ok && c->allow_wave && Lq >= 1 && Lt > 512 && cl >= (int64_t)c->wave_min_cells &&
+                           2 * ((Lt + 255) / 256) <= (int64_t)c->num_sms * 8;
+      b.fmt[(size_t)p] = packed_ok ? 1 : (wave_ok ? 2 : 0);
+      if (packed_ok) {
+        P.packed_cells += (double)cl;
+      } else if (wave_ok) {
+        S.wave.push_back((int32_t)p);
+        P.bound = std::max(P.bound, bd);
+      } else {
+        S.order[Lt <= 256 ? 0 : 1].push_back((int32_t)p);
+        P.bucket_cells[Lt <= 256 ? 0 : 1] += (double)cl;
+        P.bound = std::max(P.bound, bd);
+      }
     }
+    part[(size_t)t] = P;
+  });
+  int64_t bound = 0;
+  for (int t = 0; t < T; ++t) {
+    const Part& P = part[(size_t)t];
+    const SchedScratch& S = c->sched[(size_t)t];
+    if (P.err == 1) return fail("pair index out of range");
+    if (P.err == 2) return fail("bad sequence length");
+    b.max_Lq = std::max(b.max_Lq, P.max_Lq);
+    b.max_Lt = std::max(b.max_Lt, P.max_Lt);
+    b.cells += P.cells;
+    b.packed_cells += P.packed_cells;
+    bound = std::max(bound, P.bound);
+    for (int k = 0; k < 2; ++k) {
+      b.bucket_cells[k] += P.bucket_cells[k];
+      b.order[k].insert(b.order[k].end(), S.order[k].begin(), S.order[k].end());
+    }
+    b.wave_pairs.insert(b.wave_pairs.end(), S.wave.begin(), S.wave.end());
   }
-  build_tasks(c);
   b.st_mode = bound < 30000 ? 1 : 2;
   if (bound >= (1 << 24)) return fail("scores exceed the exactly-representable float range (2^24 units)");
-  for (int64_t p = 0; p < np; ++p) {  // product offsets (scores in int16 units; 16-byte aligned per pair)
-    const int qs = b.pair_q[p], ts = b.pair_t[p];
-    const int64_t Lq = b.seq_off[qs + 1] - b.seq_off[qs], Lt = b.seq_off[ts + 1] - b.seq_off[ts];
-    const Layout L = make_layout((int)Lq, (int)Lt, b.fmt[p] == 1, 0);
-    const int64_t units = (b.fmt[p] == 1 || b.st_mode == 1) ? 1 : 2;
-    b.tb_off[p + 1] = b.tb_off[p] + ((what & AADP_W_TB) ? round_up64(layout_tb_bytes(L), 16) : 0);
-    b.sc_off[p + 1] = b.sc_off[p] + ((what & (AADP_W_SCORES | AADP_W_MASK)) ? round_up64(layout_sc_elems(L) * units, 8) : 0);
-    b.mask_off[p + 1] = b.mask_off[p] + ((what & AADP_W_MASK) ? round_up64(layout_mask_words(L), 4) : 0);
+  // ---- pass 2: product sizes (scores in int16 units; 16-byte aligned per pair) and the packed tasks
+  const bool want_tb = (what & AADP_W_TB) != 0, want_sc = (what & (AADP_W_SCORES | AADP_W_MASK)) != 0,
+             want_mk = (what & AADP_W_MASK) != 0;
+  c->pool.run(T, [&](int t) {
+    int64_t lo, hi, s0 = 0, s1 = 0, s2 = 0;
+    range(t, &lo, &hi);
+    for (int64_t p = lo; p < hi; ++p) {
+      const Layout L = make_layout(Lq32[p], Lt32[p], b.fmt[(size_t)p] == 1, 0);
+      const int64_t units = (b.fmt[(size_t)p] == 1 || b.st_mode == 1) ? 1 : 2;
+      const int64_t z0 = want_tb ? round_up64(layout_tb_bytes(L), 16) : 0;
+      const int64_t z1 = want_sc ? round_up64(layout_sc_elems(L) * units, 8) : 0;
+      const int64_t z2 = want_mk ? round_up64(layout_mask_words(L), 4) : 0;
+      s0 += z0; s1 += z1; s2 += z2;
+      b.tb_off[(size_t)p + 1] = s0;  // range-local inclusive sums; the range base is added below
+      b.sc_off[(size_t)p + 1] = s1;
+      b.mask_off[(size_t)p + 1] = s2;
+    }
+    part[(size_t)t].sum[0] = s0; part[(size_t)t].sum[1] = s1; part[(size_t)t].sum[2] = s2;
+    build_tasks_range(b, Lq32, Lt32, lo, hi, c->sched[(size_t)t]);
+  });
+  // ---- range bases, then: add them to the offsets and interleave the per-range task lists round-robin
+  // (task i of range t goes right after task i of range t-1)
+  std::vector<int64_t> base((size_t)T * 3 + 3, 0), nt((size_t)T);
+  int64_t total = 0;
+  for (int t = 0; t < T; ++t) {
+    for (int k = 0; k < 3; ++k) base[(size_t)(t + 1) * 3 + k] = base[(size_t)t * 3 + k] + part[(size_t)t].sum[k];
+    nt[(size_t)t] = (int64_t)c->sched[(size_t)t].tasks.size() / 64;
+    total += nt[(size_t)t];
   }
+  b.n_tasks = total;
+  {
+    const size_t at = (c->pin_used + 63) / 64 * 64, bytes = (size_t)total * 64 * sizeof(int32_t);
+    if (at + bytes > c->pin_cap) return fail("internal: pinned staging pool too small");
+    *tasks_pinned = reinterpret_cast<int32_t*>(c->pin + at);
+    c->pin_used = at + bytes;
+  }
+  int32_t* const tdst = *tasks_pinned;
+  c->pool.run(T, [&](int t) {
+    int64_t lo, hi;
+    range(t, &lo, &hi);
+    const int64_t b0 = base[(size_t)t * 3], b1 = base[(size_t)t * 3 + 1], b2 = base[(size_t)t * 3 + 2];
+    if (t > 0)
+      for (int64_t p = lo; p < hi; ++p) {
+        b.tb_off[(size_t)p + 1] += b0;
+        b.sc_off[(size_t)p + 1] += b1;
+        b.mask_off[(size_t)p + 1] += b2;
+      }
+    const std::vector<int32_t>& src = c->sched[(size_t)t].tasks;
+    for (int64_t i = 0; i < nt[(size_t)t]; ++i) {
+      int64_t pos = 0;
+      for (int u = 0; u < T; ++u) pos += std::min(nt[(size_t)u], i) + ((u < t && nt[(size_t)u] > i) ? 1 : 0);
+      memcpy(tdst + pos * 64, &src[(size_t)i * 64], 64 * sizeof(int32_t));
+    }
+  });
   for (int k = 0; k < 2; ++k)
-    std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
+    std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) {
+      return (int64_t)Lq32[x] * Lt32[x] > (int64_t)Lq32[y] * Lt32[y];
+    });
   return 0;
 }
 
@@ -701,6 +886,7 @@ aadp_ctx* aadp_create(int device) {
     return nullptr;
   }
   c->stream = c->own_stream;
+  if (const char* e = getenv("AADP_HOST_THREADS")) c->host_threads = atoi(e);
   return c;
 }
 
@@ -734,6 +920,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "packed")) { c->allow_packed = value != 0; return 0; }
   if (!strcmp(key, "wave")) { c->allow_wave = value != 0; return 0; }
   if (!strcmp(key, "wave_min_cells")) { c->wave_min_cells = value; return 0; }
+  if (!strcmp(key, "host_threads")) { c->host_threads = value; return 0; }
   return fail(std::string("unknown option ") + key);
 }
 
@@ -834,11 +1021,17 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
   // 2. ... and build the schedule on the host while they run
   const auto t_meta0 = std::chrono::steady_clock::now();
-  if (build_batch_meta(c, what)) return 1;
+  int32_t* tasks_pinned = nullptr;
+  if (build_batch_meta(c, what, &tasks_pinned)) return 1;
   const auto t_meta1 = std::chrono::steady_clock::now();
   b.uploaded_what = what;
   b.ran_what = 0;
-  if (upload_vec(c, c->tasks, b.tasks)) return 1;
+  {  // the task list was assembled in the pinned pool already
+    const size_t bytes = (size_t)b.n_tasks * 64 * sizeof(int32_t);
+    if (c->tasks.reserve(std::max<size_t>(bytes, 16))) return 1;
+    if (bytes) CK(cudaMemcpyAsync(c->tasks.p, tasks_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)bytes;
+  }
   if (upload_vec(c, c->fmt, b.fmt)) return 1;
   if (upload_vec(c, c->pair_q, b.pair_q)) return 1;
   if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
