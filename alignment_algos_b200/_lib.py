@@ -59,6 +59,11 @@ def lib():
     L.aadp_batch_tb_bytes.argtypes = [vp, i64]
     L.aadp_batch_fetch_tb.argtypes = [vp, i64, C.c_int, vp, i64, vp]
     L.aadp_decode_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, vp, vp]
+    L.aadp_upload_sequences.argtypes = [vp, vp, vp, i64]
+    L.aadp_cross_run.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.aadp_cross_scores.argtypes = [vp, vp, vp, i64, vp, i64, vp, i64, vp]
+    L.aadp_last_cross_cell_updates.restype = C.c_double
+    L.aadp_last_cross_cell_updates.argtypes = [vp]
     _lib = L
     return L
 
@@ -69,5 +74,6 @@ EXPORTS = [
     "aadp_upload_batch", "aadp_run_batch", "aadp_batch_resident_bytes", "aadp_last_launch_count",
     "aadp_last_h2d_bytes", "aadp_last_d2h_bytes", "aadp_last_cell_updates", "aadp_set_profiling", "aadp_profile_count", "aadp_profile_get",
     "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes", "aadp_batch_tb_bytes",
-    "aadp_batch_fetch_tb", "aadp_decode_cell",
+    "aadp_batch_fetch_tb", "aadp_decode_cell", "aadp_upload_sequences", "aadp_cross_run", "aadp_cross_scores",
+    "aadp_last_cross_cell_updates",
 ]

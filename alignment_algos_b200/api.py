@@ -120,6 +120,27 @@ class Context:
         """d_* are raw device pointers (ints) or None."""
         self._ck(self.L.aadp_run_batch(self.h, what, delta_ratio, d_fwd, d_rev, d_thr, d_cnt))
 
+    # ---- all queries x all templates, forward score only ----
+    def upload_sequences(self, residues, seq_off):
+        self._ck(self.L.aadp_upload_sequences(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1))
+
+    def cross_run(self, q_ids, t_ids, d_scores):
+        """d_scores: raw device pointer (int) to len(q_ids)*len(t_ids) floats."""
+        q_ids = np.ascontiguousarray(q_ids, np.int32)
+        t_ids = np.ascontiguousarray(t_ids, np.int32)
+        self._ck(self.L.aadp_cross_run(self.h, _ptr(q_ids), len(q_ids), _ptr(t_ids), len(t_ids), d_scores))
+
+    def cross_scores(self, residues, seq_off, q_ids, t_ids):
+        q_ids = np.ascontiguousarray(q_ids, np.int32)
+        t_ids = np.ascontiguousarray(t_ids, np.int32)
+        out = np.zeros((len(q_ids), len(t_ids)), np.float32)
+        self._ck(self.L.aadp_cross_scores(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(q_ids),
+                                          len(q_ids), _ptr(t_ids), len(t_ids), _ptr(out)))
+        return out
+
+    def last_cross_cell_updates(self):
+        return self.L.aadp_last_cross_cell_updates(self.h)
+
     def resident_bytes(self, which):
         return self.L.aadp_batch_resident_bytes(self.h, which)
 

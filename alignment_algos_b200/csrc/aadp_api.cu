@@ -71,6 +71,7 @@ struct DevBuf {
 
 struct Batch {
   int64_t nseq = 0, npairs = 0;
+  bool have_seqs = false;
   std::vector<int64_t> seq_off;
   std::vector<int32_t> pair_q, pair_t;
   std::vector<int64_t> tb_off, sc_off, mask_off;  // per pair, +1 total at the end
@@ -137,6 +138,8 @@ struct aadp_ctx {
   std::vector<int32_t> Lq32, Lt32;
   int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
   DevBuf wave_bb, wave_ready, wave_part;
+  DevBuf x_layout, x_qc, x_qid, x_tid, x_scores;
+  double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
   uint8_t* pin = nullptr;
   size_t pin_cap = 0, pin_used = 0;
@@ -231,7 +234,7 @@ __global__ void arena_kernel(const uint8_t* __restrict__ res, const int64_t* __r
 
 template <int TBM, int FST, int MSK>
 int launch_packed_t(aadp_ctx* c, PackedParams& P) {
-  auto kern = packed_kernel<TBM, FST, MSK>;
+  auto kern = packed_kernel<TBM, FST, MSK, 0>;
   const int A = P.sc.A;
   const size_t smem = packed_smem_bytes(A, MSK);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -898,7 +901,8 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->sc_off, &c->mask_off, &c->tb[0], &c->tb[1], &c->scb[0], &c->scb[1], &c->mask, &c->fin_score[0],
                    &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
                    &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d,
-                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part};
+                   &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
+                   &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -972,20 +976,12 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
   return 0;
 }
 
-int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
-                      const int32_t* pair_t, int64_t npairs, uint32_t what) {
-  if (check_ctx(c, true)) return 1;
-  if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
-  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
-  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
-    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
-  const auto t_begin = std::chrono::steady_clock::now();
+// ---- the two halves of an upload.  Both only ENQUEUE work on the context stream (the pinned pool must
+// have been reserved by the caller) and leave the synchronisation to the caller.
+static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq) {
   Batch& b = c->b;
   b.nseq = nseq;
-  b.npairs = npairs;
   b.seq_off.assign(seq_off, seq_off + nseq + 1);
-  b.pair_q.assign(pair_q, pair_q + npairs);
-  b.pair_t.assign(pair_t, pair_t + npairs);
   const int64_t nres = seq_off[nseq];
   // aligned arena offsets (16-byte aligned sequences, zero padding absorbs read-ahead)
   b.aoff.assign(nseq + 1, 0);
@@ -999,13 +995,11 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
     cur += (L + 15) / 16 * 16;
   }
   const size_t arena_bytes = (size_t)(cur + maxL + 128);
-  // 1. start the big transfer and the device-side arena build / validation first ...
   if (!c->pin_flag && cudaHostAlloc((void**)&c->pin_flag, 64, cudaHostAllocDefault) != cudaSuccess) return fail("cudaHostAlloc failed");
-  if (pin_reserve(c, (size_t)(nseq + 1) * 12 + (size_t)npairs * (8 + 1 + 4 + 24 + 64 * 4 / 2 + 64) + 65536)) return 1;
   if (c->residues.reserve(std::max<size_t>(nres, 16))) return 1;
   if (c->arena_f.reserve(arena_bytes) || c->arena_r.reserve(arena_bytes) || c->badflag.reserve(16)) return 1;
-  c->h2d_bytes = nres;
-  c->d2h_bytes = 4;
+  c->h2d_bytes += nres;
+  c->d2h_bytes += 4;
   if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
   if (upload_vec(c, c->seq_off, b.seq_off)) return 1;
   if (upload_vec(c, c->aoff, b.aoff)) return 1;
@@ -1019,11 +1013,20 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  // 2. ... and build the schedule on the host while they run
-  const auto t_meta0 = std::chrono::steady_clock::now();
+  b.have_seqs = true;
+  return 0;
+}
+
+static size_t pairs_pin_bytes(int64_t npairs) { return (size_t)npairs * (8 + 1 + 4 + 24 + 64 * 4 / 2 + 64) + 65536; }
+
+// pair list -> classification, product sizes, packed task list, and their uploads
+static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what) {
+  Batch& b = c->b;
+  b.npairs = npairs;
+  b.pair_q.assign(pair_q, pair_q + npairs);
+  b.pair_t.assign(pair_t, pair_t + npairs);
   int32_t* tasks_pinned = nullptr;
   if (build_batch_meta(c, what, &tasks_pinned)) return 1;
-  const auto t_meta1 = std::chrono::steady_clock::now();
   b.uploaded_what = what;
   b.ran_what = 0;
   {  // the task list was assembled in the pinned pool already
@@ -1040,6 +1043,26 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   if (upload_vec(c, c->tb_off, b.tb_off)) return 1;
   if (upload_vec(c, c->sc_off, b.sc_off)) return 1;
   if (upload_vec(c, c->mask_off, b.mask_off)) return 1;
+  return 0;
+}
+
+int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                      const int32_t* pair_t, int64_t npairs, uint32_t what) {
+  if (check_ctx(c, true)) return 1;
+  if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
+  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
+    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  const auto t_begin = std::chrono::steady_clock::now();
+  Batch& b = c->b;
+  if (pin_reserve(c, (size_t)(nseq + 1) * 12 + pairs_pin_bytes(npairs))) return 1;
+  c->h2d_bytes = 0;
+  c->d2h_bytes = 0;
+  // 1. start the big transfer and the device-side arena build / validation first ...
+  if (upload_sequences_impl(c, residues, seq_off, nseq)) return 1;
+  // 2. ... and build the schedule on the host while they run
+  const auto t_meta0 = std::chrono::steady_clock::now();
+  if (set_pairs_impl(c, pair_q, pair_t, npairs, what)) return 1;
   const auto t_up = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers; the validation flag is back
   if (getenv("AADP_TIMING")) {
@@ -1047,10 +1070,171 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
       return std::chrono::duration<double, std::milli>(b - a).count();
     };
-    fprintf(stderr, "[aadp] upload: pre %.2f ms, schedule %.2f ms, stage+enqueue %.2f ms, drain %.2f ms (tasks %lld)\n",
-            ms(t_begin, t_meta0), ms(t_meta0, t_meta1), ms(t_meta1, t_up), ms(t_up, t_end), (long long)b.n_tasks);
+    fprintf(stderr, "[aadp] upload: sequences %.2f ms, schedule+stage %.2f ms, drain %.2f ms (tasks %lld)\n",
+            ms(t_begin, t_meta0), ms(t_meta0, t_up), ms(t_up, t_end), (long long)b.n_tasks);
   }
-  if (*c->pin_flag) return fail("residue code outside the substitution alphabet");
+  if (*c->pin_flag) { b.have_seqs = false; return fail("residue code outside the substitution alphabet"); }
+  return 0;
+}
+
+int aadp_upload_sequences(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq) {
+  return aadp_upload_batch(c, residues, seq_off, nseq, nullptr, nullptr, 0, 0);
+}
+
+// ---- cross mode: every query of a list against every template of a list, forward score only ----------
+__global__ void scatter_scores_kernel(const float* __restrict__ src, const int32_t* __restrict__ qi,
+                                      const int32_t* __restrict__ ti, int64_t n, int64_t nt, float* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[(int64_t)qi[i] * nt + ti[i]] = src[i];
+}
+
+int aadp_cross_run(aadp_ctx* c, const int32_t* q_ids, int64_t nq, const int32_t* t_ids, int64_t nt, float* d_scores) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (!b.have_seqs) return fail("aadp_cross_run: no resident sequences (call aadp_upload_sequences first)");
+  if (nq < 0 || nt < 0 || nq > 0x7fffffff || nt > 0x7fffffff) return fail("bad list size");
+  if ((nq && !q_ids) || (nt && !t_ids) || (nq && nt && !d_scores)) return fail("null argument");
+  c->launches = 0;
+  c->x_cells = 0;
+  if (nq == 0 || nt == 0) return 0;
+  auto len = [&](int32_t s2) { return b.seq_off[(size_t)s2 + 1] - b.seq_off[(size_t)s2]; };
+  for (int64_t i = 0; i < nq; ++i) if (q_ids[i] < 0 || q_ids[i] >= b.nseq) return fail("query id out of range");
+  for (int64_t i = 0; i < nt; ++i) if (t_ids[i] < 0 || t_ids[i] >= b.nseq) return fail("template id out of range");
+  // ---- which templates / queries qualify for the packed int16x2 kernel (same rules as build_batch_meta)
+  const bool packed_mode = c->allow_packed && !c->sc.local && c->sc.ge <= 400 && c->sc.gi <= 2048;
+  std::vector<int32_t> te, qe, tbad, qbad;  // LIST indices
+  int64_t maxLt = 0;
+  for (int64_t i = 0; i < nt; ++i) {
+    const int64_t L = len(t_ids[i]);
+    if (packed_mode && L >= 1 && L <= 512) { te.push_back((int32_t)i); maxLt = std::max(maxLt, L); }
+    else tbad.push_back((int32_t)i);
+  }
+  for (int64_t i = 0; i < nq; ++i) {
+    const int64_t L = len(q_ids[i]);
+    const int64_t bd = std::min(L, maxLt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (L + maxLt);
+    if (!te.empty() && L >= 1 && bd < kPackedBound) qe.push_back((int32_t)i);
+    else qbad.push_back((int32_t)i);
+  }
+  CK(cudaStreamSynchronize(c->stream));  // the pinned staging pool may still feed an earlier upload
+  if (pin_reserve(c, (size_t)(nq + nt) * 16 + (size_t)nt * 32 * 4 + 65536)) return 1;
+  if (!qe.empty()) {
+    // templates: best-fit decreasing by lane width into 32-lane layouts
+    std::vector<int32_t> layouts;
+    {
+      std::vector<std::vector<int32_t>> byn(33);
+      for (int32_t i : te) byn[(size_t)((len(t_ids[i]) + 15) / 16)].push_back(i);
+      std::vector<std::vector<int32_t>> open(33);  // open[u] = layouts with u lanes in use
+      int64_t nlay = 0;
+      for (int n = 32; n >= 1; --n)
+        for (int32_t i : byn[(size_t)n]) {
+          int u = 32 - n;
+          while (u > 0 && open[(size_t)u].empty()) --u;
+          int64_t lay;
+          if (u > 0) { lay = open[(size_t)u].back(); open[(size_t)u].pop_back(); }
+          else { lay = nlay++; layouts.resize(layouts.size() + 32, -1); }
+          for (int l = 0; l < n; ++l) layouts[(size_t)lay * 32 + u + l] = i;
+          if (u + n < 32) open[(size_t)(u + n)].push_back((int32_t)lay);
+        }
+    }
+    const int64_t nlay = (int64_t)layouts.size() / 32;
+    // queries: longest first, adjacent ones share a register (couple); an odd one out is paired with itself
+    std::stable_sort(qe.begin(), qe.end(), [&](int32_t x, int32_t y) { return len(q_ids[x]) > len(q_ids[y]); });
+    std::vector<int32_t> qc;
+    for (size_t i = 0; i < qe.size(); i += 2) { qc.push_back(qe[i]); qc.push_back(i + 1 < qe.size() ? qe[i + 1] : qe[i]); }
+    const int64_t nqc = (int64_t)qc.size() / 2;
+    std::vector<int32_t> qid(q_ids, q_ids + nq), tid(t_ids, t_ids + nt);
+    if (upload_vec(c, c->x_layout, layouts) || upload_vec(c, c->x_qc, qc) || upload_vec(c, c->x_qid, qid) ||
+        upload_vec(c, c->x_tid, tid)) return 1;
+    auto kern = packed_kernel<0, 0, 0, 1>;
+    const int A = c->sc.A;
+    const size_t smem = packed_smem_bytes(A, 0, 1);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
+    if (occ < 1) return fail("packed kernel does not fit on an SM");
+    const int64_t resident = (int64_t)c->num_sms * occ;
+    // query couples per item: reuse the template profile as often as possible while keeping >= 8 items per warp
+    int64_t group = std::max<int64_t>(1, std::min<int64_t>(8, nlay * nqc / (8 * resident)));
+    const int64_t ngroups = (nqc + group - 1) / group;
+    if (nlay * ngroups > 0x7fffffffLL) return fail("aadp_cross_run: too many work items; split the lists into blocks");
+    PackedParams Q{};
+    Q.sc = c->sc;
+    Q.sub8 = c->sub8.as<int8_t>();
+    Q.arena = c->arena_f.as<uint8_t>();
+    Q.aoff = c->aoff.as<int32_t>();
+    Q.seq_off = c->seq_off.as<int64_t>();
+    Q.n_tasks = (int)(nlay * ngroups);
+    Q.rev = 0;
+    if (c->counter.reserve(64)) return 1;
+    CK(cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
+    Q.counter = c->counter.as<unsigned int>() + 8;
+    Q.x_layout = c->x_layout.as<int32_t>();
+    Q.x_qc = c->x_qc.as<int32_t>();
+    Q.x_qid = c->x_qid.as<int32_t>();
+    Q.x_tid = c->x_tid.as<int32_t>();
+    Q.x_nlayouts = (int)nlay;
+    Q.x_nqc = (int)nqc;
+    Q.x_group = (int)group;
+    Q.x_nt = nt;
+    Q.x_scores = d_scores;
+    double sq = 0, st = 0;
+    for (int32_t i : qe) sq += (double)len(q_ids[i]);
+    for (int32_t i : te) st += (double)len(t_ids[i]);
+    Q.cells_hint = sq * st;
+    c->x_cells += sq * st;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(resident, Q.n_tasks));
+    c->prof_begin("packed_kernel<TB=0,FST=0,MSK=0,XM=1>fwd", Q.cells_hint);
+    kern<<<grid, kPackedWarps * 32, smem, c->stream>>>(Q);
+    c->prof_end();
+    CK(cudaGetLastError());
+    c->launches++;
+  }
+  // ---- everything else (long / empty sequences, local mode, scores beyond the int16 bound): explicit pair
+  // lists through the general batch path, scattered into the matrix.  This replaces the resident pair batch.
+  if (!qbad.empty() || !tbad.empty()) {
+    std::vector<int32_t> pq, pt, lq, lt;
+    const int64_t chunk = 1 << 20;
+    auto flush = [&]() -> int {
+      if (pq.empty()) return 0;
+      const int64_t n = (int64_t)pq.size();
+      CK(cudaStreamSynchronize(c->stream));
+      if (pin_reserve(c, pairs_pin_bytes(n) + (size_t)n * 8)) return 1;
+      const int64_t launches = c->launches;
+      if (set_pairs_impl(c, pq.data(), pt.data(), n, AADP_W_FWD)) return 1;
+      if (c->fscore[0].reserve((size_t)n * 4)) return 1;
+      if (aadp_run_batch(c, AADP_W_FWD, 0.f, c->fscore[0].as<float>(), nullptr, nullptr, nullptr)) return 1;
+      if (upload_vec(c, c->x_qc, lq) || upload_vec(c, c->x_layout, lt)) return 1;
+      scatter_scores_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(
+          c->fscore[0].as<float>(), c->x_qc.as<int32_t>(), c->x_layout.as<int32_t>(), n, nt, d_scores);
+      CK(cudaGetLastError());
+      c->launches += launches + 1;
+      c->x_cells += b.cells;
+      pq.clear(); pt.clear(); lq.clear(); lt.clear();
+      return 0;
+    };
+    auto add = [&](int32_t qi, int32_t ti) -> int {
+      pq.push_back(q_ids[qi]); pt.push_back(t_ids[ti]); lq.push_back(qi); lt.push_back(ti);
+      return (int64_t)pq.size() >= chunk ? flush() : 0;
+    };
+    for (int32_t qi : qbad) for (int64_t ti = 0; ti < nt; ++ti) if (add(qi, (int32_t)ti)) return 1;
+    for (int32_t qi : qe) for (int32_t ti : tbad) if (add(qi, ti)) return 1;
+    if (flush()) return 1;
+  }
+  return 0;
+}
+
+int aadp_cross_scores(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* q_ids,
+                      int64_t nq, const int32_t* t_ids, int64_t nt, float* scores) {
+  if (aadp_upload_sequences(c, residues, seq_off, nseq)) return 1;
+  const int64_t h2d = c->h2d_bytes;
+  if (nq <= 0 || nt <= 0) return (nq < 0 || nt < 0) ? fail("bad list size") : 0;
+  if (!scores) return fail("null argument");
+  if (c->x_scores.reserve((size_t)nq * nt * 4)) return 1;
+  if (aadp_cross_run(c, q_ids, nq, t_ids, nt, c->x_scores.as<float>())) return 1;
+  CK(cudaMemcpyAsync(scores, c->x_scores.p, (size_t)nq * nt * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->h2d_bytes += h2d;
+  c->d2h_bytes += nq * nt * 4;
   return 0;
 }
 
@@ -1202,6 +1386,8 @@ int aadp_profile_get(aadp_ctx* c, int idx, char* name, int name_cap, float* ms, 
   if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
   return 0;
 }
+
+double aadp_last_cross_cell_updates(aadp_ctx* c) { return c ? c->x_cells : 0; }
 
 double aadp_last_cell_updates(aadp_ctx* c) {
   if (!c) return 0;

@@ -46,8 +46,10 @@ constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must
 constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
 // per-warp cp.async staging: query rings (2 KB) + forward-score chunks (6 KB, reverse+mask pass only)
 __host__ __device__ constexpr int packed_stage_bytes(int msk) { return msk ? 2048 + 6144 : 2048; }
-__host__ __device__ inline size_t packed_smem_bytes(int A, int msk) {
-  return (size_t)((A * (A + 1) + 15) / 16 * 16) + (size_t)kPackedWarps * (32 * sizeof(int4) + packed_stage_bytes(msk) + 2 * A * 512);
+// xm (cross mode): both halves of a couple align against the SAME template, so one profile serves both
+__host__ __device__ inline size_t packed_smem_bytes(int A, int msk, int xm = 0) {
+  return (size_t)((A * (A + 1) + 15) / 16 * 16) +
+         (size_t)kPackedWarps * (32 * sizeof(int4) + packed_stage_bytes(msk) + (xm ? 1 : 2) * A * 512);
 }
 
 struct PackedParams {
@@ -77,6 +79,15 @@ struct PackedParams {
   int32_t* fin_kind;
   int32_t* fin_k;
   double cells_hint;
+  // ---- cross mode (XM = 1): every query of a list against every template of a list, forward score only.
+  // Work item = (layout, group of x_group query couples); a layout assigns 32 lanes to whole templates.
+  const int32_t* x_layout;   // n_layouts * 32: template LIST index of lane l, or -1
+  const int32_t* x_qc;       // n_qcouples * 2: query LIST indices of the two halves (both always valid)
+  const int32_t* x_qid;      // query list index -> sequence id
+  const int32_t* x_tid;      // template list index -> sequence id
+  int x_nlayouts, x_nqc, x_group;
+  long long x_nt;            // row stride of x_scores
+  float* x_scores;           // [query list index][template list index] = D[last][last].score
 };
 
 __device__ __forceinline__ uint32_t pk2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
@@ -130,17 +141,28 @@ struct RowSum {
   int diag, col;     // M(Lq,Lt) and the right-column candidate (lane owning column Lt only)
 };
 
-template <int TBM, int FST, int MSK>
+template <int TBM, int FST, int MSK, int XM>
 __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int8_t* prof, int4* red,
                                             uint8_t* stage, const int8_t* s_sub, int lane) {
   const Scoring& S = P.sc;
   const int gi = S.gi, ge = S.ge, A = S.A;
   const int W = 512;  // profile row stride: 32 lanes * 16 columns
   int8_t* profA = prof;
-  int8_t* profB = prof + A * W;
+  int8_t* profB = XM ? prof : prof + A * W;
 
-  // ---- who am I: pair ids of both halves, segment geometry
-  const int pid[2] = {P.tasks[task * 64 + lane], P.tasks[task * 64 + 32 + lane]};
+  // cross mode: this item's layout (which template each lane works on) and its group of query couples
+  int x_tl = -1, x_qc0 = 0, nrep = 1;
+  if (XM) {
+    const int layout = task % P.x_nlayouts, qg = task / P.x_nlayouts;
+    x_tl = P.x_layout[layout * 32 + lane];
+    x_qc0 = qg * P.x_group;
+    nrep = min(P.x_group, P.x_nqc - x_qc0);
+  }
+  for (int rep = 0; rep < nrep; ++rep) {
+  // ---- who am I: pair ids of both halves (cross mode: the template list index), segment geometry
+  int x_ql[2] = {0, 0};
+  if (XM) { x_ql[0] = P.x_qc[(x_qc0 + rep) * 2]; x_ql[1] = P.x_qc[(x_qc0 + rep) * 2 + 1]; }
+  const int pid[2] = {XM ? x_tl : P.tasks[task * 64 + lane], XM ? x_tl : P.tasks[task * 64 + 32 + lane]};
   const int prev_pid = __shfl_up_sync(0xffffffffu, pid[0], 1);
   const bool seg_start = (lane == 0) || (prev_pid != pid[0]);
   const unsigned starts = __ballot_sync(0xffffffffu, seg_start);
@@ -153,7 +175,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if (pid[h] >= 0) {
-      const int qs = P.pair_q[pid[h]], ts = P.pair_t[pid[h]];
+      const int qs = XM ? P.x_qid[x_ql[h]] : P.pair_q[pid[h]], ts = XM ? P.x_tid[pid[h]] : P.pair_t[pid[h]];
       Lq[h] = (int)(P.seq_off[qs + 1] - P.seq_off[qs]);
       Lt[h] = (int)(P.seq_off[ts + 1] - P.seq_off[ts]);
       qp[h] = P.arena + P.aoff[qs];
@@ -168,10 +190,11 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   nsteps = __reduce_max_sync(0xffffffffu, nsteps);
 
   // ---- template profiles: prof[a*512 + lane*16 + c] = sub8[a][t_(column of register c)], pads = -128
-  {
+  // (cross mode: one profile for both halves, built once per item and reused by every query couple)
+  if (!XM || rep == 0) {
     uint32_t tc[2][4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < (XM ? 1 : 2); ++h)
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         uint32_t x = 0;
@@ -188,7 +211,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     for (int a = 0; a < A; ++a) {
       const int8_t* row = s_sub + a * (A + 1);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < (XM ? 1 : 2); ++h) {
         uint4 o;
         uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
@@ -527,9 +550,13 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       int best = dg, kind = 0, k = Lt[h];
       if (Lt[h] >= 2 && rb > best) { best = rb; kind = 1; k = rk; }
       if (cl > best) { best = cl; kind = 2; k = -1; }
-      P.fin_score[pid[h]] = best;
-      P.fin_kind[pid[h]] = kind;
-      P.fin_k[pid[h]] = k;
+      if (XM) {
+        P.x_scores[(long long)x_ql[h] * P.x_nt + pid[h]] = (float)best * (1.f / (float)(1 << S.scale_log2));
+      } else {
+        P.fin_score[pid[h]] = best;
+        P.fin_kind[pid[h]] = kind;
+        P.fin_k[pid[h]] = k;
+      }
       if (MSK && P.threshold) P.threshold[pid[h]] = thr_f[h];
     }
     if (MSK && P.count) {
@@ -544,10 +571,11 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     }
   }
   __syncwarp();
+  }  // rep
 }
 
-template <int TBM, int FST, int MSK>
-__global__ void __launch_bounds__(kPackedWarps * 32, MSK ? 8 : 9) packed_kernel(const PackedParams P) {
+template <int TBM, int FST, int MSK, int XM>
+__global__ void __launch_bounds__(kPackedWarps * 32, XM ? 14 : (MSK ? 8 : 9)) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
@@ -556,7 +584,7 @@ __global__ void __launch_bounds__(kPackedWarps * 32, MSK ? 8 : 9) packed_kernel(
   int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
   constexpr int kStage = packed_stage_bytes(MSK);
   uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kStage;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kStage)) + warp * 2 * A * 512;
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kStage)) + warp * (XM ? 1 : 2) * A * 512;
   for (int x = threadIdx.x; x < A * (A + 1); x += blockDim.x) {
     const int a = x / (A + 1), b = x % (A + 1);
     s_sub[x] = (b < A) ? P.sub8[a * A + b] : (int8_t)-128;
@@ -567,7 +595,7 @@ __global__ void __launch_bounds__(kPackedWarps * 32, MSK ? 8 : 9) packed_kernel(
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_tasks) break;
-    packed_task<TBM, FST, MSK>(P, (int)item, prof, red, stage, s_sub, lane);
+    packed_task<TBM, FST, MSK, XM>(P, (int)item, prof, red, stage, s_sub, lane);
   }
 }
 

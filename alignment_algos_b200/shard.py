@@ -34,3 +34,33 @@ def gather_scores(local_values, local_idx, npairs, group=None):
         seen[idx] = True
     assert seen.all(), "a pair was not computed by any rank"
     return out
+
+
+def triangle_rects(nseq, block=1000, sub=250):
+    """Rectangles (q0, q1, t0, t1) of sequence-id ranges whose union covers every unordered pair i < j of
+    an all-vs-all job (query = i, template = j).  Off-diagonal blocks are full rectangles; a diagonal
+    block is split once more into `sub`-sized pieces whose diagonal squares are computed in full (their
+    lower halves are the only wasted work: about sub / (2 nseq) of the job)."""
+    rects = []
+    edges = list(range(0, nseq, block)) + [nseq]
+    for a in range(len(edges) - 1):
+        for b in range(a + 1, len(edges) - 1):
+            rects.append((edges[a], edges[a + 1], edges[b], edges[b + 1]))
+        se = list(range(edges[a], edges[a + 1], sub)) + [edges[a + 1]]
+        for x in range(len(se) - 1):
+            for y in range(x, len(se) - 1):
+                rects.append((se[x], se[x + 1], se[y], se[y + 1]))
+    return rects
+
+
+def rect_is_diagonal(r):
+    return r[0] == r[2] and r[1] == r[3]
+
+
+def shard_rects(rects, lens, world):
+    """Deal the rectangles of triangle_rects over ranks, balanced by cell count (LPT).  No collective on
+    the data path: every rank scores its own rectangles; the host gathers the score blocks."""
+    cs = np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.int64))])
+    cells = [(cs[r[1]] - cs[r[0]]) * (cs[r[3]] - cs[r[2]]) for r in rects]
+    parts = shard_pairs(cells, world)
+    return [[rects[i] for i in p] for p in parts]

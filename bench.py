@@ -179,6 +179,126 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks):
+    """C4: all-vs-all of N synthetic sequences (every unordered pair i<j, query=i, template=j), forward
+    score only, through the cross-mode entry points.  The upper triangle is cut into rectangles
+    (shard.triangle_rects) which are dealt over the ranks: STRONG scaling, no data-path collective."""
+    import torch
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import shard, synth
+    alpha, M = a.blosum62()
+    rng = np.random.default_rng(1004)
+    seqs = synth.random_seqs(rng, args.seqs, 100, 500)
+    lens = np.array([len(x) for x in seqs], np.int64)
+    res, off = a.Context.pack(seqs)
+    rects = shard.shard_rects(shard.triangle_rects(args.seqs), lens, world)[rank]
+    # useful work of the whole job: sum over i<j of Li*Lj
+    tot = float(lens.sum())
+    useful_cu = (tot * tot - float((lens.astype(np.float64) ** 2).sum())) / 2.0
+    n_pairs_job = args.seqs * (args.seqs - 1) // 2
+    sizes = [(r[1] - r[0]) * (r[3] - r[2]) for r in rects]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    d_scores = torch.empty(int(offs[-1]), dtype=torch.float32, device="cuda")
+    h_scores = torch.empty(int(offs[-1]), dtype=torch.float32).pin_memory()
+    res_p = torch.from_numpy(res.copy()).pin_memory()
+    off_p = torch.from_numpy(off.copy()).pin_memory()
+    ctx = a.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_scoring(M, GI, GE, a.SEMI_LOCAL)
+    ids = np.arange(args.seqs, dtype=np.int32)
+    ctx.upload_sequences(res_p.numpy(), off_p.numpy())
+    computed_cu = [0.0]
+    launches = [0]
+
+    def step_resident():
+        cu, ln = 0.0, 0
+        for k, (q0, q1, t0, t1) in enumerate(rects):
+            ctx.cross_run(ids[q0:q1], ids[t0:t1], d_scores.data_ptr() + 4 * int(offs[k]))
+            cu += ctx.last_cross_cell_updates()
+            ln += ctx.last_launch_count()
+        computed_cu[0], launches[0] = cu, ln
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.set_profiling(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    w1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    value = useful_cu * args.steps / (ms_total * 1e-3) / 1e9
+    # ---- end to end: sequences from pinned host memory, every score block back to the host
+    def step_e2e():
+        ctx.upload_sequences(res_p.numpy(), off_p.numpy())
+        step_resident()
+        h_scores.copy_(d_scores, non_blocking=True)
+        stream.synchronize()
+    step_e2e()
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    x1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(x0.elapsed_time(x1))
+    sampler.stop()
+    clocks = sampler.summary(w0, w1)
+    # spot check inside the bench: the two roles of a symmetric scoring scheme give the same optimum
+    k = next((i for i, r in enumerate(rects) if shard.rect_is_diagonal(r)), None)
+    if k is not None:
+        q0, q1, t0, t1 = rects[k]
+        blk = h_scores[int(offs[k]):int(offs[k + 1])].numpy().reshape(q1 - q0, t1 - t0)
+        assert np.array_equal(blk, blk.T), "all-vs-all block is not symmetric"
+    kms = sum(ms for _, ms, _ in prof)
+    kcells = sum(c for _, _, c in prof)
+    hbm_peak, peak_src, sm_max = load_peaks()
+    props = torch.cuda.get_device_properties(local_rank)
+    clk = (clocks["sm_mhz"] or sm_max) * 1e6
+    i_alg = 7.0  # SURVEY.md §8d instruction model of a score-only cell update
+    lane_peak = props.multi_processor_count * 128 * clk
+    dom_gcups = kcells / max(kms * 1e-3, 1e-9) / 1e9
+    # algorithmic HBM bytes: the residues of both sequences in, 4 bytes out, per pair
+    bytes_per_cu = (2 * float(lens.mean()) + 4.0) / float(lens.mean()) ** 2
+    line = {
+        "metric": "GCUPS forward score-only DP fill, all-vs-all", "value": value, "unit": "GCUPS", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "c4: all-vs-all of %d synthetic sequences (%d pairs i<j), L in [100,500], BLOSUM62 gi=12 ge=1 "
+                               "semi_local, forward score-only, cross-mode packed kernel" % (args.seqs, n_pairs_job),
+                   "rectangles_this_rank": len(rects), "cache": "each launch streams its own sequences; scores are written once",
+                   "sharding": "upper-triangle rectangles dealt over ranks (LPT by cells), no collective on the data path",
+                   "computed_over_useful": sum_over_ranks(computed_cu[0]) / useful_cu},
+        "pairs_per_s": n_pairs_job * args.steps / (ms_total * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": useful_cu * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(res.nbytes + off.nbytes),
+                "d2h_bytes_per_step": int(h_scores.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches[0] * args.steps),
+        "roofline": {"bound": "hbm", "kernel": "packed_kernel<TB=0,FST=0,MSK=0,XM=1>fwd", "achieved": dom_gcups * bytes_per_cu,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": dom_gcups * bytes_per_cu / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_cell_update": bytes_per_cu,
+                     "note": "score-only: HBM is not the binding roofline, see issue_roofline"},
+        "issue_roofline": {"kernel": "packed_kernel<TB=0,FST=0,MSK=0,XM=1>fwd", "i_alg": i_alg, "lane_ops_per_s": lane_peak,
+                           "ceiling_gcups": lane_peak / i_alg / 1e9, "achieved_gcups": dom_gcups,
+                           "frac": dom_gcups / (lane_peak / i_alg / 1e9), "sm_mhz": clk / 1e6},
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,9 +307,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pairs", type=int, default=100_000, help="pairs per GPU (C3 = 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
+    ap.add_argument("--seqs", type=int, default=20_000, help="sequences of the all-vs-all workload (C4 = 20000)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 (default, the headline): 100k pairs fwd+rev+traceback+mask; c2: 10k pairs forward "
-                         "score-only; c5: one 30k x 30k pair fwd+rev+traceback+mask (multi-CTA wavefront)")
+                         "score-only; c4: all-vs-all of --seqs sequences, forward score-only, strong scaling over ranks; "
+                         "c5: one 30k x 30k pair fwd+rev+traceback+mask (multi-CTA wavefront)")
     ap.add_argument("--long-len", type=int, default=30000)
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
@@ -230,6 +352,11 @@ def main():
 
     # ---- workload (synthetic, seeded; every rank owns its own C3-sized shard: weak scaling)
     alpha, M = a.blosum62()
+    if args.workload == "c4":
+        run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "c3":
         seqs, pq, pt = make_workload(rank, args.pairs)
         what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
@@ -344,7 +471,10 @@ def main():
     achieved_gbs = dom_cells * bytes_per_cu / (dom_ms * 1e-3) / 1e9
     props = torch.cuda.get_device_properties(local_rank)
     clk = (clocks["sm_mhz"] or sm_max) * 1e6
-    i_alg = 15.0  # SURVEY.md §8d instruction model for a cell update with traceback
+    i_alg = 15.0 if (what & a.W_TB) else 7.0  # SURVEY.md §8d instruction model: with traceback / score-only
+    if not (what & (a.W_TB | a.W_MASK | a.W_SCORES)):
+        bytes_per_cu = (2 * 300.0 + 4.0) / 300.0 ** 2  # score-only: residues in, one score out per pair
+        achieved_gbs = dom_cells * bytes_per_cu / (dom_ms * 1e-3) / 1e9
     lane_peak = props.multi_processor_count * 128 * clk
     dom_gcups = dom_cells / (dom_ms * 1e-3) / 1e9
     kernel_share = {k: v[0] / sum(x[0] for x in by.values()) for k, v in by.items()} if by else {}

@@ -102,6 +102,24 @@ int aadp_upload_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq
 int aadp_run_batch(aadp_ctx* ctx, uint32_t what, float delta_ratio, float* d_fwd_score,
                    float* d_rev_score, float* d_threshold, int64_t* d_nearopt_count);
 
+/* ---- all queries x all templates, forward score only (database-search / all-vs-all shape) ------
+ * Replaces the caller-side double loop `for q: for t: DPMatrix<..>(q, t, eval, forward, type);
+ * D[last][last].score` (aa_ali.cpp:74-90 run once per combination).  Sequences are uploaded once and
+ * stay resident; each call scores the rectangle q_ids x t_ids (sequence ids, may repeat, may overlap):
+ *   scores[i*nt + j] = forward optimum of query q_ids[i] against template t_ids[j].
+ * Templates of 1..512 residues whose scores fit the packed int16 domain run on the cross-mode packed
+ * kernel (one template profile shared by a group of query couples); every other combination is routed
+ * through the general pair-list path (which replaces the resident pair batch of this context).
+ * aadp_cross_run is asynchronous on the context stream and writes DEVICE memory (d_scores, nq*nt
+ * floats); aadp_cross_scores is the host-buffer convenience call (upload + run + download).          */
+int aadp_upload_sequences(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq);
+int aadp_cross_run(aadp_ctx* ctx, const int32_t* q_ids, int64_t nq, const int32_t* t_ids, int64_t nt,
+                   float* d_scores);
+int aadp_cross_scores(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,
+                      const int32_t* q_ids, int64_t nq, const int32_t* t_ids, int64_t nt, float* scores);
+/* Cell updates (sum of Lq*Lt over the rectangle) of the last aadp_cross_run. */
+double aadp_last_cross_cell_updates(aadp_ctx* ctx);
+
 /* Bytes of HBM the resident batch products occupy (0 if none). which: AADP_W_TB / _SCORES / _MASK */
 int64_t aadp_batch_resident_bytes(aadp_ctx* ctx, uint32_t which);
 /* Number of kernels launched by the last batch/pair call (for bench.py's gpu_launches). */

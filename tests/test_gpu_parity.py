@@ -302,3 +302,54 @@ def test_half_unit_scoring_and_large_gaps(ctx, blosum):
         for Lq, Lt in [(90, 130), (257, 31)]:
             q, t = rand_pair(rng, Lq, Lt)
             _check_pair(ctx, O, q, t, "gi%s ge%s at%d" % (gi, ge, at), mask_dr=0.05)
+
+
+@pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL, po.GLOBAL_LOCAL, po.LOCAL],
+                         ids=["global", "semi_local", "global_local", "local"])
+def test_cross_scores_all_queries_vs_all_templates(ctx, at):
+    # cross mode (one template profile shared by groups of query couples) against the oracle and against
+    # the pair-list batch path; the lists mix eligible sequences with empty ones and templates > 512
+    import alignment_algos_b200 as a
+    alpha20, M20 = a.blosum62()
+    rng = np.random.default_rng(41 + at)
+    lens = list(rng.integers(1, 140, 37)) + [0, 1, 16, 17, 512, 513, 600, 33]
+    seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in lens]
+    res, off = a.Context.pack(seqs)
+    q_ids = np.array([3, 0, 44, 38, 7, 37, 12, 5, 41, 9, 3, 20, 21, 22, 43], np.int32)   # repeats allowed, odd count
+    t_ids = np.arange(len(seqs), dtype=np.int32)[::-1].copy()
+    ctx.set_scoring(M20, 12, 1, at)
+    got = ctx.cross_scores(res, off, q_ids, t_ids)
+    O = po.Oracle(M20, 12, 1, at)
+    want = np.zeros_like(got)
+    for i, qs in enumerate(q_ids):
+        for j, ts in enumerate(t_ids):
+            want[i, j] = O.fill(seqs[qs], seqs[ts], po.FWD, False, fast=True)[0][-1, -1]
+    assert_matrix_equal("cross scores", got, want)
+    # the same rectangle as an explicit pair list
+    pq = np.repeat(q_ids, len(t_ids)).astype(np.int32)
+    pt = np.tile(t_ids, len(q_ids)).astype(np.int32)
+    out = ctx.fill_batch(res, off, pq, pt, a.W_FWD)
+    assert_matrix_equal("cross == pair list", got.reshape(-1), out["fwd_score"])
+
+
+def test_cross_scores_block_properties(ctx):
+    # larger rectangle: symmetry of semi_local/global scores under swapping roles (BLOSUM62 is symmetric),
+    # block decomposition gives the same matrix, self-scores on the diagonal
+    import alignment_algos_b200 as a
+    import torch
+    alpha20, M20 = a.blosum62()
+    rng = np.random.default_rng(5)
+    seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(100, 501, 300)]
+    res, off = a.Context.pack(seqs)
+    ids = np.arange(300, dtype=np.int32)
+    ctx.set_scoring(M20, 12, 1, a.SEMI_LOCAL)
+    full = ctx.cross_scores(res, off, ids, ids)
+    assert_matrix_equal("symmetry", full, full.T)
+    diag = np.array([sum(M20[x, x] for x in s) for s in seqs], np.float32)
+    assert_matrix_equal("self score", np.diag(full), diag)
+    ctx.upload_sequences(res, off)
+    d = torch.zeros((100, 150), dtype=torch.float32, device="cuda")
+    ctx.cross_run(ids[50:150], ids[150:300], d.data_ptr())
+    ctx.synchronize()
+    assert_matrix_equal("block", d.cpu().numpy(), full[50:150, 150:300])
+    assert ctx.last_cross_cell_updates() == float(sum(len(s) for s in seqs[50:150])) * float(sum(len(s) for s in seqs[150:300]))
