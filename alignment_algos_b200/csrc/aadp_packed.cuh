@@ -575,7 +575,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 }
 
 template <int TBM, int FST, int MSK, int XM>
-__global__ void __launch_bounds__(kPackedWarps * 32, XM ? 14 : (MSK ? 8 : 9)) packed_kernel(const PackedParams P) {
+__global__ void __launch_bounds__(kPackedWarps * 32, XM ? 12 : (MSK ? 8 : 9)) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
