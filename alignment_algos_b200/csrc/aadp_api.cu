@@ -4,6 +4,7 @@
 #include "../../include/aadp.h"
 #include "aadp_kernels.cuh"
 #include "aadp_packed.cuh"
+#include "aadp_general.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -139,6 +140,12 @@ struct aadp_ctx {
   int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
   DevBuf wave_bb, wave_ready, wave_part;
   DevBuf x_layout, x_qc, x_qid, x_tid, x_scores;
+  // exact general-gap fp32 path (aadp_general.cuh): scoring that is not on a dyadic grid, or forced
+  bool float_mode = false, force_float = false;
+  float gi_f = 0.f, ge_f = 0.f;
+  float last_delta = -1.f;
+  int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
+  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
   uint8_t* pin = nullptr;
@@ -902,7 +909,9 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fin_score[1], &c->fin_kind[0], &c->fin_kind[1], &c->fin_k[0], &c->fin_k[1], &c->counter, &c->bbuf,
                    &c->thr, &c->count, &c->fscore[0], &c->fscore[1], &c->scratch_a, &c->scratch_b, &c->scratch_c, &c->scratch_d,
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
-                   &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores};
+                   &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
+                   &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1]};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -925,6 +934,10 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "wave")) { c->allow_wave = value != 0; return 0; }
   if (!strcmp(key, "wave_min_cells")) { c->wave_min_cells = value; return 0; }
   if (!strcmp(key, "host_threads")) { c->host_threads = value; return 0; }
+  // exact_float = 1: route everything through the exact general-gap fp32 kernel (takes effect at the next
+  // aadp_set_scoring); scoring that is not on a dyadic grid always uses it
+  if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
+  if (!strcmp(key, "general_budget_mcells")) { c->gg_budget_cells = (int64_t)std::max(value, 1) * 1000000; return 0; }
   return fail(std::string("unknown option ") + key);
 }
 
@@ -947,8 +960,29 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
     for (int i = 0; i < A * A && ok; ++i) ok = (sub[i] * m == rintf(sub[i] * m));
     if (ok) s = t;
   }
-  if (s < 0)
-    return fail("scores/penalties do not share a dyadic grid (2^-8); the exact integer path cannot represent them");
+  c->sc.A = A;
+  c->sc.delfree = (align_type == AADP_LOCAL || align_type == AADP_SEMI_LOCAL || align_type == AADP_LOCAL_GLOBAL);
+  c->sc.insfree = (align_type == AADP_LOCAL || align_type == AADP_SEMI_LOCAL || align_type == AADP_GLOBAL_LOCAL);
+  c->sc.local = (align_type == AADP_LOCAL);
+  c->align_type = align_type;
+  c->flags = flags;
+  c->gi_f = gi;
+  c->ge_f = ge;
+  if (c->subf.reserve((size_t)A * A * 4)) return 1;
+  CK(cudaMemcpyAsync(c->subf.p, sub, (size_t)A * A * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->b.ran_what = 0;
+  if (s < 0 || c->force_float) {
+    // not representable on an integer grid (e.g. the reference defaults 4.73 / 0.34, alib.cpp:17-18): the exact
+    // general-gap fp32 kernel reproduces the reference's own scan and roundings (aadp_general.cuh)
+    c->float_mode = true;
+    c->sc.gi = c->sc.ge = 0;
+    c->sc.scale_log2 = 0;
+    c->max_abs_sub = 0;
+    c->have_scoring = true;
+    return 0;
+  }
+  c->float_mode = false;
   const float m = (float)(1 << s);
   c->sub8_h.resize((size_t)A * A);
   int mx = 0;
@@ -1025,6 +1059,21 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
   b.npairs = npairs;
   b.pair_q.assign(pair_q, pair_q + npairs);
   b.pair_t.assign(pair_t, pair_t + npairs);
+  if (c->float_mode) {  // exact general-gap path: no packed schedule, no resident products
+    b.cells = 0;
+    b.n_tasks = 0;
+    b.tb_off.clear();
+    for (int64_t p = 0; p < npairs; ++p) {
+      const int qs = b.pair_q[p], ts = b.pair_t[p];
+      if (qs < 0 || qs >= b.nseq || ts < 0 || ts >= b.nseq) return fail("pair index out of range");
+      b.cells += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
+    }
+    b.uploaded_what = what;
+    b.ran_what = 0;
+    if (upload_vec(c, c->pair_q, b.pair_q)) return 1;
+    if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
+    return 0;
+  }
   int32_t* tasks_pinned = nullptr;
   if (build_batch_meta(c, what, &tasks_pinned)) return 1;
   b.uploaded_what = what;
@@ -1101,7 +1150,7 @@ int aadp_cross_run(aadp_ctx* c, const int32_t* q_ids, int64_t nq, const int32_t*
   for (int64_t i = 0; i < nq; ++i) if (q_ids[i] < 0 || q_ids[i] >= b.nseq) return fail("query id out of range");
   for (int64_t i = 0; i < nt; ++i) if (t_ids[i] < 0 || t_ids[i] >= b.nseq) return fail("template id out of range");
   // ---- which templates / queries qualify for the packed int16x2 kernel (same rules as build_batch_meta)
-  const bool packed_mode = c->allow_packed && !c->sc.local && c->sc.ge <= 400 && c->sc.gi <= 2048;
+  const bool packed_mode = c->allow_packed && !c->float_mode && !c->sc.local && c->sc.ge <= 400 && c->sc.gi <= 2048;
   std::vector<int32_t> te, qe, tbad, qbad;  // LIST indices
   int64_t maxLt = 0;
   for (int64_t i = 0; i < nt; ++i) {
@@ -1238,6 +1287,163 @@ int aadp_cross_scores(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
   return 0;
 }
 
+// ---- exact general-gap fp32 path (aadp_general.cuh) ------------------------------------------------
+// Fills the n consecutive pairs [p0, p0+n) of the batch in the directions of `dirmask` (bit 0 forward,
+// bit 1 reverse) into the dense scratch matrices of the context.  off = n+1 cell offsets of the pairs.
+static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
+                   float* d_fin_fwd, float* d_fin_rev) {
+  Batch& b = c->b;
+  const int64_t cells = off[(size_t)n];
+  int maxLt = 0, maxL = 0;
+  for (int64_t p = p0; p < p0 + n; ++p) {
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+    maxLt = std::max(maxLt, Lt);
+    maxL = std::max(maxL, std::max(Lq, Lt));
+  }
+  const size_t smem = (size_t)(maxLt + 2 + maxL + 2) * sizeof(float);
+  if (smem > 220 * 1024) return fail("exact general-gap path: sequences too long for the shared-memory row and penalty tables");
+  GeneralParams G{};
+  G.A = c->sc.A;
+  G.subf = c->subf.as<float>();
+  G.gi = c->gi_f;
+  G.ge = c->ge_f;
+  G.delfree = c->sc.delfree;
+  G.insfree = c->sc.insfree;
+  G.local = c->sc.local;
+  G.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
+  G.residues = c->residues.as<uint8_t>();
+  G.seq_off = c->seq_off.as<int64_t>();
+  G.pair_q = c->pair_q.as<int32_t>();
+  G.pair_t = c->pair_t.as<int32_t>();
+  G.items = nullptr;
+  G.item0 = (int)p0;
+  int nd = 0;
+  for (int d = 0; d < 2; ++d) {
+    if (!(dirmask & (1 << d))) continue;
+    if (c->gg_score[d].reserve(std::max<size_t>((size_t)cells * 4, 16))) return 1;
+    if (tb && (c->gg_pq[d].reserve(std::max<size_t>((size_t)cells * 4, 16)) || c->gg_pt[d].reserve(std::max<size_t>((size_t)cells * 4, 16)))) return 1;
+    G.dirs[nd] = d;
+    G.score[nd] = c->gg_score[d].as<float>();
+    G.prevq[nd] = tb ? c->gg_pq[d].as<int32_t>() : nullptr;
+    G.prevt[nd] = tb ? c->gg_pt[d].as<int32_t>() : nullptr;
+    G.fin[nd] = d ? d_fin_rev : d_fin_fwd;
+    ++nd;
+  }
+  if (nd == 0) return 0;
+  CK(cudaStreamSynchronize(c->stream));  // the pinned pool may still feed an earlier copy
+  if (pin_reserve(c, (size_t)(n + 1) * 8 + 4096)) return 1;
+  if (upload_vec(c, c->gg_off, off)) return 1;
+  G.dense_off = c->gg_off.as<int64_t>();
+  const int threads = std::max(64, std::min(512, (maxLt + 31) / 32 * 32));
+  double cu = 0;
+  for (int64_t p = p0; p < p0 + n; ++p) {
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  }
+  c->prof_begin(tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
+  if (tb) {
+    CK(cudaFuncSetAttribute(general_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    general_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
+  } else {
+    CK(cudaFuncSetAttribute(general_fill_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    general_fill_kernel<0><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
+  }
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+static int gg_mask(aadp_ctx* c, int64_t p0, int64_t n, float delta_ratio, const float* d_fin_fwd, bool dense_mask,
+                   int64_t cells, float* d_threshold, int64_t* d_count) {
+  GeneralMaskParams M{};
+  M.A = c->sc.A;
+  M.subf = c->subf.as<float>();
+  M.residues = c->residues.as<uint8_t>();
+  M.seq_off = c->seq_off.as<int64_t>();
+  M.pair_q = c->pair_q.as<int32_t>();
+  M.pair_t = c->pair_t.as<int32_t>();
+  M.items = nullptr;
+  M.item0 = (int)p0;
+  M.dense_off = c->gg_off.as<int64_t>();
+  M.F = c->gg_score[0].as<float>();
+  M.R = c->gg_score[1].as<float>();
+  M.fin_fwd = d_fin_fwd;
+  M.delta_ratio = delta_ratio;
+  if (dense_mask && c->gg_mask.reserve(std::max<size_t>((size_t)cells, 16))) return 1;
+  M.mask = dense_mask ? c->gg_mask.as<uint8_t>() : nullptr;
+  M.threshold = d_threshold;
+  M.count = reinterpret_cast<long long*>(d_count);
+  c->prof_begin("general_mask_kernel", 0);
+  general_mask_kernel<<<(unsigned)n, 256, 0, c->stream>>>(M);
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+// Batch run in exact-float mode: per-pair scalars only; the dense matrices live in scratch for the
+// duration of a chunk (aadp_batch_fetch_pair recomputes the pair it is asked for).
+static int gg_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
+                        float* d_threshold, int64_t* d_nearopt_count) {
+  Batch& b = c->b;
+  const int64_t np = b.npairs;
+  const int dirmask = ((what & AADP_W_FWD) ? 1 : 0) | ((what & AADP_W_REV) ? 2 : 0);
+  float* ffwd = d_fwd_score;
+  if ((what & AADP_W_MASK) && !ffwd) {
+    if (c->gg_fin[0].reserve(std::max<size_t>((size_t)np * 4, 16))) return 1;
+    ffwd = c->gg_fin[0].as<float>();
+  }
+  std::vector<int64_t> off;
+  for (int64_t p0 = 0; p0 < np;) {
+    off.assign(1, 0);
+    int64_t p1 = p0;
+    while (p1 < np) {
+      const int qs = b.pair_q[p1], ts = b.pair_t[p1];
+      const int64_t cl = (b.seq_off[qs + 1] - b.seq_off[qs] + 2) * (b.seq_off[ts + 1] - b.seq_off[ts] + 2);
+      if (p1 > p0 && off.back() + cl > c->gg_budget_cells) break;
+      off.push_back(off.back() + cl);
+      ++p1;
+    }
+    if (gg_fill(c, p0, p1 - p0, dirmask, false, off, ffwd, d_rev_score)) return 1;
+    if ((what & AADP_W_MASK) && gg_mask(c, p0, p1 - p0, delta_ratio, ffwd, false, off.back(), d_threshold, d_nearopt_count)) return 1;
+    p0 = p1;
+  }
+  c->last_delta = delta_ratio;
+  b.ran_what = what;
+  return 0;
+}
+
+// Dense, reference-shaped matrices of pair p in exact-float mode (recomputed on demand).
+static int gg_fetch_pair(aadp_ctx* c, int64_t p, float* score_fwd, int32_t* prevq_fwd, int32_t* prevt_fwd, float* score_rev,
+                         int32_t* prevq_rev, int32_t* prevt_rev, uint8_t* nearopt) {
+  Batch& b = c->b;
+  const int qs = b.pair_q[p], ts = b.pair_t[p];
+  const int64_t n = (b.seq_off[qs + 1] - b.seq_off[qs] + 2) * (b.seq_off[ts + 1] - b.seq_off[ts] + 2);
+  int dirmask = ((score_fwd || prevq_fwd || prevt_fwd) ? 1 : 0) | ((score_rev || prevq_rev || prevt_rev) ? 2 : 0);
+  if (nearopt) {
+    if (!(b.ran_what & AADP_W_MASK)) return fail("near-optimal mask was not computed (run with AADP_W_MASK)");
+    dirmask = 3;
+  }
+  if (!dirmask) return 0;
+  std::vector<int64_t> off = {0, n};
+  if (c->gg_fin[0].reserve(std::max<size_t>((size_t)b.npairs * 4, 16))) return 1;
+  if (gg_fill(c, p, 1, dirmask, true, off, c->gg_fin[0].as<float>(), nullptr)) return 1;
+  if (nearopt) {
+    if (gg_mask(c, p, 1, c->last_delta, c->gg_fin[0].as<float>(), true, n, nullptr, nullptr)) return 1;
+    CK(cudaMemcpyAsync(nearopt, c->gg_mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (score_fwd) CK(cudaMemcpyAsync(score_fwd, c->gg_score[0].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prevq_fwd) CK(cudaMemcpyAsync(prevq_fwd, c->gg_pq[0].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prevt_fwd) CK(cudaMemcpyAsync(prevt_fwd, c->gg_pt[0].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (score_rev) CK(cudaMemcpyAsync(score_rev, c->gg_score[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prevq_rev) CK(cudaMemcpyAsync(prevq_rev, c->gg_pq[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prevt_rev) CK(cudaMemcpyAsync(prevt_rev, c->gg_pt[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
                    float* d_threshold, int64_t* d_nearopt_count) {
   if (check_ctx(c, true)) return 1;
@@ -1250,6 +1456,7 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
   c->launches = 0;
   const int64_t np = b.npairs;
   if (np == 0) { b.ran_what = what; return 0; }
+  if (c->float_mode) return gg_run_batch(c, what, delta_ratio, d_fwd_score, d_rev_score, d_threshold, d_nearopt_count);
   if (c->counter.reserve(64)) return 1;
   CK(cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
   const int threads = 256;
@@ -1352,7 +1559,7 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
 int64_t aadp_batch_resident_bytes(aadp_ctx* c, uint32_t which) {
   if (!c) return 0;
   const Batch& b = c->b;
-  if (b.tb_off.empty()) return 0;
+  if (b.tb_off.empty() || c->float_mode) return 0;
   const int ndir = ((b.ran_what & AADP_W_FWD) ? 1 : 0) + ((b.ran_what & AADP_W_REV) ? 1 : 0);
   if (which == AADP_W_TB) return (b.ran_what & AADP_W_TB) ? b.tb_off[b.npairs] * ndir : 0;
   if (which == AADP_W_SCORES) return (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) ? b.sc_off[b.npairs] * 2 * ndir : 0;
@@ -1401,6 +1608,7 @@ int aadp_batch_fetch_pair(aadp_ctx* c, int64_t p, float* score_fwd, int32_t* pre
   if (p < 0 || p >= c->b.npairs) return fail("pair index out of range");
   if ((score_fwd || prevq_fwd || prevt_fwd) && !(c->b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
   if ((score_rev || prevq_rev || prevt_rev) && !(c->b.ran_what & AADP_W_REV)) return fail("reverse fill was not run");
+  if (c->float_mode) return gg_fetch_pair(c, p, score_fwd, prevq_fwd, prevt_fwd, score_rev, prevq_rev, prevt_rev, nearopt);
   if (dense_pair(c, p, 0, score_fwd, prevq_fwd, prevt_fwd)) return 1;
   if (dense_pair(c, p, 1, score_rev, prevq_rev, prevt_rev)) return 1;
   if (dense_mask(c, p, nearopt)) return 1;
@@ -1456,6 +1664,7 @@ int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int6
   if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
   const int dir = direction - 1;
   if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
+  if (c->float_mode) return fail("exact-float mode keeps no packed traceback; use aadp_batch_fetch_pair / aadp_batch_optimal");
   if (tb) {
     if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
     const int64_t need = b.tb_off[p + 1] - b.tb_off[p];
@@ -1509,6 +1718,40 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
   if (c->sc.local) return fail("aadp_batch_optimal: local tracebacks go through aadp_batch_fetch_pair (they need find_max)");
   const int qs = b.pair_q[p], ts = b.pair_t[p];
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  if (c->float_mode) {
+    // exact-float mode: dense predecessors of this pair are recomputed, then optimal.h:57-74 / optimal_rev.h:57-76
+    if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+    const bool rev = direction == AADP_REV;
+    if (!(b.ran_what & (rev ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
+    const int sz2 = Lt + 2;
+    const size_t n = (size_t)(Lq + 2) * sz2;
+    std::vector<float> sc(n);
+    std::vector<int32_t> pq(n), pt(n);
+    if (gg_fetch_pair(c, p, rev ? nullptr : sc.data(), rev ? nullptr : pq.data(), rev ? nullptr : pt.data(),
+                      rev ? sc.data() : nullptr, rev ? pq.data() : nullptr, rev ? pt.data() : nullptr, nullptr)) return 1;
+    int i = rev ? 0 : Lq + 1, j = rev ? 0 : Lt + 1;
+    const int ei = rev ? Lq + 1 : 0, ej = rev ? Lt + 1 : 0;
+    if (score) *score = sc[(size_t)i * sz2 + j];
+    std::vector<int32_t> path = {i, j};
+    int guard = 0;
+    while (rev ? (i < ei) : (i > 0)) {
+      const int32_t pi = pq[(size_t)i * sz2 + j], pj = pt[(size_t)i * sz2 + j];
+      i = pi;
+      j = pj;
+      path.push_back(i);
+      path.push_back(j);
+      if (i < 0 || j < 0 || ++guard > Lq + Lt + 4) break;
+    }
+    const int n2 = (int)path.size() / 2;
+    if (npairs) *npairs = n2;
+    for (int k = 0; k < n2 && k < max_pairs; ++k) {
+      const int src = rev ? k : n2 - 1 - k;
+      pairs[2 * k] = path[2 * src];
+      pairs[2 * k + 1] = path[2 * src + 1];
+    }
+    if (i != ei || j != ej) { g_err = "Illegal alignment start pair"; return 3; }
+    return 0;
+  }
   std::vector<uint8_t> tb((size_t)std::max<int64_t>(b.tb_off[p + 1] - b.tb_off[p], 1));
   int32_t fin[6];
   if (aadp_batch_fetch_tb(c, p, direction, tb.data(), (int64_t)tb.size(), fin)) return 1;

@@ -1,0 +1,250 @@
+// aadp_general.cuh -- exact GENERAL-GAP fill in fp32 for sm_100a.
+//
+// The reference fill is not an affine three-state recurrence: every interior cell (i,j) scans the whole
+// previous row and the whole previous column (dpmatrix.h:459-480) and evaluates, per candidate,
+//     s = D[pred].score;  s -= gap penalty;  s += sim[i][j];  if (s > opt_s) take it
+// in fp32.  For scores/penalties that are not on a common dyadic grid (the reference defaults 4.73 / 0.34,
+// alib.cpp:17-18) the O(mn) recurrence of aadp_kernels.cuh cannot reproduce those roundings, so this kernel
+// performs the SAME scan with the SAME fp32 operations in the SAME order -- results are bit-identical to
+// the reference (scores, every DPCell predecessor, the near-optimal cell set), 0 ulp.
+//
+// Parallel mapping.  Row a of the flow depends on rows < a only (the column scan of cell (a,b) reads
+// D[k][b-1] for k < a-1, the row scan reads D[a-1][k]): one CTA owns one (pair, direction), its threads own
+// the columns, rows are processed in order with the previous row and the penalty table in shared memory.
+// The column scan reads the score matrix itself (coalesced across the threads, L1/L2 resident).
+// Cost O(Lq*Lt*(Lq+Lt)) like the reference; many pairs run concurrently (grid = pairs x directions).
+//
+// Gap penalties: pen(len) = gi + ge*(float)(len-1) (aasubalib.h:37-38, two roundings: the multiply and the
+// add, no fused multiply-add) tabulated once per CTA; free end gaps per aasubalib.h:39-42,65-68.
+// Flow coordinates as everywhere in this library: the reverse fill is the forward fill of the mirrored
+// problem (dpmatrix.h:691-877 scans k descending in matrix coordinates = ascending in flow coordinates).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aadp {
+
+struct GeneralParams {
+  int A;
+  const float* subf;         // A*A substitution scores (SubstitutionMatrix::score, submatrix.h:36-38)
+  float gi, ge;
+  int delfree, insfree, local, repro_rev_bug;
+  const uint8_t* residues;
+  const int64_t* seq_off;
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  const int32_t* items;      // pair ids of this launch (blockIdx.x indexes it); null = identity + item0
+  int item0;
+  int dirs[2];               // blockIdx.y -> 0 forward, 1 reverse
+  const int64_t* dense_off;  // per item: offset (in cells) of its (Lq+2)*(Lt+2) matrices; null = 0
+  float* score[2];           // per direction: dense score matrices (always)
+  int32_t* prevq[2];         // per direction: dense predecessor rows/cols, or null
+  int32_t* prevt[2];
+  float* fin[2];             // per direction, per PAIR: score of the final cell, or null
+};
+
+__device__ __forceinline__ float gg_pen(float gi, float ge, int len) {  // aasubalib.h:37-38
+  return __fadd_rn(gi, __fmul_rn(ge, (float)(len - 1)));
+}
+
+template <int TBM>
+__global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P) {
+  extern __shared__ __align__(16) float gg_smem[];
+  const int item = blockIdx.x;
+  const int pair = P.items ? P.items[item] : P.item0 + item;
+  const int dsel = blockIdx.y;
+  const int rev = P.dirs[dsel];
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
+  const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
+  const int sz2 = Lt + 2, q1 = Lq + 1, t1 = Lt + 1;
+  const int64_t base = P.dense_off ? P.dense_off[item] : 0;
+  float* D = P.score[dsel] + base;
+  int32_t* PQ = TBM ? P.prevq[dsel] + base : nullptr;
+  int32_t* PT = TBM ? P.prevt[dsel] + base : nullptr;
+  const uint8_t* qseq = P.residues + qo;
+  const uint8_t* tseq = P.residues + to;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const float gi = P.gi, ge = P.ge;
+  const bool local = P.local != 0;
+
+  float* prow = gg_smem;              // D[a-1][0..Lt]
+  float* pen = gg_smem + (Lt + 2);    // pen[len], len >= 1
+  const int maxlen = max(Lq, Lt);
+  for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
+
+  // matrix index of flow cell (a,b); matrix row / column of a flow row / column
+  auto at = [&](int a, int b) -> int64_t { return (int64_t)(rev ? q1 - a : a) * sz2 + (rev ? t1 - b : b); };
+  auto rowof = [&](int a) { return rev ? q1 - a : a; };
+  auto colof = [&](int b) { return rev ? t1 - b : b; };
+  auto clampl = [&](float s) { return (local && s < 0.f) ? 0.f : s; };
+  auto sim = [&](int a, int b) -> float {  // flow cell -> substitution score (interior cells only)
+    const int i = rowof(a), j = colof(b);
+    return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
+  };
+  // gap between flow columns b0 < b1 / flow rows a0 < a1, with the free end gaps of aasubalib.h:39-42,65-68
+  // (flow column 0 / t1 are the Head and the Tail in either direction)
+  auto gdel = [&](int b0, int b1) -> float {
+    const int len = b1 - b0 - 1;
+    if (len < 1) return 0.f;
+    if (P.delfree && (b0 == 0 || b1 == t1)) return 0.f;
+    return pen[len];
+  };
+  auto gins = [&](int a0, int a1) -> float {
+    const int len = a1 - a0 - 1;
+    if (len < 1) return 0.f;
+    if (P.insfree && (a0 == 0 || a1 == q1)) return 0.f;
+    return pen[len];
+  };
+
+  // DPCell::DPCell (dpmatrix.cpp:17-25): score 0, predecessors null
+  for (int64_t o = tid; o < (int64_t)(Lq + 2) * sz2; o += nth) {
+    D[o] = 0.f;
+    if (TBM) { PQ[o] = -1; PT[o] = -1; }
+  }
+  __syncthreads();
+
+  auto set_tb = [&](int a, int b, int pa, int pb, float s) {  // dpmatrix.cpp:27-32
+    const int64_t o = at(a, b);
+    D[o] = s;
+    if (TBM) { PQ[o] = rowof(pa); PT[o] = colof(pb); }
+  };
+
+  // Special cases #1/#2 (dpmatrix.h:374-390, 712-728): an empty sequence forces one gap; not clamped
+  if (Lq == 0 || Lt == 0) {
+    if (tid == 0) {
+      float s = 0.f;
+      s = __fsub_rn(s, Lq == 0 ? gdel(0, t1) : gins(0, q1));
+      s = __fadd_rn(s, 0.f);
+      set_tb(q1, t1, 0, 0, s);
+      if (P.fin[dsel]) P.fin[dsel][pair] = s;
+    }
+    return;
+  }
+
+  // boundary row and column of the flow (dpmatrix.h:408-426, 746-764, 579-599, 920-940)
+  for (int b = 1 + tid; b <= Lt; b += nth) {
+    float s = 0.f;
+    if (b >= 2) s = __fsub_rn(s, gdel(0, b));
+    s = clampl(__fadd_rn(s, sim(1, b)));
+    set_tb(1, b, 0, 0, s);
+    prow[b] = s;
+  }
+  for (int a = 2 + tid; a <= Lq; a += nth) {
+    float s = 0.f;
+    s = __fsub_rn(s, gins(0, a));
+    s = clampl(__fadd_rn(s, sim(a, 1)));
+    set_tb(a, 1, 0, 0, s);
+  }
+  __syncthreads();
+
+  // interior rows (dpmatrix.h:446-497): match, deletions k ascending, insertions k ascending, strict '>'
+  for (int a = 2; a <= Lq; ++a) {
+    const int qa = qseq[rowof(a) - 1];
+    const float* subrow = P.subf + qa * P.A;
+    for (int b = 2 + tid; b <= Lt; b += nth) {
+      const float simc = subrow[(int)tseq[colof(b) - 1]];
+      int oa = a - 1, ob = b - 1;
+      float os = clampl(__fadd_rn(prow[b - 1], simc));
+      for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
+        float s = __fsub_rn(prow[k], pen[b - k - 1]);
+        s = clampl(__fadd_rn(s, simc));
+        if (s > os) { ob = k; os = s; }
+      }
+      bool col = false;
+      int ka = 0;
+      const float* colp = D + at(1, b - 1);
+      const int64_t cstride = rev ? -(int64_t)sz2 : (int64_t)sz2;
+      for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
+        float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]);
+        s = clampl(__fadd_rn(s, simc));
+        if (s > os) { col = true; ka = k; os = s; }
+      }
+      if (col) { oa = ka; ob = b - 1; }
+      set_tb(a, b, oa, ob, os);
+    }
+    __syncthreads();  // every thread is done reading the previous row
+    for (int b = 1 + tid; b <= Lt; b += nth) prow[b] = D[at(a, b)];  // own cells (b >= 2) and the boundary column
+    __syncthreads();
+  }
+
+  // final cell (dpmatrix.h:504-534, 844-874, 654-687, 995-1028): match, bottom row, right column.
+  // Its similarity is 0 (Tail / Head).  Serial: Lq + Lt candidates.
+  if (tid == 0) {
+    int oa = Lq, ob = Lt;
+    bool from_col = false;
+    float os = clampl(__fadd_rn(D[at(Lq, Lt)], 0.f));
+    for (int k = 1; k < t1; ++k) {
+      float s = __fsub_rn(D[at(Lq, k)], gdel(k, t1));
+      s = clampl(__fadd_rn(s, 0.f));
+      if (s > os) { oa = Lq; ob = k; os = s; }
+    }
+    for (int k = 1; k < q1; ++k) {
+      float s = __fsub_rn(D[at(k, Lt)], gins(k, q1));
+      s = clampl(__fadd_rn(s, 0.f));
+      if (s > os) { oa = k; ob = Lt; os = s; from_col = true; }
+    }
+    set_tb(q1, t1, oa, ob, os);
+    // dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 for left-column candidates
+    if (TBM && rev && !local && P.repro_rev_bug && from_col) PT[at(q1, t1)] = t1 - 1;
+    if (P.fin[dsel]) P.fin[dsel][pair] = os;
+  }
+}
+
+// Near-optimal cell set on dense matrices, the reference arithmetic: v = F + R; v -= sim; v > thr
+// (ucw.h:141-180 with the threshold of cw.h:86-88).  One CTA per item.
+struct GeneralMaskParams {
+  int A;
+  const float* subf;
+  const uint8_t* residues;
+  const int64_t* seq_off;
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  const int32_t* items;
+  int item0;
+  const int64_t* dense_off;
+  const float* F;
+  const float* R;
+  const float* fin_fwd;      // per pair
+  float delta_ratio;
+  uint8_t* mask;             // dense bytes per item (same offsets), or null
+  float* threshold;          // per pair, or null
+  long long* count;          // per pair, or null
+};
+
+__global__ void __launch_bounds__(256) general_mask_kernel(const GeneralMaskParams P) {
+  const int item = blockIdx.x;
+  const int pair = P.items ? P.items[item] : P.item0 + item;
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
+  const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
+  const int sz2 = Lt + 2;
+  const int64_t base = P.dense_off ? P.dense_off[item] : 0;
+  const float opt = P.fin_fwd[pair];
+  const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // cw.h:86-88
+  long long cnt = 0;
+  const int64_t n = (int64_t)(Lq + 2) * sz2;
+  for (int64_t o = threadIdx.x; o < n; o += blockDim.x) {
+    const int i = (int)(o / sz2), j = (int)(o % sz2);
+    uint8_t m = 0;
+    if (i >= 1 && i <= Lq && j >= 1 && j <= Lt) {
+      float v = __fadd_rn(P.F[base + o], P.R[base + o]);
+      v = __fsub_rn(v, P.subf[(int)P.residues[qo + i - 1] * P.A + (int)P.residues[to + j - 1]]);
+      m = v > thr ? 1 : 0;
+    }
+    if (P.mask) P.mask[base + o] = m;
+    cnt += m;
+  }
+  __shared__ long long s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (P.count) P.count[pair] = s_cnt;
+    if (P.threshold) P.threshold[pair] = thr;
+  }
+}
+
+}  // namespace aadp

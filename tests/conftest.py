@@ -22,3 +22,10 @@ def golden():
 def blosum():
     from alignment_algos_b200.submatrix import read_matrix, BLOSUM62
     return read_matrix(BLOSUM62)
+
+
+@pytest.fixture(scope="session")
+def golden_float():
+    # reference outputs for scoring that is NOT on a dyadic grid (oracle/gen_golden_float.py)
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_float.npz"))

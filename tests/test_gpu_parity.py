@@ -177,7 +177,9 @@ def test_errors_are_loud(ctx, blosum):
     import alignment_algos_b200 as a
     _, M = blosum
     with pytest.raises(a.AadpError):
-        ctx.set_scoring(M, 4.73, 0.34, po.SEMI_LOCAL)  # not on a dyadic grid: float path is out of scope
+        ctx.set_scoring(M, -1.0, 0.34, po.SEMI_LOCAL)  # negative gap penalty
+    with pytest.raises(a.AadpError):
+        ctx.set_scoring(M, 12, 1, 7)  # "Illegal gap style" (aasubalib.h:49)
     ctx.set_scoring(M, 12, 1, po.GLOBAL)
     with pytest.raises(a.AadpError):
         ctx.fill_pair(np.array([30], np.uint8), np.array([1], np.uint8))  # code outside the alphabet
@@ -353,3 +355,127 @@ def test_cross_scores_block_properties(ctx):
     ctx.synchronize()
     assert_matrix_equal("block", d.cpu().numpy(), full[50:150, 150:300])
     assert ctx.last_cross_cell_updates() == float(sum(len(s) for s in seqs[50:150])) * float(sum(len(s) for s in seqs[150:300]))
+
+
+# ---- exact general-gap fp32 path: scoring that is not on a dyadic grid (reference defaults 4.73 / 0.34) ----
+
+def test_float_golden_vectors_of_the_reference(golden_float):
+    # bit-exact (0 ulp) scores, identical predecessors, identical optimal alignments
+    import alignment_algos_b200 as a
+    g = golden_float
+    c = a.Context(0)
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        c.set_scoring(g["sub." + str(g[name + ".sub"])], gi, ge, at)
+        out = c.fill_pair(q, t, a.BOTH)
+        for nm in ("fwd", "rev"):
+            assert_matrix_equal(name + " score_" + nm, out["score_" + nm], g[name + "." + nm + ".score"])
+            assert_matrix_equal(name + " pq_" + nm, out["prevq_" + nm], g[name + "." + nm + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + " pt_" + nm, out["prevt_" + nm], g[name + "." + nm + ".pt"].astype(np.int32))
+        if at != po.LOCAL:
+            res, off = a.Context.pack([q, t])
+            c.fill_batch(res, off, [0], [1], a.W_FWD | a.W_REV)
+            for d, nm in ((a.FWD, "fwd"), (a.REV, "rev")):
+                rc, pairs, sc = c.optimal(0, d, len(q), len(t))
+                want_rc = int(g[name + "." + nm + ".opt_rc"][0])
+                assert (rc != 0) == (want_rc != 0), name + nm
+                if rc == 0:
+                    assert_matrix_equal(name + nm + ".opt", pairs, g[name + "." + nm + ".opt_pairs"].astype(np.int32))
+                    assert sc == g[name + "." + nm + ".opt_score"][0]
+    c.close()
+
+
+def test_float_ucw_union_equals_gpu_mask(golden_float):
+    import alignment_algos_b200 as a
+    g = golden_float
+    c = a.Context(0)
+    n = 0
+    for name in golden_cases(g):
+        for dr in (5, 20):
+            key = "%s.ucw%02d" % (name, dr)
+            if key + ".union" not in g:
+                continue
+            q, t, gi, ge, at = golden_case(g, name)
+            c.set_scoring(g["sub." + str(g[name + ".sub"])], gi, ge, at)
+            out = c.fill_pair(q, t, a.BOTH, delta_ratio=dr / 100.0)
+            shape = (len(q) + 2, len(t) + 2)
+            union = np.unpackbits(g[key + ".union"])[: shape[0] * shape[1]].reshape(shape)
+            interior = np.zeros_like(union)
+            interior[1:-1, 1:-1] = union[1:-1, 1:-1]
+            assert out["threshold"] == g[key + ".thr"][0]
+            assert_matrix_equal(key, out["nearopt"], interior)
+            n += 1
+    assert n >= 6
+    c.close()
+
+
+@pytest.mark.parametrize("at", MODES, ids=[MODE_NAMES[m] for m in MODES])
+def test_float_random_pairs_vs_literal_oracle(blosum, at):
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(900 + at)
+    c = a.Context(0)
+    c.set_scoring(M, 4.73, 0.34, at)
+    O = po.Oracle(M, 4.73, 0.34, at)
+    for Lq, Lt in [(0, 0), (0, 5), (4, 0), (1, 1), (2, 3), (33, 17), (64, 65), (120, 90), (5, 700)]:
+        q, t = rand_pair(rng, Lq, Lt)
+        out = c.fill_pair(q, t, a.BOTH, delta_ratio=0.05)
+        F, fq, ft = O.fill(q, t, po.FWD, True, fast=False)
+        R, rq, rt = O.fill(q, t, po.REV, True, fast=False)
+        tag = "float at%d %dx%d " % (at, Lq, Lt)
+        assert_matrix_equal(tag + "F", out["score_fwd"], F)
+        assert_matrix_equal(tag + "R", out["score_rev"], R)
+        assert_matrix_equal(tag + "fq", out["prevq_fwd"], fq)
+        assert_matrix_equal(tag + "ft", out["prevt_fwd"], ft)
+        assert_matrix_equal(tag + "rq", out["prevq_rev"], rq)
+        assert_matrix_equal(tag + "rt", out["prevt_rev"], rt)
+        thr = O.threshold(float(F[-1, -1]), 0.05)
+        mask, _ = O.nearopt_mask(F, R, O.sim(q, t), thr)
+        assert out["threshold"] == thr
+        assert_matrix_equal(tag + "mask", out["nearopt"], mask)
+    c.close()
+
+
+def test_float_batch_scalars_and_forced_float_equals_integer_path(blosum):
+    # (1) batches in exact-float mode: per-pair scalars against the literal oracle, chunked scratch;
+    # (2) forcing the general-gap kernel on integer scoring gives exactly what the integer kernels give
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    _, M = blosum
+    seqs, pq, pt = synth.pair_workload(11, 60, 5, 90)
+    res, off = a.Context.pack(seqs)
+    c = a.Context(0)
+    c.set_option("general_budget_mcells", 1)  # forces several chunks
+    c.set_scoring(M, 4.73, 0.34, po.SEMI_LOCAL)
+    O = po.Oracle(M, 4.73, 0.34, po.SEMI_LOCAL)
+    out = c.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_MASK, 0.02)
+    for p in range(len(pq)):
+        q, t = seqs[pq[p]], seqs[pt[p]]
+        F = O.fill(q, t, po.FWD, True, fast=False)[0]
+        R = O.fill(q, t, po.REV, True, fast=False)[0]
+        thr = O.threshold(float(F[-1, -1]), 0.02)
+        _, cnt = O.nearopt_mask(F, R, O.sim(q, t), thr)
+        assert out["fwd_score"][p] == F[-1, -1] and out["rev_score"][p] == R[0, 0]
+        assert out["threshold"][p] == thr and out["nearopt_count"][p] == cnt
+    got = c.fetch_pair(7, len(seqs[pq[7]]), len(seqs[pt[7]]), fwd=True, rev=True, mask=True)
+    F, fq, ft = O.fill(seqs[pq[7]], seqs[pt[7]], po.FWD, True, fast=False)
+    assert_matrix_equal("fetch F", got["score_fwd"], F)
+    assert_matrix_equal("fetch fq", got["prevq_fwd"], fq)
+    c.set_option("exact_float", 1)
+    c.set_scoring(M, 12, 1, po.GLOBAL)
+    c2 = a.Context(0)
+    c2.set_scoring(M, 12, 1, po.GLOBAL)
+    o1 = c.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_MASK, 0.02)
+    o2 = c2.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_MASK, 0.02)
+    for k in ("fwd_score", "rev_score", "threshold", "nearopt_count"):
+        assert_matrix_equal("forced float " + k, o1[k], o2[k])
+    x1 = c.fill_pair(seqs[0], seqs[1], a.BOTH, delta_ratio=0.02)
+    x2 = c2.fill_pair(seqs[0], seqs[1], a.BOTH, delta_ratio=0.02)
+    for k in x1:
+        if x1[k] is not None and k != "threshold":
+            assert_matrix_equal("forced float pair " + k, x1[k], x2[k])
+    # cross mode falls back to the general path in exact-float mode
+    ids = np.arange(12, dtype=np.int32)
+    assert_matrix_equal("cross float", c.cross_scores(res, off, ids, ids), c2.cross_scores(res, off, ids, ids))
+    c.close()
+    c2.close()

@@ -117,3 +117,17 @@ def test_threshold_formula():
         want = np.float32(min(np.float32(np.float32(1.0) - np.float32(dr)) * np.float32(opt),
                               np.float32(opt) - np.float32(0.1)))
         assert O.threshold(opt, dr) == want
+
+
+def test_oracle_literal_fill_matches_float_golden(golden_float):
+    # non-dyadic scoring (reference defaults 4.73 / 0.34, scaled matrix): only the literal O(n^3)
+    # restatement is exact there; it must reproduce every rounding of the real reference
+    g = golden_float
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        O = po.Oracle(g["sub." + str(g[name + ".sub"])], gi, ge, at)
+        for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+            s, pq, pt = O.fill(q, t, d, True, False)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
