@@ -193,6 +193,17 @@ class Context:
             raise AadpError(self.L.aadp_last_error().decode())
         return rc, pairs[: min(n.value, cap)].copy(), s.value
 
+    def optimal_all(self, direction, npairs):
+        """Optimal alignments of every pair of the resident batch (GPU traceback).
+        Returns (ali_off, pairs[(total,2)], n[npairs], status[npairs])."""
+        off = np.zeros(npairs + 1, np.int64)
+        self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), None, 0, None, None))
+        pairs = np.zeros((max(int(off[-1]), 1), 2), np.int32)
+        n = np.zeros(npairs, np.int32)
+        st = np.zeros(npairs, np.int32)
+        self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), _ptr(pairs), int(off[-1]), _ptr(n), _ptr(st)))
+        return off, pairs, n, st
+
     def fetch_tb(self, p, direction, Lq, Lt):
         nbytes = max(int(self.L.aadp_batch_tb_bytes(self.h, p)), 1)
         tb = np.zeros(nbytes, np.uint8)

@@ -145,6 +145,7 @@ struct aadp_ctx {
   float gi_f = 0.f, ge_f = 0.f;
   float last_delta = -1.f;
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
+  DevBuf ali_cap, ali_out, ali_n, ali_status;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -911,7 +912,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1]};
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -1784,6 +1785,58 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
     g_err = "Illegal alignment start pair";  // optimal.h:74
     return 3;
   }
+  return 0;
+}
+
+int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap, int32_t* n_out,
+                           int32_t* status) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  const int dir = direction - 1;
+  if (c->float_mode) return fail("aadp_batch_optimal_all: exact-float mode keeps no packed traceback (use aadp_batch_optimal)");
+  if (c->sc.local) return fail("aadp_batch_optimal_all: local tracebacks go through aadp_batch_fetch_pair (they need find_max)");
+  if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
+  if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
+  const int64_t np = b.npairs;
+  std::vector<int64_t> cap((size_t)np + 1, 0);
+  for (int64_t p = 0; p < np; ++p) {
+    const int qs = b.pair_q[p], ts = b.pair_t[p];
+    cap[(size_t)p + 1] = cap[(size_t)p] + (b.seq_off[qs + 1] - b.seq_off[qs]) + (b.seq_off[ts + 1] - b.seq_off[ts]) + 2;
+  }
+  if (ali_off) memcpy(ali_off, cap.data(), (size_t)(np + 1) * 8);
+  if (np == 0) return 0;
+  if (pairs && pairs_cap < cap[(size_t)np]) return fail("aadp_batch_optimal_all: pairs buffer too small (needs 2*ali_off[npairs] ints)");
+  CK(cudaStreamSynchronize(c->stream));
+  if (pin_reserve(c, (size_t)(np + 1) * 8 + 4096)) return 1;
+  if (upload_vec(c, c->ali_cap, cap)) return 1;
+  if (c->ali_out.reserve((size_t)cap[(size_t)np] * 8) || c->ali_n.reserve((size_t)np * 4) || c->ali_status.reserve((size_t)np * 4)) return 1;
+  TraceParams T{};
+  T.tb = c->tb[dir].as<uint8_t>();
+  T.tb_off = c->tb_off.as<int64_t>();
+  T.fmt = c->fmt.as<uint8_t>();
+  T.seq_off = c->seq_off.as<int64_t>();
+  T.pair_q = c->pair_q.as<int32_t>();
+  T.pair_t = c->pair_t.as<int32_t>();
+  T.fin_kind = c->fin_kind[dir].as<int32_t>();
+  T.fin_k = c->fin_k[dir].as<int32_t>();
+  T.n_pairs = (int)np;
+  T.rev = dir;
+  T.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
+  T.cap_off = c->ali_cap.as<int64_t>();
+  T.out = c->ali_out.as<int2>();
+  T.out_n = c->ali_n.as<int32_t>();
+  T.out_status = c->ali_status.as<int32_t>();
+  c->prof_begin(dir ? "traceback_kernel rev" : "traceback_kernel fwd", 0);
+  traceback_kernel<<<(unsigned)((np + 127) / 128), 128, 0, c->stream>>>(T);
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches = 1;
+  c->d2h_bytes = 0;
+  if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)np] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)np] * 8; }
+  if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
+  if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

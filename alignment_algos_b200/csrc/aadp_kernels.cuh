@@ -687,4 +687,77 @@ __global__ void dense_kernel(const DenseParams P) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Optimal alignments of a whole batch on the GPU: one thread per pair follows the
+// packed traceback in HBM from the final cell to the anchor -- Optimal::enumerate (optimal.h:47-75) for the
+// forward matrices, Optimal_Rev::enumerate (optimal_rev.h:47-78) for the reverse ones.  The walk is a chain
+// of dependent byte loads (latency bound), so the parallelism is across the pairs of the batch.
+// Output slot of pair p: cap_off[p] .. cap_off[p+1] (capacity Lq+Lt+2 aligned pairs), filled front to back
+// with (query_idx, template_idx) in matrix coordinates, including (0,0) and (last,last).
+// ------------------------------------------------------------------------------------------------
+struct TraceParams {
+  const uint8_t* tb;         // packed traceback blob of the direction
+  const int64_t* tb_off;
+  const uint8_t* fmt;        // per pair: 1 = packed (diagonal-major) layout, 0/2 = row-major
+  const int64_t* seq_off;
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  const int32_t* fin_kind;
+  const int32_t* fin_k;
+  int n_pairs;
+  int rev;                   // 0: forward matrices, 1: reverse matrices
+  int repro_rev_bug;
+  const int64_t* cap_off;    // per pair: first slot (in aligned pairs); slot p has Lq+Lt+2 entries
+  int2* out;                 // aligned pairs
+  int32_t* out_n;            // per pair: number of aligned pairs written
+  int32_t* out_status;       // per pair: 0, or 3 = "Illegal alignment start pair" (optimal.h:74)
+};
+
+__global__ void __launch_bounds__(128) traceback_kernel(const TraceParams P) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= P.n_pairs) return;
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int Lq = (int)(P.seq_off[qs + 1] - P.seq_off[qs]), Lt = (int)(P.seq_off[ts + 1] - P.seq_off[ts]);
+  const uint8_t* tb = P.tb + P.tb_off[pair];
+  const Layout L = make_layout(Lq, Lt, P.fmt[pair] == 1, P.rev);
+  const int kind = P.fin_kind[pair], fk = P.fin_k[pair];
+  int2* out = P.out + P.cap_off[pair];
+  const int cap = Lq + Lt + 2;
+  // flow coordinates: (a,b) runs from the final flow cell (Lq+1,Lt+1) down to the anchor (0,0)
+  int a = Lq + 1, b = Lt + 1, n = 0;
+  bool first = true, ok = true;
+  for (;;) {
+    // matrix coordinates of the current cell; forward alignments are built with prepend(): fill from the back
+    const int i = P.rev ? Lq + 1 - a : a, j = P.rev ? Lt + 1 - b : b;
+    if (n < cap) out[P.rev ? n : cap - 1 - n] = make_int2(i, j);
+    ++n;
+    if (a <= 0 || n > cap) break;  // optimal.h:61 loops while the query index is positive (rev: below last)
+    int pa = -1, pb = -1;
+    if (first) {
+      decode_final(tb, L, kind, fk, &pa, &pb);
+      // dpmatrix.h:868: the global reverse fill stores opt_j = t1_m1 (a MATRIX column) for left-column
+      // candidates; followed literally the walk leaves the legal path and the reference throws
+      if (P.rev && P.repro_rev_bug && kind == 2 && Lq > 0 && Lt > 0) pb = Lt + 1 - Lt;  // matrix column Lt -> flow column 1
+      first = false;
+    } else if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) {
+      decode_prev(tb, L, a, b, &pa, &pb);
+    }
+    if (pa < 0 || pb < 0) {  // DPCell::null reached: recorded like the reference would read it, then stop
+      if (n < cap) out[P.rev ? n : cap - 1 - n] = make_int2(-1, -1);
+      ++n;
+      ok = false;
+      break;
+    }
+    a = pa;
+    b = pb;
+  }
+  if (ok && (a != 0 || b != 0)) ok = false;  // "Illegal alignment start pair"
+  if (n > cap) { n = cap; ok = false; }
+  if (!P.rev && n < cap)  // move the tail-filled forward alignment to the front of its slot
+    for (int k = 0; k < n; ++k) out[k] = out[cap - n + k];
+  P.out_n[pair] = n;
+  P.out_status[pair] = ok ? 0 : 3;
+}
+
 }  // namespace aadp

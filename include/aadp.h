@@ -61,14 +61,23 @@ const char* aadp_version(void);
 int aadp_set_stream(aadp_ctx* ctx, void* cuda_stream);
 int aadp_synchronize(aadp_ctx* ctx);
 /* Tuning / test switches. "packed" (default 1): use the packed int16x2 kernels for every pair that
- * qualifies (non-local, Lt <= 512, |score| bound < 8000 units); 0 forces the int32 kernels.     */
+ * qualifies (non-local, Lt <= 512, |score| bound < 7000 units); 0 forces the int32 kernels.
+ * "wave" / "wave_min_cells": multi-CTA wavefront for long pairs.  "host_threads": host scheduler
+ * threads (0 = min(hardware, 8)).  "exact_float": see aadp_set_scoring.  "general_budget_mcells":
+ * scratch budget (10^6 dense cells per direction) of one chunk of an exact-float batch.            */
 int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
 
 /* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)
  * sub is A x A row-major, sub[q_code*A + t_code] == SubstitutionMatrix::score (submatrix.h:36-38).
  * gap(len) = gi + ge*(len-1) (aasubalib.h:37-38) with the per-align_type free end gaps of
- * aasubalib.h:27-77.  All of sub, gi, ge must lie on one dyadic grid (multiples of 2^-s, s<=8;
- * integer matrices trivially do): that is the class for which results are bit-exact.          */
+ * aasubalib.h:27-77.  Two exactness classes, both BIT-EXACT against the reference:
+ *   - sub, gi, ge on one dyadic grid (multiples of 2^-s, s<=8; integer matrices trivially are): the
+ *     fast O(Lq*Lt) integer kernels (packed int16x2 / int32 / multi-CTA wavefront);
+ *   - anything else (e.g. the reference defaults 4.73 / 0.34, alib.cpp:17-18): the exact general-gap
+ *     fp32 kernel, which performs the reference's own O(Lq*Lt*(Lq+Lt)) scan (dpmatrix.h:459-480) with
+ *     the same fp32 operations in the same order.  In this mode batches return per-pair scalars,
+ *     aadp_batch_fetch_pair / aadp_batch_optimal recompute the requested pair, and no packed
+ *     traceback is kept.  aadp_set_option("exact_float", 1) forces this class for any scoring.      */
 int aadp_set_scoring(aadp_ctx* ctx, const float* sub, int A, float gi, float ge, int align_type,
                      uint32_t flags);
 
@@ -151,6 +160,16 @@ int aadp_batch_fetch_pair(aadp_ctx* ctx, int64_t p, float* score_fwd, int32_t* p
  * "Illegal alignment start pair" when the reference would throw (optimal.h:74).                 */
 int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, int32_t max_pairs,
                        int32_t* npairs, float* score);
+
+/* Optimal alignments of EVERY pair of the resident batch, traced on the GPU: one thread per pair follows
+ * the packed traceback in HBM (Optimal::enumerate, optimal.h:47-75, for AADP_FWD; Optimal_Rev::enumerate,
+ * optimal_rev.h:47-78, for AADP_REV).  Needs a batch run with AADP_W_TB; not for local alignments.
+ *   ali_off  host, npairs+1 (out, may be NULL): slot p is ali_off[p]..ali_off[p+1] = Lq+Lt+2 aligned pairs
+ *   pairs    host, 2*ali_off[npairs] ints (may be NULL; pairs_cap = its capacity in aligned pairs): slot p holds
+ *            n_out[p] (query_idx, template_idx) pairs front to back, including (0,0) and (last,last)
+ *   status   host per pair: 0, or 3 where the reference throws "Illegal alignment start pair"           */
+int aadp_batch_optimal_all(aadp_ctx* ctx, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
+                           int32_t* n_out, int32_t* status);
 
 /* ---- packed traceback format helpers (host side, no GPU needed) ---------------------------
  * Row stride in bytes of the ROW-MAJOR packed traceback (int32 kernels) for template length Lt. */

@@ -479,3 +479,34 @@ def test_float_batch_scalars_and_forced_float_equals_integer_path(blosum):
     assert_matrix_equal("cross float", c.cross_scores(res, off, ids, ids), c2.cross_scores(res, off, ids, ids))
     c.close()
     c2.close()
+
+
+@pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL, po.GLOBAL_LOCAL, po.LOCAL_GLOBAL],
+                         ids=["global", "semi_local", "global_local", "local_global"])
+def test_gpu_traceback_of_whole_batch(ctx, at):
+    # aadp_batch_optimal_all (one GPU thread per pair) against the per-pair host walk and the oracle
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha20, M20 = a.blosum62()
+    rng = np.random.default_rng(70 + at)
+    seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in list(rng.integers(1, 200, 78)) + [0, 0, 530, 600]]
+    pq = np.arange(0, len(seqs), 2, dtype=np.int32)
+    pt = pq + 1
+    res, off = a.Context.pack(seqs)
+    ctx.set_scoring(M20, 3, 1, at)   # cheap gaps: alignments with many gaps
+    O = po.Oracle(M20, 3, 1, at)
+    ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB)
+    for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+        aoff, pairs, n, st = ctx.optimal_all(d, len(pq))
+        for p in range(len(pq)):
+            q, t = seqs[pq[p]], seqs[pt[p]]
+            assert aoff[p + 1] - aoff[p] == len(q) + len(t) + 2
+            rc, hp, sc = ctx.optimal(p, d, len(q), len(t))
+            assert st[p] == rc, "pair %d dir %d status" % (p, d)
+            assert_matrix_equal("pair %d dir %d" % (p, d), pairs[aoff[p]:aoff[p] + n[p]], hp)
+            if p % 5 == 0:
+                S, Q, T = O.fill(q, t, od, True, fast=True)
+                orc, opairs, osc = O.optimal(S, Q, T, od)
+                assert (orc != 0) == (st[p] != 0)
+                if orc == 0:
+                    assert_matrix_equal("oracle pair %d dir %d" % (p, d), pairs[aoff[p]:aoff[p] + n[p]], opairs)
