@@ -25,6 +25,7 @@ namespace {
 
 thread_local std::string g_err;
 
+
 int fail(const std::string& m) {
   g_err = m;
   return 1;
@@ -139,6 +140,7 @@ struct aadp_ctx {
   std::vector<int32_t> Lq32, Lt32;
   int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
   DevBuf wave_bb, wave_ready, wave_part;
+  unsigned int wave_tag = 0;
   DevBuf x_layout, x_qc, x_qid, x_tid, x_scores;
   // exact general-gap fp32 path (aadp_general.cuh): scoring that is not on a dyadic grid, or forced
   bool float_mode = false, force_float = false;
@@ -279,16 +281,16 @@ int launch_packed(aadp_ctx* c, PackedParams& P, int tbm, int fst, int msk) {
 
 template <int TBM, int STM>
 int launch_wave_t(aadp_ctx* c, FillParams& Pf, FillParams& Pr, int ndirs, int nst) {
-  auto kern = wave_kernel<8, TBM, STM>;
+  auto kern = wave_kernel<kWaveK, TBM, STM>;
   const int A = Pf.sc.A;
-  size_t smem = (size_t)((A * A + 15) / 16 * 16) + kQRing + (size_t)A * 32 * 8;
+  size_t smem = (size_t)((A * A + 15) / 16 * 16) + kQRing + 512 + (size_t)A * 32 * kWaveK;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
   const int grid = ndirs * nst;
   if (occ < 1 || grid > occ * c->num_sms) return fail("wavefront kernel: stripes of this pair cannot all be resident");
   char nm[64];
-  snprintf(nm, sizeof nm, "wave_kernel<K=8,TB=%d,ST=%d>x%d", TBM, STM, ndirs);
+  snprintf(nm, sizeof nm, "wave_kernel<K=%d,TB=%d,ST=%d>x%d", kWaveK, TBM, STM, ndirs);
   c->prof_begin(nm, Pf.cells_hint * ndirs);
   int nd = ndirs;
   void* args[] = {(void*)&Pf, (void*)&Pr, (void*)&nd};
@@ -527,9 +529,9 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
       const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
       const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
                              c->sc.ge <= 400 && c->sc.gi <= 2048;
-      // long pairs: one CTA per 256-column stripe, all stripes of both directions co-resident
+      // long pairs: one CTA per kWaveCols-column stripe, all stripes of both directions co-resident
       const bool wave_ok = !packed_ok && c->allow_wave && Lq >= 1 && Lt > 512 && cl >= (int64_t)c->wave_min_cells &&
-                           2 * ((Lt + 255) / 256) <= (int64_t)c->num_sms * 8;
+                           2 * ((Lt + kWaveCols - 1) / kWaveCols) <= (int64_t)c->num_sms * 8;
       b.fmt[(size_t)p] = packed_ok ? 1 : (wave_ok ? 2 : 0);
       if (packed_ok) {
         P.packed_cells += (double)cl;
@@ -570,7 +572,7 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
     int64_t lo, hi, s0 = 0, s1 = 0, s2 = 0;
     range(t, &lo, &hi);
     for (int64_t p = lo; p < hi; ++p) {
-      const Layout L = make_layout(Lq32[p], Lt32[p], b.fmt[(size_t)p] == 1, 0);
+      const Layout L = make_layout(Lq32[p], Lt32[p], b.fmt[(size_t)p], 0);
       const int64_t units = (b.fmt[(size_t)p] == 1 || b.st_mode == 1) ? 1 : 2;
       const int64_t z0 = want_tb ? round_up64(layout_tb_bytes(L), 16) : 0;
       const int64_t z1 = want_sc ? round_up64(layout_sc_elems(L) * units, 8) : 0;
@@ -736,12 +738,22 @@ int run_wave_pairs(aadp_ctx* c, uint32_t what) {
   for (int32_t p : b.wave_pairs) {
     const int qs = b.pair_q[p], ts = b.pair_t[p];
     const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
-    const int nst = (Lt + 255) / 256;
+    const int nst = (Lt + kWaveCols - 1) / kWaveCols;
     const int bb_rows = Lq + 2;
     int dirs[2], nd = 0;
     if (what & AADP_W_FWD) dirs[nd++] = 0;
     if (what & AADP_W_REV) dirs[nd++] = 1;
-    if (c->wave_bb.reserve((size_t)nd * nst * bb_rows * sizeof(int4))) return 1;
+    {
+      // boundary words carry the tag of their launch; the buffer is zeroed whenever it is (re)allocated and
+      // tags never repeat within an allocation, so stale words are never mistaken for published ones
+      const void* old = c->wave_bb.p;
+      if (c->wave_bb.reserve((size_t)nd * nst * bb_rows * 3 * sizeof(unsigned long long))) return 1;
+      if (c->wave_bb.p != old || c->wave_tag == 0xffffffffu) {
+        CK(cudaMemsetAsync(c->wave_bb.p, 0, c->wave_bb.cap, c->stream));
+        c->wave_tag = 0;
+      }
+      ++c->wave_tag;
+    }
     if (c->wave_ready.reserve((size_t)nd * nst * sizeof(int) + 16)) return 1;
     if (c->wave_part.reserve((size_t)nd * nst * sizeof(int4))) return 1;
     CK(cudaMemsetAsync(c->wave_ready.p, 0, (size_t)nd * nst * sizeof(int), c->stream));
@@ -768,7 +780,8 @@ int run_wave_pairs(aadp_ctx* c, uint32_t what) {
       Q.cells_hint = (double)Lq * Lt;
       Q.wave_pair = p;
       Q.wave_nstripes = nst;
-      Q.wave_bb = c->wave_bb.as<int4>() + (size_t)k * nst * bb_rows;
+      Q.wave_ll = c->wave_bb.as<unsigned long long>() + (size_t)k * nst * bb_rows * 3;
+      Q.wave_tag = c->wave_tag;
       Q.wave_ready = c->wave_ready.as<int>() + (size_t)k * nst;
       Q.wave_part = c->wave_part.as<int4>() + (size_t)k * nst;
     }
@@ -801,7 +814,7 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   D.rev = dir;
   D.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
   const bool packed = b.fmt[p] == 1;
-  D.lay = make_layout(Lq, Lt, packed, dir);
+  D.lay = make_layout(Lq, Lt, b.fmt[p], dir);
   D.bias = packed ? kBias16 : 0;
   D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
   D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
@@ -838,7 +851,7 @@ int dense_mask(aadp_ctx* c, int64_t p, uint8_t* h_mask) {
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
   const int sz2 = Lt + 2;
   const int64_t mws = mask_row_words(Lt);
-  const Layout L = make_layout(Lq, Lt, b.fmt[p] == 1, 1);
+  const Layout L = make_layout(Lq, Lt, b.fmt[p], 1);
   const int64_t nwords = layout_mask_words(L);
   std::vector<uint32_t> bits((size_t)std::max<int64_t>(nwords, 1));
   if (nwords > 0) {
@@ -1525,7 +1538,7 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
       M.only_pair = p;
       if (d_nearopt_count) CK(cudaMemsetAsync(d_nearopt_count + p, 0, 8, c->stream));
       c->prof_begin("mask_kernel(long pair)", 0);
-      mask_kernel<<<dim3(1, 592), 256, 0, c->stream>>>(M);
+      mask_kernel<<<dim3(1, 2368), 256, 0, c->stream>>>(M);
       c->prof_end();
       CK(cudaGetLastError());
       c->launches++;
@@ -1681,7 +1694,7 @@ int aadp_batch_fetch_tb(aadp_ctx* c, int64_t p, int direction, uint8_t* tb, int6
       const int ts = b.pair_t[p];
       const int Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
       final_rec[4] = (b.fmt[p] == 1 && dir == 0) ? ((Lt + 15) / 16) * 16 - Lt : 0;  // leading pad columns of the layout
-      final_rec[5] = b.fmt[p] == 1 ? 1 : 0;                                          // 1 = diagonal-major
+      final_rec[5] = b.fmt[p];                                                       // layout class: 0 words, 1 diagonal-major, 2 nibble groups
     }
   }
   CK(cudaStreamSynchronize(c->stream));

@@ -35,6 +35,11 @@ constexpr int kNeg32 = -(1 << 30);    // "-infinity" for E/F seeds (int32 path)
 constexpr int kFloor32 = -(1 << 29);  // clamp floor of M (never reached by real scores)
 constexpr int kWarpsPerCta = 4;
 constexpr int kQRing = 1024;           // per-warp query staging ring (bytes)
+// multi-CTA wavefront (long pairs): columns per lane / per stripe (one warp per stripe).  Measured on B200
+// (30k x 30k): K = 8 -> 12.3 ms, K = 4 -> 13.9 ms: the step time is set by serialized latencies, not by the
+// cells per lane, and narrower stripes only lengthen the pipeline fill.
+constexpr int kWaveK = 8;
+constexpr int kWaveCols = 32 * kWaveK;
 
 __host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 // packed-traceback row stride in bytes: one 32-bit word per 8 columns, rows padded to 16 B
@@ -75,8 +80,11 @@ struct FillParams {
   // ---- multi-CTA wavefront mode (one long pair, one CTA per 32*K-column stripe)
   int wave_pair;             // pair id
   int wave_nstripes;
-  int4* wave_bb;             // [stripe][bb_rows] boundary (X, E, M-gi) of the stripe's last column per row
-  int* wave_ready;           // [stripe] rows published so far (Lq+1 = stripe completely done)
+  unsigned long long* wave_ll;  // [stripe][bb_rows][3] boundary (X, E, M-gi) of the stripe's last column per row, each
+                             // value published as ONE 8-byte word {value, tag}: data and flag travel together, so
+                             // neither side needs a fence or a separate progress counter (cf. NCCL's LL protocol)
+  unsigned int wave_tag;     // tag of this launch (the buffer is zeroed when allocated, tags never repeat)
+  int* wave_ready;           // [stripe] Lq+1 once the stripe is completely done (final-cell partials chain)
   int4* wave_part;           // [stripe] final-row partials (rb_val, rb_k, diag, col)
 };
 
@@ -87,6 +95,16 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// 8-byte {value, tag} words: single-copy atomic, L1-bypassing, no fence
+__device__ __forceinline__ void st_ll(unsigned long long* p, int v, unsigned int tag) {
+  const unsigned long long w = (unsigned long long)(unsigned int)v | ((unsigned long long)tag << 32);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 
 // gap(len) in integer units; 0 for len < 1 (aasubalib.h:33-38)
@@ -153,9 +171,10 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
 
   const int st_lo = WAVE ? wave_st : 0, st_hi = WAVE ? wave_st + 1 : nstripes;
   for (int st = st_lo; st < st_hi; ++st) {
-    if (WAVE) bb = P.wave_bb + (int64_t)st * P.bb_rows;  // this stripe's output; input is one stripe below
-    const int4* bb_in = WAVE ? P.wave_bb + (int64_t)(st - 1) * P.bb_rows : bb;
-    int4 bblk = make_int4(0, kNeg32, kNeg32, 0);  // WAVE: row (block start + lane) of the input boundary
+    // WAVE: this stripe's published boundary column, and the one it consumes (the stripe to its left)
+    unsigned long long* ll_out = WAVE ? P.wave_ll + (int64_t)st * P.bb_rows * 3 : nullptr;
+    const unsigned long long* ll_in = WAVE ? P.wave_ll + (int64_t)(st - 1) * P.bb_rows * 3 : nullptr;
+    int4* wblk = reinterpret_cast<int4*>(qring + kQRing);  // WAVE: 32 staged rows of the input boundary (512 B)
     const int jbase = st * W + lane * K;  // flow column of register c is jbase + c + 1
     const int cols_here = min(W, Lt - st * W);
     const int n_act = (cols_here + K - 1) / K;
@@ -244,17 +263,28 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
       if (WAVE && st > 0) {
         const int i0 = s + 1;  // row lane 0 works on in this step
         if (i0 <= Lq && ((i0 - 1) & 31) == 0) {
-          // a new 32-row block of the left neighbour's boundary: wait until it is published, then load it
-          const int need = min(i0 + 31, Lq);
-          if (lane == 0) while (ld_acquire(P.wave_ready + st - 1) < need) __nanosleep(64);
-          __syncwarp();
+          // a new 32-row block of the left neighbour's boundary: lane l fetches row i0+l and spins until all three
+          // words carry this launch's tag (they are published row by row, in order), then stages it
           const int r = i0 + lane;
-          if (r <= Lq) bblk = bb_in[r];
+          unsigned long long w0 = 0, w1 = 0, w2 = 0;
+          for (;;) {
+            bool ok = true;
+            if (r <= Lq) {
+              const unsigned long long* src = ll_in + (int64_t)r * 3;
+              w0 = ld_ll(src); w1 = ld_ll(src + 1); w2 = ld_ll(src + 2);
+              ok = (unsigned int)(w0 >> 32) == P.wave_tag && (unsigned int)(w1 >> 32) == P.wave_tag &&
+                   (unsigned int)(w2 >> 32) == P.wave_tag;
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(32);
+          }
+          wblk[lane] = make_int4((int)(unsigned int)w0, (int)(unsigned int)w1, (int)(unsigned int)w2, 0);
+          __syncwarp();
         }
-        const int src = (i0 - 1) & 31;
-        const int bx = __shfl_sync(0xffffffffu, bblk.x, src), be = __shfl_sync(0xffffffffu, bblk.y, src),
-                  bm = __shfl_sync(0xffffffffu, bblk.z, src);
-        if (lane == 0) { xn = bx; e_in = be; mg_in = bm; }
+        if (i0 <= Lq) {
+          const int4 bv = wblk[(i0 - 1) & 31];  // same address for every lane: one broadcast LDS.128
+          if (lane == 0) { xn = bv.x; e_in = bv.y; mg_in = bv.z; }
+        }
       }
       if (lane == 0) {
         if (st == 0) {
@@ -274,13 +304,15 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
         if (K == 16) {
           uint4 v = *reinterpret_cast<const uint4*>(prof + a_cur * W + lane * K);
           pw[0] = v.x; pw[1] = v.y; pw[K / 4 - 2] = v.z; pw[K / 4 - 1] = v.w;
-        } else {
+        } else if (K == 8) {
           uint2 v = *reinterpret_cast<const uint2*>(prof + a_cur * W + lane * K);
-          pw[0] = v.x; pw[1] = v.y;
+          pw[0] = v.x; pw[K / 4 - 1] = v.y;
+        } else {
+          pw[0] = *reinterpret_cast<const uint32_t*>(prof + a_cur * W + lane * K);
         }
         int Xd = xl_hold, E = e_in, Mgl = mg_in;
         uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-        uint32_t tbw[K / 8];
+        uint32_t tbw[(K + 7) / 8];
         int mrow[K];
 #pragma unroll
         for (int c = 0; c < K; ++c) {
@@ -303,8 +335,10 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
             acc1 = __funnelshift_l((uint32_t)dS2, acc1, 1);
             acc2 = __funnelshift_l((uint32_t)dE, acc2, 1);
             acc3 = __funnelshift_l((uint32_t)dF, acc3, 1);
-            if ((c & 7) == 7)
+            if (K >= 8 && (c & 7) == 7)
               tbw[c >> 3] = __byte_perm(__byte_perm(acc0, acc1, 0x0040), __byte_perm(acc2, acc3, 0x0040), 0x5410);
+            if (K == 4 && c == 3)  // nibble layout: byte 0 = planes 0|1, byte 1 = planes 2|3
+              tbw[0] = ((acc0 << 4) | acc1) | (((acc2 << 4) | acc3) << 8);
           } else {
             E = __viaddmax_s32(E, -ge, Mgl);
             F = __viaddmax_s32(Fs[c], nge[c], Mg[c]);
@@ -322,14 +356,16 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
         mg_pub = Mgl;
         if (TBM) {
           uint8_t* dst = tbp + (int64_t)(i - 1) * tbs + (int64_t)(st * W + lane * K) / 2;
-          if (K == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(tbw[0], tbw[K / 8 - 1]);
-          else *reinterpret_cast<uint32_t*>(dst) = tbw[0];
+          if (K == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(tbw[0], tbw[(K + 7) / 8 - 1]);
+          else if (K == 8) *reinterpret_cast<uint32_t*>(dst) = tbw[0];
+          else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)tbw[0];
         }
         if (STM == 1) {
           int16_t* dst = reinterpret_cast<int16_t*>(P.sc_blob) + sco + (int64_t)(i - 1) * scs + st * W + lane * K;
           uint32_t pk[K / 2];
 #pragma unroll
           for (int c = 0; c < K / 2; ++c) pk[c] = __byte_perm((uint32_t)mrow[2 * c], (uint32_t)mrow[2 * c + 1], 0x5410);
+          if (K == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(pk[0], pk[K / 2 - 1]);
 #pragma unroll
           for (int c = 0; c < K / 8; ++c)
             reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -340,10 +376,13 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
             reinterpret_cast<int4*>(dst)[c] = make_int4(mrow[4 * c], mrow[4 * c + 1], mrow[4 * c + 2], mrow[4 * c + 3]);
         }
         if (st + 1 < nstripes && lane == 31) {
-          bb[i] = make_int4(x_pub, e_pub, mg_pub, 0);
-          if (WAVE && ((i & 31) == 0 || i == Lq)) {  // publish a finished 32-row block to the next stripe
-            __threadfence();
-            st_release(P.wave_ready + st, i);
+          if (WAVE) {  // publish this row of the boundary column: three self-validating 8-byte words
+            unsigned long long* o = ll_out + (int64_t)i * 3;
+            st_ll(o, x_pub, P.wave_tag);
+            st_ll(o + 1, e_pub, P.wave_tag);
+            st_ll(o + 2, mg_pub, P.wave_tag);
+          } else {
+            bb[i] = make_int4(x_pub, e_pub, mg_pub, 0);
           }
         }
       }
@@ -450,8 +489,8 @@ __global__ void __launch_bounds__(32) wave_kernel(const FillParams Pf, const Fil
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);
   const int sub_bytes = (A * A + 15) / 16 * 16;
   const int lane = threadIdx.x;
-  uint8_t* qring = smem + sub_bytes;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kQRing);
+  uint8_t* qring = smem + sub_bytes;  // followed by the 512-byte staging block of the input boundary
+  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kQRing + 512);
   for (int x = threadIdx.x; x < A * A; x += blockDim.x) s_sub[x] = P.sub8[x];
   __syncwarp();
   fill_pair_warp<K, TBM, STM, 1>(P, P.wave_pair, prof, qring, s_sub, nullptr, lane, st);
@@ -468,15 +507,20 @@ __global__ void __launch_bounds__(32) wave_kernel(const FillParams Pf, const Fil
 //   skew = 0: row-major (int32 kernels).  1: diagonal-major (packed kernels): the 16-column chunk
 //          k of flow row a lives in "skew row" (a-1)+k, so everything a warp produces in one step
 //          is contiguous in memory (the lanes of a segment are skewed by one row per lane).
+//   nib  = 1: row-major like skew = 0, but the traceback is grouped by FOUR columns (the multi-CTA wavefront
+//          kernel owns 4 columns per lane): 2 bytes per group, byte 0 = planes 0|1, byte 1 = planes 2|3 as
+//          high|low nibbles, bit 3-(c&3) of a nibble = column c of the group.
 struct Layout {
   int Lq, Lt, n;  // n = ceil(Lt/16) chunks
-  int sig, skew;
+  int sig, skew, nib;
 };
-__host__ __device__ inline Layout make_layout(int Lq, int Lt, int packed, int rev) {
+// fmt: 0 = int32 kernels, 1 = packed kernels, 2 = wavefront kernel (the per-pair class of the host scheduler)
+__host__ __device__ inline Layout make_layout(int Lq, int Lt, int fmt, int rev) {
   Layout L;
   L.Lq = Lq; L.Lt = Lt; L.n = (Lt + 15) >> 4;
-  L.skew = packed ? 1 : 0;
-  L.sig = (packed && !rev) ? 16 * L.n - Lt : 0;
+  L.skew = fmt == 1 ? 1 : 0;
+  L.nib = (fmt == 2 && kWaveK == 4) ? 1 : 0;
+  L.sig = (fmt == 1 && !rev) ? 16 * L.n - Lt : 0;
   return L;
 }
 // bytes of packed traceback / int16 units of scores / 32-bit words of mask one pair occupies
@@ -492,6 +536,10 @@ __host__ __device__ inline int64_t layout_mask_words(const Layout& L) {
 // byte offset of the traceback byte holding plane `plane` of flow cell (a,b); *bit = bit index in it
 __host__ __device__ inline int64_t layout_tb_byte(const Layout& L, int a, int b, int plane, int* bit) {
   const int pos = b - 1 + L.sig;
+  if (L.nib) {
+    *bit = ((plane & 1) ? 0 : 4) + 3 - (pos & 3);
+    return (int64_t)(a - 1) * tb_row_bytes(L.Lt) + 2 * (pos >> 2) + (plane >> 1);
+  }
   *bit = 7 - (pos & 7);
   if (L.skew) {
     const int k = pos >> 4;
@@ -594,31 +642,46 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int A = P.sc.A;
   long long cnt = 0;
-  for (int i = 1 + warp + nw * blockIdx.y; i <= Lq; i += nw * gridDim.y) {
+  // a block owns a contiguous band of rows and walks it row by row, its warps side by side along the row:
+  // few concurrent DRAM streams (two per block), each fully sequential
+  const int rows_per_blk = (Lq + gridDim.y - 1) / gridDim.y;
+  const int i_lo = 1 + rows_per_blk * blockIdx.y, i_hi = min(Lq, i_lo + rows_per_blk - 1);
+  for (int i = i_lo; i <= i_hi; ++i) {
     const int qa = P.residues[qo + i - 1];
-    for (int j0 = 0; j0 < Lt; j0 += 32) {
-      const int j = j0 + lane + 1;
-      bool on = false;
-      if (j <= Lt) {
-        int f, r;
-        const int64_t fo = (int64_t)(i - 1) * scs + (j - 1);
-        const int64_t ro = (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
-        if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[so + fo]; r = ((const int16_t*)P.scR)[so + ro]; }
-        else { f = ((const int32_t*)((const int16_t*)P.scF + so))[fo]; r = ((const int32_t*)((const int16_t*)P.scR + so))[ro]; }
-        const int sm = P.sub8[qa * A + P.residues[to + j - 1]];
-        float v = __fadd_rn((float)f * inv, (float)r * inv);
-        v = __fsub_rn(v, (float)sm * inv);
-        on = v > thr;
+    const int8_t* subrow = P.sub8 + qa * A;
+    // 128 columns per iteration: the loads of four 32-column groups are issued before any of them is used
+    for (int j0 = 128 * warp; j0 < Lt; j0 += 128 * nw) {
+      bool on[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u + lane + 1;
+        on[u] = false;
+        if (j <= Lt) {
+          int f, r;
+          const int64_t fo = (int64_t)(i - 1) * scs + (j - 1);
+          const int64_t ro = (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
+          if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[so + fo]; r = ((const int16_t*)P.scR)[so + ro]; }
+          else { f = ((const int32_t*)((const int16_t*)P.scF + so))[fo]; r = ((const int32_t*)((const int16_t*)P.scR + so))[ro]; }
+          const int sm = subrow[P.residues[to + j - 1]];
+          float v = __fadd_rn((float)f * inv, (float)r * inv);
+          v = __fsub_rn(v, (float)sm * inv);
+          on[u] = v > thr;
+        }
       }
-      const uint32_t bits = __ballot_sync(0xffffffffu, on);
-      if (lane == 0) { mk[(int64_t)(i - 1) * mws + (j0 >> 5)] = bits; cnt += __popc(bits); }
+      uint32_t mine = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, on[u]);
+        if (lane == u) mine = bits;
+      }
+      if (lane < 4 && j0 + 32 * lane < Lt) { mk[(int64_t)(i - 1) * mws + (j0 >> 5) + lane] = mine; cnt += __popc(mine); }
     }
   }
   if (P.count) {
     __shared__ long long s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    if (lane == 0 && cnt) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
+    if (cnt) atomicAdd((unsigned long long*)&s_cnt, (unsigned long long)cnt);
     __syncthreads();
     if (threadIdx.x == 0) {
       if (gridDim.y == 1) P.count[pair] = s_cnt;
@@ -699,7 +762,7 @@ __global__ void dense_kernel(const DenseParams P) {
 struct TraceParams {
   const uint8_t* tb;         // packed traceback blob of the direction
   const int64_t* tb_off;
-  const uint8_t* fmt;        // per pair: 1 = packed (diagonal-major) layout, 0/2 = row-major
+  const uint8_t* fmt;        // per pair: layout class (see make_layout)
   const int64_t* seq_off;
   const int32_t* pair_q;
   const int32_t* pair_t;
@@ -720,7 +783,7 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TraceParams P) {
   const int qs = P.pair_q[pair], ts = P.pair_t[pair];
   const int Lq = (int)(P.seq_off[qs + 1] - P.seq_off[qs]), Lt = (int)(P.seq_off[ts + 1] - P.seq_off[ts]);
   const uint8_t* tb = P.tb + P.tb_off[pair];
-  const Layout L = make_layout(Lq, Lt, P.fmt[pair] == 1, P.rev);
+  const Layout L = make_layout(Lq, Lt, P.fmt[pair], P.rev);
   const int kind = P.fin_kind[pair], fk = P.fin_k[pair];
   int2* out = P.out + P.cap_off[pair];
   const int cap = Lq + Lt + 2;

@@ -179,7 +179,7 @@ int64_t aadp_batch_tb_bytes(aadp_ctx* ctx, int64_t p);
 /* Decode one cell of a packed traceback fetched with aadp_batch_fetch_tb. (i,j) and the result
  * are reference matrix coordinates; direction selects the fwd or rev conventions.              */
 int aadp_batch_fetch_tb(aadp_ctx* ctx, int64_t p, int direction, uint8_t* tb, int64_t tb_bytes,
-                        int32_t* final_rec /* [6]: score units, kind, k, scale_log2, leading pad columns, layout (1 = diagonal-major) */);
+                        int32_t* final_rec /* [6]: score units, kind, k, scale_log2, leading pad columns, layout class (0 = 8-column words, 1 = diagonal-major, 2 = 4-column nibble groups) */);
 int aadp_decode_cell(const uint8_t* tb, int Lq, int Lt, int direction, int align_type,
                      uint32_t flags, const int32_t* final_rec, int i, int j, int32_t* prev_q,
                      int32_t* prev_t);
