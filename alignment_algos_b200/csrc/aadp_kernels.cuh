@@ -35,9 +35,10 @@ constexpr int kNeg32 = -(1 << 30);    // "-infinity" for E/F seeds (int32 path)
 constexpr int kFloor32 = -(1 << 29);  // clamp floor of M (never reached by real scores)
 constexpr int kWarpsPerCta = 4;
 constexpr int kQRing = 1024;           // per-warp query staging ring (bytes)
-// multi-CTA wavefront (long pairs): columns per lane / per stripe (one warp per stripe).  Measured on B200
-// (30k x 30k): K = 8 -> 12.3 ms, K = 4 -> 13.9 ms: the step time is set by serialized latencies, not by the
-// cells per lane, and narrower stripes only lengthen the pipeline fill.
+// multi-CTA wavefront (long pairs): columns per lane / per stripe (one warp per stripe).  Every stripe has to
+// walk all Lq rows, so the run time is (Lq + pipeline skew) x (time of one row step); measured on B200
+// (30k x 30k, fwd+rev): K = 4 -> 13.9 ms (705 cycles/step), K = 8 -> 12.3 ms (703), K = 16 -> 13.5 ms (824):
+// the step time is set by serialized latencies (shuffle -> E chain -> publish), not by the cells per lane.
 constexpr int kWaveK = 8;
 constexpr int kWaveCols = 32 * kWaveK;
 
