@@ -89,6 +89,16 @@ class Context:
         out["threshold"] = thr.value if want_mask else None
         return out
 
+    def fill_subpair(self, q, t, rect, direction=FWD):
+        """build_subdpm (dpmatrix.h:319-353): rect = (q1_end, t1_end, q2_beg, t2_beg), matrix indices."""
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        sz = (len(q) + 2, len(t) + 2)
+        s, pq, pt = np.zeros(sz, np.float32), np.zeros(sz, np.int32), np.zeros(sz, np.int32)
+        self._ck(self.L.aadp_fill_subpair(self.h, _ptr(q), len(q), _ptr(t), len(t), int(rect[0]), int(rect[1]),
+                                          int(rect[2]), int(rect[3]), direction, _ptr(s), _ptr(pq), _ptr(pt)))
+        return s, pq, pt
+
     # ---- batches ----
     @staticmethod
     def pack(seqs):

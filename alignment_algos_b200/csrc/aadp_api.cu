@@ -147,7 +147,7 @@ struct aadp_ctx {
   float gi_f = 0.f, ge_f = 0.f;
   float last_delta = -1.f;
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
-  DevBuf ali_cap, ali_out, ali_n, ali_status;
+  DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -925,7 +925,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status};
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -1305,7 +1305,7 @@ int aadp_cross_scores(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
 // Fills the n consecutive pairs [p0, p0+n) of the batch in the directions of `dirmask` (bit 0 forward,
 // bit 1 reverse) into the dense scratch matrices of the context.  off = n+1 cell offsets of the pairs.
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
-                   float* d_fin_fwd, float* d_fin_rev) {
+                   float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr) {
   Batch& b = c->b;
   const int64_t cells = off[(size_t)n];
   int maxLt = 0, maxL = 0;
@@ -1349,6 +1349,11 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   if (pin_reserve(c, (size_t)(n + 1) * 8 + 4096)) return 1;
   if (upload_vec(c, c->gg_off, off)) return 1;
   G.dense_off = c->gg_off.as<int64_t>();
+  if (rect) {  // build_subdpm: one rectangle (the single pair of this launch)
+    std::vector<int32_t> r(rect, rect + 4);
+    if (upload_vec(c, c->gg_rect, r)) return 1;
+    G.rects = c->gg_rect.as<int4>();
+  }
   const int threads = std::max(64, std::min(512, (maxLt + 31) / 32 * 32));
   double cu = 0;
   for (int64_t p = p0; p < p0 + n; ++p) {
@@ -1850,6 +1855,34 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
   if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
   CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_fill_subpair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, int Lt, int q1_end, int t1_end, int q2_beg,
+                      int t2_beg, int direction, float* score, int32_t* prev_q, int32_t* prev_t) {
+  if (check_ctx(c, true)) return 1;
+  if (Lq < 0 || Lt < 0) return fail("Illegal bounds building DPM");
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  // dpmatrix.h:360-361 (and the matrix limits the reference does not check)
+  if (q2_beg <= q1_end || t2_beg <= t1_end) return fail("Illegal bounds building DPM");
+  if (q1_end < 0 || t1_end < 0 || q2_beg > Lq + 1 || t2_beg > Lt + 1) return fail("sub-rectangle anchors outside the matrix");
+  std::vector<uint8_t> res((size_t)Lq + Lt + 1);
+  if (Lq) memcpy(res.data(), q, Lq);
+  if (Lt) memcpy(res.data() + Lq, t, Lt);
+  const int64_t off[3] = {0, Lq, (int64_t)Lq + Lt};
+  const int32_t pq = 0, pt = 1;
+  if (aadp_upload_batch(c, res.data(), off, 2, &pq, &pt, 1, 0)) return 1;
+  const int64_t n = (int64_t)(Lq + 2) * (Lt + 2);
+  const std::vector<int64_t> doff = {0, n};
+  const int rect[4] = {q1_end, t1_end, q2_beg, t2_beg};
+  const int d = direction - 1;
+  c->launches = 0;
+  if (gg_fill(c, 0, 1, 1 << d, true, doff, nullptr, nullptr, rect)) return 1;
+  if (score) CK(cudaMemcpyAsync(score, c->gg_score[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->b.ran_what = 0;
   return 0;
 }
 

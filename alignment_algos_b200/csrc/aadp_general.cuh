@@ -37,6 +37,8 @@ struct GeneralParams {
   int item0;
   int dirs[2];               // blockIdx.y -> 0 forward, 1 reverse
   const int64_t* dense_off;  // per item: offset (in cells) of its (Lq+2)*(Lt+2) matrices; null = 0
+  const int4* rects;         // per item: anchors (q1_end, t1_end, q2_beg, t2_beg) of build_subdpm (dpmatrix.h:319-353),
+                             // matrix indices; null = the whole matrix (0, 0, Lq+1, Lt+1)
   float* score[2];           // per direction: dense score matrices (always)
   int32_t* prevq[2];         // per direction: dense predecessor rows/cols, or null
   int32_t* prevt[2];
@@ -57,7 +59,11 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   const int qs = P.pair_q[pair], ts = P.pair_t[pair];
   const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
   const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
-  const int sz2 = Lt + 2, q1 = Lq + 1, t1 = Lt + 1;
+  // anchors of the filled rectangle: (q0,t0) and (mq1,mt1) in matrix indices.  q1/t1 = FLOW index of the final
+  // cell, nq/nt = interior rows/columns of the rectangle.  A whole matrix is (0,0)-(Lq+1,Lt+1).
+  int q0 = 0, t0 = 0, mq1 = Lq + 1, mt1 = Lt + 1;
+  if (P.rects) { const int4 r = P.rects[blockIdx.x]; q0 = r.x; t0 = r.y; mq1 = r.z; mt1 = r.w; }
+  const int sz2 = Lt + 2, q1 = mq1 - q0, t1 = mt1 - t0, nq = q1 - 1, nt = t1 - 1;
   const int64_t base = P.dense_off ? P.dense_off[item] : 0;
   float* D = P.score[dsel] + base;
   int32_t* PQ = TBM ? P.prevq[dsel] + base : nullptr;
@@ -68,34 +74,43 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   const float gi = P.gi, ge = P.ge;
   const bool local = P.local != 0;
 
-  float* prow = gg_smem;              // D[a-1][0..Lt]
+  float* prow = gg_smem;              // D[a-1][0..nt]
   float* pen = gg_smem + (Lt + 2);    // pen[len], len >= 1
-  const int maxlen = max(Lq, Lt);
+  const int maxlen = max(nq, nt);
   for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
 
   // matrix index of flow cell (a,b); matrix row / column of a flow row / column
-  auto at = [&](int a, int b) -> int64_t { return (int64_t)(rev ? q1 - a : a) * sz2 + (rev ? t1 - b : b); };
-  auto rowof = [&](int a) { return rev ? q1 - a : a; };
-  auto colof = [&](int b) { return rev ? t1 - b : b; };
+  auto rowof = [&](int a) { return rev ? mq1 - a : q0 + a; };
+  auto colof = [&](int b) { return rev ? mt1 - b : t0 + b; };
+  auto at = [&](int a, int b) -> int64_t { return (int64_t)rowof(a) * sz2 + colof(b); };
   auto clampl = [&](float s) { return (local && s < 0.f) ? 0.f : s; };
   auto sim = [&](int a, int b) -> float {  // flow cell -> substitution score (interior cells only)
     const int i = rowof(a), j = colof(b);
     return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
   };
-  // gap between flow columns b0 < b1 / flow rows a0 < a1, with the free end gaps of aasubalib.h:39-42,65-68
-  // (flow column 0 / t1 are the Head and the Tail in either direction)
+  // gap between flow columns b0 < b1 / flow rows a0 < a1, with the free end gaps of aasubalib.h:39-42,65-68:
+  // free when the lower matrix position is the Head or the upper one is the Tail (anchors of a sub-rectangle
+  // are ordinary residues unless they are the Head / the Tail)
   auto gdel = [&](int b0, int b1) -> float {
     const int len = b1 - b0 - 1;
     if (len < 1) return 0.f;
-    if (P.delfree && (b0 == 0 || b1 == t1)) return 0.f;
+    const int x = colof(b0), y = colof(b1);
+    if (P.delfree && (min(x, y) == 0 || max(x, y) == Lt + 1)) return 0.f;
     return pen[len];
   };
   auto gins = [&](int a0, int a1) -> float {
     const int len = a1 - a0 - 1;
     if (len < 1) return 0.f;
-    if (P.insfree && (a0 == 0 || a1 == q1)) return 0.f;
+    const int x = rowof(a0), y = rowof(a1);
+    if (P.insfree && (min(x, y) == 0 || max(x, y) == Lq + 1)) return 0.f;
     return pen[len];
   };
+  // similarity of the final cell: 0 at the Head / Tail (aasubalib.h:19-21), a real score at an interior anchor
+  float simf = 0.f;
+  {
+    const int i = rowof(q1), j = colof(t1);
+    if (i >= 1 && i <= Lq && j >= 1 && j <= Lt) simf = P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
+  }
 
   // DPCell::DPCell (dpmatrix.cpp:17-25): score 0, predecessors null
   for (int64_t o = tid; o < (int64_t)(Lq + 2) * sz2; o += nth) {
@@ -111,11 +126,11 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   };
 
   // Special cases #1/#2 (dpmatrix.h:374-390, 712-728): an empty sequence forces one gap; not clamped
-  if (Lq == 0 || Lt == 0) {
+  if (nq == 0 || nt == 0) {
     if (tid == 0) {
       float s = 0.f;
-      s = __fsub_rn(s, Lq == 0 ? gdel(0, t1) : gins(0, q1));
-      s = __fadd_rn(s, 0.f);
+      s = __fsub_rn(s, nq == 0 ? gdel(0, t1) : gins(0, q1));
+      s = __fadd_rn(s, simf);
       set_tb(q1, t1, 0, 0, s);
       if (P.fin[dsel]) P.fin[dsel][pair] = s;
     }
@@ -123,14 +138,14 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   }
 
   // boundary row and column of the flow (dpmatrix.h:408-426, 746-764, 579-599, 920-940)
-  for (int b = 1 + tid; b <= Lt; b += nth) {
+  for (int b = 1 + tid; b <= nt; b += nth) {
     float s = 0.f;
     if (b >= 2) s = __fsub_rn(s, gdel(0, b));
     s = clampl(__fadd_rn(s, sim(1, b)));
     set_tb(1, b, 0, 0, s);
     prow[b] = s;
   }
-  for (int a = 2 + tid; a <= Lq; a += nth) {
+  for (int a = 2 + tid; a <= nq; a += nth) {
     float s = 0.f;
     s = __fsub_rn(s, gins(0, a));
     s = clampl(__fadd_rn(s, sim(a, 1)));
@@ -139,10 +154,10 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   __syncthreads();
 
   // interior rows (dpmatrix.h:446-497): match, deletions k ascending, insertions k ascending, strict '>'
-  for (int a = 2; a <= Lq; ++a) {
+  for (int a = 2; a <= nq; ++a) {
     const int qa = qseq[rowof(a) - 1];
     const float* subrow = P.subf + qa * P.A;
-    for (int b = 2 + tid; b <= Lt; b += nth) {
+    for (int b = 2 + tid; b <= nt; b += nth) {
       const float simc = subrow[(int)tseq[colof(b) - 1]];
       int oa = a - 1, ob = b - 1;
       float os = clampl(__fadd_rn(prow[b - 1], simc));
@@ -164,29 +179,29 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       set_tb(a, b, oa, ob, os);
     }
     __syncthreads();  // every thread is done reading the previous row
-    for (int b = 1 + tid; b <= Lt; b += nth) prow[b] = D[at(a, b)];  // own cells (b >= 2) and the boundary column
+    for (int b = 1 + tid; b <= nt; b += nth) prow[b] = D[at(a, b)];  // own cells (b >= 2) and the boundary column
     __syncthreads();
   }
 
   // final cell (dpmatrix.h:504-534, 844-874, 654-687, 995-1028): match, bottom row, right column.
-  // Its similarity is 0 (Tail / Head).  Serial: Lq + Lt candidates.
+  // Its similarity is 0 at the Tail / Head, a real score at an interior anchor.  Serial: nq + nt candidates.
   if (tid == 0) {
-    int oa = Lq, ob = Lt;
+    int oa = nq, ob = nt;
     bool from_col = false;
-    float os = clampl(__fadd_rn(D[at(Lq, Lt)], 0.f));
+    float os = clampl(__fadd_rn(D[at(nq, nt)], simf));
     for (int k = 1; k < t1; ++k) {
-      float s = __fsub_rn(D[at(Lq, k)], gdel(k, t1));
-      s = clampl(__fadd_rn(s, 0.f));
-      if (s > os) { oa = Lq; ob = k; os = s; }
+      float s = __fsub_rn(D[at(nq, k)], gdel(k, t1));
+      s = clampl(__fadd_rn(s, simf));
+      if (s > os) { oa = nq; ob = k; os = s; }
     }
     for (int k = 1; k < q1; ++k) {
-      float s = __fsub_rn(D[at(k, Lt)], gins(k, q1));
-      s = clampl(__fadd_rn(s, 0.f));
-      if (s > os) { oa = k; ob = Lt; os = s; from_col = true; }
+      float s = __fsub_rn(D[at(k, nt)], gins(k, q1));
+      s = clampl(__fadd_rn(s, simf));
+      if (s > os) { oa = k; ob = nt; os = s; from_col = true; }
     }
     set_tb(q1, t1, oa, ob, os);
-    // dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 for left-column candidates
-    if (TBM && rev && !local && P.repro_rev_bug && from_col) PT[at(q1, t1)] = t1 - 1;
+    // dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 (a matrix column) for left-column candidates
+    if (TBM && rev && !local && P.repro_rev_bug && from_col) PT[at(q1, t1)] = mt1 - 1;
     if (P.fin[dsel]) P.fin[dsel][pair] = os;
   }
 }

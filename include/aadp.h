@@ -92,6 +92,17 @@ int aadp_fill_pair(aadp_ctx* ctx, const uint8_t* q, int Lq, const uint8_t* t, in
                    int32_t* prevt_fwd, float* score_rev, int32_t* prevq_rev, int32_t* prevt_rev,
                    uint8_t* nearopt, float* threshold);
 
+/* ---- sub-rectangle fill: replaces the 9-argument DPMatrix constructor + build_subdpm (dpmatrix.h:169-189,
+ * 319-353; used by the loop-closure code of ssss.h:621,710).  The fill runs between the anchors
+ * (q1_end, t1_end) and (q2_beg, t2_beg) (matrix indices, 0 = Head, L+1 = Tail); both anchor scores are 0,
+ * cells outside the rectangle keep the DPCell defaults (score 0, predecessors -1).  Anchors that are ordinary
+ * residues pay gap penalties and the final cell adds its real similarity, exactly as the reference does.
+ * Always computed by the exact general-gap fp32 kernel (any scoring).  direction: AADP_FWD or AADP_REV.
+ * Outputs are (Lq+2)*(Lt+2) host arrays, any may be NULL.                                                 */
+int aadp_fill_subpair(aadp_ctx* ctx, const uint8_t* q, int Lq, const uint8_t* t, int Lt, int q1_end,
+                      int t1_end, int q2_beg, int t2_beg, int direction, float* score,
+                      int32_t* prev_q, int32_t* prev_t);
+
 /* ---- batch of pairs, HOST buffers (the end-to-end call) ------------------------------------
  * residues: all sequences back to back; sequence s is residues[seq_off[s] .. seq_off[s+1]).
  * pair p aligns query pair_q[p] against template pair_t[p].

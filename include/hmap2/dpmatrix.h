@@ -8,9 +8,11 @@
 // aadp_fill_pair (include/aadp.h) and copies the dense result into the DPCell matrix, so every
 // enumerator that walks getCell()->prev_* keeps working unchanged.
 //
+// The 9-argument sub-rectangle constructor (dpmatrix.h:169-189 -> build_subdpm, :319-353) goes through
+// aadp_fill_subpair.
+//
 // Not carried over: the 2-argument constructor (never instantiable in the reference,
-// dpmatrix.h:141-142), the linear-gap stubs (dpmatrix.h:1032-1042) and the sub-rectangle constructor
-// (dpmatrix.h:169-189, SURVEY.md §8 row f4 "next").
+// dpmatrix.h:141-142) and the linear-gap stubs (dpmatrix.h:1032-1042).
 #ifndef AADP_HMAP2_DPMATRIX_H
 #define AADP_HMAP2_DPMATRIX_H
 
@@ -50,6 +52,15 @@ class DPMatrix {
         dpmatrix(0), simmatrix(0), nearopt_delta(-1.f), nearopt_threshold(0.f) {
     allocate();
     build();
+  }
+
+  // dpmatrix.h:169-189 (argument order of the definition: q1_end, t1_end, q2_beg, t2_beg)
+  DPMatrix(const S1& query_seq_, const S2& templ_seq_, const Evaluator<S1, S2, Etype>& eval, int q1_end, int t1_end,
+           int q2_beg, int t2_beg, direction_t dir = fwd, align_t type = global)
+      : query_seq(&query_seq_), templ_seq(&templ_seq_), evaluator(&eval), direction(dir), islocal(type == local),
+        dpmatrix(0), simmatrix(0), nearopt_delta(-1.f), nearopt_threshold(0.f) {
+    allocate();
+    build_subdpm(q1_end, t1_end, q2_beg, t2_beg);
   }
 
   ~DPMatrix() {
@@ -150,6 +161,35 @@ class DPMatrix {
     else
       aadp::check(aadp_fill_pair(ctx, q.data(), (int)q.size(), t.data(), (int)t.size(), AADP_REV, -1.f, 0, 0, 0,
                                  score.data(), pq.data(), pt.data(), 0, 0));
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) {
+        const size_t o = (size_t)i * sz2 + j;
+        (*dpmatrix)(i, j).setTB(pq[o], pt[o], score[o]);
+      }
+    nearopt_delta = -1.f;
+  }
+
+  // dpmatrix.h:319-353
+  void build_subdpm(int q1_end, int t1_end, int q2_beg, int t2_beg) {
+    delete simmatrix;
+    simmatrix = 0;
+    evaluator->pre_calculate(*query_seq, *templ_seq);
+    simmatrix = new SimilarityMatrix(*query_seq, *templ_seq, *evaluator);
+    const int sz1 = getQuerySize(), sz2 = getTemplateSize();
+    if (sz1 < 2 || sz2 < 2) throw std::string("Illegal bounds building DPM");
+    std::string alphabet;
+    std::vector<float> sub;
+    float gi, ge;
+    int at;
+    describe(&alphabet, &sub, &gi, &ge, &at);
+    const std::vector<uint8_t> q = aadp::encode(*query_seq, alphabet), t = aadp::encode(*templ_seq, alphabet);
+    aadp_ctx* ctx = aadp::default_context();
+    aadp::check(aadp_set_scoring(ctx, sub.data(), (int)alphabet.size(), gi, ge, at, AADP_REPRO_REV_BUG));
+    const size_t n = (size_t)sz1 * sz2;
+    std::vector<float> score(n);
+    std::vector<int32_t> pq(n), pt(n);
+    aadp::check(aadp_fill_subpair(ctx, q.data(), (int)q.size(), t.data(), (int)t.size(), q1_end, t1_end, q2_beg, t2_beg,
+                                  direction == fwd ? AADP_FWD : AADP_REV, score.data(), pq.data(), pt.data()));
     for (int i = 0; i < sz1; ++i)
       for (int j = 0; j < sz2; ++j) {
         const size_t o = (size_t)i * sz2 + j;

@@ -59,19 +59,18 @@ static void build_sim(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const 
 /* ---------------------------------------------------------------- flow-coordinate helpers */
 
 typedef struct {
-  int rev, q1, t1, sz1, sz2, local;
+  int rev, q0, t0; /* anchors of the filled rectangle (dpmatrix.h:319-353); (0,0) for a whole matrix */
+  int q1, t1, sz1, sz2, local; /* q1/t1 = FLOW index of the final cell = matrix q1-q0 / t1-t0 */
+  int mq1, mt1;                /* matrix row / column of the far anchor */
   const orc_scoring* sc;
   const float* sim;
   float* D;
   int *pq, *pt;
 } flow_t;
 
-static size_t at(const flow_t* f, int a, int b) {
-  int i = f->rev ? f->q1 - a : a, j = f->rev ? f->t1 - b : b;
-  return (size_t)i * f->sz2 + j;
-}
-static int rowof(const flow_t* f, int a) { return f->rev ? f->q1 - a : a; }
-static int colof(const flow_t* f, int b) { return f->rev ? f->t1 - b : b; }
+static int rowof(const flow_t* f, int a) { return f->rev ? f->mq1 - a : f->q0 + a; }
+static int colof(const flow_t* f, int b) { return f->rev ? f->mt1 - b : f->t0 + b; }
+static size_t at(const flow_t* f, int a, int b) { return (size_t)rowof(f, a) * f->sz2 + colof(f, b); }
 
 /* gap between flow columns b0 < b1 (deletion) / flow rows a0 < a1 (insertion) */
 static float gdel(const flow_t* f, int b0, int b1) {
@@ -98,6 +97,9 @@ static int flow_init(flow_t* f, const uint8_t* q, int Lq, const uint8_t* t, int 
   f->rev = (direction == ORC_REV);
   f->sz1 = Lq + 2;
   f->sz2 = Lt + 2;
+  f->q0 = f->t0 = 0;
+  f->mq1 = f->sz1 - 1;
+  f->mt1 = f->sz2 - 1;
   f->q1 = f->sz1 - 1;
   f->t1 = f->sz2 - 1;
   f->local = (sc->align_type == ORC_LOCAL); /* dpmatrix.h:155 */
@@ -179,7 +181,7 @@ static void final_cell(flow_t* f, int repro_rev_bug) {
   set_tb(f, q1, t1, oa, ob, os);
   /* dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 (a matrix column) for the
    * left-column candidates instead of t0_p1. The local variant is correct (dpmatrix.h:1022). */
-  if (f->rev && !f->local && repro_rev_bug && from_col) f->pt[at(f, q1, t1)] = t1 - 1;
+  if (f->rev && !f->local && repro_rev_bug && from_col) f->pt[at(f, q1, t1)] = f->mt1 - 1;
 }
 
 /* ---------------------------------------------------------------- literal O(n^3) fill */
@@ -221,6 +223,58 @@ int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scori
     final_cell(&f, repro_rev_bug);
   }
   if (!sim_out) free(sim);
+  return 0;
+}
+
+/* build_subdpm (dpmatrix.h:319-353): the same literal fill restricted to the rectangle between the anchors
+ * (q1_end,t1_end) and (q2_beg,t2_beg); both anchor scores are zeroed (:333-334), cells outside the rectangle
+ * keep the DPCell defaults.  The anchors are ordinary residues unless they are the Head / the Tail, so the
+ * free end gaps of aasubalib.h apply only there and the final cell adds its real similarity.             */
+int orc_fill_sub(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                 int direction, int repro_rev_bug, int q1_end, int t1_end, int q2_beg, int t2_beg,
+                 float* score, int* prev_q, int* prev_t) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  size_t n = (size_t)(Lq + 2) * (Lt + 2);
+  float* sim = (float*)malloc(sizeof(float) * n);
+  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
+  if (q1_end < 0 || t1_end < 0 || q2_beg > Lq + 1 || t2_beg > Lt + 1 || q2_beg <= q1_end || t2_beg <= t1_end) {
+    free(sim);
+    return 1; /* "Illegal bounds building DPM" (dpmatrix.h:360) or out of the matrix */
+  }
+  f.q0 = q1_end;
+  f.t0 = t1_end;
+  f.mq1 = q2_beg;
+  f.mt1 = t2_beg;
+  f.q1 = q2_beg - q1_end;
+  f.t1 = t2_beg - t1_end;
+  if (!degenerate(&f)) {
+    boundary(&f);
+    for (int a = 2; a < f.q1; ++a) {
+      for (int b = 2; b < f.t1; ++b) {
+        float simc = sim[at(&f, a, b)], s;
+        int oa = a - 1, ob = b - 1;
+        float os = clampl(&f, score[at(&f, oa, ob)] + simc);
+        for (int k = 1; k < b - 1; ++k) {
+          s = score[at(&f, a - 1, k)];
+          s -= gdel(&f, k, b);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = a - 1; ob = k; os = s; }
+        }
+        for (int k = 1; k < a - 1; ++k) {
+          s = score[at(&f, k, b - 1)];
+          s -= gins(&f, k, a);
+          s += simc;
+          s = clampl(&f, s);
+          if (s > os) { oa = k; ob = b - 1; os = s; }
+        }
+        set_tb(&f, a, b, oa, ob, os);
+      }
+    }
+    final_cell(&f, repro_rev_bug);
+  }
+  free(sim);
   return 0;
 }
 

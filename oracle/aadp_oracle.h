@@ -44,6 +44,12 @@ int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scori
              int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
              float* sim_out);
 
+/* build_subdpm + the 9-argument constructor (dpmatrix.h:169-189, 319-353): the literal fill between the
+ * anchors (q1_end,t1_end) and (q2_beg,t2_beg) (matrix indices), everything else left at the DPCell defaults. */
+int orc_fill_sub(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+                 int direction, int repro_rev_bug, int q1_end, int t1_end, int q2_beg, int t2_beg,
+                 float* score, int* prev_q, int* prev_t);
+
 /* Exact O(Lq*Lt) restatement (running maxima with origin tracking).
  * Candidates are re-evaluated as (D[origin] - w(len)) + sim like dpmatrix.h:460-462, so
  * it is bit-identical to orc_fill whenever all scores/penalties lie on one dyadic grid.    */

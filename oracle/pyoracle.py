@@ -83,6 +83,21 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return (score, pq, pt, sim) if want_sim else (score, pq, pt)
 
+    def fill_sub(self, q, t, rect, direction=FWD, repro_rev_bug=True):
+        """build_subdpm (dpmatrix.h:319-353): rect = (q1_end, t1_end, q2_beg, t2_beg), matrix indices."""
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        rc = self.lib.orc_fill_sub(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), C.byref(self.sc),
+                                   direction, int(repro_rev_bug), int(rect[0]), int(rect[1]), int(rect[2]),
+                                   int(rect[3]), _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int))
+        if rc:
+            raise RuntimeError("Illegal bounds building DPM")
+        return score, pq, pt
+
     def sim(self, q, t):
         q = np.asarray(q, dtype=np.int64)
         t = np.asarray(t, dtype=np.int64)
@@ -176,6 +191,17 @@ class Reference:
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return score, pq, pt, sim
+
+    def fill_sub(self, q, t, rect, direction=FWD):
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        rc = self.lib.ref_fill_sub(*self._args(q, t), direction, int(rect[0]), int(rect[1]), int(rect[2]),
+                                   int(rect[3]), _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int))
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return score, pq, pt
 
     def optimal(self, q, t, direction=FWD):
         cap = len(q) + len(t) + 16

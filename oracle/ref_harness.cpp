@@ -120,6 +120,38 @@ int ref_fill(const char* q, const char* t, const char* matrix_file, float gi, fl
   }
 }
 
+// build_subdpm through the reference's 9-argument constructor (dpmatrix.h:169-189; real argument order
+// q1_end, t1_end, q2_beg, t2_beg). Same outputs as ref_fill.
+int ref_fill_sub(const char* q, const char* t, const char* matrix_file, float gi, float ge,
+                 int align_type, int direction, int q1_end, int t1_end, int q2_beg, int t2_beg,
+                 float* score, int* prev_q, int* prev_t) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, q1_end, t1_end, q2_beg, t2_beg, static_cast<direction_t>(direction), ap.align_type);
+    int sz1 = dpm.getQuerySize(), sz2 = dpm.getTemplateSize();
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) {
+        const DPCell* c = dpm.getCell(i, j);
+        size_t o = (size_t)i * sz2 + j;
+        if (score) score[o] = c->score;
+        if (prev_q) prev_q[o] = c->prev_query_idx;
+        if (prev_t) prev_t[o] = c->prev_template_idx;
+      }
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
 // Optimal alignment through the reference's own Optimal enumerator (optimal.h:47-124) on a
 // forward matrix. pairs receives (q,t) index pairs, 2 ints each.
 int ref_optimal(const char* q, const char* t, const char* matrix_file, float gi, float ge,

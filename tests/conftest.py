@@ -29,3 +29,10 @@ def golden_float():
     # reference outputs for scoring that is NOT on a dyadic grid (oracle/gen_golden_float.py)
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_float.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_sub():
+    # reference outputs of the 9-argument constructor / build_subdpm (oracle/gen_golden_sub.py)
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_sub.npz"))

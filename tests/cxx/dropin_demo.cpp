@@ -62,6 +62,13 @@ int main(int argc, char** argv) {
          it != alignments[0].end(); ++it)
       std::printf(" %d:%d", it->query_idx(), it->template_idx());
     std::printf("\n");
+    // sub-rectangle fill through the 9-argument constructor (dpmatrix.h:169-189 -> build_subdpm)
+    if (query.size() > 9 && templ.size() > 9) {
+      Matrix sub(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, fwd, params.align_type);
+      dump("S", sub);
+      Matrix subr(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, rev, params.align_type);
+      dump("T", subr);
+    }
 #ifdef AADP_HMAP2_DPMATRIX_H
     // extras of this build: reverse traceback and the near-optimal cell set
     try {

@@ -510,3 +510,43 @@ def test_gpu_traceback_of_whole_batch(ctx, at):
                 assert (orc != 0) == (st[p] != 0)
                 if orc == 0:
                     assert_matrix_equal("oracle pair %d dir %d" % (p, d), pairs[aoff[p]:aoff[p] + n[p]], opairs)
+
+
+def test_sub_rectangle_fill_golden_and_random(golden_sub, blosum):
+    # aadp_fill_subpair == the reference's 9-argument constructor (build_subdpm, dpmatrix.h:319-353)
+    import alignment_algos_b200 as a
+    g = golden_sub
+    c = a.Context(0)
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        c.set_scoring(g["sub"], gi, ge, at)
+        for d, tag in ((a.FWD, "fwd"), (a.REV, "rev")):
+            s, pq, pt = c.fill_subpair(q, t, g[name + ".rect"], d)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+    _, M = blosum
+    rng = np.random.default_rng(23)
+    for gi, ge, at in [(12, 1, po.SEMI_LOCAL), (4.73, 0.34, po.GLOBAL), (3, 1, po.LOCAL), (10.5, 0.25, po.GLOBAL_LOCAL)]:
+        c.set_scoring(M, gi, ge, at)
+        O = po.Oracle(M, gi, ge, at)
+        for trial in range(10):
+            Lq, Lt = int(rng.integers(1, 120)), int(rng.integers(1, 700 if trial == 0 else 120))
+            q, t = rand_pair(rng, Lq, Lt)
+            q0 = int(rng.integers(0, Lq + 1)); q1 = int(rng.integers(q0 + 1, Lq + 2))
+            t0 = int(rng.integers(0, Lt + 1)); t1 = int(rng.integers(t0 + 1, Lt + 2))
+            for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+                s, pq, pt = c.fill_subpair(q, t, (q0, t0, q1, t1), d)
+                ws, wq, wt = O.fill_sub(q, t, (q0, t0, q1, t1), od)
+                assert_matrix_equal("sub score", s, ws)
+                assert_matrix_equal("sub pq", pq, wq)
+                assert_matrix_equal("sub pt", pt, wt)
+        # the whole matrix as a rectangle is the ordinary fill
+        q, t = rand_pair(rng, 40, 33)
+        s, pq, pt = c.fill_subpair(q, t, (0, 0, 41, 34), a.FWD)
+        out = c.fill_pair(q, t, a.FWD)
+        assert_matrix_equal("full rect score", s, out["score_fwd"])
+        assert_matrix_equal("full rect pq", pq, out["prevq_fwd"])
+    with pytest.raises(a.AadpError):
+        c.fill_subpair(q, t, (5, 5, 5, 9), a.FWD)  # "Illegal bounds building DPM"
+    c.close()

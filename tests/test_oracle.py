@@ -131,3 +131,37 @@ def test_oracle_literal_fill_matches_float_golden(golden_float):
             assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
             assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
             assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+
+
+def test_oracle_sub_rectangle_fill_matches_golden(golden_sub):
+    # build_subdpm (dpmatrix.h:319-353): anchors inside the matrix, at the Head / Tail, degenerate rectangles
+    g = golden_sub
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        O = po.Oracle(g["sub"], gi, ge, at)
+        for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+            s, pq, pt = O.fill_sub(q, t, g[name + ".rect"], d)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_sub_rectangle_fill_matches_reference_random(blosum):
+    alpha, M = blosum
+    rng = np.random.default_rng(17)
+    for gi, ge in [(12, 1), (4.73, 0.34)]:
+        for at in MODES:
+            O = po.Oracle(M, gi, ge, at)
+            R = po.Reference(alpha, M, gi, ge, at)
+            for trial in range(12):
+                Lq, Lt = int(rng.integers(1, 30)), int(rng.integers(1, 30))
+                q, t = rand_pair(rng, Lq, Lt)
+                q0 = int(rng.integers(0, Lq + 1)); q1 = int(rng.integers(q0 + 1, Lq + 2))
+                t0 = int(rng.integers(0, Lt + 1)); t1 = int(rng.integers(t0 + 1, Lt + 2))
+                for d in (po.FWD, po.REV):
+                    rs, rq, rt = R.fill_sub(q, t, (q0, t0, q1, t1), d)
+                    s, pq, pt = O.fill_sub(q, t, (q0, t0, q1, t1), d)
+                    assert_matrix_equal("score", s, rs)
+                    assert_matrix_equal("pq", pq, rq)
+                    assert_matrix_equal("pt", pt, rt)
