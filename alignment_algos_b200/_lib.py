@@ -61,6 +61,7 @@ def lib():
     L.aadp_decode_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, vp, vp]
     L.aadp_batch_optimal_all.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp]
     L.aadp_fill_subpair.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.aadp_fill_pair_general.argtypes = [vp, vp, C.c_int, C.c_int, f32, f32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
     L.aadp_upload_sequences.argtypes = [vp, vp, vp, i64]
     L.aadp_cross_run.argtypes = [vp, vp, i64, vp, i64, vp]
     L.aadp_cross_scores.argtypes = [vp, vp, vp, i64, vp, i64, vp, i64, vp]
@@ -77,5 +78,5 @@ EXPORTS = [
     "aadp_last_h2d_bytes", "aadp_last_d2h_bytes", "aadp_last_cell_updates", "aadp_set_profiling", "aadp_profile_count", "aadp_profile_get",
     "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes", "aadp_batch_tb_bytes",
     "aadp_batch_fetch_tb", "aadp_decode_cell", "aadp_upload_sequences", "aadp_cross_run", "aadp_cross_scores",
-    "aadp_last_cross_cell_updates", "aadp_batch_optimal_all", "aadp_fill_subpair",
+    "aadp_last_cross_cell_updates", "aadp_batch_optimal_all", "aadp_fill_subpair", "aadp_fill_pair_general",
 ]

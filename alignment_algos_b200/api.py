@@ -99,6 +99,16 @@ class Context:
                                           int(rect[2]), int(rect[3]), direction, _ptr(s), _ptr(pq), _ptr(pt)))
         return s, pq, pt
 
+    def fill_pair_general(self, sim, gi, ge, align_type, direction=FWD, rect=None, flags=REPRO_REV_BUG):
+        """Any evaluator with uniform affine gaps: sim is the (Lq+2, Lt+2) similarity matrix of simmatrix.h."""
+        sim = np.ascontiguousarray(sim, dtype=np.float32)
+        sz = sim.shape
+        s, pq, pt = np.zeros(sz, np.float32), np.zeros(sz, np.int32), np.zeros(sz, np.int32)
+        r = np.ascontiguousarray(rect, np.int32) if rect is not None else None
+        self._ck(self.L.aadp_fill_pair_general(self.h, _ptr(sim), sz[0] - 2, sz[1] - 2, gi, ge, align_type, flags,
+                                               direction, _ptr(r), _ptr(s), _ptr(pq), _ptr(pt)))
+        return s, pq, pt
+
     # ---- batches ----
     @staticmethod
     def pack(seqs):

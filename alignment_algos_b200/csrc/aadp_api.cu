@@ -1304,8 +1304,17 @@ int aadp_cross_scores(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
 // ---- exact general-gap fp32 path (aadp_general.cuh) ------------------------------------------------
 // Fills the n consecutive pairs [p0, p0+n) of the batch in the directions of `dirmask` (bit 0 forward,
 // bit 1 reverse) into the dense scratch matrices of the context.  off = n+1 cell offsets of the pairs.
+// Scoring override of one general-gap launch (aadp_fill_pair_general): a dense similarity matrix from any
+// Evaluator plus the uniform affine gap model, instead of the context's substitution table.
+struct GeneralOverride {
+  float gi, ge;
+  int align_type;
+  uint32_t flags;
+  const float* d_sim;
+};
+
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
-                   float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr) {
+                   float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr, const GeneralOverride* ov = nullptr) {
   Batch& b = c->b;
   const int64_t cells = off[(size_t)n];
   int maxLt = 0, maxL = 0;
@@ -1326,6 +1335,16 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   G.insfree = c->sc.insfree;
   G.local = c->sc.local;
   G.repro_rev_bug = (c->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
+  if (ov) {
+    G.gi = ov->gi;
+    G.ge = ov->ge;
+    G.delfree = (ov->align_type == AADP_LOCAL || ov->align_type == AADP_SEMI_LOCAL || ov->align_type == AADP_LOCAL_GLOBAL);
+    G.insfree = (ov->align_type == AADP_LOCAL || ov->align_type == AADP_SEMI_LOCAL || ov->align_type == AADP_GLOBAL_LOCAL);
+    G.local = ov->align_type == AADP_LOCAL;
+    G.repro_rev_bug = (ov->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
+    G.simov = ov->d_sim;
+    G.A = 1;
+  }
   G.residues = c->residues.as<uint8_t>();
   G.seq_off = c->seq_off.as<int64_t>();
   G.pair_q = c->pair_q.as<int32_t>();
@@ -1883,6 +1902,50 @@ int aadp_fill_subpair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, i
   if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->b.ran_what = 0;
+  return 0;
+}
+
+int aadp_fill_pair_general(aadp_ctx* c, const float* sim, int Lq, int Lt, float gi, float ge, int align_type, uint32_t flags,
+                           int direction, const int* rect, float* score, int32_t* prev_q, int32_t* prev_t) {
+  if (check_ctx(c, false)) return 1;
+  if (Lq < 0 || Lt < 0) return fail("Illegal bounds building DPM");
+  if (!sim) return fail("null argument");
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  if (align_type < 0 || align_type > 4) return fail("Illegal gap style");
+  if (!(gi >= 0.f) || !(ge >= 0.f)) return fail("gap penalties must be non-negative");
+  if (rect) {
+    if (rect[2] <= rect[0] || rect[3] <= rect[1]) return fail("Illegal bounds building DPM");
+    if (rect[0] < 0 || rect[1] < 0 || rect[2] > Lq + 1 || rect[3] > Lt + 1) return fail("sub-rectangle anchors outside the matrix");
+  }
+  // a one-pair batch without residues: the similarity matrix carries everything the fill needs
+  Batch& b = c->b;
+  b.nseq = 2;
+  b.npairs = 1;
+  b.seq_off = {0, Lq, (int64_t)Lq + Lt};
+  b.pair_q = {0};
+  b.pair_t = {1};
+  b.have_seqs = false;
+  b.ran_what = 0;
+  b.uploaded_what = 0;
+  b.tb_off.clear();
+  CK(cudaStreamSynchronize(c->stream));
+  if (pin_reserve(c, 4096)) return 1;
+  if (upload_vec(c, c->seq_off, b.seq_off) || upload_vec(c, c->pair_q, b.pair_q) || upload_vec(c, c->pair_t, b.pair_t)) return 1;
+  if (c->residues.reserve((size_t)Lq + Lt + 16)) return 1;
+  CK(cudaMemsetAsync(c->residues.p, 0, (size_t)Lq + Lt + 16, c->stream));
+  const int64_t n = (int64_t)(Lq + 2) * (Lt + 2);
+  if (c->scratch_d.reserve((size_t)n * 4)) return 1;
+  CK(cudaMemcpyAsync(c->scratch_d.p, sim, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // gg_fill recycles the pinned pool; the caller's sim buffer is free again
+  const std::vector<int64_t> doff = {0, n};
+  GeneralOverride ov{gi, ge, align_type, flags, c->scratch_d.as<float>()};
+  const int d = direction - 1;
+  c->launches = 0;
+  if (gg_fill(c, 0, 1, 1 << d, true, doff, nullptr, nullptr, rect, &ov)) return 1;
+  if (score) CK(cudaMemcpyAsync(score, c->gg_score[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -37,6 +37,9 @@ struct GeneralParams {
   int item0;
   int dirs[2];               // blockIdx.y -> 0 forward, 1 reverse
   const int64_t* dense_off;  // per item: offset (in cells) of its (Lq+2)*(Lt+2) matrices; null = 0
+  const float* simov;        // similarity override: dense (Lq+2)*(Lt+2) matrices per item (same offsets as the
+                             // outputs), as SimilarityMatrix (simmatrix.h:40-73) built them from ANY Evaluator; null =
+                             // substitution table lookup
   const int4* rects;         // per item: anchors (q1_end, t1_end, q2_beg, t2_beg) of build_subdpm (dpmatrix.h:319-353),
                              // matrix indices; null = the whole matrix (0, 0, Lq+1, Lt+1)
   float* score[2];           // per direction: dense score matrices (always)
@@ -84,8 +87,10 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   auto colof = [&](int b) { return rev ? mt1 - b : t0 + b; };
   auto at = [&](int a, int b) -> int64_t { return (int64_t)rowof(a) * sz2 + colof(b); };
   auto clampl = [&](float s) { return (local && s < 0.f) ? 0.f : s; };
-  auto sim = [&](int a, int b) -> float {  // flow cell -> substitution score (interior cells only)
+  const float* simov = P.simov ? P.simov + base : nullptr;
+  auto sim = [&](int a, int b) -> float {  // flow cell -> similarity (interior cells only)
     const int i = rowof(a), j = colof(b);
+    if (simov) return simov[(int64_t)i * sz2 + j];
     return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
   };
   // gap between flow columns b0 < b1 / flow rows a0 < a1, with the free end gaps of aasubalib.h:39-42,65-68:
@@ -109,7 +114,8 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   float simf = 0.f;
   {
     const int i = rowof(q1), j = colof(t1);
-    if (i >= 1 && i <= Lq && j >= 1 && j <= Lt) simf = P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
+    if (simov) simf = simov[(int64_t)i * sz2 + j];
+    else if (i >= 1 && i <= Lq && j >= 1 && j <= Lt) simf = P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
   }
 
   // DPCell::DPCell (dpmatrix.cpp:17-25): score 0, predecessors null
@@ -155,10 +161,9 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
 
   // interior rows (dpmatrix.h:446-497): match, deletions k ascending, insertions k ascending, strict '>'
   for (int a = 2; a <= nq; ++a) {
-    const int qa = qseq[rowof(a) - 1];
-    const float* subrow = P.subf + qa * P.A;
+    const float* subrow = simov ? simov + (int64_t)rowof(a) * sz2 : P.subf + (int)qseq[rowof(a) - 1] * P.A;
     for (int b = 2 + tid; b <= nt; b += nth) {
-      const float simc = subrow[(int)tseq[colof(b) - 1]];
+      const float simc = simov ? subrow[colof(b)] : subrow[(int)tseq[colof(b) - 1]];
       int oa = a - 1, ob = b - 1;
       float os = clampl(__fadd_rn(prow[b - 1], simc));
       for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468

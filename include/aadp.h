@@ -103,6 +103,18 @@ int aadp_fill_subpair(aadp_ctx* ctx, const uint8_t* q, int Lq, const uint8_t* t,
                       int t1_end, int q2_beg, int t2_beg, int direction, float* score,
                       int32_t* prev_q, int32_t* prev_t);
 
+/* ---- ANY Evaluator with a uniform affine gap model: the similarity matrix the reference builds on the host
+ * (SimilarityMatrix, simmatrix.h:40-73: sim[i][j] = evaluator.similarity(q,t,i,j), after post_process) is handed
+ * over as it is -- (Lq+2)*(Lt+2) floats, row-major -- together with gap(len) = gi + ge*(len-1) and the align
+ * type that selects the free end gaps (aasubalib.h:27-77).  This is what DPMatrix<S1,S2,Etype>::build() /
+ * build_subdpm() can bind to for every Etype whose gap functions have that form, without describing residues
+ * or a substitution table (tests/cxx/refpatch_demo.cpp does exactly that to the UNMODIFIED reference headers).
+ * rect: NULL for the whole matrix, or {q1_end, t1_end, q2_beg, t2_beg}.  Exact general-gap fp32 kernel; needs
+ * no aadp_set_scoring.                                                                                    */
+int aadp_fill_pair_general(aadp_ctx* ctx, const float* sim, int Lq, int Lt, float gi, float ge,
+                           int align_type, uint32_t flags, int direction, const int* rect, float* score,
+                           int32_t* prev_q, int32_t* prev_t);
+
 /* ---- batch of pairs, HOST buffers (the end-to-end call) ------------------------------------
  * residues: all sequences back to back; sequence s is residues[seq_off[s] .. seq_off[s+1]).
  * pair p aligns query pair_q[p] against template pair_t[p].

@@ -94,3 +94,35 @@ def test_gpu_dropin_equals_reference_build(blosum, at):
             mask, cnt = O.nearopt_mask(F, R, O.sim(q, t), thr)
             no = [l for l in got if l.startswith("#NEAROPT")][0].split()
             assert int(no[-1]) == cnt and float(no[4]) == pytest.approx(thr, rel=1e-6)
+
+
+REFPATCH_GPU = os.path.join(CXX, "refpatch_gpu")
+REFPATCH_CPU = os.path.join(CXX, "refpatch_cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("at", MODES, ids=[MODE_NAMES[m] for m in MODES])
+def test_unmodified_reference_with_gpu_fill_enumerates_the_same_alignments(at):
+    """tests/cxx/refpatch_demo.cpp: the reference's own headers + sources, with DPMatrix::build()/build_subdpm()
+    specialised from the outside to call aadp_fill_pair_general.  The reference's own Optimal, UCW and CNO
+    enumerators then run over the GPU-filled matrices and must print exactly what the pure reference prints:
+    every DPCell, the optimal alignment, and every near-optimal alignment with its score."""
+    if not (os.path.exists(REFPATCH_GPU) and os.path.exists(REFPATCH_CPU)):
+        pytest.skip("refpatch binaries not built (they need /root/reference at build time)")
+    rng = np.random.default_rng(300 + at)
+    cases = [(12, 1, 0.2, 18, 22), (4.73, 0.34, 0.1, 25, 21), (3, 1, 0.05, 30, 30), (12, 1, 0.3, 4, 9)]
+    n_alignments = 0
+    for gi, ge, delta, Lq, Lt in cases:
+        # related sequences (a mutated copy) so that the near-optimal set is not trivial
+        q = rng.integers(0, 20, Lq).astype(np.uint8)
+        t = np.resize(q, Lt).copy()
+        mut = rng.random(Lt) < 0.25
+        t[mut] = rng.integers(0, 20, int(mut.sum()))
+        args = [MATRIX, str(at), str(gi), str(ge), str(delta), _letters(q), _letters(t)]
+        got = subprocess.run([REFPATCH_GPU] + args, capture_output=True, text=True, timeout=300)
+        want = subprocess.run([REFPATCH_CPU] + args, capture_output=True, text=True, timeout=300)
+        assert got.returncode == 0, got.stdout[-400:] + got.stderr[-400:]
+        assert want.returncode == 0
+        assert got.stdout == want.stdout, "GPU-filled reference and pure reference print different results"
+        n_alignments += sum(1 for l in got.stdout.splitlines() if l.startswith(("UCW ", "CNO ")))
+    assert at == po.LOCAL or n_alignments > 10

@@ -550,3 +550,31 @@ def test_sub_rectangle_fill_golden_and_random(golden_sub, blosum):
     with pytest.raises(a.AadpError):
         c.fill_subpair(q, t, (5, 5, 5, 9), a.FWD)  # "Illegal bounds building DPM"
     c.close()
+
+
+def test_general_entry_with_similarity_matrix(blosum):
+    # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(77)
+    c = a.Context(0)   # no aadp_set_scoring needed
+    for gi, ge, at in [(12, 1, po.SEMI_LOCAL), (4.73, 0.34, po.GLOBAL), (2.5, 0.5, po.LOCAL), (7, 0.3, po.LOCAL_GLOBAL)]:
+        O = po.Oracle(M, gi, ge, at)
+        for Lq, Lt in [(0, 3), (1, 1), (17, 40), (90, 61)]:
+            q, t = rand_pair(rng, Lq, Lt)
+            sim = O.sim(q, t)
+            for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+                s, pq, pt = c.fill_pair_general(sim, gi, ge, at, d)
+                ws, wq, wt = O.fill(q, t, od, True, fast=False)
+                assert_matrix_equal("general score", s, ws)
+                assert_matrix_equal("general pq", pq, wq)
+                assert_matrix_equal("general pt", pt, wt)
+    # a similarity matrix no substitution table could produce (position specific, like a profile evaluator):
+    # symmetry check against the transposed problem with swapped free-end roles
+    sim = rng.normal(0, 3, (42, 37)).astype(np.float32)
+    sim[0, :] = sim[-1, :] = 0
+    sim[:, 0] = sim[:, -1] = 0
+    s1, _, _ = c.fill_pair_general(sim, 4.73, 0.34, po.GLOBAL, a.FWD)
+    s2, _, _ = c.fill_pair_general(np.ascontiguousarray(sim.T), 4.73, 0.34, po.GLOBAL, a.FWD)
+    assert s1[-1, -1] == s2[-1, -1]
+    c.close()
