@@ -13,7 +13,9 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if _build.needs_build():
+    if os.environ.get("AADP_LIB"):  # A/B measurements: an alternative build of the same library
+        path = os.environ["AADP_LIB"]
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # no nvcc on the box: use the shipped .so if there is one

@@ -417,7 +417,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           cp_async16(qst[h] + 16 * ((blk - 1) & 1), qp[h] + 16 * (blk - 1), newblk);
           if (MSK) {
             const int more = pid[h] >= 0 && (i + 2) <= Lq[h];
-            const int16_t* src = fp[h] - (int64_t)(s + 2) * nl * 16;
+            const int16_t* src = fp[h] - (size_t)((uint32_t)(s + 2) * (uint32_t)nl * 16u);
             cp_async16(fst[h] + 32 * ((i + 2) % 3), src, more);
             cp_async16(fst[h] + 32 * ((i + 2) % 3) + 16, src + nl * 8, more);
           }
@@ -503,27 +503,30 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       x_pub = Xp[15];
       e_pub = E;
       mg_pub = Mgl;
+      // byte offsets of this step inside a pair's products fit 32 bits (Lt <= 512, bounded Lq): one 32-bit
+      // multiply shared by both halves, then base + offset per store
+      const uint32_t snl = (uint32_t)s * (uint32_t)nl;
       if (act0) {
-        if (TBM) *reinterpret_cast<uint2*>(tbp[0] + (int64_t)s * nl * 8) = make_uint2(tbA[0], tbA[1]);
+        if (TBM) *reinterpret_cast<uint2*>(tbp[0] + (size_t)(snl * 8u)) = make_uint2(tbA[0], tbA[1]);
         if (FST) {
-          int16_t* d = scp[0] + (int64_t)s * nl * 16;
+          uint8_t* d = reinterpret_cast<uint8_t*>(scp[0]) + (size_t)(snl * 32u);
           *reinterpret_cast<uint4*>(d) = make_uint4(oA[0], oA[1], oA[2], oA[3]);
-          *reinterpret_cast<uint4*>(d + nl * 8) = make_uint4(oA[4], oA[5], oA[6], oA[7]);
+          *reinterpret_cast<uint4*>(d + (size_t)((uint32_t)nl * 16u)) = make_uint4(oA[4], oA[5], oA[6], oA[7]);
         }
         if (MSK) {
-          *reinterpret_cast<uint16_t*>(mkp[0] + (int64_t)s * nl * 2) = (uint16_t)(accM & 0xffffu);
+          *reinterpret_cast<uint16_t*>(mkp[0] + (size_t)(snl * 2u)) = (uint16_t)(accM & 0xffffu);
           cnt[0] += __popc(accM & 0xffffu);
         }
       }
       if (act1) {
-        if (TBM) *reinterpret_cast<uint2*>(tbp[1] + (int64_t)s * nl * 8) = make_uint2(tbB[0], tbB[1]);
+        if (TBM) *reinterpret_cast<uint2*>(tbp[1] + (size_t)(snl * 8u)) = make_uint2(tbB[0], tbB[1]);
         if (FST) {
-          int16_t* d = scp[1] + (int64_t)s * nl * 16;
+          uint8_t* d = reinterpret_cast<uint8_t*>(scp[1]) + (size_t)(snl * 32u);
           *reinterpret_cast<uint4*>(d) = make_uint4(oB[0], oB[1], oB[2], oB[3]);
-          *reinterpret_cast<uint4*>(d + nl * 8) = make_uint4(oB[4], oB[5], oB[6], oB[7]);
+          *reinterpret_cast<uint4*>(d + (size_t)((uint32_t)nl * 16u)) = make_uint4(oB[4], oB[5], oB[6], oB[7]);
         }
         if (MSK) {
-          *reinterpret_cast<uint16_t*>(mkp[1] + (int64_t)s * nl * 2) = (uint16_t)(accM >> 16);
+          *reinterpret_cast<uint16_t*>(mkp[1] + (size_t)(snl * 2u)) = (uint16_t)(accM >> 16);
           cnt[1] += __popc(accM >> 16);
         }
         // the shorter query of the couple ends first: keep its final row before later rows overwrite it
@@ -575,12 +578,16 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
 }
 
 template <int TBM, int FST, int MSK, int XM>
-__global__ void __launch_bounds__(kPackedWarps * 32, XM ? 12 : (MSK ? 8 : 9)) packed_kernel(const PackedParams P) {
+__global__ void __launch_bounds__(kPackedWarps * 32) __maxnreg__(XM ? 168 : (MSK ? 255 : 224)) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
   int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
   const int sub_bytes = (A * (A + 1) + 15) / 16 * 16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int lane;
+  // read once and pinned in a register: the compiler otherwise re-reads SR_TID.X (S2R, ~25 cycles) in every
+  // step of the row loop to rebuild the per-lane shared-memory addresses
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
   int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
   constexpr int kStage = packed_stage_bytes(MSK);
   uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kStage;
