@@ -128,6 +128,7 @@ struct aadp_ctx {
   uint32_t flags = 0;
   std::vector<int8_t> sub8_h;
   int max_abs_sub = 0;
+  DevBuf sub8p;
   DevBuf sub8, residues, seq_off, pair_q, pair_t, order[2], tb_off, sc_off, mask_off;
   DevBuf tb[2], scb[2], mask, fin_score[2], fin_kind[2], fin_k[2], counter, bbuf, thr, count, fscore[2];
   DevBuf scratch_a, scratch_b, scratch_c, scratch_d;
@@ -672,6 +673,7 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
     PackedParams Q{};
     Q.sc = c->sc;
     Q.sub8 = c->sub8.as<int8_t>();
+    Q.sub8p = c->sub8p.as<int8_t>();
     Q.arena = dir ? c->arena_r.as<uint8_t>() : c->arena_f.as<uint8_t>();
     Q.aoff = c->aoff.as<int32_t>();
     Q.seq_off = c->seq_off.as<int64_t>();
@@ -925,7 +927,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect};
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -1019,6 +1021,13 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
   c->flags = flags;
   if (c->sub8.reserve((size_t)A * A)) return 1;
   CK(cudaMemcpyAsync(c->sub8.p, c->sub8_h.data(), (size_t)A * A, cudaMemcpyHostToDevice, c->stream));
+  {  // padded copy for the packed kernels' profile build: A rows of A+1 entries, entry A = pad column (-128)
+    std::vector<int8_t> pad((size_t)packed_sub_bytes(A), (int8_t)-128);
+    for (int a = 0; a < A; ++a)
+      for (int b2 = 0; b2 < A; ++b2) pad[(size_t)a * (A + 1) + b2] = c->sub8_h[(size_t)a * A + b2];
+    if (c->sub8p.reserve(pad.size())) return 1;
+    CK(cudaMemcpy(c->sub8p.p, pad.data(), pad.size(), cudaMemcpyHostToDevice));
+  }
   CK(cudaStreamSynchronize(c->stream));
   c->have_scoring = true;
   return 0;
@@ -1223,6 +1232,7 @@ int aadp_cross_run(aadp_ctx* c, const int32_t* q_ids, int64_t nq, const int32_t*
     PackedParams Q{};
     Q.sc = c->sc;
     Q.sub8 = c->sub8.as<int8_t>();
+    Q.sub8p = c->sub8p.as<int8_t>();
     Q.arena = c->arena_f.as<uint8_t>();
     Q.aoff = c->aoff.as<int32_t>();
     Q.seq_off = c->seq_off.as<int64_t>();

@@ -44,17 +44,28 @@ constexpr int kNeg16 = -20000;    // "-infinity" seed of E/F chains (only ever e
 constexpr int kFloor16 = -13000;  // clamp floor of M / slack
 constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must satisfy to use this kernel
 constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
-// per-warp cp.async staging: query rings (2 KB) + forward-score chunks (6 KB, reverse+mask pass only)
-__host__ __device__ constexpr int packed_stage_bytes(int msk) { return msk ? 2048 + 6144 : 2048; }
+// per-warp cp.async staging: query rings (1 KB: 2 halves x 2 blocks of 8 rows per lane) + forward-score chunks
+// (6 KB, reverse+mask pass only).  Shared memory is what bounds the warps per SM, so nothing else gets a region of
+// its own: the padded substitution table is only needed while a profile is being built and ALIASES the staging
+// area (copied in per task, before the first cp.async of the task is issued), and the 512-byte reduction scratch
+// of the final cells aliases the profile (dead by then) -- except in cross mode, where the profile outlives the
+// query couples of an item and the scratch has its own 512 bytes.
+// Per CTA: forward 21.5 KB -> 10 warps/SM, reverse+mask 27 KB -> 8 warps/SM (was 23.5 / 29.6 KB: 9 and 7).
+// bytes of the padded substitution table: A rows of A+1 entries (entry A = pad = -128), rounded up to 16
+__host__ __device__ inline int packed_sub_bytes(int A) { return (A * (A + 1) + 15) / 16 * 16; }
+__host__ __device__ inline int packed_stage_bytes(int A, int msk) {
+  const int st = msk ? 1024 + 6144 : 1024;
+  return st > packed_sub_bytes(A) ? st : packed_sub_bytes(A);  // alphabets above 31 letters need more than 1 KB
+}
 // xm (cross mode): both halves of a couple align against the SAME template, so one profile serves both
 __host__ __device__ inline size_t packed_smem_bytes(int A, int msk, int xm = 0) {
-  return (size_t)((A * (A + 1) + 15) / 16 * 16) +
-         (size_t)kPackedWarps * (32 * sizeof(int4) + packed_stage_bytes(msk) + (xm ? 1 : 2) * A * 512);
+  return (size_t)kPackedWarps * ((xm ? 32 * sizeof(int4) : 0) + packed_stage_bytes(A, msk) + (xm ? 1 : 2) * A * 512);
 }
 
 struct PackedParams {
   Scoring sc;
   const int8_t* sub8;        // A*A scaled substitution scores
+  const int8_t* sub8p;       // the same, padded: A rows of A+1 entries (entry A = -128), packed_sub_bytes(A) bytes
   const uint8_t* arena;      // 4-byte aligned sequence arena in the FLOW order of this direction
   const int32_t* aoff;       // per sequence: byte offset into arena
   const int64_t* seq_off;    // nseq+1 (lengths)
@@ -128,6 +139,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 16; }"
                :: "r"(sa), "l"(gsrc), "r"(cond) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int cond) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 8; }"
+               :: "r"(sa), "l"(gsrc), "r"(cond) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>
@@ -143,7 +159,7 @@ struct RowSum {
 
 template <int TBM, int FST, int MSK, int XM>
 __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int8_t* prof, int4* red,
-                                            uint8_t* stage, const int8_t* s_sub, int lane) {
+                                            uint8_t* stage, int lane) {
   const Scoring& S = P.sc;
   const int gi = S.gi, ge = S.ge, A = S.A;
   const int W = 512;  // profile row stride: 32 lanes * 16 columns
@@ -192,6 +208,12 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   // ---- template profiles: prof[a*512 + lane*16 + c] = sub8[a][t_(column of register c)], pads = -128
   // (cross mode: one profile for both halves, built once per item and reused by every query couple)
   if (!XM || rep == 0) {
+    // padded substitution table (A rows of A+1 entries, entry A = pad = -128) into the staging area: no cp.async
+    // of this task has been issued yet and the previous task drained its own
+    int8_t* s_sub = reinterpret_cast<int8_t*>(stage);
+    __syncwarp();
+    for (int x = lane; x < packed_sub_bytes(A) / 16; x += 32)
+      reinterpret_cast<uint4*>(s_sub)[x] = reinterpret_cast<const uint4*>(P.sub8p)[x];
     uint32_t tc[2][4];
 #pragma unroll
     for (int h = 0; h < (XM ? 1 : 2); ++h)
@@ -305,15 +327,15 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     THR2 = pkb(ti[0], ti[1]);
   }
 
-  // ---- query residues: each lane stages its own rows in a private 32-byte ring per half
-  // (two 16-row blocks), refilled with cp.async one block (16 rows) ahead of use.
-  uint8_t* qst[2] = {stage + lane * 64, stage + lane * 64 + 32};
+  // ---- query residues: each lane stages its own rows in a private 16-byte ring per half
+  // (two 8-row blocks), refilled with cp.async one block (8 rows) ahead of use.
+  uint8_t* qst[2] = {stage + lane * 32, stage + lane * 32 + 16};
   // forward-score chunks (MSK): private triple buffer (3 x 32 bytes per half), requested two rows ahead
-  uint8_t* fst[2] = {stage + 2048 + lane * 192, stage + 2048 + lane * 192 + 96};
+  uint8_t* fst[2] = {stage + 1024 + lane * 192, stage + 1024 + lane * 192 + 96};
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    cp_async16(qst[h], qp[h], 1);
-    cp_async16(qst[h] + 16, qp[h] + 16, 1);
+    cp_async8(qst[h], qp[h], 1);
+    cp_async8(qst[h] + 8, qp[h] + 8, 1);
   }
 
   uint32_t x_pub = FLOOR2, e_pub = NEG2, mg_pub = NEG2;
@@ -383,19 +405,19 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     const bool act1 = pid[1] >= 0 && i >= 1 && i <= Lq[1];
     if (act0 || act1) {
       const int r0 = i - 1;
-      // One cp.async group is committed per row.  Query blocks are requested 16 rows ahead and forward
+      // One cp.async group is committed per row.  Query blocks are requested 8 rows ahead and forward
       // scores 2 rows ahead, so only the most recent group(s) may still be in flight.
       if (i == 1) {
         cp_async_wait_all();
         qa_n0 = qst[0][0];
         qa_n1 = qst[1][0];
       } else if (MSK) cp_async_wait_group<1>();
-      else cp_async_wait_group<8>();
+      else cp_async_wait_group<4>();
       const int qa0 = qa_n0, qa1 = qa_n1;
       const uint4 pa = *reinterpret_cast<const uint4*>(profA + qa0 * W + lane * 16);
       const uint4 pb = *reinterpret_cast<const uint4*>(profB + qa1 * W + lane * 16);
-      qa_n0 = qst[0][i & 31];
-      qa_n1 = qst[1][i & 31];
+      qa_n0 = qst[0][i & 15];
+      qa_n1 = qst[1][i & 15];
       const uint32_t pwA[4] = {pa.x, pa.y, pa.z, pa.w};
       const uint32_t pwB[4] = {pb.x, pb.y, pb.z, pb.w};
       uint32_t fcur[2][8];
@@ -409,12 +431,12 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         }
       }
       {
-        // stage ahead: the next 16-row query block (once per 16 rows) and the forward scores of row i+2
-        const int blk = (r0 >> 4) + 2;  // blocks 0 and 1 were requested up front
-        const int newblk = ((r0 & 15) == 0) && r0 > 0;
+        // stage ahead: the next 8-row query block (once per 8 rows) and the forward scores of row i+2
+        const int blk = (r0 >> 3) + 2;  // blocks 0 and 1 were requested up front
+        const int newblk = ((r0 & 7) == 0) && r0 > 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          cp_async16(qst[h] + 16 * ((blk - 1) & 1), qp[h] + 16 * (blk - 1), newblk);
+          cp_async8(qst[h] + 8 * ((blk - 1) & 1), qp[h] + 8 * (blk - 1), newblk);
           if (MSK) {
             const int more = pid[h] >= 0 && (i + 2) <= Lq[h];
             const int16_t* src = fp[h] - (size_t)((uint32_t)(s + 2) * (uint32_t)nl * 16u);
@@ -573,36 +595,32 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       }
     }
   }
+  cp_async_wait_all();  // the staging area is recycled by the next couple / task
   __syncwarp();
   }  // rep
 }
 
 template <int TBM, int FST, int MSK, int XM>
-__global__ void __launch_bounds__(kPackedWarps * 32) __maxnreg__(XM ? 168 : (MSK ? 255 : 224)) packed_kernel(const PackedParams P) {
+__global__ void __launch_bounds__(kPackedWarps * 32) __maxnreg__(XM ? 168 : (MSK ? 255 : (TBM ? 224 : 200))) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
-  int8_t* s_sub = reinterpret_cast<int8_t*>(smem);  // A rows of A+1 entries; entry A = pad (-128)
-  const int sub_bytes = (A * (A + 1) + 15) / 16 * 16;
   const int warp = threadIdx.x >> 5;
   int lane;
   // read once and pinned in a register: the compiler otherwise re-reads SR_TID.X (S2R, ~25 cycles) in every
   // step of the row loop to rebuild the per-lane shared-memory addresses
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-  int4* red = reinterpret_cast<int4*>(smem + sub_bytes) + warp * 32;
-  constexpr int kStage = packed_stage_bytes(MSK);
-  uint8_t* stage = smem + sub_bytes + kPackedWarps * 32 * sizeof(int4) + warp * kStage;
-  int8_t* prof = reinterpret_cast<int8_t*>(smem + sub_bytes + kPackedWarps * (32 * sizeof(int4) + kStage)) + warp * (XM ? 1 : 2) * A * 512;
-  for (int x = threadIdx.x; x < A * (A + 1); x += blockDim.x) {
-    const int a = x / (A + 1), b = x % (A + 1);
-    s_sub[x] = (b < A) ? P.sub8[a * A + b] : (int8_t)-128;
-  }
-  __syncthreads();
+  const int kStage = packed_stage_bytes(A, MSK);
+  const int per_warp = (XM ? 512 : 0) + kStage + (XM ? 1 : 2) * A * 512;
+  unsigned char* mine = smem + warp * per_warp;
+  uint8_t* stage = mine + (XM ? 512 : 0);
+  int8_t* prof = reinterpret_cast<int8_t*>(stage + kStage);
+  int4* red = XM ? reinterpret_cast<int4*>(mine) : reinterpret_cast<int4*>(prof);
   for (;;) {
     unsigned int item = 0;
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_tasks) break;
-    packed_task<TBM, FST, MSK, XM>(P, (int)item, prof, red, stage, s_sub, lane);
+    packed_task<TBM, FST, MSK, XM>(P, (int)item, prof, red, stage, lane);
   }
 }
 
