@@ -43,6 +43,7 @@ constexpr int kBias16 = 21500;
 constexpr int kNeg16 = -20000;    // "-infinity" seed of E/F chains (only ever extended once)
 constexpr int kFloor16 = -13000;  // clamp floor of M / slack
 constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must satisfy to use this kernel
+constexpr int kFwdAhead = 8;      // rows of L2 prefetch distance for the forward scores the reverse+mask pass reads
 constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
 // per-warp cp.async staging: query rings (1 KB: 2 halves x 2 blocks of 8 rows per lane) + forward-score chunks
 // (6 KB, reverse+mask pass only).  Shared memory is what bounds the warps per SM, so nothing else gets a region of
@@ -143,6 +144,10 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int 
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 8; }"
                :: "r"(sa), "l"(gsrc), "r"(cond) : "memory");
+}
+// L2 prefetch of one sector (no destination, no scoreboard): the DRAM latency of a later cp.async is paid early
+__device__ __forceinline__ void prefetch_l2(const void* gsrc, int cond) {
+  asm volatile("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q prefetch.global.L2 [%0]; }" :: "l"(gsrc), "r"(cond) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -442,6 +447,12 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             const int16_t* src = fp[h] - (size_t)((uint32_t)(s + 2) * (uint32_t)nl * 16u);
             cp_async16(fst[h] + 32 * ((i + 2) % 3), src, more);
             cp_async16(fst[h] + 32 * ((i + 2) % 3) + 16, src + nl * 8, more);
+            // two rows (~700 cycles) do not cover a DRAM round trip under load: pull the chunk of row
+            // i+kFwdAhead into L2 now, so that the cp.async issued for it later is an L2 hit
+            const int far = pid[h] >= 0 && (i + kFwdAhead) <= Lq[h];
+            const int16_t* psrc = fp[h] - (size_t)((uint32_t)(s + kFwdAhead) * (uint32_t)nl * 16u);
+            prefetch_l2(psrc, far);
+            prefetch_l2(psrc + nl * 8, far);
           }
         }
         cp_async_commit();
