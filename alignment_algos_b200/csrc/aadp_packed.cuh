@@ -370,6 +370,9 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         if (pid[h] >= 0 && j >= 1 && j <= Lt[h]) VM |= 1u << (8 * (2 * h + (c & 1)) + 7 - (c >> 1));
       }
   }
+  // triple-buffer offsets of the forward-score chunks: row i lives at 32*(i % 3), row i+2 at 32*((i+2) % 3) =
+  // 32*((i-1) % 3); rotated once per row instead of dividing by 3 (a lane's active rows are consecutive, from 1)
+  int fcur_off = 32, fnxt_off = 0;
   long long cnt[2] = {0, 0};
   RowSum capB = {kNeg32, 0, kNeg32, kNeg32};
   bool have_capB = false;
@@ -429,7 +432,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       if (MSK) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint4* src = reinterpret_cast<const uint4*>(fst[h] + 32 * (i % 3));
+          const uint4* src = reinterpret_cast<const uint4*>(fst[h] + fcur_off);
           const uint4 a = src[0], b = src[1];
           fcur[h][0] = a.x; fcur[h][1] = a.y; fcur[h][2] = a.z; fcur[h][3] = a.w;
           fcur[h][4] = b.x; fcur[h][5] = b.y; fcur[h][6] = b.z; fcur[h][7] = b.w;
@@ -445,8 +448,8 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           if (MSK) {
             const int more = pid[h] >= 0 && (i + 2) <= Lq[h];
             const int16_t* src = fp[h] - (size_t)((uint32_t)(s + 2) * (uint32_t)nl * 16u);
-            cp_async16(fst[h] + 32 * ((i + 2) % 3), src, more);
-            cp_async16(fst[h] + 32 * ((i + 2) % 3) + 16, src + nl * 8, more);
+            cp_async16(fst[h] + fnxt_off, src, more);
+            cp_async16(fst[h] + fnxt_off + 16, src + nl * 8, more);
             // two rows (~700 cycles) do not cover a DRAM round trip under load: pull the chunk of row
             // i+kFwdAhead into L2 now, so that the cp.async issued for it later is an L2 hit
             const int far = pid[h] >= 0 && (i + kFwdAhead) <= Lq[h];
@@ -531,7 +534,11 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           oB[c >> 1] = prmt(Mv[c - 1], M, 0x7632u);
         }
       }
-      if (MSK) accM &= VM;
+      if (MSK) {
+        accM &= VM;
+        fnxt_off = fcur_off;
+        fcur_off = fcur_off == 64 ? 0 : fcur_off + 32;
+      }
       xl_hold = xn;
       x_pub = Xp[15];
       e_pub = E;
