@@ -140,7 +140,7 @@ struct aadp_ctx {
   std::vector<SchedScratch> sched;
   std::vector<int32_t> Lq32, Lt32;
   int64_t wave_min_cells = 4000000;  // pairs at least this large use the multi-CTA wavefront
-  DevBuf wave_bb, wave_ready, wave_part;
+  DevBuf wave_bb, wave_ready, wave_part, wave_dbg;
   unsigned int wave_tag = 0;
   DevBuf x_layout, x_qc, x_qid, x_tid, x_scores;
   // exact general-gap fp32 path (aadp_general.cuh): scoring that is not on a dyadic grid, or forced
@@ -784,11 +784,28 @@ int run_wave_pairs(aadp_ctx* c, uint32_t what) {
       Q.wave_nstripes = nst;
       Q.wave_ll = c->wave_bb.as<unsigned long long>() + (size_t)k * nst * bb_rows * 3;
       Q.wave_tag = c->wave_tag;
+      Q.wave_dbg = nullptr;
+      if (getenv("AADP_WAVE_DEBUG")) {
+        if (c->wave_dbg.reserve((size_t)2 * nst * 2 * sizeof(long long))) return 1;
+        Q.wave_dbg = c->wave_dbg.as<long long>() + (size_t)k * nst * 2;
+      }
       Q.wave_ready = c->wave_ready.as<int>() + (size_t)k * nst;
       Q.wave_part = c->wave_part.as<int4>() + (size_t)k * nst;
     }
     if (nd == 1) P[1] = P[0];
     if (launch_wave(c, P[0], P[1], nd, nst, tbm, stm)) return 1;
+    if (getenv("AADP_WAVE_DEBUG")) {  // per-stripe wait / total cycles of the launch (diagnostics)
+      std::vector<long long> h((size_t)nd * nst * 2);
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaMemcpy(h.data(), c->wave_dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < nd; ++k) {
+        fprintf(stderr, "[aadp] wave dir %d: stripe wait%%:", dirs[k]);
+        for (int st = 0; st < nst; st += std::max(1, nst / 24))
+          fprintf(stderr, " %d:%.0f/%.2fms", st, 100.0 * (double)h[((size_t)k * nst + st) * 2] / (double)std::max<long long>(1, h[((size_t)k * nst + st) * 2 + 1]),
+                  (double)h[((size_t)k * nst + st) * 2 + 1] / 1.965e6);
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return 0;
 }

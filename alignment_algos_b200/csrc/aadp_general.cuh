@@ -166,21 +166,34 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       const float simc = simov ? subrow[colof(b)] : subrow[(int)tseq[colof(b) - 1]];
       int oa = a - 1, ob = b - 1;
       float os = clampl(__fadd_rn(prow[b - 1], simc));
-      for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
-        float s = __fsub_rn(prow[k], pen[b - k - 1]);
-        s = clampl(__fadd_rn(s, simc));
-        if (s > os) { ob = k; os = s; }
+      if (TBM) {
+        for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
+          float s = __fsub_rn(prow[k], pen[b - k - 1]);
+          s = clampl(__fadd_rn(s, simc));
+          if (s > os) { ob = k; os = s; }
+        }
+      } else {
+        // score only: the strict-'>' scan and a running maximum give the same value; the clamp commutes with max
+#pragma unroll 4
+        for (int k = 1; k < b - 1; ++k) os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], pen[b - k - 1]), simc));
       }
       bool col = false;
       int ka = 0;
       const float* colp = D + at(1, b - 1);
       const int64_t cstride = rev ? -(int64_t)sz2 : (int64_t)sz2;
-      for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
-        float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]);
-        s = clampl(__fadd_rn(s, simc));
-        if (s > os) { col = true; ka = k; os = s; }
+      if (TBM) {
+        for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
+          float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]);
+          s = clampl(__fadd_rn(s, simc));
+          if (s > os) { col = true; ka = k; os = s; }
+        }
+        if (col) { oa = ka; ob = b - 1; }
+      } else {
+#pragma unroll 4
+        for (int k = 1; k < a - 1; ++k)
+          os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc));
+        os = clampl(os);
       }
-      if (col) { oa = ka; ob = b - 1; }
       set_tb(a, b, oa, ob, os);
     }
     __syncthreads();  // every thread is done reading the previous row

@@ -87,6 +87,7 @@ struct FillParams {
   unsigned int wave_tag;     // tag of this launch (the buffer is zeroed when allocated, tags never repeat)
   int* wave_ready;           // [stripe] Lq+1 once the stripe is completely done (final-cell partials chain)
   int4* wave_part;           // [stripe] final-row partials (rb_val, rb_k, diag, col)
+  long long* wave_dbg;       // optional [stripe][2]: cycles spent waiting for the left neighbour, total cycles
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -241,6 +242,8 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
     if (lane == 0) a_nxt = qring[0];
 
     const int nsteps = Lq + n_act - 1;
+    long long dbg_wait = 0;
+    const long long dbg_t0 = (WAVE && P.wave_dbg) ? clock64() : 0;
     for (int s = 0; s < nsteps; ++s) {
       if (s >= H + 32 && ((s - 32) & (H - 1)) == 0) {  // refill: block b = (s-32)/H + 1
         const int r0 = ((s - 32) / H + 1) * H;
@@ -268,6 +271,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
           // words carry this launch's tag (they are published row by row, in order), then stages it
           const int r = i0 + lane;
           unsigned long long w0 = 0, w1 = 0, w2 = 0;
+          const long long t_w0 = P.wave_dbg ? clock64() : 0;
           for (;;) {
             bool ok = true;
             if (r <= Lq) {
@@ -279,6 +283,7 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(32);
           }
+          if (P.wave_dbg) dbg_wait += clock64() - t_w0;
           wblk[lane] = make_int4((int)(unsigned int)w0, (int)(unsigned int)w1, (int)(unsigned int)w2, 0);
           __syncwarp();
         }
@@ -389,6 +394,10 @@ __device__ __forceinline__ void fill_pair_warp(const FillParams& P, int pair, in
       }
     }
 
+    if (WAVE && P.wave_dbg && lane == 0) {
+      P.wave_dbg[2 * st] = dbg_wait;
+      P.wave_dbg[2 * st + 1] = clock64() - dbg_t0;
+    }
     // ---- after the last row: contributions of this stripe's columns to the final cell
     // (dpmatrix.h:504-534).  Mg[c] + gi = M(Lq, j).
 #pragma unroll

@@ -53,6 +53,12 @@ def triangle_rects(nseq, block=1000, sub=250):
     return rects
 
 
+def choose_block(nseq, world):
+    """Block edge for triangle_rects: large enough that a rectangle is a full launch (>= 250 sequences per
+    side), small enough that every rank gets a few dozen rectangles to balance (about 6*world blocks per side)."""
+    return int(min(1000, max(250, nseq // (6 * max(world, 1)) or 1)))
+
+
 def rect_is_diagonal(r):
     return r[0] == r[2] and r[1] == r[3]
 

@@ -191,7 +191,8 @@ def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_rank
     seqs = synth.random_seqs(rng, args.seqs, 100, 500)
     lens = np.array([len(x) for x in seqs], np.int64)
     res, off = a.Context.pack(seqs)
-    rects = shard.shard_rects(shard.triangle_rects(args.seqs), lens, world)[rank]
+    blk = shard.choose_block(args.seqs, world)
+    rects = shard.shard_rects(shard.triangle_rects(args.seqs, blk, max(blk // 4, 1)), lens, world)[rank]
     # useful work of the whole job: sum over i<j of Li*Lj
     tot = float(lens.sum())
     useful_cu = (tot * tot - float((lens.astype(np.float64) ** 2).sum())) / 2.0
@@ -275,7 +276,7 @@ def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_rank
     line = {
         "metric": "GCUPS forward score-only DP fill, all-vs-all", "value": value, "unit": "GCUPS", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
         "config": {"workload": "c4: all-vs-all of %d synthetic sequences (%d pairs i<j), L in [100,500], BLOSUM62 gi=12 ge=1 "
                                "semi_local, forward score-only, cross-mode packed kernel" % (args.seqs, n_pairs_job),
                    "rectangles_this_rank": len(rects), "cache": "each launch streams its own sequences; scores are written once",
@@ -490,7 +491,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic",
+        "dtype": "int32" if args.workload == "c5" else "i16", "data": "synthetic",
         "config": {"workload": wl_desc,
                    "pairs_per_gpu": n, "cache": "outputs (%.1f GB/step) exceed L2; no flush needed" % (
                        (ctx.resident_bytes(a.W_TB) + ctx.resident_bytes(a.W_SCORES) + ctx.resident_bytes(a.W_MASK)) / 1e9),
