@@ -17,6 +17,7 @@
 #include "alignment.h"
 #include "dpmatrix.h"
 #include "optimal.h"
+#include "optimal_subali.h"
 #include "submatrix.h"
 #ifdef AADP_HMAP2_DPMATRIX_H
 #include "optimal_rev.h"  // abstract (un-instantiable) in the reference: optimal_rev.h:29-30
@@ -66,6 +67,13 @@ int main(int argc, char** argv) {
     if (query.size() > 9 && templ.size() > 9) {
       Matrix sub(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, fwd, params.align_type);
       dump("S", sub);
+      // ... and the optimal alignment through that region (optimal_subali.h; used together in ssss.h:621-633)
+      Optimal_Subali<AASequence, AASequence, AAEval> osub(2, 3, (int)query.size() - 3, (int)templ.size() - 2);
+      AlignmentSet<AASequence, AASequence, AAEval> subali(sub, osub);
+      std::printf("SUBOPT score %.6g pairs", subali[0].score);
+      for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = subali[0].begin(); it != subali[0].end(); ++it)
+        std::printf(" %d:%d", it->query_idx(), it->template_idx());
+      std::printf("\n");
       Matrix subr(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, rev, params.align_type);
       dump("T", subr);
     }
