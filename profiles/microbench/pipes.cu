@@ -13,9 +13,11 @@ __device__ __forceinline__ uint32_t hset(uint32_t a, uint32_t b) { return __hgt2
 __device__ __forceinline__ uint32_t hsetbf(uint32_t a, uint32_t b) { __half2 r = __hgt2(*(__half2*)&a, *(__half2*)&b); return *(uint32_t*)&r; }
 __device__ __forceinline__ uint32_t hfma(uint32_t a, uint32_t b, uint32_t c) { __half2 r = __hfma2(*(__half2*)&a, *(__half2*)&b, *(__half2*)&c); return *(uint32_t*)&r; }
 
-enum { OP_VIMNMX, OP_VIADDMNMX, OP_VIADD16, OP_PRMT, OP_LOP3, OP_IMAD, OP_HSET, OP_HSETBF, OP_HFMA, OP_IADD, OP_VIMNMX3, OP_NONE };
+enum { OP_HMNMX, OP_HADD, OP_VIMNMX, OP_VIADDMNMX, OP_VIADD16, OP_PRMT, OP_LOP3, OP_IMAD, OP_HSET, OP_HSETBF, OP_HFMA, OP_IADD, OP_VIMNMX3, OP_NONE };
 template <int OP>
 __device__ __forceinline__ uint32_t op(uint32_t x, uint32_t y, uint32_t z) {
+  if (OP == OP_HMNMX) { __half2 r = __hmax2(*(__half2*)&x, *(__half2*)&y); return *(uint32_t*)&r; }
+  if (OP == OP_HADD) { __half2 r = __hsub2(*(__half2*)&x, *(__half2*)&y); return *(uint32_t*)&r; }
   if (OP == OP_VIMNMX) return __vmaxs2(x, y);
   if (OP == OP_VIADDMNMX) return __viaddmax_s16x2(x, y, z);
   if (OP == OP_VIADD16) return __vadd2(x, y);
@@ -121,6 +123,7 @@ int main() {
   cudaMalloc(&d_cyc, 148 * 8);
 #define ONE(X) run<X, OP_NONE>(#X, d_out, d_cyc)
 #define TWO(X, Y) run<X, Y>(#X " + " #Y, d_out, d_cyc)
+  ONE(OP_HMNMX); ONE(OP_HADD); TWO(OP_HMNMX, OP_VIMNMX); TWO(OP_HMNMX, OP_PRMT); TWO(OP_HMNMX, OP_HADD); TWO(OP_HMNMX, OP_IMAD); TWO(OP_HMNMX, OP_LOP3); TWO(OP_HADD, OP_IMAD); TWO(OP_HADD, OP_VIMNMX);
   ONE(OP_VIMNMX); ONE(OP_VIADDMNMX); ONE(OP_VIMNMX3); ONE(OP_VIADD16); ONE(OP_PRMT); ONE(OP_LOP3); ONE(OP_IADD); ONE(OP_IMAD); ONE(OP_HSET); ONE(OP_HSETBF); ONE(OP_HFMA);
   TWO(OP_VIMNMX, OP_LOP3); TWO(OP_VIMNMX, OP_PRMT); TWO(OP_VIMNMX, OP_VIADD16); TWO(OP_VIMNMX, OP_IMAD); TWO(OP_VIMNMX, OP_HSET); TWO(OP_VIMNMX, OP_HSETBF);
   TWO(OP_VIMNMX, OP_HFMA); TWO(OP_IMAD, OP_HSET); TWO(OP_IMAD, OP_HFMA); TWO(OP_HSET, OP_HFMA); TWO(OP_LOP3, OP_HSET); TWO(OP_IMAD, OP_VIADD16); TWO(OP_LOP3, OP_IADD);
