@@ -1,7 +1,7 @@
-// hmap2/optimal_rev.h -- optimal traceback over a REVERSE matrix (reference optimal_rev.h:23-131).
-// In the reference this class cannot be instantiated: its enumerate(const DPMatrix&, ...) const does
-// not override Enumerator::enumerate(DPMatrix&, ...) (optimal_rev.h:29-30 vs enumerator.h:23-24).
-// Here the override has the base signature, so the class works as it was evidently meant to.
+// hmap2/optimal_rev.h -- the optimal alignment of a REVERSE matrix (replaces reference optimal_rev.h:23-131).
+// In the reference this class cannot be instantiated: its enumerate(const DPMatrix&, ...) const does not override
+// Enumerator::enumerate(DPMatrix&, ...) (optimal_rev.h:29-30 vs enumerator.h:23-24).  Here the override has the
+// base signature, so the class works as it was evidently meant to.  Reverse alignments grow at the back.
 #ifndef AADP_HMAP2_OPTIMAL_REV_H
 #define AADP_HMAP2_OPTIMAL_REV_H
 
@@ -18,61 +18,45 @@ class Optimal_Rev : public Enumerator<S1, S2, Etype> {
   int estimateSize() const { return 1; }
 
   void enumerate(DPMatrix<S1, S2, Etype>& dpm, AlignmentSet<S1, S2, Etype>& as) {
-    if (islocal) {
-      enumerate_local(dpm, as);
+    const size_t slot = as.size();
+    as.resize(slot + 1);
+    AlignedPairList<S1, S2>& ali = as[slot];
+    const int q_end = dpm.getQuerySize() - 1, t_end = dpm.getTemplateSize() - 1;
+    aadp::CellPath cells;
+    ali.append(0, 0);
+    if (!islocal) {
+      // optimal_rev.h:57-76: from the Head/Head cell forward to the Tail/Tail anchor.  dpmatrix.h:868 can point the
+      // walk at a cell that was never filled (the reference then loops); follow_predecessors stops there.
+      ali.score = dpm.getCell(0, 0)->score;
+      const aadp::WalkEnd end = aadp::follow_predecessors(dpm, 0, 0, q_end, true, false, &cells);
+      for (size_t k = 0; k < cells.size(); ++k) ali.append(cells[k].first, cells[k].second);
+      if (end.q != q_end || end.t != t_end) throw std::string("Illegal alignment start pair");
       return;
     }
-    const size_t k = as.size();
-    as.resize(k + 1);
-    const int q_last = dpm.getQuerySize() - 1, t_last = dpm.getTemplateSize() - 1;
+    // optimal_rev.h:84-110
     int q = 0, t = 0;
-    as[k].score = dpm.getCell(0, 0)->score;
-    as[k].append(0, 0);
-    int guard = 0;
-    while (q < q_last) {  // optimal_rev.h:68-73
-      const DPCell* c = dpm.getCell(q, t);
-      q = c->prev_query_idx;
-      t = c->prev_template_idx;
-      as[k].append(q, t);
-      // dpmatrix.h:868 can point the walk at a cell that was never filled; the reference then loops
-      if (q < 0 || t < 0 || ++guard > q_last + t_last + 4) break;
-    }
-    if (q != q_last || t != t_last) throw std::string("Illegal alignment start pair");  // optimal_rev.h:76
+    float best = 0.f;
+    find_max(dpm, &q, &t, &best);
+    ali.score = best;
+    ali.append(q, t);
+    const aadp::WalkEnd end = aadp::follow_predecessors(dpm, q, t, q_end, true, true, &cells);
+    for (size_t k = 0; k < cells.size(); ++k) ali.append(cells[k].first, cells[k].second);
+    if (end.q != q_end && end.t != t_end) ali.append(q_end, t_end);
   }
 
-  void enumerate_local(DPMatrix<S1, S2, Etype>& dpm, AlignmentSet<S1, S2, Etype>& as) {
-    const size_t k = as.size();
-    as.resize(k + 1);
-    const int q_last = dpm.getQuerySize() - 1, t_last = dpm.getTemplateSize() - 1;
-    int q = 0, t = 0;
-    float s = 0.f;
-    as[k].append(0, 0);
-    find_max(dpm, &q, &t, &s);
-    as[k].score = s;
-    as[k].append(q, t);
-    while (q < q_last) {  // optimal_rev.h:102-108
-      const DPCell* c = dpm.getCell(q, t);
-      q = c->prev_query_idx;
-      t = c->prev_template_idx;
-      if (q < 0 || t < 0) break;
-      if (dpm.getCell(q, t)->score <= 0.f) break;
-      as[k].append(q, t);
-    }
-    if (q != q_last && t != t_last) as[k].append(q_last, t_last);
-  }
-
-  // first maximum scanning from the bottom-right corner (optimal_rev.h:114-131)
+  // optimal_rev.h:114-131: first maximum scanning backwards from the bottom-right corner over rows/columns > 0,
+  // seeded with the Head/Head cell
   void find_max(const DPMatrix<S1, S2, Etype>& dpm, int* q, int* t, float* s) const {
-    *q = 0;
-    *t = 0;
-    *s = dpm.getCell(0, 0)->score;
+    int bq = 0, bt = 0;
+    float bs = dpm.getCell(0, 0)->score;
     for (int i = dpm.getQuerySize() - 1; i > 0; --i)
-      for (int j = dpm.getTemplateSize() - 1; j > 0; --j)
-        if (*s < dpm.getCell(i, j)->score) {
-          *q = i;
-          *t = j;
-          *s = dpm.getCell(i, j)->score;
-        }
+      for (int j = dpm.getTemplateSize() - 1; j > 0; --j) {
+        const float v = dpm.getCell(i, j)->score;
+        if (bs < v) { bs = v; bq = i; bt = j; }
+      }
+    *q = bq;
+    *t = bt;
+    *s = bs;
   }
 
  private:
