@@ -87,6 +87,10 @@ struct Batch {
   std::vector<int32_t> aoff;      // per sequence byte offset into the aligned arenas
   double packed_cells = 0;
   int64_t n_tasks = 0;
+  // the packed task list may be built (and launched) in several chunks of consecutive pair ids, so that the
+  // kernels of chunk k run while the host schedules chunk k+1 (aadp_fill_batch)
+  std::vector<int64_t> chunk_first, chunk_ntasks;
+  std::vector<double> chunk_cells;
   double cells = 0;
   uint32_t uploaded_what = 0;
   uint32_t ran_what = 0;
@@ -136,6 +140,7 @@ struct aadp_ctx {
   bool allow_packed = true;
   bool allow_wave = true;
   int host_threads = 0;  // 0 = min(hardware threads, 8)
+  int pipeline_chunks = 2;  // aadp_fill_batch: task-list chunks whose scheduling overlaps the previous chunk's kernel
   HostPool pool;
   std::vector<SchedScratch> sched;
   std::vector<int32_t> Lq32, Lt32;
@@ -155,6 +160,7 @@ struct aadp_ctx {
   uint8_t* pin = nullptr;
   size_t pin_cap = 0, pin_used = 0;
   int* pin_flag = nullptr;
+  cudaEvent_t ev_flag = nullptr;  // recorded after the residue validation flag has been copied back
   Batch b;
   int64_t launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last upload / fill call
@@ -235,8 +241,8 @@ __global__ void arena_kernel(const uint8_t* __restrict__ res, const int64_t* __r
     const int L = (int)(seq_off[sq + 1] - o);
     const int64_t d = aoff[sq];
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
-      const uint8_t v = res[o + i];
-      if (v >= A) *bad = 1;
+      uint8_t v = res[o + i];
+      if (v >= A) { *bad = 1; v = 0; }  // reported as an error by the host; kernels already in flight stay in bounds
       af[d + i] = v;
       ar[d + L - 1 - i] = v;
     }
@@ -473,8 +479,8 @@ void build_tasks_range(const Batch& b, const int32_t* Lq32, const int32_t* Lt32,
 // Classifies every pair (packed / int32 / wavefront), sizes its resident products and builds the packed
 // task list.  All O(npairs) passes run on `host_threads` threads over disjoint pair ranges; the per-range
 // task lists (each longest first) are interleaved round-robin so the global order stays longest first.
-// The interleaved task list is assembled directly in the pinned staging pool (*tasks_pinned).
-int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
+// (build_task_chunk builds the packed task list, per chunk of consecutive pair ids.)
+int build_batch_meta(aadp_ctx* c, uint32_t what) {
   Batch& b = c->b;
   const int64_t np = b.npairs;
   b.tb_off.resize(np + 1);
@@ -490,7 +496,9 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
   b.wave_pairs.clear();
   b.packed_cells = 0;
   b.n_tasks = 0;
-  *tasks_pinned = nullptr;
+  b.chunk_first.clear();
+  b.chunk_ntasks.clear();
+  b.chunk_cells.clear();
   int T = c->host_threads;
   if (T <= 0) T = (int)std::min<unsigned>(std::max<unsigned>(std::thread::hardware_concurrency(), 1u), 8u);
   T = (int)std::max<int64_t>(1, std::min<int64_t>(T, np / 4096));
@@ -584,25 +592,11 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
       b.mask_off[(size_t)p + 1] = s2;
     }
     part[(size_t)t].sum[0] = s0; part[(size_t)t].sum[1] = s1; part[(size_t)t].sum[2] = s2;
-    build_tasks_range(b, Lq32, Lt32, lo, hi, c->sched[(size_t)t]);
   });
-  // ---- range bases, then: add them to the offsets and interleave the per-range task lists round-robin
-  // (task i of range t goes right after task i of range t-1)
-  std::vector<int64_t> base((size_t)T * 3 + 3, 0), nt((size_t)T);
-  int64_t total = 0;
-  for (int t = 0; t < T; ++t) {
+  // ---- range bases, added to the range-local sums
+  std::vector<int64_t> base((size_t)T * 3 + 3, 0);
+  for (int t = 0; t < T; ++t)
     for (int k = 0; k < 3; ++k) base[(size_t)(t + 1) * 3 + k] = base[(size_t)t * 3 + k] + part[(size_t)t].sum[k];
-    nt[(size_t)t] = (int64_t)c->sched[(size_t)t].tasks.size() / 64;
-    total += nt[(size_t)t];
-  }
-  b.n_tasks = total;
-  {
-    const size_t at = (c->pin_used + 63) / 64 * 64, bytes = (size_t)total * 64 * sizeof(int32_t);
-    if (at + bytes > c->pin_cap) return fail("internal: pinned staging pool too small");
-    *tasks_pinned = reinterpret_cast<int32_t*>(c->pin + at);
-    c->pin_used = at + bytes;
-  }
-  int32_t* const tdst = *tasks_pinned;
   c->pool.run(T, [&](int t) {
     int64_t lo, hi;
     range(t, &lo, &hi);
@@ -613,6 +607,40 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
         b.sc_off[(size_t)p + 1] += b1;
         b.mask_off[(size_t)p + 1] += b2;
       }
+  });
+  for (int k = 0; k < 2; ++k)
+    std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) {
+      return (int64_t)Lq32[x] * Lt32[x] > (int64_t)Lq32[y] * Lt32[y];
+    });
+  return 0;
+}
+
+// Packed task list of the pairs [lo,hi): scheduled on the host threads over sub-ranges, the per-range lists (each
+// longest first) interleaved round-robin (task i of range t right after task i of range t-1) directly into the
+// pinned staging pool.  Appends one chunk to the batch; *tasks_pinned / *ntasks describe it.
+int build_task_chunk(aadp_ctx* c, int64_t lo, int64_t hi, int32_t** tasks_pinned, int64_t* ntasks) {
+  Batch& b = c->b;
+  int T = c->host_threads;
+  if (T <= 0) T = (int)std::min<unsigned>(std::max<unsigned>(std::thread::hardware_concurrency(), 1u), 8u);
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(T, (hi - lo) / 4096));
+  if ((int)c->sched.size() < T) c->sched.resize((size_t)T);
+  const int32_t* Lq32 = c->Lq32.data();
+  const int32_t* Lt32 = c->Lt32.data();
+  c->pool.run(T, [&](int t) {
+    const int64_t l2 = lo + (hi - lo) * t / T, h2 = lo + (hi - lo) * (t + 1) / T;
+    build_tasks_range(b, Lq32, Lt32, l2, h2, c->sched[(size_t)t]);
+  });
+  std::vector<int64_t> nt((size_t)T);
+  int64_t total = 0;
+  for (int t = 0; t < T; ++t) {
+    nt[(size_t)t] = (int64_t)c->sched[(size_t)t].tasks.size() / 64;
+    total += nt[(size_t)t];
+  }
+  const size_t at = (c->pin_used + 63) / 64 * 64, bytes = (size_t)total * 64 * sizeof(int32_t);
+  if (at + bytes > c->pin_cap) return fail("internal: pinned staging pool too small");
+  int32_t* const tdst = reinterpret_cast<int32_t*>(c->pin + at);
+  c->pin_used = at + bytes;
+  c->pool.run(T, [&](int t) {
     const std::vector<int32_t>& src = c->sched[(size_t)t].tasks;
     for (int64_t i = 0; i < nt[(size_t)t]; ++i) {
       int64_t pos = 0;
@@ -620,10 +648,15 @@ int build_batch_meta(aadp_ctx* c, uint32_t what, int32_t** tasks_pinned) {
       memcpy(tdst + pos * 64, &src[(size_t)i * 64], 64 * sizeof(int32_t));
     }
   });
-  for (int k = 0; k < 2; ++k)
-    std::stable_sort(b.order[k].begin(), b.order[k].end(), [&](int32_t x, int32_t y) {
-      return (int64_t)Lq32[x] * Lt32[x] > (int64_t)Lq32[y] * Lt32[y];
-    });
+  double cells = 0;
+  for (int64_t p = lo; p < hi; ++p)
+    if (b.fmt[(size_t)p] == 1) cells += (double)Lq32[p] * (double)Lt32[p];
+  b.chunk_first.push_back(b.n_tasks);
+  b.chunk_ntasks.push_back(total);
+  b.chunk_cells.push_back(cells);
+  b.n_tasks += total;
+  *tasks_pinned = tdst;
+  *ntasks = total;
   return 0;
 }
 
@@ -654,11 +687,10 @@ int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v) {
   return 0;
 }
 
-int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float delta_ratio, float* d_threshold,
-                  int64_t* d_count) {
+// Device buffers of one direction (sizes are known once build_batch_meta has run).
+int reserve_direction(aadp_ctx* c, int dir, uint32_t what) {
   Batch& b = c->b;
   const int tbm = (what & AADP_W_TB) ? 1 : 0;
-  const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
   const int64_t np = b.npairs;
   const bool have_v1 = !b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty();
   // the packed reverse pass fuses the mask and needs no reverse score matrix of its own
@@ -668,8 +700,17 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
   if (c->fin_k[dir].reserve(std::max<size_t>(np * 4, 16))) return 1;
   if (tbm && c->tb[dir].reserve(std::max<size_t>((size_t)b.tb_off[np], 16))) return 1;
   if (need_blob && c->scb[dir].reserve(std::max<size_t>((size_t)b.sc_off[np] * 2, 16))) return 1;
-  if (c->counter.reserve(64)) return 1;
-  if (b.n_tasks) {
+  return 0;
+}
+
+// Packed kernel of one direction over the tasks of one chunk.
+int launch_packed_chunk(aadp_ctx* c, int dir, uint32_t what, float delta_ratio, float* d_threshold, int64_t* d_count,
+                        size_t chunk) {
+  Batch& b = c->b;
+  const int tbm = (what & AADP_W_TB) ? 1 : 0;
+  if (chunk >= b.chunk_ntasks.size() || b.chunk_ntasks[chunk] == 0) return 0;
+  if (chunk >= 8) return fail("internal: too many task chunks");
+  {
     PackedParams Q{};
     Q.sc = c->sc;
     Q.sub8 = c->sub8.as<int8_t>();
@@ -679,10 +720,10 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
     Q.seq_off = c->seq_off.as<int64_t>();
     Q.pair_q = c->pair_q.as<int32_t>();
     Q.pair_t = c->pair_t.as<int32_t>();
-    Q.tasks = c->tasks.as<int32_t>();
-    Q.n_tasks = (int)b.n_tasks;
+    Q.tasks = c->tasks.as<int32_t>() + b.chunk_first[chunk] * 64;
+    Q.n_tasks = (int)b.chunk_ntasks[chunk];
     Q.rev = dir;
-    Q.counter = c->counter.as<unsigned int>() + (4 + dir);
+    Q.counter = c->counter.as<unsigned int>() + (16 + 8 * dir + (int)chunk);
     Q.tb = tbm ? c->tb[dir].as<uint8_t>() : nullptr;
     Q.tb_off = c->tb_off.as<int64_t>();
     const int msk = (dir == 1 && (what & AADP_W_MASK)) ? 1 : 0;
@@ -699,9 +740,17 @@ int run_direction(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what, float del
     Q.fin_score = c->fin_score[dir].as<int32_t>();
     Q.fin_kind = c->fin_kind[dir].as<int32_t>();
     Q.fin_k = c->fin_k[dir].as<int32_t>();
-    Q.cells_hint = b.packed_cells;
+    Q.cells_hint = b.chunk_cells[chunk];
     if (launch_packed(c, Q, tbm, fst, msk)) return 1;
   }
+  return 0;
+}
+
+// The int32 kernels of one direction (pairs that do not qualify for the packed path).
+int run_direction_int32(aadp_ctx* c, int dir /*0 fwd,1 rev*/, uint32_t what) {
+  Batch& b = c->b;
+  const int tbm = (what & AADP_W_TB) ? 1 : 0;
+  const int stm = (what & (AADP_W_SCORES | AADP_W_MASK)) ? b.st_mode : 0;
   for (int k = 0; k < 2; ++k) {
     if (b.order[k].empty()) continue;
     FillParams P{};
@@ -930,6 +979,7 @@ aadp_ctx* aadp_create(int device) {
   }
   c->stream = c->own_stream;
   if (const char* e = getenv("AADP_HOST_THREADS")) c->host_threads = atoi(e);
+  if (const char* e = getenv("AADP_PIPELINE_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(e), 8));
   return c;
 }
 
@@ -948,6 +998,7 @@ void aadp_destroy(aadp_ctx* c) {
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
+  if (c->ev_flag) cudaEventDestroy(c->ev_flag);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -967,6 +1018,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "wave")) { c->allow_wave = value != 0; return 0; }
   if (!strcmp(key, "wave_min_cells")) { c->wave_min_cells = value; return 0; }
   if (!strcmp(key, "host_threads")) { c->host_threads = value; return 0; }
+  if (!strcmp(key, "pipeline_chunks")) { c->pipeline_chunks = std::max(1, std::min(value, 8)); return 0; }
   // exact_float = 1: route everything through the exact general-gap fp32 kernel (takes effect at the next
   // aadp_set_scoring); scoring that is not on a dyadic grid always uses it
   if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
@@ -1087,14 +1139,20 @@ static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (!c->ev_flag) CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->ev_flag, c->stream));
   b.have_seqs = true;
   return 0;
 }
 
 static size_t pairs_pin_bytes(int64_t npairs) { return (size_t)npairs * (8 + 1 + 4 + 24 + 64 * 4 / 2 + 64) + 65536; }
 
-// pair list -> classification, product sizes, packed task list, and their uploads
-static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what) {
+// pair list -> classification, product sizes, packed task list, and their uploads.  With nsplit > 1 the task
+// list is built in chunks of consecutive pair ids and on_chunk(k) runs right after chunk k is enqueued for
+// upload -- aadp_fill_batch launches the forward kernel of chunk k there, so the GPU works on it while the host
+// schedules chunk k+1.
+static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what,
+                          int nsplit = 1, const std::function<int(size_t)>* on_chunk = nullptr) {
   Batch& b = c->b;
   b.npairs = npairs;
   b.pair_q.assign(pair_q, pair_q + npairs);
@@ -1114,16 +1172,9 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
     if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
     return 0;
   }
-  int32_t* tasks_pinned = nullptr;
-  if (build_batch_meta(c, what, &tasks_pinned)) return 1;
+  if (build_batch_meta(c, what)) return 1;
   b.uploaded_what = what;
   b.ran_what = 0;
-  {  // the task list was assembled in the pinned pool already
-    const size_t bytes = (size_t)b.n_tasks * 64 * sizeof(int32_t);
-    if (c->tasks.reserve(std::max<size_t>(bytes, 16))) return 1;
-    if (bytes) CK(cudaMemcpyAsync(c->tasks.p, tasks_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
-    c->h2d_bytes += (int64_t)bytes;
-  }
   if (upload_vec(c, c->fmt, b.fmt)) return 1;
   if (upload_vec(c, c->pair_q, b.pair_q)) return 1;
   if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
@@ -1132,6 +1183,21 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
   if (upload_vec(c, c->tb_off, b.tb_off)) return 1;
   if (upload_vec(c, c->sc_off, b.sc_off)) return 1;
   if (upload_vec(c, c->mask_off, b.mask_off)) return 1;
+  // packed task list: at most one task per couple, one unpaired couple per lane width, host range and chunk
+  nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsplit, 8), npairs / 16384));
+  if (c->tasks.reserve(((size_t)npairs / 2 + (size_t)33 * 8 * nsplit + 64) * 64 * sizeof(int32_t))) return 1;
+  for (int k = 0; k < nsplit; ++k) {
+    // the first chunk is the smallest: its kernel should start as early as possible
+    const int64_t lo = k == 0 ? 0 : npairs * (2 * k - 1) / (2 * nsplit - 1), hi = npairs * (2 * k + 1) / (2 * nsplit - 1);
+    int32_t* tasks_pinned = nullptr;
+    int64_t nt = 0;
+    if (build_task_chunk(c, lo, std::min(hi, npairs), &tasks_pinned, &nt)) return 1;
+    const size_t bytes = (size_t)nt * 64 * sizeof(int32_t);
+    if (bytes)
+      CK(cudaMemcpyAsync(c->tasks.as<int32_t>() + b.chunk_first[(size_t)k] * 64, tasks_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (int64_t)bytes;
+    if (on_chunk && (*on_chunk)((size_t)k)) return 1;
+  }
   return 0;
 }
 
@@ -1509,26 +1575,34 @@ static int gg_fetch_pair(aadp_ctx* c, int64_t p, float* score_fwd, int32_t* prev
   return 0;
 }
 
-int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
-                   float* d_threshold, int64_t* d_nearopt_count) {
-  if (check_ctx(c, true)) return 1;
+}  // extern "C"
+
+// Buffers and work counters of a run (everything the first kernel launch needs).
+static int run_prepare(aadp_ctx* c, uint32_t what) {
   Batch& b = c->b;
-  if ((what & ~b.uploaded_what) & (AADP_W_TB | AADP_W_SCORES | AADP_W_MASK))
-    return fail("aadp_run_batch asks for products the batch was not uploaded for");
-  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
-    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
-  if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
   c->launches = 0;
+  if (c->counter.reserve(256)) return 1;
+  CK(cudaMemsetAsync(c->counter.p, 0, 256, c->stream));
+  if ((what & AADP_W_MASK) && c->mask.reserve(std::max<size_t>((size_t)b.mask_off[b.npairs] * 4, 16))) return 1;
+  if ((what & AADP_W_FWD) && reserve_direction(c, 0, what)) return 1;
+  if ((what & AADP_W_REV) && reserve_direction(c, 1, what)) return 1;
+  return 0;
+}
+
+// The launches of a run.  fwd_packed_done: run_prepare and the forward packed kernels of every chunk were already
+// issued (interleaved with the host scheduling, aadp_fill_batch).
+static int run_batch_impl(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
+                          float* d_threshold, int64_t* d_nearopt_count, bool fwd_packed_done) {
+  Batch& b = c->b;
   const int64_t np = b.npairs;
-  if (np == 0) { b.ran_what = what; return 0; }
-  if (c->float_mode) return gg_run_batch(c, what, delta_ratio, d_fwd_score, d_rev_score, d_threshold, d_nearopt_count);
-  if (c->counter.reserve(64)) return 1;
-  CK(cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
+  if (!fwd_packed_done && run_prepare(c, what)) return 1;
   const int threads = 256;
   const int g1 = (int)std::min<int64_t>((np + threads - 1) / threads, 148 * 8);
-  if ((what & AADP_W_MASK) && c->mask.reserve(std::max<size_t>((size_t)b.mask_off[np] * 4, 16))) return 1;
   if (what & AADP_W_FWD) {
-    if (run_direction(c, 0, what, delta_ratio, d_threshold, d_nearopt_count)) return 1;
+    if (!fwd_packed_done)
+      for (size_t k = 0; k < b.chunk_ntasks.size(); ++k)
+        if (launch_packed_chunk(c, 0, what, delta_ratio, d_threshold, d_nearopt_count, k)) return 1;
+    if (run_direction_int32(c, 0, what)) return 1;
     if (d_fwd_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[0].as<int32_t>(), d_fwd_score, np, c->sc.scale_log2);
       CK(cudaGetLastError());
@@ -1536,7 +1610,9 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
     }
   }
   if (what & AADP_W_REV) {
-    if (run_direction(c, 1, what, delta_ratio, d_threshold, d_nearopt_count)) return 1;
+    for (size_t k = 0; k < b.chunk_ntasks.size(); ++k)
+      if (launch_packed_chunk(c, 1, what, delta_ratio, d_threshold, d_nearopt_count, k)) return 1;
+    if (run_direction_int32(c, 1, what)) return 1;
     if (d_rev_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[1].as<int32_t>(), d_rev_score, np, c->sc.scale_log2);
       CK(cudaGetLastError());
@@ -1599,10 +1675,32 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
   return 0;
 }
 
+extern "C" {
+
+int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_score, float* d_rev_score,
+                   float* d_threshold, int64_t* d_nearopt_count) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if ((what & ~b.uploaded_what) & (AADP_W_TB | AADP_W_SCORES | AADP_W_MASK))
+    return fail("aadp_run_batch asks for products the batch was not uploaded for");
+  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
+    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
+  c->launches = 0;
+  if (b.npairs == 0) { b.ran_what = what; return 0; }
+  if (c->float_mode) return gg_run_batch(c, what, delta_ratio, d_fwd_score, d_rev_score, d_threshold, d_nearopt_count);
+  return run_batch_impl(c, what, delta_ratio, d_fwd_score, d_rev_score, d_threshold, d_nearopt_count, false);
+}
+
 int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
                     const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
                     float* rev_score, float* threshold, int64_t* nearopt_count) {
-  if (aadp_upload_batch(c, residues, seq_off, nseq, pair_q, pair_t, npairs, what)) return 1;
+  if (check_ctx(c, true)) return 1;
+  if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
+  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
+    return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
+  if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
   const size_t nb = std::max<size_t>((size_t)npairs * 4, 16);
   float *df = nullptr, *dr = nullptr, *dt = nullptr;
   int64_t* dc = nullptr;
@@ -1610,7 +1708,33 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
   if (rev_score) { if (c->fscore[1].reserve(nb)) return 1; dr = c->fscore[1].as<float>(); }
   if (threshold) { if (c->thr.reserve(nb)) return 1; dt = c->thr.as<float>(); }
   if (nearopt_count) { if (c->count.reserve(nb * 2)) return 1; dc = c->count.as<int64_t>(); }
-  if (aadp_run_batch(c, what, delta_ratio, df, dr, dt, dc)) return 1;
+  Batch& b = c->b;
+  // Large batches are pipelined: the packed task list is built in chunks and the forward kernel of a chunk is
+  // launched as soon as its tasks are on their way, so the GPU computes while the host schedules the next chunk.
+  const bool pipelined = !c->float_mode && npairs >= 32768 && (what & AADP_W_FWD) && c->pipeline_chunks > 1;
+  if (!pipelined) {
+    if (aadp_upload_batch(c, residues, seq_off, nseq, pair_q, pair_t, npairs, what)) return 1;
+    if (npairs && aadp_run_batch(c, what, delta_ratio, df, dr, dt, dc)) return 1;
+  } else {
+    if (pin_reserve(c, (size_t)(nseq + 1) * 12 + pairs_pin_bytes(npairs))) return 1;
+    c->h2d_bytes = 0;
+    c->d2h_bytes = 0;
+    if (upload_sequences_impl(c, residues, seq_off, nseq)) return 1;
+    const std::function<int(size_t)> on_chunk = [&](size_t k) -> int {
+      if (k == 0 && run_prepare(c, what)) return 1;
+      return launch_packed_chunk(c, 0, what, delta_ratio, dt, dc, k);
+    };
+    if (set_pairs_impl(c, pair_q, pair_t, npairs, what, c->pipeline_chunks, &on_chunk)) return 1;
+    // the residue validation flag came back long ago (it was queued right after the arena kernel); the int32 and
+    // wavefront kernels read the raw residues, so they are only launched on validated input
+    CK(cudaEventSynchronize(c->ev_flag));
+    if (*c->pin_flag) {
+      CK(cudaStreamSynchronize(c->stream));
+      b.have_seqs = false;
+      return fail("residue code outside the substitution alphabet");
+    }
+    if (run_batch_impl(c, what, delta_ratio, df, dr, dt, dc, true)) return 1;
+  }
   if (npairs) {
     if (fwd_score && (what & AADP_W_FWD)) { CK(cudaMemcpyAsync(fwd_score, df, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
     if (rev_score && (what & AADP_W_REV)) { CK(cudaMemcpyAsync(rev_score, dr, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
