@@ -91,6 +91,9 @@ struct Batch {
   // kernels of chunk k run while the host schedules chunk k+1 (aadp_fill_batch)
   std::vector<int64_t> chunk_first, chunk_ntasks;
   std::vector<double> chunk_cells;
+  std::vector<int64_t> chunk_max_seq;  // largest sequence id a chunk references
+  std::vector<int64_t> piece_end;      // residue pieces of a pipelined upload: first sequence id after piece j
+  size_t piece_waited = 0;             // pieces the compute stream already waits for
   double cells = 0;
   uint32_t uploaded_what = 0;
   uint32_t ran_what = 0;
@@ -161,6 +164,8 @@ struct aadp_ctx {
   size_t pin_cap = 0, pin_used = 0;
   int* pin_flag = nullptr;
   cudaEvent_t ev_flag = nullptr;  // recorded after the residue validation flag has been copied back
+  cudaStream_t copy_stream = nullptr;  // pipelined uploads (aadp_fill_batch)
+  cudaEvent_t ev_piece[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_start = nullptr;
   Batch b;
   int64_t launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last upload / fill call
@@ -234,9 +239,9 @@ int launch_fill_k(aadp_ctx* c, FillParams& P, int tbm, int stm) {
 // Builds the 16-byte aligned forward and reversed sequence arenas on the device and validates the
 // residue codes (submatrix.h:36-38 is undefined behaviour for letters outside the matrix).
 __global__ void arena_kernel(const uint8_t* __restrict__ res, const int64_t* __restrict__ seq_off,
-                             const int32_t* __restrict__ aoff, int64_t nseq, int A, uint8_t* __restrict__ af,
-                             uint8_t* __restrict__ ar, int* __restrict__ bad) {
-  for (int64_t sq = blockIdx.x; sq < nseq; sq += gridDim.x) {
+                             const int32_t* __restrict__ aoff, int64_t s_begin, int64_t nseq, int A,
+                             uint8_t* __restrict__ af, uint8_t* __restrict__ ar, int* __restrict__ bad) {
+  for (int64_t sq = s_begin + blockIdx.x; sq < nseq; sq += gridDim.x) {
     const int64_t o = seq_off[sq];
     const int L = (int)(seq_off[sq + 1] - o);
     const int64_t d = aoff[sq];
@@ -499,6 +504,7 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
   b.chunk_first.clear();
   b.chunk_ntasks.clear();
   b.chunk_cells.clear();
+  b.chunk_max_seq.clear();
   int T = c->host_threads;
   if (T <= 0) T = (int)std::min<unsigned>(std::max<unsigned>(std::thread::hardware_concurrency(), 1u), 8u);
   T = (int)std::max<int64_t>(1, std::min<int64_t>(T, np / 4096));
@@ -649,8 +655,12 @@ int build_task_chunk(aadp_ctx* c, int64_t lo, int64_t hi, int32_t** tasks_pinned
     }
   });
   double cells = 0;
-  for (int64_t p = lo; p < hi; ++p)
+  int64_t max_seq = 0;
+  for (int64_t p = lo; p < hi; ++p) {
     if (b.fmt[(size_t)p] == 1) cells += (double)Lq32[p] * (double)Lt32[p];
+    max_seq = std::max<int64_t>(max_seq, std::max(b.pair_q[(size_t)p], b.pair_t[(size_t)p]));
+  }
+  b.chunk_max_seq.push_back(max_seq);
   b.chunk_first.push_back(b.n_tasks);
   b.chunk_ntasks.push_back(total);
   b.chunk_cells.push_back(cells);
@@ -674,7 +684,7 @@ int pin_reserve(aadp_ctx* c, size_t bytes) {
 
 // copy a host vector into the pinned pool and start its (truly asynchronous) upload
 template <class T>
-int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v) {
+int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v, cudaStream_t stream = nullptr, bool use_stream = false) {
   const size_t bytes = v.size() * sizeof(T);
   if (d.reserve(std::max<size_t>(bytes, 16))) return 1;
   if (!bytes) return 0;
@@ -683,7 +693,7 @@ int upload_vec(aadp_ctx* c, DevBuf& d, const std::vector<T>& v) {
   memcpy(c->pin + at, v.data(), bytes);
   c->pin_used = at + bytes;
   c->h2d_bytes += (int64_t)bytes;
-  CK(cudaMemcpyAsync(d.p, c->pin + at, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.p, c->pin + at, bytes, cudaMemcpyHostToDevice, use_stream ? stream : c->stream));
   return 0;
 }
 
@@ -999,6 +1009,9 @@ void aadp_destroy(aadp_ctx* c) {
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
   if (c->ev_flag) cudaEventDestroy(c->ev_flag);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  for (int j = 0; j < 8; ++j) if (c->ev_piece[j]) cudaEventDestroy(c->ev_piece[j]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1104,7 +1117,10 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
 
 // ---- the two halves of an upload.  Both only ENQUEUE work on the context stream (the pinned pool must
 // have been reserved by the caller) and leave the synchronisation to the caller.
-static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq) {
+// npieces > 1 (aadp_fill_batch): the residues travel in pieces of consecutive sequences on a separate copy stream,
+// each followed by its part of the arena build and an event; the compute stream only waits for the piece a
+// chunk of pairs actually references, so the first kernels run while the rest of the residues are still in flight.
+static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, int npieces = 1) {
   Batch& b = c->b;
   b.nseq = nseq;
   b.seq_off.assign(seq_off, seq_off + nseq + 1);
@@ -1126,22 +1142,61 @@ static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int
   if (c->arena_f.reserve(arena_bytes) || c->arena_r.reserve(arena_bytes) || c->badflag.reserve(16)) return 1;
   c->h2d_bytes += nres;
   c->d2h_bytes += 4;
-  if (nres) CK(cudaMemcpyAsync(c->residues.p, residues, nres, cudaMemcpyHostToDevice, c->stream));
-  if (upload_vec(c, c->seq_off, b.seq_off)) return 1;
-  if (upload_vec(c, c->aoff, b.aoff)) return 1;
-  CK(cudaMemsetAsync(c->arena_f.p, 0, arena_bytes, c->stream));
-  CK(cudaMemsetAsync(c->arena_r.p, 0, arena_bytes, c->stream));
-  CK(cudaMemsetAsync(c->badflag.p, 0, 16, c->stream));
-  if (nseq) {
-    const int grid = (int)std::min<int64_t>(nseq, 148 * 32);
-    arena_kernel<<<grid, 128, 0, c->stream>>>(c->residues.as<uint8_t>(), c->seq_off.as<int64_t>(), c->aoff.as<int32_t>(), nseq,
-                                             c->sc.A, c->arena_f.as<uint8_t>(), c->arena_r.as<uint8_t>(), c->badflag.as<int>());
-    CK(cudaGetLastError());
-  }
-  CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
   if (!c->ev_flag) CK(cudaEventCreateWithFlags(&c->ev_flag, cudaEventDisableTiming));
-  CK(cudaEventRecord(c->ev_flag, c->stream));
+  npieces = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(npieces, 8), nres >> 22));  // >= 4 MB per piece
+  b.piece_end.clear();
+  cudaStream_t cs = c->stream;
+  if (npieces > 1) {
+    if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int j = 0; j < npieces; ++j)
+      if (!c->ev_piece[j]) CK(cudaEventCreateWithFlags(&c->ev_piece[j], cudaEventDisableTiming));
+    if (!c->ev_start) CK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    // the copy stream may not touch the buffers before earlier work of the compute stream is done with them
+    CK(cudaEventRecord(c->ev_start, c->stream));
+    cs = c->copy_stream;
+    CK(cudaStreamWaitEvent(cs, c->ev_start, 0));
+  }
+  if (upload_vec(c, c->seq_off, b.seq_off, cs, true)) return 1;
+  if (upload_vec(c, c->aoff, b.aoff, cs, true)) return 1;
+  CK(cudaMemsetAsync(c->arena_f.p, 0, arena_bytes, cs));
+  CK(cudaMemsetAsync(c->arena_r.p, 0, arena_bytes, cs));
+  CK(cudaMemsetAsync(c->badflag.p, 0, 16, cs));
+  int64_t s_begin = 0;
+  for (int j = 0; j < npieces; ++j) {
+    // piece j: sequences [s_begin, s_end) holding about 1/npieces of the residues
+    int64_t s_end = nseq;
+    if (j + 1 < npieces) {
+      const int64_t target = nres * (j + 1) / npieces;
+      s_end = std::upper_bound(seq_off, seq_off + nseq + 1, target) - seq_off - 1;
+      s_end = std::max(s_begin, std::min(s_end, nseq));
+    }
+    const int64_t r0 = seq_off[s_begin], r1 = seq_off[s_end];
+    if (r1 > r0) CK(cudaMemcpyAsync(c->residues.as<uint8_t>() + r0, residues + r0, (size_t)(r1 - r0), cudaMemcpyHostToDevice, cs));
+    if (s_end > s_begin) {
+      const int grid = (int)std::min<int64_t>(s_end - s_begin, 148 * 32);
+      arena_kernel<<<grid, 128, 0, cs>>>(c->residues.as<uint8_t>(), c->seq_off.as<int64_t>(), c->aoff.as<int32_t>(), s_begin, s_end,
+                                         c->sc.A, c->arena_f.as<uint8_t>(), c->arena_r.as<uint8_t>(), c->badflag.as<int>());
+      CK(cudaGetLastError());
+    }
+    if (npieces > 1) CK(cudaEventRecord(c->ev_piece[j], cs));
+    b.piece_end.push_back(s_end);
+    s_begin = s_end;
+  }
+  CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, cs));
+  CK(cudaEventRecord(c->ev_flag, cs));
   b.have_seqs = true;
+  return 0;
+}
+
+// Makes the compute stream wait for the residue pieces that hold every sequence up to `max_seq` (no-op when the
+// sequences were uploaded on the compute stream itself).
+static int wait_for_sequences(aadp_ctx* c, int64_t max_seq) {
+  Batch& b = c->b;
+  if (b.piece_end.size() <= 1) return 0;
+  size_t j = 0;
+  while (j + 1 < b.piece_end.size() && b.piece_end[j] <= max_seq) ++j;
+  for (size_t k = b.piece_waited; k <= j; ++k) CK(cudaStreamWaitEvent(c->stream, c->ev_piece[k], 0));
+  b.piece_waited = std::max(b.piece_waited, j + 1);
   return 0;
 }
 
@@ -1709,6 +1764,10 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
   if (threshold) { if (c->thr.reserve(nb)) return 1; dt = c->thr.as<float>(); }
   if (nearopt_count) { if (c->count.reserve(nb * 2)) return 1; dc = c->count.as<int64_t>(); }
   Batch& b = c->b;
+  const bool timing = getenv("AADP_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto ms_since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_seq = 0, t_chunk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_launched = 0;
   // Large batches are pipelined: the packed task list is built in chunks and the forward kernel of a chunk is
   // launched as soon as its tasks are on their way, so the GPU computes while the host schedules the next chunk.
   const bool pipelined = !c->float_mode && npairs >= 32768 && (what & AADP_W_FWD) && c->pipeline_chunks > 1;
@@ -1719,12 +1778,18 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     if (pin_reserve(c, (size_t)(nseq + 1) * 12 + pairs_pin_bytes(npairs))) return 1;
     c->h2d_bytes = 0;
     c->d2h_bytes = 0;
-    if (upload_sequences_impl(c, residues, seq_off, nseq)) return 1;
+    b.piece_waited = 0;
+    if (upload_sequences_impl(c, residues, seq_off, nseq, 2 * c->pipeline_chunks)) return 1;
+    t_seq = ms_since();
     const std::function<int(size_t)> on_chunk = [&](size_t k) -> int {
       if (k == 0 && run_prepare(c, what)) return 1;
-      return launch_packed_chunk(c, 0, what, delta_ratio, dt, dc, k);
+      if (wait_for_sequences(c, b.chunk_max_seq[k])) return 1;  // only the residue pieces this chunk references
+      const int rc = launch_packed_chunk(c, 0, what, delta_ratio, dt, dc, k);
+      if (k < 8) t_chunk[k] = ms_since();
+      return rc;
     };
     if (set_pairs_impl(c, pair_q, pair_t, npairs, what, c->pipeline_chunks, &on_chunk)) return 1;
+    if (wait_for_sequences(c, nseq)) return 1;  // everything that follows may read any sequence
     // the residue validation flag came back long ago (it was queued right after the arena kernel); the int32 and
     // wavefront kernels read the raw residues, so they are only launched on validated input
     CK(cudaEventSynchronize(c->ev_flag));
@@ -1734,6 +1799,7 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
       return fail("residue code outside the substitution alphabet");
     }
     if (run_batch_impl(c, what, delta_ratio, df, dr, dt, dc, true)) return 1;
+    t_launched = ms_since();
   }
   if (npairs) {
     if (fwd_score && (what & AADP_W_FWD)) { CK(cudaMemcpyAsync(fwd_score, df, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
@@ -1742,6 +1808,9 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     if (nearopt_count && (what & AADP_W_MASK)) { CK(cudaMemcpyAsync(nearopt_count, dc, npairs * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 8; }
   }
   CK(cudaStreamSynchronize(c->stream));
+  if (timing && pipelined)
+    fprintf(stderr, "[aadp] fill_batch host timeline (ms): sequences enqueued %.2f, fwd chunk launches %.2f %.2f %.2f, all launched %.2f, done %.2f\n",
+            t_seq, t_chunk[0], t_chunk[1], t_chunk[2], t_launched, ms_since());
   return 0;
 }
 
