@@ -578,3 +578,62 @@ def test_general_entry_with_similarity_matrix(blosum):
     s2, _, _ = c.fill_pair_general(np.ascontiguousarray(sim.T), 4.73, 0.34, po.GLOBAL, a.FWD)
     assert s1[-1, -1] == s2[-1, -1]
     c.close()
+
+
+def test_pipelined_fill_batch_equals_plain_path(blosum):
+    # aadp_fill_batch pipelines large batches (residues in pieces on a copy stream, task list in chunks, forward
+    # kernel of chunk k while the host schedules chunk k+1).  Same batch through the plain path (one chunk) and the
+    # resident upload+run path must give identical scalars, matrices and alignments; the batch mixes packed pairs with
+    # int32-path pairs (templates > 512) and shuffled pair order (chunks reference every residue piece).
+    import alignment_algos_b200 as a
+    import torch
+    from alignment_algos_b200 import synth
+    _, M = blosum
+    rng = np.random.default_rng(99)
+    seqs = synth.random_seqs(rng, 70000, 20, 90) + [rng.integers(0, 20, L).astype(np.uint8) for L in (530, 700, 0, 1)]
+    n = 36000
+    pq = rng.integers(0, 70000, n).astype(np.int32)
+    pt = rng.integers(0, 70000, n).astype(np.int32)
+    pt[::3000] = 70000 + (np.arange(len(pt[::3000])) % 4)   # int32-path / degenerate templates sprinkled in
+    res, off = a.Context.pack(seqs)
+    what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK | a.W_SCORES
+    outs = []
+    for chunks in (1, 2, 3):
+        c = a.Context(0)
+        c.set_option("pipeline_chunks", chunks)
+        c.set_scoring(M, 12, 1, po.SEMI_LOCAL)
+        out = c.fill_batch(res, off, pq, pt, what, 0.02)
+        samp = [0, 1, 2999, 3000, 17777, n - 1]
+        det = [c.fetch_pair(p, len(seqs[pq[p]]), len(seqs[pt[p]]), fwd=True, rev=True, mask=True) for p in samp]
+        ali = [c.optimal(p, a.FWD, len(seqs[pq[p]]), len(seqs[pt[p]])) for p in samp]
+        outs.append((out, det, ali))
+        if chunks == 2:   # the resident path on the same context
+            df = torch.zeros(n, dtype=torch.float32, device="cuda")
+            c.upload_batch(res, off, pq, pt, what)
+            c.run_batch(what, 0.02, d_fwd=df.data_ptr())
+            c.synchronize()
+            assert_matrix_equal("resident fwd", df.cpu().numpy(), out["fwd_score"])
+        c.close()
+    O = po.Oracle(M, 12, 1, po.SEMI_LOCAL)
+    for p in (0, 3000, 6000, 17777):
+        assert outs[0][0]["fwd_score"][p] == O.fill(seqs[pq[p]], seqs[pt[p]], po.FWD, fast=True)[0][-1, -1]
+    for k in (1, 2):
+        for key in ("fwd_score", "rev_score", "threshold", "nearopt_count"):
+            assert_matrix_equal("chunks %s" % key, outs[k][0][key], outs[0][0][key])
+        for d0, d1 in zip(outs[0][1], outs[k][1]):
+            for key in d0:
+                if d0[key] is not None:
+                    assert_matrix_equal("chunks fetch " + key, d1[key], d0[key])
+        for a0, a1 in zip(outs[0][2], outs[k][2]):
+            assert a0[0] == a1[0] and a0[2] == a1[2]
+            assert_matrix_equal("chunks alignment", a1[1], a0[1])
+    # loud failure on a residue outside the alphabet, also on the pipelined path
+    bad = res.copy()
+    bad[len(bad) // 2] = 77
+    c = a.Context(0)
+    c.set_scoring(M, 12, 1, po.SEMI_LOCAL)
+    with pytest.raises(a.AadpError):
+        c.fill_batch(bad, off, pq, pt, what, 0.02)
+    out = c.fill_batch(res, off, pq, pt, a.W_FWD)   # the context is still usable
+    assert_matrix_equal("after error", out["fwd_score"], outs[0][0]["fwd_score"])
+    c.close()
