@@ -989,6 +989,12 @@ aadp_ctx* aadp_create(int device) {
   }
   c->stream = c->own_stream;
   if (const char* e = getenv("AADP_HOST_THREADS")) c->host_threads = atoi(e);
+  else if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+    // one process per GPU (torchrun): the ranks of a box share its cores, so each scheduler takes its share
+    const int ranks = std::max(1, atoi(lw));
+    const int hw = (int)std::max<unsigned>(std::thread::hardware_concurrency(), 1u);
+    c->host_threads = std::max(2, std::min(8, hw / ranks));
+  }
   if (const char* e = getenv("AADP_PIPELINE_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(e), 8));
   return c;
 }
