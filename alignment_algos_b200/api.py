@@ -99,6 +99,29 @@ class Context:
                                           int(rect[2]), int(rect[3]), direction, _ptr(s), _ptr(pq), _ptr(pt)))
         return s, pq, pt
 
+    def fill_subpair_batch(self, residues, seq_off, item_q, item_t, rects, direction=FWD, want_alignments=True):
+        """Many build_subdpm fills + Optimal_Subali tracebacks in one call (ssss.h:621-633 loop closure).
+        rects: (n, 4) = (q1_end, t1_end, q2_beg, t2_beg) per item.  Returns (score[n], ali_off[n+1], pairs[(total,2)],
+        n_out[n], status[n]); the last three are None when want_alignments is False (or direction is REV)."""
+        item_q = np.ascontiguousarray(item_q, np.int32)
+        item_t = np.ascontiguousarray(item_t, np.int32)
+        rects = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        n = len(item_q)
+        assert len(item_t) == n and len(rects) == n
+        off = np.zeros(n + 1, np.int64)
+        self._ck(self.L.aadp_fill_subpair_batch(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(item_q),
+                                                _ptr(item_t), _ptr(rects), n, direction, None, _ptr(off), None, 0, None,
+                                                None))
+        score = np.zeros(n, np.float32)
+        ali = want_alignments and direction == FWD
+        pairs = np.zeros((max(int(off[-1]), 1), 2), np.int32) if ali else None
+        n_out = np.zeros(n, np.int32) if ali else None
+        st = np.zeros(n, np.int32) if ali else None
+        self._ck(self.L.aadp_fill_subpair_batch(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(item_q),
+                                                _ptr(item_t), _ptr(rects), n, direction, _ptr(score), _ptr(off),
+                                                _ptr(pairs), int(off[-1]), _ptr(n_out), _ptr(st)))
+        return score, off, pairs, n_out, st
+
     def fill_pair_general(self, sim, gi, ge, align_type, direction=FWD, rect=None, flags=REPRO_REV_BUG):
         """Any evaluator with uniform affine gaps: sim is the (Lq+2, Lt+2) similarity matrix of simmatrix.h."""
         sim = np.ascontiguousarray(sim, dtype=np.float32)

@@ -1468,7 +1468,8 @@ struct GeneralOverride {
 };
 
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
-                   float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr, const GeneralOverride* ov = nullptr) {
+                   float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr, const GeneralOverride* ov = nullptr,
+                   bool compact = false) {
   Batch& b = c->b;
   const int64_t cells = off[(size_t)n];
   int maxLt = 0, maxL = 0;
@@ -1519,20 +1520,31 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   }
   if (nd == 0) return 0;
   CK(cudaStreamSynchronize(c->stream));  // the pinned pool may still feed an earlier copy
-  if (pin_reserve(c, (size_t)(n + 1) * 8 + 4096)) return 1;
+  if (pin_reserve(c, (size_t)(n + 1) * 8 + (rect ? (size_t)n * 16 : 0) + 4096)) return 1;
   if (upload_vec(c, c->gg_off, off)) return 1;
   G.dense_off = c->gg_off.as<int64_t>();
-  if (rect) {  // build_subdpm: one rectangle (the single pair of this launch)
-    std::vector<int32_t> r(rect, rect + 4);
+  if (rect) {  // build_subdpm: one rectangle per item of this launch (4 ints each)
+    std::vector<int32_t> r(rect, rect + 4 * n);
     if (upload_vec(c, c->gg_rect, r)) return 1;
     G.rects = c->gg_rect.as<int4>();
   }
-  const int threads = std::max(64, std::min(512, (maxLt + 31) / 32 * 32));
+  G.compact = compact ? 1 : 0;      // compact batches (aadp_fill_subpair_batch) keep only the rectangles and
+  G.fin_by_item = compact ? 1 : 0;  // index the final scores by item: several items may share one pair
+  int width = maxLt;  // threads own columns: of the matrix, or of the widest rectangle
   double cu = 0;
-  for (int64_t p = p0; p < p0 + n; ++p) {
-    const int qs = b.pair_q[p], ts = b.pair_t[p];
-    cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  if (rect) {
+    width = 1;
+    for (int64_t k = 0; k < n; ++k) {
+      width = std::max(width, rect[4 * k + 3] - rect[4 * k + 1] - 1);
+      cu += (double)(rect[4 * k + 2] - rect[4 * k] - 1) * (double)(rect[4 * k + 3] - rect[4 * k + 1] - 1);
+    }
+  } else {
+    for (int64_t p = p0; p < p0 + n; ++p) {
+      const int qs = b.pair_q[p], ts = b.pair_t[p];
+      cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
+    }
   }
+  const int threads = std::max(compact ? 32 : 64, std::min(512, (width + 31) / 32 * 32));
   c->prof_begin(tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
   if (tb) {
     CK(cudaFuncSetAttribute(general_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
@@ -2126,6 +2138,83 @@ int aadp_fill_subpair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, i
   if (score) CK(cudaMemcpyAsync(score, c->gg_score[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->b.ran_what = 0;
+  return 0;
+}
+
+int aadp_fill_subpair_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* item_q,
+                            const int32_t* item_t, const int32_t* rects, int64_t nitems, int direction, float* score,
+                            int64_t* ali_off, int32_t* pairs, int64_t pairs_cap, int32_t* n_out, int32_t* status) {
+  if (check_ctx(c, true)) return 1;
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  if (nitems < 0 || nitems > 0x7fffffff) return fail("bad batch size");
+  if (nitems && (!item_q || !item_t || !rects || !seq_off)) return fail("null input");
+  if (direction == AADP_REV && (pairs || n_out || status))
+    return fail("aadp_fill_subpair_batch: sub-alignments are traced over forward fills only (optimal_subali.h:59-83)");
+  // bounds (dpmatrix.h:360-361 and the matrix limits), slots and compact cell offsets
+  std::vector<int64_t> cap((size_t)nitems + 1, 0), cells((size_t)nitems, 0);
+  for (int64_t k = 0; k < nitems; ++k) {
+    const int32_t* r = rects + 4 * k;
+    if (item_q[k] < 0 || item_q[k] >= nseq || item_t[k] < 0 || item_t[k] >= nseq) return fail("sequence id out of range");
+    const int64_t Lq = seq_off[item_q[k] + 1] - seq_off[item_q[k]], Lt = seq_off[item_t[k] + 1] - seq_off[item_t[k]];
+    if (r[2] <= r[0] || r[3] <= r[1]) return fail("Illegal bounds building DPM");
+    if (r[0] < 0 || r[1] < 0 || r[2] > Lq + 1 || r[3] > Lt + 1) return fail("sub-rectangle anchors outside the matrix");
+    cap[(size_t)k + 1] = cap[(size_t)k] + (r[2] - r[0] + 1);
+    cells[(size_t)k] = (int64_t)(r[2] - r[0] + 1) * (r[3] - r[1] + 1);
+  }
+  if (ali_off) memcpy(ali_off, cap.data(), (size_t)(nitems + 1) * 8);
+  if (nitems == 0 || (!score && !pairs && !n_out && !status)) return 0;
+  if (pairs && pairs_cap < cap[(size_t)nitems]) return fail("aadp_fill_subpair_batch: pairs buffer too small (needs 2*ali_off[nitems] ints)");
+  if (aadp_upload_batch(c, residues, seq_off, nseq, item_q, item_t, nitems, 0)) return 1;
+  const int d = direction - 1;
+  const bool trace = d == 0 && (pairs || n_out || status);
+  c->launches = 0;
+  if (c->gg_fin[d].reserve((size_t)nitems * 4)) return 1;
+  if (trace) {
+    if (pin_reserve(c, (size_t)(nitems + 1) * 8 + 4096)) return 1;
+    if (upload_vec(c, c->ali_cap, cap)) return 1;
+    if (c->ali_out.reserve((size_t)cap[(size_t)nitems] * 8) || c->ali_n.reserve((size_t)nitems * 4) ||
+        c->ali_status.reserve((size_t)nitems * 4)) return 1;
+  }
+  std::vector<int64_t> off;
+  for (int64_t p0 = 0; p0 < nitems;) {
+    off.assign(1, 0);
+    int64_t p1 = p0;
+    while (p1 < nitems && (p1 == p0 || off.back() + cells[(size_t)p1] <= c->gg_budget_cells) && p1 - p0 < 65535 * 16) {
+      off.push_back(off.back() + cells[(size_t)p1]);
+      ++p1;
+    }
+    const int64_t n = p1 - p0;
+    if (gg_fill(c, p0, n, 1 << d, trace, off, d ? nullptr : c->gg_fin[0].as<float>(), d ? c->gg_fin[1].as<float>() : nullptr,
+                rects + 4 * p0, nullptr, true)) return 1;
+    if (trace) {
+      SubTraceParams T{};
+      T.PQ = c->gg_pq[0].as<int32_t>();
+      T.PT = c->gg_pt[0].as<int32_t>();
+      T.D = c->gg_score[0].as<float>();
+      T.dense_off = c->gg_off.as<int64_t>();
+      T.rects = c->gg_rect.as<int4>();
+      T.cap_off = c->ali_cap.as<int64_t>();
+      T.item0 = (int)p0;
+      T.n = (int)n;
+      T.out = c->ali_out.as<int2>();
+      T.out_n = c->ali_n.as<int32_t>();
+      T.out_status = c->ali_status.as<int32_t>();
+      T.out_score = nullptr;
+      c->prof_begin("subali_trace_kernel", 0);
+      subali_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+    p0 = p1;
+  }
+  c->d2h_bytes = 0;
+  if (score) { CK(cudaMemcpyAsync(score, c->gg_fin[d].p, (size_t)nitems * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += nitems * 4; }
+  if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)nitems] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)nitems] * 8; }
+  if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)nitems * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += nitems * 4; }
+  if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)nitems * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += nitems * 4; }
   CK(cudaStreamSynchronize(c->stream));
   c->b.ran_what = 0;
   return 0;

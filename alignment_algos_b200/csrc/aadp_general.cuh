@@ -42,6 +42,10 @@ struct GeneralParams {
                              // substitution table lookup
   const int4* rects;         // per item: anchors (q1_end, t1_end, q2_beg, t2_beg) of build_subdpm (dpmatrix.h:319-353),
                              // matrix indices; null = the whole matrix (0, 0, Lq+1, Lt+1)
+  int compact;               // 1: an item stores only its rectangle, (q2_beg-q1_end+1) x (t2_beg-t1_end+1) cells with the
+                             // first anchor at offset 0 (batched loop-closure fills: many small rectangles of large
+                             // matrices); predecessors stay matrix indices
+  int fin_by_item;           // 1: fin[] is indexed by item0 + item instead of by pair
   float* score[2];           // per direction: dense score matrices (always)
   int32_t* prevq[2];         // per direction: dense predecessor rows/cols, or null
   int32_t* prevt[2];
@@ -67,6 +71,10 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   int q0 = 0, t0 = 0, mq1 = Lq + 1, mt1 = Lt + 1;
   if (P.rects) { const int4 r = P.rects[blockIdx.x]; q0 = r.x; t0 = r.y; mq1 = r.z; mt1 = r.w; }
   const int sz2 = Lt + 2, q1 = mq1 - q0, t1 = mt1 - t0, nq = q1 - 1, nt = t1 - 1;
+  // storage of the outputs: the whole matrix, or (compact) the rectangle alone
+  const int ld = P.compact ? t1 + 1 : sz2, nrows = P.compact ? q1 + 1 : Lq + 2;
+  const int r0 = P.compact ? q0 : 0, c0 = P.compact ? t0 : 0;
+  const int fin_idx = P.fin_by_item ? P.item0 + item : pair;
   const int64_t base = P.dense_off ? P.dense_off[item] : 0;
   float* D = P.score[dsel] + base;
   int32_t* PQ = TBM ? P.prevq[dsel] + base : nullptr;
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   // matrix index of flow cell (a,b); matrix row / column of a flow row / column
   auto rowof = [&](int a) { return rev ? mq1 - a : q0 + a; };
   auto colof = [&](int b) { return rev ? mt1 - b : t0 + b; };
-  auto at = [&](int a, int b) -> int64_t { return (int64_t)rowof(a) * sz2 + colof(b); };
+  auto at = [&](int a, int b) -> int64_t { return (int64_t)(rowof(a) - r0) * ld + (colof(b) - c0); };
   auto clampl = [&](float s) { return (local && s < 0.f) ? 0.f : s; };
   const float* simov = P.simov ? P.simov + base : nullptr;
   auto sim = [&](int a, int b) -> float {  // flow cell -> similarity (interior cells only)
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   }
 
   // DPCell::DPCell (dpmatrix.cpp:17-25): score 0, predecessors null
-  for (int64_t o = tid; o < (int64_t)(Lq + 2) * sz2; o += nth) {
+  for (int64_t o = tid; o < (int64_t)nrows * ld; o += nth) {
     D[o] = 0.f;
     if (TBM) { PQ[o] = -1; PT[o] = -1; }
   }
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       s = __fsub_rn(s, nq == 0 ? gdel(0, t1) : gins(0, q1));
       s = __fadd_rn(s, simf);
       set_tb(q1, t1, 0, 0, s);
-      if (P.fin[dsel]) P.fin[dsel][pair] = s;
+      if (P.fin[dsel]) P.fin[dsel][fin_idx] = s;
     }
     return;
   }
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       bool col = false;
       int ka = 0;
       const float* colp = D + at(1, b - 1);
-      const int64_t cstride = rev ? -(int64_t)sz2 : (int64_t)sz2;
+      const int64_t cstride = rev ? -(int64_t)ld : (int64_t)ld;
       if (TBM) {
         for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
           float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]);
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
     set_tb(q1, t1, oa, ob, os);
     // dpmatrix.h:868: the global reverse fill records opt_j = t1_m1 (a matrix column) for left-column candidates
     if (TBM && rev && !local && P.repro_rev_bug && from_col) PT[at(q1, t1)] = mt1 - 1;
-    if (P.fin[dsel]) P.fin[dsel][pair] = os;
+    if (P.fin[dsel]) P.fin[dsel][fin_idx] = os;
   }
 }
 
@@ -278,6 +286,57 @@ __global__ void __launch_bounds__(256) general_mask_kernel(const GeneralMaskPara
     if (P.count) P.count[pair] = s_cnt;
     if (P.threshold) P.threshold[pair] = thr;
   }
+}
+
+// Optimal sub-alignment of every rectangle of a compact batch: Optimal_Subali::enumerate (optimal_subali.h:59-83).
+// One thread per item follows DPCell::prev_* from (q2_beg, t2_beg) while q_last > q1_end, then requires the walk to
+// have ended on (q1_end, t1_end) (status 3 = "Illegal alignment start pair", optimal_subali.h:80).  Every step lowers
+// the query index, so a slot of q2_beg - q1_end + 1 aligned pairs always suffices.
+struct SubTraceParams {
+  const int32_t* PQ;
+  const int32_t* PT;
+  const float* D;
+  const int64_t* dense_off;  // per item of this launch
+  const int4* rects;         // per item of this launch
+  const int64_t* cap_off;    // per item of the whole batch (index item0 + item)
+  int item0, n;
+  int2* out;                 // slots, front to back
+  int32_t* out_n;
+  int32_t* out_status;
+  float* out_score;          // D[q2_beg][t2_beg].score (optimal_subali.h:68), or null
+};
+
+__global__ void __launch_bounds__(128) subali_trace_kernel(const SubTraceParams P) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P.n) return;
+  const int4 r = P.rects[item];
+  const int ld = r.w - r.y + 1;
+  const int64_t base = P.dense_off[item];
+  auto idx = [&](int i, int j) -> int64_t { return base + (int64_t)(i - r.x) * ld + (j - r.y); };
+  const int cap = r.z - r.x + 1;
+  int len = 1, i = r.z, j = r.w;
+  while (i > r.x && len <= cap) {
+    const int64_t o = idx(i, j);
+    i = P.PQ[o];
+    j = P.PT[o];
+    ++len;
+  }
+  const bool ok = (i == r.x && j == r.y);
+  const int64_t slot = P.cap_off[P.item0 + item];
+  len = min(len, cap);
+  i = r.z;
+  j = r.w;
+  for (int k = len - 1; k >= 0; --k) {  // prepend order: the slot reads front to back
+    P.out[slot + k] = make_int2(i, j);
+    if (k) {
+      const int64_t o = idx(i, j);
+      i = P.PQ[o];
+      j = P.PT[o];
+    }
+  }
+  P.out_n[P.item0 + item] = len;
+  P.out_status[P.item0 + item] = ok ? 0 : 3;
+  if (P.out_score) P.out_score[P.item0 + item] = P.D[idx(r.z, r.w)];
 }
 
 }  // namespace aadp

@@ -103,6 +103,25 @@ int aadp_fill_subpair(aadp_ctx* ctx, const uint8_t* q, int Lq, const uint8_t* t,
                       int t1_end, int q2_beg, int t2_beg, int direction, float* score,
                       int32_t* prev_q, int32_t* prev_t);
 
+/* ---- many sub-rectangle fills + their optimal sub-alignments in ONE call: the loop-closure
+ * pattern of ssss.h:600-633,700-720 -- per loop a 9-argument DPMatrix (dpmatrix.h:169-189, build_subdpm :319-353)
+ * followed by Optimal_Subali::enumerate (optimal_subali.h:59-83) -- for a whole list of loops.
+ * Item k fills the rectangle rects[4k..4k+3] = (q1_end, t1_end, q2_beg, t2_beg) of query sequence item_q[k] against
+ * template sequence item_t[k] (ids into residues/seq_off as in aadp_fill_batch; items may share sequences).  Each
+ * item runs on the exact general-gap fp32 kernel in COMPACT storage: only its rectangle lives in HBM, not the
+ * (Lq+2)*(Lt+2) matrix around it.  direction: AADP_FWD or AADP_REV (REV: scores only).  Host outputs (any may be NULL):
+ *   score    nitems: score of the final cell, D[q2_beg][t2_beg] (FWD, = AlignedPairList::score of
+ *            optimal_subali.h:68) or D[q1_end][t1_end] (REV)
+ *   ali_off  nitems+1: slot k is ali_off[k]..ali_off[k+1] = q2_beg-q1_end+1 aligned pairs (every traceback step lowers
+ *            the query index); computed on the host -- call with every other output NULL to size `pairs`
+ *   pairs    2*ali_off[nitems] ints (pairs_cap = capacity in aligned pairs): slot k holds n_out[k] (query_idx,
+ *            template_idx) pairs front to back, from (q1_end, t1_end) to (q2_beg, t2_beg)
+ *   status   0, or 3 where the reference throws "Illegal alignment start pair" (optimal_subali.h:80)          */
+int aadp_fill_subpair_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,
+                            const int32_t* item_q, const int32_t* item_t, const int32_t* rects, int64_t nitems,
+                            int direction, float* score, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
+                            int32_t* n_out, int32_t* status);
+
 /* ---- ANY Evaluator with a uniform affine gap model: the similarity matrix the reference builds on the host
  * (SimilarityMatrix, simmatrix.h:40-73: sim[i][j] = evaluator.similarity(q,t,i,j), after post_process) is handed
  * over as it is -- (Lq+2)*(Lt+2) floats, row-major -- together with gap(len) = gi + ge*(len-1) and the align

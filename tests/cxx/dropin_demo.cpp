@@ -76,6 +76,30 @@ int main(int argc, char** argv) {
       std::printf("\n");
       Matrix subr(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, rev, params.align_type);
       dump("T", subr);
+      // a list of loops closed one after the other, as ssss.h:600-633 does: per loop a sub-matrix and its optimal
+      // sub-alignment.  This build hands the whole list to the GPU in one call; the output must not differ.
+      const int nq = (int)query.size(), nt = (int)templ.size();
+      const int loops[5][4] = {{0, 0, 4, 5}, {3, 2, nq - 4, nt - 3}, {nq - 6, nt - 5, nq - 1, nt - 1}, {1, 1, 2, 6}, {2, 4, 7, 5}};
+#ifdef AADP_HMAP2_DPMATRIX_H
+      std::vector<aadp::LoopRect> lr(5);
+      for (int k = 0; k < 5; ++k) { lr[k].q1_end = loops[k][0]; lr[k].t1_end = loops[k][1]; lr[k].q2_beg = loops[k][2]; lr[k].t2_beg = loops[k][3]; }
+      std::vector<AlignedPairList<AASequence, AASequence> > closed;
+      aadp::optimal_subalignments(query, templ, eval, lr, &closed);
+#endif
+      for (int k = 0; k < 5; ++k) {
+#ifdef AADP_HMAP2_DPMATRIX_H
+        const AlignedPairList<AASequence, AASequence>& la = closed[k];
+#else
+        Matrix lm(query, templ, eval, loops[k][0], loops[k][1], loops[k][2], loops[k][3], fwd, params.align_type);
+        Optimal_Subali<AASequence, AASequence, AAEval> lo(loops[k][0], loops[k][1], loops[k][2], loops[k][3]);
+        AlignmentSet<AASequence, AASequence, AAEval> ls(lm, lo);
+        const AlignedPairList<AASequence, AASequence>& la = ls[0];
+#endif
+        std::printf("LOOP %d score %.6g pairs", k, la.score);
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = la.begin(); it != la.end(); ++it)
+          std::printf(" %d:%d", it->query_idx(), it->template_idx());
+        std::printf("\n");
+      }
     }
 #ifdef AADP_HMAP2_DPMATRIX_H
     // extras of this build: reverse traceback and the near-optimal cell set

@@ -75,6 +75,8 @@ def test_gpu_dropin_equals_reference_build(blosum, at):
         if os.path.exists(REF_DEMO) and Lq * Lt < 5000:
             ref = [l for l in _run(REF_DEMO, at, gi, ge, q, t) if not l.startswith("#")]
             assert core == ref, "GPU drop-in build and reference build print different results"
+            if Lq > 7 and Lt > 7:  # the loop list closed in ONE aadp_fill_subpair_batch call vs. one sub-matrix per loop
+                assert len([l for l in core if l.startswith("LOOP ")]) == 5
         # optimal alignment line against the oracle traceback
         F, fq, ft = res["F"]
         rc, pairs, sc = O.optimal(F, fq, ft, po.FWD)

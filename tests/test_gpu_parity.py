@@ -552,6 +552,83 @@ def test_sub_rectangle_fill_golden_and_random(golden_sub, blosum):
     c.close()
 
 
+def _subali_walk(S, PQ, PT, rect):
+    """Optimal_Subali::enumerate (optimal_subali.h:59-83) over reference-shaped dense matrices."""
+    q1, t1, q2, t2 = [int(x) for x in rect]
+    i, j = q2, t2
+    path = [(i, j)]
+    while i > q1:
+        i, j = int(PQ[i, j]), int(PT[i, j])
+        path.insert(0, (i, j))
+    return (0 if (i, j) == (q1, t1) else 3), np.array(path, np.int32).reshape(-1, 2), S[q2, t2]
+
+
+def test_sub_rectangle_batch_golden_and_random(golden_sub, blosum):
+    # aadp_fill_subpair_batch (row f4): many build_subdpm fills + Optimal_Subali tracebacks in one call, compact storage
+    import alignment_algos_b200 as a
+    g = golden_sub
+    c = a.Context(0)
+    groups = {}
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        groups.setdefault((float(gi), float(ge), int(at), q.tobytes(), t.tobytes()), []).append(name)
+    assert len(groups) >= 10
+    for (gi, ge, at, _, _), names in groups.items():
+        q, t, _, _, _ = golden_case(g, names[0])
+        c.set_scoring(g["sub"], gi, ge, at)
+        res, off = a.Context.pack([q, t])
+        rects = np.array([g[n + ".rect"] for n in names], np.int32)
+        iq, it = np.zeros(len(names), np.int32), np.ones(len(names), np.int32)
+        score, aoff, pairs, n_out, st = c.fill_subpair_batch(res, off, iq, it, rects, a.FWD)
+        rscore, _, _, _, _ = c.fill_subpair_batch(res, off, iq, it, rects, a.REV)
+        for k, n in enumerate(names):
+            wst, wpairs, wscore = _subali_walk(g[n + ".fwd.score"], g[n + ".fwd.pq"], g[n + ".fwd.pt"], rects[k])
+            assert aoff[k + 1] - aoff[k] == rects[k][2] - rects[k][0] + 1
+            assert st[k] == wst, n
+            assert score[k] == wscore, n
+            assert_matrix_equal(n + " subali", pairs[aoff[k]:aoff[k] + n_out[k]], wpairs)
+            assert rscore[k] == g[n + ".rev.score"][rects[k][0], rects[k][1]], n
+    # random: several pairs, many loops each, chunked by a small scratch budget; oracle + the single-fill entry
+    _, M = blosum
+    rng = np.random.default_rng(31)
+    for gi, ge, at in [(12, 1, po.SEMI_LOCAL), (4.73, 0.34, po.GLOBAL), (10.5, 0.25, po.GLOBAL_LOCAL)]:
+        c.set_scoring(M, gi, ge, at)
+        O = po.Oracle(M, gi, ge, at)
+        seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(100, 300, 12)]
+        res, off = a.Context.pack(seqs)
+        n = 400
+        iq = rng.integers(0, 12, n).astype(np.int32)
+        it = rng.integers(0, 12, n).astype(np.int32)
+        rects = np.zeros((n, 4), np.int32)
+        for k in range(n):
+            Lq, Lt = len(seqs[iq[k]]), len(seqs[it[k]])
+            q0 = int(rng.integers(0, Lq + 1)); t0 = int(rng.integers(0, Lt + 1))
+            rects[k] = (q0, t0, min(Lq + 1, q0 + int(rng.integers(1, 150))), min(Lt + 1, t0 + int(rng.integers(1, 150))))
+        rects[0] = (0, 0, len(seqs[iq[0]]) + 1, len(seqs[it[0]]) + 1)   # a whole matrix among the loops
+        c.set_option("general_budget_mcells", 1)
+        score, aoff, pairs, n_out, st = c.fill_subpair_batch(res, off, iq, it, rects, a.FWD)
+        c.set_option("general_budget_mcells", 400)
+        score2, aoff2, pairs2, n2, st2 = c.fill_subpair_batch(res, off, iq, it, rects, a.FWD)
+        assert_matrix_equal("chunked score", score, score2)
+        assert_matrix_equal("chunked pairs", pairs, pairs2)
+        assert_matrix_equal("chunked n", n_out, n2)
+        sonly = c.fill_subpair_batch(res, off, iq, it, rects, a.FWD, want_alignments=False)[0]
+        assert_matrix_equal("score-only", sonly, score)
+        for k in list(range(0, n, 7)) + [n - 1]:
+            q, t = seqs[iq[k]], seqs[it[k]]
+            ws, wq, wt = O.fill_sub(q, t, tuple(int(x) for x in rects[k]), po.FWD)
+            wst, wpairs, wscore = _subali_walk(ws, wq, wt, rects[k])
+            assert st[k] == wst and score[k] == wscore, k
+            assert_matrix_equal("item %d subali" % k, pairs[aoff[k]:aoff[k] + n_out[k]], wpairs)
+        s1, _, _ = c.fill_subpair(seqs[iq[5]], seqs[it[5]], rects[5], a.FWD)
+        assert s1[rects[5][2], rects[5][3]] == score[5]
+    with pytest.raises(a.AadpError):
+        c.fill_subpair_batch(res, off, iq[:1], it[:1], np.array([[5, 5, 5, 9]], np.int32), a.FWD)
+    z = c.fill_subpair_batch(res, off, iq[:0], it[:0], np.zeros((0, 4), np.int32), a.FWD)
+    assert len(z[0]) == 0 and z[1][0] == 0
+    c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a
