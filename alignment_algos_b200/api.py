@@ -132,6 +132,19 @@ class Context:
                                                direction, _ptr(r), _ptr(s), _ptr(pq), _ptr(pt)))
         return s, pq, pt
 
+    def fill_pair_tabulated(self, sim, del_tab, ins_tab, is_local=False, direction=FWD, flags=REPRO_REV_BUG):
+        """Any evaluator, position-dependent gaps included: sim (Lq+2, Lt+2), del_tab (Lt+2, Lt+2), ins_tab (Lq+1, Lt+2)
+        as described in include/aadp.h (aadp_fill_pair_tabulated)."""
+        sim = np.ascontiguousarray(sim, dtype=np.float32)
+        del_tab = np.ascontiguousarray(del_tab, dtype=np.float32)
+        ins_tab = np.ascontiguousarray(ins_tab, dtype=np.float32)
+        sz = sim.shape
+        assert del_tab.shape == (sz[1], sz[1]) and ins_tab.shape == (sz[0] - 1, sz[1])
+        s, pq, pt = np.zeros(sz, np.float32), np.zeros(sz, np.int32), np.zeros(sz, np.int32)
+        self._ck(self.L.aadp_fill_pair_tabulated(self.h, _ptr(sim), sz[0] - 2, sz[1] - 2, _ptr(del_tab), _ptr(ins_tab),
+                                                 int(bool(is_local)), flags, direction, _ptr(s), _ptr(pq), _ptr(pt)))
+        return s, pq, pt
+
     # ---- batches ----
     @staticmethod
     def pack(seqs):

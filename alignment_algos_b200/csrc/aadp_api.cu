@@ -1465,6 +1465,11 @@ struct GeneralOverride {
   int align_type;
   uint32_t flags;
   const float* d_sim;
+  // tabulated gap model (aadp_fill_pair_tabulated); null = the affine model above
+  const float* d_del;
+  const float* d_delT;
+  const float* d_ins;
+  int tab_local;
 };
 
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
@@ -1499,7 +1504,15 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     G.repro_rev_bug = (ov->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
     G.simov = ov->d_sim;
     G.A = 1;
+    if (ov->d_del) {
+      G.del_tab = ov->d_del;
+      G.del_tabT = ov->d_delT;
+      G.ins_tab = ov->d_ins;
+      G.delfree = G.insfree = 0;  // free end gaps are whatever the tables say
+      G.local = ov->tab_local;
+    }
   }
+  const bool tab = ov && ov->d_del;
   G.residues = c->residues.as<uint8_t>();
   G.seq_off = c->seq_off.as<int64_t>();
   G.pair_q = c->pair_q.as<int32_t>();
@@ -1545,8 +1558,11 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     }
   }
   const int threads = std::max(compact ? 32 : 64, std::min(512, (width + 31) / 32 * 32));
-  c->prof_begin(tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
-  if (tb) {
+  c->prof_begin(tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
+  if (tab) {
+    CK(cudaFuncSetAttribute(general_fill_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    general_fill_kernel<1, 1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
+  } else if (tb) {
     CK(cudaFuncSetAttribute(general_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     general_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
   } else {
@@ -2253,13 +2269,65 @@ int aadp_fill_pair_general(aadp_ctx* c, const float* sim, int Lq, int Lt, float 
   CK(cudaMemcpyAsync(c->scratch_d.p, sim, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // gg_fill recycles the pinned pool; the caller's sim buffer is free again
   const std::vector<int64_t> doff = {0, n};
-  GeneralOverride ov{gi, ge, align_type, flags, c->scratch_d.as<float>()};
+  GeneralOverride ov{gi, ge, align_type, flags, c->scratch_d.as<float>(), nullptr, nullptr, nullptr, 0};
   const int d = direction - 1;
   c->launches = 0;
   if (gg_fill(c, 0, 1, 1 << d, true, doff, nullptr, nullptr, rect, &ov)) return 1;
   if (score) CK(cudaMemcpyAsync(score, c->gg_score[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[d].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_fill_pair_tabulated(aadp_ctx* c, const float* sim, int Lq, int Lt, const float* del_tab, const float* ins_tab,
+                             int is_local, uint32_t flags, int direction, float* score, int32_t* prev_q, int32_t* prev_t) {
+  if (check_ctx(c, false)) return 1;
+  if (Lq < 0 || Lt < 0) return fail("Illegal bounds building DPM");
+  if (!sim || !del_tab || !ins_tab) return fail("null argument");
+  if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+  const int sz1 = Lq + 2, sz2 = Lt + 2;
+  // every evaluator of the reference returns 0 for adjacent positions (aasubalib.h:36,62; hmap_eval.h:69,95;
+  // gn2_eval.h:104,138) and the kernel relies on it for the final cell; refuse a table that says otherwise
+  for (int k = 0; k + 1 < sz2; ++k)
+    if (del_tab[(size_t)k * sz2 + k + 1] != 0.f) return fail("tabulated gap model: deletion between adjacent positions must be 0");
+  for (int j = 0; j < sz2; ++j)
+    if (ins_tab[j] != 0.f) return fail("tabulated gap model: insertion between adjacent positions must be 0");
+  Batch& b = c->b;
+  b.nseq = 2;
+  b.npairs = 1;
+  b.seq_off = {0, Lq, (int64_t)Lq + Lt};
+  b.pair_q = {0};
+  b.pair_t = {1};
+  b.have_seqs = false;
+  b.ran_what = 0;
+  b.uploaded_what = 0;
+  b.tb_off.clear();
+  CK(cudaStreamSynchronize(c->stream));
+  if (pin_reserve(c, 4096)) return 1;
+  if (upload_vec(c, c->seq_off, b.seq_off) || upload_vec(c, c->pair_q, b.pair_q) || upload_vec(c, c->pair_t, b.pair_t)) return 1;
+  if (c->residues.reserve((size_t)Lq + Lt + 16)) return 1;
+  CK(cudaMemsetAsync(c->residues.p, 0, (size_t)Lq + Lt + 16, c->stream));
+  const int64_t n = (int64_t)sz1 * sz2, nd = (int64_t)sz2 * sz2, ni = (int64_t)(Lq + 1) * sz2;
+  std::vector<float> delT((size_t)nd);
+  for (int x = 0; x < sz2; ++x)
+    for (int y = 0; y < sz2; ++y) delT[(size_t)y * sz2 + x] = del_tab[(size_t)x * sz2 + y];
+  // one scratch block: sim | del | del^T | ins
+  if (c->scratch_d.reserve((size_t)(n + 2 * nd + ni) * 4)) return 1;
+  float* d = c->scratch_d.as<float>();
+  CK(cudaMemcpyAsync(d, sim, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + n, del_tab, (size_t)nd * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + n + nd, delT.data(), (size_t)nd * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d + n + 2 * nd, ins_tab, (size_t)ni * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const std::vector<int64_t> doff = {0, n};
+  GeneralOverride ov{0.f, 0.f, is_local ? AADP_LOCAL : AADP_GLOBAL, flags, d, d + n, d + n + nd, d + n + 2 * nd, is_local ? 1 : 0};
+  const int dd = direction - 1;
+  c->launches = 0;
+  if (gg_fill(c, 0, 1, 1 << dd, true, doff, nullptr, nullptr, nullptr, &ov)) return 1;
+  if (score) CK(cudaMemcpyAsync(score, c->gg_score[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -42,6 +42,12 @@ struct GeneralParams {
                              // substitution table lookup
   const int4* rects;         // per item: anchors (q1_end, t1_end, q2_beg, t2_beg) of build_subdpm (dpmatrix.h:319-353),
                              // matrix indices; null = the whole matrix (0, 0, Lq+1, Lt+1)
+  // Tabulated gap model (TAB=1, single pair, whole matrix): the two gap functions of ANY Evaluator over every
+  // argument combination the fill can pass (dpmatrix.h:356-1030), so evaluators with position-dependent penalties
+  // (hmap_eval.h:63-117, gn2_eval.h:99-158) run the same scan.  sz2 = Lt+2:
+  const float* del_tab;      //   [t_pos1*sz2 + t_pos2] = deletion(., ., t_pos1, t_pos2), t_pos1 < t_pos2
+  const float* del_tabT;     //   its transpose (the reverse fill scans it by column)
+  const float* ins_tab;      //   [(q_pos2-q_pos1-1)*sz2 + t_pos2] = insertion(q_pos1, q_pos2, t_pos2-1, t_pos2)
   int compact;               // 1: an item stores only its rectangle, (q2_beg-q1_end+1) x (t2_beg-t1_end+1) cells with the
                              // first anchor at offset 0 (batched loop-closure fills: many small rectangles of large
                              // matrices); predecessors stay matrix indices
@@ -56,7 +62,7 @@ __device__ __forceinline__ float gg_pen(float gi, float ge, int len) {  // aasub
   return __fadd_rn(gi, __fmul_rn(ge, (float)(len - 1)));
 }
 
-template <int TBM>
+template <int TBM, int TAB = 0>
 __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P) {
   extern __shared__ __align__(16) float gg_smem[];
   const int item = blockIdx.x;
@@ -88,7 +94,8 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   float* prow = gg_smem;              // D[a-1][0..nt]
   float* pen = gg_smem + (Lt + 2);    // pen[len], len >= 1
   const int maxlen = max(nq, nt);
-  for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
+  if (!TAB)
+    for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
 
   // matrix index of flow cell (a,b); matrix row / column of a flow row / column
   auto rowof = [&](int a) { return rev ? mq1 - a : q0 + a; };
@@ -104,16 +111,21 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   // gap between flow columns b0 < b1 / flow rows a0 < a1, with the free end gaps of aasubalib.h:39-42,65-68:
   // free when the lower matrix position is the Head or the upper one is the Tail (anchors of a sub-rectangle
   // are ordinary residues unless they are the Head / the Tail)
+  // template position pair of an insertion taken by a cell of flow column b: (j-1, j) forward (dpmatrix.h:473),
+  // (j, j+1) reverse (dpmatrix.h:812); the table is indexed by the upper one
+  auto t2of = [&](int b) { return rev ? colof(b) + 1 : colof(b); };
   auto gdel = [&](int b0, int b1) -> float {
     const int len = b1 - b0 - 1;
     if (len < 1) return 0.f;
     const int x = colof(b0), y = colof(b1);
+    if (TAB) return P.del_tab[(int64_t)min(x, y) * sz2 + max(x, y)];
     if (P.delfree && (min(x, y) == 0 || max(x, y) == Lt + 1)) return 0.f;
     return pen[len];
   };
-  auto gins = [&](int a0, int a1) -> float {
+  auto gins = [&](int a0, int a1, int b) -> float {
     const int len = a1 - a0 - 1;
     if (len < 1) return 0.f;
+    if (TAB) return P.ins_tab[(int64_t)len * sz2 + t2of(b)];
     const int x = rowof(a0), y = rowof(a1);
     if (P.insfree && (min(x, y) == 0 || max(x, y) == Lq + 1)) return 0.f;
     return pen[len];
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   if (nq == 0 || nt == 0) {
     if (tid == 0) {
       float s = 0.f;
-      s = __fsub_rn(s, nq == 0 ? gdel(0, t1) : gins(0, q1));
+      s = __fsub_rn(s, nq == 0 ? gdel(0, t1) : gins(0, q1, t1));
       s = __fadd_rn(s, simf);
       set_tb(q1, t1, 0, 0, s);
       if (P.fin[dsel]) P.fin[dsel][fin_idx] = s;
@@ -161,7 +173,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   }
   for (int a = 2 + tid; a <= nq; a += nth) {
     float s = 0.f;
-    s = __fsub_rn(s, gins(0, a));
+    s = __fsub_rn(s, gins(0, a, 1));
     s = clampl(__fadd_rn(s, sim(a, 1)));
     set_tb(a, 1, 0, 0, s);
   }
@@ -174,16 +186,20 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       const float simc = simov ? subrow[colof(b)] : subrow[(int)tseq[colof(b) - 1]];
       int oa = a - 1, ob = b - 1;
       float os = clampl(__fadd_rn(prow[b - 1], simc));
+      // tabulated penalties of this cell: deletion column (rows = the other template position), insertion column
+      const float* dcol = TAB ? (rev ? P.del_tabT : P.del_tab) + colof(b) : nullptr;
+      const float* icol = TAB ? P.ins_tab + t2of(b) : nullptr;
       if (TBM) {
         for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
-          float s = __fsub_rn(prow[k], pen[b - k - 1]);
+          float s = __fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]);
           s = clampl(__fadd_rn(s, simc));
           if (s > os) { ob = k; os = s; }
         }
       } else {
         // score only: the strict-'>' scan and a running maximum give the same value; the clamp commutes with max
 #pragma unroll 4
-        for (int k = 1; k < b - 1; ++k) os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], pen[b - k - 1]), simc));
+        for (int k = 1; k < b - 1; ++k)
+          os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]), simc));
       }
       bool col = false;
       int ka = 0;
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       const int64_t cstride = rev ? -(int64_t)ld : (int64_t)ld;
       if (TBM) {
         for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
-          float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]);
+          float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], TAB ? icol[(int64_t)(a - k - 1) * sz2] : pen[a - k - 1]);
           s = clampl(__fadd_rn(s, simc));
           if (s > os) { col = true; ka = k; os = s; }
         }
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       } else {
 #pragma unroll 4
         for (int k = 1; k < a - 1; ++k)
-          os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc));
+          os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], TAB ? icol[(int64_t)(a - k - 1) * sz2] : pen[a - k - 1]), simc));
         os = clampl(os);
       }
       set_tb(a, b, oa, ob, os);
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       if (s > os) { oa = nq; ob = k; os = s; }
     }
     for (int k = 1; k < q1; ++k) {
-      float s = __fsub_rn(D[at(k, nt)], gins(k, q1));
+      float s = __fsub_rn(D[at(k, nt)], gins(k, q1, t1));
       s = clampl(__fadd_rn(s, simf));
       if (s > os) { oa = k; ob = nt; os = s; from_col = true; }
     }

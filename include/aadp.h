@@ -134,6 +134,23 @@ int aadp_fill_pair_general(aadp_ctx* ctx, const float* sim, int Lq, int Lt, floa
                            int align_type, uint32_t flags, int direction, const int* rect, float* score,
                            int32_t* prev_q, int32_t* prev_t);
 
+/* ---- ANY Evaluator, position-dependent gap penalties included: the fill asks an Evaluator
+ * (evaluator.h:20-147) for similarity(i,j), deletion(.,.,t1,t2) and insertion(q1,q2,t2-1,t2); the host tabulates
+ * the three over every argument combination dpmatrix.h:356-1030 can pass and the exact general-gap kernel runs the
+ * reference's own scan over the tables -- bit-exact for hmap_eval.h:63-117 (gi/ge = min over the two template
+ * positions) and gn2_eval.h:99-158 (pairwise deletion table, per-position insertion) style models as well.
+ * Requirements (all reference evaluators meet them): deletion ignores the query positions; insertion sees the query
+ * only through q2-q1 except at the Head/Tail; both are 0 for adjacent positions.  sz1 = Lq+2, sz2 = Lt+2:
+ *   sim      sz1*sz2   SimilarityMatrix (simmatrix.h:40-73)
+ *   del_tab  sz2*sz2   [t1*sz2 + t2] = deletion(q, q+1, t1, t2) for 0 <= t1 < t2 <= Lt+1 (other entries unused)
+ *   ins_tab  (Lq+1)*sz2  [len*sz2 + t2] = insertion(q1, q1+len+1, t2-1, t2), len = 0..Lq, t2 = 1..Lt+1, where
+ *            t2 == 1 means q1 = Head (boundary column, dpmatrix.h:421) and t2 == Lt+1 means q1+len+1 = Tail
+ *            (final cell, dpmatrix.h:520); any interior q1 for the other columns
+ * include/hmap2/dpmatrix.h builds these tables for every Etype without a DeviceScoring mapping.             */
+int aadp_fill_pair_tabulated(aadp_ctx* ctx, const float* sim, int Lq, int Lt, const float* del_tab,
+                             const float* ins_tab, int is_local, uint32_t flags, int direction, float* score,
+                             int32_t* prev_q, int32_t* prev_t);
+
 /* ---- batch of pairs, HOST buffers (the end-to-end call) ------------------------------------
  * residues: all sequences back to back; sequence s is residues[seq_off[s] .. seq_off[s+1]).
  * pair p aligns query pair_q[p] against template pair_t[p].

@@ -66,6 +66,11 @@ typedef struct {
   const float* sim;
   float* D;
   int *pq, *pt;
+  /* tabulated gap model (orc_fill_tab): any Evaluator whose deletion() ignores the query positions and whose
+   * insertion() sees the query only through q_pos2-q_pos1 away from the Head/Tail (hmap_eval.h:63-117,
+   * gn2_eval.h:99-158, aasubalib.h:27-77 all do).  NULL = the affine model of sc.                          */
+  const float* del_tab; /* sz2*sz2:  [t_pos1*sz2 + t_pos2] = deletion(.,.,t_pos1,t_pos2), t_pos1 < t_pos2 */
+  const float* ins_tab; /* sz1*sz2:  [(q_pos2-q_pos1-1)*sz2 + t_pos2] = insertion(q_pos1,q_pos2,t_pos2-1,t_pos2) */
 } flow_t;
 
 static int rowof(const flow_t* f, int a) { return f->rev ? f->mq1 - a : f->q0 + a; }
@@ -75,10 +80,14 @@ static size_t at(const flow_t* f, int a, int b) { return (size_t)rowof(f, a) * f
 /* gap between flow columns b0 < b1 (deletion) / flow rows a0 < a1 (insertion) */
 static float gdel(const flow_t* f, int b0, int b1) {
   int x = colof(f, b0), y = colof(f, b1);
+  if (f->del_tab) return f->del_tab[(size_t)(x < y ? x : y) * f->sz2 + (x < y ? y : x)];
   return orc_deletion(f->sc, f->sz2, x < y ? x : y, x < y ? y : x);
 }
-static float gins(const flow_t* f, int a0, int a1) {
+/* b = flow column of the cell that takes the gap: the insertion is evaluated between the template positions
+ * (j-1, j) in the forward fill (dpmatrix.h:473) and (j, j+1) in the reverse fill (dpmatrix.h:812)           */
+static float gins(const flow_t* f, int a0, int a1, int b) {
   int x = rowof(f, a0), y = rowof(f, a1);
+  if (f->ins_tab) return f->ins_tab[(size_t)(a1 - a0 - 1) * f->sz2 + (f->rev ? colof(f, b) + 1 : colof(f, b))];
   return orc_insertion(f->sc, f->sz1, x < y ? x : y, x < y ? y : x);
 }
 static float clampl(const flow_t* f, float s) { /* dpmatrix.h:580 etc.: s = max(0.f,s) */
@@ -104,6 +113,7 @@ static int flow_init(flow_t* f, const uint8_t* q, int Lq, const uint8_t* t, int 
   f->t1 = f->sz2 - 1;
   f->local = (sc->align_type == ORC_LOCAL); /* dpmatrix.h:155 */
   f->sc = sc;
+  f->del_tab = f->ins_tab = 0;
   f->sim = sim;
   f->D = score;
   f->pq = prev_q;
@@ -131,7 +141,7 @@ static int degenerate(flow_t* f) {
   }
   if (f->t1 == 1) {
     s = f->D[at(f, 0, 0)];
-    s -= gins(f, 0, f->q1);
+    s -= gins(f, 0, f->q1, f->t1);
     s += f->sim[at(f, f->q1, f->t1)];
     set_tb(f, f->q1, f->t1, 0, 0, s);
     return 1;
@@ -152,7 +162,7 @@ static void boundary(flow_t* f) {
   }
   for (int a = 2; a < f->q1; ++a) {
     s = s0;
-    s -= gins(f, 0, a);
+    s -= gins(f, 0, a, 1);
     s += f->sim[at(f, a, 1)];
     set_tb(f, a, 1, 0, 0, clampl(f, s));
   }
@@ -173,7 +183,7 @@ static void final_cell(flow_t* f, int repro_rev_bug) {
   }
   for (int k = 1; k < q1; ++k) {
     s = f->D[at(f, k, t1 - 1)];
-    s -= gins(f, k, q1);
+    s -= gins(f, k, q1, t1);
     s += simf;
     s = clampl(f, s);
     if (s > os) { oa = k; ob = t1 - 1; os = s; from_col = 1; }
@@ -186,16 +196,10 @@ static void final_cell(flow_t* f, int repro_rev_bug) {
 
 /* ---------------------------------------------------------------- literal O(n^3) fill */
 
-int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
-             int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
-             float* sim_out) {
-  if (Lq < 0 || Lt < 0) return 1;
-  flow_t f;
-  size_t n = (size_t)(Lq + 2) * (Lt + 2);
-  float* sim = sim_out ? sim_out : (float*)malloc(sizeof(float) * n);
-  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
-  /* dpmatrix.h:306-307: both corner scores are zeroed; bounds check :360 */
-  if (f.q1 <= 0 || f.t1 <= 0) { if (!sim_out) free(sim); return 1; }
+static void literal_fill(flow_t* fp, int repro_rev_bug) {
+  flow_t f = *fp;
+  const float* sim = f.sim;
+  float* score = f.D;
   if (!degenerate(&f)) {
     boundary(&f);
     for (int a = 2; a < f.q1; ++a) {
@@ -212,7 +216,7 @@ int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scori
         }
         for (int k = 1; k < a - 1; ++k) {                     /* insertions, :471-480 */
           s = score[at(&f, k, b - 1)];
-          s -= gins(&f, k, a);
+          s -= gins(&f, k, a, b);
           s += simc;
           s = clampl(&f, s);
           if (s > os) { oa = k; ob = b - 1; os = s; }
@@ -222,7 +226,51 @@ int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scori
     }
     final_cell(&f, repro_rev_bug);
   }
+}
+
+int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
+             int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
+             float* sim_out) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  size_t n = (size_t)(Lq + 2) * (Lt + 2);
+  float* sim = sim_out ? sim_out : (float*)malloc(sizeof(float) * n);
+  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
+  /* dpmatrix.h:306-307: both corner scores are zeroed; bounds check :360 */
+  if (f.q1 <= 0 || f.t1 <= 0) { if (!sim_out) free(sim); return 1; }
+  literal_fill(&f, repro_rev_bug);
   if (!sim_out) free(sim);
+  return 0;
+}
+
+/* The same literal fill for ANY evaluator, described by what the fill asks of it: the similarity matrix
+ * (simmatrix.h:40-73) and the two gap functions tabulated over every argument combination dpmatrix.h:356-1030
+ * can pass (see flow_t).                                                                                   */
+int orc_fill_tab(const float* sim, int Lq, int Lt, const float* del_tab, const float* ins_tab, int is_local,
+                 int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  f.rev = (direction == ORC_REV);
+  f.sz1 = Lq + 2;
+  f.sz2 = Lt + 2;
+  f.q0 = f.t0 = 0;
+  f.mq1 = f.q1 = f.sz1 - 1;
+  f.mt1 = f.t1 = f.sz2 - 1;
+  f.local = is_local;
+  f.sc = 0;
+  f.del_tab = del_tab;
+  f.ins_tab = ins_tab;
+  f.sim = sim;
+  f.D = score;
+  f.pq = prev_q;
+  f.pt = prev_t;
+  size_t n = (size_t)f.sz1 * f.sz2;
+  for (size_t o = 0; o < n; ++o) {
+    score[o] = 0.f;
+    prev_q[o] = ORC_NULL;
+    prev_t[o] = ORC_NULL;
+  }
+  literal_fill(&f, repro_rev_bug);
   return 0;
 }
 
@@ -264,7 +312,7 @@ int orc_fill_sub(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_s
         }
         for (int k = 1; k < a - 1; ++k) {
           s = score[at(&f, k, b - 1)];
-          s -= gins(&f, k, a);
+          s -= gins(&f, k, a, b);
           s += simc;
           s = clampl(&f, s);
           if (s > os) { oa = k; ob = b - 1; os = s; }
@@ -317,13 +365,13 @@ int orc_fill_fast(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_
           int kn = a - 2, ko = colorg[b - 1];
           if (ko == 0) ko = kn;
           else {
-            float ext = score[at(&f, ko, b - 1)] - gins(&f, ko, a);
-            float opn = score[at(&f, kn, b - 1)] - gins(&f, kn, a);
+            float ext = score[at(&f, ko, b - 1)] - gins(&f, ko, a, b);
+            float opn = score[at(&f, kn, b - 1)] - gins(&f, kn, a, b);
             if (opn > ext) ko = kn;
           }
           colorg[b - 1] = ko;
           s = score[at(&f, ko, b - 1)];
-          s -= gins(&f, ko, a);
+          s -= gins(&f, ko, a, b);
           s += simc;
           s = clampl(&f, s);
           if (s > os) { oa = ko; ob = b - 1; os = s; }

@@ -44,6 +44,12 @@ int orc_fill(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scori
              int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t,
              float* sim_out);
 
+/* The literal fill for ANY Evaluator (evaluator.h:20-147) described by tables: sim = (Lq+2)*(Lt+2) similarity
+ * matrix; del_tab[t1*sz2+t2] = deletion(.,.,t1,t2); ins_tab[(q2-q1-1)*sz2 + t2] = insertion(q1,q2,t2-1,t2).
+ * Covers hmap_eval.h:63-117 and gn2_eval.h:99-158 style position-dependent gap penalties.                  */
+int orc_fill_tab(const float* sim, int Lq, int Lt, const float* del_tab, const float* ins_tab, int is_local,
+                 int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t);
+
 /* build_subdpm + the 9-argument constructor (dpmatrix.h:169-189, 319-353): the literal fill between the
  * anchors (q1_end,t1_end) and (q2_beg,t2_beg) (matrix indices), everything else left at the DPCell defaults. */
 int orc_fill_sub(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,

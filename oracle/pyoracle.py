@@ -98,6 +98,25 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return score, pq, pt
 
+    @staticmethod
+    def fill_tab(sim, del_tab, ins_tab, is_local=False, direction=FWD, repro_rev_bug=True):
+        """orc_fill_tab: the literal fill for any evaluator given as tables (see aadp_oracle.h)."""
+        build()
+        lib = C.CDLL(LIB_ORACLE)
+        sim = np.ascontiguousarray(sim, np.float32)
+        del_tab = np.ascontiguousarray(del_tab, np.float32)
+        ins_tab = np.ascontiguousarray(ins_tab, np.float32)
+        sz1, sz2 = sim.shape
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        rc = lib.orc_fill_tab(_p(sim, C.c_float), sz1 - 2, sz2 - 2, _p(del_tab, C.c_float), _p(ins_tab, C.c_float),
+                              int(bool(is_local)), direction, int(repro_rev_bug), _p(score, C.c_float), _p(pq, C.c_int),
+                              _p(pt, C.c_int))
+        if rc:
+            raise RuntimeError("Illegal bounds building DPM")
+        return score, pq, pt
+
     def sim(self, q, t):
         q = np.asarray(q, dtype=np.int64)
         t = np.asarray(t, dtype=np.int64)
@@ -139,6 +158,99 @@ class Oracle:
                                    _p(np.ascontiguousarray(sim), C.c_float), C.c_float(thr),
                                    C.c_long(max_alignments), _p(mark, C.c_uint8))
         return mark, n
+
+
+def reference_fill_tab(sim, del_tab, ins_tab, is_local=False, direction=FWD):
+    """The REAL reference fill (libaadp_ref.so, ref_fill_tab) driven by a table-backed Evaluator."""
+    build()
+    if not os.path.exists(LIB_REF):
+        raise FileNotFoundError(LIB_REF)
+    lib = C.CDLL(LIB_REF)
+    lib.ref_last_error.restype = C.c_char_p
+    sim = np.ascontiguousarray(sim, np.float32)
+    del_tab = np.ascontiguousarray(del_tab, np.float32)
+    ins_tab = np.ascontiguousarray(ins_tab, np.float32)
+    sz1, sz2 = sim.shape
+    score = np.zeros((sz1, sz2), np.float32)
+    pq = np.zeros((sz1, sz2), np.int32)
+    pt = np.zeros((sz1, sz2), np.int32)
+    rc = lib.ref_fill_tab(sz1 - 2, sz2 - 2, _p(sim, C.c_float), _p(del_tab, C.c_float), _p(ins_tab, C.c_float),
+                          int(bool(is_local)), direction, _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int))
+    if rc:
+        raise RuntimeError(lib.ref_last_error().decode())
+    return score, pq, pt
+
+
+def hmap_like_tables(rng, Lq, Lt, align_type, dyadic=False):
+    """Tables of an evaluator shaped like hmap_eval.h:63-117: per-template-position gap_init/gap_extn, a gap between
+    t1 and t2 costs min(gi[t1],gi[t2]) + min(ge[t1],ge[t2])*(dist-2) -- for deletions AND insertions (the insertion
+    takes its parameters from the two template positions it sits between) -- with the free end gaps of the align type;
+    similarity is position specific (a profile score)."""
+    sz1, sz2 = Lq + 2, Lt + 2
+    f32 = np.float32
+    if dyadic:
+        gi = (rng.integers(16, 64, sz2) / 4.0).astype(f32)
+        ge = (rng.integers(1, 12, sz2) / 4.0).astype(f32)
+        sim = (rng.integers(-16, 28, (sz1, sz2)) / 2.0).astype(f32)
+    else:
+        gi = rng.uniform(3, 14, sz2).astype(f32)
+        ge = rng.uniform(0.1, 2.5, sz2).astype(f32)
+        sim = rng.normal(0.3, 3.0, (sz1, sz2)).astype(f32)
+    sim[0, :] = sim[-1, :] = 0
+    sim[:, 0] = sim[:, -1] = 0
+    del_free = align_type in (LOCAL, SEMI_LOCAL, LOCAL_GLOBAL)
+    ins_free = align_type in (LOCAL, SEMI_LOCAL, GLOBAL_LOCAL)
+    dt = np.zeros((sz2, sz2), f32)
+    for t1 in range(sz2):
+        for t2 in range(t1 + 2, sz2):
+            if del_free and (t1 == 0 or t2 == sz2 - 1):
+                continue
+            dt[t1, t2] = f32(min(gi[t1], gi[t2]) + f32(min(ge[t1], ge[t2]) * f32(t2 - t1 - 2)))
+    it = np.zeros((sz1 - 1, sz2), f32)
+    for ln in range(1, sz1 - 1):
+        for t2 in range(1, sz2):
+            if ins_free and (t2 == 1 or t2 == sz2 - 1):   # q1 is the Head / q2 is the Tail for these columns
+                continue
+            it[ln, t2] = f32(min(gi[t2 - 1], gi[t2]) + f32(min(ge[t2 - 1], ge[t2]) * f32(ln - 1)))
+    return sim, dt, it
+
+
+def gn2_like_tables(rng, Lq, Lt, align_type):
+    """Tables of an evaluator shaped like gn2_eval.h:99-158: deletions from a pairwise table (8100 beyond a distance
+    cutoff, else gi[p2][p1] + ge[p2][p1]*(di-2) + cd[p2][p1]), insertions from per-position vectors
+    v_gi[t1] + v_ge[t1]*(di-2) + v_cn[t1]."""
+    sz1, sz2 = Lq + 2, Lt + 2
+    f32 = np.float32
+    sim = rng.normal(0.2, 2.5, (sz1, sz2)).astype(f32)
+    sim[0, :] = sim[-1, :] = 0
+    sim[:, 0] = sim[:, -1] = 0
+    del_free = align_type in (LOCAL, SEMI_LOCAL, LOCAL_GLOBAL)
+    ins_free = align_type in (LOCAL, SEMI_LOCAL, GLOBAL_LOCAL)
+    dist = rng.uniform(3, 30, (sz2, sz2)).astype(f32)
+    vgi = rng.uniform(4, 12, (sz2, sz2)).astype(f32)
+    vge = rng.uniform(0.2, 1.5, (sz2, sz2)).astype(f32)
+    vcd = rng.uniform(0, 3, (sz2, sz2)).astype(f32)
+    dt = np.zeros((sz2, sz2), f32)
+    for t1 in range(sz2):
+        for t2 in range(t1 + 2, sz2):
+            if del_free and (t1 == 0 or t2 == sz2 - 1):
+                continue
+            p1, p2 = t1, t2 - 2
+            gp = f32(8100.0)
+            if dist[p2, p1] < 18.0:
+                gp = f32(f32(vgi[p2, p1] + f32(vge[p2, p1] * f32(t2 - t1 - 2))) + vcd[p2, p1])
+            dt[t1, t2] = gp
+    wgi = rng.uniform(4, 12, sz2).astype(f32)
+    wge = rng.uniform(0.2, 1.5, sz2).astype(f32)
+    wcn = rng.uniform(0, 4, sz2).astype(f32)
+    it = np.zeros((sz1 - 1, sz2), f32)
+    for ln in range(1, sz1 - 1):
+        for t2 in range(1, sz2):
+            if ins_free and (t2 == 1 or t2 == sz2 - 1):
+                continue
+            t1 = t2 - 1
+            it[ln, t2] = f32(f32(wgi[t1] + f32(wge[t1] * f32(ln - 1))) + wcn[t1])
+    return sim, dt, it
 
 
 def write_matrix_file(path, alphabet, sub):

@@ -48,6 +48,28 @@
 typedef AASubstitutionEval<AASequence, AASequence> AAEval;
 typedef DPMatrix<AASequence, AASequence, AAEval> AADPM;
 
+// A table-driven Evaluator (evaluator.h:20-147): the three scoring functions read what the caller tabulated, so the
+// reference's own fill (dpmatrix.h:356-1030) can be driven with position-dependent gap models shaped like
+// hmap_eval.h:63-117 / gn2_eval.h:99-158 (which cannot compile here: Troll is not vendored).
+class TableEval : public Evaluator<AASequence, AASequence, TableEval> {
+ public:
+  TableEval(const float* sim_, const float* del_, const float* ins_, int sz2_) : sim(sim_), del(del_), ins(ins_), sz2(sz2_) {}
+  float similarity(const AASequence&, const AASequence&, int q_pos, int t_pos) const { return sim[(size_t)q_pos * sz2 + t_pos]; }
+  float deletion(const AASequence&, const AASequence&, int, int, int t_pos1, int t_pos2) const {
+    return del[(size_t)t_pos1 * sz2 + t_pos2];
+  }
+  float insertion(const AASequence&, const AASequence&, int q_pos1, int q_pos2, int, int t_pos2) const {
+    return ins[(size_t)(q_pos2 - q_pos1 - 1) * sz2 + t_pos2];
+  }
+  void pre_calculate(const AASequence&, const AASequence&) const {}
+  void post_process(SimilarityMatrix&) const {}
+
+ private:
+  const float *sim, *del, *ins;
+  int sz2;
+};
+typedef DPMatrix<AASequence, AASequence, TableEval> TabDPM;
+
 namespace {
 
 thread_local std::string g_err;
@@ -109,6 +131,35 @@ int ref_fill(const char* q, const char* t, const char* matrix_file, float gi, fl
         if (prev_q) prev_q[o] = c->prev_query_idx;
         if (prev_t) prev_t[o] = c->prev_template_idx;
         if (sim) sim[o] = dpm.getSim(i, j);
+      }
+    return 0;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
+// The reference fill driven by TableEval: sim (Lq+2)*(Lt+2), del_tab (Lt+2)^2, ins_tab (Lq+1)*(Lt+2) as in
+// include/aadp.h (aadp_fill_pair_tabulated).  align_type only selects local vs. global fills (dpmatrix.h:155).
+int ref_fill_tab(int Lq, int Lt, const float* sim, const float* del_tab, const float* ins_tab, int is_local,
+                 int direction, float* score, int* prev_q, int* prev_t) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, std::string((size_t)Lq, 'A').c_str());
+    make_seq(ts, std::string((size_t)Lt, 'A').c_str());
+    TableEval ev(sim, del_tab, ins_tab, Lt + 2);
+    TabDPM dpm(qs, ts, ev, static_cast<direction_t>(direction), is_local ? local : global);
+    int sz1 = dpm.getQuerySize(), sz2 = dpm.getTemplateSize();
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) {
+        const DPCell* c = dpm.getCell(i, j);
+        size_t o = (size_t)i * sz2 + j;
+        if (score) score[o] = c->score;
+        if (prev_q) prev_q[o] = c->prev_query_idx;
+        if (prev_t) prev_t[o] = c->prev_template_idx;
       }
     return 0;
   } catch (std::string& e) {

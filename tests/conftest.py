@@ -36,3 +36,10 @@ def golden_sub():
     # reference outputs of the 9-argument constructor / build_subdpm (oracle/gen_golden_sub.py)
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_sub.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_tab():
+    # reference fills driven by a table-backed Evaluator with position-dependent gaps (oracle/gen_golden_tab.py)
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_tab.npz"))

@@ -629,6 +629,46 @@ def test_sub_rectangle_batch_golden_and_random(golden_sub, blosum):
     c.close()
 
 
+def test_tabulated_gap_model_golden_and_random(golden_tab):
+    # aadp_fill_pair_tabulated (row f3): position-dependent gap penalties (hmap_eval.h:63-117 / gn2_eval.h:99-158 shaped)
+    # through the exact general-gap kernel; golden = the REAL reference fill driven by a table-backed Evaluator
+    import alignment_algos_b200 as a
+    g = golden_tab
+    c = a.Context(0)   # no aadp_set_scoring needed
+    for name in golden_cases(g):
+        for d, tag in ((a.FWD, "fwd"), (a.REV, "rev")):
+            s, pq, pt = c.fill_pair_tabulated(g[name + ".sim"], g[name + ".del"], g[name + ".ins"], int(g[name + ".local"]), d)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+    rng = np.random.default_rng(61)
+    for at in (po.GLOBAL, po.SEMI_LOCAL, po.LOCAL):
+        for gen, (Lq, Lt) in ((po.hmap_like_tables, (130, 97)), (po.gn2_like_tables, (64, 150)), (po.hmap_like_tables, (3, 600))):
+            sim, dt, it = gen(rng, Lq, Lt, at)
+            for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+                got = c.fill_pair_tabulated(sim, dt, it, at == po.LOCAL, d)
+                want = po.Oracle.fill_tab(sim, dt, it, at == po.LOCAL, od)
+                for x, y, nm in zip(got, want, ("score", "pq", "pt")):
+                    assert_matrix_equal("tab %s" % nm, x, y)
+    # the affine model written as tables is the ordinary path (ties the table layout to aadp_fill_pair_general)
+    sim, dt, it = po.hmap_like_tables(rng, 30, 41, po.GLOBAL)
+    gi, ge = np.float32(4.73), np.float32(0.34)
+    for t1 in range(43):
+        for t2 in range(t1 + 2, 43):
+            dt[t1, t2] = np.float32(gi + np.float32(ge * np.float32(t2 - t1 - 2)))
+    for ln in range(1, 31):
+        it[ln, 1:] = np.float32(gi + np.float32(ge * np.float32(ln - 1)))
+    s1, q1, t1_ = c.fill_pair_tabulated(sim, dt, it, False, a.FWD)
+    s2, q2, t2_ = c.fill_pair_general(sim, 4.73, 0.34, po.GLOBAL, a.FWD)
+    assert_matrix_equal("affine tables score", s1, s2)
+    assert_matrix_equal("affine tables pq", q1, q2)
+    bad = dt.copy()
+    bad[4, 5] = 1.0
+    with pytest.raises(a.AadpError):
+        c.fill_pair_tabulated(sim, bad, it, False, a.FWD)   # adjacent positions must cost nothing
+    c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a

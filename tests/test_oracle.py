@@ -165,3 +165,54 @@ def test_oracle_sub_rectangle_fill_matches_reference_random(blosum):
                     assert_matrix_equal("score", s, rs)
                     assert_matrix_equal("pq", pq, rq)
                     assert_matrix_equal("pt", pt, rt)
+
+
+def test_oracle_tabulated_gap_fill_matches_golden(golden_tab):
+    # position-dependent gap models (hmap_eval.h:63-117 / gn2_eval.h:99-158 shaped) through the table-driven fill
+    g = golden_tab
+    for name in golden_cases(g):
+        for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+            s, pq, pt = po.Oracle.fill_tab(g[name + ".sim"], g[name + ".del"], g[name + ".ins"], int(g[name + ".local"]), d)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_tabulated_gap_fill_matches_reference_random(blosum):
+    rng = np.random.default_rng(29)
+    for at in MODES:
+        for gen in (po.hmap_like_tables, po.gn2_like_tables):
+            for trial in range(4):
+                Lq, Lt = int(rng.integers(0, 45)), int(rng.integers(0, 45))
+                sim, dt, it = gen(rng, Lq, Lt, at)
+                for d in (po.FWD, po.REV):
+                    want = po.reference_fill_tab(sim, dt, it, at == po.LOCAL, d)
+                    got = po.Oracle.fill_tab(sim, dt, it, at == po.LOCAL, d)
+                    for a, b, nm in zip(got, want, ("score", "pq", "pt")):
+                        assert_matrix_equal(nm, a, b)
+    # tables tabulated from the affine AASubstitutionEval model reproduce the ordinary reference fill
+    alpha, M = blosum
+    for at in MODES:
+        gi, ge = 4.73, 0.34
+        O = po.Oracle(M, gi, ge, at)
+        R = po.Reference(alpha, M, gi, ge, at)
+        q, t = rand_pair(rng, 27, 22)
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        dt = np.zeros((sz2, sz2), np.float32)
+        it = np.zeros((sz1 - 1, sz2), np.float32)
+        f32 = np.float32
+        pen = lambda ln: f32(f32(gi) + f32(f32(ge) * f32(ln - 1)))
+        dfree = at in (po.LOCAL, po.SEMI_LOCAL, po.LOCAL_GLOBAL)
+        ifree = at in (po.LOCAL, po.SEMI_LOCAL, po.GLOBAL_LOCAL)
+        for t1 in range(sz2):
+            for t2 in range(t1 + 2, sz2):
+                dt[t1, t2] = 0 if (dfree and (t1 == 0 or t2 == sz2 - 1)) else pen(t2 - t1 - 1)
+        for ln in range(1, sz1 - 1):
+            for t2 in range(1, sz2):
+                it[ln, t2] = 0 if (ifree and (t2 == 1 or t2 == sz2 - 1)) else pen(ln)
+        for d in (po.FWD, po.REV):
+            want = R.fill(q, t, d)
+            got = po.Oracle.fill_tab(O.sim(q, t), dt, it, at == po.LOCAL, d)
+            for a, b, nm in zip(got, want[:3], ("score", "pq", "pt")):
+                assert_matrix_equal("affine-as-table " + nm, a, b)
