@@ -121,14 +121,19 @@ class DPMatrix {
       }
   }
 
+  // Evaluators with a DeviceScoring mapping (aadp_binding.h) are described as residues + table + affine gaps;
+  // every other Etype runs through the tabulated gap model (build_tabulated below).
+  template <bool B>
+  struct mapped_tag {};
   void describe(std::string* alphabet, std::vector<float>* sub, float* gi, float* ge, int* at) const {
-    if (!aadp::DeviceScoring<Etype>::supported)
-      throw std::string("DPMatrix: this Evaluator has no device scoring model (only AASubstitutionEval is mapped)");
-    describe_impl(alphabet, sub, gi, ge, at, aadp::DeviceScoring<Etype>());
+    describe_impl(alphabet, sub, gi, ge, at, mapped_tag<aadp::DeviceScoring<Etype>::supported>());
   }
-  template <class DS>
-  void describe_impl(std::string* alphabet, std::vector<float>* sub, float* gi, float* ge, int* at, DS) const {
-    DS::describe(static_cast<const Etype&>(*evaluator), alphabet, sub, gi, ge, at);
+  void describe_impl(std::string* alphabet, std::vector<float>* sub, float* gi, float* ge, int* at, mapped_tag<true>) const {
+    aadp::DeviceScoring<Etype>::describe(static_cast<const Etype&>(*evaluator), alphabet, sub, gi, ge, at);
+  }
+  void describe_impl(std::string*, std::vector<float>*, float*, float*, int*, mapped_tag<false>) const {
+    throw std::string("DPMatrix: this Evaluator has no residue/affine device mapping (sub-rectangles and the near-optimal "
+                      "cell set need one; whole-matrix fills of any Evaluator use the tabulated gap model)");
   }
 
   // dpmatrix.h:291-317
@@ -140,7 +145,60 @@ class DPMatrix {
 
     const int sz1 = getQuerySize(), sz2 = getTemplateSize();
     if (sz1 < 2 || sz2 < 2) throw std::string("Illegal bounds building DPM");  // dpmatrix.h:360-361
+    build_fill(mapped_tag<aadp::DeviceScoring<Etype>::supported>());
+    nearopt_delta = -1.f;
+  }
 
+  // ANY Evaluator: the fill sees an Evaluator only through similarity(i,j),
+  // deletion(q,q+1,t1,t2) and insertion(q1,q2,t2-1,t2) (dpmatrix.h:356-1030); tabulate the three on the host over every
+  // argument combination the fill can pass and run the reference's own scan over the tables on the GPU
+  // (aadp_fill_pair_tabulated).  Position-dependent gap penalties (hmap_eval.h:63-117, gn2_eval.h:99-158) are covered.
+  // The tables assume what every reference evaluator satisfies -- deletion ignores the query positions, insertion sees
+  // the query only through q2-q1 away from the Head/Tail -- and the assumption is spot-checked here, loudly.
+  void build_fill(mapped_tag<false>) {
+    const int sz1 = getQuerySize(), sz2 = getTemplateSize(), Lq = sz1 - 2, Lt = sz2 - 2;
+    const S1& q = *query_seq;
+    const S2& t = *templ_seq;
+    const Evaluator<S1, S2, Etype>& ev = *evaluator;
+    std::vector<float> sim((size_t)sz1 * sz2), del((size_t)sz2 * sz2, 0.f), ins((size_t)(Lq + 1) * sz2, 0.f);
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) sim[(size_t)i * sz2 + j] = (*simmatrix)(i, j);
+    for (int t1 = 0; t1 < sz2; ++t1)
+      for (int t2 = t1 + 1; t2 < sz2; ++t2) {
+        // query positions as the fill passes them: boundary row (0,1), final cell (Lq,Lq+1), interior (i-1,i)
+        const int qa = t1 == 0 ? 0 : (t2 == sz2 - 1 ? Lq : (Lq >= 1 ? 1 : 0));
+        const float v = ev.deletion(q, t, qa, qa + 1, t1, t2);
+        del[(size_t)t1 * sz2 + t2] = v;
+        if (t1 > 0 && t2 < sz2 - 1 && Lq >= 3 && ((t1 * 31 + t2) % 7 == 0) && ev.deletion(q, t, Lq - 1, Lq, t1, t2) != v)
+          throw std::string("DPMatrix: deletion() of this Evaluator depends on the query position; no device mapping");
+      }
+    for (int len = 0; len <= Lq; ++len)
+      for (int t2 = 1; t2 < sz2; ++t2) {
+        float v = 0.f;
+        if (t2 == 1) v = ev.insertion(q, t, 0, len + 1, 0, 1);                              // Head: dpmatrix.h:421, 861
+        else if (t2 == sz2 - 1) v = ev.insertion(q, t, Lq - len, Lq + 1, sz2 - 2, sz2 - 1);  // Tail: dpmatrix.h:520, 759
+        else if (len + 2 <= Lq) {
+          v = ev.insertion(q, t, 1, len + 2, t2 - 1, t2);                                    // interior: dpmatrix.h:473, 812
+          if (len + 3 <= Lq && ((len * 31 + t2) % 7 == 0) && ev.insertion(q, t, 2, len + 3, t2 - 1, t2) != v)
+            throw std::string("DPMatrix: insertion() of this Evaluator depends on the query position; no device mapping");
+        }
+        ins[(size_t)len * sz2 + t2] = v;
+      }
+    aadp_ctx* ctx = aadp::default_context();
+    const size_t n = (size_t)sz1 * sz2;
+    std::vector<float> score(n);
+    std::vector<int32_t> pq(n), pt(n);
+    aadp::check(aadp_fill_pair_tabulated(ctx, sim.data(), Lq, Lt, del.data(), ins.data(), islocal ? 1 : 0, AADP_REPRO_REV_BUG,
+                                         direction == fwd ? AADP_FWD : AADP_REV, score.data(), pq.data(), pt.data()));
+    for (int i = 0; i < sz1; ++i)
+      for (int j = 0; j < sz2; ++j) {
+        const size_t o = (size_t)i * sz2 + j;
+        (*dpmatrix)(i, j).setTB(pq[o], pt[o], score[o]);
+      }
+  }
+
+  void build_fill(mapped_tag<true>) {
+    const int sz1 = getQuerySize(), sz2 = getTemplateSize();
     std::string alphabet;
     std::vector<float> sub;
     float gi, ge;

@@ -128,3 +128,29 @@ def test_unmodified_reference_with_gpu_fill_enumerates_the_same_alignments(at):
         assert got.stdout == want.stdout, "GPU-filled reference and pure reference print different results"
         n_alignments += sum(1 for l in got.stdout.splitlines() if l.startswith(("UCW ", "CNO ")))
     assert at == po.LOCAL or n_alignments > 10
+
+
+TAB_DEMO = os.path.join(CXX, "tabeval_demo")
+TAB_REF = os.path.join(CXX, "tabeval_ref")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("at", MODES, ids=[MODE_NAMES[m] for m in MODES])
+def test_user_evaluator_with_positional_gaps_equals_reference_build(at):
+    # tests/cxx/tabeval_demo.cpp: a user-defined Evaluator whose gap penalties depend on the template position
+    # (hmap_eval.h:63-117 / gn2_eval.h:99-158 shaped).  hmap2::DPMatrix tabulates it and fills on the GPU
+    # (aadp_fill_pair_tabulated); the unmodified reference fills on the CPU.  Same source, identical output.
+    if not (os.path.exists(TAB_DEMO) and os.path.exists(TAB_REF)):
+        pytest.skip("tabeval demos not built")
+    rng = np.random.default_rng(70 + at)
+    for style in (1, 2):
+        for (gi, ge, Lq, Lt) in [(4.73, 0.34, 33, 47), (7.1, 0.9, 5, 1), (10, 0.5, 80, 75)]:
+            q = rng.integers(0, 20, Lq).astype(np.uint8)
+            t = rng.integers(0, 20, Lt).astype(np.uint8)
+            args = [MATRIX, str(at), str(gi), str(ge), str(style), _letters(q), _letters(t)]
+            got = subprocess.run([TAB_DEMO] + args, capture_output=True, text=True, timeout=120)
+            ref = subprocess.run([TAB_REF] + args, capture_output=True, text=True, timeout=300)
+            assert ref.returncode == 0, ref.stdout[-300:] + ref.stderr[-300:]
+            assert got.returncode == 0, got.stdout[-300:] + got.stderr[-300:]
+            assert len(ref.stdout.splitlines()) == 2 * (Lq + 2) * (Lt + 2) + 1
+            assert got.stdout == ref.stdout, "style %d %dx%d: GPU tabulated fill differs from the reference build" % (style, Lq, Lt)
