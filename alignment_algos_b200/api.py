@@ -260,6 +260,28 @@ class Context:
         self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), _ptr(pairs), int(off[-1]), _ptr(n), _ptr(st)))
         return off, pairs, n, st
 
+    def near_optimal(self, pair_ids, delta_ratio, max_alignments):
+        """UnconstrainedNearOptimal::enumerate (ucw.h:63-191, before sortSet) of the listed pairs on the GPU.
+        Returns a list (one entry per listed pair) of (status, threshold, [(score, pairs[(len,2)]) in depth-first order])."""
+        ids = np.ascontiguousarray(pair_ids, np.int64)
+        n, K = len(ids), int(max_alignments)
+        off = np.zeros(n + 1, np.int64)
+        self._ck(self.L.aadp_batch_near_optimal(self.h, _ptr(ids), n, delta_ratio, K, None, None, None, None, _ptr(off),
+                                                None, 0, None))
+        n_ali, st = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        scores, ln = np.zeros((n, K), np.float32), np.zeros((n, K), np.int32)
+        paths = np.zeros((max(int(off[-1]), 1), 2), np.int32)
+        thr = np.zeros(n, np.float32)
+        self._ck(self.L.aadp_batch_near_optimal(self.h, _ptr(ids), n, delta_ratio, K, _ptr(n_ali), _ptr(st), _ptr(scores),
+                                                _ptr(ln), _ptr(off), _ptr(paths), int(off[-1]), _ptr(thr)))
+        out = []
+        for k in range(n):
+            slot = (off[k + 1] - off[k]) // K
+            alis = [(float(scores[k, a]), paths[off[k] + a * slot: off[k] + a * slot + ln[k, a]].copy())
+                    for a in range(n_ali[k])]
+            out.append((int(st[k]), float(thr[k]), alis))
+        return out
+
     def fetch_tb(self, p, direction, Lq, Lt):
         nbytes = max(int(self.L.aadp_batch_tb_bytes(self.h, p)), 1)
         tb = np.zeros(nbytes, np.uint8)

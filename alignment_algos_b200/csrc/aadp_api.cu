@@ -5,6 +5,7 @@
 #include "aadp_kernels.cuh"
 #include "aadp_packed.cuh"
 #include "aadp_general.cuh"
+#include "aadp_enum.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -157,6 +158,7 @@ struct aadp_ctx {
   float last_delta = -1.f;
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
+  DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -1010,7 +1012,8 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p};
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
+                   &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -2127,6 +2130,86 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)np] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)np] * 8; }
   if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
   if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, float delta_ratio, int32_t max_alignments,
+                            int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len, int64_t* path_off, int32_t* paths,
+                            int64_t paths_cap, float* threshold) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (n < 0 || (n && !pair_ids)) return fail("null input");
+  if (max_alignments < 1) return fail("max_alignments must be positive");
+  if (c->float_mode) return fail("aadp_batch_near_optimal: exact-float mode keeps no resident score matrices (enumerate on the host over aadp_batch_fetch_pair)");
+  if (c->sc.local) return fail("aadp_batch_near_optimal: not for local alignments");
+  if (!(b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
+  if (!(b.ran_what & (AADP_W_SCORES | AADP_W_MASK))) return fail("score matrices were not kept (run with AADP_W_SCORES or AADP_W_MASK)");
+  std::vector<int64_t> poff((size_t)n + 1, 0), soff((size_t)n + 1, 0);
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t p = pair_ids[k];
+    if (p < 0 || p >= b.npairs) return fail("pair index out of range");
+    const int64_t Lq = b.seq_off[b.pair_q[p] + 1] - b.seq_off[b.pair_q[p]];
+    poff[(size_t)k + 1] = poff[(size_t)k] + (int64_t)max_alignments * (Lq + 2);  // an alignment has at most Lq+2 pairs
+    soff[(size_t)k + 1] = soff[(size_t)k] + (Lq + 2);
+  }
+  if (path_off) memcpy(path_off, poff.data(), (size_t)(n + 1) * 8);
+  if (n == 0 || (!n_ali && !status && !scores && !ali_len && !paths && !threshold)) return 0;
+  if (paths && paths_cap < poff[(size_t)n]) return fail("aadp_batch_near_optimal: paths buffer too small (needs 2*path_off[n] ints)");
+  CK(cudaStreamSynchronize(c->stream));
+  if (pin_reserve(c, (size_t)(n + 1) * 24 + 4096)) return 1;
+  std::vector<int64_t> ids(pair_ids, pair_ids + n);
+  if (upload_vec(c, c->ucw_ids, ids) || upload_vec(c, c->ucw_path_off, poff) || upload_vec(c, c->ucw_stack_off, soff)) return 1;
+  if (c->ucw_paths.reserve(std::max<size_t>((size_t)poff[(size_t)n] * 8, 16)) || c->ucw_stack.reserve(std::max<size_t>((size_t)soff[(size_t)n] * 16, 16)) ||
+      c->ucw_len.reserve((size_t)n * max_alignments * 4) || c->ucw_scores.reserve((size_t)n * max_alignments * 4) ||
+      c->ucw_n.reserve((size_t)n * 4) || c->ucw_status.reserve((size_t)n * 4) || c->ucw_thr.reserve((size_t)n * 4)) return 1;
+  UcwParams U{};
+  U.A = c->sc.A;
+  U.subf = c->subf.as<float>();
+  U.gi = c->gi_f;
+  U.ge = c->ge_f;
+  U.delfree = c->sc.delfree;
+  U.insfree = c->sc.insfree;
+  U.inv_scale = 1.f / (float)(1 << c->sc.scale_log2);
+  U.residues = c->residues.as<uint8_t>();
+  U.seq_off = c->seq_off.as<int64_t>();
+  U.pair_q = c->pair_q.as<int32_t>();
+  U.pair_t = c->pair_t.as<int32_t>();
+  U.fmt = c->fmt.as<uint8_t>();
+  U.sc_blob = c->scb[0].p;
+  U.sc_off = c->sc_off.as<int64_t>();
+  U.st_mode_v1 = b.st_mode;
+  U.bias16 = kBias16;
+  U.fin_score = c->fin_score[0].as<int32_t>();
+  U.ids = c->ucw_ids.as<int64_t>();
+  U.n = (int)n;
+  U.delta_ratio = delta_ratio;
+  U.max_ali = max_alignments;
+  U.path_off = c->ucw_path_off.as<int64_t>();
+  U.paths = c->ucw_paths.as<int2>();
+  U.ali_len = c->ucw_len.as<int32_t>();
+  U.scores = c->ucw_scores.as<float>();
+  U.n_ali = c->ucw_n.as<int32_t>();
+  U.status = c->ucw_status.as<int32_t>();
+  U.threshold = c->ucw_thr.as<float>();
+  U.stack_off = c->ucw_stack_off.as<int64_t>();
+  U.stack = c->ucw_stack.as<int4>();
+  c->prof_begin("ucw_enum_kernel", 0);
+  ucw_enum_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
+  c->prof_end();
+  CK(cudaGetLastError());
+  c->launches = 1;
+  c->d2h_bytes = 0;
+  auto back = [&](void* dst, const DevBuf& src, size_t bytes) {
+    if (!dst || !bytes) return 0;
+    if (cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return 1;
+    c->d2h_bytes += (int64_t)bytes;
+    return 0;
+  };
+  if (back(n_ali, c->ucw_n, (size_t)n * 4) || back(status, c->ucw_status, (size_t)n * 4) ||
+      back(scores, c->ucw_scores, (size_t)n * max_alignments * 4) || back(ali_len, c->ucw_len, (size_t)n * max_alignments * 4) ||
+      back(paths, c->ucw_paths, (size_t)poff[(size_t)n] * 8) || back(threshold, c->ucw_thr, (size_t)n * 4))
+    return fail("device to host copy failed");
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

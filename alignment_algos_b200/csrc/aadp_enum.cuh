@@ -1,0 +1,175 @@
+// aadp_enum.cuh -- near-optimal ENUMERATION on the GPU for sm_100a.
+//
+// UnconstrainedNearOptimal::enumerate / branch (ucw.h:63-191): a depth-first walk from the final cell towards the
+// anchor that follows every predecessor satisfying Waterman's condition  F[pred] + r - g > threshold, where r is the
+// score accumulated from the end of the alignment and g the gap penalty of the step.  Each root-to-leaf path of the
+// walk is one near-optimal alignment; the reference numbers them in depth-first order (slot k of the AlignmentSet)
+// and sorts them by score afterwards (sortSet, alignment.h:922-932).
+//
+// Mapping.  The walk of ONE pair is sequential, but the two candidate scans of a node (ucw.h:154-180: a whole row and
+// a whole column of the forward matrix) are not: one WARP owns a pair, its 32 lanes test 32 candidates at a time and a
+// ballot picks the first one in the reference's order (match, deletions t0-2..1, insertions q0-2..1).  The
+// recursion is an explicit stack of frames in HBM (one frame per alignment position, <= Lq+1 deep).  The forward
+// scores are read straight from the RESIDENT batch products (packed int16 diagonal-major blob of the packed kernels or
+// the row-major blob of the int32 kernels) -- no dense matrix is expanded.  Batch-level parallelism: one warp per
+// listed pair, thousands of pairs per launch.
+//
+// Arithmetic is the reference's fp32 in the reference's order: r = curr + sim; (f + r) - g > thr; score = r - g;
+// leaf: score += D[q0][t0].score.  On the dyadic grid the integer kernels require, every value is exact, so the
+// alignments, their order and their scores are bit-identical.  The opt_path fallback (ucw.h:182-236) is only reachable
+// through rounding (a cell that passed always has a passing predecessor in exact arithmetic) or through the 100000
+// alignment user limit; here a pair that exceeds its output budget is flagged (status 1) instead, and a node without
+// a passing predecessor -- impossible on the dyadic grid -- is flagged with status 2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "aadp_kernels.cuh"
+
+namespace aadp {
+
+struct UcwParams {
+  int A;
+  const float* subf;          // A*A substitution scores
+  float gi, ge;               // gap(len) = gi + ge*(len-1) (aasubalib.h:37-38)
+  int delfree, insfree;       // free end gaps (aasubalib.h:39-42, 65-68)
+  float inv_scale;            // score units -> float
+  const uint8_t* residues;
+  const int64_t* seq_off;
+  const int32_t* pair_q;
+  const int32_t* pair_t;
+  const uint8_t* fmt;         // per pair: layout class (1 = packed)
+  const void* sc_blob;        // forward score blob
+  const int64_t* sc_off;      // per pair
+  int st_mode_v1;             // storage of the non-packed pairs: 1 = int16, 2 = int32
+  int bias16;                 // bias of the packed int16 domain
+  const int32_t* fin_score;   // per pair: D[last][last].score in score units
+  const int64_t* ids;         // listed pairs
+  int n;
+  float delta_ratio;
+  int max_ali;                // output budget per pair
+  const int64_t* path_off;    // per listed pair: first slot; alignment a of pair k lives at path_off[k] + a*(Lq+2)
+  int2* paths;                // aligned pairs front to back, (0,0) first
+  int32_t* ali_len;           // [k*max_ali + a]
+  float* scores;              // [k*max_ali + a]
+  int32_t* n_ali;             // per listed pair
+  int32_t* status;            // per listed pair: 0, 1 = more than max_ali alignments (output truncated), 2 = see above
+  float* threshold;           // per listed pair, or null
+  const int64_t* stack_off;   // per listed pair: first frame of its stack (Lq+2 frames)
+  int4* stack;                // frames: (q0, t0, __float_as_int(curr), next candidate | any<<30)
+};
+
+__global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.n) return;
+  const int64_t pair = P.ids[warp];
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int64_t qo = P.seq_off[qs], to = P.seq_off[ts];
+  const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
+  const uint8_t* qseq = P.residues + qo;
+  const uint8_t* tseq = P.residues + to;
+  const int fmt = P.fmt[pair];
+  const Layout L = make_layout(Lq, Lt, fmt, 0);
+  const int st_mode = fmt == 1 ? 1 : P.st_mode_v1;
+  const int bias = fmt == 1 ? P.bias16 : 0;
+  const int64_t sco = P.sc_off[pair];
+  const float inv = P.inv_scale;
+  // DPCell::score of the forward matrix (interior cells and the final cell)
+  auto F = [&](int i, int j) -> float {
+    if (i == Lq + 1 && j == Lt + 1) return (float)P.fin_score[pair] * inv;
+    int si;
+    if (st_mode == 1) si = (int)((const int16_t*)P.sc_blob)[sco + layout_sc_index(L, i, j)] - bias;
+    else si = ((const int32_t*)((const int16_t*)P.sc_blob + sco))[layout_sc_index(L, i, j)];
+    return (float)si * inv;
+  };
+  auto sim = [&](int i, int j) -> float {  // aasubalib.h:17-25
+    if (i < 1 || i > Lq || j < 1 || j > Lt) return 0.f;
+    return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
+  };
+  auto pen = [&](int len) { return __fadd_rn(P.gi, __fmul_rn(P.ge, (float)(len - 1))); };
+  const float opt = (float)P.fin_score[pair] * inv;
+  const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // ucw.h:81-83
+  if (lane == 0 && P.threshold) P.threshold[warp] = thr;
+
+  const int cap = Lq + 2;  // every step lowers the query index: at most Lq+2 aligned pairs
+  int2* paths = P.paths + P.path_off[warp];
+  int4* stack = P.stack + P.stack_off[warp];
+  int32_t* ali_len = P.ali_len + (int64_t)warp * P.max_ali;
+  float* scores = P.scores + (int64_t)warp * P.max_ali;
+  int count = 0, status = 0;
+
+  // frame in registers (uniform across the warp); stack[d] holds the frames below it
+  int q0 = Lq + 1, t0 = Lt + 1, next = 0, any = 0, depth = 0;
+  float curr = 0.f;
+  for (;;) {
+    if (q0 == 1 || t0 == 1) {
+      // base case (ucw.h:94-101): the alignment is (0,0), (q0,t0), then the frames from the deepest to the root
+      if (count >= P.max_ali) { status = 1; break; }
+      const float s = __fadd_rn(curr, F(q0, t0));
+      int2* out = paths + (int64_t)count * cap;
+      const int len = depth + 2;
+      for (int k = lane; k < len; k += 32) {
+        int2 v;
+        if (k == 0) v = make_int2(0, 0);
+        else if (k == 1) v = make_int2(q0, t0);
+        else { const int4 f = stack[depth - (k - 1)]; v = make_int2(f.x, f.y); }
+        out[k] = v;
+      }
+      if (lane == 0) { ali_len[count] = len; scores[count] = s; }
+      ++count;
+    } else {
+      const float r = __fadd_rn(curr, sim(q0, t0));  // ucw.h:141
+      const int ndel = t0 - 2, total = 1 + ndel + (q0 - 2);
+      int found = -1, cq = 0, ct = 0;
+      float cg = 0.f;
+      for (int base = next; base < total && found < 0; base += 32) {
+        const int idx = base + lane;
+        bool pass = false;
+        int iq = 0, it = 0;
+        float g = 0.f;
+        if (idx < total) {
+          if (idx == 0) {  // match (ucw.h:142-150)
+            iq = q0 - 1; it = t0 - 1;
+            pass = __fadd_rn(F(iq, it), r) > thr;
+          } else if (idx <= ndel) {  // deletions, i = t0-2 .. 1 (ucw.h:154-165)
+            iq = q0 - 1; it = t0 - 1 - idx;
+            const int len = t0 - it - 1;
+            g = (P.delfree && t0 == Lt + 1) ? 0.f : pen(len);  // aasubalib.h:39-42 (it >= 1: never the Head)
+            pass = __fsub_rn(__fadd_rn(F(iq, it), r), g) > thr;
+          } else {  // insertions, j = q0-2 .. 1 (ucw.h:169-180)
+            iq = q0 - 1 - (idx - ndel); it = t0 - 1;
+            const int len = q0 - iq - 1;
+            g = (P.insfree && q0 == Lq + 1) ? 0.f : pen(len);  // aasubalib.h:65-68
+            pass = __fsub_rn(__fadd_rn(F(iq, it), r), g) > thr;
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+          const int src = __ffs(m) - 1;
+          found = base + src;
+          cq = __shfl_sync(0xffffffffu, iq, src);
+          ct = __shfl_sync(0xffffffffu, it, src);
+          cg = __shfl_sync(0xffffffffu, g, src);
+        }
+      }
+      if (found >= 0) {
+        // descend: the child continues slot k (first passing branch) or a copy of `curr` (later ones), ucw.h:145-149
+        if (lane == 0) stack[depth] = make_int4(q0, t0, __float_as_int(curr), (found + 1) | (1 << 30));
+        __syncwarp();
+        curr = found == 0 ? r : __fsub_rn(r, cg);
+        q0 = cq; t0 = ct; next = 0; any = 0;
+        ++depth;
+        continue;
+      }
+      if (!any) { status = 2; break; }  // opt_path fallback (ucw.h:182-189): unreachable on the dyadic grid
+    }
+    // return to the parent frame
+    if (depth == 0) break;
+    --depth;
+    const int4 f = stack[depth];
+    q0 = f.x; t0 = f.y; curr = __int_as_float(f.z); next = f.w & 0x3fffffff; any = (f.w >> 30) & 1;
+  }
+  if (lane == 0) { P.n_ali[warp] = count; P.status[warp] = status; }
+}
+
+}  // namespace aadp

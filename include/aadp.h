@@ -230,6 +230,24 @@ int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, 
 int aadp_batch_optimal_all(aadp_ctx* ctx, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
                            int32_t* n_out, int32_t* status);
 
+/* ---- near-optimal ENUMERATION of listed pairs of the resident batch on the GPU: replaces
+ * UnconstrainedNearOptimal::enumerate / branch (ucw.h:63-191) up to, not including, its final sortSet.  One warp per
+ * listed pair walks the Waterman branching depth first over the RESIDENT forward scores (no dense expansion); the
+ * alignments come back in the reference's depth-first slot order with the reference's fp32 scores.  Needs a batch run
+ * with AADP_W_FWD and (AADP_W_SCORES or AADP_W_MASK) on the integer (dyadic-grid) kernels; not for local alignments.
+ * Host outputs (any may be NULL); K = max_alignments is the output budget per pair:
+ *   n_ali      n: alignments emitted for listed pair k (<= K)
+ *   status     n: 0; 1 = the pair has more than K alignments (the first K in depth-first order are returned; the
+ *              reference itself stops branching at 100000, ucw.h:72,115-126)
+ *   scores     n*K: AlignedPairList::score of alignment a of pair k at [k*K + a]
+ *   ali_len    n*K: aligned pairs of that alignment, including (0,0) and (last,last)
+ *   path_off   n+1 (computed on the host; call with every other output NULL to size `paths`): alignment a of pair k
+ *              occupies paths[2*(path_off[k] + a*(Lq+2)) ...], (query_idx, template_idx) front to back
+ *   threshold  n: min((1-delta_ratio)*opt, opt-0.1f) (ucw.h:81-83)                                                */
+int aadp_batch_near_optimal(aadp_ctx* ctx, const int64_t* pair_ids, int64_t n, float delta_ratio,
+                            int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
+                            int64_t* path_off, int32_t* paths, int64_t paths_cap, float* threshold);
+
 /* ---- packed traceback format helpers (host side, no GPU needed) ---------------------------
  * Row stride in bytes of the ROW-MAJOR packed traceback (int32 kernels) for template length Lt. */
 int64_t aadp_tb_row_bytes(int Lt);

@@ -562,3 +562,71 @@ long orc_ucw_cells(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc
   ucw_branch(&u, u.sz1 - 1, u.sz2 - 1, 0.f);
   return u.count;
 }
+
+/* ---------------------------------------------------------------- UCW enumeration (ucw.h:63-191) */
+
+/* The same Waterman branching as ucw_branch above, but EMITTING the alignments in the reference's depth-first slot
+ * order (slot k of the AlignmentSet before sortSet): path = aligned pairs front to back, score as the reference
+ * accumulates it (r = curr + sim; child score r - g; leaf += D[q0][t0].score).                                  */
+typedef struct {
+  const orc_scoring* sc;
+  const float* F;
+  const float* sim;
+  int sz1, sz2;
+  float thr;
+  long count, limit, status;
+  int* stack; /* 2 ints per frame */
+  int depth;
+  float* scores;
+  int* ali_len;
+  int* pairs; /* limit * (sz1) * 2 ints: fixed slots of sz1 aligned pairs */
+} ucwe_t;
+
+static void ucwe_branch(ucwe_t* u, int q0, int t0, float curr) {
+  if (u->status) return;
+  int sz2 = u->sz2;
+  if (q0 == 1 || t0 == 1) { /* ucw.h:94-101 */
+    if (u->count >= u->limit) { u->status = 1; return; }
+    int* out = u->pairs + (size_t)u->count * u->sz1 * 2;
+    int n = 0;
+    out[0] = 0; out[1] = 0; ++n;
+    out[2] = q0; out[3] = t0; ++n;
+    for (int d = u->depth - 1; d >= 0; --d, ++n) { out[2 * n] = u->stack[2 * d]; out[2 * n + 1] = u->stack[2 * d + 1]; }
+    u->ali_len[u->count] = n;
+    u->scores[u->count] = curr + u->F[(size_t)q0 * sz2 + t0];
+    ++u->count;
+    return;
+  }
+  float r = curr + u->sim[(size_t)q0 * sz2 + t0];
+  float f = u->F[(size_t)(q0 - 1) * sz2 + (t0 - 1)];
+  int any = 0;
+  u->stack[2 * u->depth] = q0;
+  u->stack[2 * u->depth + 1] = t0;
+  ++u->depth;
+  if (f + r > u->thr) { any = 1; ucwe_branch(u, q0 - 1, t0 - 1, r); }
+  for (int i = t0 - 2; i > 0 && !u->status; --i) {
+    f = u->F[(size_t)(q0 - 1) * sz2 + i];
+    float g = orc_deletion(u->sc, u->sz2, i, t0);
+    if (f + r - g > u->thr) { any = 1; ucwe_branch(u, q0 - 1, i, r - g); }
+  }
+  for (int j = q0 - 2; j > 0 && !u->status; --j) {
+    f = u->F[(size_t)j * sz2 + (t0 - 1)];
+    float g = orc_insertion(u->sc, u->sz1, j, q0);
+    if (f + r - g > u->thr) { any = 1; ucwe_branch(u, j, t0 - 1, r - g); }
+  }
+  --u->depth;
+  if (!any && !u->status) u->status = 2; /* opt_path fallback (ucw.h:182-189): not restated */
+}
+
+long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status) {
+  ucwe_t u;
+  u.sc = sc; u.F = F; u.sim = sim; u.sz1 = Lq + 2; u.sz2 = Lt + 2; u.thr = thr;
+  u.count = 0; u.limit = max_alignments; u.status = 0; u.depth = 0;
+  u.stack = (int*)malloc(sizeof(int) * 2 * (size_t)(Lq + 3));
+  u.scores = scores; u.ali_len = ali_len; u.pairs = pairs;
+  ucwe_branch(&u, u.sz1 - 1, u.sz2 - 1, 0.f);
+  free(u.stack);
+  *status = (int)u.status;
+  return u.count;
+}

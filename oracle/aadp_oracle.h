@@ -91,6 +91,13 @@ long orc_ucw_cells(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc
 float orc_deletion(const orc_scoring* sc, int sz2, int t_pos1, int t_pos2);
 float orc_insertion(const orc_scoring* sc, int sz1, int q_pos1, int q_pos2);
 
+/* UnconstrainedNearOptimal::enumerate (ucw.h:63-191) up to, not including, its final sortSet: the alignments in the
+ * reference's depth-first slot order.  pairs holds max_alignments fixed slots of (Lq+2) aligned pairs (2 ints each),
+ * front to back.  status: 0, 1 = more than max_alignments, 2 = a node without a passing predecessor (the reference
+ * would take opt_path, ucw.h:182-189; cannot happen in exact arithmetic).  Returns the number of alignments.   */
+long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status);
+
 #ifdef __cplusplus
 }
 #endif

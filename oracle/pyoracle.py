@@ -98,6 +98,20 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return score, pq, pt
 
+    def ucw_enumerate(self, q, t, F, sim, thr, max_alignments=20000):
+        """orc_ucw_enumerate: (status, [(score, pairs[(len,2)])]) in the reference's depth-first slot order."""
+        Lq, Lt = len(q), len(t)
+        K = int(max_alignments)
+        scores = np.zeros(K, np.float32)
+        ln = np.zeros(K, np.int32)
+        pairs = np.zeros((K, Lq + 2, 2), np.int32)
+        st = C.c_int(0)
+        self.lib.orc_ucw_enumerate.restype = C.c_long
+        n = self.lib.orc_ucw_enumerate(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
+                                       _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
+                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st))
+        return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
+
     @staticmethod
     def fill_tab(sim, del_tab, ins_tab, is_local=False, direction=FWD, repro_rev_bug=True):
         """orc_fill_tab: the literal fill for any evaluator given as tables (see aadp_oracle.h)."""
@@ -341,6 +355,26 @@ class Reference:
         if rc:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return union, n.value, scores[: min(n.value, max_scores)].copy(), thr.value
+
+    def ucw_alignments(self, q, t, delta_ratio, max_alignments=20000):
+        """Every alignment of the reference's UnconstrainedNearOptimal (sorted by its sortSet): [(score, pairs)]."""
+        K = int(max_alignments)
+        cap = K * (len(q) + 2)
+        scores = np.zeros(K, np.float32)
+        ln = np.zeros(K, np.int32)
+        pairs = np.zeros((cap, 2), np.int32)
+        n, tot = C.c_int(0), C.c_long(0)
+        rc = self.lib.ref_ucw_alignments(*self._args(q, t), C.c_float(delta_ratio), K, C.c_long(cap), C.byref(n),
+                                         C.byref(tot), _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int))
+        if rc == 5:
+            raise OverflowError("%d alignments" % n.value)
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        out, o = [], 0
+        for k in range(n.value):
+            out.append((float(scores[k]), pairs[o:o + ln[k]].copy()))
+            o += ln[k]
+        return out
 
     def time_fills(self, seqs, pair_q, pair_t, what=3, nthreads=1):
         """Time the reference DPMatrix constructor over pairs. Returns (seconds, cells, checksum)."""

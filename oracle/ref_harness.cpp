@@ -386,6 +386,61 @@ int ref_nearopt(const char* q, const char* t, const char* matrix_file, float gi,
   }
 }
 
+// Every alignment UnconstrainedNearOptimal::enumerate (ucw.h:63-86) produces, with its score and its aligned pairs, in
+// the order the reference leaves them in (sorted by sortSet; number_suboptimal is forced huge so nothing is dropped).
+// pairs: concatenated (query_idx, template_idx); alignment k has ali_len[k] of them.  Returns 5 when the buffers are
+// too small (n_alignments / total pairs are still reported).
+int ref_ucw_alignments(const char* q, const char* t, const char* matrix_file, float gi, float ge, int align_type,
+                       float delta_ratio, int max_alignments, long max_pairs, int* n_alignments, long* total_pairs,
+                       float* scores, int* ali_len, int* pairs) {
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, fwd, ap.align_type);
+    NOaliParams np;
+    np.delta_ratio = delta_ratio;
+    np.number_suboptimal = 0x3fffffff / 32;
+    Optimal<AASequence, AASequence, AAEval> opt(ap.align_type);
+    AlignmentSet<AASequence, AASequence, AAEval> as(dpm, opt);
+    as.clear();
+    UnconstrainedNearOptimal<AASequence, AASequence, AAEval> u(np);
+    u.enumerate(dpm, as);
+    *n_alignments = (int)as.size();
+    long tot = 0;
+    bool fits = (int)as.size() <= max_alignments;
+    for (size_t k = 0; k < as.size(); ++k) {
+      long len = (long)as[k].size();
+      if (fits && tot + len <= max_pairs) {
+        scores[k] = as[k].score;
+        ali_len[k] = (int)len;
+        long o = tot;
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = as[k].begin(); it != as[k].end(); ++it, ++o) {
+          pairs[2 * o] = it->query_idx();
+          pairs[2 * o + 1] = it->template_idx();
+        }
+      } else {
+        fits = false;
+      }
+      tot += len;
+    }
+    *total_pairs = tot;
+    return fits ? 0 : 5;
+  } catch (std::string& e) {
+    g_err = e;
+    return 1;
+  } catch (std::bad_alloc&) {
+    g_err = "bad_alloc";
+    return 4;
+  } catch (...) {
+    g_err = "unknown exception";
+    return 2;
+  }
+}
+
 // CPU baseline timing: runs the reference's DPMatrix constructor (fill only, as BASELINE.md §3
 // states) over `npairs` pairs given as offsets into one residue arena, on `nthreads` host threads
 // (one worker per thread over a shared atomic cursor; the fill is single-threaded and shares no

@@ -669,6 +669,67 @@ def test_tabulated_gap_model_golden_and_random(golden_tab):
     c.close()
 
 
+def test_near_optimal_enumeration_on_gpu(blosum):
+    # aadp_batch_near_optimal (row f1): UnconstrainedNearOptimal::enumerate (ucw.h:63-191) of listed pairs of a resident
+    # batch, one warp per pair over the packed score blob.  Oracle = orc_ucw_enumerate (pinned to the reference in
+    # tests/test_oracle.py): same alignments in the same depth-first order with bit-identical fp32 scores.
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(83)
+    for gi, ge, at, delta in [(12, 1, po.SEMI_LOCAL, 0.08), (3, 1, po.GLOBAL, 0.12), (10.5, 0.25, po.GLOBAL_LOCAL, 0.2),
+                              (3, 1, po.LOCAL_GLOBAL, 0.15)]:
+        seqs = []
+        for k in range(24):
+            L = int(rng.integers(8, 70))
+            s = rng.integers(0, 20, L).astype(np.uint8)
+            seqs.append(s)
+            m = s.copy()                      # a mutated copy: related pairs have many near-optimal alignments
+            m[::5] = rng.integers(0, 20, len(m[::5]))
+            seqs.append(np.concatenate([m[: L // 2], m[L // 2 + int(rng.integers(0, 3)):]]))
+        seqs += [rng.integers(0, 20, L).astype(np.uint8) for L in (0, 1, 2, 530)]
+        res, off = a.Context.pack(seqs)
+        pq = np.array(list(range(0, 48, 2)) + [48, 49, 50, 3, 51, 6], np.int32)
+        pt = np.array(list(range(1, 48, 2)) + [5, 49, 7, 48, 9, 51], np.int32)
+        c = a.Context(0)
+        c.set_scoring(M, gi, ge, at)
+        what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+        c.fill_batch(res, off, pq, pt, what, delta)
+        K = 3000
+        ids = np.arange(len(pq))[::-1].copy()          # any order, any subset
+        got = c.near_optimal(ids, delta, K)
+        O = po.Oracle(M, gi, ge, at)
+        n_multi = 0
+        for k, p in enumerate(ids):
+            q, t = seqs[pq[p]], seqs[pt[p]]
+            F, _, _ = O.fill(q, t, po.FWD, True, fast=True)
+            thr = O.threshold(float(F[-1, -1]), delta)
+            st, want = O.ucw_enumerate(q, t, F, O.sim(q, t), thr, K)
+            gst, gthr, alis = got[k]
+            assert gst == st, (p, gst, st)
+            assert gthr == thr
+            assert len(alis) == len(want), (p, len(alis), len(want))
+            n_multi += len(alis) > 1
+            for (gs, gp), (ws, wp) in zip(alis, want):
+                assert gs == ws
+                assert_matrix_equal("pair %d alignment" % p, gp, wp)
+        assert n_multi >= 5
+        # a budget smaller than the number of alignments: status 1 and the first K in depth-first order
+        big = max(range(len(ids)), key=lambda k: len(got[k][2]))
+        nbig = len(got[big][2])
+        if nbig > 3:
+            small = c.near_optimal(ids[big:big + 1], delta, nbig - 2)[0]
+            assert small[0] == 1 and len(small[2]) == nbig - 2
+            for (gs, gp), (ws, wp) in zip(small[2], got[big][2]):
+                assert gs == ws and np.array_equal(gp, wp)
+        c.close()
+    c = a.Context(0)
+    c.set_scoring(M, 4.73, 0.34, po.GLOBAL)      # exact-float mode keeps no resident scores: loud refusal
+    c.fill_batch(res, off, pq[:2], pt[:2], a.W_FWD | a.W_REV | a.W_MASK, 0.05)
+    with pytest.raises(a.AadpError):
+        c.near_optimal([0], 0.05, 10)
+    c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a

@@ -216,3 +216,32 @@ def test_oracle_tabulated_gap_fill_matches_reference_random(blosum):
             got = po.Oracle.fill_tab(O.sim(q, t), dt, it, at == po.LOCAL, d)
             for a, b, nm in zip(got, want[:3], ("score", "pq", "pt")):
                 assert_matrix_equal("affine-as-table " + nm, a, b)
+
+
+def _canon(alis):
+    return sorted((s, tuple(map(tuple, p))) for s, p in alis)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_ucw_enumeration_matches_reference(blosum):
+    # orc_ucw_enumerate == UnconstrainedNearOptimal::enumerate (ucw.h:63-191): same alignments, same fp32 scores
+    # (the reference sorts its set at the end, so the comparison is on canonically sorted lists)
+    alpha, M = blosum
+    rng = np.random.default_rng(4)
+    total = 0
+    for at in (po.GLOBAL_LOCAL, po.GLOBAL, po.LOCAL_GLOBAL, po.SEMI_LOCAL):
+        for gi, ge in ((12, 1), (3, 1)):
+            O = po.Oracle(M, gi, ge, at)
+            R = po.Reference(alpha, M, gi, ge, at)
+            for Lq, Lt, delta in ((20, 25, 0.3), (30, 30, 0.2), (12, 40, 0.5), (0, 4, 0.1), (5, 1, 0.1)):
+                q = rng.integers(0, 20, Lq).astype(np.uint8)
+                t = q.copy() if Lq == Lt else rng.integers(0, 20, Lt).astype(np.uint8)
+                t[::4] = rng.integers(0, 20, len(t[::4]))
+                F, _, _ = O.fill(q, t, po.FWD, True, fast=True)
+                thr = O.threshold(float(F[-1, -1]), delta)
+                st, alis = O.ucw_enumerate(q, t, F, O.sim(q, t), thr, 100000)
+                assert st == 0
+                ref = R.ucw_alignments(q, t, delta, 100000)
+                assert _canon(alis) == _canon(ref), (at, gi, Lq, Lt)
+                total += len(alis)
+    assert total > 2000
