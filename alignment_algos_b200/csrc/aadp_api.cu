@@ -2141,10 +2141,9 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
   Batch& b = c->b;
   if (n < 0 || (n && !pair_ids)) return fail("null input");
   if (max_alignments < 1) return fail("max_alignments must be positive");
-  if (c->float_mode) return fail("aadp_batch_near_optimal: exact-float mode keeps no resident score matrices (enumerate on the host over aadp_batch_fetch_pair)");
   if (c->sc.local) return fail("aadp_batch_near_optimal: not for local alignments");
   if (!(b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
-  if (!(b.ran_what & (AADP_W_SCORES | AADP_W_MASK))) return fail("score matrices were not kept (run with AADP_W_SCORES or AADP_W_MASK)");
+  if (!c->float_mode && !(b.ran_what & (AADP_W_SCORES | AADP_W_MASK))) return fail("score matrices were not kept (run with AADP_W_SCORES or AADP_W_MASK)");
   std::vector<int64_t> poff((size_t)n + 1, 0), soff((size_t)n + 1, 0);
   for (int64_t k = 0; k < n; ++k) {
     const int64_t p = pair_ids[k];
@@ -2194,11 +2193,42 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
   U.threshold = c->ucw_thr.as<float>();
   U.stack_off = c->ucw_stack_off.as<int64_t>();
   U.stack = c->ucw_stack.as<int4>();
-  c->prof_begin("ucw_enum_kernel", 0);
-  ucw_enum_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
-  c->prof_end();
-  CK(cudaGetLastError());
-  c->launches = 1;
+  c->launches = 0;
+  if (!c->float_mode) {
+    c->prof_begin("ucw_enum_kernel", 0);
+    ucw_enum_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
+    c->prof_end();
+    CK(cudaGetLastError());
+    c->launches++;
+  } else {
+    // exact-float mode keeps no resident matrices: refill each listed pair with the exact general-gap kernel (dense fp32
+    // scores + predecessors in scratch) and walk that; one pair per launch
+    if (c->gg_fin[0].reserve(std::max<size_t>((size_t)b.npairs * 4, 16))) return 1;
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t p = pair_ids[k];
+      const int64_t cl = (b.seq_off[b.pair_q[p] + 1] - b.seq_off[b.pair_q[p]] + 2) * (b.seq_off[b.pair_t[p] + 1] - b.seq_off[b.pair_t[p]] + 2);
+      const std::vector<int64_t> doff = {0, cl};
+      if (gg_fill(c, p, 1, 1, true, doff, c->gg_fin[0].as<float>(), nullptr)) return 1;
+      UcwParams V = U;
+      V.denseF = c->gg_score[0].as<float>();
+      V.densePQ = c->gg_pq[0].as<int32_t>();
+      V.densePT = c->gg_pt[0].as<int32_t>();
+      V.n = 1;
+      V.ids = U.ids + k;
+      V.path_off = U.path_off + k;
+      V.stack_off = U.stack_off + k;
+      V.ali_len = U.ali_len + k * max_alignments;
+      V.scores = U.scores + k * max_alignments;
+      V.n_ali = U.n_ali + k;
+      V.status = U.status + k;
+      V.threshold = U.threshold + k;
+      c->prof_begin("ucw_enum_kernel (exact float)", 0);
+      ucw_enum_kernel<<<1, 128, 0, c->stream>>>(V);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+    }
+  }
   c->d2h_bytes = 0;
   auto back = [&](void* dst, const DevBuf& src, size_t bytes) {
     if (!dst || !bytes) return 0;

@@ -44,6 +44,11 @@ struct UcwParams {
   int st_mode_v1;             // storage of the non-packed pairs: 1 = int16, 2 = int32
   int bias16;                 // bias of the packed int16 domain
   const int32_t* fin_score;   // per pair: D[last][last].score in score units
+  // exact-float mode (one listed pair per launch): the dense fp32 forward matrix of the general-gap kernel and its
+  // predecessors instead of the resident integer products; null otherwise
+  const float* denseF;
+  const int32_t* densePQ;
+  const int32_t* densePT;
   const int64_t* ids;         // listed pairs
   int n;
   float delta_ratio;
@@ -68,14 +73,16 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
   const int Lq = (int)(P.seq_off[qs + 1] - qo), Lt = (int)(P.seq_off[ts + 1] - to);
   const uint8_t* qseq = P.residues + qo;
   const uint8_t* tseq = P.residues + to;
-  const int fmt = P.fmt[pair];
+  const int fmt = P.denseF ? 0 : P.fmt[pair];  // exact-float batches have no layout tables
   const Layout L = make_layout(Lq, Lt, fmt, 0);
   const int st_mode = fmt == 1 ? 1 : P.st_mode_v1;
   const int bias = fmt == 1 ? P.bias16 : 0;
-  const int64_t sco = P.sc_off[pair];
+  const int64_t sco = P.denseF ? 0 : P.sc_off[pair];
   const float inv = P.inv_scale;
   // DPCell::score of the forward matrix (interior cells and the final cell)
+  const int sz2 = Lt + 2;
   auto F = [&](int i, int j) -> float {
+    if (P.denseF) return P.denseF[(int64_t)i * sz2 + j];
     if (i == Lq + 1 && j == Lt + 1) return (float)P.fin_score[pair] * inv;
     int si;
     if (st_mode == 1) si = (int)((const int16_t*)P.sc_blob)[sco + layout_sc_index(L, i, j)] - bias;
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
     return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
   };
   auto pen = [&](int len) { return __fadd_rn(P.gi, __fmul_rn(P.ge, (float)(len - 1))); };
-  const float opt = (float)P.fin_score[pair] * inv;
+  const float opt = F(Lq + 1, Lt + 1);
   const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // ucw.h:81-83
   if (lane == 0 && P.threshold) P.threshold[warp] = thr;
 
@@ -161,7 +168,45 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
         ++depth;
         continue;
       }
-      if (!any) { status = 2; break; }  // opt_path fallback (ucw.h:182-189): unreachable on the dyadic grid
+      if (!any) {
+        // The score fell below the threshold after extending the branch (ucw.h:182-189): only rounding can do that
+        // (exact-float mode); the reference then forces the optimal path to the beginning (opt_path, ucw.h:194-236).
+        if (!P.densePQ) { status = 2; break; }
+        if (count >= P.max_ali) { status = 1; break; }
+        int2* out = paths + (int64_t)count * cap;
+        int m = 0;
+        if (lane == 0) {
+          float s = curr;
+          int a = q0, b = t0;
+          while (a > 1 && b > 1) {
+            s = __fadd_rn(s, sim(a, b));
+            const int pa = P.densePQ[(int64_t)a * sz2 + b], pb = P.densePT[(int64_t)a * sz2 + b];
+            float g = 0.f;
+            if (a - pa == 1) {  // deletion(pq,q0,pt,t0), aasubalib.h:27-51
+              const int len = b - pb - 1;
+              if (len >= 1 && !(P.delfree && (pb == 0 || b == Lt + 1))) g = pen(len);
+            } else {            // insertion(pq,q0,pt,t0), aasubalib.h:53-77
+              const int len = a - pa - 1;
+              if (len >= 1 && !(P.insfree && (pa == 0 || a == Lq + 1))) g = pen(len);
+            }
+            s = __fsub_rn(s, g);
+            a = pa; b = pb;
+            ++m;
+          }
+          s = __fadd_rn(s, F(a, b));
+          out[0] = make_int2(0, 0);
+          a = q0; b = t0;
+          for (int k = 0; k <= m; ++k) {  // n_0 = (q0,t0) ... n_m = the base-case cell, stored back to front
+            out[1 + m - k] = make_int2(a, b);
+            if (k < m) { const int pa = P.densePQ[(int64_t)a * sz2 + b], pb = P.densePT[(int64_t)a * sz2 + b]; a = pa; b = pb; }
+          }
+          ali_len[count] = depth + m + 2;
+          scores[count] = s;
+        }
+        m = __shfl_sync(0xffffffffu, m, 0);
+        for (int k = lane; k < depth; k += 32) { const int4 f = stack[depth - 1 - k]; out[m + 2 + k] = make_int2(f.x, f.y); }
+        ++count;
+      }
     }
     // return to the parent frame
     if (depth == 0) break;

@@ -110,6 +110,46 @@ class DPMatrix {
     return nearopt;
   }
 
+  // ---- extension: the near-optimal ALIGNMENTS themselves, enumerated on the GPU (aadp_batch_near_optimal =
+  // UnconstrainedNearOptimal::branch, ucw.h:88-191) in the reference's depth-first slot order; include/hmap2/ucw.h
+  // is the enumerator class on top of it.  budget = maximum number of alignments; *overflow tells when there are more.
+  template <class Alignment>
+  void nearOptimalAlignments(float delta_ratio, int budget, std::vector<Alignment>* out, bool* overflow) {
+    std::string alphabet;
+    std::vector<float> sub;
+    float gi, ge;
+    int at;
+    describe(&alphabet, &sub, &gi, &ge, &at);
+    const std::vector<uint8_t> q = aadp::encode(*query_seq, alphabet), t = aadp::encode(*templ_seq, alphabet);
+    std::vector<uint8_t> residues(q);
+    residues.insert(residues.end(), t.begin(), t.end());
+    residues.push_back(0);
+    const int64_t seq_off[3] = {0, (int64_t)q.size(), (int64_t)(q.size() + t.size())};
+    const int32_t pq = 0, pt = 1;
+    aadp_ctx* ctx = aadp::default_context();
+    aadp::check(aadp_set_scoring(ctx, sub.data(), (int)alphabet.size(), gi, ge, at, AADP_REPRO_REV_BUG));
+    float fs = 0.f;
+    aadp::check(aadp_fill_batch(ctx, residues.data(), seq_off, 2, &pq, &pt, 1, AADP_W_FWD | AADP_W_SCORES, delta_ratio, &fs, 0, 0, 0));
+    const int64_t id = 0;
+    int64_t off[2] = {0, 0};
+    aadp::check(aadp_batch_near_optimal(ctx, &id, 1, delta_ratio, budget, 0, 0, 0, 0, off, 0, 0, 0));
+    std::vector<int32_t> paths(2 * (size_t)off[1] + 2), len((size_t)budget);
+    std::vector<float> scores((size_t)budget);
+    int32_t n = 0, status = 0;
+    aadp::check(aadp_batch_near_optimal(ctx, &id, 1, delta_ratio, budget, &n, &status, scores.data(), len.data(), off,
+                                        paths.data(), off[1], 0));
+    if (status == 2) throw std::string("near-optimal enumeration: a cell without a passing predecessor (ucw.h:182-189)");
+    *overflow = status == 1;
+    out->clear();
+    out->resize((size_t)n);
+    const int64_t slot = (int64_t)q.size() + 2;
+    for (int32_t k = 0; k < n; ++k) {
+      Alignment& ali = (*out)[(size_t)k];
+      ali.score = scores[(size_t)k];
+      for (int32_t m = 0; m < len[(size_t)k]; ++m) ali.append(paths[2 * (k * slot + m)], paths[2 * (k * slot + m) + 1]);
+    }
+  }
+
  protected:
   void allocate() {
     const int sz1 = getQuerySize(), sz2 = getTemplateSize();

@@ -580,7 +580,36 @@ typedef struct {
   float* scores;
   int* ali_len;
   int* pairs; /* limit * (sz1) * 2 ints: fixed slots of sz1 aligned pairs */
+  const int *pq, *pt; /* DPCell predecessors of the forward matrix (for opt_path), or NULL */
 } ucwe_t;
+
+/* opt_path (ucw.h:194-236): no branching any more, follow the stored predecessors to the base case */
+static void ucwe_opt_path(ucwe_t* u, int q0, int t0, float score) {
+  int sz2 = u->sz2;
+  if (u->count >= u->limit) { u->status = 1; return; }
+  int* out = u->pairs + (size_t)u->count * u->sz1 * 2;
+  int m = 0, a = q0, b = t0;
+  while (b > 1 && a > 1) {
+    score += u->sim[(size_t)a * sz2 + b];
+    int pa = u->pq[(size_t)a * sz2 + b], pb = u->pt[(size_t)a * sz2 + b];
+    float g = (a - pa == 1) ? orc_deletion(u->sc, u->sz2, pb, b) : orc_insertion(u->sc, u->sz1, pa, a);
+    score -= g;
+    a = pa; b = pb;
+    ++m;
+  }
+  score += u->F[(size_t)a * sz2 + b];
+  out[0] = 0; out[1] = 0;
+  a = q0; b = t0;
+  for (int k = 0; k <= m; ++k) {
+    out[2 * (1 + m - k)] = a; out[2 * (1 + m - k) + 1] = b;
+    if (k < m) { int pa = u->pq[(size_t)a * sz2 + b], pb = u->pt[(size_t)a * sz2 + b]; a = pa; b = pb; }
+  }
+  int n = m + 2;
+  for (int d = u->depth - 1; d >= 0; --d, ++n) { out[2 * n] = u->stack[2 * d]; out[2 * n + 1] = u->stack[2 * d + 1]; }
+  u->ali_len[u->count] = n;
+  u->scores[u->count] = score;
+  ++u->count;
+}
 
 static void ucwe_branch(ucwe_t* u, int q0, int t0, float curr) {
   if (u->status) return;
@@ -615,12 +644,17 @@ static void ucwe_branch(ucwe_t* u, int q0, int t0, float curr) {
     if (f + r - g > u->thr) { any = 1; ucwe_branch(u, j, t0 - 1, r - g); }
   }
   --u->depth;
-  if (!any && !u->status) u->status = 2; /* opt_path fallback (ucw.h:182-189): not restated */
+  if (!any && !u->status) { /* ucw.h:182-189 */
+    if (u->pq) ucwe_opt_path(u, q0, t0, curr);
+    else u->status = 2;
+  }
 }
 
 long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
-                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status) {
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                       const int* prev_q, const int* prev_t) {
   ucwe_t u;
+  u.pq = prev_q; u.pt = prev_t;
   u.sc = sc; u.F = F; u.sim = sim; u.sz1 = Lq + 2; u.sz2 = Lt + 2; u.thr = thr;
   u.count = 0; u.limit = max_alignments; u.status = 0; u.depth = 0;
   u.stack = (int*)malloc(sizeof(int) * 2 * (size_t)(Lq + 3));

@@ -93,10 +93,13 @@ float orc_insertion(const orc_scoring* sc, int sz1, int q_pos1, int q_pos2);
 
 /* UnconstrainedNearOptimal::enumerate (ucw.h:63-191) up to, not including, its final sortSet: the alignments in the
  * reference's depth-first slot order.  pairs holds max_alignments fixed slots of (Lq+2) aligned pairs (2 ints each),
- * front to back.  status: 0, 1 = more than max_alignments, 2 = a node without a passing predecessor (the reference
- * would take opt_path, ucw.h:182-189; cannot happen in exact arithmetic).  Returns the number of alignments.   */
+ * front to back.  status: 0, 1 = more than max_alignments, 2 = a node without a passing predecessor and no
+ * predecessors given.  prev_q/prev_t (the forward DPCell predecessors, may be NULL) enable opt_path (ucw.h:182-236),
+ * which only rounding can trigger (a cell that passed has a passing predecessor in exact arithmetic).  The 100000
+ * alignment user limit (ucw.h:72,115-126) is not restated.  Returns the number of alignments.                 */
 long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
-                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status);
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                       const int* prev_q, const int* prev_t);
 
 #ifdef __cplusplus
 }

@@ -98,7 +98,7 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return score, pq, pt
 
-    def ucw_enumerate(self, q, t, F, sim, thr, max_alignments=20000):
+    def ucw_enumerate(self, q, t, F, sim, thr, max_alignments=20000, pq=None, pt=None):
         """orc_ucw_enumerate: (status, [(score, pairs[(len,2)])]) in the reference's depth-first slot order."""
         Lq, Lt = len(q), len(t)
         K = int(max_alignments)
@@ -109,7 +109,9 @@ class Oracle:
         self.lib.orc_ucw_enumerate.restype = C.c_long
         n = self.lib.orc_ucw_enumerate(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
                                        _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
-                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st))
+                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
+                                       _p(np.ascontiguousarray(pq, np.int32), C.c_int) if pq is not None else None,
+                                       _p(np.ascontiguousarray(pt, np.int32), C.c_int) if pt is not None else None)
         return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
 
     @staticmethod

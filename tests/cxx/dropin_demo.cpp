@@ -17,7 +17,9 @@
 #include "alignment.h"
 #include "dpmatrix.h"
 #include "optimal.h"
+#include "noalib.h"
 #include "optimal_subali.h"
+#include "ucw.h"
 #include "submatrix.h"
 #ifdef AADP_HMAP2_DPMATRIX_H
 #include "optimal_rev.h"  // abstract (un-instantiable) in the reference: optimal_rev.h:29-30
@@ -63,6 +65,23 @@ int main(int argc, char** argv) {
          it != alignments[0].end(); ++it)
       std::printf(" %d:%d", it->query_idx(), it->template_idx());
     std::printf("\n");
+    // every near-optimal alignment within 20 % of the optimum (ucw.h): this build enumerates on the GPU
+    // (aadp_batch_near_optimal), the reference recurses on the host.  '@' lines are compared as a sorted set (the
+    // reference's final sortSet is not stable on equal scores).
+    if (params.align_type != local && query.size() * templ.size() < 4000) {
+      NOaliParams np;
+      np.delta_ratio = 0.2f;
+      np.number_suboptimal = 50000;
+      UnconstrainedNearOptimal<AASequence, AASequence, AAEval> ucw(np);
+      AlignmentSet<AASequence, AASequence, AAEval> near(forward, ucw);
+      std::printf("@UCW count %d\n", (int)near.size());
+      for (size_t k = 0; k < near.size(); ++k) {
+        std::printf("@UCW score %.6g identity %.6g pairs", near[k].score, near[k].identity);
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = near[k].begin(); it != near[k].end(); ++it)
+          std::printf(" %d:%d", it->query_idx(), it->template_idx());
+        std::printf("\n");
+      }
+    }
     // sub-rectangle fill through the 9-argument constructor (dpmatrix.h:169-189 -> build_subdpm)
     if (query.size() > 9 && templ.size() > 9) {
       Matrix sub(query, templ, eval, 2, 3, (int)query.size() - 3, (int)templ.size() - 2, fwd, params.align_type);

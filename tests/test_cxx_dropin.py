@@ -68,13 +68,19 @@ def test_gpu_dropin_equals_reference_build(blosum, at):
         q = rng.integers(0, 20, Lq).astype(np.uint8)
         t = rng.integers(0, 20, Lt).astype(np.uint8)
         got = _run(DEMO, at, gi, ge, q, t)
-        core = [l for l in got if not l.startswith("#")]
+        core = [l for l in got if not l.startswith("#") and not l.startswith("@")]
         O = po.Oracle(M, gi, ge, at)
         want, res = _expected_lines(O, q, t, M, fast=(gi != 4.73))
         assert core[:len(want)] == want
         if os.path.exists(REF_DEMO) and Lq * Lt < 5000:
-            ref = [l for l in _run(REF_DEMO, at, gi, ge, q, t) if not l.startswith("#")]
+            ref_all = _run(REF_DEMO, at, gi, ge, q, t)
+            ref = [l for l in ref_all if not l.startswith("#") and not l.startswith("@")]
             assert core == ref, "GPU drop-in build and reference build print different results"
+            # near-optimal alignments (ucw.h) enumerated on the GPU vs. the reference recursion: same set, same scores
+            ucw_got, ucw_ref = sorted(l for l in got if l.startswith("@")), sorted(l for l in ref_all if l.startswith("@"))
+            assert ucw_got == ucw_ref, "GPU enumeration and the reference's UnconstrainedNearOptimal differ"
+            if at != po.LOCAL:
+                assert len(ucw_got) >= 2
             if Lq > 7 and Lt > 7:  # the loop list closed in ONE aadp_fill_subpair_batch call vs. one sub-matrix per loop
                 assert len([l for l in core if l.startswith("LOOP ")]) == 5
         # optimal alignment line against the oracle traceback

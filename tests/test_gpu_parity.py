@@ -722,9 +722,29 @@ def test_near_optimal_enumeration_on_gpu(blosum):
             for (gs, gp), (ws, wp) in zip(small[2], got[big][2]):
                 assert gs == ws and np.array_equal(gp, wp)
         c.close()
+    # exact-float mode (scoring off the dyadic grid, the reference defaults): each listed pair is refilled by the exact
+    # general-gap kernel and walked over its dense fp32 matrix, opt_path (ucw.h:194-236) included
+    for gi, ge, at, delta in [(4.73, 0.34, po.GLOBAL, 0.1), (4.73, 0.34, po.SEMI_LOCAL, 0.06), (2.17, 0.61, po.GLOBAL_LOCAL, 0.15)]:
+        c = a.Context(0)
+        c.set_scoring(M, gi, ge, at)
+        sel = np.array([0, 3, 7, 11, 24, 25, 27], np.int64)
+        c.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_MASK, delta)
+        got = c.near_optimal(sel, delta, 4000)
+        O = po.Oracle(M, gi, ge, at)
+        for k, p in enumerate(sel):
+            q, t = seqs[pq[p]], seqs[pt[p]]
+            F, fq, ft = O.fill(q, t, po.FWD, True, fast=False)
+            thr = O.threshold(float(F[-1, -1]), delta)
+            st, want = O.ucw_enumerate(q, t, F, O.sim(q, t), thr, 4000, fq, ft)
+            gst, gthr, alis = got[k]
+            assert (gst, gthr, len(alis)) == (st, thr, len(want)), (p, gst, st, len(alis), len(want))
+            for (gs, gp), (ws, wp) in zip(alis, want):
+                assert gs == ws
+                assert_matrix_equal("float pair %d alignment" % p, gp, wp)
+        c.close()
     c = a.Context(0)
-    c.set_scoring(M, 4.73, 0.34, po.GLOBAL)      # exact-float mode keeps no resident scores: loud refusal
-    c.fill_batch(res, off, pq[:2], pt[:2], a.W_FWD | a.W_REV | a.W_MASK, 0.05)
+    c.set_scoring(M, 3, 1, po.LOCAL)             # local alignments: loud refusal
+    c.fill_batch(res, off, pq[:2], pt[:2], a.W_FWD | a.W_SCORES, 0.05)
     with pytest.raises(a.AadpError):
         c.near_optimal([0], 0.05, 10)
     c.close()
