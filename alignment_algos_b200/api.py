@@ -260,20 +260,32 @@ class Context:
         self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), _ptr(pairs), int(off[-1]), _ptr(n), _ptr(st)))
         return off, pairs, n, st
 
-    def near_optimal(self, pair_ids, delta_ratio, max_alignments):
-        """UnconstrainedNearOptimal::enumerate (ucw.h:63-191, before sortSet) of the listed pairs on the GPU.
+    def near_optimal(self, pair_ids, delta_ratio, max_alignments, subopt_flags=None, constrained=False):
+        """UnconstrainedNearOptimal::enumerate (ucw.h:63-191, before sortSet) of the listed pairs on the GPU -- or, with
+        constrained=True, ConstrainedNearOptimal::enumerate (cw.h:60-284) with subopt_flags = one array of Lt+2 flags per
+        listed pair (None = all true).
         Returns a list (one entry per listed pair) of (status, threshold, [(score, pairs[(len,2)]) in depth-first order])."""
         ids = np.ascontiguousarray(pair_ids, np.int64)
         n, K = len(ids), int(max_alignments)
         off = np.zeros(n + 1, np.int64)
-        self._ck(self.L.aadp_batch_near_optimal(self.h, _ptr(ids), n, delta_ratio, K, None, None, None, None, _ptr(off),
-                                                None, 0, None))
+        if constrained:
+            fl, fo = None, None
+            if subopt_flags is not None:
+                fo = np.zeros(n + 1, np.int64)
+                fo[1:] = np.cumsum([len(f) for f in subopt_flags])
+                fl = np.ascontiguousarray(np.concatenate([np.asarray(f, np.uint8) for f in subopt_flags]), np.uint8)
+
+            def call(*a):
+                return self.L.aadp_batch_near_optimal_constrained(self.h, _ptr(ids), n, _ptr(fl), _ptr(fo), delta_ratio, K, *a)
+        else:
+            def call(*a):
+                return self.L.aadp_batch_near_optimal(self.h, _ptr(ids), n, delta_ratio, K, *a)
+        self._ck(call(None, None, None, None, _ptr(off), None, 0, None))
         n_ali, st = np.zeros(n, np.int32), np.zeros(n, np.int32)
         scores, ln = np.zeros((n, K), np.float32), np.zeros((n, K), np.int32)
         paths = np.zeros((max(int(off[-1]), 1), 2), np.int32)
         thr = np.zeros(n, np.float32)
-        self._ck(self.L.aadp_batch_near_optimal(self.h, _ptr(ids), n, delta_ratio, K, _ptr(n_ali), _ptr(st), _ptr(scores),
-                                                _ptr(ln), _ptr(off), _ptr(paths), int(off[-1]), _ptr(thr)))
+        self._ck(call(_ptr(n_ali), _ptr(st), _ptr(scores), _ptr(ln), _ptr(off), _ptr(paths), int(off[-1]), _ptr(thr)))
         out = []
         for k in range(n):
             slot = (off[k + 1] - off[k]) // K

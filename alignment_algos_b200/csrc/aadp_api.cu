@@ -158,7 +158,7 @@ struct aadp_ctx {
   float last_delta = -1.f;
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
-  DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr;
+  DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -1013,7 +1013,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
                    &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
-                   &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr};
+                   &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr, &c->ucw_plen, &c->ucw_pathbuf, &c->ucw_flags, &c->ucw_flag_off};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
   if (c->pin_flag) cudaFreeHost(c->pin_flag);
@@ -2134,9 +2134,13 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   return 0;
 }
 
-int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, float delta_ratio, int32_t max_alignments,
-                            int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len, int64_t* path_off, int32_t* paths,
-                            int64_t paths_cap, float* threshold) {
+}  // extern "C"
+
+// UnconstrainedNearOptimal (cno = 0) / ConstrainedNearOptimal (cno = 1, flags = SuboptFlags per template position of
+// every listed pair, flag_off = n+1 offsets; flags == nullptr: all true) of the listed pairs.
+static int near_optimal_impl(aadp_ctx* c, int cno, const uint8_t* flags, const int64_t* flag_off, const int64_t* pair_ids,
+                             int64_t n, float delta_ratio, int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores,
+                             int32_t* ali_len, int64_t* path_off, int32_t* paths, int64_t paths_cap, float* threshold) {
   if (check_ctx(c, true)) return 1;
   Batch& b = c->b;
   if (n < 0 || (n && !pair_ids)) return fail("null input");
@@ -2144,6 +2148,8 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
   if (c->sc.local) return fail("aadp_batch_near_optimal: not for local alignments");
   if (!(b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
   if (!c->float_mode && !(b.ran_what & (AADP_W_SCORES | AADP_W_MASK))) return fail("score matrices were not kept (run with AADP_W_SCORES or AADP_W_MASK)");
+  if (cno && !c->float_mode && !(b.ran_what & AADP_W_TB)) return fail("the constrained enumeration follows the optimal predecessors: run with AADP_W_TB");
+  if (flags && !flag_off) return fail("null input");
   std::vector<int64_t> poff((size_t)n + 1, 0), soff((size_t)n + 1, 0);
   for (int64_t k = 0; k < n; ++k) {
     const int64_t p = pair_ids[k];
@@ -2151,14 +2157,26 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
     const int64_t Lq = b.seq_off[b.pair_q[p] + 1] - b.seq_off[b.pair_q[p]];
     poff[(size_t)k + 1] = poff[(size_t)k] + (int64_t)max_alignments * (Lq + 2);  // an alignment has at most Lq+2 pairs
     soff[(size_t)k + 1] = soff[(size_t)k] + (Lq + 2);
+    if (flags) {
+      const int64_t Lt = b.seq_off[b.pair_t[p] + 1] - b.seq_off[b.pair_t[p]];
+      if (flag_off[k + 1] - flag_off[k] != Lt + 2) return fail("SuboptFlags: one flag per template position including both sentinels");
+    }
   }
   if (path_off) memcpy(path_off, poff.data(), (size_t)(n + 1) * 8);
   if (n == 0 || (!n_ali && !status && !scores && !ali_len && !paths && !threshold)) return 0;
   if (paths && paths_cap < poff[(size_t)n]) return fail("aadp_batch_near_optimal: paths buffer too small (needs 2*path_off[n] ints)");
   CK(cudaStreamSynchronize(c->stream));
-  if (pin_reserve(c, (size_t)(n + 1) * 24 + 4096)) return 1;
+  const size_t nflag = flags ? (size_t)(flag_off[n] - flag_off[0]) : 0;
+  if (pin_reserve(c, (size_t)(n + 1) * 32 + nflag + 4096)) return 1;
   std::vector<int64_t> ids(pair_ids, pair_ids + n);
   if (upload_vec(c, c->ucw_ids, ids) || upload_vec(c, c->ucw_path_off, poff) || upload_vec(c, c->ucw_stack_off, soff)) return 1;
+  if (flags) {
+    std::vector<int64_t> fo((size_t)n + 1);
+    for (int64_t k = 0; k <= n; ++k) fo[(size_t)k] = flag_off[k] - flag_off[0];
+    std::vector<uint8_t> fl(flags + flag_off[0], flags + flag_off[n]);
+    if (upload_vec(c, c->ucw_flag_off, fo) || upload_vec(c, c->ucw_flags, fl)) return 1;
+  }
+  if (c->ucw_plen.reserve(std::max<size_t>((size_t)soff[(size_t)n] * 4, 16)) || c->ucw_pathbuf.reserve(std::max<size_t>((size_t)soff[(size_t)n] * 8, 16))) return 1;
   if (c->ucw_paths.reserve(std::max<size_t>((size_t)poff[(size_t)n] * 8, 16)) || c->ucw_stack.reserve(std::max<size_t>((size_t)soff[(size_t)n] * 16, 16)) ||
       c->ucw_len.reserve((size_t)n * max_alignments * 4) || c->ucw_scores.reserve((size_t)n * max_alignments * 4) ||
       c->ucw_n.reserve((size_t)n * 4) || c->ucw_status.reserve((size_t)n * 4) || c->ucw_thr.reserve((size_t)n * 4)) return 1;
@@ -2180,6 +2198,12 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
   U.st_mode_v1 = b.st_mode;
   U.bias16 = kBias16;
   U.fin_score = c->fin_score[0].as<int32_t>();
+  U.tb = (!c->float_mode && (b.ran_what & AADP_W_TB)) ? c->tb[0].as<uint8_t>() : nullptr;
+  U.tb_off = c->tb_off.as<int64_t>();
+  U.subopt = flags ? c->ucw_flags.as<uint8_t>() : nullptr;
+  U.subopt_off = flags ? c->ucw_flag_off.as<int64_t>() : nullptr;
+  U.frame_plen = c->ucw_plen.as<int32_t>();
+  U.pathbuf = c->ucw_pathbuf.as<int2>();
   U.ids = c->ucw_ids.as<int64_t>();
   U.n = (int)n;
   U.delta_ratio = delta_ratio;
@@ -2195,8 +2219,9 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
   U.stack = c->ucw_stack.as<int4>();
   c->launches = 0;
   if (!c->float_mode) {
-    c->prof_begin("ucw_enum_kernel", 0);
-    ucw_enum_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
+    c->prof_begin(cno ? "ucw_enum_kernel<CNO=1>" : "ucw_enum_kernel<CNO=0>", 0);
+    if (cno) ucw_enum_kernel<1><<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
+    else ucw_enum_kernel<0><<<(unsigned)((n * 32 + 127) / 128), 128, 0, c->stream>>>(U);
     c->prof_end();
     CK(cudaGetLastError());
     c->launches++;
@@ -2222,8 +2247,10 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
       V.n_ali = U.n_ali + k;
       V.status = U.status + k;
       V.threshold = U.threshold + k;
+      if (flags) V.subopt_off = U.subopt_off + k;
       c->prof_begin("ucw_enum_kernel (exact float)", 0);
-      ucw_enum_kernel<<<1, 128, 0, c->stream>>>(V);
+      if (cno) ucw_enum_kernel<1><<<1, 128, 0, c->stream>>>(V);
+      else ucw_enum_kernel<0><<<1, 128, 0, c->stream>>>(V);
       c->prof_end();
       CK(cudaGetLastError());
       c->launches++;
@@ -2242,6 +2269,23 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
     return fail("device to host copy failed");
   CK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+extern "C" {
+
+int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, float delta_ratio, int32_t max_alignments,
+                            int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len, int64_t* path_off, int32_t* paths,
+                            int64_t paths_cap, float* threshold) {
+  return near_optimal_impl(c, 0, nullptr, nullptr, pair_ids, n, delta_ratio, max_alignments, n_ali, status, scores, ali_len,
+                           path_off, paths, paths_cap, threshold);
+}
+
+int aadp_batch_near_optimal_constrained(aadp_ctx* c, const int64_t* pair_ids, int64_t n, const uint8_t* subopt_flags,
+                                        const int64_t* flag_off, float delta_ratio, int32_t max_alignments, int32_t* n_ali,
+                                        int32_t* status, float* scores, int32_t* ali_len, int64_t* path_off, int32_t* paths,
+                                        int64_t paths_cap, float* threshold) {
+  return near_optimal_impl(c, 1, subopt_flags, flag_off, pair_ids, n, delta_ratio, max_alignments, n_ali, status, scores, ali_len,
+                           path_off, paths, paths_cap, threshold);
 }
 
 int aadp_fill_subpair(aadp_ctx* c, const uint8_t* q, int Lq, const uint8_t* t, int Lt, int q1_end, int t1_end, int q2_beg,

@@ -14,6 +14,12 @@
 // the row-major blob of the int32 kernels) -- no dense matrix is expanded.  Batch-level parallelism: one warp per
 // listed pair, thousands of pairs per launch.
 //
+// ConstrainedNearOptimal (cw.h:60-284, template CNO=1) is the same walk with branching restricted by per-template-
+// position SuboptFlags: after every accepted branch the optimal predecessors (DPCell::prev_*, here the packed traceback
+// decoded on the fly) are followed until the flag changes state (cw.h:247-272, rule #1), and only there the candidates
+// are scanned again.  Both variants share one kernel: the current partial alignment lives in a per-warp path buffer,
+// a frame remembers its length.
+//
 // Arithmetic is the reference's fp32 in the reference's order: r = curr + sim; (f + r) - g > thr; score = r - g;
 // leaf: score += D[q0][t0].score.  On the dyadic grid the integer kernels require, every value is exact, so the
 // alignments, their order and their scores are bit-identical.  The opt_path fallback (ucw.h:182-236) is only reachable
@@ -44,6 +50,8 @@ struct UcwParams {
   int st_mode_v1;             // storage of the non-packed pairs: 1 = int16, 2 = int32
   int bias16;                 // bias of the packed int16 domain
   const int32_t* fin_score;   // per pair: D[last][last].score in score units
+  const uint8_t* tb;          // packed forward traceback blob (the optimal walks of cw.h), or null
+  const int64_t* tb_off;
   // exact-float mode (one listed pair per launch): the dense fp32 forward matrix of the general-gap kernel and its
   // predecessors instead of the resident integer products; null otherwise
   const float* denseF;
@@ -53,6 +61,8 @@ struct UcwParams {
   int n;
   float delta_ratio;
   int max_ali;                // output budget per pair
+  const uint8_t* subopt;      // CNO: SuboptFlags per template position (Lt+2 bytes per listed pair), null = all true
+  const int64_t* subopt_off;  // per listed pair
   const int64_t* path_off;    // per listed pair: first slot; alignment a of pair k lives at path_off[k] + a*(Lq+2)
   int2* paths;                // aligned pairs front to back, (0,0) first
   int32_t* ali_len;           // [k*max_ali + a]
@@ -60,10 +70,13 @@ struct UcwParams {
   int32_t* n_ali;             // per listed pair
   int32_t* status;            // per listed pair: 0, 1 = more than max_ali alignments (output truncated), 2 = see above
   float* threshold;           // per listed pair, or null
-  const int64_t* stack_off;   // per listed pair: first frame of its stack (Lq+2 frames)
+  const int64_t* stack_off;   // per listed pair: first entry of its frame stack / path buffer (Lq+2 entries each)
   int4* stack;                // frames: (q0, t0, __float_as_int(curr), next candidate | any<<30)
+  int32_t* frame_plen;        // per frame: length of the path buffer when the frame was entered
+  int2* pathbuf;              // the partial alignment from the final cell down to the current node
 };
 
+template <int CNO>
 __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= P.n) return;
@@ -78,9 +91,10 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
   const int st_mode = fmt == 1 ? 1 : P.st_mode_v1;
   const int bias = fmt == 1 ? P.bias16 : 0;
   const int64_t sco = P.denseF ? 0 : P.sc_off[pair];
+  const uint8_t* tb = (P.denseF || !P.tb) ? nullptr : P.tb + P.tb_off[pair];
   const float inv = P.inv_scale;
-  // DPCell::score of the forward matrix (interior cells and the final cell)
   const int sz2 = Lt + 2;
+  // DPCell::score of the forward matrix (interior cells and the final cell)
   auto F = [&](int i, int j) -> float {
     if (P.denseF) return P.denseF[(int64_t)i * sz2 + j];
     if (i == Lq + 1 && j == Lt + 1) return (float)P.fin_score[pair] * inv;
@@ -94,36 +108,72 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
     return P.subf[(int)qseq[i - 1] * P.A + (int)tseq[j - 1]];
   };
   auto pen = [&](int len) { return __fadd_rn(P.gi, __fmul_rn(P.ge, (float)(len - 1))); };
+  // DPCell::prev_* of an interior cell; false when this batch cannot answer (no traceback kept / the final cell)
+  auto prev = [&](int a, int b, int* pa, int* pb) -> bool {
+    if (P.densePQ) { *pa = P.densePQ[(int64_t)a * sz2 + b]; *pb = P.densePT[(int64_t)a * sz2 + b]; return true; }
+    if (!tb || a > Lq || b > Lt) return false;
+    decode_prev(tb, L, a, b, pa, pb);
+    return true;
+  };
+  // gap penalty of the step (pa,pb) -> (a,b) as opt_path evaluates it (ucw.h:222-226, cw.h:262-266)
+  auto step_gap = [&](int pa, int pb, int a, int b) -> float {
+    if (a - pa == 1) {  // deletion(pq,q0,pt,t0), aasubalib.h:27-51
+      const int len = b - pb - 1;
+      return (len >= 1 && !(P.delfree && (pb == 0 || b == Lt + 1))) ? pen(len) : 0.f;
+    }
+    const int len = a - pa - 1;  // insertion(pq,q0,pt,t0), aasubalib.h:53-77
+    return (len >= 1 && !(P.insfree && (pa == 0 || a == Lq + 1))) ? pen(len) : 0.f;
+  };
+  const uint8_t* so_flags = (CNO && P.subopt) ? P.subopt + P.subopt_off[warp] : nullptr;
+  auto subopt = [&](int t) -> bool { return so_flags ? so_flags[t] != 0 : true; };
+
   const float opt = F(Lq + 1, Lt + 1);
-  const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // ucw.h:81-83
+  const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // ucw.h:81-83, cw.h:86-88
   if (lane == 0 && P.threshold) P.threshold[warp] = thr;
 
   const int cap = Lq + 2;  // every step lowers the query index: at most Lq+2 aligned pairs
   int2* paths = P.paths + P.path_off[warp];
   int4* stack = P.stack + P.stack_off[warp];
+  int32_t* frame_plen = P.frame_plen + P.stack_off[warp];
+  int2* pathbuf = P.pathbuf + P.stack_off[warp];
   int32_t* ali_len = P.ali_len + (int64_t)warp * P.max_ali;
   float* scores = P.scores + (int64_t)warp * P.max_ali;
-  int count = 0, status = 0;
+  int count = 0, status = 0, plen = 0;
+
+  // base case (ucw.h:94-101, cw.h:102-110): the alignment is (0,0), the leaf, then the path buffer back to front
+  auto emit = [&](int lq, int lt, float s) -> bool {
+    if (count >= P.max_ali) { status = 1; return false; }
+    __syncwarp();
+    int2* out = paths + (int64_t)count * cap;
+    const int len = plen + 2;
+    for (int k = lane; k < len; k += 32) out[k] = k == 0 ? make_int2(0, 0) : (k == 1 ? make_int2(lq, lt) : pathbuf[plen + 1 - k]);
+    if (lane == 0) { ali_len[count] = len; scores[count] = s; }
+    ++count;
+    return true;
+  };
+  // opt_path (ucw.h:194-236, cw.h:213-281): follow the stored predecessors from (a,b), extending the alignment and its
+  // score; forced = to the base case, otherwise (cw.h rule #1) until the SuboptFlag of the template position changes.
+  auto walk = [&](int& a, int& b, float& s, bool forced) -> bool {
+    const bool flag = !subopt(b);
+    while (b > 1 && a > 1) {
+      if (!forced && subopt(b) == flag) break;
+      if (lane == 0) pathbuf[plen] = make_int2(a, b);
+      ++plen;
+      s = __fadd_rn(s, sim(a, b));
+      int pa, pb;
+      if (!prev(a, b, &pa, &pb)) { status = 2; return false; }
+      s = __fsub_rn(s, step_gap(pa, pb, a, b));
+      a = pa; b = pb;
+    }
+    return true;
+  };
 
   // frame in registers (uniform across the warp); stack[d] holds the frames below it
   int q0 = Lq + 1, t0 = Lt + 1, next = 0, any = 0, depth = 0;
   float curr = 0.f;
   for (;;) {
     if (q0 == 1 || t0 == 1) {
-      // base case (ucw.h:94-101): the alignment is (0,0), (q0,t0), then the frames from the deepest to the root
-      if (count >= P.max_ali) { status = 1; break; }
-      const float s = __fadd_rn(curr, F(q0, t0));
-      int2* out = paths + (int64_t)count * cap;
-      const int len = depth + 2;
-      for (int k = lane; k < len; k += 32) {
-        int2 v;
-        if (k == 0) v = make_int2(0, 0);
-        else if (k == 1) v = make_int2(q0, t0);
-        else { const int4 f = stack[depth - (k - 1)]; v = make_int2(f.x, f.y); }
-        out[k] = v;
-      }
-      if (lane == 0) { ali_len[count] = len; scores[count] = s; }
-      ++count;
+      if (!emit(q0, t0, __fadd_rn(curr, F(q0, t0)))) break;
     } else {
       const float r = __fadd_rn(curr, sim(q0, t0));  // ucw.h:141
       const int ndel = t0 - 2, total = 1 + ndel + (q0 - 2);
@@ -161,58 +211,35 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
       }
       if (found >= 0) {
         // descend: the child continues slot k (first passing branch) or a copy of `curr` (later ones), ucw.h:145-149
-        if (lane == 0) stack[depth] = make_int4(q0, t0, __float_as_int(curr), (found + 1) | (1 << 30));
-        __syncwarp();
+        if (lane == 0) {
+          stack[depth] = make_int4(q0, t0, __float_as_int(curr), (found + 1) | (1 << 30));
+          frame_plen[depth] = plen;
+          pathbuf[plen] = make_int2(q0, t0);
+        }
+        ++plen;
+        ++depth;
         curr = found == 0 ? r : __fsub_rn(r, cg);
         q0 = cq; t0 = ct; next = 0; any = 0;
-        ++depth;
+        // cw.h:150,163,177: the constrained variant continues with opt_path -- no branching until the flag changes
+        if (CNO && q0 > 1 && t0 > 1 && !walk(q0, t0, curr, false)) break;
         continue;
       }
       if (!any) {
-        // The score fell below the threshold after extending the branch (ucw.h:182-189): only rounding can do that
-        // (exact-float mode); the reference then forces the optimal path to the beginning (opt_path, ucw.h:194-236).
-        if (!P.densePQ) { status = 2; break; }
-        if (count >= P.max_ali) { status = 1; break; }
-        int2* out = paths + (int64_t)count * cap;
-        int m = 0;
-        if (lane == 0) {
-          float s = curr;
-          int a = q0, b = t0;
-          while (a > 1 && b > 1) {
-            s = __fadd_rn(s, sim(a, b));
-            const int pa = P.densePQ[(int64_t)a * sz2 + b], pb = P.densePT[(int64_t)a * sz2 + b];
-            float g = 0.f;
-            if (a - pa == 1) {  // deletion(pq,q0,pt,t0), aasubalib.h:27-51
-              const int len = b - pb - 1;
-              if (len >= 1 && !(P.delfree && (pb == 0 || b == Lt + 1))) g = pen(len);
-            } else {            // insertion(pq,q0,pt,t0), aasubalib.h:53-77
-              const int len = a - pa - 1;
-              if (len >= 1 && !(P.insfree && (pa == 0 || a == Lq + 1))) g = pen(len);
-            }
-            s = __fsub_rn(s, g);
-            a = pa; b = pb;
-            ++m;
-          }
-          s = __fadd_rn(s, F(a, b));
-          out[0] = make_int2(0, 0);
-          a = q0; b = t0;
-          for (int k = 0; k <= m; ++k) {  // n_0 = (q0,t0) ... n_m = the base-case cell, stored back to front
-            out[1 + m - k] = make_int2(a, b);
-            if (k < m) { const int pa = P.densePQ[(int64_t)a * sz2 + b], pb = P.densePT[(int64_t)a * sz2 + b]; a = pa; b = pb; }
-          }
-          ali_len[count] = depth + m + 2;
-          scores[count] = s;
-        }
-        m = __shfl_sync(0xffffffffu, m, 0);
-        for (int k = lane; k < depth; k += 32) { const int4 f = stack[depth - 1 - k]; out[m + 2 + k] = make_int2(f.x, f.y); }
-        ++count;
+        // The score fell below the threshold after extending the branch (ucw.h:182-189, cw.h:195-201): only rounding can
+        // do that; the reference then forces the optimal path to the beginning.
+        int a = q0, b = t0;
+        float s = curr;
+        if (!walk(a, b, s, true)) break;
+        if (!emit(a, b, __fadd_rn(s, F(a, b)))) break;
       }
     }
     // return to the parent frame
     if (depth == 0) break;
     --depth;
+    __syncwarp();
     const int4 f = stack[depth];
     q0 = f.x; t0 = f.y; curr = __int_as_float(f.z); next = f.w & 0x3fffffff; any = (f.w >> 30) & 1;
+    plen = frame_plen[depth];
   }
   if (lane == 0) { P.n_ali[warp] = count; P.status[warp] = status; }
 }

@@ -248,6 +248,18 @@ int aadp_batch_near_optimal(aadp_ctx* ctx, const int64_t* pair_ids, int64_t n, f
                             int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
                             int64_t* path_off, int32_t* paths, int64_t paths_cap, float* threshold);
 
+/* The constrained variant: ConstrainedNearOptimal::enumerate (cw.h:60-284) up to its final sortSet.  Branching is
+ * restricted by SuboptFlags (cw.h:62-63, built per template position as nalign.cpp:84 does): after every accepted branch
+ * the optimal predecessors are followed (opt_path, cw.h:213-281, here the packed traceback decoded on the fly) until
+ * the flag of the template position changes state, and only there the candidates are scanned again.
+ *   subopt_flags / flag_off: one byte per template position INCLUDING both sentinels for every listed pair, pair k at
+ *   subopt_flags[flag_off[k] .. flag_off[k+1]) (Lt+2 bytes); subopt_flags == NULL means all true.
+ * Needs AADP_W_TB in addition to what aadp_batch_near_optimal needs.  Outputs as above.                          */
+int aadp_batch_near_optimal_constrained(aadp_ctx* ctx, const int64_t* pair_ids, int64_t n, const uint8_t* subopt_flags,
+                                        const int64_t* flag_off, float delta_ratio, int32_t max_alignments,
+                                        int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
+                                        int64_t* path_off, int32_t* paths, int64_t paths_cap, float* threshold);
+
 /* ---- packed traceback format helpers (host side, no GPU needed) ---------------------------
  * Row stride in bytes of the ROW-MAJOR packed traceback (int32 kernels) for template length Lt. */
 int64_t aadp_tb_row_bytes(int Lt);

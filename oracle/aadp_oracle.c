@@ -664,3 +664,91 @@ long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, co
   *status = (int)u.status;
   return u.count;
 }
+
+/* ---------------------------------------------------------------- constrained enumeration (cw.h:60-284) */
+
+/* ConstrainedNearOptimal: the Waterman branching of cw.h:94-210 alternating with opt_path (cw.h:213-281), which
+ * follows the stored predecessors until the SuboptFlag of the template position changes state (rule #1, cw.h:247-256)
+ * -- or to the base case when forced.  The partial alignment is kept as a node list from the final cell downwards
+ * (u->stack / u->depth), an alignment is emitted at every base case in the reference's slot order.            */
+typedef struct {
+  ucwe_t u;
+  const uint8_t* subopt; /* sz2 flags, NULL = all true */
+} cnoe_t;
+
+static int cno_flag(const cnoe_t* c, int t) { return c->subopt ? (c->subopt[t] != 0) : 1; }
+static void cno_branch(cnoe_t* c, int q0, int t0, float score, int force_opt);
+
+static void cno_leaf(ucwe_t* u, int q0, int t0, float score) {
+  if (u->count >= u->limit) { u->status = 1; return; }
+  int* out = u->pairs + (size_t)u->count * u->sz1 * 2;
+  int n = 0;
+  out[0] = 0; out[1] = 0; ++n;
+  out[2] = q0; out[3] = t0; ++n;
+  for (int d = u->depth - 1; d >= 0; --d, ++n) { out[2 * n] = u->stack[2 * d]; out[2 * n + 1] = u->stack[2 * d + 1]; }
+  u->ali_len[u->count] = n;
+  u->scores[u->count] = score + u->F[(size_t)q0 * u->sz2 + t0];
+  ++u->count;
+}
+
+static void cno_opt_path(cnoe_t* c, int q0, int t0, float score, int force_opt) { /* cw.h:213-281 */
+  ucwe_t* u = &c->u;
+  if (u->status) return;
+  if (q0 == 1 || t0 == 1) { cno_leaf(u, q0, t0, score); return; }
+  int sz2 = u->sz2, depth0 = u->depth;
+  int flag = !cno_flag(c, t0);
+  int pq = -1, pt = -1;
+  while (t0 > 1 && q0 > 1) {
+    if (!force_opt && cno_flag(c, t0) == flag) break;
+    u->stack[2 * u->depth] = q0; u->stack[2 * u->depth + 1] = t0; ++u->depth;
+    score += u->sim[(size_t)q0 * sz2 + t0];
+    pq = u->pq[(size_t)q0 * sz2 + t0];
+    pt = u->pt[(size_t)q0 * sz2 + t0];
+    float g = (q0 - pq == 1) ? orc_deletion(u->sc, u->sz2, pt, t0) : orc_insertion(u->sc, u->sz1, pq, q0);
+    score -= g;
+    t0 = pt; q0 = pq;
+  }
+  cno_branch(c, pq, pt, score, force_opt);
+  u->depth = depth0;
+}
+
+static void cno_branch(cnoe_t* c, int q0, int t0, float curr, int force_opt) { /* cw.h:94-210 */
+  ucwe_t* u = &c->u;
+  if (u->status) return;
+  if (q0 == 1 || t0 == 1) { cno_leaf(u, q0, t0, curr); return; }
+  if (force_opt) { cno_opt_path(c, q0, t0, curr, 1); return; }
+  int sz2 = u->sz2, any = 0;
+  float r = curr + u->sim[(size_t)q0 * sz2 + t0];
+  float f = u->F[(size_t)(q0 - 1) * sz2 + (t0 - 1)];
+  u->stack[2 * u->depth] = q0; u->stack[2 * u->depth + 1] = t0; ++u->depth;
+  if (f + r > u->thr) { any = 1; cno_opt_path(c, q0 - 1, t0 - 1, r, 0); }
+  for (int i = t0 - 2; i > 0 && !u->status; --i) {
+    f = u->F[(size_t)(q0 - 1) * sz2 + i];
+    float g = orc_deletion(u->sc, u->sz2, i, t0);
+    if (f + r - g > u->thr) { any = 1; cno_opt_path(c, q0 - 1, i, r - g, 0); }
+  }
+  for (int j = q0 - 2; j > 0 && !u->status; --j) {
+    f = u->F[(size_t)j * sz2 + (t0 - 1)];
+    float g = orc_insertion(u->sc, u->sz1, j, q0);
+    if (f + r - g > u->thr) { any = 1; cno_opt_path(c, j, t0 - 1, r - g, 0); }
+  }
+  --u->depth;
+  if (!any && !u->status) cno_opt_path(c, q0, t0, curr, 1); /* cw.h:195-201 */
+}
+
+long orc_cno_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                       const int* prev_q, const int* prev_t, const uint8_t* subopt_flags) {
+  cnoe_t c;
+  ucwe_t* u = &c.u;
+  u->pq = prev_q; u->pt = prev_t;
+  u->sc = sc; u->F = F; u->sim = sim; u->sz1 = Lq + 2; u->sz2 = Lt + 2; u->thr = thr;
+  u->count = 0; u->limit = max_alignments; u->status = 0; u->depth = 0;
+  u->stack = (int*)malloc(sizeof(int) * 2 * (size_t)(Lq + 3));
+  u->scores = scores; u->ali_len = ali_len; u->pairs = pairs;
+  c.subopt = subopt_flags;
+  cno_branch(&c, u->sz1 - 1, u->sz2 - 1, 0.f, 0);
+  free(u->stack);
+  *status = (int)u->status;
+  return u->count;
+}

@@ -101,6 +101,13 @@ long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, co
                        long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
                        const int* prev_q, const int* prev_t);
 
+/* ConstrainedNearOptimal::enumerate (cw.h:60-284) up to its final sortSet: branching restricted by SuboptFlags
+ * (one byte per template position incl. sentinels, NULL = all true; rule #1 of cw.h:247-256).  Same output layout
+ * as orc_ucw_enumerate; prev_q/prev_t are required (the optimal walks between the branch points).           */
+long orc_cno_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                       long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                       const int* prev_q, const int* prev_t, const uint8_t* subopt_flags);
+
 #ifdef __cplusplus
 }
 #endif

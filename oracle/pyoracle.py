@@ -114,6 +114,24 @@ class Oracle:
                                        _p(np.ascontiguousarray(pt, np.int32), C.c_int) if pt is not None else None)
         return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
 
+    def cno_enumerate(self, q, t, F, sim, thr, pq, pt, flags=None, max_alignments=20000):
+        """orc_cno_enumerate (cw.h): (status, [(score, pairs)]) in the reference's slot order."""
+        Lq, Lt = len(q), len(t)
+        K = int(max_alignments)
+        scores = np.zeros(K, np.float32)
+        ln = np.zeros(K, np.int32)
+        pairs = np.zeros((K, Lq + 2, 2), np.int32)
+        st = C.c_int(0)
+        fl = np.ascontiguousarray(flags, np.uint8) if flags is not None else None
+        self.lib.orc_cno_enumerate.restype = C.c_long
+        n = self.lib.orc_cno_enumerate(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
+                                       _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
+                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
+                                       _p(np.ascontiguousarray(pq, np.int32), C.c_int),
+                                       _p(np.ascontiguousarray(pt, np.int32), C.c_int),
+                                       _p(fl, C.c_uint8) if fl is not None else None)
+        return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
+
     @staticmethod
     def fill_tab(sim, del_tab, ins_tab, is_local=False, direction=FWD, repro_rev_bug=True):
         """orc_fill_tab: the literal fill for any evaluator given as tables (see aadp_oracle.h)."""
@@ -358,15 +376,19 @@ class Reference:
             raise RuntimeError(self.lib.ref_last_error().decode())
         return union, n.value, scores[: min(n.value, max_scores)].copy(), thr.value
 
-    def ucw_alignments(self, q, t, delta_ratio, max_alignments=20000):
-        """Every alignment of the reference's UnconstrainedNearOptimal (sorted by its sortSet): [(score, pairs)]."""
+    def ucw_alignments(self, q, t, delta_ratio, max_alignments=20000, which=0, flags=None):
+        """Every alignment of the reference's UnconstrainedNearOptimal (which=0) or ConstrainedNearOptimal (which=1,
+        flags = SuboptFlags per template position incl. sentinels, None = all true), sorted by its sortSet."""
         K = int(max_alignments)
+        fl = None
+        if flags is not None:
+            fl = "".join("1" if f else "0" for f in flags).encode()
         cap = K * (len(q) + 2)
         scores = np.zeros(K, np.float32)
         ln = np.zeros(K, np.int32)
         pairs = np.zeros((cap, 2), np.int32)
         n, tot = C.c_int(0), C.c_long(0)
-        rc = self.lib.ref_ucw_alignments(*self._args(q, t), C.c_float(delta_ratio), K, C.c_long(cap), C.byref(n),
+        rc = self.lib.ref_ucw_alignments(*self._args(q, t), C.c_float(delta_ratio), int(which), fl, K, C.c_long(cap), C.byref(n),
                                          C.byref(tot), _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int))
         if rc == 5:
             raise OverflowError("%d alignments" % n.value)

@@ -386,12 +386,13 @@ int ref_nearopt(const char* q, const char* t, const char* matrix_file, float gi,
   }
 }
 
-// Every alignment UnconstrainedNearOptimal::enumerate (ucw.h:63-86) produces, with its score and its aligned pairs, in
+// Every alignment UnconstrainedNearOptimal::enumerate (ucw.h:63-86; which = 0) or ConstrainedNearOptimal::enumerate
+// (cw.h:67-92; which = 1 with SuboptFlags `flags`, one char '0'/'1' per template position, NULL = all true) produces, with its score and its aligned pairs, in
 // the order the reference leaves them in (sorted by sortSet; number_suboptimal is forced huge so nothing is dropped).
 // pairs: concatenated (query_idx, template_idx); alignment k has ali_len[k] of them.  Returns 5 when the buffers are
 // too small (n_alignments / total pairs are still reported).
 int ref_ucw_alignments(const char* q, const char* t, const char* matrix_file, float gi, float ge, int align_type,
-                       float delta_ratio, int max_alignments, long max_pairs, int* n_alignments, long* total_pairs,
+                       float delta_ratio, int which, const char* flags, int max_alignments, long max_pairs, int* n_alignments, long* total_pairs,
                        float* scores, int* ali_len, int* pairs) {
   try {
     AASequence qs, ts;
@@ -407,8 +408,17 @@ int ref_ucw_alignments(const char* q, const char* t, const char* matrix_file, fl
     Optimal<AASequence, AASequence, AAEval> opt(ap.align_type);
     AlignmentSet<AASequence, AASequence, AAEval> as(dpm, opt);
     as.clear();
-    UnconstrainedNearOptimal<AASequence, AASequence, AAEval> u(np);
-    u.enumerate(dpm, as);
+    if (which == 0) {
+      UnconstrainedNearOptimal<AASequence, AASequence, AAEval> u(np);
+      u.enumerate(dpm, as);
+    } else {  // cw.h with SuboptFlags built as nalign.cpp:84 does (one flag per template position)
+      int sz2 = dpm.getTemplateSize();
+      SuboptFlags sf(true, (size_t)sz2);
+      if (flags)
+        for (int j = 0; j < sz2; ++j) sf.Set(j, flags[j] != '0');
+      ConstrainedNearOptimal<AASequence, AASequence, AAEval> cn(np, sf);
+      cn.enumerate(dpm, as);
+    }
     *n_alignments = (int)as.size();
     long tot = 0;
     bool fits = (int)as.size() <= max_alignments;

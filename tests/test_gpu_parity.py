@@ -750,6 +750,52 @@ def test_near_optimal_enumeration_on_gpu(blosum):
     c.close()
 
 
+def test_constrained_near_optimal_enumeration_on_gpu(blosum):
+    # aadp_batch_near_optimal_constrained: ConstrainedNearOptimal::enumerate (cw.h:60-284) -- branching only where the
+    # SuboptFlag of the template position changes state, optimal predecessors (packed traceback) in between
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(91)
+    for gi, ge, at, delta in [(3, 1, po.SEMI_LOCAL, 0.2), (12, 1, po.GLOBAL, 0.15), (4.73, 0.34, po.GLOBAL_LOCAL, 0.2)]:
+        seqs = []
+        for k in range(16):
+            L = int(rng.integers(8, 60))
+            s = rng.integers(0, 20, L).astype(np.uint8)
+            m = s.copy()
+            m[::4] = rng.integers(0, 20, len(m[::4]))
+            seqs += [s, np.concatenate([m[: L // 2], m[L // 2 + int(rng.integers(0, 3)):]])]
+        seqs += [rng.integers(0, 20, L).astype(np.uint8) for L in (0, 1, 520)]
+        res, off = a.Context.pack(seqs)
+        pq = np.array(list(range(0, 32, 2)) + [32, 33, 34, 5], np.int32)
+        pt = np.array(list(range(1, 32, 2)) + [3, 33, 7, 34], np.int32)
+        c = a.Context(0)
+        c.set_scoring(M, gi, ge, at)
+        c.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB | a.W_MASK, delta)
+        ids = np.arange(len(pq))
+        O = po.Oracle(M, gi, ge, at)
+        total = 0
+        for mode in ("all", "stripes", "random"):
+            flags = []
+            for p in ids:
+                n = len(seqs[pt[p]]) + 2
+                flags.append({"all": np.ones(n, np.uint8), "stripes": ((np.arange(n) // 4) % 2).astype(np.uint8),
+                              "random": rng.integers(0, 2, n).astype(np.uint8)}[mode])
+            got = c.near_optimal(ids, delta, 3000, subopt_flags=None if mode == "all" else flags, constrained=True)
+            for k, p in enumerate(ids):
+                q, t = seqs[pq[p]], seqs[pt[p]]
+                F, fq, ft = O.fill(q, t, po.FWD, True, fast=(gi != 4.73))
+                thr = O.threshold(float(F[-1, -1]), delta)
+                st, want = O.cno_enumerate(q, t, F, O.sim(q, t), thr, fq, ft, flags[k], 3000)
+                gst, gthr, alis = got[k]
+                assert (gst, gthr, len(alis)) == (st, thr, len(want)), (mode, p, gst, st, len(alis), len(want))
+                total += len(alis)
+                for (gs, gp), (ws, wp) in zip(alis, want):
+                    assert gs == ws
+                    assert_matrix_equal("%s pair %d alignment" % (mode, p), gp, wp)
+        assert total > 3 * len(ids)
+        c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a

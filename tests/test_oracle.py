@@ -245,3 +245,29 @@ def test_oracle_ucw_enumeration_matches_reference(blosum):
                 assert _canon(alis) == _canon(ref), (at, gi, Lq, Lt)
                 total += len(alis)
     assert total > 2000
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_constrained_enumeration_matches_reference(blosum):
+    # orc_cno_enumerate == ConstrainedNearOptimal::enumerate (cw.h:60-284) for all-true, striped, random and all-false
+    # SuboptFlags; integer and default float scoring
+    alpha, M = blosum
+    rng = np.random.default_rng(12)
+    total = 0
+    for at in (po.GLOBAL, po.SEMI_LOCAL, po.GLOBAL_LOCAL):
+        for gi, ge in ((3, 1), (4.73, 0.34)):
+            O = po.Oracle(M, gi, ge, at)
+            R = po.Reference(alpha, M, gi, ge, at)
+            for Lq, Lt, delta in ((30, 30, 0.25), (12, 40, 0.5), (33, 33, 0.2), (1, 4, 0.2), (0, 3, 0.2)):
+                q = rng.integers(0, 20, Lq).astype(np.uint8)
+                t = q.copy() if Lq == Lt else rng.integers(0, 20, Lt).astype(np.uint8)
+                t[::4] = rng.integers(0, 20, len(t[::4]))
+                F, pq, pt = O.fill(q, t, po.FWD, True, fast=False)
+                thr = O.threshold(float(F[-1, -1]), delta)
+                for flags in (None, (np.arange(Lt + 2) // 5) % 2, rng.integers(0, 2, Lt + 2), np.zeros(Lt + 2, int)):
+                    st, alis = O.cno_enumerate(q, t, F, O.sim(q, t), thr, pq, pt, flags, 100000)
+                    assert st == 0
+                    ref = R.ucw_alignments(q, t, delta, 100000, 1, flags)
+                    assert _canon(alis) == _canon(ref), (at, gi, Lq, Lt)
+                    total += len(alis)
+    assert total > 1000
