@@ -113,8 +113,10 @@ class DPMatrix {
   // ---- extension: the near-optimal ALIGNMENTS themselves, enumerated on the GPU (aadp_batch_near_optimal =
   // UnconstrainedNearOptimal::branch, ucw.h:88-191) in the reference's depth-first slot order; include/hmap2/ucw.h
   // is the enumerator class on top of it.  budget = maximum number of alignments; *overflow tells when there are more.
+  // subopt_flags != 0: the constrained enumeration of cw.h with one flag per template position (sentinels included).
   template <class Alignment>
-  void nearOptimalAlignments(float delta_ratio, int budget, std::vector<Alignment>* out, bool* overflow) {
+  void nearOptimalAlignments(float delta_ratio, int budget, std::vector<Alignment>* out, bool* overflow,
+                             const std::vector<unsigned char>* subopt_flags = 0) {
     std::string alphabet;
     std::vector<float> sub;
     float gi, ge;
@@ -129,15 +131,21 @@ class DPMatrix {
     aadp_ctx* ctx = aadp::default_context();
     aadp::check(aadp_set_scoring(ctx, sub.data(), (int)alphabet.size(), gi, ge, at, AADP_REPRO_REV_BUG));
     float fs = 0.f;
-    aadp::check(aadp_fill_batch(ctx, residues.data(), seq_off, 2, &pq, &pt, 1, AADP_W_FWD | AADP_W_SCORES, delta_ratio, &fs, 0, 0, 0));
+    aadp::check(aadp_fill_batch(ctx, residues.data(), seq_off, 2, &pq, &pt, 1, AADP_W_FWD | AADP_W_SCORES | AADP_W_TB, delta_ratio,
+                                &fs, 0, 0, 0));
     const int64_t id = 0;
     int64_t off[2] = {0, 0};
+    const int64_t flag_off[2] = {0, subopt_flags ? (int64_t)subopt_flags->size() : 0};
     aadp::check(aadp_batch_near_optimal(ctx, &id, 1, delta_ratio, budget, 0, 0, 0, 0, off, 0, 0, 0));
     std::vector<int32_t> paths(2 * (size_t)off[1] + 2), len((size_t)budget);
     std::vector<float> scores((size_t)budget);
     int32_t n = 0, status = 0;
-    aadp::check(aadp_batch_near_optimal(ctx, &id, 1, delta_ratio, budget, &n, &status, scores.data(), len.data(), off,
-                                        paths.data(), off[1], 0));
+    if (subopt_flags)
+      aadp::check(aadp_batch_near_optimal_constrained(ctx, &id, 1, subopt_flags->data(), flag_off, delta_ratio, budget, &n, &status,
+                                                      scores.data(), len.data(), off, paths.data(), off[1], 0));
+    else
+      aadp::check(aadp_batch_near_optimal(ctx, &id, 1, delta_ratio, budget, &n, &status, scores.data(), len.data(), off,
+                                          paths.data(), off[1], 0));
     if (status == 2) throw std::string("near-optimal enumeration: a cell without a passing predecessor (ucw.h:182-189)");
     *overflow = status == 1;
     out->clear();

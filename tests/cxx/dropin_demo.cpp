@@ -15,6 +15,7 @@
 #include "aasubalib.h"
 #include "alib.h"
 #include "alignment.h"
+#include "cw.h"
 #include "dpmatrix.h"
 #include "optimal.h"
 #include "noalib.h"
@@ -77,6 +78,24 @@ int main(int argc, char** argv) {
       std::printf("@UCW count %d\n", (int)near.size());
       for (size_t k = 0; k < near.size(); ++k) {
         std::printf("@UCW score %.6g identity %.6g pairs", near[k].score, near[k].identity);
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = near[k].begin(); it != near[k].end(); ++it)
+          std::printf(" %d:%d", it->query_idx(), it->template_idx());
+        std::printf("\n");
+      }
+    }
+    // ... and the constrained variant (cw.h) with suboptimal regions marked on every second block of four template
+    // positions (SuboptFlags as nalign.cpp:84-91 builds them)
+    if (params.align_type != local && query.size() * templ.size() < 4000) {
+      NOaliParams np;
+      np.delta_ratio = 0.25f;
+      np.number_suboptimal = 50000;
+      SuboptFlags flags(true, templ.size());
+      for (unsigned int j = 0; j < templ.size(); ++j) flags.Set(j, (j / 4) % 2 == 0);
+      ConstrainedNearOptimal<AASequence, AASequence, AAEval> cno(np, flags);
+      AlignmentSet<AASequence, AASequence, AAEval> near(forward, cno);
+      std::printf("@CNO count %d\n", (int)near.size());
+      for (size_t k = 0; k < near.size(); ++k) {
+        std::printf("@CNO score %.6g identity %.6g pairs", near[k].score, near[k].identity);
         for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = near[k].begin(); it != near[k].end(); ++it)
           std::printf(" %d:%d", it->query_idx(), it->template_idx());
         std::printf("\n");
