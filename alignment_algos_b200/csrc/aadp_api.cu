@@ -159,7 +159,8 @@ struct aadp_ctx {
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
-  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2];
+  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2];
+  int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
   uint8_t* pin = nullptr;
@@ -1012,7 +1013,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->gg_pm[0], &c->gg_pm[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
                    &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr, &c->ucw_plen, &c->ucw_pathbuf, &c->ucw_flags, &c->ucw_flag_off};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
@@ -1044,6 +1045,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   // exact_float = 1: route everything through the exact general-gap fp32 kernel (takes effect at the next
   // aadp_set_scoring); scoring that is not on a dyadic grid always uses it
   if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
+  if (!strcmp(key, "general_prune")) { c->gg_prune = value ? 1 : 0; return 0; }
   if (!strcmp(key, "general_budget_mcells")) { c->gg_budget_cells = (int64_t)std::max(value, 1) * 1000000; return 0; }
   return fail(std::string("unknown option ") + key);
 }
@@ -1487,7 +1489,7 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     maxLt = std::max(maxLt, Lt);
     maxL = std::max(maxL, std::max(Lq, Lt));
   }
-  const size_t smem = (size_t)(maxLt + 2 + maxL + 2) * sizeof(float);
+  const size_t smem = (size_t)(2 * (maxLt + 2) + maxL + 2 + 32) * sizeof(float);
   if (smem > 220 * 1024) return fail("exact general-gap path: sequences too long for the shared-memory row and penalty tables");
   GeneralParams G{};
   G.A = c->sc.A;
@@ -1532,6 +1534,11 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     G.prevq[nd] = tb ? c->gg_pq[d].as<int32_t>() : nullptr;
     G.prevt[nd] = tb ? c->gg_pt[d].as<int32_t>() : nullptr;
     G.fin[nd] = d ? d_fin_rev : d_fin_fwd;
+    G.pmcol[nd] = nullptr;
+    if (c->gg_prune && !(ov && ov->d_del) && G.gi >= 0.f && G.ge >= 0.f) {  // the pruning needs pen(len) to grow with len
+      if (c->gg_pm[d].reserve(std::max<size_t>((size_t)cells * 4, 16))) return 1;
+      G.pmcol[nd] = c->gg_pm[d].as<float>();
+    }
     ++nd;
   }
   if (nd == 0) return 0;

@@ -56,10 +56,27 @@ struct GeneralParams {
   int32_t* prevq[2];         // per direction: dense predecessor rows/cols, or null
   int32_t* prevt[2];
   float* fin[2];             // per direction, per PAIR: score of the final cell, or null
+  float* pmcol[2];           // per direction: dense matrices of column prefix maxima (same offsets as score), or null.
+                             // With them the scans are PRUNED without changing any result: max(D[1..k]) - pen(len) + sim is
+                             // monotone in k (fp32 rounding preserves order, pen grows with len) and bounds every candidate
+                             // up to k, so a binary search finds the first candidate that can still beat the current optimum;
+                             // every earlier one fails the reference's strict '>' anyway.  Not for tabulated penalties.
 };
 
 __device__ __forceinline__ float gg_pen(float gi, float ge, int len) {  // aasubalib.h:37-38
   return __fadd_rn(gi, __fmul_rn(ge, (float)(len - 1)));
+}
+
+// First k in [lo, hi) for which the MONOTONE predicate viable(k) holds (false ... false true ... true), hi if none.
+// Plain binary search: an 8-ary variant (seven independent probes per round) was measured 48 % slower -- the kernel is
+// bound by executed instructions, not by the latency of the probes.
+template <class Pred>
+__device__ __forceinline__ int first_viable(int lo, int hi, Pred viable) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (viable(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
 }
 
 template <int TBM, int TAB = 0>
@@ -93,6 +110,10 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
 
   float* prow = gg_smem;              // D[a-1][0..nt]
   float* pen = gg_smem + (Lt + 2);    // pen[len], len >= 1
+  float* pm = pen + (max(Lq, Lt) + 2);  // pm[k] = max(prow[1..k])  (pruned scans)
+  float* wmax = pm + (Lt + 2);          // 32 warp maxima of the block-wide prefix scan
+  const bool PRUNE = !TAB && P.pmcol[dsel] != nullptr;
+  float* PMC = PRUNE ? P.pmcol[dsel] + base : nullptr;
   const int maxlen = max(nq, nt);
   if (!TAB)
     for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
@@ -179,6 +200,36 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   }
   __syncthreads();
 
+  // inclusive prefix maximum of prow[1..nt] into pm[1..nt] (block-wide: warp shuffles + one hop through shared memory)
+  auto build_pm = [&]() {
+    float carry = -3.0e38f;
+    const int lane = tid & 31, wid = tid >> 5, nw = (nth + 31) >> 5;
+    for (int c0 = 1; c0 <= nt; c0 += nth) {
+      const int b = c0 + tid;
+      float v = b <= nt ? prow[b] : -3.0e38f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = fmaxf(v, u);
+      }
+      if (lane == 31) wmax[wid] = v;
+      __syncthreads();
+      float pre = carry, tot = carry;
+      for (int w = 0; w < nw; ++w) {
+        const float x = wmax[w];
+        if (w < wid) pre = fmaxf(pre, x);
+        tot = fmaxf(tot, x);
+      }
+      if (b <= nt) pm[b] = fmaxf(v, pre);
+      carry = tot;
+      __syncthreads();
+    }
+  };
+  if (PRUNE) {
+    for (int b = 1 + tid; b <= nt; b += nth) PMC[at(1, b)] = prow[b];
+    build_pm();
+  }
+
   // interior rows (dpmatrix.h:446-497): match, deletions k ascending, insertions k ascending, strict '>'
   for (int a = 2; a <= nq; ++a) {
     const float* subrow = simov ? simov + (int64_t)rowof(a) * sz2 : P.subf + (int)qseq[rowof(a) - 1] * P.A;
@@ -189,23 +240,45 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       // tabulated penalties of this cell: deletion column (rows = the other template position), insertion column
       const float* dcol = TAB ? (rev ? P.del_tabT : P.del_tab) + colof(b) : nullptr;
       const float* icol = TAB ? P.ins_tab + t2of(b) : nullptr;
-      if (TBM) {
+      const float* colp = D + at(1, b - 1);
+      const int64_t cstride = rev ? -(int64_t)ld : (int64_t)ld;
+      // Pruned scans: bound(k) = rn(rn(max(D[1..k]) - pen(len)) + sim) is monotone in k and bounds candidate k, so every
+      // candidate before the first k with bound(k) > os fails the reference's strict '>' and is skipped (binary search).
+      // A variant scanning down from the nearest candidate with a running bound was also exact but 60 % slower.
+      int kr = 1, kc = 1;
+      if (PRUNE) {
+        kr = first_viable(1, b - 1, [&](int k) { return clampl(__fadd_rn(__fsub_rn(pm[k], pen[b - k - 1]), simc)) > os; });
+      }
+      if (PRUNE && TBM) {
+        for (int k = kr; k < b - 1; ++k) {  // dpmatrix.h:459-468
+          const float s = clampl(__fadd_rn(__fsub_rn(prow[k], pen[b - k - 1]), simc));
+          if (s > os) { ob = k; os = s; }
+        }
+        const float* pmp = PMC + at(1, b - 1);
+        kc = first_viable(1, a - 1, [&](int k) { return clampl(__fadd_rn(__fsub_rn(pmp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc)) > os; });
+        bool col = false;
+        int ka = 0;
+        for (int k = kc; k < a - 1; ++k) {  // dpmatrix.h:471-480
+          const float s = clampl(__fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc));
+          if (s > os) { col = true; ka = k; os = s; }
+        }
+        if (col) { oa = ka; ob = b - 1; }
+      } else if (PRUNE) {
+#pragma unroll 4
+        for (int k = kr; k < b - 1; ++k) os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], pen[b - k - 1]), simc));
+        const float* pmp = PMC + at(1, b - 1);
+        kc = first_viable(1, a - 1, [&](int k) { return __fadd_rn(__fsub_rn(pmp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc) > os; });
+#pragma unroll 4
+        for (int k = kc; k < a - 1; ++k) os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], pen[a - k - 1]), simc));
+        os = clampl(os);
+      } else if (TBM) {
         for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
           float s = __fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]);
           s = clampl(__fadd_rn(s, simc));
           if (s > os) { ob = k; os = s; }
         }
-      } else {
-        // score only: the strict-'>' scan and a running maximum give the same value; the clamp commutes with max
-#pragma unroll 4
-        for (int k = 1; k < b - 1; ++k)
-          os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]), simc));
-      }
-      bool col = false;
-      int ka = 0;
-      const float* colp = D + at(1, b - 1);
-      const int64_t cstride = rev ? -(int64_t)ld : (int64_t)ld;
-      if (TBM) {
+        bool col = false;
+        int ka = 0;
         for (int k = 1; k < a - 1; ++k) {  // dpmatrix.h:471-480
           float s = __fsub_rn(colp[(int64_t)(k - 1) * cstride], TAB ? icol[(int64_t)(a - k - 1) * sz2] : pen[a - k - 1]);
           s = clampl(__fadd_rn(s, simc));
@@ -213,6 +286,10 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
         }
         if (col) { oa = ka; ob = b - 1; }
       } else {
+        // score only: the strict-'>' scan and a running maximum give the same value; the clamp commutes with max
+#pragma unroll 4
+        for (int k = 1; k < b - 1; ++k)
+          os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]), simc));
 #pragma unroll 4
         for (int k = 1; k < a - 1; ++k)
           os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], TAB ? icol[(int64_t)(a - k - 1) * sz2] : pen[a - k - 1]), simc));
@@ -221,8 +298,13 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       set_tb(a, b, oa, ob, os);
     }
     __syncthreads();  // every thread is done reading the previous row
-    for (int b = 1 + tid; b <= nt; b += nth) prow[b] = D[at(a, b)];  // own cells (b >= 2) and the boundary column
+    for (int b = 1 + tid; b <= nt; b += nth) {  // own cells (b >= 2) and the boundary column
+      const float v = D[at(a, b)];
+      prow[b] = v;
+      if (PRUNE) PMC[at(a, b)] = fmaxf(PMC[at(a - 1, b)], v);
+    }
     __syncthreads();
+    if (PRUNE) build_pm();
   }
 
   // final cell (dpmatrix.h:504-534, 844-874, 654-687, 995-1028): match, bottom row, right column.

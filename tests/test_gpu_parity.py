@@ -796,6 +796,52 @@ def test_constrained_near_optimal_enumeration_on_gpu(blosum):
         c.close()
 
 
+def test_pruned_general_gap_scans_change_nothing(blosum):
+    # "general_prune" (default on) skips scan candidates that provably fail the reference's strict '>' (prefix-maximum
+    # bound + binary search).  Every output must equal the unpruned scan, and the oracle: all align types incl. local,
+    # both directions, whole matrices, sub-rectangles, and the batch scalars.
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(55)
+    for gi, ge, at in [(4.73, 0.34, po.SEMI_LOCAL), (4.73, 0.34, po.LOCAL), (2.17, 0.61, po.GLOBAL), (0.9, 0.0, po.GLOBAL_LOCAL),
+                       (12, 1, po.LOCAL_GLOBAL)]:
+        cp, cn = a.Context(0), a.Context(0)
+        for c, prune in ((cp, 1), (cn, 0)):
+            c.set_option("general_prune", prune)
+            c.set_option("exact_float", 1)
+            c.set_scoring(M, gi, ge, at)
+        O = po.Oracle(M, gi, ge, at)
+        for Lq, Lt in [(2, 2), (3, 40), (61, 5), (97, 130), (150, 620)]:
+            q, t = rand_pair(rng, Lq, Lt)
+            if Lq == 97:
+                t[:90] = q[:90]          # a related pair: the pruning bites hardest there
+            x, y = cp.fill_pair(q, t, a.BOTH, delta_ratio=0.03), cn.fill_pair(q, t, a.BOTH, delta_ratio=0.03)
+            for key in x:
+                if x[key] is not None and key != "threshold":
+                    assert_matrix_equal("prune %s" % key, x[key], y[key])
+            assert x["threshold"] == y["threshold"]
+            if Lq * Lt < 20000:
+                for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+                    ws, wq, wt = O.fill(q, t, d, True, fast=False)
+                    assert_matrix_equal("oracle score", x["score_" + tag], ws)
+                    assert_matrix_equal("oracle pq", x["prevq_" + tag], wq)
+                    assert_matrix_equal("oracle pt", x["prevt_" + tag], wt)
+            rect = (1, 0, Lq, Lt + 1) if Lq > 2 else (0, 0, Lq + 1, Lt + 1)
+            for d in (a.FWD, a.REV):
+                for u, v in zip(cp.fill_subpair(q, t, rect, d), cn.fill_subpair(q, t, rect, d)):
+                    assert_matrix_equal("prune sub-rectangle", u, v)
+        seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(1, 200, 40)]
+        res, off = a.Context.pack(seqs)
+        pq, pt = rng.integers(0, 40, 300).astype(np.int32), rng.integers(0, 40, 300).astype(np.int32)
+        what = a.W_FWD | a.W_REV | (0 if at == po.LOCAL else a.W_MASK)
+        o1, o2 = cp.fill_batch(res, off, pq, pt, what, 0.02), cn.fill_batch(res, off, pq, pt, what, 0.02)
+        for key in o1:
+            if o1[key] is not None:
+                assert_matrix_equal("prune batch %s" % key, o1[key], o2[key])
+        cp.close()
+        cn.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a
