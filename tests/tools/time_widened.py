@@ -3,7 +3,7 @@
   f1  aadp_batch_near_optimal      UCW enumeration of a whole batch (one warp per pair over the resident scores)
   f4  aadp_fill_subpair_batch      loop-closure rectangles + Optimal_Subali in one call
   f3  aadp_fill_pair_tabulated     position-dependent gap penalties (HMAP-shaped tables)
-usage: python profiles/tools/time_widened.py [npairs]   -> one JSON line
+usage: python tests/tools/time_widened.py [npairs]   -> one JSON line
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
