@@ -160,6 +160,7 @@ struct aadp_ctx {
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2];
+  int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -1045,6 +1046,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   // exact_float = 1: route everything through the exact general-gap fp32 kernel (takes effect at the next
   // aadp_set_scoring); scoring that is not on a dyadic grid always uses it
   if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
+  if (!strcmp(key, "general_threads")) { c->gg_threads_cap = std::max(32, std::min(512, value / 32 * 32)); return 0; }
   if (!strcmp(key, "general_prune")) { c->gg_prune = value ? 1 : 0; return 0; }
   if (!strcmp(key, "general_budget_mcells")) { c->gg_budget_cells = (int64_t)std::max(value, 1) * 1000000; return 0; }
   return fail(std::string("unknown option ") + key);
@@ -1567,7 +1569,7 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
       cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
     }
   }
-  const int threads = std::max(compact ? 32 : 64, std::min(512, (width + 31) / 32 * 32));
+  const int threads = std::max(compact ? 32 : 64, std::min(c->gg_threads_cap, (width + 31) / 32 * 32));
   c->prof_begin(tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
   if (tab) {
     CK(cudaFuncSetAttribute(general_fill_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));

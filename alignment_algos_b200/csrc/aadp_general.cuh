@@ -200,35 +200,42 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   }
   __syncthreads();
 
-  // inclusive prefix maximum of prow[1..nt] into pm[1..nt] (block-wide: warp shuffles + one hop through shared memory)
-  auto build_pm = [&]() {
+  // Row hand-over: prow[1..nt] <- row a of D (own cells and the boundary column), the column prefix maxima of that row,
+  // and pm[1..nt] = inclusive prefix maximum of prow (block-wide: warp shuffles + one hop through shared memory).
+  // load_row = false: prow is already in place (the boundary row).  Two barriers per chunk of blockDim columns.
+  auto hand_over = [&](int a, bool load_row) {
     float carry = -3.0e38f;
     const int lane = tid & 31, wid = tid >> 5, nw = (nth + 31) >> 5;
     for (int c0 = 1; c0 <= nt; c0 += nth) {
       const int b = c0 + tid;
-      float v = b <= nt ? prow[b] : -3.0e38f;
+      float v = -3.0e38f;
+      if (b <= nt) {
+        if (load_row) { v = D[at(a, b)]; prow[b] = v; } else v = prow[b];
+        if (PRUNE) PMC[at(a, b)] = a > 1 ? fmaxf(PMC[at(a - 1, b)], v) : v;
+      }
+      if (PRUNE) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v = fmaxf(v, u);
+        for (int o = 1; o < 32; o <<= 1) {
+          const float u = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v = fmaxf(v, u);
+        }
+        if (lane == 31) wmax[wid] = v;
       }
-      if (lane == 31) wmax[wid] = v;
       __syncthreads();
-      float pre = carry, tot = carry;
-      for (int w = 0; w < nw; ++w) {
-        const float x = wmax[w];
-        if (w < wid) pre = fmaxf(pre, x);
-        tot = fmaxf(tot, x);
+      if (PRUNE) {
+        float pre = carry, tot = carry;
+        for (int w = 0; w < nw; ++w) {
+          const float x = wmax[w];
+          if (w < wid) pre = fmaxf(pre, x);
+          tot = fmaxf(tot, x);
+        }
+        if (b <= nt) pm[b] = fmaxf(v, pre);
+        carry = tot;
+        __syncthreads();
       }
-      if (b <= nt) pm[b] = fmaxf(v, pre);
-      carry = tot;
-      __syncthreads();
     }
   };
-  if (PRUNE) {
-    for (int b = 1 + tid; b <= nt; b += nth) PMC[at(1, b)] = prow[b];
-    build_pm();
-  }
+  if (PRUNE) hand_over(1, false);
 
   // interior rows (dpmatrix.h:446-497): match, deletions k ascending, insertions k ascending, strict '>'
   for (int a = 2; a <= nq; ++a) {
@@ -298,13 +305,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       set_tb(a, b, oa, ob, os);
     }
     __syncthreads();  // every thread is done reading the previous row
-    for (int b = 1 + tid; b <= nt; b += nth) {  // own cells (b >= 2) and the boundary column
-      const float v = D[at(a, b)];
-      prow[b] = v;
-      if (PRUNE) PMC[at(a, b)] = fmaxf(PMC[at(a - 1, b)], v);
-    }
-    __syncthreads();
-    if (PRUNE) build_pm();
+    hand_over(a, true);
   }
 
   // final cell (dpmatrix.h:504-534, 844-874, 654-687, 995-1028): match, bottom row, right column.

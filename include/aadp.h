@@ -65,7 +65,8 @@ int aadp_synchronize(aadp_ctx* ctx);
  * "wave" / "wave_min_cells": multi-CTA wavefront for long pairs.  "host_threads": host scheduler
  * threads (0 = min(hardware, 8)).  "exact_float": see aadp_set_scoring.  "general_budget_mcells":
  * scratch budget (10^6 dense cells per direction) of one chunk of an exact-float batch.  "general_prune" (default 1):
- * pruned candidate scans in the exact general-gap kernel (identical results; 0 = scan every candidate).  */
+ * pruned candidate scans in the exact general-gap kernel (identical results; 0 = scan every candidate).
+ * "general_threads" (default 256): CTA size limit of that kernel.                                        */
 int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
 
 /* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)

@@ -10,6 +10,8 @@ seqs, pq, pt = synth.pair_workload(1003, n, 100, 500)
 res, off = a.Context.pack(seqs)
 c = a.Context(0)
 c.set_scoring(M, 4.73, 0.34, a.SEMI_LOCAL)
+if len(sys.argv) > 2:
+    c.set_option("general_threads", int(sys.argv[2]))
 what = a.W_FWD | a.W_REV | a.W_MASK
 c.fill_batch(res, off, pq, pt, what, 0.01)
 c.set_profiling(True)
