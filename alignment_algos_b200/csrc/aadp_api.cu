@@ -2098,9 +2098,9 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
   const int dir = direction - 1;
   if (c->float_mode) return fail("aadp_batch_optimal_all: exact-float mode keeps no packed traceback (use aadp_batch_optimal)");
-  if (c->sc.local) return fail("aadp_batch_optimal_all: local tracebacks go through aadp_batch_fetch_pair (they need find_max)");
   if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
   if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
+  if (c->sc.local && !(b.ran_what & AADP_W_SCORES)) return fail("local tracebacks need AADP_W_SCORES (find_max, optimal.h:107-124)");
   const int64_t np = b.npairs;
   std::vector<int64_t> cap((size_t)np + 1, 0);
   for (int64_t p = 0; p < np; ++p) {
@@ -2130,9 +2130,24 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   T.out = c->ali_out.as<int2>();
   T.out_n = c->ali_n.as<int32_t>();
   T.out_status = c->ali_status.as<int32_t>();
-  c->prof_begin(dir ? "traceback_kernel rev" : "traceback_kernel fwd", 0);
-  traceback_kernel<<<(unsigned)((np + 127) / 128), 128, 0, c->stream>>>(T);
-  c->prof_end();
+  if (c->sc.local) {  // Optimal[_Rev]::enumerate_local + find_max: one warp per pair
+    LocalTraceParams Q{};
+    Q.t = T;
+    Q.sc_blob = c->scb[dir].p;
+    Q.sc_off = c->sc_off.as<int64_t>();
+    Q.st_mode_v1 = b.st_mode;
+    Q.bias16 = kBias16;
+    Q.fin_score = c->fin_score[dir].as<int32_t>();
+    Q.inv_scale = 1.f / (float)(1 << c->sc.scale_log2);
+    Q.out_score = nullptr;
+    c->prof_begin(dir ? "local_traceback_kernel rev" : "local_traceback_kernel fwd", 0);
+    local_traceback_kernel<<<(unsigned)((np * 32 + 127) / 128), 128, 0, c->stream>>>(Q);
+    c->prof_end();
+  } else {
+    c->prof_begin(dir ? "traceback_kernel rev" : "traceback_kernel fwd", 0);
+    traceback_kernel<<<(unsigned)((np + 127) / 128), 128, 0, c->stream>>>(T);
+    c->prof_end();
+  }
   CK(cudaGetLastError());
   c->launches = 1;
   c->d2h_bytes = 0;

@@ -27,6 +27,7 @@
 // walking eopen / fopen bits (see decode_prev below).
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 namespace aadp {
@@ -831,6 +832,109 @@ __global__ void __launch_bounds__(128) traceback_kernel(const TraceParams P) {
     for (int k = 0; k < n; ++k) out[k] = out[cap - n + k];
   P.out_n[pair] = n;
   P.out_status[pair] = ok ? 0 : 3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LOCAL optimal alignments of a whole batch: Optimal::enumerate_local + find_max (optimal.h:76-124) for the forward
+// matrices, Optimal_Rev::enumerate_local + find_max (optimal_rev.h:79-131) for the reverse ones.  One warp per pair:
+// the 32 lanes search the stored score matrix for its first maximum in the reference's scan order (strict '<' over
+// ascending flow coordinates; the starting candidate is D[sz1-2][sz2-2] forward but D[0][0] -- the final cell of the
+// reverse fill -- in reverse, an asymmetry of the reference that is kept), then lane 0 follows the packed traceback
+// until a predecessor with score <= 0.  Scores are compared in integer units (exact).
+// Output slot as in traceback_kernel; (last,last) forward / (0,0) reverse frames the alignment as the reference does.
+// ------------------------------------------------------------------------------------------------
+struct LocalTraceParams {
+  TraceParams t;
+  const void* sc_blob;       // score blob of the direction
+  const int64_t* sc_off;
+  int st_mode_v1;            // storage of the non-packed pairs: 1 = int16, 2 = int32
+  int bias16;
+  const int32_t* fin_score;  // per pair: score of the final flow cell
+  float inv_scale;
+  float* out_score;          // per pair: AlignedPairList::score, or null
+};
+
+__global__ void __launch_bounds__(128) local_traceback_kernel(const LocalTraceParams Q) {
+  const TraceParams& P = Q.t;
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pair >= P.n_pairs) return;
+  const int qs = P.pair_q[pair], ts = P.pair_t[pair];
+  const int Lq = (int)(P.seq_off[qs + 1] - P.seq_off[qs]), Lt = (int)(P.seq_off[ts + 1] - P.seq_off[ts]);
+  const uint8_t* tb = P.tb + P.tb_off[pair];
+  const int fmt = P.fmt[pair];
+  const Layout L = make_layout(Lq, Lt, fmt, P.rev);
+  const int st_mode = fmt == 1 ? 1 : Q.st_mode_v1, bias = fmt == 1 ? Q.bias16 : 0;
+  const int64_t sco = Q.sc_off[pair];
+  const int fin = Q.fin_score[pair];
+  auto score = [&](int a, int b) -> int {  // flow cell -> DPCell::score in integer units
+    if (a >= 1 && a <= Lq && b >= 1 && b <= Lt) {
+      if (st_mode == 1) return (int)((const int16_t*)Q.sc_blob)[sco + layout_sc_index(L, a, b)] - bias;
+      return ((const int32_t*)((const int16_t*)Q.sc_blob + sco))[layout_sc_index(L, a, b)];
+    }
+    return (a == Lq + 1 && b == Lt + 1) ? fin : 0;
+  };
+  // find_max: first interior maximum in ascending flow order (cells of flow row/column 0 hold 0 and never win '<')
+  int best = INT_MIN;
+  int64_t bidx = 0;
+  const int64_t ncell = (int64_t)Lq * Lt;
+  for (int64_t i = lane; i < ncell; i += 32) {
+    const int v = score((int)(i / Lt) + 1, (int)(i % Lt) + 1);
+    if (v > best) { best = v; bidx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  if (lane != 0) return;
+  // the starting candidate of the reference's scan (optimal.h:111-113 / optimal_rev.h:118-120)
+  int a = P.rev ? Lq + 1 : Lq, b = P.rev ? Lt + 1 : Lt;
+  int s = score(a, b);
+  if (ncell > 0 && best > s) { a = (int)(bidx / Lt) + 1; b = (int)(bidx % Lt) + 1; s = best; }
+  auto prev = [&](int ca, int cb, int* pa, int* pb) {
+    *pa = -1; *pb = -1;
+    if (ca == Lq + 1 && cb == Lt + 1) { decode_final(tb, L, P.fin_kind[pair], P.fin_k[pair], pa, pb); return; }
+    if (ca < 1 || ca > Lq || cb < 1 || cb > Lt) return;
+    decode_prev(tb, L, ca, cb, pa, pb);
+    if (score(ca, cb) == 0 && ca > 1 && cb > 1) { *pa = ca - 1; *pb = cb - 1; }  // clamped cell: dpmatrix.h:616-646
+  };
+  // two passes over the same walk: count, then write front to back in matrix order
+  const int cap = Lq + Lt + 2;
+  int2* out = P.out + P.cap_off[pair];
+  int n_walk = 1, ea = a, eb = b;  // cells from the maximum down the traceback (the maximum included)
+  {
+    int ca = a, cb = b;
+    while (ca > 0) {
+      int pa, pb;
+      prev(ca, cb, &pa, &pb);
+      ca = pa; cb = pb;
+      ea = ca; eb = cb;
+      if (ca < 0 || score(ca, cb) <= 0) break;
+      ++n_walk;
+    }
+  }
+  const bool frame0 = (ea != 0 && eb != 0);  // optimal.h:105: prepend (0,0) unless the walk ended on row or column 0
+  const int total = n_walk + 1 + (frame0 ? 1 : 0);
+  auto put = [&](int k, int fa, int fb) {  // k-th pair counted from the frame (last,last) [fwd] / (0,0) [rev]
+    const int i = P.rev ? Lq + 1 - fa : fa, j = P.rev ? Lt + 1 - fb : fb;
+    const int pos = P.rev ? k : total - 1 - k;
+    if (pos >= 0 && pos < cap) out[pos] = make_int2(i, j);
+  };
+  put(0, Lq + 1, Lt + 1);
+  {
+    int ca = a, cb = b;
+    for (int k = 0; k < n_walk; ++k) {
+      put(1 + k, ca, cb);
+      int pa, pb;
+      prev(ca, cb, &pa, &pb);
+      ca = pa; cb = pb;
+    }
+  }
+  if (frame0) put(1 + n_walk, 0, 0);
+  P.out_n[pair] = min(total, cap);
+  P.out_status[pair] = 0;
+  if (Q.out_score) Q.out_score[pair] = (float)s * Q.inv_scale;
 }
 
 }  // namespace aadp

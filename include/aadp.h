@@ -224,7 +224,9 @@ int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, 
 
 /* Optimal alignments of EVERY pair of the resident batch, traced on the GPU: one thread per pair follows
  * the packed traceback in HBM (Optimal::enumerate, optimal.h:47-75, for AADP_FWD; Optimal_Rev::enumerate,
- * optimal_rev.h:47-78, for AADP_REV).  Needs a batch run with AADP_W_TB; not for local alignments.
+ * optimal_rev.h:47-78, for AADP_REV).  Needs a batch run with AADP_W_TB.  Local alignments (align type local): one warp
+ * per pair runs find_max + enumerate_local (optimal.h:76-124, optimal_rev.h:79-131) over the stored scores instead
+ * (needs AADP_W_SCORES as well); status is always 0 there, as the reference never throws in that mode.
  *   ali_off  host, npairs+1 (out, may be NULL): slot p is ali_off[p]..ali_off[p+1] = Lq+Lt+2 aligned pairs
  *   pairs    host, 2*ali_off[npairs] ints (may be NULL; pairs_cap = its capacity in aligned pairs): slot p holds
  *            n_out[p] (query_idx, template_idx) pairs front to back, including (0,0) and (last,last)

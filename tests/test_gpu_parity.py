@@ -842,6 +842,37 @@ def test_pruned_general_gap_scans_change_nothing(blosum):
         cn.close()
 
 
+def test_local_optimal_alignments_of_a_batch_on_gpu(blosum):
+    # aadp_batch_optimal_all in LOCAL mode: find_max + enumerate_local (optimal.h:76-124, optimal_rev.h:79-131), one warp
+    # per pair over the stored scores and the packed traceback
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(47)
+    for gi, ge in [(12, 1), (3, 1), (10.5, 0.25)]:
+        seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(1, 160, 60)]
+        for k in range(0, 20, 2):      # related pairs: a shared core with different flanks
+            core = rng.integers(0, 20, int(rng.integers(10, 60))).astype(np.uint8)
+            seqs[k] = np.concatenate([rng.integers(0, 20, 7).astype(np.uint8), core, rng.integers(0, 20, 12).astype(np.uint8)])
+            seqs[k + 1] = np.concatenate([rng.integers(0, 20, 15).astype(np.uint8), core, rng.integers(0, 20, 3).astype(np.uint8)])
+        seqs += [np.zeros(0, np.uint8), rng.integers(0, 20, 600).astype(np.uint8)]
+        res, off = a.Context.pack(seqs)
+        pq = np.concatenate([np.arange(0, 20, 2), rng.integers(0, 62, 50)]).astype(np.int32)
+        pt = np.concatenate([np.arange(1, 20, 2), rng.integers(0, 62, 50)]).astype(np.int32)
+        c = a.Context(0)
+        c.set_scoring(M, gi, ge, po.LOCAL)
+        c.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB | a.W_SCORES)
+        O = po.Oracle(M, gi, ge, po.LOCAL)
+        for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+            aoff, pairs, n, st = c.optimal_all(d, len(pq))
+            for p in range(len(pq)):
+                q, t = seqs[pq[p]], seqs[pt[p]]
+                S, Q, T = O.fill(q, t, od, True, fast=True)
+                orc, opairs, osc = O.optimal(S, Q, T, od)
+                assert st[p] == 0 and orc == 0
+                assert_matrix_equal("local pair %d dir %d" % (p, d), pairs[aoff[p]:aoff[p] + n[p]], opairs)
+        c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a
