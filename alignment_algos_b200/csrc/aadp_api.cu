@@ -1493,6 +1493,14 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   }
   const size_t smem = (size_t)(2 * (maxLt + 2) + maxL + 2 + 32) * sizeof(float);
   if (smem > 220 * 1024) return fail("exact general-gap path: sequences too long for the shared-memory row and penalty tables");
+  // the pruned scans (prefix maxima + binary searches) only pay off when the scans are long
+  int longest = maxL;
+  if (rect) {
+    longest = 1;
+    for (int64_t k = 0; k < n; ++k)
+      longest = std::max(longest, std::max(rect[4 * k + 2] - rect[4 * k], rect[4 * k + 3] - rect[4 * k + 1]));
+  }
+  const bool prune_pays = longest >= 96;
   GeneralParams G{};
   G.A = c->sc.A;
   G.subf = c->subf.as<float>();
@@ -1537,7 +1545,7 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     G.prevt[nd] = tb ? c->gg_pt[d].as<int32_t>() : nullptr;
     G.fin[nd] = d ? d_fin_rev : d_fin_fwd;
     G.pmcol[nd] = nullptr;
-    if (c->gg_prune && !(ov && ov->d_del) && G.gi >= 0.f && G.ge >= 0.f) {  // the pruning needs pen(len) to grow with len
+    if (c->gg_prune && prune_pays && !(ov && ov->d_del) && G.gi >= 0.f && G.ge >= 0.f) {  // the pruning needs pen(len) to grow with len
       if (c->gg_pm[d].reserve(std::max<size_t>((size_t)cells * 4, 16))) return 1;
       G.pmcol[nd] = c->gg_pm[d].as<float>();
     }
@@ -1569,7 +1577,9 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
       cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
     }
   }
-  const int threads = std::max(compact ? 32 : 64, std::min(c->gg_threads_cap, (width + 31) / 32 * 32));
+  // few CTAs (single pairs): latency counts, one column per thread; many CTAs: smaller CTAs hide each other's barriers
+  const int tcap = n * nd < 296 ? 512 : c->gg_threads_cap;
+  const int threads = std::max(compact ? 32 : 64, std::min(tcap, (width + 31) / 32 * 32));
   c->prof_begin(tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
   if (tab) {
     CK(cudaFuncSetAttribute(general_fill_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));

@@ -77,7 +77,7 @@ struct UcwParams {
 };
 
 template <int CNO>
-__global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
+__global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= P.n) return;
   const int64_t pair = P.ids[warp];
@@ -138,15 +138,24 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
   int2* pathbuf = P.pathbuf + P.stack_off[warp];
   int32_t* ali_len = P.ali_len + (int64_t)warp * P.max_ali;
   float* scores = P.scores + (int64_t)warp * P.max_ali;
-  int count = 0, status = 0, plen = 0;
+  int count = 0, status = 0, plen = 0, depth = 0;
 
-  // base case (ucw.h:94-101, cw.h:102-110): the alignment is (0,0), the leaf, then the path buffer back to front
+  // base case (ucw.h:94-101, cw.h:102-110): the alignment is (0,0), the leaf, then the partial alignment back to front.
+  // CNO keeps all of it in the path buffer (frames and optimal walks interleaved); UCW has one node per frame, so the
+  // frame stack IS the path and the buffer only holds the nodes of a forced optimal walk below the deepest frame.
   auto emit = [&](int lq, int lt, float s) -> bool {
     if (count >= P.max_ali) { status = 1; return false; }
     __syncwarp();
     int2* out = paths + (int64_t)count * cap;
-    const int len = plen + 2;
-    for (int k = lane; k < len; k += 32) out[k] = k == 0 ? make_int2(0, 0) : (k == 1 ? make_int2(lq, lt) : pathbuf[plen + 1 - k]);
+    const int len = (CNO ? 0 : depth) + plen + 2;
+    for (int k = lane; k < len; k += 32) {
+      int2 v;
+      if (k == 0) v = make_int2(0, 0);
+      else if (k == 1) v = make_int2(lq, lt);
+      else if (k < plen + 2) v = pathbuf[plen + 1 - k];
+      else { const int4 f = stack[depth - 1 - (k - plen - 2)]; v = make_int2(f.x, f.y); }
+      out[k] = v;
+    }
     if (lane == 0) { ali_len[count] = len; scores[count] = s; }
     ++count;
     return true;
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
   };
 
   // frame in registers (uniform across the warp); stack[d] holds the frames below it
-  int q0 = Lq + 1, t0 = Lt + 1, next = 0, any = 0, depth = 0;
+  int q0 = Lq + 1, t0 = Lt + 1, next = 0, any = 0;
   float curr = 0.f;
   for (;;) {
     if (q0 == 1 || t0 == 1) {
@@ -213,10 +222,12 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
         // descend: the child continues slot k (first passing branch) or a copy of `curr` (later ones), ucw.h:145-149
         if (lane == 0) {
           stack[depth] = make_int4(q0, t0, __float_as_int(curr), (found + 1) | (1 << 30));
-          frame_plen[depth] = plen;
-          pathbuf[plen] = make_int2(q0, t0);
+          if (CNO) {
+            frame_plen[depth] = plen;
+            pathbuf[plen] = make_int2(q0, t0);
+          }
         }
-        ++plen;
+        if (CNO) ++plen;
         ++depth;
         curr = found == 0 ? r : __fsub_rn(r, cg);
         q0 = cq; t0 = ct; next = 0; any = 0;
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(128) ucw_enum_kernel(const UcwParams P) {
     __syncwarp();
     const int4 f = stack[depth];
     q0 = f.x; t0 = f.y; curr = __int_as_float(f.z); next = f.w & 0x3fffffff; any = (f.w >> 30) & 1;
-    plen = frame_plen[depth];
+    plen = CNO ? frame_plen[depth] : 0;
   }
   if (lane == 0) { P.n_ali[warp] = count; P.status[warp] = status; }
 }

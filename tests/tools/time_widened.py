@@ -74,12 +74,15 @@ Lq_all = np.array([len(seqs[i]) for i in iq]); Lt_all = np.array([len(seqs[i]) f
 q0 = (rng.random(nl) * (Lq_all - 30)).astype(np.int32); t0_ = (rng.random(nl) * (Lt_all - 30)).astype(np.int32)
 rects[:, 0], rects[:, 1] = q0, t0_
 rects[:, 2] = q0 + rng.integers(2, 26, nl); rects[:, 3] = t0_ + rng.integers(2, 26, nl)
-c.fill_subpair_batch(res, off, iq[:100], it[:100], rects[:100], a.FWD)
+c.fill_subpair_batch(res, off, iq, it, rects, a.FWD)      # first call: buffers grow
+c.set_profiling(True)
 t0 = time.time()
 sc, aoff, pairs, nout, st = c.fill_subpair_batch(res, off, iq, it, rects, a.FWD)
 t1 = time.time()
-out["f4_subpair_batch"] = {"loops": int(nl), "rect_edge": "2..25", "call_ms": round((t1 - t0) * 1e3, 1), "loops_per_s": round(nl / (t1 - t0)),
-                           "illegal_start": int((st != 0).sum())}
+kms4 = sum(ms for name, ms, _ in c.profile())
+c.set_profiling(False)
+out["f4_subpair_batch"] = {"loops": int(nl), "rect_edge": "2..25", "call_ms": round((t1 - t0) * 1e3, 1), "kernel_ms": round(kms4, 2),
+                           "loops_per_s": round(nl / (t1 - t0)), "illegal_start": int((st != 0).sum())}
 if os.path.exists(po.LIB_REF):
     ns = 200
     t0 = time.time()
@@ -102,5 +105,37 @@ if os.path.exists(po.LIB_REF):
     rs, _, _ = po.reference_fill_tab(sim, dt, itab, False, po.FWD)
     out["f3_tabulated"]["reference_cpu_ms_1core"] = round((time.time() - t0) * 1e3, 1)
     out["f3_tabulated"]["identical"] = bool(np.array_equal(rs, s))
+c.close()
+
+# ---- C1 (BASELINE.json configs[0]): ONE pair of 250-residue proteins, fwd+rev fill with dense DPCell-shaped outputs on
+# the host, optimal alignment and UCW enumeration (delta 0.01) -- the latency case, next to the reference on one core
+rng1 = np.random.default_rng(1001)
+q1 = rng1.integers(0, 20, 250).astype(np.uint8)
+t1 = q1.copy()
+t1[::6] = rng1.integers(0, 20, len(t1[::6]))
+c = a.Context(0)
+c.set_scoring(M, 12, 1, a.SEMI_LOCAL)
+res1, off1 = a.Context.pack([q1, t1])
+one = np.array([0], np.int32), np.array([1], np.int32)
+def c1_gpu():
+    o = c.fill_pair(q1, t1, a.BOTH, delta_ratio=0.01)
+    c.fill_batch(res1, off1, one[0], one[1], a.W_FWD | a.W_REV | a.W_TB | a.W_MASK, 0.01)
+    rc, ali, sc = c.optimal(0, a.FWD, 250, 250)
+    return o, c.near_optimal([0], 0.01, 1024)[0]
+c1_gpu()
+t0 = time.time()
+for _ in range(5):
+    o, (st1, thr1, alis1) = c1_gpu()
+tg = (time.time() - t0) / 5
+out["c1_single_pair"] = {"pair": "250x250 related", "gpu_ms": round(tg * 1e3, 2), "near_optimal_alignments": len(alis1)}
+if os.path.exists(po.LIB_REF):
+    t0 = time.time()
+    rf = R.fill(q1, t1, po.FWD)
+    rr = R.fill(q1, t1, po.REV)
+    ra = R.ucw_alignments(q1, t1, 0.01, 100000)
+    out["c1_single_pair"]["reference_cpu_ms_1core"] = round((time.time() - t0) * 1e3, 1)
+    out["c1_single_pair"]["identical"] = bool(np.array_equal(rf[0], o["score_fwd"]) and np.array_equal(rr[0], o["score_rev"])
+                                               and len(ra) == len(alis1)
+                                               and sorted(s for s, _ in ra) == sorted(s for s, _ in alis1))
 c.close()
 print(json.dumps(out))
