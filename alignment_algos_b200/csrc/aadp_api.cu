@@ -2029,9 +2029,66 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
   if (check_ctx(c, true)) return 1;
   Batch& b = c->b;
   if (p < 0 || p >= b.npairs) return fail("pair index out of range");
-  if (c->sc.local) return fail("aadp_batch_optimal: local tracebacks go through aadp_batch_fetch_pair (they need find_max)");
   const int qs = b.pair_q[p], ts = b.pair_t[p];
   const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  if (c->sc.local) {
+    // Optimal::enumerate_local + find_max (optimal.h:76-124) / Optimal_Rev (optimal_rev.h:79-131) over the dense view of
+    // this one pair (either exactness class); whole batches: aadp_batch_optimal_all traces them on the GPU
+    if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
+    const bool rev = direction == AADP_REV;
+    const int sz1 = Lq + 2, sz2 = Lt + 2;
+    const size_t n = (size_t)sz1 * sz2;
+    std::vector<float> sc(n);
+    std::vector<int32_t> pq(n), pt(n);
+    if (aadp_batch_fetch_pair(c, p, rev ? nullptr : sc.data(), rev ? nullptr : pq.data(), rev ? nullptr : pt.data(),
+                              rev ? sc.data() : nullptr, rev ? pq.data() : nullptr, rev ? pt.data() : nullptr, nullptr)) return 1;
+    auto D = [&](int i, int j) { return sc[(size_t)i * sz2 + j]; };
+    std::vector<int32_t> path;  // in walk order, framed afterwards
+    int i, j;
+    float s;
+    if (!rev) {  // optimal.h:107-124
+      i = sz1 - 2; j = sz2 - 2; s = D(i, j);
+      for (int a = 0; a < sz1 - 1; ++a)
+        for (int bb = 0; bb < sz2 - 1; ++bb)
+          if (s < D(a, bb)) { i = a; j = bb; s = D(a, bb); }
+    } else {     // optimal_rev.h:114-131
+      i = 0; j = 0; s = D(0, 0);
+      for (int a = sz1 - 1; a > 0; --a)
+        for (int bb = sz2 - 1; bb > 0; --bb)
+          if (s < D(a, bb)) { i = a; j = bb; s = D(a, bb); }
+    }
+    if (score) *score = s;
+    path.push_back(i);
+    path.push_back(j);
+    int guard = 0;
+    while (rev ? (i < sz1 - 1) : (i > 0)) {
+      const int32_t pi = pq[(size_t)i * sz2 + j], pj = pt[(size_t)i * sz2 + j];
+      i = pi;
+      j = pj;
+      if (i < 0 || j < 0 || ++guard > Lq + Lt + 4) break;
+      if (D(i, j) <= 0.f) break;
+      path.push_back(i);
+      path.push_back(j);
+    }
+    const bool frame = rev ? (i != sz1 - 1 && j != sz2 - 1) : (i != 0 && j != 0);  // optimal.h:105, optimal_rev.h:111
+    std::vector<int32_t> ali;  // front to back in matrix order
+    const int nw = (int)path.size() / 2;
+    if (!rev) {
+      if (frame) { ali.push_back(0); ali.push_back(0); }
+      for (int k = nw - 1; k >= 0; --k) { ali.push_back(path[2 * k]); ali.push_back(path[2 * k + 1]); }
+      ali.push_back(sz1 - 1);
+      ali.push_back(sz2 - 1);
+    } else {
+      ali.push_back(0);
+      ali.push_back(0);
+      for (int k = 0; k < nw; ++k) { ali.push_back(path[2 * k]); ali.push_back(path[2 * k + 1]); }
+      if (frame) { ali.push_back(sz1 - 1); ali.push_back(sz2 - 1); }
+    }
+    const int n2 = (int)ali.size() / 2;
+    if (npairs) *npairs = n2;
+    for (int k = 0; k < n2 && k < max_pairs; ++k) { pairs[2 * k] = ali[2 * k]; pairs[2 * k + 1] = ali[2 * k + 1]; }
+    return 0;
+  }
   if (c->float_mode) {
     // exact-float mode: dense predecessors of this pair are recomputed, then optimal.h:57-74 / optimal_rev.h:57-76
     if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");

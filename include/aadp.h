@@ -218,7 +218,8 @@ int aadp_batch_fetch_pair(aadp_ctx* ctx, int64_t p, float* score_fwd, int32_t* p
  * Optimal::enumerate (optimal.h:47-75) for direction AADP_FWD and Optimal_Rev::enumerate
  * (optimal_rev.h:47-78) for AADP_REV. pairs receives 2 ints (query_idx, template_idx) per
  * aligned pair in alignment order, including (0,0) and (last,last). Returns 3 with
- * "Illegal alignment start pair" when the reference would throw (optimal.h:74).                 */
+ * "Illegal alignment start pair" when the reference would throw (optimal.h:74).  Local alignments: find_max +
+ * enumerate_local (optimal.h:76-124, optimal_rev.h:79-131) over the dense view of the pair.       */
 int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, int32_t max_pairs,
                        int32_t* npairs, float* score);
 

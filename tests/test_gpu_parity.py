@@ -870,7 +870,25 @@ def test_local_optimal_alignments_of_a_batch_on_gpu(blosum):
                 orc, opairs, osc = O.optimal(S, Q, T, od)
                 assert st[p] == 0 and orc == 0
                 assert_matrix_equal("local pair %d dir %d" % (p, d), pairs[aoff[p]:aoff[p] + n[p]], opairs)
+                if p % 7 == 0:    # the per-pair entry (host walk over the dense view) agrees
+                    rc, hp, hs = c.optimal(p, d, len(q), len(t))
+                    assert rc == 0 and hs == osc
+                    assert_matrix_equal("local per-pair %d dir %d" % (p, d), hp, opairs)
         c.close()
+    # exact-float mode, local: per-pair entry only
+    c = a.Context(0)
+    c.set_scoring(M, 4.73, 0.34, po.LOCAL)
+    c.fill_batch(res, off, pq[:12], pt[:12], a.W_FWD | a.W_REV)
+    O = po.Oracle(M, 4.73, 0.34, po.LOCAL)
+    for p in range(12):
+        q, t = seqs[pq[p]], seqs[pt[p]]
+        for d, od in ((a.FWD, po.FWD), (a.REV, po.REV)):
+            S, Q, T = O.fill(q, t, od, True, fast=False)
+            orc, opairs, osc = O.optimal(S, Q, T, od)
+            rc, hp, hs = c.optimal(p, d, len(q), len(t))
+            assert rc == 0 and hs == osc
+            assert_matrix_equal("float local per-pair %d dir %d" % (p, d), hp, opairs)
+    c.close()
 
 
 def test_general_entry_with_similarity_matrix(blosum):
