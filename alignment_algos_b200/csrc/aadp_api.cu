@@ -159,7 +159,7 @@ struct aadp_ctx {
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
-  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2];
+  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2], gg_items;
   int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
@@ -1014,7 +1014,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->gg_pm[0], &c->gg_pm[1], &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->gg_pm[0], &c->gg_pm[1], &c->gg_items, &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
                    &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr, &c->ucw_plen, &c->ucw_pathbuf, &c->ucw_flags, &c->ucw_flag_off};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
@@ -1481,11 +1481,13 @@ struct GeneralOverride {
 
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
                    float* d_fin_fwd, float* d_fin_rev, const int* rect = nullptr, const GeneralOverride* ov = nullptr,
-                   bool compact = false) {
+                   bool compact = false, const int64_t* ids = nullptr) {
+  // ids != nullptr: the n items are the listed pairs ids[0..n) instead of the consecutive pairs p0..p0+n
   Batch& b = c->b;
   const int64_t cells = off[(size_t)n];
   int maxLt = 0, maxL = 0;
-  for (int64_t p = p0; p < p0 + n; ++p) {
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t p = ids ? ids[k] : p0 + k;
     const int qs = b.pair_q[p], ts = b.pair_t[p];
     const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
     maxLt = std::max(maxLt, Lt);
@@ -1553,9 +1555,15 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   }
   if (nd == 0) return 0;
   CK(cudaStreamSynchronize(c->stream));  // the pinned pool may still feed an earlier copy
-  if (pin_reserve(c, (size_t)(n + 1) * 8 + (rect ? (size_t)n * 16 : 0) + 4096)) return 1;
+  if (pin_reserve(c, (size_t)(n + 1) * 8 + (rect ? (size_t)n * 16 : 0) + (ids ? (size_t)n * 4 : 0) + 4096)) return 1;
   if (upload_vec(c, c->gg_off, off)) return 1;
   G.dense_off = c->gg_off.as<int64_t>();
+  if (ids) {
+    std::vector<int32_t> it32((size_t)n);
+    for (int64_t k = 0; k < n; ++k) it32[(size_t)k] = (int32_t)ids[k];
+    if (upload_vec(c, c->gg_items, it32)) return 1;
+    G.items = c->gg_items.as<int32_t>();
+  }
   if (rect) {  // build_subdpm: one rectangle per item of this launch (4 ints each)
     std::vector<int32_t> r(rect, rect + 4 * n);
     if (upload_vec(c, c->gg_rect, r)) return 1;
@@ -1572,7 +1580,8 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
       cu += (double)(rect[4 * k + 2] - rect[4 * k] - 1) * (double)(rect[4 * k + 3] - rect[4 * k + 1] - 1);
     }
   } else {
-    for (int64_t p = p0; p < p0 + n; ++p) {
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t p = ids ? ids[k] : p0 + k;
       const int qs = b.pair_q[p], ts = b.pair_t[p];
       cu += (double)(b.seq_off[qs + 1] - b.seq_off[qs]) * (double)(b.seq_off[ts + 1] - b.seq_off[ts]);
     }
@@ -2317,34 +2326,44 @@ static int near_optimal_impl(aadp_ctx* c, int cno, const uint8_t* flags, const i
     CK(cudaGetLastError());
     c->launches++;
   } else {
-    // exact-float mode keeps no resident matrices: refill each listed pair with the exact general-gap kernel (dense fp32
-    // scores + predecessors in scratch) and walk that; one pair per launch
+    // exact-float mode keeps no resident matrices: refill the listed pairs with the exact general-gap kernel (dense fp32
+    // scores + predecessors in scratch), a chunk of the scratch budget at a time, and walk those
     if (c->gg_fin[0].reserve(std::max<size_t>((size_t)b.npairs * 4, 16))) return 1;
-    for (int64_t k = 0; k < n; ++k) {
-      const int64_t p = pair_ids[k];
-      const int64_t cl = (b.seq_off[b.pair_q[p] + 1] - b.seq_off[b.pair_q[p]] + 2) * (b.seq_off[b.pair_t[p] + 1] - b.seq_off[b.pair_t[p]] + 2);
-      const std::vector<int64_t> doff = {0, cl};
-      if (gg_fill(c, p, 1, 1, true, doff, c->gg_fin[0].as<float>(), nullptr)) return 1;
+    std::vector<int64_t> doff;
+    for (int64_t k0 = 0; k0 < n;) {
+      doff.assign(1, 0);
+      int64_t k1 = k0;
+      while (k1 < n) {
+        const int64_t p = pair_ids[k1];
+        const int64_t cl = (b.seq_off[b.pair_q[p] + 1] - b.seq_off[b.pair_q[p]] + 2) * (b.seq_off[b.pair_t[p] + 1] - b.seq_off[b.pair_t[p]] + 2);
+        if (k1 > k0 && doff.back() + cl > c->gg_budget_cells / 4) break;  // scores + two predecessor matrices (+ prefix maxima)
+        doff.push_back(doff.back() + cl);
+        ++k1;
+      }
+      const int64_t m = k1 - k0;
+      if (gg_fill(c, 0, m, 1, true, doff, c->gg_fin[0].as<float>(), nullptr, nullptr, nullptr, false, pair_ids + k0)) return 1;
       UcwParams V = U;
       V.denseF = c->gg_score[0].as<float>();
       V.densePQ = c->gg_pq[0].as<int32_t>();
       V.densePT = c->gg_pt[0].as<int32_t>();
-      V.n = 1;
-      V.ids = U.ids + k;
-      V.path_off = U.path_off + k;
-      V.stack_off = U.stack_off + k;
-      V.ali_len = U.ali_len + k * max_alignments;
-      V.scores = U.scores + k * max_alignments;
-      V.n_ali = U.n_ali + k;
-      V.status = U.status + k;
-      V.threshold = U.threshold + k;
-      if (flags) V.subopt_off = U.subopt_off + k;
+      V.dense_off = c->gg_off.as<int64_t>();
+      V.n = (int)m;
+      V.ids = U.ids + k0;
+      V.path_off = U.path_off + k0;
+      V.stack_off = U.stack_off + k0;
+      V.ali_len = U.ali_len + k0 * max_alignments;
+      V.scores = U.scores + k0 * max_alignments;
+      V.n_ali = U.n_ali + k0;
+      V.status = U.status + k0;
+      V.threshold = U.threshold + k0;
+      if (flags) V.subopt_off = U.subopt_off + k0;
       c->prof_begin("ucw_enum_kernel (exact float)", 0);
-      if (cno) ucw_enum_kernel<1><<<1, 128, 0, c->stream>>>(V);
-      else ucw_enum_kernel<0><<<1, 128, 0, c->stream>>>(V);
+      if (cno) ucw_enum_kernel<1><<<(unsigned)((m * 32 + 127) / 128), 128, 0, c->stream>>>(V);
+      else ucw_enum_kernel<0><<<(unsigned)((m * 32 + 127) / 128), 128, 0, c->stream>>>(V);
       c->prof_end();
       CK(cudaGetLastError());
       c->launches++;
+      k0 = k1;
     }
   }
   c->d2h_bytes = 0;

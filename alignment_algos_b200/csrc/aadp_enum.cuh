@@ -57,6 +57,7 @@ struct UcwParams {
   const float* denseF;
   const int32_t* densePQ;
   const int32_t* densePT;
+  const int64_t* dense_off;   // per listed pair of the launch: offset of its dense matrices
   const int64_t* ids;         // listed pairs
   int n;
   float delta_ratio;
@@ -94,9 +95,13 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   const uint8_t* tb = (P.denseF || !P.tb) ? nullptr : P.tb + P.tb_off[pair];
   const float inv = P.inv_scale;
   const int sz2 = Lt + 2;
+  const int64_t dbase = P.denseF ? P.dense_off[warp] : 0;
+  const float* denseF = P.denseF ? P.denseF + dbase : nullptr;
+  const int32_t* densePQ = P.densePQ ? P.densePQ + dbase : nullptr;
+  const int32_t* densePT = P.densePT ? P.densePT + dbase : nullptr;
   // DPCell::score of the forward matrix (interior cells and the final cell)
   auto F = [&](int i, int j) -> float {
-    if (P.denseF) return P.denseF[(int64_t)i * sz2 + j];
+    if (denseF) return denseF[(int64_t)i * sz2 + j];
     if (i == Lq + 1 && j == Lt + 1) return (float)P.fin_score[pair] * inv;
     int si;
     if (st_mode == 1) si = (int)((const int16_t*)P.sc_blob)[sco + layout_sc_index(L, i, j)] - bias;
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   auto pen = [&](int len) { return __fadd_rn(P.gi, __fmul_rn(P.ge, (float)(len - 1))); };
   // DPCell::prev_* of an interior cell; false when this batch cannot answer (no traceback kept / the final cell)
   auto prev = [&](int a, int b, int* pa, int* pb) -> bool {
-    if (P.densePQ) { *pa = P.densePQ[(int64_t)a * sz2 + b]; *pb = P.densePT[(int64_t)a * sz2 + b]; return true; }
+    if (densePQ) { *pa = densePQ[(int64_t)a * sz2 + b]; *pb = densePT[(int64_t)a * sz2 + b]; return true; }
     if (!tb || a > Lq || b > Lt) return false;
     decode_prev(tb, L, a, b, pa, pb);
     return true;
