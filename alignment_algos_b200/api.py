@@ -145,6 +145,34 @@ class Context:
                                                  int(bool(is_local)), flags, direction, _ptr(s), _ptr(pq), _ptr(pt)))
         return s, pq, pt
 
+    def fill_batch_tabulated(self, sims, dels, inss, is_local=False, direction=BOTH, want_alignments=True, flags=REPRO_REV_BUG):
+        """Many tabulated pairs in one call (aadp_fill_batch_tabulated): lists of per-item sim / del_tab / ins_tab arrays.
+        Returns (fwd_score, rev_score, ali_off, pairs, n_out, status)."""
+        n = len(sims)
+        Lq = np.array([s.shape[0] - 2 for s in sims], np.int32)
+        Lt = np.array([s.shape[1] - 2 for s in sims], np.int32)
+
+        def blob(arrs):
+            off = np.zeros(n + 1, np.int64)
+            off[1:] = np.cumsum([a.size for a in arrs])
+            data = np.concatenate([np.ascontiguousarray(a, np.float32).ravel() for a in arrs]) if n else np.zeros(0, np.float32)
+            return np.ascontiguousarray(data, np.float32), off
+
+        (sb, so), (db, do), (ib, io) = blob(sims), blob(dels), blob(inss)
+        fs = np.zeros(n, np.float32) if direction & 1 else None
+        rs = np.zeros(n, np.float32) if direction & 2 else None
+        aoff = np.zeros(n + 1, np.int64)
+        ali = want_alignments and not is_local and (direction & 1)
+        args = [self.h, n, _ptr(Lq), _ptr(Lt), _ptr(sb), _ptr(so), _ptr(db), _ptr(do), _ptr(ib), _ptr(io), int(bool(is_local)),
+                flags, direction]
+        self._ck(self.L.aadp_fill_batch_tabulated(*args, None, None, _ptr(aoff), None, 0, None, None))
+        pairs = np.zeros((max(int(aoff[-1]), 1), 2), np.int32) if ali else None
+        n_out = np.zeros(n, np.int32) if ali else None
+        st = np.zeros(n, np.int32) if ali else None
+        self._ck(self.L.aadp_fill_batch_tabulated(*args, _ptr(fs), _ptr(rs), _ptr(aoff), _ptr(pairs), int(aoff[-1]), _ptr(n_out),
+                                                  _ptr(st)))
+        return fs, rs, aoff, pairs, n_out, st
+
     # ---- batches ----
     @staticmethod
     def pack(seqs):

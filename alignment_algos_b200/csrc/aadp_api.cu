@@ -159,7 +159,7 @@ struct aadp_ctx {
   int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
-  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2], gg_items;
+  DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2], gg_items, tb_del, tb_ins, tb_del_off, tb_ins_off;
   int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
@@ -1014,7 +1014,7 @@ void aadp_destroy(aadp_ctx* c) {
                    &c->fmt, &c->tasks, &c->aoff, &c->arena_f, &c->arena_r, &c->badflag, &c->wave_bb, &c->wave_ready, &c->wave_part,
                    &c->x_layout, &c->x_qc, &c->x_qid, &c->x_tid, &c->x_scores,
                    &c->subf, &c->gg_score[0], &c->gg_score[1], &c->gg_pq[0], &c->gg_pq[1], &c->gg_pt[0], &c->gg_pt[1],
-                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->gg_pm[0], &c->gg_pm[1], &c->gg_items, &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
+                   &c->gg_mask, &c->gg_off, &c->gg_fin[0], &c->gg_fin[1], &c->gg_pm[0], &c->gg_pm[1], &c->gg_items, &c->tb_del, &c->tb_ins, &c->tb_del_off, &c->tb_ins_off, &c->ali_cap, &c->ali_out, &c->ali_n, &c->ali_status, &c->gg_rect, &c->sub8p,
                    &c->ucw_ids, &c->ucw_path_off, &c->ucw_stack_off, &c->ucw_stack, &c->ucw_paths, &c->ucw_len, &c->ucw_scores, &c->ucw_n, &c->ucw_status, &c->ucw_thr, &c->ucw_plen, &c->ucw_pathbuf, &c->ucw_flags, &c->ucw_flag_off};
   for (DevBuf* d : all) d->release();
   if (c->pin) cudaFreeHost(c->pin);
@@ -1477,6 +1477,8 @@ struct GeneralOverride {
   const float* d_delT;
   const float* d_ins;
   int tab_local;
+  const int64_t* d_del_off;  // batches of tabulated pairs: per-item table offsets (device), or null
+  const int64_t* d_ins_off;
 };
 
 static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, const std::vector<int64_t>& off,
@@ -1525,6 +1527,8 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
       G.del_tab = ov->d_del;
       G.del_tabT = ov->d_delT;
       G.ins_tab = ov->d_ins;
+      G.del_off = ov->d_del_off;
+      G.ins_off = ov->d_ins_off;
       G.delfree = G.insfree = 0;  // free end gaps are whatever the tables say
       G.local = ov->tab_local;
     }
@@ -2536,7 +2540,7 @@ int aadp_fill_pair_general(aadp_ctx* c, const float* sim, int Lq, int Lt, float 
   CK(cudaMemcpyAsync(c->scratch_d.p, sim, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));  // gg_fill recycles the pinned pool; the caller's sim buffer is free again
   const std::vector<int64_t> doff = {0, n};
-  GeneralOverride ov{gi, ge, align_type, flags, c->scratch_d.as<float>(), nullptr, nullptr, nullptr, 0};
+  GeneralOverride ov{gi, ge, align_type, flags, c->scratch_d.as<float>(), nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   const int d = direction - 1;
   c->launches = 0;
   if (gg_fill(c, 0, 1, 1 << d, true, doff, nullptr, nullptr, rect, &ov)) return 1;
@@ -2588,13 +2592,146 @@ int aadp_fill_pair_tabulated(aadp_ctx* c, const float* sim, int Lq, int Lt, cons
   CK(cudaMemcpyAsync(d + n + 2 * nd, ins_tab, (size_t)ni * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const std::vector<int64_t> doff = {0, n};
-  GeneralOverride ov{0.f, 0.f, is_local ? AADP_LOCAL : AADP_GLOBAL, flags, d, d + n, d + n + nd, d + n + 2 * nd, is_local ? 1 : 0};
+  GeneralOverride ov{0.f, 0.f, is_local ? AADP_LOCAL : AADP_GLOBAL, flags, d, d + n, d + n + nd, d + n + 2 * nd, is_local ? 1 : 0, nullptr, nullptr};
   const int dd = direction - 1;
   c->launches = 0;
   if (gg_fill(c, 0, 1, 1 << dd, true, doff, nullptr, nullptr, nullptr, &ov)) return 1;
   if (score) CK(cudaMemcpyAsync(score, c->gg_score[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_q) CK(cudaMemcpyAsync(prev_q, c->gg_pq[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (prev_t) CK(cudaMemcpyAsync(prev_t, c->gg_pt[dd].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int aadp_fill_batch_tabulated(aadp_ctx* c, int64_t n, const int32_t* Lq, const int32_t* Lt, const float* sim, const int64_t* sim_off,
+                              const float* del_tab, const int64_t* del_off, const float* ins_tab, const int64_t* ins_off,
+                              int is_local, uint32_t flags, int direction, float* fwd_score, float* rev_score, int64_t* ali_off,
+                              int32_t* pairs, int64_t pairs_cap, int32_t* n_out, int32_t* status) {
+  if (check_ctx(c, false)) return 1;
+  if (n < 0 || n > 0x3fffffff) return fail("bad batch size");
+  if (n && (!Lq || !Lt || !sim || !sim_off || !del_tab || !del_off || !ins_tab || !ins_off)) return fail("null argument");
+  if (direction < 1 || direction > 3) return fail("bad direction");
+  const bool want_ali = pairs || n_out || status;
+  if (want_ali && (is_local || !(direction & 1))) return fail("aadp_fill_batch_tabulated: optimal alignments are traced over non-local forward fills");
+  std::vector<int64_t> cap((size_t)n + 1, 0), cells((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    if (Lq[k] < 0 || Lt[k] < 0) return fail("Illegal bounds building DPM");
+    const int sz2 = Lt[k] + 2;
+    const float* dt = del_tab + del_off[k];
+    const float* it = ins_tab + ins_off[k];
+    for (int x = 0; x + 1 < sz2; ++x)
+      if (dt[(size_t)x * sz2 + x + 1] != 0.f) return fail("tabulated gap model: deletion between adjacent positions must be 0");
+    for (int j = 0; j < sz2; ++j)
+      if (it[j] != 0.f) return fail("tabulated gap model: insertion between adjacent positions must be 0");
+    cap[(size_t)k + 1] = cap[(size_t)k] + Lq[k] + 2;
+    cells[(size_t)k] = (int64_t)(Lq[k] + 2) * sz2;
+  }
+  if (ali_off) memcpy(ali_off, cap.data(), (size_t)(n + 1) * 8);
+  if (n == 0 || (!fwd_score && !rev_score && !want_ali)) return 0;
+  if (pairs && pairs_cap < cap[(size_t)n]) return fail("aadp_fill_batch_tabulated: pairs buffer too small (needs 2*ali_off[n] ints)");
+  // a batch without residues: item k is the pair of sequences 2k (Lq[k] positions) and 2k+1 (Lt[k] positions)
+  Batch& b = c->b;
+  b.nseq = 2 * n;
+  b.npairs = n;
+  b.seq_off.assign((size_t)(2 * n + 1), 0);
+  b.pair_q.resize((size_t)n);
+  b.pair_t.resize((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    b.seq_off[(size_t)(2 * k + 1)] = b.seq_off[(size_t)(2 * k)] + Lq[k];
+    b.seq_off[(size_t)(2 * k + 2)] = b.seq_off[(size_t)(2 * k + 1)] + Lt[k];
+    b.pair_q[(size_t)k] = (int32_t)(2 * k);
+    b.pair_t[(size_t)k] = (int32_t)(2 * k + 1);
+  }
+  b.have_seqs = false;
+  b.ran_what = 0;
+  b.uploaded_what = 0;
+  b.tb_off.clear();
+  CK(cudaStreamSynchronize(c->stream));
+  if (pin_reserve(c, (size_t)(2 * n + 1) * 8 + (size_t)n * 8 + (size_t)(n + 1) * 8 + 4096)) return 1;
+  if (upload_vec(c, c->seq_off, b.seq_off) || upload_vec(c, c->pair_q, b.pair_q) || upload_vec(c, c->pair_t, b.pair_t)) return 1;
+  const size_t nres = (size_t)b.seq_off.back() + 16;
+  if (c->residues.reserve(nres)) return 1;
+  CK(cudaMemsetAsync(c->residues.p, 0, nres, c->stream));
+  if (want_ali) {
+    if (upload_vec(c, c->ali_cap, cap)) return 1;
+    if (c->ali_out.reserve((size_t)cap[(size_t)n] * 8) || c->ali_n.reserve((size_t)n * 4) || c->ali_status.reserve((size_t)n * 4)) return 1;
+  }
+  if (c->gg_fin[0].reserve((size_t)n * 4) || c->gg_fin[1].reserve((size_t)n * 4)) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  c->launches = 0;
+  c->h2d_bytes = 0;
+  const int dirmask = direction;
+  std::vector<int64_t> off, doff, ioff;
+  std::vector<int32_t> rects;
+  for (int64_t p0 = 0; p0 < n;) {
+    // one chunk: dense outputs + sim share the offsets `off`; the tables are packed next to each other
+    off.assign(1, 0);
+    doff.clear();
+    ioff.clear();
+    int64_t nd_cells = 0, ni_cells = 0, p1 = p0;
+    while (p1 < n && (p1 == p0 || off.back() + cells[(size_t)p1] <= c->gg_budget_cells / 4)) {
+      off.push_back(off.back() + cells[(size_t)p1]);
+      doff.push_back(nd_cells);
+      ioff.push_back(ni_cells);
+      nd_cells += (int64_t)(Lt[p1] + 2) * (Lt[p1] + 2);
+      ni_cells += (int64_t)(Lq[p1] + 1) * (Lt[p1] + 2);
+      ++p1;
+    }
+    const int64_t m = p1 - p0;
+    if (c->scratch_d.reserve((size_t)off.back() * 4) || c->tb_del.reserve((size_t)nd_cells * 4) || c->tb_ins.reserve((size_t)ni_cells * 4)) return 1;
+    for (int64_t k = p0; k < p1; ++k) {
+      const int64_t sz2 = Lt[k] + 2;
+      CK(cudaMemcpyAsync(c->scratch_d.as<float>() + off[(size_t)(k - p0)], sim + sim_off[k], (size_t)cells[(size_t)k] * 4, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->tb_del.as<float>() + doff[(size_t)(k - p0)], del_tab + del_off[k], (size_t)(sz2 * sz2) * 4, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(c->tb_ins.as<float>() + ioff[(size_t)(k - p0)], ins_tab + ins_off[k], (size_t)((Lq[k] + 1) * sz2) * 4, cudaMemcpyHostToDevice, c->stream));
+      c->h2d_bytes += (cells[(size_t)k] + sz2 * sz2 + (Lq[k] + 1) * sz2) * 4;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (pin_reserve(c, (size_t)m * 16 + 4096)) return 1;
+    if (upload_vec(c, c->tb_del_off, doff) || upload_vec(c, c->tb_ins_off, ioff)) return 1;
+    CK(cudaStreamSynchronize(c->stream));  // gg_fill recycles the pinned pool
+    GeneralOverride ov{0.f, 0.f, is_local ? AADP_LOCAL : AADP_GLOBAL, flags, c->scratch_d.as<float>(), c->tb_del.as<float>(), nullptr,
+                       c->tb_ins.as<float>(), is_local ? 1 : 0, c->tb_del_off.as<int64_t>(), c->tb_ins_off.as<int64_t>()};
+    if (gg_fill(c, p0, m, dirmask, true, off, c->gg_fin[0].as<float>(), c->gg_fin[1].as<float>(), nullptr, &ov)) return 1;
+    if (want_ali) {  // Optimal::enumerate (optimal.h:47-75) = the sub-alignment walk over the whole matrix
+      rects.resize((size_t)m * 4);
+      for (int64_t k = p0; k < p1; ++k) {
+        rects[(size_t)(k - p0) * 4] = 0;
+        rects[(size_t)(k - p0) * 4 + 1] = 0;
+        rects[(size_t)(k - p0) * 4 + 2] = Lq[k] + 1;
+        rects[(size_t)(k - p0) * 4 + 3] = Lt[k] + 1;
+      }
+      CK(cudaStreamSynchronize(c->stream));
+      if (pin_reserve(c, (size_t)m * 16 + 4096)) return 1;
+      if (upload_vec(c, c->gg_rect, rects)) return 1;
+      SubTraceParams T{};
+      T.PQ = c->gg_pq[0].as<int32_t>();
+      T.PT = c->gg_pt[0].as<int32_t>();
+      T.D = c->gg_score[0].as<float>();
+      T.dense_off = c->gg_off.as<int64_t>();
+      T.rects = c->gg_rect.as<int4>();
+      T.cap_off = c->ali_cap.as<int64_t>();
+      T.item0 = (int)p0;
+      T.n = (int)m;
+      T.out = c->ali_out.as<int2>();
+      T.out_n = c->ali_n.as<int32_t>();
+      T.out_status = c->ali_status.as<int32_t>();
+      T.out_score = nullptr;
+      c->prof_begin("subali_trace_kernel", 0);
+      subali_trace_kernel<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(T);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    p0 = p1;
+  }
+  c->d2h_bytes = 0;
+  if (fwd_score && (direction & 1)) { CK(cudaMemcpyAsync(fwd_score, c->gg_fin[0].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * 4; }
+  if (rev_score && (direction & 2)) { CK(cudaMemcpyAsync(rev_score, c->gg_fin[1].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * 4; }
+  if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)n] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)n] * 8; }
+  if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * 4; }
+  if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += n * 4; }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

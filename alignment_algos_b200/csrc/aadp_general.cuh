@@ -48,6 +48,8 @@ struct GeneralParams {
   const float* del_tab;      //   [t_pos1*sz2 + t_pos2] = deletion(., ., t_pos1, t_pos2), t_pos1 < t_pos2
   const float* del_tabT;     //   its transpose (the reverse fill scans it by column)
   const float* ins_tab;      //   [(q_pos2-q_pos1-1)*sz2 + t_pos2] = insertion(q_pos1, q_pos2, t_pos2-1, t_pos2)
+  const int64_t* del_off;    //   per item: offset of its deletion table (batches of tabulated pairs), or null
+  const int64_t* ins_off;    //   per item: offset of its insertion table, or null
   int compact;               // 1: an item stores only its rectangle, (q2_beg-q1_end+1) x (t2_beg-t1_end+1) cells with the
                              // first anchor at offset 0 (batched loop-closure fills: many small rectangles of large
                              // matrices); predecessors stay matrix indices
@@ -114,6 +116,9 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
   float* wmax = pm + (Lt + 2);          // 32 warp maxima of the block-wide prefix scan
   const bool PRUNE = !TAB && P.pmcol[dsel] != nullptr;
   float* PMC = PRUNE ? P.pmcol[dsel] + base : nullptr;
+  const float* del_tab = TAB ? P.del_tab + (P.del_off ? P.del_off[item] : 0) : nullptr;
+  const float* del_tabT = (TAB && P.del_tabT) ? P.del_tabT + (P.del_off ? P.del_off[item] : 0) : nullptr;
+  const float* ins_tab = TAB ? P.ins_tab + (P.ins_off ? P.ins_off[item] : 0) : nullptr;
   const int maxlen = max(nq, nt);
   if (!TAB)
     for (int l = 1 + tid; l <= maxlen; l += nth) pen[l] = gg_pen(gi, ge, l);
@@ -139,14 +144,14 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
     const int len = b1 - b0 - 1;
     if (len < 1) return 0.f;
     const int x = colof(b0), y = colof(b1);
-    if (TAB) return P.del_tab[(int64_t)min(x, y) * sz2 + max(x, y)];
+    if (TAB) return del_tab[(int64_t)min(x, y) * sz2 + max(x, y)];
     if (P.delfree && (min(x, y) == 0 || max(x, y) == Lt + 1)) return 0.f;
     return pen[len];
   };
   auto gins = [&](int a0, int a1, int b) -> float {
     const int len = a1 - a0 - 1;
     if (len < 1) return 0.f;
-    if (TAB) return P.ins_tab[(int64_t)len * sz2 + t2of(b)];
+    if (TAB) return ins_tab[(int64_t)len * sz2 + t2of(b)];
     const int x = rowof(a0), y = rowof(a1);
     if (P.insfree && (min(x, y) == 0 || max(x, y) == Lq + 1)) return 0.f;
     return pen[len];
@@ -245,8 +250,11 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
       int oa = a - 1, ob = b - 1;
       float os = clampl(__fadd_rn(prow[b - 1], simc));
       // tabulated penalties of this cell: deletion column (rows = the other template position), insertion column
-      const float* dcol = TAB ? (rev ? P.del_tabT : P.del_tab) + colof(b) : nullptr;
-      const float* icol = TAB ? P.ins_tab + t2of(b) : nullptr;
+      // (reverse fill without a transposed table: the row of the table is scanned instead of its column)
+      const bool dT = TAB && rev && !del_tabT;
+      const float* dcol = TAB ? (dT ? del_tab + (int64_t)colof(b) * sz2 : (rev ? del_tabT : del_tab) + colof(b)) : nullptr;
+      const int64_t dstr = dT ? 1 : sz2;
+      const float* icol = TAB ? ins_tab + t2of(b) : nullptr;
       const float* colp = D + at(1, b - 1);
       const int64_t cstride = rev ? -(int64_t)ld : (int64_t)ld;
       // Pruned scans: bound(k) = rn(rn(max(D[1..k]) - pen(len)) + sim) is monotone in k and bounds candidate k, so every
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
         os = clampl(os);
       } else if (TBM) {
         for (int k = 1; k < b - 1; ++k) {  // dpmatrix.h:459-468
-          float s = __fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]);
+          float s = __fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * dstr] : pen[b - k - 1]);
           s = clampl(__fadd_rn(s, simc));
           if (s > os) { ob = k; os = s; }
         }
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(512) general_fill_kernel(const GeneralParams P
         // score only: the strict-'>' scan and a running maximum give the same value; the clamp commutes with max
 #pragma unroll 4
         for (int k = 1; k < b - 1; ++k)
-          os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * sz2] : pen[b - k - 1]), simc));
+          os = fmaxf(os, __fadd_rn(__fsub_rn(prow[k], TAB ? dcol[(int64_t)colof(k) * dstr] : pen[b - k - 1]), simc));
 #pragma unroll 4
         for (int k = 1; k < a - 1; ++k)
           os = fmaxf(os, __fadd_rn(__fsub_rn(colp[(int64_t)(k - 1) * cstride], TAB ? icol[(int64_t)(a - k - 1) * sz2] : pen[a - k - 1]), simc));

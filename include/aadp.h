@@ -153,6 +153,19 @@ int aadp_fill_pair_tabulated(aadp_ctx* ctx, const float* sim, int Lq, int Lt, co
                              const float* ins_tab, int is_local, uint32_t flags, int direction, float* score,
                              int32_t* prev_q, int32_t* prev_t);
 
+/* The same for MANY pairs in one call (database search with a profile evaluator): item k has Lq[k] x Lt[k] positions
+ * and its three tables at sim + sim_off[k], del_tab + del_off[k], ins_tab + ins_off[k] (offsets in floats, layouts as
+ * above).  One CTA per (item, direction), chunked by the dense-scratch budget.  direction: AADP_FWD, AADP_REV or 3.
+ * Host outputs (any may be NULL): fwd_score[k] = D[last][last] of the forward fill, rev_score[k] = D[0][0] of the
+ * reverse fill, and -- non-local forward fills only -- the optimal alignment of every item traced on the GPU
+ * (Optimal::enumerate, optimal.h:47-75): ali_off (n+1, slot k = Lq[k]+2 aligned pairs, computed on the host), pairs
+ * (2*ali_off[n] ints), n_out, status (3 = "Illegal alignment start pair").                                      */
+int aadp_fill_batch_tabulated(aadp_ctx* ctx, int64_t n, const int32_t* Lq, const int32_t* Lt, const float* sim,
+                              const int64_t* sim_off, const float* del_tab, const int64_t* del_off,
+                              const float* ins_tab, const int64_t* ins_off, int is_local, uint32_t flags,
+                              int direction, float* fwd_score, float* rev_score, int64_t* ali_off, int32_t* pairs,
+                              int64_t pairs_cap, int32_t* n_out, int32_t* status);
+
 /* ---- batch of pairs, HOST buffers (the end-to-end call) ------------------------------------
  * residues: all sequences back to back; sequence s is residues[seq_off[s] .. seq_off[s+1]).
  * pair p aligns query pair_q[p] against template pair_t[p].

@@ -891,6 +891,48 @@ def test_local_optimal_alignments_of_a_batch_on_gpu(blosum):
     c.close()
 
 
+def test_batch_of_tabulated_pairs(golden_tab):
+    # aadp_fill_batch_tabulated: many pairs with position-dependent gap tables in one call; golden = the real reference
+    # fill driven by a table-backed Evaluator; optimal alignments = Optimal::enumerate over the reference matrices
+    import alignment_algos_b200 as a
+    g = golden_tab
+    c = a.Context(0)
+    for local in (0, 1):
+        names = [n for n in golden_cases(g) if int(g[n + ".local"]) == local]
+        sims, dels, inss = [g[n + ".sim"] for n in names], [g[n + ".del"] for n in names], [g[n + ".ins"] for n in names]
+        c.set_option("general_budget_mcells", 1)     # several chunks
+        fs, rs, aoff, pairs, n_out, st = c.fill_batch_tabulated(sims, dels, inss, bool(local), a.BOTH)
+        c.set_option("general_budget_mcells", 400)
+        fs2, rs2, _, pairs2, n2, st2 = c.fill_batch_tabulated(sims, dels, inss, bool(local), a.BOTH)
+        assert_matrix_equal("chunked fwd", fs, fs2)
+        assert_matrix_equal("chunked rev", rs, rs2)
+        for k, n in enumerate(names):
+            F = g[n + ".fwd.score"]
+            assert fs[k] == F[-1, -1], n
+            assert rs[k] == g[n + ".rev.score"][0, 0], n
+            if not local:
+                wst, wpairs, _ = _subali_walk(F, g[n + ".fwd.pq"], g[n + ".fwd.pt"], (0, 0, F.shape[0] - 1, F.shape[1] - 1))
+                assert st[k] == wst, n
+                assert aoff[k + 1] - aoff[k] == F.shape[0]
+                assert_matrix_equal(n + " optimal", pairs[aoff[k]:aoff[k] + n_out[k]], wpairs)
+                assert_matrix_equal(n + " chunked optimal", pairs2[aoff[k]:aoff[k] + n2[k]], wpairs)
+    # random larger items against the oracle, forward only
+    rng = np.random.default_rng(77)
+    items = [po.hmap_like_tables(rng, int(rng.integers(20, 140)), int(rng.integers(20, 140)), po.SEMI_LOCAL) for _ in range(40)]
+    fs, rs, aoff, pairs, n_out, st = c.fill_batch_tabulated([x[0] for x in items], [x[1] for x in items], [x[2] for x in items],
+                                                            False, a.FWD)
+    assert rs is None
+    for k in range(0, 40, 3):
+        sim, dt, it = items[k]
+        F, fq, ft = po.Oracle.fill_tab(sim, dt, it, False, po.FWD)
+        wst, wpairs, _ = _subali_walk(F, fq, ft, (0, 0, F.shape[0] - 1, F.shape[1] - 1))
+        assert fs[k] == F[-1, -1] and st[k] == wst
+        assert_matrix_equal("random item %d optimal" % k, pairs[aoff[k]:aoff[k] + n_out[k]], wpairs)
+    z = c.fill_batch_tabulated([], [], [], False, a.BOTH)
+    assert len(z[0]) == 0
+    c.close()
+
+
 def test_general_entry_with_similarity_matrix(blosum):
     # aadp_fill_pair_general: the fill from a host-built similarity matrix (any Evaluator) + affine gaps
     import alignment_algos_b200 as a
