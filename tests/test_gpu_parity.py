@@ -277,6 +277,60 @@ def test_large_batch_size_independent_properties(ctx):
                     assert rp[1][1] == len(t), "only the :868 pattern may produce such a step"
 
 
+def test_large_batch_enumeration_properties(ctx):
+    # near-optimal enumeration at a size the oracle cannot sweep (8000 related pairs of 100-500 residues): every
+    # alignment (1) is a valid alignment from (0,0) to (last,last) whose rescored value equals the returned score,
+    # (2) scores above the pair's threshold, (3) lies inside the near-optimal cell set of the fused mask pass;
+    # (4) the alignments of a pair are pairwise different and (5) the optimal alignment is among them;
+    # (6) constrained enumeration with all flags set = the optimal alignment of every branch taken at the root
+    import alignment_algos_b200 as a
+    alpha20, M20 = a.blosum62()
+    rng = np.random.default_rng(2027)
+    seqs, pq, pt = [], [], []
+    for k in range(8000):
+        L = int(rng.integers(100, 501))
+        s = rng.integers(0, 20, L).astype(np.uint8)
+        m = s.copy()
+        m[::9] = rng.integers(0, 20, len(m[::9]))
+        cut = int(rng.integers(10, L - 10))
+        seqs += [s, np.concatenate([m[:cut], m[cut + int(rng.integers(0, 3)):]])]
+        pq.append(2 * k)
+        pt.append(2 * k + 1)
+    pq, pt = np.array(pq, np.int32), np.array(pt, np.int32)
+    res, off = a.Context.pack(seqs)
+    at, delta, K = po.SEMI_LOCAL, 0.01, 48
+    ctx.set_scoring(M20, 12, 1, at)
+    out = ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV | a.W_TB | a.W_MASK, delta)
+    got = ctx.near_optimal(np.arange(8000), delta, K)
+    con = ctx.near_optimal(np.arange(0, 8000, 40), delta, K, constrained=True)
+    n_multi = 0
+    for p in range(8000):
+        st, thr, alis = got[p]
+        assert st in (0, 1) and len(alis) >= 1 and thr == out["threshold"][p]
+        assert st == 0 or len(alis) == K
+        n_multi += len(alis) > 1
+        if p % 40:
+            continue
+        q, t = seqs[pq[p]], seqs[pt[p]]
+        mask = ctx.fetch_pair(p, len(q), len(t), fwd=False, rev=False, tb=False, scores=False, mask=True)["nearopt"]
+        rc, opt_pairs, opt_sc = ctx.optimal(p, a.FWD, len(q), len(t))
+        seen = set()
+        for sc, pairs in alis:
+            pl = [tuple(int(v) for v in x) for x in pairs]
+            assert pl[0] == (0, 0) and pl[-1] == (len(q) + 1, len(t) + 1)
+            assert _rescore(None, q, t, pl, M20, 12, 1, at) == sc and sc > thr
+            assert all(mask[i, j] == 1 for (i, j) in pl[1:-1])
+            seen.add(tuple(pl))
+        assert len(seen) == len(alis)
+        assert tuple(tuple(int(v) for v in x) for x in opt_pairs) in seen or st == 1
+        cst, cthr, calis = con[p // 40]
+        assert cst == 0 and cthr == thr and 1 <= len(calis)
+        for sc, pairs in calis:
+            pl = [tuple(int(v) for v in x) for x in pairs]
+            assert _rescore(None, q, t, pl, M20, 12, 1, at) == sc
+    assert n_multi > 2000
+
+
 @pytest.mark.parametrize("at", [po.GLOBAL, po.SEMI_LOCAL], ids=["global", "semi_local"])
 def test_extreme_scores_near_the_packed_bound(ctx, blosum, at):
     # identical poly-W sequences (largest positive scores the packed int16 path accepts), all-mismatch
