@@ -2468,7 +2468,7 @@ int aadp_fill_subpair_batch(aadp_ctx* c, const uint8_t* residues, const int64_t*
   for (int64_t p0 = 0; p0 < nitems;) {
     off.assign(1, 0);
     int64_t p1 = p0;
-    while (p1 < nitems && (p1 == p0 || off.back() + cells[(size_t)p1] <= c->gg_budget_cells) && p1 - p0 < 65535 * 16) {
+    while (p1 < nitems && (p1 == p0 || off.back() + cells[(size_t)p1] <= c->gg_budget_cells)) {
       off.push_back(off.back() + cells[(size_t)p1]);
       ++p1;
     }
