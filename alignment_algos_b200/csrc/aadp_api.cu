@@ -2379,8 +2379,21 @@ static int near_optimal_impl(aadp_ctx* c, int cno, const uint8_t* flags, const i
   };
   if (back(n_ali, c->ucw_n, (size_t)n * 4) || back(status, c->ucw_status, (size_t)n * 4) ||
       back(scores, c->ucw_scores, (size_t)n * max_alignments * 4) || back(ali_len, c->ucw_len, (size_t)n * max_alignments * 4) ||
-      back(paths, c->ucw_paths, (size_t)poff[(size_t)n] * 8) || back(threshold, c->ucw_thr, (size_t)n * 4))
+      back(threshold, c->ucw_thr, (size_t)n * 4))
     return fail("device to host copy failed");
+  if (paths) {
+    // only the slots that hold an alignment travel: the budget is usually far larger than what a pair emits
+    std::vector<int32_t> cnt((size_t)n);
+    CK(cudaMemcpyAsync(cnt.data(), c->ucw_n.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t slot = (poff[(size_t)k + 1] - poff[(size_t)k]) / max_alignments;
+      const size_t bytes = (size_t)cnt[(size_t)k] * (size_t)slot * 8;
+      if (!bytes) continue;
+      CK(cudaMemcpyAsync(paths + 2 * poff[(size_t)k], c->ucw_paths.as<int2>() + poff[(size_t)k], bytes, cudaMemcpyDeviceToHost, c->stream));
+      c->d2h_bytes += (int64_t)bytes;
+    }
+  }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

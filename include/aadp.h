@@ -260,7 +260,8 @@ int aadp_batch_optimal_all(aadp_ctx* ctx, int direction, int64_t* ali_off, int32
  *   scores     n*K: AlignedPairList::score of alignment a of pair k at [k*K + a]
  *   ali_len    n*K: aligned pairs of that alignment, including (0,0) and (last,last)
  *   path_off   n+1 (computed on the host; call with every other output NULL to size `paths`): alignment a of pair k
- *              occupies paths[2*(path_off[k] + a*(Lq+2)) ...], (query_idx, template_idx) front to back
+ *              occupies paths[2*(path_off[k] + a*(Lq+2)) ...], (query_idx, template_idx) front to back; only the
+ *              slots a < n_ali[k] are written
  *   threshold  n: min((1-delta_ratio)*opt, opt-0.1f) (ucw.h:81-83)                                                */
 int aadp_batch_near_optimal(aadp_ctx* ctx, const int64_t* pair_ids, int64_t n, float delta_ratio,
                             int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
