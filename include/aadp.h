@@ -3,7 +3,9 @@
  * Drop-in boundary for ONE path of christang/alignment-algos: the dynamic-programming matrix
  * fill of dpmatrix.{h,cpp} (forward + reverse, global + local), the optimal tracebacks of
  * optimal.h / optimal_rev.h and the near-optimal cell set the enumerators of ucw.h / cw.h
- * consume.  The reference has no FFI of its own (it is one C++ template library); the entry
+ * consume -- plus the callers either side of it: those two enumerators themselves,
+ * sub-rectangle fills with optimal_subali.h for loop closure, and evaluators with tabulated
+ * (position-dependent) gap penalties.  The reference has no FFI of its own (it is one C++ template library); the entry
  * points below are what its DPMatrix<S1,S2,Etype>::build() (dpmatrix.h:291-317) binds to when
  * the fill is moved to the GPU -- see INTEGRATION.md for the C++ side of the binding
  * (include/hmap2/dpmatrix.h is that binding, source compatible with the reference class).
