@@ -98,6 +98,11 @@ struct Batch {
   double cells = 0;
   uint32_t uploaded_what = 0;
   uint32_t ran_what = 0;
+  // The schedule (pair classes, product offsets, task lists, score-storage mode) and the residue validation were
+  // derived from the scoring in force at upload time.  sched_ok is cleared by aadp_set_scoring and by every entry
+  // point that reuses the batch storage for its own items; aadp_run_batch refuses to run a stale schedule.
+  bool sched_ok = false;
+  int seq_A = 0;  // alphabet size the resident residues were validated against
 };
 
 struct HostPool {
@@ -1083,7 +1088,18 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
   CK(cudaMemcpyAsync(c->subf.p, sub, (size_t)A * A * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->b.ran_what = 0;
-  if (s < 0 || c->force_float) {
+  c->b.sched_ok = false;  // classification, score bounds and storage modes depend on the scoring
+  if (c->b.seq_A != A) c->b.have_seqs = false;  // the residues were validated against another alphabet
+  // the integer kernels also need the scaled substitution scores inside the int8 profile range and moderate gap
+  // penalties; anything else (e.g. an integer matrix scaled by 10 whose entries exceed 127) is still a legal
+  // reference input and takes the exact general-gap path instead of being refused
+  bool fits = s >= 0;
+  if (fits) {
+    const float m = (float)(1 << s);
+    for (int i = 0; i < A * A && fits; ++i) fits = fabsf(sub[i] * m) <= 127.f;
+    fits = fits && gi * m <= 1e6f && ge * m <= 1e5f;
+  }
+  if (!fits || c->force_float) {
     // not representable on an integer grid (e.g. the reference defaults 4.73 / 0.34, alib.cpp:17-18): the exact
     // general-gap fp32 kernel reproduces the reference's own scan and roundings (aadp_general.cuh)
     c->float_mode = true;
@@ -1099,11 +1115,9 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
   int mx = 0;
   for (int i = 0; i < A * A; ++i) {
     const float v = sub[i] * m;
-    if (fabsf(v) > 127.f) return fail("substitution scores exceed the int8 profile range after scaling");
     c->sub8_h[i] = (int8_t)(int)v;
     mx = std::max(mx, std::abs((int)v));
   }
-  if (gi * m > 1e6f || ge * m > 1e5f) return fail("gap penalties too large");
   c->max_abs_sub = mx;
   c->sc.A = A;
   c->sc.gi = (int)(gi * m);
@@ -1198,6 +1212,7 @@ static int upload_sequences_impl(aadp_ctx* c, const uint8_t* residues, const int
   CK(cudaMemcpyAsync(c->pin_flag, c->badflag.p, 4, cudaMemcpyDeviceToHost, cs));
   CK(cudaEventRecord(c->ev_flag, cs));
   b.have_seqs = true;
+  b.seq_A = c->sc.A;
   return 0;
 }
 
@@ -1222,6 +1237,7 @@ static size_t pairs_pin_bytes(int64_t npairs) { return (size_t)npairs * (8 + 1 +
 static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what,
                           int nsplit = 1, const std::function<int(size_t)>* on_chunk = nullptr) {
   Batch& b = c->b;
+  b.sched_ok = false;
   b.npairs = npairs;
   b.pair_q.assign(pair_q, pair_q + npairs);
   b.pair_t.assign(pair_t, pair_t + npairs);
@@ -1238,8 +1254,10 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
     b.ran_what = 0;
     if (upload_vec(c, c->pair_q, b.pair_q)) return 1;
     if (upload_vec(c, c->pair_t, b.pair_t)) return 1;
+    b.sched_ok = true;
     return 0;
   }
+  b.sched_ok = false;
   if (build_batch_meta(c, what)) return 1;
   b.uploaded_what = what;
   b.ran_what = 0;
@@ -1264,8 +1282,10 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
     if (bytes)
       CK(cudaMemcpyAsync(c->tasks.as<int32_t>() + b.chunk_first[(size_t)k] * 64, tasks_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += (int64_t)bytes;
+    if (k == 0) b.sched_ok = true;  // on_chunk launches from this schedule
     if (on_chunk && (*on_chunk)((size_t)k)) return 1;
   }
+  b.sched_ok = true;
   return 0;
 }
 
@@ -1273,7 +1293,9 @@ int aadp_upload_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_o
                       const int32_t* pair_t, int64_t npairs, uint32_t what) {
   if (check_ctx(c, true)) return 1;
   if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
-  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if (!seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if (seq_off[0] < 0) return fail("sequence offsets must start at a non-negative offset");
+  if (nseq && !residues && seq_off[nseq] > seq_off[0]) return fail("null input");
   if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
     return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1520,6 +1542,8 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     G.delfree = (ov->align_type == AADP_LOCAL || ov->align_type == AADP_SEMI_LOCAL || ov->align_type == AADP_LOCAL_GLOBAL);
     G.insfree = (ov->align_type == AADP_LOCAL || ov->align_type == AADP_SEMI_LOCAL || ov->align_type == AADP_GLOBAL_LOCAL);
     G.local = ov->align_type == AADP_LOCAL;
+    if (ov->flags & AADP_CLAMP_ON) G.local = 1;   // dpmatrix.h:155: the constructor's align_t, not the evaluator's
+    if (ov->flags & AADP_CLAMP_OFF) G.local = 0;
     G.repro_rev_bug = (ov->flags & AADP_REPRO_REV_BUG) ? 1 : 0;
     G.simov = ov->d_sim;
     G.A = 1;
@@ -1805,6 +1829,9 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
                    float* d_threshold, int64_t* d_nearopt_count) {
   if (check_ctx(c, true)) return 1;
   Batch& b = c->b;
+  if (!b.sched_ok || !b.have_seqs)
+    return fail("aadp_run_batch: no valid resident batch (the batch must be uploaded again after aadp_set_scoring or "
+                "after a single-pair / general-gap / tabulated call reused the context)");
   if ((what & ~b.uploaded_what) & (AADP_W_TB | AADP_W_SCORES | AADP_W_MASK))
     return fail("aadp_run_batch asks for products the batch was not uploaded for");
   if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
@@ -1821,7 +1848,9 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
                     float* rev_score, float* threshold, int64_t* nearopt_count) {
   if (check_ctx(c, true)) return 1;
   if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
-  if ((nseq && (!residues && seq_off[nseq] > 0)) || !seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if (!seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
+  if (seq_off[0] < 0) return fail("sequence offsets must start at a non-negative offset");
+  if (nseq && !residues && seq_off[nseq] > seq_off[0]) return fail("null input");
   if ((what & AADP_W_MASK) && (what & (AADP_W_FWD | AADP_W_REV)) != (AADP_W_FWD | AADP_W_REV))
     return fail("AADP_W_MASK needs both AADP_W_FWD and AADP_W_REV");
   if (!(what & (AADP_W_FWD | AADP_W_REV))) return fail("nothing to do: neither AADP_W_FWD nor AADP_W_REV");
@@ -2542,6 +2571,7 @@ int aadp_fill_pair_general(aadp_ctx* c, const float* sim, int Lq, int Lt, float 
   b.have_seqs = false;
   b.ran_what = 0;
   b.uploaded_what = 0;
+  b.sched_ok = false;
   b.tb_off.clear();
   CK(cudaStreamSynchronize(c->stream));
   if (pin_reserve(c, 4096)) return 1;
@@ -2586,6 +2616,7 @@ int aadp_fill_pair_tabulated(aadp_ctx* c, const float* sim, int Lq, int Lt, cons
   b.have_seqs = false;
   b.ran_what = 0;
   b.uploaded_what = 0;
+  b.sched_ok = false;
   b.tb_off.clear();
   CK(cudaStreamSynchronize(c->stream));
   if (pin_reserve(c, 4096)) return 1;
@@ -2658,6 +2689,7 @@ int aadp_fill_batch_tabulated(aadp_ctx* c, int64_t n, const int32_t* Lq, const i
   b.have_seqs = false;
   b.ran_what = 0;
   b.uploaded_what = 0;
+  b.sched_ok = false;
   b.tb_off.clear();
   CK(cudaStreamSynchronize(c->stream));
   if (pin_reserve(c, (size_t)(2 * n + 1) * 8 + (size_t)n * 8 + (size_t)(n + 1) * 8 + 4096)) return 1;

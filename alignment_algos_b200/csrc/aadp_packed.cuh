@@ -39,7 +39,11 @@ namespace aadp {
 // 0xFFFF/0 mask per half for the traceback decisions.  (2) Adding a packed non-positive constant is
 // a plain 32-bit add (the low half always carries into the high half, which the constant
 // pre-compensates), so those adds can issue on the FMA pipe (IMAD.IADD) instead of the ALU pipe.
-constexpr int kBias16 = 21500;
+// kBias16 is chosen so that (a) single-biased values v + B stay inside [1024, 0x7C00) for v in [kNeg16 - drift, bound)
+// and (b) DOUBLY biased sums F + X (the near-optimal slack, v in [-2*bound, bound)) stay inside (0x8000, 0xFC00):
+// there they are negative, finite fp16 patterns whose fp16 order is the REVERSE of their integer order, so the same
+// one-instruction sign test decides slack > thr without removing a bias first (see the MSK pass).
+constexpr int kBias16 = 24000;
 constexpr int kNeg16 = -20000;    // "-infinity" seed of E/F chains (only ever extended once)
 constexpr int kFloor16 = -13000;  // clamp floor of M / slack
 constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must satisfy to use this kernel
@@ -186,8 +190,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-// acc | (t & pat)
-__device__ __forceinline__ uint32_t or_and(uint32_t acc, uint32_t t, uint32_t pat) { return acc | (t & pat); }
+// Bit gather on the FMA pipe.  t holds four bytes that are 0xFF or 0x00 (PRMT sign replication); bit k of byte j of
+// the result must be set where byte j of t is 0xFF.  Instead of  acc |= t & (0x01010101 << k)  (LOP3, ALU pipe -- the
+// pipe the VIMNMX/PRMT recurrence saturates), accumulate  acc -= t << k  with ONE multiply-add (IMAD, FMA pipe):
+// 0xFF << (8j+k) = 2^(8j+8+k) - 2^(8j+k), so the sum over the eight cells of a group telescopes to B - (B << 8),
+// B being the wanted word, and B = acc * (1 + 2^8 + 2^16 + 2^24) mod 2^32 -- one more IMAD per group (gat_fin).
+__device__ __forceinline__ uint32_t gat(uint32_t acc, uint32_t t, int k) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(t), "r"(0u - (1u << k)), "r"(acc));
+  return d;
+}
+__device__ __forceinline__ uint32_t gat_fin(uint32_t acc) {
+  uint32_t d;
+  asm("mul.lo.u32 %0, %1, 0x01010101;" : "=r"(d) : "r"(acc));
+  return d;
+}
 
 // Per-lane, per-half final-row summary (what the final cell needs from this lane's 16 columns).
 struct RowSum {
@@ -288,9 +305,13 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     __syncwarp();
   }
 
-  // ---- state for virtual row 0 (packed: A low, B high)
-  uint32_t Xp[16], Fs[16], Mg[16], nge[16];
+  // ---- state for virtual row 0 (packed: A low, B high).  Fn[c] is the F of the row ABOUT to be processed: it is
+  // updated as soon as M of the current row is known (F(i+1,c) = max(F(i,c) - ge, M(i,c) - gi)), so no copy of
+  // M - gi has to live across a row; its open/extend decision bit belongs to the next row's traceback word and is
+  // carried there in fprev[].
+  uint32_t Xp[16], Fn[16], nge[16];
   uint32_t xl_hold;
+  uint32_t fprev[2] = {0u, 0u};  // fopen plane of the next row: byte 1 = pair A, byte 3 = pair B (8 columns per word)
   {
     int xh[2];
 #pragma unroll
@@ -311,10 +332,12 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           m[h] = kNeg16;
           g[h] = (S.insfree && j == Lt[h]) ? 0 : -ge;  // zero-penalty F chain in the last column
         }
+        // F of row 1 and its decision bit ("the open candidate wins strictly")
+        if (TBM && f[h] + g[h] < m[h]) fprev[c >> 3] |= 1u << (8 * (2 * h + 1) + 7 - (c & 7));
+        f[h] = max(f[h] + g[h], m[h]);
       }
       Xp[c] = pkb(x[0], x[1]);
-      Fs[c] = pkb(f[0], f[1]);
-      Mg[c] = pkb(m[0], m[1]);
+      Fn[c] = pkb(f[0], f[1]);
       nge[c] = pkdec(-g[0], -g[1]);
     }
 #pragma unroll
@@ -324,15 +347,19 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     }
     xl_hold = pkb(xh[0], xh[1]);
   }
-  // injection at the segment's first lane: X(i,0) when register 0 is column 1, "-inf" when it is a pad
+  // injection at the segment's first lane: X(i,0) when register 0 is column 1, "-inf" when it is a pad.
+  // xn = (shuffled & inj_keep) | (binj & inj_b_mask) | inj_floor;  binj = X(s+1,0) of the segment's first lane,
+  // advanced by one gap extension per step (dpmatrix.h:420-426)
   const uint32_t inj_b_mask = (seg_start ? ((sig[0] == 0 ? 0x0000ffffu : 0u) | (sig[1] == 0 ? 0xffff0000u : 0u)) : 0u);
-  const uint32_t inj_mask = seg_start ? 0xffffffffu : 0u;
+  const uint32_t inj_keep = seg_start ? 0u : 0xffffffffu;
   const uint32_t NEG2 = pkb(kNeg16, kNeg16);
   const uint32_t FLOOR2 = pkb(kFloor16, kFloor16);
+  const uint32_t inj_floor = seg_start ? (FLOOR2 & ~inj_b_mask) : 0u;
+  const uint32_t inj_neg = seg_start ? NEG2 : 0u;
   const uint32_t NGE2 = pkdec(ge, ge);
   const uint32_t NGI2 = pkdec(gi, gi);
-  const uint32_t NBIASC = pkdec(kBias16, kBias16);
-
+  uint32_t binj = S.insfree ? pkb(0, 0) : pkb(-gi, -gi);
+  const uint32_t binj_step = S.insfree ? 0u : NGE2;
   // ---- per-half output bases (diagonal-major: the address of a step is base + step * stride)
   uint8_t* tbp[2] = {nullptr, nullptr};
   int16_t* scp[2] = {nullptr, nullptr};
@@ -362,7 +389,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       float t = floorf(thr_f[h] * (float)(1 << S.scale_log2));  // slack (integer) > thr  <=>  slack > floor(thr)
       ti[h] = (int)fminf(fmaxf(t, (float)kFloor16), (float)kPackedBound);
     }
-    THR2 = pkb(ti[0], ti[1]);
+    THR2 = pk2(ti[0] + 2 * kBias16, ti[1] + 2 * kBias16);  // compared with the doubly biased sum F + X
   }
 
   // ---- query residues: each lane stages its own rows in a private 16-byte ring per half
@@ -409,45 +436,37 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   // 32*((i-1) % 3); rotated once per row instead of dividing by 3 (a lane's active rows are consecutive, from 1)
   int fcur_off = 32, fnxt_off = 0;
   long long cnt[2] = {0, 0};
-  RowSum capB = {kNeg32, 0, kNeg32, kNeg32};
-  bool have_capB = false;
+  RowSum fin[2] = {{kNeg32, 0, kNeg32, kNeg32}, {kNeg32, 0, kNeg32, kNeg32}};
 
-  // final-row summary of half h from the live state
-  auto row_summary = [&](int h) -> RowSum {
-    RowSum r = {kNeg32, 0, kNeg32, kNeg32};
+  // What the final cell needs from this lane's 16 columns (RowSum) is M(Lq,.) and F(Lq,Lt).  The loop-carried state
+  // holds exactly the inputs of that row -- X(Lq-1,.) and F(Lq,.) -- at the END of the step of row Lq-1 (before the
+  // loop when Lq = 1), and the two halves of a couple get there at different steps.  A rare branch at that point
+  // only parks the raw registers in local memory (volatile: the compiler otherwise promotes the arrays to 66 more
+  // registers); the summary itself is computed after the loop.  Computing it inside the loop cost ~50 registers.
+  volatile uint32_t capX[2][17], capF[2][16];
+  int capQ[2] = {0, 0};
+  auto capture = [&](int h, int qa) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int j = off * 16 + c + 1 - sig[h];
-      const int m = unb16(Mg[c], h) + gi;  // M(Lq, j)
-      if (j >= 1 && j < Lt[h]) {
-        const int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt[h] - j));
-        if (v > r.rb_val) { r.rb_val = v; r.rb_k = j; }
-      } else if (j == Lt[h]) {
-        r.diag = m;
-        r.col = (Lq[h] >= 2) ? unb16(Fs[c], h) + (S.insfree ? gi : 0) : kNeg32;
-      }
-    }
-    return r;
+    for (int c = 0; c < 16; ++c) { capX[h][c + 1] = Xp[c]; capF[h][c] = Fn[c]; }
+    capX[h][0] = xl_hold;
+    capQ[h] = qa;
   };
+  for (int h = 0; h < 2; ++h)
+    if (pid[h] >= 0 && Lq[h] == 1) capture(h, (int)qp[h][0]);
 
   for (int s = 0; s < nsteps; ++s) {
     uint32_t xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
     uint32_t e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
     uint32_t mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
-    const int i = s - off + 1;
-    {
-      // X(i,0), dpmatrix.h:420-426; only the segment's first lane uses it
-      const int b = (i <= 0) ? 0 : -(S.insfree ? 0 : gi + ge * (i - 1));
-      const uint32_t b2 = pkb(b, b);
-      const uint32_t inj = (b2 & inj_b_mask) | (FLOOR2 & ~inj_b_mask);
-      xn = (xn & ~inj_mask) | (inj & inj_mask);
-      e_in = (e_in & ~inj_mask) | (NEG2 & inj_mask);
-      mg_in = (mg_in & ~inj_mask) | (NEG2 & inj_mask);
-    }
-    const bool act0 = pid[0] >= 0 && i >= 1 && i <= Lq[0];
-    const bool act1 = pid[1] >= 0 && i >= 1 && i <= Lq[1];
+    const int r0 = s - off;  // row - 1 of this lane
+    const int i = r0 + 1;
+    xn = (xn & inj_keep) | ((binj & inj_b_mask) | inj_floor);
+    e_in = (e_in & inj_keep) | inj_neg;
+    mg_in = (mg_in & inj_keep) | inj_neg;
+    binj = addc(binj, binj_step);
+    const bool act0 = (unsigned)r0 < (unsigned)Lq[0];  // Lq is 0 for an empty half
+    const bool act1 = (unsigned)r0 < (unsigned)Lq[1];
     if (act0 || act1) {
-      const int r0 = i - 1;
       // One cp.async group is committed per row.  Query blocks are requested 8 rows ahead and forward
       // scores 2 rows ahead, so only the most recent group(s) may still be in flight.
       if (i == 1) {
@@ -513,63 +532,67 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           Mv[c] = __vadd2(simp, Xd);
           if (MSK) {
             // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
-            // element 15-c of the forward chunk.  One bias is removed so that the sum is biased once.
+            // element 15-c of the forward chunk.
             const int e = 15 - c;
             const uint32_t fv = prmt(fcur[0][e >> 1], fcur[1][e >> 1], (e & 1) ? 0x7632u : 0x5410u);
-            // both halves are positive 16-bit numbers whose sum stays below 65536, so fv + Xd is a plain 32-bit
-            // add without a carry between the halves; removing one bias uses the carry-compensated constant
-            // (the low sum of a real cell is >= bias, so the borrow pattern is fixed).  One IADD3.
-            const uint32_t slack = fv + Xd + NBIASC;
-            const uint32_t d5 = lt_sign(THR2, slack);  // sign <=> thr < slack
+            // both halves are positive 16-bit numbers whose sum stays below 65536: a plain 32-bit add (IMAD, FMA
+            // pipe) without a carry between the halves.  The sum carries the bias TWICE and is a negative fp16
+            // pattern, like THR2: among negative patterns the larger integer is the smaller fp16 number, so the
+            // sign of (slack - thr) as fp16 numbers is set exactly where slack > thr as integers.
+            const uint32_t slack = addc(fv, Xd);
+            const uint32_t d5 = lt_sign(slack, THR2);
             // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
-            if (c & 1) accM |= prmt(d5prev, d5, 0xFBD9u) & (0x01010101u << (7 - (c >> 1)));
+            if (c & 1) accM = gat(accM, prmt(d5prev, d5, 0xFBD9u), 7 - (c >> 1));
             else d5prev = d5;
           }
           Xd = Xp[c];
         }
       }
-      // ---- phase 2: E chain, F, X, traceback bits
+      // ---- phase 2: E chain, X, next row's F, traceback bits
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const uint32_t M = Mv[c];
-        uint32_t F, X;
+        const uint32_t F = Fn[c];
+        uint32_t X;
         if (TBM) {
           const uint32_t Eext = addc(E, NGE2);
-          const uint32_t Fext = addc(Fs[c], nge[c]);
           const uint32_t dE = lt_sign(Eext, Mgl);   // the open candidate wins strictly
           E = __vmaxs2(Eext, Mgl);
-          const uint32_t dF = lt_sign(Fext, Mg[c]);
-          F = __vmaxs2(Fext, Mg[c]);
           const uint32_t dS1 = lt_sign(M, E);       // E > M
           const uint32_t t = __vmaxs2(M, E);
           const uint32_t dS2 = lt_sign(t, F);       // F > max(M,E)
           X = __vmaxs2(t, F);
+          Mgl = addc(M, NGI2);
+          const uint32_t Fext = addc(F, nge[c]);
+          const uint32_t dF = lt_sign(Fext, Mgl);   // decision of the NEXT row's F
+          Fn[c] = __vmaxs2(Fext, Mgl);
           // PRMT with sign replication turns four sign bits into four 0xFF/0x00 bytes [A.x, A.y, B.x, B.y]
-          const uint32_t pat = 0x01010101u << (7 - (c & 7));
-          acc01 |= prmt(dS1, dS2, 0xFBD9u) & pat;
-          acc23 |= prmt(dE, dF, 0xFBD9u) & pat;
+          acc01 = gat(acc01, prmt(dS1, dS2, 0xFBD9u), 7 - (c & 7));
+          acc23 = gat(acc23, prmt(dE, dF, 0xFBD9u), 7 - (c & 7));
           if ((c & 7) == 7) {
-            tbA[c >> 3] = prmt(acc01, acc23, 0x5410u);  // planes selE, selF, eopen, fopen of pair A
-            tbB[c >> 3] = prmt(acc01, acc23, 0x7632u);
+            const uint32_t b01 = gat_fin(acc01), b23 = gat_fin(acc23);
+            // eopen of this row, fopen computed one row earlier
+            const uint32_t m23 = (b23 & 0x00ff00ffu) | (fprev[c >> 3] & 0xff00ff00u);
+            fprev[c >> 3] = b23;
+            tbA[c >> 3] = prmt(b01, m23, 0x5410u);  // planes selE, selF, eopen, fopen of pair A
+            tbB[c >> 3] = prmt(b01, m23, 0x7632u);
             acc01 = 0;
             acc23 = 0;
           }
         } else {
           E = __viaddmax_s16x2(E, pk2(-ge, -ge), Mgl);
-          F = __vmaxs2(addc(Fs[c], nge[c]), Mg[c]);
           X = __vimax3_s16x2(M, E, F);
+          Mgl = addc(M, NGI2);
+          Fn[c] = __vmaxs2(addc(F, nge[c]), Mgl);
         }
-        Mgl = addc(M, NGI2);
         Xp[c] = X;
-        Fs[c] = F;
-        Mg[c] = Mgl;
         if (FST && (c & 1)) {
           oA[c >> 1] = prmt(Mv[c - 1], M, 0x5410u);
           oB[c >> 1] = prmt(Mv[c - 1], M, 0x7632u);
         }
       }
       if (MSK) {
-        accM &= VM;
+        accM = gat_fin(accM) & VM;
         fnxt_off = fcur_off;
         fcur_off = fcur_off == 64 ? 0 : fcur_off + 32;
       }
@@ -603,16 +626,36 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           *reinterpret_cast<uint16_t*>(mkp[1] + (size_t)(snl * 2u)) = (uint16_t)(accM >> 16);
           cnt[1] += __popc(accM >> 16);
         }
-        // the shorter query of the couple ends first: keep its final row before later rows overwrite it
-        if (i == Lq[1] && Lq[1] < Lq[0]) { capB = row_summary(1); have_capB = true; }
+      }
+      if (i + 1 == Lq[0] || i + 1 == Lq[1]) {
+        for (int h = 0; h < 2; ++h)
+          if (i + 1 == Lq[h]) capture(h, h ? qa_n1 : qa_n0);
       }
     }
   }
 
+  // ---- final-row summaries from the parked state: M(Lq,j) = sim(Lq,j) + X(Lq-1,j-1)
+  for (int h = 0; h < 2; ++h) {
+    if (pid[h] < 0) continue;
+    const int8_t* prow = (h ? profB : profA) + capQ[h] * W + lane * 16;
+    RowSum r = {kNeg32, 0, kNeg32, kNeg32};
+    for (int c = 0; c < 16; ++c) {
+      const int j = off * 16 + c + 1 - sig[h];
+      const int m = unb16(capX[h][c], h) + (int)prow[c];  // M(Lq, j)
+      if (j >= 1 && j < Lt[h]) {
+        const int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt[h] - j));
+        if (v > r.rb_val) { r.rb_val = v; r.rb_k = j; }
+      } else if (j == Lt[h]) {
+        r.diag = m;
+        r.col = (Lq[h] >= 2) ? unb16(capF[h][c], h) + (S.insfree ? gi : 0) : kNeg32;
+      }
+    }
+    fin[h] = r;
+  }
   // ---- final cells (dpmatrix.h:504-534 / 844-874): match, bottom row (k ascending), right column
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    RowSum r = (h == 1 && have_capB) ? capB : row_summary(h);
+    const RowSum r = fin[h];
     __syncwarp();
     red[lane] = make_int4(r.rb_val, r.rb_k, r.diag, r.col);
     __syncwarp();

@@ -44,6 +44,12 @@ typedef struct aadp_ctx aadp_ctx;
 
 /* aadp_set_scoring flags */
 #define AADP_REPRO_REV_BUG 1u /* reproduce dpmatrix.h:868 (opt_j = t1_m1) -- the reference's behaviour */
+/* aadp_fill_pair_general only.  In the reference the DPMatrix constructor's align_t alone selects the 0-clamp of the
+ * local fills (dpmatrix.h:155, 310) while the evaluator's AliParams alone selects the free end gaps
+ * (aasubalib.h:27-77); the two may disagree (e.g. a `global` constructor over semi_local AliParams).  These flags
+ * override the clamp that `align_type` would imply. */
+#define AADP_CLAMP_ON 2u   /* local (0-clamped) fill whatever align_type says */
+#define AADP_CLAMP_OFF 4u  /* non-local fill whatever align_type says */
 
 /* `what` bits of the batch calls */
 #define AADP_W_FWD 1u    /* forward fill (build_forw[_local]_dpm_nonlinear_gaps, dpmatrix.h:356,538) */

@@ -7,6 +7,7 @@
 
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 

@@ -252,8 +252,26 @@ class DPMatrix {
     float gi, ge;
     int at;
     describe(&alphabet, &sub, &gi, &ge, &at);
-    if (islocal != (at == (int)local))
-      throw std::string("DPMatrix: align_t of the constructor and of the evaluator's AliParams disagree");
+    if (islocal != (at == (int)local)) {
+      // The reference takes the 0-clamp from the constructor's align_t (dpmatrix.h:155, 310) and the free end gaps
+      // from the evaluator's AliParams (aasubalib.h:27-77); when the two disagree the similarity matrix goes to the
+      // exact general-gap fill with the clamp stated separately.
+      const size_t n = (size_t)sz1 * sz2;
+      std::vector<float> sim(n), score(n);
+      std::vector<int32_t> pq(n), pt(n);
+      for (int i = 0; i < sz1; ++i)
+        for (int j = 0; j < sz2; ++j) sim[(size_t)i * sz2 + j] = (*simmatrix)(i, j);
+      aadp::check(aadp_fill_pair_general(aadp::default_context(), sim.data(), sz1 - 2, sz2 - 2, gi, ge, at,
+                                         AADP_REPRO_REV_BUG | (islocal ? AADP_CLAMP_ON : AADP_CLAMP_OFF),
+                                         direction == fwd ? AADP_FWD : AADP_REV, 0, score.data(), pq.data(), pt.data()));
+      for (int i = 0; i < sz1; ++i)
+        for (int j = 0; j < sz2; ++j) {
+          const size_t o = (size_t)i * sz2 + j;
+          (*dpmatrix)(i, j).setTB(pq[o], pt[o], score[o]);
+        }
+      nearopt_delta = -1.f;
+      return;
+    }
     const std::vector<uint8_t> q = aadp::encode(*query_seq, alphabet), t = aadp::encode(*templ_seq, alphabet);
 
     aadp_ctx* ctx = aadp::default_context();
