@@ -277,14 +277,20 @@ class Context:
             raise AadpError(self.L.aadp_last_error().decode())
         return rc, pairs[: min(n.value, cap)].copy(), s.value
 
-    def optimal_all(self, direction, npairs):
+    def optimal_all(self, direction, npairs, bufs=None):
         """Optimal alignments of every pair of the resident batch (GPU traceback).
-        Returns (ali_off, pairs[(total,2)], n[npairs], status[npairs])."""
-        off = np.zeros(npairs + 1, np.int64)
+        Returns (ali_off, pairs[(total,2)], n[npairs], status[npairs]).  bufs = (off, pairs, n, status): caller-owned
+        (e.g. pinned) arrays reused across calls; pairs must hold ali_off[-1] rows."""
+        off = np.zeros(npairs + 1, np.int64) if bufs is None else bufs[0]
         self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), None, 0, None, None))
-        pairs = np.zeros((max(int(off[-1]), 1), 2), np.int32)
-        n = np.zeros(npairs, np.int32)
-        st = np.zeros(npairs, np.int32)
+        if bufs is None:
+            pairs = np.zeros((max(int(off[-1]), 1), 2), np.int32)
+            n = np.zeros(npairs, np.int32)
+            st = np.zeros(npairs, np.int32)
+        else:
+            _, pairs, n, st = bufs
+            if len(pairs) < int(off[-1]):
+                raise AadpError("optimal_all: pairs buffer too small (%d rows needed)" % int(off[-1]))
         self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), _ptr(pairs), int(off[-1]), _ptr(n), _ptr(st)))
         return off, pairs, n, st
 

@@ -33,19 +33,20 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: an alternative build of the same library for A/B measurements (loaded with AADP_LIB=...)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines]
     # the image's default host compiler links libstdc++ statically (dangling .so link);
     # use the system g++ so the library shares libstdc++ with the host process
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

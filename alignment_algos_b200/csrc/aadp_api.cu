@@ -166,6 +166,7 @@ struct aadp_ctx {
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2], gg_items, tb_del, tb_ins, tb_del_off, tb_ins_off;
   int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
+  int ucw_user_limit = 100000, cw_user_limit = 1000000;  // ucw.h:72, cw.h:76
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -267,7 +268,12 @@ template <int TBM, int FST, int MSK>
 int launch_packed_t(aadp_ctx* c, PackedParams& P) {
   auto kern = packed_kernel<TBM, FST, MSK, 0>;
   const int A = P.sc.A;
-  const size_t smem = packed_smem_bytes(A, MSK);
+  size_t smem = packed_smem_bytes(A, MSK);
+  // measurement aid: AADP_PACKED_SMEM_PAD="fwd,rev" extra bytes per CTA lower the resident warps per SM
+  if (const char* e = getenv("AADP_PACKED_SMEM_PAD")) {
+    int pf = 0, pr = 0;
+    if (sscanf(e, "%d,%d", &pf, &pr) >= 1) smem += (size_t)(P.rev ? pr : pf);
+  }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
@@ -903,10 +909,13 @@ int dense_pair(aadp_ctx* c, int64_t p, int dir, float* h_score, int32_t* h_pq, i
   const bool packed = b.fmt[p] == 1;
   D.lay = make_layout(Lq, Lt, b.fmt[p], dir);
   D.bias = packed ? kBias16 : 0;
-  D.st_mode = have_sc ? (packed ? 1 : b.st_mode) : 0;
-  D.sc_blob = have_sc ? c->scb[dir].p : nullptr;
-  if (h_score && packed && dir == 1 && !(b.ran_what & AADP_W_SCORES))
-    return fail("reverse score matrices were not kept (run with AADP_W_SCORES)");
+  // the packed reverse pass fuses the near-optimal mask and writes no score matrix of its own unless AADP_W_SCORES asks
+  // for it: there is nothing to read then (reading it anyway was an out-of-bounds access when only the traceback of such
+  // a pair was fetched)
+  const bool sc_here = have_sc && !(packed && dir == 1 && !(b.ran_what & AADP_W_SCORES));
+  if (h_score && !sc_here) return fail("reverse score matrices were not kept (run with AADP_W_SCORES)");
+  D.st_mode = sc_here ? (packed ? 1 : b.st_mode) : 0;
+  D.sc_blob = sc_here ? c->scb[dir].p : nullptr;
   D.sc_off = b.sc_off[p];
   D.tb = have_tb ? c->tb[dir].as<uint8_t>() + b.tb_off[p] : nullptr;
   D.fin_score = fin[0];
@@ -1053,6 +1062,10 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
   if (!strcmp(key, "general_threads")) { c->gg_threads_cap = std::max(32, std::min(512, value / 32 * 32)); return 0; }
   if (!strcmp(key, "general_prune")) { c->gg_prune = value ? 1 : 0; return 0; }
+  // alignment limits of the enumerators (ucw.h:72 hard-codes 100000, cw.h:76 1000000): beyond them the reference
+  // forces optimal paths instead of branching; <= 0 restores the reference's value
+  if (!strcmp(key, "ucw_user_limit")) { c->ucw_user_limit = value > 0 ? value : 100000; return 0; }
+  if (!strcmp(key, "cw_user_limit")) { c->cw_user_limit = value > 0 ? value : 1000000; return 0; }
   if (!strcmp(key, "general_budget_mcells")) { c->gg_budget_cells = (int64_t)std::max(value, 1) * 1000000; return 0; }
   return fail(std::string("unknown option ") + key);
 }
@@ -2341,6 +2354,7 @@ static int near_optimal_impl(aadp_ctx* c, int cno, const uint8_t* flags, const i
   U.n = (int)n;
   U.delta_ratio = delta_ratio;
   U.max_ali = max_alignments;
+  U.user_limit = cno ? c->cw_user_limit : c->ucw_user_limit;
   U.path_off = c->ucw_path_off.as<int64_t>();
   U.paths = c->ucw_paths.as<int2>();
   U.ali_len = c->ucw_len.as<int32_t>();

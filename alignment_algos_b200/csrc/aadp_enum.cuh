@@ -22,10 +22,11 @@
 //
 // Arithmetic is the reference's fp32 in the reference's order: r = curr + sim; (f + r) - g > thr; score = r - g;
 // leaf: score += D[q0][t0].score.  On the dyadic grid the integer kernels require, every value is exact, so the
-// alignments, their order and their scores are bit-identical.  The opt_path fallback (ucw.h:182-236) is only reachable
-// through rounding (a cell that passed always has a passing predecessor in exact arithmetic) or through the 100000
-// alignment user limit; here a pair that exceeds its output budget is flagged (status 1) instead, and a node without
-// a passing predecessor -- impossible on the dyadic grid -- is flagged with status 2.
+// alignments, their order and their scores are bit-identical.  The opt_path fallback (ucw.h:182-236) is reachable
+// through rounding (a cell that passed always has a passing predecessor in exact arithmetic) and through the
+// reference's alignment limit (ucw.h:72: 100000, cw.h:76: 1000000), reproduced here as `user_limit`: beyond it every
+// further branch() completes its alignment along the optimal predecessors (needs the traceback).  A pair that exceeds
+// its OUTPUT budget is flagged (status 1); a walk that needs predecessors the batch did not keep is flagged status 2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -62,6 +63,8 @@ struct UcwParams {
   int n;
   float delta_ratio;
   int max_ali;                // output budget per pair
+  int user_limit;             // ucw.h:72 / cw.h:76: once this many alignments are complete, every further branch() forces
+                              // the optimal path to the beginning (ucw.h:115-126, cw.h:118-130) instead of branching
   const uint8_t* subopt;      // CNO: SuboptFlags per template position (Lt+2 bytes per listed pair), null = all true
   const int64_t* subopt_off;  // per listed pair
   const int64_t* path_off;    // per listed pair: first slot; alignment a of pair k lives at path_off[k] + a*(Lq+2)
@@ -188,6 +191,13 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   for (;;) {
     if (q0 == 1 || t0 == 1) {
       if (!emit(q0, t0, __fadd_rn(curr, F(q0, t0)))) break;
+    } else if (count >= P.user_limit) {
+      // as.size() > user_limit at the entry of branch() (as.size() = completed alignments + the one in progress): the
+      // reference stops branching and completes this alignment along the optimal predecessors
+      int a = q0, b = t0;
+      float s = curr;
+      if (!walk(a, b, s, true)) break;
+      if (!emit(a, b, __fadd_rn(s, F(a, b)))) break;
     } else {
       const float r = __fadd_rn(curr, sim(q0, t0));  // ucw.h:141
       const int ndel = t0 - 2, total = 1 + ndel + (q0 - 2);

@@ -29,6 +29,7 @@
 #pragma once
 #include "aadp_kernels.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace aadp {
 
@@ -47,6 +48,19 @@ constexpr int kBias16 = 24000;
 constexpr int kNeg16 = -20000;    // "-infinity" seed of E/F chains (only ever extended once)
 constexpr int kFloor16 = -13000;  // clamp floor of M / slack
 constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must satisfy to use this kernel
+// Build-time toggles of the variant measurements (profiles/r02_packed_variants.md); the defaults are the shipped kernel.
+#ifndef AADP_GAT_IMAD
+#define AADP_GAT_IMAD 1   // traceback / mask bit gather: 1 = multiply-add on the FMA pipe, 0 = LOP3 on the ALU pipe
+#endif
+#ifndef AADP_PROF_AHEAD
+#define AADP_PROF_AHEAD 1  // profile words of the next row loaded during the current step (software pipelining)
+#endif
+#ifndef AADP_TWO_LOOPS
+#define AADP_TWO_LOOPS 1   // steps before the first final-row capture of a warp run in a loop without the capture branch
+#endif
+#ifndef AADP_SLACK_IMAD
+#define AADP_SLACK_IMAD 1  // near-optimal slack: 1 = one FMA-pipe add + double-biased compare, 0 = three-input ALU add
+#endif
 constexpr int kFwdAhead = 8;      // rows of L2 prefetch distance for the forward scores the reverse+mask pass reads
 constexpr int kPackedWarps = 1;   // warps per CTA (one: finest shared-memory granularity -> most warps per SM)
 // per-warp cp.async staging: query rings (1 KB: 2 halves x 2 blocks of 8 rows per lane) + forward-score chunks
@@ -196,14 +210,22 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // 0xFF << (8j+k) = 2^(8j+8+k) - 2^(8j+k), so the sum over the eight cells of a group telescopes to B - (B << 8),
 // B being the wanted word, and B = acc * (1 + 2^8 + 2^16 + 2^24) mod 2^32 -- one more IMAD per group (gat_fin).
 __device__ __forceinline__ uint32_t gat(uint32_t acc, uint32_t t, int k) {
+#if AADP_GAT_IMAD
   uint32_t d;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(t), "r"(0u - (1u << k)), "r"(acc));
   return d;
+#else
+  return acc | (t & (0x01010101u << k));
+#endif
 }
 __device__ __forceinline__ uint32_t gat_fin(uint32_t acc) {
+#if AADP_GAT_IMAD
   uint32_t d;
   asm("mul.lo.u32 %0, %1, 0x01010101;" : "=r"(d) : "r"(acc));
   return d;
+#else
+  return acc;
+#endif
 }
 
 // Per-lane, per-half final-row summary (what the final cell needs from this lane's 16 columns).
@@ -365,7 +387,8 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   int16_t* scp[2] = {nullptr, nullptr};
   const int16_t* fp[2] = {nullptr, nullptr};
   uint8_t* mkp[2] = {nullptr, nullptr};
-  uint32_t THR2 = 0;
+  uint32_t THR2 = 0, THR1 = 0;
+  const uint32_t NBIAS1 = pkdec(kBias16, kBias16);
   float thr_f[2] = {0.f, 0.f};
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -390,15 +413,22 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       ti[h] = (int)fminf(fmaxf(t, (float)kFloor16), (float)kPackedBound);
     }
     THR2 = pk2(ti[0] + 2 * kBias16, ti[1] + 2 * kBias16);  // compared with the doubly biased sum F + X
+    THR1 = pkb(ti[0], ti[1]);
   }
 
   // ---- query residues: each lane stages its own rows in a private 16-byte ring per half
   // (two 8-row blocks), refilled with cp.async one block (8 rows) ahead of use.
   constexpr bool SA = (TBM == 0);
   const SPtr stage_s = sptr<SA>(stage), profA_s = sptr<SA>(profA) + lane * 16, profB_s = XM ? profA_s : sptr<SA>(profB) + lane * 16;
+  // Per-lane staging: a 16-byte query ring per half and (MSK) a private triple buffer of forward-score chunks
+  // (3 x 32 bytes per half), requested two rows ahead.  These strides make the ring byte loads 8-way and the chunk
+  // loads / cp.async writes 4-way bank conflicted (ncu: L1/shared data pipe of the reverse+mask kernel at 72 %), but the
+  // conflict-free layouts ([buffer][quarter][lane] chunks, word-interleaved rings) were MEASURED SLOWER on every
+  // workload (profiles/r02_packed_variants.md #14: C3 -1.3 %, C2 -9 %, C4 -11 % against this layout): their extra address
+  // arithmetic per step costs more than the wavefronts they save.
   const SPtr qst[2] = {stage_s + lane * 32, stage_s + (lane * 32 + 16)};
-  // forward-score chunks (MSK): private triple buffer (3 x 32 bytes per half), requested two rows ahead
   const SPtr fst[2] = {stage_s + (1024 + lane * 192), stage_s + (1024 + lane * 192 + 96)};
+  constexpr int kFBuf = 32;  // bytes per chunk buffer of a lane and half
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     cpa8<SA>(qst[h], qp[h], 1);
@@ -414,13 +444,14 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       for (int r = 1; r <= 2; ++r) {
         const int ok = pid[h] >= 0 && Lq[h] >= r;
         const int16_t* src = fp[h] - (int64_t)(off + r - 1) * nl * 16;
-        cpa16<SA>(fst[h] + 32 * (r % 3), src, ok);
-        cpa16<SA>(fst[h] + (32 * (r % 3) + 16), src + nl * 8, ok);
+        cpa16<SA>(fst[h] + kFBuf * (r % 3), src, ok);
+        cpa16<SA>(fst[h] + (kFBuf * (r % 3) + 16), src + nl * 8, ok);
       }
     }
   }
   cp_async_commit();
   int qa_n0 = 0, qa_n1 = 0;  // query residues of the NEXT row (read one row ahead to shorten the LDS chain)
+  uint4 pnA = make_uint4(0, 0, 0, 0), pnB = make_uint4(0, 0, 0, 0);  // profile words of the next row
   // valid (non-pad) registers in the layout of accM: A bytes 0/1 (even/odd c), B bytes 2/3
   uint32_t VM = 0;
   if (MSK) {
@@ -432,9 +463,9 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         if (pid[h] >= 0 && j >= 1 && j <= Lt[h]) VM |= 1u << (8 * (2 * h + (c & 1)) + 7 - (c >> 1));
       }
   }
-  // triple-buffer offsets of the forward-score chunks: row i lives at 32*(i % 3), row i+2 at 32*((i+2) % 3) =
-  // 32*((i-1) % 3); rotated once per row instead of dividing by 3 (a lane's active rows are consecutive, from 1)
-  int fcur_off = 32, fnxt_off = 0;
+  // triple-buffer offsets of the forward-score chunks: row i lives in buffer i % 3, row i+2 in buffer (i+2) % 3 =
+  // (i-1) % 3; rotated once per row instead of dividing by 3 (a lane's active rows are consecutive, from 1)
+  int fcur_off = kFBuf, fnxt_off = 0;
   long long cnt[2] = {0, 0};
   RowSum fin[2] = {{kNeg32, 0, kNeg32, kNeg32}, {kNeg32, 0, kNeg32, kNeg32}};
 
@@ -454,7 +485,11 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   for (int h = 0; h < 2; ++h)
     if (pid[h] >= 0 && Lq[h] == 1) capture(h, (int)qp[h][0]);
 
-  for (int s = 0; s < nsteps; ++s) {
+  // One row step of the warp.  CAP = false compiles the step without the (rare) capture branch: the steps before the
+  // first capture of any lane of the warp -- about 85 % of a task -- run in a loop whose schedule the branch does not
+  // disturb (measured: the branch costs 2-4 % of a step although it is taken twice per lane and task).
+  auto step = [&](const int s, auto cap_tag) {
+    constexpr bool CAP = decltype(cap_tag)::value;
     uint32_t xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
     uint32_t e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
     uint32_t mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
@@ -475,6 +510,21 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         qa_n1 = ld1<SA>(qst[1]);
       } else if (MSK) cp_async_wait_group<1>();
       else cp_async_wait_group<4>();
+#if AADP_PROF_AHEAD
+      // The profile words of THIS row were loaded during the previous step (the first row loads them here): the
+      // step starts with register operands only.  The residue of the next row comes out of the ring now and its
+      // profile row follows as soon as the residue is there -- both loads have a whole step to complete.
+      if (i == 1) {
+        pnA = ld16<SA>(profA_s + qa_n0 * W);
+        pnB = ld16<SA>(profB_s + qa_n1 * W);
+      }
+      const uint32_t pwA[4] = {pnA.x, pnA.y, pnA.z, pnA.w};
+      const uint32_t pwB[4] = {pnB.x, pnB.y, pnB.z, pnB.w};
+      qa_n0 = ld1<SA>(qst[0] + (i & 15));
+      qa_n1 = ld1<SA>(qst[1] + (i & 15));
+      pnA = ld16<SA>(profA_s + qa_n0 * W);
+      pnB = ld16<SA>(profB_s + qa_n1 * W);
+#else
       const int qa0 = qa_n0, qa1 = qa_n1;
       const uint4 pa = ld16<SA>(profA_s + qa0 * W);
       const uint4 pb = ld16<SA>(profB_s + qa1 * W);
@@ -482,6 +532,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       qa_n1 = ld1<SA>(qst[1] + (i & 15));
       const uint32_t pwA[4] = {pa.x, pa.y, pa.z, pa.w};
       const uint32_t pwB[4] = {pb.x, pb.y, pb.z, pb.w};
+#endif
       uint32_t fcur[2][8];
       if (MSK) {
 #pragma unroll
@@ -539,8 +590,13 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
             // pipe) without a carry between the halves.  The sum carries the bias TWICE and is a negative fp16
             // pattern, like THR2: among negative patterns the larger integer is the smaller fp16 number, so the
             // sign of (slack - thr) as fp16 numbers is set exactly where slack > thr as integers.
+#if AADP_SLACK_IMAD
             const uint32_t slack = addc(fv, Xd);
             const uint32_t d5 = lt_sign(slack, THR2);
+#else
+            const uint32_t slack = fv + Xd + NBIAS1;  // one bias removed on the ALU pipe (IADD3), singly biased compare
+            const uint32_t d5 = lt_sign(THR1, slack);
+#endif
             // gather the sign bits of two cells at once: bytes [A(c-1), A(c), B(c-1), B(c)] = 0xFF / 0x00
             if (c & 1) accM = gat(accM, prmt(d5prev, d5, 0xFBD9u), 7 - (c >> 1));
             else d5prev = d5;
@@ -594,7 +650,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
       if (MSK) {
         accM = gat_fin(accM) & VM;
         fnxt_off = fcur_off;
-        fcur_off = fcur_off == 64 ? 0 : fcur_off + 32;
+        fcur_off = fcur_off == 2 * kFBuf ? 0 : fcur_off + kFBuf;
       }
       xl_hold = xn;
       x_pub = Xp[15];
@@ -627,12 +683,27 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           cnt[1] += __popc(accM >> 16);
         }
       }
-      if (i + 1 == Lq[0] || i + 1 == Lq[1]) {
+#ifndef AADP_EXP_NOCAP  // (timing experiment only: without the capture the final scores are wrong)
+      if (CAP && (i + 1 == Lq[0] || i + 1 == Lq[1])) {
         for (int h = 0; h < 2; ++h)
           if (i + 1 == Lq[h]) capture(h, h ? qa_n1 : qa_n0);
       }
+#endif
     }
-  }
+  };
+#if AADP_TWO_LOOPS
+  // first step in which any lane of the warp captures: row Lq-1 of lane `off` is step Lq-2+off (Lq = 1 captured above)
+  int s_cap = nsteps;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (pid[h] >= 0 && Lq[h] >= 2) s_cap = min(s_cap, Lq[h] - 2 + off);
+  s_cap = __reduce_min_sync(0xffffffffu, s_cap);
+  int s = 0;
+  for (; s < s_cap; ++s) step(s, std::false_type());
+  for (; s < nsteps; ++s) step(s, std::true_type());
+#else
+  for (int s = 0; s < nsteps; ++s) step(s, std::true_type());
+#endif
 
   // ---- final-row summaries from the parked state: M(Lq,j) = sim(Lq,j) + X(Lq-1,j-1)
   for (int h = 0; h < 2; ++h) {

@@ -150,6 +150,41 @@ def reference_timer(seqs, pq, pt, budget_s, nthreads, what=3):
             "seconds": sec, "pairs": n}
 
 
+def fair_cpu_timer(seqs, pq, pt, budget_s, what=3):
+    """The O(mn) three-state restatement of the same recurrence (oracle/aadp_oracle.c, `fast` fill: scores + traceback,
+    both directions) on ONE host thread and on ALL host cores, over a bounded sample of the workload: the CPU baseline
+    with the reference's O(n) algorithmic handicap removed."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    import alignment_algos_b200 as a
+    alpha, M = a.blosum62()
+    O = po.Oracle(M, GI, GE, po.SEMI_LOCAL)
+    ndir = 2 if (what & 2) else 1
+
+    def one(p):
+        O.fill(seqs[pq[p]], seqs[pt[p]], po.FWD, True, fast=True)
+        if what & 2:
+            O.fill(seqs[pq[p]], seqs[pt[p]], po.REV, True, fast=True)
+        return float(len(seqs[pq[p]])) * float(len(seqs[pt[p]]))
+
+    t0 = time.perf_counter()
+    one(0)
+    per = max(time.perf_counter() - t0, 1e-4)
+    n1 = int(max(8, min(len(pq), budget_s / per)))
+    t0 = time.perf_counter()
+    cells1 = sum(one(p) for p in range(n1))
+    s1 = time.perf_counter() - t0
+    ncores = os.cpu_count() or 1
+    nall = int(min(len(pq), n1 * ncores))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(ncores) as ex:  # the C fill releases the GIL (ctypes)
+        cellsN = sum(ex.map(one, range(nall), chunksize=max(1, nall // (ncores * 8))))
+    sN = time.perf_counter() - t0
+    return {"unit": "GCUPS", "kind": "port, O(mn) restatement (oracle fast fill: scores + traceback)",
+            "value_1_thread": cells1 * ndir / s1 / 1e9, "value": cellsN * ndir / sN / 1e9, "cores": ncores,
+            "sample": "first %d pairs on 1 thread in %.2f s; first %d pairs on %d threads in %.2f s" % (n1, s1, nall, ncores, sN)}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -179,13 +214,15 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks):
+def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, emit=True, steps=None, warmup=None):
     """C4: all-vs-all of N synthetic sequences (every unordered pair i<j, query=i, template=j), forward
     score only, through the cross-mode entry points.  The upper triangle is cut into rectangles
     (shard.triangle_rects) which are dealt over the ranks: STRONG scaling, no data-path collective."""
     import torch
     import alignment_algos_b200 as a
     from alignment_algos_b200 import shard, synth
+    if steps is not None:
+        args = argparse.Namespace(**dict(vars(args), steps=steps, warmup=warmup))
     alpha, M = a.blosum62()
     rng = np.random.default_rng(1004)
     seqs = synth.random_seqs(rng, args.seqs, 100, 500)
@@ -295,9 +332,91 @@ def run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_rank
                            "ceiling_gcups": lane_peak / i_alg / 1e9, "achieved_gcups": dom_gcups,
                            "frac": dom_gcups / (lane_peak / i_alg / 1e9), "sm_mhz": clk / 1e6},
     }
-    if rank == 0:
+    if rank == 0 and emit:
         print(json.dumps(line), flush=True)
     ctx.close()
+    return line
+
+
+def quick_pairlist(workload, args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, steps, warmup):
+    """Device-timed value of one of the pair-list workloads (inputs resident), for the `extra` keys of the default
+    line: c2 (10k pairs forward score-only) and c5 (one 30k x 30k pair fwd+rev+traceback+mask, one replica per rank)."""
+    import torch
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha, M = a.blosum62()
+    if workload == "c2":
+        seqs, pq, pt = synth.pair_workload(1002 + rank, 10_000, 100, 500)
+        what = a.W_FWD
+    else:
+        rng = np.random.default_rng(1005 + rank)
+        seqs = [rng.integers(0, 20, args.long_len).astype(np.uint8) for _ in range(2)]
+        pq, pt = np.array([0], np.int32), np.array([1], np.int32)
+        what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+    res, off = a.Context.pack(seqs)
+    ctx = a.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_scoring(M, GI, GE, a.SEMI_LOCAL)
+    n = len(pq)
+    d_f = torch.empty(n, dtype=torch.float32, device="cuda")
+    d_r = torch.empty(n, dtype=torch.float32, device="cuda")
+    d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+    d_c = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.upload_batch(res, off, pq, pt, what)
+    for _ in range(warmup):
+        ctx.run_batch(what, DELTA, d_f.data_ptr(), d_r.data_ptr(), d_t.data_ptr(), d_c.data_ptr())
+    torch.cuda.synchronize()
+    cu_step = ctx.last_cell_updates()
+    ctx.set_profiling(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.run_batch(what, DELTA, d_f.data_ptr(), d_r.data_ptr(), d_t.data_ptr(), d_c.data_ptr())
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    if what & a.W_REV:
+        assert torch.equal(d_f, d_r), "forward and reverse optima differ"
+    by = {}
+    for name, kms, cells in prof:
+        d = by.setdefault(name, [0.0, 0.0])
+        d[0] += kms
+        d[1] += cells
+    out = {"value": sum_over_ranks(cu_step) * steps / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms / steps,
+           "steps": steps, "scaling": "weak (one replica per rank)" if workload == "c5" else "weak",
+           "kernel_ms_per_step": {k: v[0] / steps for k, v in by.items()}}
+    dom = max(((k, v) for k, v in by.items() if v[1] > 0), key=lambda kv: kv[1][0], default=None)
+    if dom:
+        bpc = kernel_bytes_per_cu(dom[0], what)
+        hbm_peak, peak_src, _ = load_peaks()
+        gcups = dom[1][1] / (dom[1][0] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": dom[0], "achieved": gcups * bpc, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": gcups * bpc / hbm_peak, "bytes_per_cell_update": bpc, "kernel_gcups": gcups}
+    ctx.close()
+    return out
+
+
+def kernel_bytes_per_cu(kernel, what):
+    """Algorithmic HBM bytes per cell update of a fill kernel:
+    packed forward + traceback + score spill: 0.5 B traceback + 2 B int16 score written            = 2.5
+    packed reverse + traceback + fused mask:  0.5 B traceback + 2 B int16 score read + 1/8 B mask  = 2.625
+    long-pair wavefront (int32 scores):       0.5 B traceback + 4 B score written                  = 4.5
+    score-only kernels: residues in, one score out per pair."""
+    if "wave" in kernel:
+        return 4.5
+    if "MSK=1" in kernel:
+        return 2.625
+    if "TB=1" in kernel and "FST=1" in kernel:
+        return 2.5
+    if "TB=1" in kernel:
+        return 0.5
+    if "FST=1" in kernel or "ST=" in kernel:
+        return 2.0
+    return (2 * 300.0 + 4.0) / 300.0 ** 2
 
 
 def main():
@@ -315,6 +434,8 @@ def main():
                          "score-only; c4: all-vs-all of --seqs sequences, forward score-only, strong scaling over ranks; "
                          "c5: one 30k x 30k pair fwd+rev+traceback+mask (multi-CTA wavefront)")
     ap.add_argument("--long-len", type=int, default=30000)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default (c3) run only: skip the `extra` keys (C2, C4 strong scaling, C5, alignments end to end)")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
@@ -455,6 +576,39 @@ def main():
     e2e_serial_ms = e2e_ms
     e2e_mode = "one context, one aadp_fill_batch call after the other"
 
+    # ---- leg 2a: the same call followed by the product a caller of this path actually reads (optimal.h:47-75): the
+    # optimal alignment of EVERY pair, traced on the GPU over the packed traceback (aadp_batch_optimal_all) and copied to
+    # pinned host memory -- inputs H2D, alignments D2H, all inside the timed region
+    e2e_ali = None
+    if (what & a.W_TB) and (what & a.W_FWD):
+        off_b = np.zeros(n + 1, np.int64)
+        cap_rows = int(sum(len(seqs[pq[p]]) + len(seqs[pt[p]]) + 2 for p in range(n)))
+        pairs_t = torch.empty((cap_rows, 2), dtype=torch.int32).pin_memory()
+        n_t = torch.empty(n, dtype=torch.int32).pin_memory()
+        st_t = torch.empty(n, dtype=torch.int32).pin_memory()
+        bufs = (off_b, pairs_t.numpy(), n_t.numpy(), st_t.numpy())
+        asteps = max(2, min(args.steps, 5))
+
+        def step_ali():
+            ctx.fill_batch(hb["res"], hb["off"], hb["pq"], hb["pt"], what, DELTA)
+            return ctx.optimal_all(a.FWD, n, bufs=bufs)
+
+        step_ali()
+        barrier()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record(stream)
+        for _ in range(asteps):
+            ao, ap_, an, ast_ = step_ali()
+        z1.record(stream)
+        barrier()
+        ali_ms = max_over_ranks(z0.elapsed_time(z1))
+        assert int(ast_.max()) == 0 and int(an.min()) >= 2
+        e2e_ali = {"value": total_cu * asteps / (ali_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ali_ms / asteps,
+                   "steps": asteps, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": int(d2h + ctx.last_transfer_bytes()[1]),  # scalars + the alignment slots copied back
+                   "aligned_pairs_per_step": int(an.astype(np.int64).sum()),
+                   "what": "aadp_fill_batch + aadp_batch_optimal_all(forward): every optimal alignment back in pinned host memory"}
+
     # ---- leg 2b: the same calls from THREE host threads over three contexts (independent contexts are thread-safe,
     # include/aadp.h), each on its own non-blocking stream: while the GPU fills the batch of one call, the other threads
     # schedule and upload theirs.  Every step still copies its own inputs H2D and its own results D2H inside the timed
@@ -519,28 +673,28 @@ def main():
     dom_ms = dom[1][0] / dom[1][2]
     dom_cells = dom[1][1] / dom[1][2]
     hbm_peak, peak_src, sm_max = load_peaks()
-    # algorithmic bytes per cell update of the dominant fill kernel:
-    # 0.5 B packed traceback + 2 B int16 score spill (feeds the near-optimal mask)
-    bytes_per_cu = 2.5
+    # algorithmic bytes per cell update of the dominant fill kernel: per kernel, not one constant
+    bytes_per_cu = kernel_bytes_per_cu(dom[0], what)
     achieved_gbs = dom_cells * bytes_per_cu / (dom_ms * 1e-3) / 1e9
     props = torch.cuda.get_device_properties(local_rank)
     clk = (clocks["sm_mhz"] or sm_max) * 1e6
     i_alg = 15.0 if (what & a.W_TB) else 7.0  # SURVEY.md §8d instruction model: with traceback / score-only
-    if not (what & (a.W_TB | a.W_MASK | a.W_SCORES)):
-        bytes_per_cu = (2 * 300.0 + 4.0) / 300.0 ** 2  # score-only: residues in, one score out per pair
-        achieved_gbs = dom_cells * bytes_per_cu / (dom_ms * 1e-3) / 1e9
     lane_peak = props.multi_processor_count * 128 * clk
     dom_gcups = dom_cells / (dom_ms * 1e-3) / 1e9
     kernel_share = {k: v[0] / sum(x[0] for x in by.values()) for k, v in by.items()} if by else {}
 
-    # measured DRAM traffic of that kernel (one ncu --set full capture, profiles/), scaled to this launch
-    traffic = None
+    # measured DRAM traffic and executed instructions of that kernel: one `ncu --set full` capture of THIS build
+    # (profiles/r02_kernel_counts.json, written by profiles/tools/ncu_counts.py from the .ncu-rep), scaled to this launch
+    traffic, i_cell_sass, counts_src = None, None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_counts.json")))
         if dom[0] in tj["kernels"]:
-            traffic = tj["kernels"][dom[0]]["bytes_per_cell_update"] * dom_cells
+            kc = tj["kernels"][dom[0]]
+            traffic = kc["dram_bytes_per_cell_update"] * dom_cells
+            i_cell_sass = kc["lane_ops_per_cell_update"]
+            counts_src = tj.get("source")
     except Exception:
-        traffic = None
+        pass
     line = {
         "metric": METRIC if args.workload != "c2" else "GCUPS forward score-only DP fill", "value": value, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -559,20 +713,37 @@ def main():
         "gpu_launches": int(launches_step * args.steps),
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per cell update) x cell updates of this launch",
-                     "bytes_per_cell_update": bytes_per_cu, "ms_per_launch": dom_ms},
+                     "traffic_source": ("%s: ncu dram bytes per cell update x cell updates of this launch" % counts_src) if counts_src else None,
+                     "bytes_per_cell_update": bytes_per_cu, "ms_per_launch": dom_ms,
+                     "i_cell_sass": i_cell_sass},
         "issue_roofline": {"kernel": dom[0], "i_alg": i_alg, "lane_ops_per_s": lane_peak, "ceiling_gcups": lane_peak / i_alg / 1e9,
                            "achieved_gcups": dom_gcups, "frac": dom_gcups / (lane_peak / i_alg / 1e9), "sm_mhz": clk / 1e6},
         "kernel_share": kernel_share,
     }
+    if e2e_ali:
+        line["e2e_alignments"] = e2e_ali
+    ctx.close()
+    # ---- extra keys of the default (C3) line: the other headline configs, so that the driver's N = 1, 2, 4, 8 runs record
+    # them too.  C2 and C5 run one replica per rank (weak); C4 is the all-vs-all job dealt over the ranks (STRONG scaling).
+    if args.workload == "c3" and not args.no_extras:
+        extra = {}
+        try:
+            extra["c2"] = quick_pairlist("c2", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, 20, 5)
+            extra["c5"] = quick_pairlist("c5", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, 3, 2)
+            c4 = run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, emit=False, steps=1, warmup=1)
+            extra["c4"] = {k: c4[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "pairs_per_s", "e2e", "issue_roofline")}
+            extra["c4"]["workload"] = c4["config"]["workload"]
+        except Exception as e:  # an extra must never take the headline line down
+            extra["error"] = repr(e)
+        line["extra"] = extra
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.workload == "c5":  # the reference cannot run 30k x 30k (21.6 GB of DPCell, O(n^3)): C3-shaped sample
             seqs, pq, pt = make_workload(0, 2048)
         cb = reference_timer(seqs, pq, pt, 15.0, os.cpu_count() or 1, 3 if (what & a.W_REV) else 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline_fair"] = fair_cpu_timer(seqs, pq, pt, 4.0, 3 if (what & a.W_REV) else 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

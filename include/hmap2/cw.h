@@ -36,13 +36,11 @@ class ConstrainedNearOptimal : public Enumerator<S1, S2, Etype> {
     std::vector<SingleAlignment> found;
     int budget = 4 * params->number_suboptimal;
     if (budget < 1024) budget = 1024;
-    for (;;) {  // grow the output budget up to the reference's own limit (beyond it cw.h:124-137 truncates: refused)
-      if (budget > (int)user_limit + 1) budget = (int)user_limit + 1;
+    for (;;) {  // grow the output budget until the pair fits; beyond user_limit the GPU walk truncates like cw.h:118-130
       bool overflow = false;
-      dpm.nearOptimalAlignments(params->delta_ratio, budget, &found, &overflow, &flags);
+      dpm.nearOptimalAlignments(params->delta_ratio, budget, &found, &overflow, &flags, user_limit);
       if (!overflow) break;
-      if (budget >= (int)user_limit + 1)
-        throw std::string("ConstrainedNearOptimal: more alignments than user_limit; lower delta_ratio or constrain further");
+      if (budget > 1 << 24) throw std::string("ConstrainedNearOptimal: alignment set does not fit the output budget");
       budget *= 8;
     }
     for (size_t k = 0; k < found.size(); ++k) {

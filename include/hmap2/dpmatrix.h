@@ -115,8 +115,10 @@ class DPMatrix {
   // is the enumerator class on top of it.  budget = maximum number of alignments; *overflow tells when there are more.
   // subopt_flags != 0: the constrained enumeration of cw.h with one flag per template position (sentinels included).
   template <class Alignment>
+  // user_limit: the enumerator's alignment limit (ucw.h:72, cw.h:76); beyond it the GPU walk forces optimal paths
+  // exactly as the reference does (ucw.h:115-126, cw.h:118-130).  0 keeps the reference's own value.
   void nearOptimalAlignments(float delta_ratio, int budget, std::vector<Alignment>* out, bool* overflow,
-                             const std::vector<unsigned char>* subopt_flags = 0) {
+                             const std::vector<unsigned char>* subopt_flags = 0, unsigned int user_limit = 0) {
     std::string alphabet;
     std::vector<float> sub;
     float gi, ge;
@@ -130,6 +132,7 @@ class DPMatrix {
     const int32_t pq = 0, pt = 1;
     aadp_ctx* ctx = aadp::default_context();
     aadp::check(aadp_set_scoring(ctx, sub.data(), (int)alphabet.size(), gi, ge, at, AADP_REPRO_REV_BUG));
+    aadp::check(aadp_set_option(ctx, subopt_flags ? "cw_user_limit" : "ucw_user_limit", (int)user_limit));
     float fs = 0.f;
     aadp::check(aadp_fill_batch(ctx, residues.data(), seq_off, 2, &pq, &pt, 1, AADP_W_FWD | AADP_W_SCORES | AADP_W_TB, delta_ratio,
                                 &fs, 0, 0, 0));

@@ -30,19 +30,19 @@ class UnconstrainedNearOptimal : public Enumerator<S1, S2, Etype> {
 
   void enumerate(DPMatrix<S1, S2, Etype>& dpm, AlignmentSet<S1, S2, Etype>& as) {
     if (dpm.getDirection() != fwd) throw std::string("UnconstrainedNearOptimal: needs a forward DPMatrix");
-    // output budget: grown until the pair fits or the reference's own limit is reached.  Beyond user_limit the
-    // reference forces the optimal path for every further branch (opt_path, ucw.h:115-126); that truncation is not
-    // reproduced -- refuse loudly instead of returning a different set.
+    // Beyond user_limit the reference forces the optimal path for every further branch (opt_path, ucw.h:115-126);
+    // the GPU walk reproduces that truncation, so the set is the reference's in every case.  The output budget is
+    // grown until the pair fits: past the limit only the pending branches of the current stack complete, so the final
+    // count stays within a small multiple of user_limit.
     std::vector<SingleAlignment> found;
-    int budget = 4 * params->number_suboptimal;
+    long long budget = 4LL * params->number_suboptimal;
     if (budget < 1024) budget = 1024;
     for (;;) {
-      if (budget > (int)user_limit + 1) budget = (int)user_limit + 1;
       bool overflow = false;
-      dpm.nearOptimalAlignments(params->delta_ratio, budget, &found, &overflow);
+      dpm.nearOptimalAlignments(params->delta_ratio, (int)budget, &found, &overflow, 0, user_limit);
       if (!overflow) break;
-      if (budget >= (int)user_limit + 1)
-        throw std::string("UnconstrainedNearOptimal: more alignments than user_limit; lower delta_ratio");
+      if (budget > 8LL * user_limit + 65536)
+        throw std::string("UnconstrainedNearOptimal: alignment set does not fit the output budget");
       budget *= 8;
     }
     for (size_t k = 0; k < found.size(); ++k) as.push_back(found[k]);  // slot order of ucw.h:77-85

@@ -575,6 +575,8 @@ typedef struct {
   int sz1, sz2;
   float thr;
   long count, limit, status;
+  long user_limit; /* ucw.h:72 / cw.h:76: once this many alignments are complete, every further branch() call forces the
+                    * optimal path instead of branching (as.size() = completed + 1 at the entry of a branch() call) */
   int* stack; /* 2 ints per frame */
   int depth;
   float* scores;
@@ -626,6 +628,11 @@ static void ucwe_branch(ucwe_t* u, int q0, int t0, float curr) {
     ++u->count;
     return;
   }
+  if (u->count >= u->user_limit) { /* ucw.h:115-126: as.size() > user_limit */
+    if (u->pq) ucwe_opt_path(u, q0, t0, curr);
+    else u->status = 2;
+    return;
+  }
   float r = curr + u->sim[(size_t)q0 * sz2 + t0];
   float f = u->F[(size_t)(q0 - 1) * sz2 + (t0 - 1)];
   int any = 0;
@@ -653,7 +660,15 @@ static void ucwe_branch(ucwe_t* u, int q0, int t0, float curr) {
 long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
                        long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
                        const int* prev_q, const int* prev_t) {
+  return orc_ucw_enumerate_lim(Lq, Lt, sc, F, sim, thr, max_alignments, scores, ali_len, pairs, status, prev_q, prev_t,
+                               100000 /* ucw.h:72 */);
+}
+
+long orc_ucw_enumerate_lim(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                           long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                           const int* prev_q, const int* prev_t, long user_limit) {
   ucwe_t u;
+  u.user_limit = user_limit;
   u.pq = prev_q; u.pt = prev_t;
   u.sc = sc; u.F = F; u.sim = sim; u.sz1 = Lq + 2; u.sz2 = Lt + 2; u.thr = thr;
   u.count = 0; u.limit = max_alignments; u.status = 0; u.depth = 0;
@@ -717,6 +732,7 @@ static void cno_branch(cnoe_t* c, int q0, int t0, float curr, int force_opt) { /
   if (u->status) return;
   if (q0 == 1 || t0 == 1) { cno_leaf(u, q0, t0, curr); return; }
   if (force_opt) { cno_opt_path(c, q0, t0, curr, 1); return; }
+  if (u->count >= u->user_limit) { cno_opt_path(c, q0, t0, curr, 1); return; } /* cw.h:118-130 */
   int sz2 = u->sz2, any = 0;
   float r = curr + u->sim[(size_t)q0 * sz2 + t0];
   float f = u->F[(size_t)(q0 - 1) * sz2 + (t0 - 1)];
@@ -739,8 +755,16 @@ static void cno_branch(cnoe_t* c, int q0, int t0, float curr, int force_opt) { /
 long orc_cno_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
                        long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
                        const int* prev_q, const int* prev_t, const uint8_t* subopt_flags) {
+  return orc_cno_enumerate_lim(Lq, Lt, sc, F, sim, thr, max_alignments, scores, ali_len, pairs, status, prev_q, prev_t,
+                               subopt_flags, 1000000 /* cw.h:76 */);
+}
+
+long orc_cno_enumerate_lim(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                           long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                           const int* prev_q, const int* prev_t, const uint8_t* subopt_flags, long user_limit) {
   cnoe_t c;
   ucwe_t* u = &c.u;
+  u->user_limit = user_limit;
   u->pq = prev_q; u->pt = prev_t;
   u->sc = sc; u->F = F; u->sim = sim; u->sz1 = Lq + 2; u->sz2 = Lt + 2; u->thr = thr;
   u->count = 0; u->limit = max_alignments; u->status = 0; u->depth = 0;

@@ -101,6 +101,16 @@ long orc_ucw_enumerate(int Lq, int Lt, const orc_scoring* sc, const float* F, co
                        long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
                        const int* prev_q, const int* prev_t);
 
+/* The same with the reference's alignment limit as a parameter (ucw.h:72 hard-codes 100000, cw.h:76 1000000): once
+ * `user_limit` alignments are complete every further branch() forces the optimal path (ucw.h:115-126, cw.h:118-130);
+ * prev_q/prev_t are then required.                                                                            */
+long orc_ucw_enumerate_lim(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                           long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                           const int* prev_q, const int* prev_t, long user_limit);
+long orc_cno_enumerate_lim(int Lq, int Lt, const orc_scoring* sc, const float* F, const float* sim, float thr,
+                           long max_alignments, float* scores, int* ali_len, int* pairs, int* status,
+                           const int* prev_q, const int* prev_t, const uint8_t* subopt_flags, long user_limit);
+
 /* ConstrainedNearOptimal::enumerate (cw.h:60-284) up to its final sortSet: branching restricted by SuboptFlags
  * (one byte per template position incl. sentinels, NULL = all true; rule #1 of cw.h:247-256).  Same output layout
  * as orc_ucw_enumerate; prev_q/prev_t are required (the optimal walks between the branch points).           */

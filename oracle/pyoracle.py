@@ -98,23 +98,25 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return score, pq, pt
 
-    def ucw_enumerate(self, q, t, F, sim, thr, max_alignments=20000, pq=None, pt=None):
-        """orc_ucw_enumerate: (status, [(score, pairs[(len,2)])]) in the reference's depth-first slot order."""
+    def ucw_enumerate(self, q, t, F, sim, thr, max_alignments=20000, pq=None, pt=None, user_limit=100000):
+        """orc_ucw_enumerate: (status, [(score, pairs[(len,2)])]) in the reference's depth-first slot order.
+        user_limit: ucw.h:72 (beyond it the reference forces optimal paths, ucw.h:115-126; needs pq/pt)."""
         Lq, Lt = len(q), len(t)
         K = int(max_alignments)
         scores = np.zeros(K, np.float32)
         ln = np.zeros(K, np.int32)
         pairs = np.zeros((K, Lq + 2, 2), np.int32)
         st = C.c_int(0)
-        self.lib.orc_ucw_enumerate.restype = C.c_long
-        n = self.lib.orc_ucw_enumerate(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
-                                       _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
-                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
-                                       _p(np.ascontiguousarray(pq, np.int32), C.c_int) if pq is not None else None,
-                                       _p(np.ascontiguousarray(pt, np.int32), C.c_int) if pt is not None else None)
+        self.lib.orc_ucw_enumerate_lim.restype = C.c_long
+        n = self.lib.orc_ucw_enumerate_lim(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
+                                           _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
+                                           _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
+                                           _p(np.ascontiguousarray(pq, np.int32), C.c_int) if pq is not None else None,
+                                           _p(np.ascontiguousarray(pt, np.int32), C.c_int) if pt is not None else None,
+                                           C.c_long(int(user_limit)))
         return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
 
-    def cno_enumerate(self, q, t, F, sim, thr, pq, pt, flags=None, max_alignments=20000):
+    def cno_enumerate(self, q, t, F, sim, thr, pq, pt, flags=None, max_alignments=20000, user_limit=1000000):
         """orc_cno_enumerate (cw.h): (status, [(score, pairs)]) in the reference's slot order."""
         Lq, Lt = len(q), len(t)
         K = int(max_alignments)
@@ -123,13 +125,13 @@ class Oracle:
         pairs = np.zeros((K, Lq + 2, 2), np.int32)
         st = C.c_int(0)
         fl = np.ascontiguousarray(flags, np.uint8) if flags is not None else None
-        self.lib.orc_cno_enumerate.restype = C.c_long
-        n = self.lib.orc_cno_enumerate(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
-                                       _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
-                                       _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
-                                       _p(np.ascontiguousarray(pq, np.int32), C.c_int),
-                                       _p(np.ascontiguousarray(pt, np.int32), C.c_int),
-                                       _p(fl, C.c_uint8) if fl is not None else None)
+        self.lib.orc_cno_enumerate_lim.restype = C.c_long
+        n = self.lib.orc_cno_enumerate_lim(Lq, Lt, C.byref(self.sc), _p(np.ascontiguousarray(F, np.float32), C.c_float),
+                                           _p(np.ascontiguousarray(sim, np.float32), C.c_float), C.c_float(thr), C.c_long(K),
+                                           _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int), C.byref(st),
+                                           _p(np.ascontiguousarray(pq, np.int32), C.c_int),
+                                           _p(np.ascontiguousarray(pt, np.int32), C.c_int),
+                                           _p(fl, C.c_uint8) if fl is not None else None, C.c_long(int(user_limit)))
         return st.value, [(float(scores[a]), pairs[a, :ln[a]].copy()) for a in range(n)]
 
     @staticmethod

@@ -1072,3 +1072,46 @@ def test_pipelined_fill_batch_equals_plain_path(blosum):
     out = c.fill_batch(res, off, pq, pt, a.W_FWD)   # the context is still usable
     assert_matrix_equal("after error", out["fwd_score"], outs[0][0]["fwd_score"])
     c.close()
+
+
+def test_enumeration_user_limit_truncation_on_gpu(blosum):
+    # ucw.h:72,115-126 / cw.h:76,118-130: once `user_limit` alignments are complete the reference stops branching and
+    # completes every pending branch along the optimal predecessors.  The oracle's truncation is pinned to the live
+    # reference at its hard-coded limit (tests/test_oracle.py); the GPU walk must give the oracle's set -- same slot
+    # order, same fp32 scores -- for small limits, for the constrained variant, and at the reference's own 100000.
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(21)
+    L = 26
+    q = rng.integers(0, 20, L).astype(np.uint8)
+    t = q.copy()
+    t[::3] = rng.integers(0, 20, len(t[::3]))
+    res, off = a.Context.pack([q, t])
+    c = a.Context(0)
+    c.set_scoring(M, 3, 1, po.SEMI_LOCAL)
+    O = po.Oracle(M, 3, 1, po.SEMI_LOCAL)
+    F, fq, ft = O.fill(q, t, po.FWD, True, fast=False)
+    sim = O.sim(q, t)
+    c.fill_batch(res, off, np.array([0], np.int32), np.array([1], np.int32), a.W_FWD | a.W_SCORES | a.W_TB, 0.5)
+    flags = (np.arange(L + 2) // 4) % 2
+    for delta, limit, K, constrained in [(0.3, 50, 4000, False), (0.3, 1, 4000, False), (0.35, 700, 20000, False),
+                                         (0.4, 300, 20000, True), (0.5, 100000, 120000, False)]:
+        thr = O.threshold(float(F[-1, -1]), delta)
+        c.set_option("cw_user_limit" if constrained else "ucw_user_limit", limit)
+        if constrained:
+            st, want = O.cno_enumerate(q, t, F, sim, thr, fq, ft, flags, K, user_limit=limit)
+            gst, gthr, alis = c.near_optimal([0], delta, K, subopt_flags=[flags], constrained=True)[0]
+        else:
+            st, want = O.ucw_enumerate(q, t, F, sim, thr, K, fq, ft, user_limit=limit)
+            gst, gthr, alis = c.near_optimal([0], delta, K)[0]
+        assert st == 0 and gst == 0 and gthr == thr
+        assert len(want) > limit, "the case must cross the limit"
+        assert len(alis) == len(want), (delta, limit, len(alis), len(want))
+        for (gs, gp), (ws, wp) in zip(alis, want):
+            assert gs == ws and np.array_equal(gp, wp)
+        # and the limit matters: without it the set is larger
+        if limit < 1000:
+            c.set_option("cw_user_limit" if constrained else "ucw_user_limit", 0)
+            full = c.near_optimal([0], delta, K, **({"subopt_flags": [flags], "constrained": True} if constrained else {}))[0]
+            assert len(full[2]) > len(alis) or full[0] == 1
+    c.close()

@@ -271,3 +271,25 @@ def test_oracle_constrained_enumeration_matches_reference(blosum):
                     assert _canon(alis) == _canon(ref), (at, gi, Lq, Lt)
                     total += len(alis)
     assert total > 1000
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference library not built")
+def test_oracle_user_limit_truncation_matches_reference(blosum):
+    # ucw.h:72 hard-codes user_limit = 100000; beyond it every further branch() forces the optimal path (ucw.h:115-126).
+    # A 26 x 26 related pair at delta 0.5 has 251972 near-optimal alignments; the reference returns 100075.
+    alpha, M = blosum
+    rng = np.random.default_rng(21)
+    L = 26
+    q = rng.integers(0, 20, L).astype(np.uint8)
+    t = q.copy()
+    t[::3] = rng.integers(0, 20, len(t[::3]))
+    O = po.Oracle(M, 3, 1, po.SEMI_LOCAL)
+    R = po.Reference(alpha, M, 3, 1, po.SEMI_LOCAL)
+    F, pq, pt = O.fill(q, t, po.FWD, True, fast=False)
+    thr = O.threshold(float(F[-1, -1]), 0.5)
+    st, alis = O.ucw_enumerate(q, t, F, O.sim(q, t), thr, 300000, pq, pt)
+    ref = R.ucw_alignments(q, t, 0.5, 300000)
+    assert st == 0 and len(alis) == len(ref) > 100000
+    assert _canon(alis) == _canon(ref)
+    st, full = O.ucw_enumerate(q, t, F, O.sim(q, t), thr, 300000, pq, pt, user_limit=10 ** 9)
+    assert len(full) > 2 * len(alis)
