@@ -62,12 +62,14 @@ def lib():
     L.aadp_batch_fetch_tb.argtypes = [vp, i64, C.c_int, vp, i64, vp]
     L.aadp_decode_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, u32, vp, C.c_int, C.c_int, vp, vp]
     L.aadp_batch_optimal_all.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp]
+    L.aadp_batch_optimal_all_compact.argtypes = [vp, C.c_int, vp, vp, i64, vp, vp]
     L.aadp_fill_subpair.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.aadp_fill_subpair_batch.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, C.c_int, vp, vp, vp, i64, vp, vp]
     L.aadp_fill_pair_general.argtypes = [vp, vp, C.c_int, C.c_int, f32, f32, C.c_int, u32, C.c_int, vp, vp, vp, vp]
     L.aadp_fill_pair_tabulated.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, u32, C.c_int, vp, vp, vp]
     L.aadp_batch_near_optimal.argtypes = [vp, vp, i64, f32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     L.aadp_batch_near_optimal_constrained.argtypes = [vp, vp, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.aadp_batch_near_optimal_pruned.argtypes = [vp, i64, C.c_int, vp, f32, u32, u32, f32, u32, i32, vp, vp, vp, vp, vp, i64, vp]
     L.aadp_fill_batch_tabulated.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u32, C.c_int, vp, vp, vp, vp, i64, vp, vp]
     L.aadp_upload_sequences.argtypes = [vp, vp, vp, i64]
     L.aadp_cross_run.argtypes = [vp, vp, i64, vp, i64, vp]
@@ -87,4 +89,5 @@ EXPORTS = [
     "aadp_batch_fetch_tb", "aadp_decode_cell", "aadp_upload_sequences", "aadp_cross_run", "aadp_cross_scores",
     "aadp_last_cross_cell_updates", "aadp_batch_optimal_all", "aadp_fill_subpair", "aadp_fill_pair_general",
     "aadp_fill_subpair_batch", "aadp_fill_pair_tabulated", "aadp_fill_batch_tabulated", "aadp_batch_near_optimal", "aadp_batch_near_optimal_constrained",
+    "aadp_batch_near_optimal_pruned", "aadp_batch_optimal_all_compact",
 ]

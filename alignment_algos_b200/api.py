@@ -294,6 +294,19 @@ class Context:
         self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(off), _ptr(pairs), int(off[-1]), _ptr(n), _ptr(st)))
         return off, pairs, n, st
 
+    def optimal_all_compact(self, direction, npairs, pairs=None, pairs_cap=None):
+        """Optimal alignments of every pair, packed: (ali_off[npairs+1], pairs[(cap,2)], n[npairs], status[npairs]).
+        pairs: caller-owned (e.g. pinned) (cap,2) int32 array; by default sized by the capacity bound."""
+        off = np.zeros(npairs + 1, np.int64)
+        if pairs is None:
+            capo = np.zeros(npairs + 1, np.int64)
+            self._ck(self.L.aadp_batch_optimal_all(self.h, direction, _ptr(capo), None, 0, None, None))
+            pairs = np.zeros((max(int(capo[-1]), 1), 2), np.int32)
+        n = np.zeros(npairs, np.int32)
+        st = np.zeros(npairs, np.int32)
+        self._ck(self.L.aadp_batch_optimal_all_compact(self.h, direction, _ptr(off), _ptr(pairs), len(pairs), _ptr(n), _ptr(st)))
+        return off, pairs, n, st
+
     def near_optimal(self, pair_ids, delta_ratio, max_alignments, subopt_flags=None, constrained=False):
         """UnconstrainedNearOptimal::enumerate (ucw.h:63-191, before sortSet) of the listed pairs on the GPU -- or, with
         constrained=True, ConstrainedNearOptimal::enumerate (cw.h:60-284) with subopt_flags = one array of Lt+2 flags per
@@ -327,6 +340,27 @@ class Context:
                     for a in range(n_ali[k])]
             out.append((int(st[k]), float(thr[k]), alis))
         return out
+
+    def near_optimal_pruned(self, p, variant, delta_ratio, Lq, Lt, flags=None, k_limit=16, sort_limit=100, max_overlap=0.30,
+                            user_limit=100000, max_alignments=20000):
+        """KSConstrainedNearOptimal (variant=PRUNE_KSORTED, kscw.h) / CRConstrainedNearOptimal (PRUNE_REDUNDANCY, crcw.h) of
+        pair p of the resident batch: (status, threshold, [(score, pairs[(len,2)])]) in the reference's slot order."""
+        K = int(max_alignments)
+        cap = K * (Lq + Lt + 4)
+        scores = np.zeros(K, np.float32)
+        ln = np.zeros(K, np.int32)
+        paths = np.zeros((cap, 2), np.int32)
+        n, st, thr = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        fl = np.ascontiguousarray(flags, np.uint8) if flags is not None else None
+        self._ck(self.L.aadp_batch_near_optimal_pruned(
+            self.h, int(p), int(variant), _ptr(fl) if fl is not None else None, delta_ratio, k_limit, sort_limit, max_overlap,
+            user_limit, K, C.cast(C.byref(n), C.c_void_p), C.cast(C.byref(st), C.c_void_p), _ptr(scores), _ptr(ln), _ptr(paths),
+            cap, C.cast(C.byref(thr), C.c_void_p)))
+        out, o = [], 0
+        for k in range(min(n.value, K)):
+            out.append((float(scores[k]), paths[o:o + ln[k]].copy()))
+            o += ln[k]
+        return st.value, thr.value, out
 
     def fetch_tb(self, p, direction, Lq, Lt):
         nbytes = max(int(self.L.aadp_batch_tb_bytes(self.h, p)), 1)

@@ -6,6 +6,7 @@
 #include "aadp_packed.cuh"
 #include "aadp_general.cuh"
 #include "aadp_enum.cuh"
+#include "aadp_pruned.h"
 
 #include <algorithm>
 #include <chrono>
@@ -140,6 +141,7 @@ struct aadp_ctx {
   int align_type = AADP_GLOBAL;
   uint32_t flags = 0;
   std::vector<int8_t> sub8_h;
+  std::vector<float> subf_h;  // the substitution table as given (host copy: similarity matrix of the pruned enumerators)
   int max_abs_sub = 0;
   DevBuf sub8p;
   DevBuf sub8, residues, seq_off, pair_q, pair_t, order[2], tb_off, sc_off, mask_off;
@@ -1097,6 +1099,7 @@ int aadp_set_scoring(aadp_ctx* c, const float* sub, int A, float gi, float ge, i
   c->flags = flags;
   c->gi_f = gi;
   c->ge_f = ge;
+  c->subf_h.assign(sub, sub + (size_t)A * A);
   if (c->subf.reserve((size_t)A * A * 4)) return 1;
   CK(cudaMemcpyAsync(c->subf.p, sub, (size_t)A * A * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -2213,8 +2216,23 @@ int aadp_batch_optimal(aadp_ctx* c, int64_t p, int direction, int32_t* pairs, in
   return 0;
 }
 
-int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap, int32_t* n_out,
-                           int32_t* status) {
+}  // extern "C"
+
+// packs the capacity-sized alignment slots of a batch front to back: one warp per pair
+__global__ void compact_alignments_kernel(const int2* __restrict__ slots, const int64_t* __restrict__ cap_off,
+                                          const int32_t* __restrict__ n, const int64_t* __restrict__ out_off, int64_t npairs,
+                                          int2* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; p < npairs; p += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int2* src = slots + cap_off[p];
+    int2* dst = out + out_off[p];
+    for (int k = lane; k < n[p]; k += 32) dst[k] = src[k];
+  }
+}
+
+// compact_off != nullptr: aadp_batch_optimal_all_compact
+static int optimal_all_impl(aadp_ctx* c, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap, int32_t* n_out,
+                            int32_t* status, int64_t* compact_off) {
   if (check_ctx(c, true)) return 1;
   Batch& b = c->b;
   if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
@@ -2231,7 +2249,7 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   }
   if (ali_off) memcpy(ali_off, cap.data(), (size_t)(np + 1) * 8);
   if (np == 0) return 0;
-  if (pairs && pairs_cap < cap[(size_t)np]) return fail("aadp_batch_optimal_all: pairs buffer too small (needs 2*ali_off[npairs] ints)");
+  if (!compact_off && pairs && pairs_cap < cap[(size_t)np]) return fail("aadp_batch_optimal_all: pairs buffer too small (needs 2*ali_off[npairs] ints)");
   CK(cudaStreamSynchronize(c->stream));
   if (pin_reserve(c, (size_t)(np + 1) * 8 + 4096)) return 1;
   if (upload_vec(c, c->ali_cap, cap)) return 1;
@@ -2273,11 +2291,50 @@ int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t
   CK(cudaGetLastError());
   c->launches = 1;
   c->d2h_bytes = 0;
-  if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)np] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)np] * 8; }
-  if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
+  if (compact_off) {
+    // compact form: only the aligned pairs that exist travel.  The lengths come back first (4 bytes per pair), the host
+    // turns them into offsets, a gather kernel packs the slots front to back, and one copy brings the packed pairs.
+    std::vector<int32_t> nn((size_t)np);
+    CK(cudaMemcpyAsync(nn.data(), c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += np * 4;
+    compact_off[0] = 0;
+    for (int64_t p = 0; p < np; ++p) compact_off[p + 1] = compact_off[p] + nn[(size_t)p];
+    const int64_t total = compact_off[np];
+    if (pairs && pairs_cap < total) return fail("aadp_batch_optimal_all_compact: pairs buffer too small");
+    if (pairs && total > 0) {
+      std::vector<int64_t> offv(compact_off, compact_off + np + 1);
+      if (pin_reserve(c, (size_t)(np + 1) * 8 + 4096)) return 1;
+      if (upload_vec(c, c->scratch_a, offv)) return 1;
+      if (c->scratch_b.reserve((size_t)total * 8)) return 1;
+      compact_alignments_kernel<<<(unsigned)std::min<int64_t>((np * 32 + 255) / 256, 148 * 16), 256, 0, c->stream>>>(
+          c->ali_out.as<int2>(), c->ali_cap.as<int64_t>(), c->ali_n.as<int32_t>(), c->scratch_a.as<int64_t>(), np, c->scratch_b.as<int2>());
+      CK(cudaGetLastError());
+      c->launches++;
+      CK(cudaMemcpyAsync(pairs, c->scratch_b.p, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+      c->d2h_bytes += total * 8;
+    }
+    if (n_out) memcpy(n_out, nn.data(), (size_t)np * 4);
+  } else {
+    if (pairs) { CK(cudaMemcpyAsync(pairs, c->ali_out.p, (size_t)cap[(size_t)np] * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += cap[(size_t)np] * 8; }
+    if (n_out) { CK(cudaMemcpyAsync(n_out, c->ali_n.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
+  }
   if (status) { CK(cudaMemcpyAsync(status, c->ali_status.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += np * 4; }
   CK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+extern "C" {
+
+int aadp_batch_optimal_all(aadp_ctx* c, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap, int32_t* n_out,
+                           int32_t* status) {
+  return optimal_all_impl(c, direction, ali_off, pairs, pairs_cap, n_out, status, nullptr);
+}
+
+int aadp_batch_optimal_all_compact(aadp_ctx* c, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
+                                   int32_t* n_out, int32_t* status) {
+  if (!ali_off) return fail("aadp_batch_optimal_all_compact: ali_off is required");
+  return optimal_all_impl(c, direction, nullptr, pairs, pairs_cap, n_out, status, ali_off);
 }
 
 }  // extern "C"
@@ -2448,6 +2505,68 @@ int aadp_batch_near_optimal(aadp_ctx* c, const int64_t* pair_ids, int64_t n, flo
                             int64_t paths_cap, float* threshold) {
   return near_optimal_impl(c, 0, nullptr, nullptr, pair_ids, n, delta_ratio, max_alignments, n_ali, status, scores, ali_len,
                            path_off, paths, paths_cap, threshold);
+}
+
+int aadp_batch_near_optimal_pruned(aadp_ctx* c, int64_t pair_id, int variant, const uint8_t* subopt_flags, float delta_ratio,
+                                   uint32_t k_limit, uint32_t sort_limit, float max_overlap, uint32_t user_limit,
+                                   int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
+                                   int32_t* paths, int64_t paths_cap, float* threshold) {
+  if (check_ctx(c, true)) return 1;
+  Batch& b = c->b;
+  if (variant != AADP_PRUNE_KSORTED && variant != AADP_PRUNE_REDUNDANCY) return fail("unknown pruning variant");
+  if (pair_id < 0 || pair_id >= b.npairs) return fail("pair index out of range");
+  if (max_alignments < 1 || !n_ali || !status) return fail("bad output arguments");
+  if (k_limit < 1 || sort_limit < 1) return fail("k_limit and sort_limit must be positive");
+  if (c->sc.local) return fail("near-optimal enumeration of local alignments is not defined by the reference");
+  if (!(b.ran_what & AADP_W_FWD)) return fail("forward fill was not run");
+  if (!c->float_mode && (!(b.ran_what & AADP_W_TB) || !(b.ran_what & (AADP_W_SCORES | AADP_W_MASK))))
+    return fail("the pruned enumerators walk the forward scores and the optimal predecessors: run with AADP_W_TB and AADP_W_SCORES");
+  const int qs = b.pair_q[(size_t)pair_id], ts = b.pair_t[(size_t)pair_id];
+  const int Lq = (int)(b.seq_off[qs + 1] - b.seq_off[qs]), Lt = (int)(b.seq_off[ts + 1] - b.seq_off[ts]);
+  const size_t ncell = (size_t)(Lq + 2) * (Lt + 2);
+  std::vector<float> F(ncell), sim(ncell, 0.f);
+  std::vector<int32_t> pq(ncell), pt(ncell);
+  if (aadp_batch_fetch_pair(c, pair_id, F.data(), pq.data(), pt.data(), nullptr, nullptr, nullptr, nullptr)) return 1;
+  // SimilarityMatrix (simmatrix.h:40-73): interior = substitution score of the two residues, borders 0
+  std::vector<uint8_t> qr((size_t)Lq + 1), tr((size_t)Lt + 1);
+  if (!b.have_seqs) return fail("the batch has no resident residues");
+  if (Lq) CK(cudaMemcpyAsync(qr.data(), c->residues.as<uint8_t>() + b.seq_off[qs], (size_t)Lq, cudaMemcpyDeviceToHost, c->stream));
+  if (Lt) CK(cudaMemcpyAsync(tr.data(), c->residues.as<uint8_t>() + b.seq_off[ts], (size_t)Lt, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int A = c->sc.A;
+  for (int i = 1; i <= Lq; ++i)
+    for (int j = 1; j <= Lt; ++j) sim[(size_t)i * (Lt + 2) + j] = c->subf_h[(size_t)qr[(size_t)i - 1] * A + tr[(size_t)j - 1]];
+  PrunedParams Q;
+  Q.Lq = Lq; Q.Lt = Lt;
+  Q.F = F.data(); Q.pq = pq.data(); Q.pt = pt.data(); Q.sim = sim.data();
+  Q.flags = subopt_flags;
+  Q.gi = c->gi_f; Q.ge = c->ge_f;
+  Q.delfree = c->sc.delfree; Q.insfree = c->sc.insfree;
+  Q.delta_ratio = delta_ratio;
+  Q.k_limit = k_limit; Q.sort_limit = sort_limit; Q.user_limit = user_limit; Q.max_overlap = max_overlap;
+  Q.max_alignments = max_alignments;
+  PrunedWalk W(Q);
+  if (variant == AADP_PRUNE_KSORTED) W.run_ksorted(); else W.run_controlled();
+  if (threshold) *threshold = W.threshold;
+  *status = W.overflow ? 1 : 0;
+  const size_t n_out = std::min<size_t>(W.as.size(), (size_t)max_alignments);
+  *n_ali = (int32_t)n_out;
+  int64_t at = 0;
+  for (size_t k = 0; k < n_out; ++k) {
+    const PrunedAlignment& a = W.as[k];
+    if (scores) scores[k] = a.score;
+    if (ali_len) ali_len[k] = (int32_t)a.back.size();
+    if (paths) {
+      if (at + (int64_t)a.back.size() > paths_cap) return fail("aadp_batch_near_optimal_pruned: paths buffer too small");
+      for (size_t m = 0; m < a.back.size(); ++m) {  // front to back: (0,0) first
+        const std::pair<int, int>& pr = a.back[a.back.size() - 1 - m];
+        paths[2 * (at + (int64_t)m)] = pr.first;
+        paths[2 * (at + (int64_t)m) + 1] = pr.second;
+      }
+    }
+    at += (int64_t)a.back.size();
+  }
+  return 0;
 }
 
 int aadp_batch_near_optimal_constrained(aadp_ctx* c, const int64_t* pair_ids, int64_t n, const uint8_t* subopt_flags,

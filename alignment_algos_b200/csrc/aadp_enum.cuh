@@ -191,9 +191,10 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   for (;;) {
     if (q0 == 1 || t0 == 1) {
       if (!emit(q0, t0, __fadd_rn(curr, F(q0, t0)))) break;
-    } else if (count >= P.user_limit) {
-      // as.size() > user_limit at the entry of branch() (as.size() = completed alignments + the one in progress): the
-      // reference stops branching and completes this alignment along the optimal predecessors
+    } else if (next == 0 && count >= P.user_limit) {
+      // as.size() > user_limit at the ENTRY of a branch() call (as.size() = completed alignments + the one in progress):
+      // the reference stops branching and completes this alignment along the optimal predecessors.  A frame that is
+      // re-entered (next > 0) is a branch() that started before the limit was reached: its candidate loops continue.
       int a = q0, b = t0;
       float s = curr;
       if (!walk(a, b, s, true)) break;

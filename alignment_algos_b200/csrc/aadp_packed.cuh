@@ -29,7 +29,6 @@
 #pragma once
 #include "aadp_kernels.cuh"
 #include <cuda_fp16.h>
-#include <type_traits>
 
 namespace aadp {
 
@@ -54,9 +53,6 @@ constexpr int kPackedBound = 7000;  // |score| bound (integer units) a pair must
 #endif
 #ifndef AADP_PROF_AHEAD
 #define AADP_PROF_AHEAD 1  // profile words of the next row loaded during the current step (software pipelining)
-#endif
-#ifndef AADP_TWO_LOOPS
-#define AADP_TWO_LOOPS 1   // steps before the first final-row capture of a warp run in a loop without the capture branch
 #endif
 #ifndef AADP_SLACK_IMAD
 #define AADP_SLACK_IMAD 1  // near-optimal slack: 1 = one FMA-pipe add + double-biased compare, 0 = three-input ALU add
@@ -485,11 +481,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   for (int h = 0; h < 2; ++h)
     if (pid[h] >= 0 && Lq[h] == 1) capture(h, (int)qp[h][0]);
 
-  // One row step of the warp.  CAP = false compiles the step without the (rare) capture branch: the steps before the
-  // first capture of any lane of the warp -- about 85 % of a task -- run in a loop whose schedule the branch does not
-  // disturb (measured: the branch costs 2-4 % of a step although it is taken twice per lane and task).
-  auto step = [&](const int s, auto cap_tag) {
-    constexpr bool CAP = decltype(cap_tag)::value;
+  for (int s = 0; s < nsteps; ++s) {
     uint32_t xn = __shfl_up_sync(0xffffffffu, x_pub, 1);
     uint32_t e_in = __shfl_up_sync(0xffffffffu, e_pub, 1);
     uint32_t mg_in = __shfl_up_sync(0xffffffffu, mg_pub, 1);
@@ -684,26 +676,13 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         }
       }
 #ifndef AADP_EXP_NOCAP  // (timing experiment only: without the capture the final scores are wrong)
-      if (CAP && (i + 1 == Lq[0] || i + 1 == Lq[1])) {
+      if (i + 1 == Lq[0] || i + 1 == Lq[1]) {
         for (int h = 0; h < 2; ++h)
           if (i + 1 == Lq[h]) capture(h, h ? qa_n1 : qa_n0);
       }
 #endif
     }
-  };
-#if AADP_TWO_LOOPS
-  // first step in which any lane of the warp captures: row Lq-1 of lane `off` is step Lq-2+off (Lq = 1 captured above)
-  int s_cap = nsteps;
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-    if (pid[h] >= 0 && Lq[h] >= 2) s_cap = min(s_cap, Lq[h] - 2 + off);
-  s_cap = __reduce_min_sync(0xffffffffu, s_cap);
-  int s = 0;
-  for (; s < s_cap; ++s) step(s, std::false_type());
-  for (; s < nsteps; ++s) step(s, std::true_type());
-#else
-  for (int s = 0; s < nsteps; ++s) step(s, std::true_type());
-#endif
+  }
 
   // ---- final-row summaries from the parked state: M(Lq,j) = sim(Lq,j) + X(Lq-1,j-1)
   for (int h = 0; h < 2; ++h) {

@@ -77,7 +77,7 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self, t0, t1):
+    def summary(self, t0, t1, _widened=False):
         sm, mx, reasons = [], 0.0, set()
         for ts, line in self.samples:
             if ts < t0 - 0.05 or ts > t1 + 0.05:
@@ -93,6 +93,11 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+        if not sm and not _widened:
+            # a timed region shorter than the sampling interval: take the samples of the second around it
+            out = self.summary(t0 - 0.5, t1 + 0.5, True)
+            out["note"] = "timed region shorter than the sampling interval: samples within 0.5 s of it"
+            return out
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
@@ -406,17 +411,23 @@ def kernel_bytes_per_cu(kernel, what):
     packed reverse + traceback + fused mask:  0.5 B traceback + 2 B int16 score read + 1/8 B mask  = 2.625
     long-pair wavefront (int32 scores):       0.5 B traceback + 4 B score written                  = 4.5
     score-only kernels: residues in, one score out per pair."""
+    import re
     if "wave" in kernel:
         return 4.5
-    if "MSK=1" in kernel:
-        return 2.625
-    if "TB=1" in kernel and "FST=1" in kernel:
-        return 2.5
-    if "TB=1" in kernel:
-        return 0.5
-    if "FST=1" in kernel or "ST=" in kernel:
-        return 2.0
-    return (2 * 300.0 + 4.0) / 300.0 ** 2
+    score_only = (2 * 300.0 + 4.0) / 300.0 ** 2
+    m = re.search(r"packed_kernel<TB=(\d),FST=(\d),MSK=(\d)", kernel)
+    if m:
+        tb, fst, msk = (int(x) for x in m.groups())
+        if msk:
+            return 0.5 * tb + 2.0 + 0.125 + 2.0 * fst
+        b = 0.5 * tb + 2.0 * fst
+        return b if b > 0 else score_only
+    m = re.search(r"fill_kernel<K=\d+,TB=(\d),ST=(\d)", kernel)
+    if m:
+        tb, st = int(m.group(1)), int(m.group(2))
+        b = 0.5 * tb + 2.0 * st
+        return b if b > 0 else score_only
+    return score_only
 
 
 def main():
@@ -581,17 +592,15 @@ def main():
     # pinned host memory -- inputs H2D, alignments D2H, all inside the timed region
     e2e_ali = None
     if (what & a.W_TB) and (what & a.W_FWD):
-        off_b = np.zeros(n + 1, np.int64)
         cap_rows = int(sum(len(seqs[pq[p]]) + len(seqs[pt[p]]) + 2 for p in range(n)))
         pairs_t = torch.empty((cap_rows, 2), dtype=torch.int32).pin_memory()
         n_t = torch.empty(n, dtype=torch.int32).pin_memory()
         st_t = torch.empty(n, dtype=torch.int32).pin_memory()
-        bufs = (off_b, pairs_t.numpy(), n_t.numpy(), st_t.numpy())
         asteps = max(2, min(args.steps, 5))
 
         def step_ali():
             ctx.fill_batch(hb["res"], hb["off"], hb["pq"], hb["pt"], what, DELTA)
-            return ctx.optimal_all(a.FWD, n, bufs=bufs)
+            return ctx.optimal_all_compact(a.FWD, n, pairs=pairs_t.numpy())
 
         step_ali()
         barrier()
@@ -607,7 +616,7 @@ def main():
                    "steps": asteps, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": int(d2h + ctx.last_transfer_bytes()[1]),  # scalars + the alignment slots copied back
                    "aligned_pairs_per_step": int(an.astype(np.int64).sum()),
-                   "what": "aadp_fill_batch + aadp_batch_optimal_all(forward): every optimal alignment back in pinned host memory"}
+                   "what": "aadp_fill_batch + aadp_batch_optimal_all_compact(forward): every optimal alignment, packed, back in pinned host memory"}
 
     # ---- leg 2b: the same calls from THREE host threads over three contexts (independent contexts are thread-safe,
     # include/aadp.h), each on its own non-blocking stream: while the GPU fills the batch of one call, the other threads

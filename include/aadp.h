@@ -255,6 +255,12 @@ int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, 
  *   status   host per pair: 0, or 3 where the reference throws "Illegal alignment start pair"           */
 int aadp_batch_optimal_all(aadp_ctx* ctx, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
                            int32_t* n_out, int32_t* status);
+/* The same, COMPACT: ali_off (npairs+1, required) receives the offsets of the alignments packed one after the other
+ * (ali_off[p+1] - ali_off[p] = n_out[p] aligned pairs), and only those pairs are copied back -- for 100 k pairs of the
+ * C3 shape 28 MB instead of the 485 MB of the capacity-sized slots.  pairs_cap (in aligned pairs) must hold
+ * ali_off[npairs]; the capacity total of aadp_batch_optimal_all is always enough.                               */
+int aadp_batch_optimal_all_compact(aadp_ctx* ctx, int direction, int64_t* ali_off, int32_t* pairs, int64_t pairs_cap,
+                                   int32_t* n_out, int32_t* status);
 
 /* ---- near-optimal ENUMERATION of listed pairs of the resident batch on the GPU: replaces
  * UnconstrainedNearOptimal::enumerate / branch (ucw.h:63-191) up to, not including, its final sortSet.  One warp per
@@ -286,6 +292,27 @@ int aadp_batch_near_optimal_constrained(aadp_ctx* ctx, const int64_t* pair_ids, 
                                         const int64_t* flag_off, float delta_ratio, int32_t max_alignments,
                                         int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
                                         int64_t* path_off, int32_t* paths, int64_t paths_cap, float* threshold);
+
+/* ---- the PRUNED near-optimal enumerators of ONE pair of the resident batch:
+ *   AADP_PRUNE_KSORTED     KSConstrainedNearOptimal::enumerate  (kscw.h:113-351): every branch point ranks its passing
+ *                          predecessors by f + r - g and keeps the k_limit best (the best one keeps the budget, the
+ *                          others continue with half of it)
+ *   AADP_PRUNE_REDUNDANCY  CRConstrainedNearOptimal::enumerate  (crcw.h:134-594): ranked predecessors (at most sort_limit)
+ *                          are extended along their optimal sub-paths to the next SuboptFlags region boundary; one that
+ *                          shares more than max_overlap of an accepted sub-path is dropped
+ * subopt_flags: Lt+2 bytes (sflags.h), NULL = all true.  k_limit / sort_limit / max_overlap / user_limit: the fields of
+ * NOaliParams (noalib.cpp:16-22).  The batch must have been run with AADP_W_FWD | AADP_W_TB | AADP_W_SCORES.  Output: the
+ * alignments in the reference's slot order BEFORE its final sortSet -- scores[k], ali_len[k], and the aligned pairs of
+ * alignment k packed one after the other in `paths` (2 ints per pair, (0,0) first; paths_cap in pairs).  status: 0, or 1
+ * when more than max_alignments alignments exist (the first max_alignments are returned).  The walk itself runs on the
+ * host over the GPU-filled matrices of the pair (csrc/aadp_pruned.h): it is a short sequential recursion whose width the
+ * pruning bounds.  Equal-score cuts are resolved by std::sort / std::partial_sort as in the reference.              */
+#define AADP_PRUNE_KSORTED 2
+#define AADP_PRUNE_REDUNDANCY 3
+int aadp_batch_near_optimal_pruned(aadp_ctx* ctx, int64_t pair_id, int variant, const uint8_t* subopt_flags, float delta_ratio,
+                                   uint32_t k_limit, uint32_t sort_limit, float max_overlap, uint32_t user_limit,
+                                   int32_t max_alignments, int32_t* n_ali, int32_t* status, float* scores, int32_t* ali_len,
+                                   int32_t* paths, int64_t paths_cap, float* threshold);
 
 /* ---- packed traceback format helpers (host side, no GPU needed) ---------------------------
  * Row stride in bytes of the ROW-MAJOR packed traceback (int32 kernels) for template length Lt. */

@@ -114,6 +114,45 @@ class DPMatrix {
   // UnconstrainedNearOptimal::branch, ucw.h:88-191) in the reference's depth-first slot order; include/hmap2/ucw.h
   // is the enumerator class on top of it.  budget = maximum number of alignments; *overflow tells when there are more.
   // subopt_flags != 0: the constrained enumeration of cw.h with one flag per template position (sentinels included).
+  // The pruned enumerators (kscw.h / crcw.h): forward fill with traceback and scores on the GPU,
+  // then aadp_batch_near_optimal_pruned over the resident pair.  variant: AADP_PRUNE_KSORTED / AADP_PRUNE_REDUNDANCY.
+  template <class Alignment, class Params>
+  void prunedAlignments(int variant, const Params& np, const std::vector<unsigned char>& subopt_flags, int budget,
+                        std::vector<Alignment>* out, bool* overflow) {
+    std::string alphabet;
+    std::vector<float> sub;
+    float gi, ge;
+    int at;
+    describe(&alphabet, &sub, &gi, &ge, &at);
+    const std::vector<uint8_t> q = aadp::encode(*query_seq, alphabet), t = aadp::encode(*templ_seq, alphabet);
+    std::vector<uint8_t> residues(q);
+    residues.insert(residues.end(), t.begin(), t.end());
+    residues.push_back(0);
+    const int64_t seq_off[3] = {0, (int64_t)q.size(), (int64_t)(q.size() + t.size())};
+    const int32_t pq = 0, pt = 1;
+    aadp_ctx* ctx = aadp::default_context();
+    aadp::check(aadp_set_scoring(ctx, sub.data(), (int)alphabet.size(), gi, ge, at, AADP_REPRO_REV_BUG));
+    float fs = 0.f;
+    aadp::check(aadp_fill_batch(ctx, residues.data(), seq_off, 2, &pq, &pt, 1, AADP_W_FWD | AADP_W_SCORES | AADP_W_TB,
+                                np.delta_ratio, &fs, 0, 0, 0));
+    const size_t slot = q.size() + t.size() + 4;
+    std::vector<int32_t> paths(2 * (size_t)budget * slot), len((size_t)budget);
+    std::vector<float> scores((size_t)budget);
+    int32_t n = 0, status = 0;
+    aadp::check(aadp_batch_near_optimal_pruned(ctx, 0, variant, subopt_flags.data(), np.delta_ratio, np.k_limit, np.sort_limit,
+                                               np.max_overlap, np.user_limit, budget, &n, &status, scores.data(), len.data(),
+                                               paths.data(), (int64_t)budget * (int64_t)slot, 0));
+    *overflow = status == 1;
+    out->clear();
+    out->resize((size_t)n);
+    size_t at_pair = 0;
+    for (int32_t k = 0; k < n; ++k) {
+      Alignment& ali = (*out)[(size_t)k];
+      ali.score = scores[(size_t)k];
+      for (int32_t m = 0; m < len[(size_t)k]; ++m, ++at_pair) ali.append(paths[2 * at_pair], paths[2 * at_pair + 1]);
+    }
+  }
+
   template <class Alignment>
   // user_limit: the enumerator's alignment limit (ucw.h:72, cw.h:76); beyond it the GPU walk forces optimal paths
   // exactly as the reference does (ucw.h:115-126, cw.h:118-130).  0 keeps the reference's own value.

@@ -402,6 +402,32 @@ class Reference:
             o += ln[k]
         return out
 
+    def pruned_alignments(self, q, t, delta_ratio, which, flags=None, k_limit=16, sort_limit=100, max_overlap=0.30,
+                          user_limit=100000, max_alignments=20000):
+        """Every alignment of the reference's KSConstrainedNearOptimal (which=2, kscw.h) or CRConstrainedNearOptimal
+        (which=3, crcw.h), sorted by its sortSet.  flags: SuboptFlags per template position incl. sentinels."""
+        K = int(max_alignments)
+        fl = None
+        if flags is not None:
+            fl = "".join("1" if f else "0" for f in flags).encode()
+        cap = K * (len(q) + len(t) + 4)
+        scores = np.zeros(K, np.float32)
+        ln = np.zeros(K, np.int32)
+        pairs = np.zeros((cap, 2), np.int32)
+        n, tot = C.c_int(0), C.c_long(0)
+        rc = self.lib.ref_pruned_alignments(*self._args(q, t), C.c_float(delta_ratio), int(which), fl, C.c_uint(k_limit),
+                                            C.c_uint(sort_limit), C.c_float(max_overlap), C.c_uint(user_limit), K, C.c_long(cap),
+                                            C.byref(n), C.byref(tot), _p(scores, C.c_float), _p(ln, C.c_int), _p(pairs, C.c_int))
+        if rc == 5:
+            raise OverflowError("%d alignments" % n.value)
+        if rc:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        out, o = [], 0
+        for k in range(n.value):
+            out.append((float(scores[k]), pairs[o:o + ln[k]].copy()))
+            o += ln[k]
+        return out
+
     def time_fills(self, seqs, pair_q, pair_t, what=3, nthreads=1):
         """Time the reference DPMatrix constructor over pairs. Returns (seconds, cells, checksum)."""
         arena = b"".join(self.letters(s) for s in seqs)

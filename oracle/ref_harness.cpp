@@ -33,6 +33,17 @@
 #include <chrono>
 #include <atomic>
 
+// kscw.h:98-104 and crcw.h:120-126 define debug operator<< overloads for HMAP-only instantiations at namespace scope;
+// the four classes only have to be declared for those headers to parse.
+class HMAPSequence;
+class SMAPSequence;
+class Gn2Eval;
+class Hmap2Eval;
+// kscw.h:188 and crcw.h:268 call min(as.capacity()*2, params->user_limit) with a size_t and an unsigned int: that only
+// deduces on ILP32, where the reference was written.  A non-template overload lets the unmodified lines compile on LP64.
+#include <cstddef>
+inline size_t min(size_t a, const unsigned int& b) { return a < (size_t)b ? a : (size_t)b; }
+
 #include "aa_seq.h"
 #include "aasubalib.h"
 #include "alib.h"
@@ -44,9 +55,24 @@
 #include "sflags.h"
 #include "submatrix.h"
 #include "ucw.h"
+#include "kscw.h"
+#include "crcw.h"
 
 typedef AASubstitutionEval<AASequence, AASequence> AAEval;
 typedef DPMatrix<AASequence, AASequence, AAEval> AADPM;
+
+// kscw.h:243 and crcw.h:235 stream every operation to cerr; the AAEval instantiation needs its own overloads (found by
+// argument-dependent lookup at the point of instantiation).  Same text as the reference's HMAP overloads.
+std::ostream& operator<<(std::ostream& os, KSConstrainedNearOptimal<AASequence, AASequence, AAEval>::op_data& op) {
+  os << "limit=" << op.limit << ",q0=" << op.q0 << ",t0=" << op.t0 << ",k0=" << op.k0 << ",s=" << op.score
+     << ",ns=" << op.new_r << ",t=" << op.thresh;
+  return os;
+}
+std::ostream& operator<<(std::ostream& os, CRConstrainedNearOptimal<AASequence, AASequence, AAEval>::op_data& op) {
+  os << "limit=" << op.limit << ",q0=" << op.q0 << ",t0=" << op.t0 << ",k0=" << op.k0 << ",s=" << op.score
+     << ",ns=" << op.new_r;
+  return os;
+}
 
 // A table-driven Evaluator (evaluator.h:20-147): the three scoring functions read what the caller tabulated, so the
 // reference's own fill (dpmatrix.h:356-1030) can be driven with position-dependent gap models shaped like
@@ -449,6 +475,81 @@ int ref_ucw_alignments(const char* q, const char* t, const char* matrix_file, fl
     g_err = "unknown exception";
     return 2;
   }
+}
+
+// KSConstrainedNearOptimal::enumerate (kscw.h:113-134; which = 2) and CRConstrainedNearOptimal::enumerate
+// (crcw.h:134-170; which = 3): every alignment in the order the reference leaves them in (sortSet with a huge
+// number_suboptimal, so nothing is dropped).  k_limit / sort_limit / max_overlap / user_limit as in NOaliParams
+// (noalib.cpp:16-22).  Both enumerators log every operation to cerr; it is silenced for the duration of the call.
+int ref_pruned_alignments(const char* q, const char* t, const char* matrix_file, float gi, float ge, int align_type,
+                          float delta_ratio, int which, const char* flags, unsigned k_limit, unsigned sort_limit,
+                          float max_overlap, unsigned user_limit, int max_alignments, long max_pairs, int* n_alignments,
+                          long* total_pairs, float* scores, int* ali_len, int* pairs) {
+  std::streambuf* old = std::cerr.rdbuf();
+  std::ostringstream sink;
+  std::cerr.rdbuf(sink.rdbuf());
+  int rc = 0;
+  try {
+    AASequence qs, ts;
+    make_seq(qs, q);
+    make_seq(ts, t);
+    AliParams ap = make_params(gi, ge, align_type);
+    BlosumMatrix bm(matrix_file);
+    AAEval ev(ap, bm);
+    AADPM dpm(qs, ts, ev, fwd, ap.align_type);
+    NOaliParams np;
+    np.delta_ratio = delta_ratio;
+    np.number_suboptimal = 0x3fffffff / 32;
+    np.k_limit = k_limit;
+    np.sort_limit = sort_limit;
+    np.max_overlap = max_overlap;
+    np.user_limit = user_limit;
+    Optimal<AASequence, AASequence, AAEval> opt(ap.align_type);
+    AlignmentSet<AASequence, AASequence, AAEval> as(dpm, opt);
+    as.clear();
+    int sz2 = dpm.getTemplateSize();
+    SuboptFlags sf(true, (size_t)sz2);
+    if (flags)
+      for (int j = 0; j < sz2; ++j) sf.Set(j, flags[j] != '0');
+    if (which == 2) {
+      KSConstrainedNearOptimal<AASequence, AASequence, AAEval> ks(np, sf);
+      ks.enumerate(dpm, as);
+    } else {
+      CRConstrainedNearOptimal<AASequence, AASequence, AAEval> cr(np, sf);
+      cr.enumerate(dpm, as);
+    }
+    *n_alignments = (int)as.size();
+    long tot = 0;
+    bool fits = (int)as.size() <= max_alignments;
+    for (size_t k = 0; k < as.size(); ++k) {
+      long len = (long)as[k].size();
+      if (fits && tot + len <= max_pairs) {
+        scores[k] = as[k].score;
+        ali_len[k] = (int)len;
+        long o = tot;
+        for (std::list<AlignedPair<AASequence, AASequence> >::const_iterator it = as[k].begin(); it != as[k].end(); ++it, ++o) {
+          pairs[2 * o] = it->query_idx();
+          pairs[2 * o + 1] = it->template_idx();
+        }
+      } else {
+        fits = false;
+      }
+      tot += len;
+    }
+    *total_pairs = tot;
+    rc = fits ? 0 : 5;
+  } catch (std::string& e) {
+    g_err = e;
+    rc = 1;
+  } catch (std::bad_alloc&) {
+    g_err = "bad_alloc";
+    rc = 4;
+  } catch (...) {
+    g_err = "unknown exception";
+    rc = 2;
+  }
+  std::cerr.rdbuf(old);
+  return rc;
 }
 
 // CPU baseline timing: runs the reference's DPMatrix constructor (fill only, as BASELINE.md §3

@@ -160,3 +160,45 @@ def test_user_evaluator_with_positional_gaps_equals_reference_build(at):
             assert got.returncode == 0, got.stdout[-300:] + got.stderr[-300:]
             assert len(ref.stdout.splitlines()) == 2 * (Lq + 2) * (Lt + 2) + 1
             assert got.stdout == ref.stdout, "style %d %dx%d: GPU tabulated fill differs from the reference build" % (style, Lq, Lt)
+
+
+PRUNED_DEMO = os.path.join(CXX, "pruned_demo")
+PRUNED_REF = os.path.join(CXX, "pruned_ref")
+
+
+def _run_pruned(binary, at, gi, ge, delta, kl, sl, mo, flags, q, t):
+    fl = "-" if flags is None else "".join("1" if f else "0" for f in flags)
+    out = subprocess.run([binary, MATRIX, str(at), str(gi), str(ge), str(delta), str(kl), str(sl), str(mo), fl, _letters(q),
+                          _letters(t)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    return out.stdout.splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("at", [po.SEMI_LOCAL, po.GLOBAL, po.GLOBAL_LOCAL], ids=["semi_local", "global", "global_local"])
+def test_pruned_enumerators_dropin_equals_reference_build(at):
+    # include/hmap2/kscw.h + crcw.h (GPU fill + aadp_batch_near_optimal_pruned) against the UNMODIFIED
+    # reference headers compiled from the same source: the printed alignment sets (scores and aligned pairs, after the
+    # reference's sortSet) must be the same.  Alignments of equal score may be listed in either order.
+    if not (os.path.exists(PRUNED_DEMO) and os.path.exists(PRUNED_REF)):
+        pytest.skip("pruned demos not built")
+    rng = np.random.default_rng(60 + at)
+    n = 0
+    for gi, ge in ((3, 1), (12, 1), (4.73, 0.34)):
+        for L, delta in ((24, 0.25), (48, 0.12), (96, 0.06)):
+            q = rng.integers(0, 20, L).astype(np.uint8)
+            t = q.copy()
+            t[::4] = rng.integers(0, 20, len(t[::4]))
+            t = np.concatenate([t[: L // 3], t[L // 3 + 2:]])
+            for flags in (None, (np.arange(len(t) + 2) // 7) % 2):
+                for kl, sl, mo in ((16, 100, 0.3), (4, 10, 0.5)):
+                    got = _run_pruned(PRUNED_DEMO, at, gi, ge, delta, kl, sl, mo, flags, q, t)
+                    ref = _run_pruned(PRUNED_REF, at, gi, ge, delta, kl, sl, mo, flags, q, t)
+                    assert [l for l in got if " n " in l] == [l for l in ref if " n " in l]
+                    assert sorted(got) == sorted(ref), (gi, ge, L, kl)
+                    # sortSet order: scores must be non-increasing in both
+                    for tag in ("KS", "CR"):
+                        sc = [float(l.split()[1]) for l in got if l.startswith(tag + " ") and " pairs" in l]
+                        assert sc == sorted(sc, reverse=True)
+                    n += len(got)
+    assert n > 200
