@@ -308,11 +308,25 @@ int launch_packed(aadp_ctx* c, PackedParams& P, int tbm, int fst, int msk) {
   }
 }
 
+// shared memory of a wavefront CTA (one warp = one stripe): substitution table, query ring + staging block, profile
+static size_t wave_smem_bytes(int A) {
+  return (size_t)((A * A + 15) / 16 * 16) + kQRing + 512 + (size_t)A * 32 * kWaveK;
+}
+// CTAs of the wavefront kernel that can be resident at once (all stripes of a pair wait on each other)
+static int wave_resident_ctas(aadp_ctx* c, int A) {
+  auto kern = wave_kernel<kWaveK, 1, 2>;  // the largest variant
+  const size_t smem = wave_smem_bytes(A);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem) != cudaSuccess) return 0;
+  return occ * c->num_sms;
+}
+
 template <int TBM, int STM>
 int launch_wave_t(aadp_ctx* c, FillParams& Pf, FillParams& Pr, int ndirs, int nst) {
   auto kern = wave_kernel<kWaveK, TBM, STM>;
   const int A = Pf.sc.A;
-  size_t smem = (size_t)((A * A + 15) / 16 * 16) + kQRing + 512 + (size_t)A * 32 * kWaveK;
+  const size_t smem = wave_smem_bytes(A);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
@@ -536,6 +550,7 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
     double cells = 0, packed_cells = 0, bucket_cells[2] = {0, 0};
   };
   std::vector<Part> part((size_t)T);
+  const int wave_budget = c->allow_wave ? wave_resident_ctas(c, c->sc.A) : 0;
   auto range = [&](int t, int64_t* lo, int64_t* hi) { *lo = np * t / T; *hi = np * (t + 1) / T; };
   // ---- pass 1: lengths, class, score bound
   c->pool.run(T, [&](int t) {
@@ -562,8 +577,10 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
       const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
                              c->sc.ge <= 400 && c->sc.gi <= 2048;
       // long pairs: one CTA per kWaveCols-column stripe, all stripes of both directions co-resident
+      // (both directions in one cooperative launch: every CTA of both must be resident; the budget is the kernel's real
+      // occupancy, queried once per batch -- a pair that does not fit takes the int32 kernel instead of failing later)
       const bool wave_ok = !packed_ok && c->allow_wave && Lq >= 1 && Lt > 512 && cl >= (int64_t)c->wave_min_cells &&
-                           2 * ((Lt + kWaveCols - 1) / kWaveCols) <= (int64_t)c->num_sms * 8;
+                           2 * ((Lt + kWaveCols - 1) / kWaveCols) <= (int64_t)wave_budget;
       b.fmt[(size_t)p] = packed_ok ? 1 : (wave_ok ? 2 : 0);
       if (packed_ok) {
         P.packed_cells += (double)cl;
@@ -875,10 +892,11 @@ int run_wave_pairs(aadp_ctx* c, uint32_t what) {
       CK(cudaStreamSynchronize(c->stream));
       CK(cudaMemcpy(h.data(), c->wave_dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       for (int k = 0; k < nd; ++k) {
-        fprintf(stderr, "[aadp] wave dir %d: stripe wait%%:", dirs[k]);
-        for (int st = 0; st < nst; st += std::max(1, nst / 24))
-          fprintf(stderr, " %d:%.0f/%.2fms", st, 100.0 * (double)h[((size_t)k * nst + st) * 2] / (double)std::max<long long>(1, h[((size_t)k * nst + st) * 2 + 1]),
-                  (double)h[((size_t)k * nst + st) * 2 + 1] / 1.965e6);
+        fprintf(stderr, "[aadp] wave dir %d: stripe wait%%/total:", dirs[k]);
+        for (int st = 0; st < nst; st += std::max(1, nst / 24)) {
+          const long long* e = &h[((size_t)k * nst + st) * 2];
+          fprintf(stderr, " %d:%.0f/%.2fms", st, 100.0 * (double)e[0] / (double)std::max<long long>(1, e[1]), (double)e[1] / 1.965e6);
+        }
         fprintf(stderr, "\n");
       }
     }

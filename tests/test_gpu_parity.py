@@ -1115,3 +1115,83 @@ def test_enumeration_user_limit_truncation_on_gpu(blosum):
             full = c.near_optimal([0], delta, K, **({"subopt_flags": [flags], "constrained": True} if constrained else {}))[0]
             assert len(full[2]) > len(alis) or full[0] == 1
     c.close()
+
+
+def _rescore(q, t, pairs, M, gi, ge, delfree, insfree):
+    """Score of an alignment given as aligned pairs incl. (0,0) and (last,last): substitution scores minus gap(len) =
+    gi + ge*(len-1) per run of skipped residues, end gaps free where the align type says so (aasubalib.h:27-77)."""
+    Lq, Lt = len(q), len(t)
+    s = 0.0
+    for (a0, b0), (a1, b1) in zip(pairs[:-1], pairs[1:]):
+        if 1 <= a1 <= Lq and 1 <= b1 <= Lt:
+            s += float(M[q[a1 - 1], t[b1 - 1]])
+        dl, il = b1 - b0 - 1, a1 - a0 - 1
+        assert dl == 0 or il == 0, "a step skips residues of one sequence only"
+        if dl >= 1 and not (delfree and (b0 == 0 or b1 == Lt + 1)):
+            s -= gi + ge * (dl - 1)
+        if il >= 1 and not (insfree and (a0 == 0 or a1 == Lq + 1)):
+            s -= gi + ge * (il - 1)
+    return s
+
+
+def test_long_pair_wavefront_8000_full_parity(blosum):
+    # the multi-CTA wavefront at a size where the stripe hand-off is live for thousands of rows (32 stripes per
+    # direction): scores, BOTH traceback matrices and the near-optimal set against the oracle's O(mn) fill, cell by cell
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(1005)
+    Lq, Lt = 8000, 8050
+    q, t = rand_pair(rng, Lq, Lt)
+    t[1000:5000] = q[900:4900]          # a related stretch: a real optimum away from the borders
+    t[1500:4800:7] = rng.integers(0, 20, len(t[1500:4800:7]))
+    c = a.Context(0)
+    try:
+        for at in (po.SEMI_LOCAL, po.GLOBAL):
+            c.set_scoring(M, 12, 1, at)
+            O = po.Oracle(M, 12, 1, at)
+            out = c.fill_pair(q, t, a.BOTH, delta_ratio=0.01)
+            F, fq, ft = O.fill(q, t, po.FWD, True, fast=True)
+            assert_matrix_equal("F", out["score_fwd"], F)
+            assert_matrix_equal("fq", out["prevq_fwd"], fq)
+            assert_matrix_equal("ft", out["prevt_fwd"], ft)
+            del fq, ft
+            R, rq, rt = O.fill(q, t, po.REV, True, fast=True)
+            assert_matrix_equal("R", out["score_rev"], R)
+            assert_matrix_equal("rq", out["prevq_rev"], rq)
+            assert_matrix_equal("rt", out["prevt_rev"], rt)
+            del rq, rt
+            thr = O.threshold(float(F[-1, -1]), 0.01)
+            mask, _ = O.nearopt_mask(F, R, O.sim(q, t), thr)
+            assert out["threshold"] == thr
+            assert_matrix_equal("nearopt", out["nearopt"], mask)
+            del out, F, R, mask
+    finally:
+        c.close()
+
+
+def test_long_pair_wavefront_30000_properties(blosum):
+    # BASELINE.json configs[4] at full size (the oracle would need 11 GB per matrix): size-independent properties --
+    # forward optimum == reverse optimum, both optimal alignments are valid paths whose rescoring gives the optimum,
+    # and the near-optimal set contains every cell of the optimal alignment
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(1005)
+    L = 30000
+    seqs = [rng.integers(0, 20, L).astype(np.uint8) for _ in range(2)]
+    res, off = a.Context.pack(seqs)
+    c = a.Context(0)
+    try:
+        c.set_scoring(M, 12, 1, po.SEMI_LOCAL)
+        out = c.fill_batch(res, off, np.array([0], np.int32), np.array([1], np.int32),
+                           a.W_FWD | a.W_REV | a.W_TB | a.W_MASK, 0.01)
+        assert out["fwd_score"][0] == out["rev_score"][0]
+        opt = float(out["fwd_score"][0])
+        for d in (a.FWD, a.REV):
+            rc, pairs, sc = c.optimal(0, d, L, L)
+            assert rc == 0 and sc == opt
+            assert tuple(pairs[0]) == (0, 0) and tuple(pairs[-1]) == (L + 1, L + 1)
+            assert np.all(np.diff(pairs[:, 0]) >= 1) and np.all(np.diff(pairs[:, 1]) >= 1)
+            assert _rescore(seqs[0], seqs[1], [tuple(p) for p in pairs], M, 12.0, 1.0, True, True) == opt
+        assert out["nearopt_count"][0] >= len(pairs) - 2
+    finally:
+        c.close()
