@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaadp.so")
 SOURCES = ["aadp_api.cu"]
-DEPS = ["aadp_api.cu", "aadp_kernels.cuh", "aadp_packed.cuh", "aadp_general.cuh", "aadp_enum.cuh", os.path.join("..", "..", "include", "aadp.h")]
+DEPS = ["aadp_api.cu", "aadp_kernels.cuh", "aadp_packed.cuh", "aadp_general.cuh", "aadp_frec.cuh", "aadp_enum.cuh", "aadp_pruned.h", os.path.join("..", "..", "include", "aadp.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

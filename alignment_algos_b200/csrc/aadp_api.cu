@@ -5,6 +5,7 @@
 #include "aadp_kernels.cuh"
 #include "aadp_packed.cuh"
 #include "aadp_general.cuh"
+#include "aadp_frec.cuh"
 #include "aadp_enum.cuh"
 #include "aadp_pruned.h"
 
@@ -170,6 +171,7 @@ struct aadp_ctx {
   int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
   int ucw_user_limit = 100000, cw_user_limit = 1000000;  // ucw.h:72, cw.h:76
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
+  int gg_records = 1;  // record-list kernel (aadp_frec.cuh) for affine gaps in exact-float mode (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
   uint8_t* pin = nullptr;
@@ -1082,6 +1084,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "exact_float")) { c->force_float = value != 0; return 0; }
   if (!strcmp(key, "general_threads")) { c->gg_threads_cap = std::max(32, std::min(512, value / 32 * 32)); return 0; }
   if (!strcmp(key, "general_prune")) { c->gg_prune = value ? 1 : 0; return 0; }
+  if (!strcmp(key, "general_records")) { c->gg_records = value ? 1 : 0; return 0; }
   // alignment limits of the enumerators (ucw.h:72 hard-codes 100000, cw.h:76 1000000): beyond them the reference
   // forces optimal paths instead of branching; <= 0 restores the reference's value
   if (!strcmp(key, "ucw_user_limit")) { c->ucw_user_limit = value > 0 ? value : 100000; return 0; }
@@ -1561,6 +1564,10 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
       longest = std::max(longest, std::max(rect[4 * k + 2] - rect[4 * k], rect[4 * k + 3] - rect[4 * k + 1]));
   }
   const bool prune_pays = longest >= 96;
+  // record-list kernel (aadp_frec.cuh): affine gaps only; one warp per (pair, direction), rows and column leaders in
+  // shared memory, 16-bit row/column indices
+  const int rec_cap = frec_cap(maxLt);
+  const bool use_rec = c->gg_records && !(ov && ov->d_del) && maxL < 32000 && maxLt <= 1024 && frec_smem_bytes(rec_cap) <= 200 * 1024;
   GeneralParams G{};
   G.A = c->sc.A;
   G.subf = c->subf.as<float>();
@@ -1609,7 +1616,7 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
     G.prevt[nd] = tb ? c->gg_pt[d].as<int32_t>() : nullptr;
     G.fin[nd] = d ? d_fin_rev : d_fin_fwd;
     G.pmcol[nd] = nullptr;
-    if (c->gg_prune && prune_pays && !(ov && ov->d_del) && G.gi >= 0.f && G.ge >= 0.f) {  // the pruning needs pen(len) to grow with len
+    if (use_rec || (c->gg_prune && prune_pays && !(ov && ov->d_del) && G.gi >= 0.f && G.ge >= 0.f)) {  // the pruning needs pen(len) to grow with len; the record kernel keeps its column links here
       if (c->gg_pm[d].reserve(std::max<size_t>((size_t)cells * 4, 16))) return 1;
       G.pmcol[nd] = c->gg_pm[d].as<float>();
     }
@@ -1651,8 +1658,18 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   // few CTAs (single pairs): latency counts, one column per thread; many CTAs: smaller CTAs hide each other's barriers
   const int tcap = n * nd < 296 ? 512 : c->gg_threads_cap;
   const int threads = std::max(compact ? 32 : 64, std::min(tcap, (width + 31) / 32 * 32));
-  c->prof_begin(tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
-  if (tab) {
+  c->prof_begin(use_rec ? (tb ? "frec_fill_kernel<TB=1>" : "frec_fill_kernel<TB=0>")
+                        : tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
+  if (use_rec) {
+    const size_t rsm = frec_smem_bytes(rec_cap);
+    if (tb) {
+      CK(cudaFuncSetAttribute(frec_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      frec_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
+    } else {
+      CK(cudaFuncSetAttribute(frec_fill_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      frec_fill_kernel<0><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
+    }
+  } else if (tab) {
     CK(cudaFuncSetAttribute(general_fill_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     general_fill_kernel<1, 1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
   } else if (tb) {

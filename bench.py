@@ -350,9 +350,16 @@ def quick_pairlist(workload, args, rank, local_rank, world, barrier, max_over_ra
     import alignment_algos_b200 as a
     from alignment_algos_b200 import synth
     alpha, M = a.blosum62()
+    gi, ge = GI, GE
     if workload == "c2":
         seqs, pq, pt = synth.pair_workload(1002 + rank, 10_000, 100, 500)
         what = a.W_FWD
+    elif workload == "c3f":
+        # the C3 shape under the reference's DEFAULT penalties (alib.cpp:17-18): off the dyadic grid, so the exact fp32
+        # general-gap path runs (record-list kernel, 0 ulp); scores + near-optimal counts, no resident traceback
+        seqs, pq, pt = synth.pair_workload(1003 + rank, 20_000, 100, 500)
+        what = a.W_FWD | a.W_REV | a.W_MASK
+        gi, ge = 4.73, 0.34
     else:
         rng = np.random.default_rng(1005 + rank)
         seqs = [rng.integers(0, 20, args.long_len).astype(np.uint8) for _ in range(2)]
@@ -362,7 +369,7 @@ def quick_pairlist(workload, args, rank, local_rank, world, barrier, max_over_ra
     ctx = a.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_scoring(M, GI, GE, a.SEMI_LOCAL)
+    ctx.set_scoring(M, gi, ge, a.SEMI_LOCAL)
     n = len(pq)
     d_f = torch.empty(n, dtype=torch.float32, device="cuda")
     d_r = torch.empty(n, dtype=torch.float32, device="cuda")
@@ -384,7 +391,7 @@ def quick_pairlist(workload, args, rank, local_rank, world, barrier, max_over_ra
     ms = max_over_ranks(e0.elapsed_time(e1))
     prof = ctx.profile()
     ctx.set_profiling(False)
-    if what & a.W_REV:
+    if (what & a.W_REV) and workload != "c3f":  # (fp32 scoring: the two directions round differently)
         assert torch.equal(d_f, d_r), "forward and reverse optima differ"
     by = {}
     for name, kms, cells in prof:
@@ -394,6 +401,12 @@ def quick_pairlist(workload, args, rank, local_rank, world, barrier, max_over_ra
     out = {"value": sum_over_ranks(cu_step) * steps / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms / steps,
            "steps": steps, "scaling": "weak (one replica per rank)" if workload == "c5" else "weak",
            "kernel_ms_per_step": {k: v[0] / steps for k, v in by.items()}}
+    if workload == "c3f":
+        out["pairs_per_s"] = sum_over_ranks(n) * steps / (ms * 1e-3)
+        out["workload"] = "c3 shape (20000 pairs per GPU, L in [100,500]), BLOSUM62 with the reference's default gi=4.73 ge=0.34, semi_local: exact fp32 general-gap fill fwd+rev + near-optimal counts"
+        out["dtype"] = "f32"
+        ctx.close()
+        return out
     dom = max(((k, v) for k, v in by.items() if v[1] > 0), key=lambda kv: kv[1][0], default=None)
     if dom:
         bpc = kernel_bytes_per_cu(dom[0], what)
@@ -440,7 +453,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-overlap", action="store_true", help="skip the three-context end-to-end leg")
     ap.add_argument("--seqs", type=int, default=20_000, help="sequences of the all-vs-all workload (C4 = 20000)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "c3f"],
                     help="c3 (default, the headline): 100k pairs fwd+rev+traceback+mask; c2: 10k pairs forward "
                          "score-only; c4: all-vs-all of --seqs sequences, forward score-only, strong scaling over ranks; "
                          "c5: one 30k x 30k pair fwd+rev+traceback+mask (multi-CTA wavefront)")
@@ -491,6 +504,14 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.workload == "c3f":  # the C3 shape under the reference's default (non-dyadic) penalties: exact fp32 path
+        r = quick_pairlist("c3f", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, max(1, args.steps // 5), 1)
+        if rank == 0:
+            print(json.dumps({"metric": "GCUPS fwd+rev exact fp32 general-gap fill + near-optimal counts", "n_gpus": world,
+                              "higher_is_better": True, "data": "synthetic", "vs_baseline": None, **r}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "c3":
         seqs, pq, pt = make_workload(rank, args.pairs)
         what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
@@ -525,7 +546,7 @@ def main():
     ctx = a.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_scoring(M, GI, GE, a.SEMI_LOCAL)
+    ctx.set_scoring(M, gi, ge, a.SEMI_LOCAL)
     n = len(pq)
     d_f = torch.empty(n, dtype=torch.float32, device="cuda")
     d_r = torch.empty(n, dtype=torch.float32, device="cuda")
@@ -739,6 +760,7 @@ def main():
         try:
             extra["c2"] = quick_pairlist("c2", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, 20, 5)
             extra["c5"] = quick_pairlist("c5", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, 3, 2)
+            extra["c3_float_default"] = quick_pairlist("c3f", args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, 2, 1)
             c4 = run_c4(args, rank, local_rank, world, barrier, max_over_ranks, sum_over_ranks, emit=False, steps=1, warmup=1)
             extra["c4"] = {k: c4[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "pairs_per_s", "e2e", "issue_roofline")}
             extra["c4"]["workload"] = c4["config"]["workload"]

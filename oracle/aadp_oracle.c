@@ -386,6 +386,136 @@ int orc_fill_fast(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_
   return 0;
 }
 
+/* ---------------------------------------------------------------- exact output-sensitive fill for ANY fp32 scoring
+ *
+ * CPU model of the GPU's record-list kernel (csrc/aadp_frec.cuh); same arithmetic, same decisions.
+ *
+ * In real arithmetic the order of the deletion candidates k of a cell (a,b) does not depend on b:
+ *   D[a-1][k] - gi - ge*(b-k-2) = (D[a-1][k] + ge*k) - const(b),      KEY(k) = D[a-1][k] + ge*k,
+ * so a running maximum of the key would do.  In fp32 (dpmatrix.h:460-462: s = D; s -= pen; s += sim, pen = gi +
+ * ge*(len-1) rounded twice) candidates whose keys differ by less than the accumulated rounding noise MU can swap
+ * places, and the strict '>' of the ascending scan (:463) lets the FIRST of equal fp32 values win.  Hence:
+ *   * a candidate k is DOMINATED for ever when an earlier k' < k has KEY(k') > KEY(k) + MU: wherever k is a candidate
+ *     k' is one too and its fp32 value is strictly larger.  The others -- KEY(k) >= max(KEY(1..k-1)) - MU -- are the
+ *     RECORDS of the row (column); only they can ever win;
+ *   * for a given cell only the records within 2*MU of the running key maximum can win: walking the record list
+ *     backwards, the walk stops at the first record whose key is below max - 2*MU (everything before it is below
+ *     max - MU);
+ *   * the visited records are evaluated with the reference's own three fp32 operations and the first maximum
+ *     (smallest k) is taken, exactly as the ascending strict-'>' scan would.
+ * Cost per cell = size of the group of noise-tied leaders (1-2 on average), not the length of the scan.
+ * MU bounds: |key error| + |pen error| + the three roundings of a candidate value, all <= 2^-22 * W with
+ * W = max|D| so far + |pen(maxlen)| + ge*maxlen + max|sim| + 1; MU = 2^-19 * W (8x safety).
+ * stats[0..3] = cells, row-walk steps, column-walk steps, cells whose column leader was ambiguous.               */
+int orc_fill_rec(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc, int direction,
+                 int repro_rev_bug, float* score, int* prev_q, int* prev_t, long* stats) {
+  if (Lq < 0 || Lt < 0) return 1;
+  flow_t f;
+  size_t n = (size_t)(Lq + 2) * (Lt + 2);
+  float* sim = (float*)malloc(sizeof(float) * n);
+  flow_init(&f, q, Lq, t, Lt, sc, direction, score, prev_q, prev_t, sim);
+  if (f.q1 <= 0 || f.t1 <= 0) { free(sim); return 1; }
+  long st_cells = 0, st_row = 0, st_col = 0, st_amb = 0;
+  if (!degenerate(&f)) {
+    boundary(&f);
+    const int nq = f.q1 - 1, nt = f.t1 - 1;
+    float smax = 0.f;
+    for (int x = 0; x < sc->A * sc->A; ++x) { float v = sc->sub[x] < 0 ? -sc->sub[x] : sc->sub[x]; if (v > smax) smax = v; }
+    const int maxlen = nq > nt ? nq : nt;
+    float pmaxabs = affine(sc, maxlen); if (pmaxabs < 0) pmaxabs = -pmaxabs;
+    float gemax = sc->ge * (float)maxlen; if (gemax < 0) gemax = -gemax;
+    const float wconst = pmaxabs + gemax + smax + 1.0f;
+    const float ge = sc->ge;
+    const float NEGK = -3.0e38f;
+    /* row structures of the previous row */
+    float* key = (float*)malloc(sizeof(float) * (size_t)(nt + 2));
+    float* pmin = (float*)malloc(sizeof(float) * (size_t)(nt + 2)); /* inclusive prefix maximum of key */
+    int* cnt = (int*)malloc(sizeof(int) * (size_t)(nt + 2));       /* records among 1..k */
+    int* rl = (int*)malloc(sizeof(int) * (size_t)(nt + 2));
+    /* column structures: leader (largest key, smallest row on ties), runner-up key, last record, record links */
+    float* ckey = (float*)malloc(sizeof(float) * (size_t)(nt + 2));
+    float* c2key = (float*)malloc(sizeof(float) * (size_t)(nt + 2));
+    float* cD = (float*)malloc(sizeof(float) * (size_t)(nt + 2));
+    int* ck = (int*)malloc(sizeof(int) * (size_t)(nt + 2));
+    int* clast = (int*)malloc(sizeof(int) * (size_t)(nt + 2));
+    int* link = (int*)calloc((size_t)(nq + 2) * (nt + 2), sizeof(int)); /* link[k][c] = record of column c before row k */
+    for (int c = 0; c <= nt + 1; ++c) { ckey[c] = NEGK; c2key[c] = NEGK; cD[c] = 0.f; ck[c] = 0; clast[c] = 0; }
+    float dmax = 0.f;
+    for (int b = 1; b <= nt; ++b) { float v = score[at(&f, 1, b)]; v = v < 0 ? -v : v; if (v > dmax) dmax = v; }
+    for (int a = 2; a <= nq; ++a) {
+      /* hand-over of row a-1: keys, prefix maxima, records (uses max|D| over rows <= a-1) */
+      { float v = score[at(&f, a - 1, 1)]; v = v < 0 ? -v : v; if (v > dmax) dmax = v; }
+      const float mu = (dmax + wconst) * (1.0f / 524288.0f);
+      float run = NEGK; int nrec = 0;
+      for (int k = 1; k <= nt; ++k) {
+        float kk = score[at(&f, a - 1, k)] + ge * (float)k;
+        key[k] = kk;
+        if (kk >= run - mu) rl[nrec++] = k;
+        if (kk > run) run = kk;
+        pmin[k] = run;
+        cnt[k] = nrec;
+      }
+      float rowabs = 0.f;
+      for (int b = 2; b <= nt; ++b) {
+        float simc = sim[at(&f, a, b)], s;
+        int oa = a - 1, ob = b - 1;
+        float os = clampl(&f, score[at(&f, oa, ob)] + simc);
+        st_cells++;
+        if (b >= 3) { /* deletions: records of row a-1 among 1..b-2, from the last one backwards */
+          const float lim = pmin[b - 2] - 2.0f * mu;
+          float bs = 0.f; int bk = 0;
+          for (int i = cnt[b - 2] - 1; i >= 0; --i) {
+            const int k = rl[i];
+            if (key[k] < lim) break;
+            st_row++;
+            s = score[at(&f, a - 1, k)]; s -= gdel(&f, k, b); s += simc; s = clampl(&f, s);
+            if (bk == 0 || s >= bs) { bs = s; bk = k; }
+          }
+          if (bk && bs > os) { oa = a - 1; ob = bk; os = bs; }
+        }
+        if (a >= 3) { /* insertions: column b-1, candidate rows 1..a-2 */
+          const int c = b - 1;
+          float bs; int bk;
+          if (c2key[c] < ckey[c] - 2.0f * mu) { /* a clear leader */
+            bk = ck[c];
+            s = cD[c]; s -= gins(&f, bk, a, b); s += simc; bs = clampl(&f, s);
+            st_col++;
+          } else {
+            st_amb++;
+            const float lim = ckey[c] - 2.0f * mu;
+            bs = 0.f; bk = 0;
+            for (int k = clast[c]; k > 0; k = link[(size_t)k * (nt + 2) + c]) {
+              const float dk = score[at(&f, k, c)];
+              if (dk + ge * (float)k < lim) break;
+              st_col++;
+              s = dk; s -= gins(&f, k, a, b); s += simc; s = clampl(&f, s);
+              if (bk == 0 || s >= bs) { bs = s; bk = k; }
+            }
+          }
+          if (bk && bs > os) { oa = bk; ob = b - 1; os = bs; }
+        }
+        set_tb(&f, a, b, oa, ob, os);
+        { float v = os < 0 ? -os : os; if (v > rowabs) rowabs = v; }
+        /* column b-1 receives the candidate of row a-1 (used from row a+1 on) */
+        {
+          const int c = b - 1, k = a - 1;
+          const float dk = score[at(&f, k, c)];
+          const float kk = dk + ge * (float)k;
+          if (kk >= ckey[c] - mu) { link[(size_t)k * (nt + 2) + c] = clast[c]; clast[c] = k; }
+          if (kk > ckey[c]) { c2key[c] = ckey[c]; ckey[c] = kk; ck[c] = k; cD[c] = dk; }
+          else if (kk > c2key[c]) c2key[c] = kk;
+        }
+      }
+      if (rowabs > dmax) dmax = rowabs;
+    }
+    free(key); free(pmin); free(cnt); free(rl); free(ckey); free(c2key); free(cD); free(ck); free(clast); free(link);
+    final_cell(&f, repro_rev_bug);
+  }
+  if (stats) { stats[0] = st_cells; stats[1] = st_row; stats[2] = st_col; stats[3] = st_amb; }
+  free(sim);
+  return 0;
+}
+
 /* ---------------------------------------------------------------- optimal tracebacks */
 
 /* optimal.h:47-124 */

@@ -62,6 +62,12 @@ int orc_fill_sub(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_s
 int orc_fill_fast(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc,
                   int direction, int repro_rev_bug, float* score, int* prev_q, int* prev_t);
 
+/* Exact fill for ANY fp32 scoring at a cost per cell that does not grow with the scans: record lists (see the
+ * comment at the definition).  CPU model of csrc/aadp_frec.cuh; bit-identical to orc_fill for every scoring.
+ * stats (may be NULL): cells, row-walk steps, column-walk steps, cells with an ambiguous column leader.       */
+int orc_fill_rec(const uint8_t* q, int Lq, const uint8_t* t, int Lt, const orc_scoring* sc, int direction,
+                 int repro_rev_bug, float* score, int* prev_q, int* prev_t, long* stats);
+
 /* optimal.h:47-124 on a forward matrix. pairs = 2 ints per aligned pair, front to back.
  * Returns 0, or 3 for "Illegal alignment start pair" (optimal.h:74).                        */
 int orc_optimal_fwd(const float* score, const int* prev_q, const int* prev_t, int sz1, int sz2,

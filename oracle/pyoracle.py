@@ -83,6 +83,22 @@ class Oracle:
             raise RuntimeError("Illegal bounds building DPM")
         return (score, pq, pt, sim) if want_sim else (score, pq, pt)
 
+    def fill_rec(self, q, t, direction=FWD, repro_rev_bug=True):
+        """orc_fill_rec: the record-list fill (CPU model of csrc/aadp_frec.cuh).  Returns (score, pq, pt, stats) with
+        stats = (cells, row-walk steps, column-walk steps, cells with an ambiguous column leader)."""
+        q = np.ascontiguousarray(q, dtype=np.uint8)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        sz1, sz2 = len(q) + 2, len(t) + 2
+        score = np.zeros((sz1, sz2), np.float32)
+        pq = np.zeros((sz1, sz2), np.int32)
+        pt = np.zeros((sz1, sz2), np.int32)
+        st = (C.c_long * 4)()
+        rc = self.lib.orc_fill_rec(_p(q, C.c_uint8), len(q), _p(t, C.c_uint8), len(t), C.byref(self.sc), direction,
+                                   int(repro_rev_bug), _p(score, C.c_float), _p(pq, C.c_int), _p(pt, C.c_int), st)
+        if rc:
+            raise RuntimeError("Illegal bounds building DPM")
+        return score, pq, pt, tuple(st)
+
     def fill_sub(self, q, t, rect, direction=FWD, repro_rev_bug=True):
         """build_subdpm (dpmatrix.h:319-353): rect = (q1_end, t1_end, q2_beg, t2_beg), matrix indices."""
         q = np.ascontiguousarray(q, dtype=np.uint8)

@@ -850,50 +850,61 @@ def test_constrained_near_optimal_enumeration_on_gpu(blosum):
         c.close()
 
 
-def test_pruned_general_gap_scans_change_nothing(blosum):
-    # "general_prune" (default on) skips scan candidates that provably fail the reference's strict '>' (prefix-maximum
-    # bound + binary search).  Every output must equal the unpruned scan, and the oracle: all align types incl. local,
-    # both directions, whole matrices, sub-rectangles, and the batch scalars.
+def test_record_and_pruned_general_gap_kernels_change_nothing(blosum):
+    # Three implementations of the exact fp32 fill must agree on every output, and with the oracle's literal scan:
+    # the record-list kernel (aadp_frec.cuh, default), the pruned scans ("general_records" 0: prefix-maximum bound +
+    # binary search) and the literal scans ("general_prune" 0 as well).  All align types incl. local, both directions,
+    # whole matrices (short, wider than 512 columns, related pairs), sub-rectangles, and the batch scalars.
     import alignment_algos_b200 as a
     _, M = blosum
     rng = np.random.default_rng(55)
     for gi, ge, at in [(4.73, 0.34, po.SEMI_LOCAL), (4.73, 0.34, po.LOCAL), (2.17, 0.61, po.GLOBAL), (0.9, 0.0, po.GLOBAL_LOCAL),
                        (12, 1, po.LOCAL_GLOBAL)]:
-        cp, cn = a.Context(0), a.Context(0)
-        for c, prune in ((cp, 1), (cn, 0)):
+        cr, cp, cn = a.Context(0), a.Context(0), a.Context(0)
+        for c, rec, prune in ((cr, 1, 1), (cp, 0, 1), (cn, 0, 0)):
+            c.set_option("general_records", rec)
             c.set_option("general_prune", prune)
             c.set_option("exact_float", 1)
             c.set_scoring(M, gi, ge, at)
         O = po.Oracle(M, gi, ge, at)
-        for Lq, Lt in [(2, 2), (3, 40), (61, 5), (97, 130), (150, 620)]:
+        for Lq, Lt in [(2, 2), (3, 40), (61, 5), (1, 77), (97, 130), (150, 620), (333, 31), (300, 300)]:
             q, t = rand_pair(rng, Lq, Lt)
             if Lq == 97:
                 t[:90] = q[:90]          # a related pair: the pruning bites hardest there
-            x, y = cp.fill_pair(q, t, a.BOTH, delta_ratio=0.03), cn.fill_pair(q, t, a.BOTH, delta_ratio=0.03)
-            for key in x:
-                if x[key] is not None and key != "threshold":
-                    assert_matrix_equal("prune %s" % key, x[key], y[key])
-            assert x["threshold"] == y["threshold"]
+            if Lq == 300:
+                t[10:290] = q[5:285]     # a related pair with mutations: groups of noise-tied leaders
+                t[20:280:5] = rng.integers(0, 20, len(t[20:280:5]))
+            y = cn.fill_pair(q, t, a.BOTH, delta_ratio=0.03)
+            for tag, c in (("record", cr), ("prune", cp)):
+                x = c.fill_pair(q, t, a.BOTH, delta_ratio=0.03)
+                for key in x:
+                    if x[key] is not None and key != "threshold":
+                        assert_matrix_equal("%s %s" % (tag, key), x[key], y[key])
+                assert x["threshold"] == y["threshold"]
             if Lq * Lt < 20000:
                 for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
                     ws, wq, wt = O.fill(q, t, d, True, fast=False)
-                    assert_matrix_equal("oracle score", x["score_" + tag], ws)
-                    assert_matrix_equal("oracle pq", x["prevq_" + tag], wq)
-                    assert_matrix_equal("oracle pt", x["prevt_" + tag], wt)
+                    assert_matrix_equal("oracle score", y["score_" + tag], ws)
+                    assert_matrix_equal("oracle pq", y["prevq_" + tag], wq)
+                    assert_matrix_equal("oracle pt", y["prevt_" + tag], wt)
             rect = (1, 0, Lq, Lt + 1) if Lq > 2 else (0, 0, Lq + 1, Lt + 1)
             for d in (a.FWD, a.REV):
-                for u, v in zip(cp.fill_subpair(q, t, rect, d), cn.fill_subpair(q, t, rect, d)):
-                    assert_matrix_equal("prune sub-rectangle", u, v)
+                want = cn.fill_subpair(q, t, rect, d)
+                for c in (cr, cp):
+                    for u, v in zip(c.fill_subpair(q, t, rect, d), want):
+                        assert_matrix_equal("sub-rectangle", u, v)
         seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(1, 200, 40)]
         res, off = a.Context.pack(seqs)
         pq, pt = rng.integers(0, 40, 300).astype(np.int32), rng.integers(0, 40, 300).astype(np.int32)
         what = a.W_FWD | a.W_REV | (0 if at == po.LOCAL else a.W_MASK)
-        o1, o2 = cp.fill_batch(res, off, pq, pt, what, 0.02), cn.fill_batch(res, off, pq, pt, what, 0.02)
-        for key in o1:
-            if o1[key] is not None:
-                assert_matrix_equal("prune batch %s" % key, o1[key], o2[key])
-        cp.close()
-        cn.close()
+        o2 = cn.fill_batch(res, off, pq, pt, what, 0.02)
+        for c in (cr, cp):
+            o1 = c.fill_batch(res, off, pq, pt, what, 0.02)
+            for key in o1:
+                if o1[key] is not None:
+                    assert_matrix_equal("batch %s" % key, o1[key], o2[key])
+        for c in (cr, cp, cn):
+            c.close()
 
 
 def test_local_optimal_alignments_of_a_batch_on_gpu(blosum):
@@ -1117,23 +1128,6 @@ def test_enumeration_user_limit_truncation_on_gpu(blosum):
     c.close()
 
 
-def _rescore(q, t, pairs, M, gi, ge, delfree, insfree):
-    """Score of an alignment given as aligned pairs incl. (0,0) and (last,last): substitution scores minus gap(len) =
-    gi + ge*(len-1) per run of skipped residues, end gaps free where the align type says so (aasubalib.h:27-77)."""
-    Lq, Lt = len(q), len(t)
-    s = 0.0
-    for (a0, b0), (a1, b1) in zip(pairs[:-1], pairs[1:]):
-        if 1 <= a1 <= Lq and 1 <= b1 <= Lt:
-            s += float(M[q[a1 - 1], t[b1 - 1]])
-        dl, il = b1 - b0 - 1, a1 - a0 - 1
-        assert dl == 0 or il == 0, "a step skips residues of one sequence only"
-        if dl >= 1 and not (delfree and (b0 == 0 or b1 == Lt + 1)):
-            s -= gi + ge * (dl - 1)
-        if il >= 1 and not (insfree and (a0 == 0 or a1 == Lq + 1)):
-            s -= gi + ge * (il - 1)
-    return s
-
-
 def test_long_pair_wavefront_8000_full_parity(blosum):
     # the multi-CTA wavefront at a size where the stripe hand-off is live for thousands of rows (32 stripes per
     # direction): scores, BOTH traceback matrices and the near-optimal set against the oracle's O(mn) fill, cell by cell
@@ -1191,7 +1185,7 @@ def test_long_pair_wavefront_30000_properties(blosum):
             assert rc == 0 and sc == opt
             assert tuple(pairs[0]) == (0, 0) and tuple(pairs[-1]) == (L + 1, L + 1)
             assert np.all(np.diff(pairs[:, 0]) >= 1) and np.all(np.diff(pairs[:, 1]) >= 1)
-            assert _rescore(seqs[0], seqs[1], [tuple(p) for p in pairs], M, 12.0, 1.0, True, True) == opt
+            assert _rescore(None, seqs[0], seqs[1], [tuple(p) for p in pairs], M, 12.0, 1.0, po.SEMI_LOCAL) == opt
         assert out["nearopt_count"][0] >= len(pairs) - 2
     finally:
         c.close()

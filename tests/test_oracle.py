@@ -133,6 +133,46 @@ def test_oracle_literal_fill_matches_float_golden(golden_float):
             assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
 
 
+def test_record_list_fill_is_the_literal_fill(golden_float, blosum):
+    # orc_fill_rec (the CPU model of the GPU's record-list kernel, csrc/aadp_frec.cuh) against the reference's golden
+    # float vectors and against the literal O(n^3) restatement: default penalties, a scaled matrix, integer scoring
+    # (exact key ties everywhere), zero gap extension; all align types, both directions; related and random pairs
+    g = golden_float
+    for name in golden_cases(g):
+        q, t, gi, ge, at = golden_case(g, name)
+        O = po.Oracle(g["sub." + str(g[name + ".sub"])], gi, ge, at)
+        for d, tag in ((po.FWD, "fwd"), (po.REV, "rev")):
+            s, pq, pt, _ = O.fill_rec(q, t, d, True)
+            assert_matrix_equal(name + tag + ".score", s, g[name + "." + tag + ".score"])
+            assert_matrix_equal(name + tag + ".pq", pq, g[name + "." + tag + ".pq"].astype(np.int32))
+            assert_matrix_equal(name + tag + ".pt", pt, g[name + "." + tag + ".pt"].astype(np.int32))
+    _, M = blosum
+    rng = np.random.default_rng(77)
+    visited = cells = 0
+    for gi, ge, scale in ((4.73, 0.34, 1.0), (12.0, 1.0, 1.0), (3.3, 0.7, 0.37), (0.5, 0.0, 0.1)):
+        Ms = (M.astype(np.float32) * np.float32(scale)).astype(np.float32)
+        for at in (po.SEMI_LOCAL, po.GLOBAL, po.LOCAL, po.GLOBAL_LOCAL, po.LOCAL_GLOBAL):
+            O = po.Oracle(Ms, gi, ge, at)
+            for related in (0, 1):
+                Lq, Lt = (int(x) for x in rng.integers(1, 140, 2))
+                q = rng.integers(0, 20, Lq).astype(np.uint8)
+                t = rng.integers(0, 20, Lt).astype(np.uint8)
+                n = min(Lq, Lt) - 6
+                if related and n > 10:
+                    t[3:3 + n] = q[2:2 + n]
+                    idx = rng.integers(3, 3 + n, n // 4)
+                    t[idx] = rng.integers(0, 20, len(idx))
+                for d in (po.FWD, po.REV):
+                    want = O.fill(q, t, d, True)
+                    s, pq, pt, st = O.fill_rec(q, t, d, True)
+                    assert_matrix_equal("rec score", s, want[0])
+                    assert_matrix_equal("rec pq", pq, want[1])
+                    assert_matrix_equal("rec pt", pt, want[2])
+                    cells += st[0]
+                    visited += st[1] + st[2]
+    assert visited < 4 * cells  # output-sensitive: a few candidates per cell, not a scan
+
+
 def test_oracle_sub_rectangle_fill_matches_golden(golden_sub):
     # build_subdpm (dpmatrix.h:319-353): anchors inside the matrix, at the Head / Tail, degenerate rectangles
     g = golden_sub
