@@ -1686,7 +1686,8 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
 }
 
 static int gg_mask(aadp_ctx* c, int64_t p0, int64_t n, float delta_ratio, const float* d_fin_fwd, bool dense_mask,
-                   int64_t cells, float* d_threshold, int64_t* d_count) {
+                   int64_t cells, float* d_threshold, int64_t* d_count, bool listed = false) {
+  // listed: the items are the pairs gg_fill was given as a list (c->gg_items still holds them)
   GeneralMaskParams M{};
   M.A = c->sc.A;
   M.subf = c->subf.as<float>();
@@ -1694,7 +1695,7 @@ static int gg_mask(aadp_ctx* c, int64_t p0, int64_t n, float delta_ratio, const 
   M.seq_off = c->seq_off.as<int64_t>();
   M.pair_q = c->pair_q.as<int32_t>();
   M.pair_t = c->pair_t.as<int32_t>();
-  M.items = nullptr;
+  M.items = listed ? c->gg_items.as<int32_t>() : nullptr;
   M.item0 = (int)p0;
   M.dense_off = c->gg_off.as<int64_t>();
   M.F = c->gg_score[0].as<float>();
@@ -1725,19 +1726,29 @@ static int gg_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_
     if (c->gg_fin[0].reserve(std::max<size_t>((size_t)np * 4, 16))) return 1;
     ffwd = c->gg_fin[0].as<float>();
   }
+  // Chunks of pairs of SIMILAR template length: the record-list kernel sizes its shared memory (and with it the warps
+  // per SM) by the longest template of a launch, and a launch ends with its longest pair.  Results are per pair id.
+  std::vector<int64_t> order((size_t)np);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  auto len_t = [&](int64_t p) { const int ts = b.pair_t[p]; return b.seq_off[ts + 1] - b.seq_off[ts]; };
+  if (c->gg_records) std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return len_t(x) > len_t(y); });
   std::vector<int64_t> off;
   for (int64_t p0 = 0; p0 < np;) {
     off.assign(1, 0);
     int64_t p1 = p0;
+    const int64_t lt0 = len_t(order[(size_t)p0]);
     while (p1 < np) {
-      const int qs = b.pair_q[p1], ts = b.pair_t[p1];
+      const int64_t p = order[(size_t)p1];
+      const int qs = b.pair_q[p], ts = b.pair_t[p];
       const int64_t cl = (b.seq_off[qs + 1] - b.seq_off[qs] + 2) * (b.seq_off[ts + 1] - b.seq_off[ts] + 2);
       if (p1 > p0 && off.back() + cl > c->gg_budget_cells) break;
+      // a new launch when the templates have become a shared-memory class (64 columns) shorter -- but not for a handful of pairs
+      if (c->gg_records && p1 - p0 >= 2048 && (lt0 + 63) / 64 != (len_t(p) + 63) / 64) break;
       off.push_back(off.back() + cl);
       ++p1;
     }
-    if (gg_fill(c, p0, p1 - p0, dirmask, false, off, ffwd, d_rev_score)) return 1;
-    if ((what & AADP_W_MASK) && gg_mask(c, p0, p1 - p0, delta_ratio, ffwd, false, off.back(), d_threshold, d_nearopt_count)) return 1;
+    if (gg_fill(c, 0, p1 - p0, dirmask, false, off, ffwd, d_rev_score, nullptr, nullptr, false, order.data() + p0)) return 1;
+    if ((what & AADP_W_MASK) && gg_mask(c, 0, p1 - p0, delta_ratio, ffwd, false, off.back(), d_threshold, d_nearopt_count, true)) return 1;
     p0 = p1;
   }
   c->last_delta = delta_ratio;
