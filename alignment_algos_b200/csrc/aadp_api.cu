@@ -268,9 +268,9 @@ __global__ void arena_kernel(const uint8_t* __restrict__ res, const int64_t* __r
   }
 }
 
-template <int TBM, int FST, int MSK>
+template <int TBM, int FST, int MSK, int LOC = 0>
 int launch_packed_t(aadp_ctx* c, PackedParams& P) {
-  auto kern = packed_kernel<TBM, FST, MSK, 0>;
+  auto kern = packed_kernel<TBM, FST, MSK, 0, LOC>;
   const int A = P.sc.A;
   size_t smem = packed_smem_bytes(A, MSK);
   // measurement aid: AADP_PACKED_SMEM_PAD="fwd,rev" extra bytes per CTA lower the resident warps per SM
@@ -287,7 +287,7 @@ int launch_packed_t(aadp_ctx* c, PackedParams& P) {
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   char nm[64];
-  snprintf(nm, sizeof nm, "packed_kernel<TB=%d,FST=%d,MSK=%d>%s", TBM, FST, MSK, P.rev ? "rev" : "fwd");
+  snprintf(nm, sizeof nm, "packed_kernel<TB=%d,FST=%d,MSK=%d%s>%s", TBM, FST, MSK, LOC ? ",LOC=1" : "", P.rev ? "rev" : "fwd");
   c->prof_begin(nm, P.cells_hint);
   kern<<<grid, kPackedWarps * 32, smem, c->stream>>>(P);
   c->prof_end();
@@ -298,6 +298,15 @@ int launch_packed_t(aadp_ctx* c, PackedParams& P) {
 
 int launch_packed(aadp_ctx* c, PackedParams& P, int tbm, int fst, int msk) {
   const int key = tbm * 4 + fst * 2 + msk;
+  if (P.sc.local) {  // local alignments: the clamped variants (never with the fused near-optimal pass)
+    if (msk) return fail("internal: local alignments have no fused near-optimal pass");
+    switch (key) {
+      case 0: return launch_packed_t<0, 0, 0, 1>(c, P);
+      case 2: return launch_packed_t<0, 1, 0, 1>(c, P);
+      case 4: return launch_packed_t<1, 0, 0, 1>(c, P);
+      default: return launch_packed_t<1, 1, 0, 1>(c, P);
+    }
+  }
   switch (key) {
     case 0: return launch_packed_t<0, 0, 0>(c, P);
     case 1: return launch_packed_t<0, 0, 1>(c, P);
@@ -576,7 +585,9 @@ int build_batch_meta(aadp_ctx* c, uint32_t what) {
       P.cells += (double)cl;
       // |score| bound in integer units: matches + one end gap on each side
       const int64_t bd = std::min(Lq, Lt) * (int64_t)c->max_abs_sub + 2 * (int64_t)c->sc.gi + (int64_t)c->sc.ge * (Lq + Lt);
-      const bool packed_ok = c->allow_packed && !c->sc.local && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
+      // (local alignments: the packed kernel has no fused near-optimal pass for them -- F + R - sim needs both clamped
+      // matrices -- so a local run that asks for the cell set keeps the int32 kernels + mask_kernel)
+      const bool packed_ok = c->allow_packed && (!c->sc.local || !(what & AADP_W_MASK)) && Lq >= 1 && Lt >= 1 && Lt <= 512 && bd < kPackedBound &&
                              c->sc.ge <= 400 && c->sc.gi <= 2048;
       // long pairs: one CTA per kWaveCols-column stripe, all stripes of both directions co-resident
       // (both directions in one cooperative launch: every CTA of both must be resident; the budget is the kernel's real

@@ -230,7 +230,11 @@ struct RowSum {
   int diag, col;     // M(Lq,Lt) and the right-column candidate (lane owning column Lt only)
 };
 
-template <int TBM, int FST, int MSK, int XM>
+// LOC = 1: local alignments (dpmatrix.h:538-689, 879-1030): every candidate is clamped at 0 before it is compared
+// (s = max(0.f, s), :580 etc.), i.e. M = max(0, sim + X); the gap states stay unclamped (they only ever lose against
+// M >= 0 where the clamp would have mattered), a cell clamped to 0 keeps its match predecessor (decoded from the
+// stored score, dense_kernel / local_traceback_kernel).  One more VIMNMX per packed cell.
+template <int TBM, int FST, int MSK, int XM, int LOC = 0>
 __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int8_t* prof, int4* red,
                                             uint8_t* stage, int lane) {
   const Scoring& S = P.sc;
@@ -375,6 +379,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   const uint32_t inj_floor = seg_start ? (FLOOR2 & ~inj_b_mask) : 0u;
   const uint32_t inj_neg = seg_start ? NEG2 : 0u;
   const uint32_t NGE2 = pkdec(ge, ge);
+  const uint32_t ZERO2 = pkb(0, 0);
   const uint32_t NGI2 = pkdec(gi, gi);
   uint32_t binj = S.insfree ? pkb(0, 0) : pkb(-gi, -gi);
   const uint32_t binj_step = S.insfree ? 0u : NGE2;
@@ -572,7 +577,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
           const uint32_t simp = prmt(pwA[c >> 2], pwB[c >> 2], ssel);
           // plain packed add (VIADD.16x2, off the ALU pipe): no clamp is needed -- real cells stay far above the
           // floor and pad columns only drift down by ge per row (bounded by the host-side score bound)
-          Mv[c] = __vadd2(simp, Xd);
+          Mv[c] = LOC ? __vmaxs2(__vadd2(simp, Xd), ZERO2) : __vadd2(simp, Xd);
           if (MSK) {
             // slack = F(i,j) + R(i,j) - sim(i,j) = F(i,j) + X_rev(i+1,j+1) (<= optimum, so it stays in range);
             // element 15-c of the forward chunk.
@@ -691,7 +696,8 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
     RowSum r = {kNeg32, 0, kNeg32, kNeg32};
     for (int c = 0; c < 16; ++c) {
       const int j = off * 16 + c + 1 - sig[h];
-      const int m = unb16(capX[h][c], h) + (int)prow[c];  // M(Lq, j)
+      int m = unb16(capX[h][c], h) + (int)prow[c];  // M(Lq, j)
+      if (LOC) m = max(m, 0);
       if (j >= 1 && j < Lt[h]) {
         const int v = m - (S.delfree ? 0 : gap_w(gi, ge, Lt[h] - j));
         if (v > r.rb_val) { r.rb_val = v; r.rb_k = j; }
@@ -718,6 +724,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
         cl = max(cl, v.w);
       }
       int best = dg, kind = 0, k = Lt[h];
+      if (LOC) best = max(best, 0);
       if (Lt[h] >= 2 && rb > best) { best = rb; kind = 1; k = rk; }
       if (cl > best) { best = cl; kind = 2; k = -1; }
       if (XM) {
@@ -745,7 +752,7 @@ __device__ __forceinline__ void packed_task(const PackedParams& P, int task, int
   }  // rep
 }
 
-template <int TBM, int FST, int MSK, int XM>
+template <int TBM, int FST, int MSK, int XM, int LOC = 0>
 __global__ void __launch_bounds__(kPackedWarps * 32) __maxnreg__(XM ? 168 : (MSK ? 255 : (TBM ? 224 : 200))) packed_kernel(const PackedParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int A = P.sc.A;
@@ -765,7 +772,7 @@ __global__ void __launch_bounds__(kPackedWarps * 32) __maxnreg__(XM ? 168 : (MSK
     if (lane == 0) item = atomicAdd(P.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= (unsigned int)P.n_tasks) break;
-    packed_task<TBM, FST, MSK, XM>(P, (int)item, prof, red, stage, lane);
+    packed_task<TBM, FST, MSK, XM, LOC>(P, (int)item, prof, red, stage, lane);
   }
 }
 

@@ -546,7 +546,7 @@ def main():
     ctx = a.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_scoring(M, gi, ge, a.SEMI_LOCAL)
+    ctx.set_scoring(M, GI, GE, a.SEMI_LOCAL)
     n = len(pq)
     d_f = torch.empty(n, dtype=torch.float32, device="cuda")
     d_r = torch.empty(n, dtype=torch.float32, device="cuda")

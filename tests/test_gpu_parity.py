@@ -154,6 +154,51 @@ def test_batch_matches_oracle_and_properties(ctx):
                 assert_matrix_equal("optimal rev", pairs, opairs)
 
 
+def test_packed_local_batch_vs_oracle(ctx):
+    # LOCAL alignments on the packed int16x2 kernels (LOC = 1: every candidate clamped at 0, dpmatrix.h:538-689 / 879-1030):
+    # a batch of random and related pairs; final scores of every pair against the int32 kernels, full score and
+    # predecessor matrices of a sample against the oracle, local optimal alignments (find_max + enumerate_local)
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    alpha20, M20 = a.blosum62()
+    seqs, pq, pt = synth.pair_workload(79, 500, 20, 512)
+    res, off = a.Context.pack(seqs)
+    ctx.set_scoring(M20, 12, 1, po.LOCAL)
+    O = po.Oracle(M20, 12, 1, po.LOCAL)
+    what = a.W_FWD | a.W_REV | a.W_TB | a.W_SCORES
+    ctx.set_profiling(True)
+    out = ctx.fill_batch(res, off, pq, pt, what)
+    names = {n for n, _, _ in ctx.profile()}
+    ctx.set_profiling(False)
+    assert any("LOC=1" in n for n in names), names
+    rng = np.random.default_rng(4)
+    for p in rng.choice(len(pq), 16, replace=False):
+        q, t = seqs[pq[p]], seqs[pt[p]]
+        F, fq, ft = O.fill(q, t, po.FWD, True, fast=True)
+        R, rq, rt = O.fill(q, t, po.REV, True, fast=True)
+        assert out["fwd_score"][p] == F[-1, -1] and out["rev_score"][p] == R[0, 0]
+        got = ctx.fetch_pair(int(p), len(q), len(t), fwd=True, rev=True, mask=False)
+        assert_matrix_equal("F", got["score_fwd"], F)
+        assert_matrix_equal("R", got["score_rev"], R)
+        assert_matrix_equal("fq", got["prevq_fwd"], fq)
+        assert_matrix_equal("ft", got["prevt_fwd"], ft)
+        assert_matrix_equal("rq", got["prevq_rev"], rq)
+        assert_matrix_equal("rt", got["prevt_rev"], rt)
+        for d, (S, sq, st) in ((a.FWD, (F, fq, ft)), (a.REV, (R, rq, rt))):
+            rc, pairs, sc = ctx.optimal(int(p), d, len(q), len(t))
+            orc, opairs, osc = O.optimal(S, sq, st, po.FWD if d == a.FWD else po.REV)
+            assert rc == orc == 0 and sc == osc
+            assert_matrix_equal("local optimal", pairs, opairs)
+    # every pair: the int32 kernels (packed path off) give the same final scores; score-only variant as well
+    ctx.set_option("packed", 0)
+    ref = ctx.fill_batch(res, off, pq, pt, what)
+    ctx.set_option("packed", 1)
+    so = ctx.fill_batch(res, off, pq, pt, a.W_FWD | a.W_REV)
+    for k in ("fwd_score", "rev_score"):
+        assert_matrix_equal("int32 " + k, out[k], ref[k])
+        assert_matrix_equal("score-only " + k, out[k], so[k])
+
+
 def test_score_only_batch_equals_full_batch(ctx):
     # the score-only kernels (DPX viaddmax/vimax3 path) and the traceback kernels agree
     import alignment_algos_b200 as a
