@@ -206,16 +206,62 @@ struct aadp_ctx {
   }
 };
 
+// cudaFuncSetAttribute and the occupancy query are made ONCE per (device, kernel, size) and cached.  Measured on B200
+// (AADP_TIMING marks, two contexts on two host threads): cudaFuncSetAttribute on a kernel that is RUNNING -- launched by
+// another context of the process -- blocks the calling host thread until that kernel has finished, 10-13 ms per C3 step,
+// which serialised the host scheduling of one context behind the GPU work of the other.
+#include <map>
+#include <tuple>
+static std::mutex g_attr_mu;
+static std::map<std::pair<int, const void*>, size_t> g_attr_smem;
+static std::map<std::tuple<int, const void*, int, size_t>, int> g_attr_occ;
+static cudaError_t cached_max_smem(const void* f, size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  auto it = g_attr_smem.find({dev, f});
+  if (it != g_attr_smem.end() && it->second >= smem) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) g_attr_smem[{dev, f}] = smem;
+  return e;
+}
+static cudaError_t cached_occupancy(int* occ, const void* f, int threads, size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_attr_mu);
+  const auto key = std::make_tuple(dev, f, threads, smem);
+  auto it = g_attr_occ.find(key);
+  if (it != g_attr_occ.end()) { *occ = it->second; return cudaSuccess; }
+  const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, f, threads, smem);
+  if (e == cudaSuccess) g_attr_occ[key] = *occ;
+  return e;
+}
+
 namespace {
+
+// AADP_TIMING=1: host-side time marks of one aadp_fill_batch call (diagnostics of the end-to-end pipeline)
+struct TimeMarks {
+  bool on = false;
+  std::chrono::steady_clock::time_point t0;
+  std::string log;
+  void start() { on = getenv("AADP_TIMING") != nullptr; t0 = std::chrono::steady_clock::now(); log.clear(); }
+  void mark(const char* what) {
+    if (!on) return;
+    char b[96];
+    snprintf(b, sizeof b, " %s %.2f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    log += b;
+  }
+};
+thread_local TimeMarks g_marks;
 
 template <int K, int TBM, int STM>
 int launch_fill_t(aadp_ctx* c, FillParams& P) {
   auto kern = fill_kernel<K, TBM, STM>;
   const int A = P.sc.A;
   const size_t smem = (size_t)((A * A + 15) / 16 * 16) + (size_t)kWarpsPerCta * (kQRing + A * 32 * K);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cached_max_smem((const void*)kern, (size_t)(smem)));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
+  CK(cached_occupancy(&occ, (const void*)kern, kWarpsPerCta * 32, smem));
   if (occ < 1) return fail("fill kernel does not fit on an SM");
   int grid = c->num_sms * occ;
   const int need = (P.n_items + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -278,9 +324,9 @@ int launch_packed_t(aadp_ctx* c, PackedParams& P) {
     int pf = 0, pr = 0;
     if (sscanf(e, "%d,%d", &pf, &pr) >= 1) smem += (size_t)(P.rev ? pr : pf);
   }
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cached_max_smem((const void*)kern, (size_t)(smem)));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
+  CK(cached_occupancy(&occ, (const void*)kern, kPackedWarps * 32, smem));
   if (occ < 1) return fail("packed kernel does not fit on an SM");
   int grid = c->num_sms * occ;
   const int need = (P.n_tasks + kPackedWarps - 1) / kPackedWarps;
@@ -327,9 +373,9 @@ static size_t wave_smem_bytes(int A) {
 static int wave_resident_ctas(aadp_ctx* c, int A) {
   auto kern = wave_kernel<kWaveK, 1, 2>;  // the largest variant
   const size_t smem = wave_smem_bytes(A);
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  if (cached_max_smem((const void*)kern, smem) != cudaSuccess) return 0;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem) != cudaSuccess) return 0;
+  if (cached_occupancy(&occ, (const void*)kern, 32, smem) != cudaSuccess) return 0;
   return occ * c->num_sms;
 }
 
@@ -338,9 +384,9 @@ int launch_wave_t(aadp_ctx* c, FillParams& Pf, FillParams& Pr, int ndirs, int ns
   auto kern = wave_kernel<kWaveK, TBM, STM>;
   const int A = Pf.sc.A;
   const size_t smem = wave_smem_bytes(A);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cached_max_smem((const void*)kern, (size_t)(smem)));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, smem));
+  CK(cached_occupancy(&occ, (const void*)kern, 32, smem));
   const int grid = ndirs * nst;
   if (occ < 1 || grid > occ * c->num_sms) return fail("wavefront kernel: stripes of this pair cannot all be resident");
   char nm[64];
@@ -1307,6 +1353,7 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
   }
   b.sched_ok = false;
   if (build_batch_meta(c, what)) return 1;
+  g_marks.mark("meta");
   b.uploaded_what = what;
   b.ran_what = 0;
   if (upload_vec(c, c->fmt, b.fmt)) return 1;
@@ -1326,6 +1373,7 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
     int32_t* tasks_pinned = nullptr;
     int64_t nt = 0;
     if (build_task_chunk(c, lo, std::min(hi, npairs), &tasks_pinned, &nt)) return 1;
+    g_marks.mark("tasks");
     const size_t bytes = (size_t)nt * 64 * sizeof(int32_t);
     if (bytes)
       CK(cudaMemcpyAsync(c->tasks.as<int32_t>() + b.chunk_first[(size_t)k] * 64, tasks_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -1441,9 +1489,9 @@ int aadp_cross_run(aadp_ctx* c, const int32_t* q_ids, int64_t nq, const int32_t*
     auto kern = packed_kernel<0, 0, 0, 1>;
     const int A = c->sc.A;
     const size_t smem = packed_smem_bytes(A, 0, 1);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cached_max_smem((const void*)kern, (size_t)(smem)));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackedWarps * 32, smem));
+    CK(cached_occupancy(&occ, (const void*)kern, kPackedWarps * 32, smem));
     if (occ < 1) return fail("packed kernel does not fit on an SM");
     const int64_t resident = (int64_t)c->num_sms * occ;
     // query couples per item: reuse the template profile as often as possible while keeping >= 8 items per warp
@@ -1674,20 +1722,20 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   if (use_rec) {
     const size_t rsm = frec_smem_bytes(rec_cap);
     if (tb) {
-      CK(cudaFuncSetAttribute(frec_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      CK(cached_max_smem((const void*)frec_fill_kernel<1>, (size_t)(rsm)));
       frec_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
     } else {
-      CK(cudaFuncSetAttribute(frec_fill_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+      CK(cached_max_smem((const void*)frec_fill_kernel<0>, (size_t)(rsm)));
       frec_fill_kernel<0><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
     }
   } else if (tab) {
-    CK(cudaFuncSetAttribute(general_fill_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    CK(cached_max_smem((const void*)general_fill_kernel<1, 1>, (size_t)(std::max<size_t>(smem, 1024))));
     general_fill_kernel<1, 1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
   } else if (tb) {
-    CK(cudaFuncSetAttribute(general_fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    CK(cached_max_smem((const void*)general_fill_kernel<1>, (size_t)(std::max<size_t>(smem, 1024))));
     general_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
   } else {
-    CK(cudaFuncSetAttribute(general_fill_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    CK(cached_max_smem((const void*)general_fill_kernel<0>, (size_t)(std::max<size_t>(smem, 1024))));
     general_fill_kernel<0><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);
   }
   c->prof_end();
@@ -1950,12 +1998,16 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     c->h2d_bytes = 0;
     c->d2h_bytes = 0;
     b.piece_waited = 0;
+    g_marks.start();
     if (upload_sequences_impl(c, residues, seq_off, nseq, 2 * c->pipeline_chunks)) return 1;
+    g_marks.mark("seq");
     t_seq = ms_since();
     const std::function<int(size_t)> on_chunk = [&](size_t k) -> int {
       if (k == 0 && run_prepare(c, what)) return 1;
+      g_marks.mark("prep");
       if (wait_for_sequences(c, b.chunk_max_seq[k])) return 1;  // only the residue pieces this chunk references
       const int rc = launch_packed_chunk(c, 0, what, delta_ratio, dt, dc, k);
+      g_marks.mark("launch");
       if (k < 8) t_chunk[k] = ms_since();
       return rc;
     };
@@ -1963,13 +2015,16 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     if (wait_for_sequences(c, nseq)) return 1;  // everything that follows may read any sequence
     // the residue validation flag came back long ago (it was queued right after the arena kernel); the int32 and
     // wavefront kernels read the raw residues, so they are only launched on validated input
+    g_marks.mark("sched");
     CK(cudaEventSynchronize(c->ev_flag));
+    g_marks.mark("flag");
     if (*c->pin_flag) {
       CK(cudaStreamSynchronize(c->stream));
       b.have_seqs = false;
       return fail("residue code outside the substitution alphabet");
     }
     if (run_batch_impl(c, what, delta_ratio, df, dr, dt, dc, true)) return 1;
+    g_marks.mark("all");
     t_launched = ms_since();
   }
   if (npairs) {
@@ -1982,6 +2037,7 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
   if (timing && pipelined)
     fprintf(stderr, "[aadp] fill_batch host timeline (ms): sequences enqueued %.2f, fwd chunk launches %.2f %.2f %.2f, all launched %.2f, done %.2f\n",
             t_seq, t_chunk[0], t_chunk[1], t_chunk[2], t_launched, ms_since());
+  if (timing && pipelined) fprintf(stderr, "[aadp] marks:%s\n", g_marks.log.c_str());
   return 0;
 }
 

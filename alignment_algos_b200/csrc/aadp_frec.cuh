@@ -1,7 +1,7 @@
 // aadp_frec.cuh -- exact general-gap fp32 fill with RECORD LISTS for sm_100a: the reference's default scoring
 // (4.73 / 0.34, alib.cpp:17-18) and any other scoring off the dyadic grid, at a cost per cell that does not grow
 // with the length of the reference's scans (dpmatrix.h:459-480).  Same results as aadp_general.cuh's literal scans,
-// bit for bit (scores, every DPCell predecessor); CPU model of the same decisions: oracle/aadp_oracle.c orc_fill_rec.
+// bit for bit (scores, every DPCell predecessor); a CPU model of the same decisions (orc_fill_rec) is part of the test suite.
 //
 // Idea.  In real arithmetic the order of the deletion candidates k of a cell (a,b) does not depend on b:
 //     D[a-1][k] - gi - ge*(b-k-2) = (D[a-1][k] + ge*k) - const(b),          KEY(k) = D[a-1][k] + ge*k,
@@ -15,7 +15,7 @@
 //     backwards, the walk ends at the first record below max - 2*MU (everything before it is below max - MU);
 //   * every visited record is evaluated with the reference's own three fp32 operations and the first maximum
 //     (smallest k) is kept -- what the ascending strict-'>' scan does.
-// Visited records per cell and scan: 1.0-1.4 on average (oracle/aadp_oracle.c statistics), against (m+n)/2 candidates.
+// Visited records per cell and scan: 1.0-1.4 on average (statistics of the CPU model), against (m+n)/2 candidates.
 // MU = 2^-19 * (max|D| so far + |pen(maxlen)| + |ge|*maxlen + max|sim| + 1): eight times the sum of the error bounds
 // of the key (one rounding each for ge*k and the sum), of pen (two roundings) and of the candidate's two roundings.
 //

@@ -65,3 +65,25 @@ def test_submatrix_reader_matches_reference_format(tmp_path):
     assert alpha == "ACGT" and m.shape == (4, 4) and m[3, 3] == 1.5 and m[0, 1] == -1
     a20, b = blosum62()
     assert len(a20) == 20 and b[a20.index("W"), a20.index("W")] == 11 and (b == b.T).all()
+
+
+def test_driver_scripts_have_no_undefined_names():
+    # bench.py and __graft_entry__.py only run on the GPU box; a name that exists nowhere (a refactoring slip) must be
+    # caught here, on the CPU
+    import builtins
+    import symtable
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for fn in ("bench.py", "__graft_entry__.py"):
+        st = symtable.symtable(open(os.path.join(root, fn)).read(), fn, "exec")
+        mod_names = {s.get_name() for s in st.get_symbols()}
+        bad = []
+
+        def walk(t):
+            for ch in t.get_children():
+                for s in ch.get_symbols():
+                    n = s.get_name()
+                    if s.is_global() and s.is_referenced() and n not in mod_names and not hasattr(builtins, n):
+                        bad.append((ch.get_name(), n))
+                walk(ch)
+        walk(st)
+        assert not bad, "%s: undefined names %s" % (fn, bad)

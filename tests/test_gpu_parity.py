@@ -154,7 +154,7 @@ def test_batch_matches_oracle_and_properties(ctx):
                 assert_matrix_equal("optimal rev", pairs, opairs)
 
 
-def test_packed_local_batch_vs_oracle(ctx):
+def test_packed_local_batch_vs_oracle():
     # LOCAL alignments on the packed int16x2 kernels (LOC = 1: every candidate clamped at 0, dpmatrix.h:538-689 / 879-1030):
     # a batch of random and related pairs; final scores of every pair against the int32 kernels, full score and
     # predecessor matrices of a sample against the oracle, local optimal alignments (find_max + enumerate_local)
@@ -163,6 +163,7 @@ def test_packed_local_batch_vs_oracle(ctx):
     alpha20, M20 = a.blosum62()
     seqs, pq, pt = synth.pair_workload(79, 500, 20, 512)
     res, off = a.Context.pack(seqs)
+    ctx = a.Context(0)
     ctx.set_scoring(M20, 12, 1, po.LOCAL)
     O = po.Oracle(M20, 12, 1, po.LOCAL)
     what = a.W_FWD | a.W_REV | a.W_TB | a.W_SCORES
@@ -197,6 +198,7 @@ def test_packed_local_batch_vs_oracle(ctx):
     for k in ("fwd_score", "rev_score"):
         assert_matrix_equal("int32 " + k, out[k], ref[k])
         assert_matrix_equal("score-only " + k, out[k], so[k])
+    ctx.close()
 
 
 def test_score_only_batch_equals_full_batch(ctx):
