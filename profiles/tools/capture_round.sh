@@ -6,7 +6,7 @@
 TAG=${1:-rXX}
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests -x -q -m gpu --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/${TAG}_pytest_gpu.log
+if [ -z "$SKIP_PYTEST" ]; then python -m pytest tests -x -q -m gpu --durations=15 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/${TAG}_pytest_gpu.log; fi
 python bench.py > $O/${TAG}_bench_default.json 2>$O/${TAG}_bench_default.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2>$O/${TAG}_bench_reference.err; echo "ref rc=$?"
 for w in c2 c4 c5 c3f; do

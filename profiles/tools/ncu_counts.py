@@ -33,7 +33,8 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[0]
     col = {h: i for i, h in enumerate(hdr)}
-    out = {"source": "profiles/%s (ncu --set full of bench.py --pairs %d, %s)" % (os.path.basename(args.rep), args.pairs, args.tag),
+    out = {"source": "%s (ncu --set full of bench.py --pairs %d, %s; summary committed as profiles/%s_ncu_full_packed_kernels.txt)"
+                     % (os.path.basename(args.rep), args.pairs, args.tag, args.tag),
            "cell_updates_per_launch": cu, "kernels": {}}
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
