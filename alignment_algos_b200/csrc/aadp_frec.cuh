@@ -40,10 +40,10 @@ namespace aadp {
 // template of the launch (frec_cap): lane l keeps its K columns at l*Kp .. l*Kp+K-1 with Kp = K | 1, an ODD stride, so
 // that the 32 lanes of every access fall into 32 different banks (a stride of K = 16 words was a 16-way conflict).
 __host__ __device__ inline int frec_cap(int max_nt) { return 32 * (((max_nt + 31) / 32) | 1) + 8; }
-__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 6 + 2 * 3 + 1) + 16 + 64 * 20; }
+__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 6 + 2 * 3 + 1) + 16 + 64 * 8; }
 
 // a cell waiting for the record chain of its column (see the row loop)
-struct __align__(4) FrecDeferred { float os, simc, lim; short b, klast, ob, pad; };
+struct __align__(4) FrecDeferred { float run; short b, ri; };
 
 __device__ __forceinline__ float frec_key(float d, float ge, int k) { return __fadd_rn(d, __fmul_rn(ge, (float)k)); }
 
@@ -206,20 +206,36 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
   for (int a = 2; a <= nq; ++a) {
     const float mu = __fmul_rn(__fadd_rn(dmax, wconst), 1.0f / 524288.0f);
     const float mu2 = __fmul_rn(2.0f, mu);
-    // ---- records of row a-1: lane-local key maximum, exclusive prefix over the lanes, record segments
-    float m = NEGK;
-    for (int k = k0, p = p0; k <= k1; ++k, ++p) m = fmaxf(m, frec_key(cur[p], ge, k));
-    float inc = m;
+    // ---- row a-1, seen from the deletion scans of row a: per lane the LEADER of its key columns (largest key,
+    // smallest column on ties), the runner-up key; exclusive prefix of that summary over the lanes
+    float lk1 = NEGK, ld1 = 0.f, lk2 = NEGK;
+    int lc1 = 0;
+    for (int k = k0, p = p0; k <= k1; ++k, ++p) {
+      const float d = cur[p];
+      const float key = frec_key(d, ge, k);
+      if (key > lk1) { lk2 = lk1; lk1 = key; ld1 = d; lc1 = k; }
+      else lk2 = fmaxf(lk2, key);
+    }
+    float ik1 = lk1, id1 = ld1, ik2 = lk2;  // inclusive scan: (earlier prefix) merged with (this lane)
+    int ic1 = lc1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const float u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc = fmaxf(inc, u);
+      const float uk1 = __shfl_up_sync(0xffffffffu, ik1, o), ud1 = __shfl_up_sync(0xffffffffu, id1, o);
+      const float uk2 = __shfl_up_sync(0xffffffffu, ik2, o);
+      const int uc1 = __shfl_up_sync(0xffffffffu, ic1, o);
+      if (lane >= o) {
+        if (ik1 > uk1) { ik2 = fmaxf(uk1, ik2); }                       // the later block keeps the lead
+        else { ik2 = fmaxf(uk2, ik1); ik1 = uk1; id1 = ud1; ic1 = uc1; }  // ties: the earlier column leads
+      }
     }
-    float pre = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) pre = NEGK;
+    float ek1 = __shfl_up_sync(0xffffffffu, ik1, 1), ed1 = __shfl_up_sync(0xffffffffu, id1, 1);
+    float ek2 = __shfl_up_sync(0xffffffffu, ik2, 1);
+    int ec1 = __shfl_up_sync(0xffffffffu, ic1, 1);
+    if (lane == 0) { ek1 = NEGK; ed1 = 0.f; ek2 = NEGK; ec1 = 0; }
+    const float pre = ek1;
     // records of this lane's columns (a bit mask: K <= 32 per lane is guaranteed by the host), their number before
     // this lane (exclusive prefix sum), and the list itself: ONE ascending list for the row, so that a walk is a
-    // plain descending index
+    // plain descending index.  Only the slow path (below) reads it.
     unsigned recmask = 0;
     {
       float run = pre;
@@ -245,39 +261,95 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
     const float* srow = simrow(a);
     const int ra = rowof(a);
     const int64_t rowbase = (int64_t)(ra - r0) * ld - c0;
+    const int64_t lkbase = (int64_t)(rowof(a - 1) - r0) * ld - c0;  // row a-1 of the link matrix
     float rowabs = 0.f;
-    // A cell whose column has three or more leaders within the noise needs the column's record chain from HBM (a chain
-    // of dependent loads).  Such cells are not finished in place: they are queued, and the queue is worked off by all
-    // lanes at once -- one queued cell per lane -- so the warp pays one chain latency per 32 such cells, not one per
-    // loop iteration.
-    auto finish = [&](int bq, int oa, int ob, float os) {
+    auto finish = [&](int bq, int pb, int oa, int ob, float os) {
       if (TBM) {
         const int64_t o = rowbase + colof(bq);
         PQ[o] = rowof(oa);
         PT[o] = colof(ob);
       }
-      nxt[ph(bq)] = os;
+      nxt[pb] = os;
       rowabs = fmaxf(rowabs, fabsf(os));
+    };
+    // column b-1 receives the candidate of row a-1 (used from row a+1 on)
+    auto column_update = [&](int c, int pc, float dc, float key1, float key2, float key3, float d1, int kk1) {
+      const int kc = a - 1;
+      const float kk = frec_key(dc, ge, kc);
+      if (kk >= __fsub_rn(key1, mu)) { LK[lkbase + colof(c)] = (int)clast[pc]; clast[pc] = (short)kc; }
+      if (kk > key1) { ckey3[pc] = key2; cD2[pc] = d1; ck2[pc] = (short)kk1; cD1[pc] = dc; ck1[pc] = (short)kc; }
+      else if (kk > key2) { ckey3[pc] = key2; cD2[pc] = dc; ck2[pc] = (short)kc; }
+      else if (kk > key3) ckey3[pc] = kk;
+    };
+    // SLOW PATH: a cell whose deletion scan has two or more leaders within the noise, or whose insertion scan has three
+    // or more.  Such cells (6-14 %) are queued and worked off by all lanes at once, one queued cell per lane: the record
+    // walks -- through the row's list in shared memory, through the column's chain in HBM -- then cost the warp one walk
+    // latency per 32 cells instead of one per loop iteration, and the common case stays free of them.
+    auto slow_cell = [&](int bq, float run, int ri) {
+      const int pb = ph(bq), pc = ph(bq - 1);
+      const float simc = simat(srow, bq, pb);
+      const float dc = cur[pc];
+      int oa = a - 1, ob = bq - 1;
+      float os = clampl(__fadd_rn(dc, simc));
+      if (bq >= 3) {  // deletions (dpmatrix.h:459-468): records of row a-1 among 1..b-2, last one first
+        const float lim = __fsub_rn(run, mu2);
+        float bs = 0.f;
+        int bk = 0;
+        int i = ri;
+        if (i >= 0) {
+          uint32_t e = rl[i];
+          float d = cur[e >> 16];
+          for (;;) {
+            // the next record is fetched before this one is evaluated (its key ends the walk)
+            const int kr = (int)(e & 0xffffu);
+            --i;
+            uint32_t en = 0;
+            float dn = 0.f;
+            if (i >= 0) { en = rl[i]; dn = cur[en >> 16]; }
+            if (frec_key(d, ge, kr) < lim) break;
+            const float sv = clampl(__fadd_rn(__fsub_rn(d, gg_pen(gi, ge, bq - kr - 1)), simc));
+            if (bk == 0 || sv >= bs) { bs = sv; bk = kr; }
+            if (i < 0) break;
+            e = en;
+            d = dn;
+          }
+        }
+        if (bk && bs > os) { ob = bk; os = bs; }
+      }
+      const int kk1 = (int)ck1[pc], kk2 = (int)ck2[pc];
+      const float d1 = cD1[pc], d2 = cD2[pc], key3 = ckey3[pc];
+      const float key1 = kk1 ? frec_key(d1, ge, kk1) : NEGK, key2 = kk2 ? frec_key(d2, ge, kk2) : NEGK;
+      if (a >= 3) {  // insertions (dpmatrix.h:471-480): candidate rows 1..a-2 of column b-1
+        const float lim = __fsub_rn(key1, mu2);
+        float bs = 0.f;
+        int bk = 0;
+        if (FREC_EXP_NOWALK || key3 < lim) {  // at most two candidates can win: both are at hand
+          bk = kk1;
+          bs = clampl(__fadd_rn(__fsub_rn(d1, gg_pen(gi, ge, a - kk1 - 1)), simc));
+          if (kk2 && key2 >= lim) {
+            const float s2 = clampl(__fadd_rn(__fsub_rn(d2, gg_pen(gi, ge, a - kk2 - 1)), simc));
+            if (s2 > bs || (s2 == bs && kk2 < kk1)) { bs = s2; bk = kk2; }
+          }
+        } else {  // three or more within the noise: the record chain of the column (dense link matrix in HBM)
+          for (int k = (int)clast[pc]; k > 0;) {
+            const int64_t o = at(k, bq - 1);
+            const float d = D[o];
+            const int kn = LK[o];
+            if (frec_key(d, ge, k) < lim) break;
+            const float sv = clampl(__fadd_rn(__fsub_rn(d, gg_pen(gi, ge, a - k - 1)), simc));
+            if (bk == 0 || sv >= bs) { bs = sv; bk = k; }
+            k = kn;
+          }
+        }
+        if (bk && bs > os) { oa = bk; ob = bq - 1; os = bs; }
+      }
+      finish(bq, pb, oa, ob, os);
+      column_update(bq - 1, pc, dc, key1, key2, key3, d1, kk1);
     };
     auto flush = [&](int n) {  // the first n (<= 32) queued cells
       if (lane < n) {
         const FrecDeferred e = dq[lane];
-        const int bq = (int)e.b, c = bq - 1;
-        float bs = 0.f;
-        int bk = 0;
-        for (int k = (int)e.klast; k > 0;) {
-          const int64_t o = at(k, c);
-          const float d = D[o];
-          const int kn = LK[o];
-          if (frec_key(d, ge, k) < e.lim) break;
-          const float sv = clampl(__fadd_rn(__fsub_rn(d, gg_pen(gi, ge, a - k - 1)), e.simc));
-          if (bk == 0 || sv >= bs) { bs = sv; bk = k; }
-          k = kn;
-        }
-        int oa = a - 1, ob = (int)e.ob;
-        float os = e.os;
-        if (bk && bs > os) { oa = bk; ob = bq - 1; os = bs; }
-        finish(bq, oa, ob, os);
+        slow_cell((int)e.b, e.run, (int)e.ri);
       }
       __syncwarp();
     };
@@ -291,85 +363,67 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
       nxt[0] = sv;
       rowabs = fmaxf(rowabs, fabsf(sv));
     }
-    float run = pre;
+    // FAST PATH: running leader of the keys 1..k (from the exclusive prefix on), one candidate per scan class
+    float rk1 = ek1, rd1 = ed1, rk2 = ek2;
+    int rc1 = ec1;
     int ri = rbase - 1;  // index of the last record among 1..k
     for (int j = 0; j < K; ++j) {  // the same trip count for every lane: the queue is filled with warp votes
       const int k = k0 + j, p = p0 + j;
-      int bcell = 0;
+      int bq = 0;
       if (k <= k1) {
-        run = fmaxf(run, frec_key(cur[p], ge, k));
+        const float d = cur[p];
+        const float key = frec_key(d, ge, k);
+        if (key > rk1) { rk2 = rk1; rk1 = key; rd1 = d; rc1 = k; }
+        else rk2 = fmaxf(rk2, key);
         ri += (recmask >> j) & 1u;
-        bcell = k + 2;
+        bq = k + 2;
         // the lane that owns key column nt has no cell of its own there: it takes the first interior cell, b = 2
-        if (bcell > nt) bcell = (k == nt && nt >= 2) ? 2 : 0;
+        if (bq > nt) bq = (k == nt && nt >= 2) ? 2 : 0;
       }
       bool defer = false;
-      FrecDeferred de;
-      if (bcell) {
-        const int bq = bcell;
-        const int pb = ph(bq), pc = ph(bq - 1);
-        const float simc = simat(srow, bq, pb);
-        const float dc = cur[pc];  // D[a-1][b-1]: the match predecessor, and the new candidate of column b-1
-        int oa = a - 1, ob = bq - 1;
-        float os = clampl(__fadd_rn(dc, simc));
-        if (bq >= 3) {  // deletions (dpmatrix.h:459-468): records of row a-1 among 1..b-2, last one first
-          const float lim = __fsub_rn(run, mu2);
-          float bs = 0.f;
-          int bk = 0;
-          int i = ri;
-          if (i >= 0) {
-            uint32_t e = rl[i];
-            float d = cur[e >> 16];
-            for (;;) {
-              // the next record is fetched before this one is evaluated (its key ends the walk)
-              const int kr = (int)(e & 0xffffu);
-              --i;
-              uint32_t en = 0;
-              float dn = 0.f;
-              if (i >= 0) { en = rl[i]; dn = cur[en >> 16]; }
-              if (frec_key(d, ge, kr) < lim) break;
-              const float sv = clampl(__fadd_rn(__fsub_rn(d, gg_pen(gi, ge, bq - kr - 1)), simc));
-              if (bk == 0 || sv >= bs) { bs = sv; bk = kr; }
-              if (i < 0) break;
-              e = en;
-              d = dn;
-            }
-          }
-          if (bk && bs > os) { ob = bk; os = bs; }
-        }
-        // column b-1: leader, runner-up, third-best key
+      if (bq) {
+        // padded positions of columns b and b-1 (pad is non-zero for even K only; then b and b-1 lie at most one lane
+        // segment to the right of key column k)
+        const bool first = bq == 2;
+        const int pb = first ? 1 : (bq - 1) + pad * (lane + (j + 2 >= K ? 1 : 0));
+        const int pc = first ? 0 : (bq - 2) + pad * (lane + (j + 1 >= K ? 1 : 0));
         const int kk1 = (int)ck1[pc], kk2 = (int)ck2[pc];
         const float d1 = cD1[pc], d2 = cD2[pc], key3 = ckey3[pc];
         const float key1 = kk1 ? frec_key(d1, ge, kk1) : NEGK, key2 = kk2 ? frec_key(d2, ge, kk2) : NEGK;
-        if (a >= 3) {  // insertions (dpmatrix.h:471-480): candidate rows 1..a-2 of column b-1
-          const float lim = __fsub_rn(key1, mu2);
-          if (FREC_EXP_NOWALK || key3 < lim) {  // at most two candidates can win: both are at hand
+        const float climit = __fsub_rn(key1, mu2);
+        const bool row_clear = first || rk2 < __fsub_rn(rk1, mu2);
+        const bool col_clear = a < 3 || FREC_EXP_NOWALK || key3 < climit;
+        if (row_clear && col_clear) {
+          const float simc = simat(srow, bq, pb);
+          const float dc = cur[pc];  // D[a-1][b-1]: the match predecessor, and the new candidate of column b-1
+          int oa = a - 1, ob = bq - 1;
+          float os = clampl(__fadd_rn(dc, simc));
+          if (!first) {  // deletions (dpmatrix.h:459-468): the one leader of row a-1 among 1..b-2
+            const float sv = clampl(__fadd_rn(__fsub_rn(rd1, gg_pen(gi, ge, bq - rc1 - 1)), simc));
+            if (sv > os) { ob = rc1; os = sv; }
+          }
+          if (a >= 3) {  // insertions (dpmatrix.h:471-480): leader and runner-up of column b-1
             int bk = kk1;
             float bs = clampl(__fadd_rn(__fsub_rn(d1, gg_pen(gi, ge, a - kk1 - 1)), simc));
-            if (kk2 && key2 >= lim) {
+            if (kk2 && key2 >= climit) {
               const float s2 = clampl(__fadd_rn(__fsub_rn(d2, gg_pen(gi, ge, a - kk2 - 1)), simc));
               if (s2 > bs || (s2 == bs && kk2 < kk1)) { bs = s2; bk = kk2; }
             }
             if (bs > os) { oa = bk; ob = bq - 1; os = bs; }
-          } else {  // three or more within the noise: the record chain of the column, deferred
-            defer = true;
-            de.os = os; de.simc = simc; de.lim = lim;
-            de.b = (short)bq; de.klast = clast[pc]; de.ob = (short)ob; de.pad = 0;
           }
-        }
-        if (!defer) finish(bq, oa, ob, os);
-        {  // column b-1 receives the candidate of row a-1 (used from row a+1 on)
-          const int kc = a - 1;
-          const float kk = frec_key(dc, ge, kc);
-          if (kk >= __fsub_rn(key1, mu)) { LK[at(kc, bq - 1)] = (int)clast[pc]; clast[pc] = (short)kc; }
-          if (kk > key1) { ckey3[pc] = key2; cD2[pc] = d1; ck2[pc] = (short)kk1; cD1[pc] = dc; ck1[pc] = (short)kc; }
-          else if (kk > key2) { ckey3[pc] = key2; cD2[pc] = dc; ck2[pc] = (short)kc; }
-          else if (kk > key3) ckey3[pc] = kk;
+          finish(bq, pb, oa, ob, os);
+          column_update(bq - 1, pc, dc, key1, key2, key3, d1, kk1);
+        } else {
+          defer = true;
         }
       }
       const unsigned dm = __ballot_sync(0xffffffffu, defer);
       if (dm) {
-        if (defer) dq[qn + __popc(dm & ((1u << lane) - 1u))] = de;
+        if (defer) {
+          FrecDeferred de;
+          de.run = rk1; de.b = (short)bq; de.ri = (short)ri;
+          dq[qn + __popc(dm & ((1u << lane) - 1u))] = de;
+        }
         qn += __popc(dm);
         __syncwarp();
         if (qn >= 32) {
