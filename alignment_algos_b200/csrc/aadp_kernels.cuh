@@ -636,6 +636,10 @@ __device__ __forceinline__ float nearopt_threshold(float opt, float delta_ratio)
   return fminf(thr, alt);
 }
 
+#ifndef AADP_MASK_U
+#define AADP_MASK_U 4
+#endif
+constexpr int kMaskU = AADP_MASK_U;  // 32-column groups a warp loads before it uses any (bytes in flight per thread)
 __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
   const int pair = P.only_pair >= 0 ? P.only_pair : blockIdx.x;
   if (P.fmt[pair] != P.want_fmt) return;
@@ -660,11 +664,11 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
   for (int i = i_lo; i <= i_hi; ++i) {
     const int qa = P.residues[qo + i - 1];
     const int8_t* subrow = P.sub8 + qa * A;
-    // 128 columns per iteration: the loads of four 32-column groups are issued before any of them is used
-    for (int j0 = 128 * warp; j0 < Lt; j0 += 128 * nw) {
-      bool on[4];
+    // kMaskU*32 columns per iteration: the loads of kMaskU 32-column groups are issued before any of them is used
+    for (int j0 = 32 * kMaskU * warp; j0 < Lt; j0 += 32 * kMaskU * nw) {
+      bool on[kMaskU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kMaskU; ++u) {
         const int j = j0 + 32 * u + lane + 1;
         on[u] = false;
         if (j <= Lt) {
@@ -681,11 +685,11 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
       }
       uint32_t mine = 0;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kMaskU; ++u) {
         const uint32_t bits = __ballot_sync(0xffffffffu, on[u]);
         if (lane == u) mine = bits;
       }
-      if (lane < 4 && j0 + 32 * lane < Lt) { mk[(int64_t)(i - 1) * mws + (j0 >> 5) + lane] = mine; cnt += __popc(mine); }
+      if (lane < kMaskU && j0 + 32 * lane < Lt) { mk[(int64_t)(i - 1) * mws + (j0 >> 5) + lane] = mine; cnt += __popc(mine); }
     }
   }
   if (P.count) {

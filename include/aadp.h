@@ -69,12 +69,16 @@ const char* aadp_version(void);
 int aadp_set_stream(aadp_ctx* ctx, void* cuda_stream);
 int aadp_synchronize(aadp_ctx* ctx);
 /* Tuning / test switches. "packed" (default 1): use the packed int16x2 kernels for every pair that
- * qualifies (non-local, Lt <= 512, |score| bound < 7000 units); 0 forces the int32 kernels.
+ * qualifies (Lt <= 512, |score| bound < 7000 units; local alignments unless the run asks for the near-optimal
+ * cell set); 0 forces the int32 kernels.
  * "wave" / "wave_min_cells": multi-CTA wavefront for long pairs.  "host_threads": host scheduler
  * threads (0 = min(hardware, 8)).  "exact_float": see aadp_set_scoring.  "general_budget_mcells":
  * scratch budget (10^6 dense cells per direction) of one chunk of an exact-float batch.  "general_prune" (default 1):
  * pruned candidate scans in the exact general-gap kernel (identical results; 0 = scan every candidate).
- * "general_threads" (default 256): CTA size limit of that kernel.                                        */
+ * "general_threads" (default 256): CTA size limit of that kernel.  "general_records" (default 1): the record-list
+ * kernel for affine gaps in exact-float mode (identical results at a cost per cell that does not grow with the
+ * reference's scans; 0 = the scan kernel).  "ucw_user_limit" / "cw_user_limit": alignment limits of the
+ * enumerators (<= 0 restores the reference's 100000 / 1000000).                                          */
 int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
 
 /* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)
@@ -84,8 +88,9 @@ int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
  *   - sub, gi, ge on one dyadic grid (multiples of 2^-s, s<=8; integer matrices trivially are): the
  *     fast O(Lq*Lt) integer kernels (packed int16x2 / int32 / multi-CTA wavefront);
  *   - anything else (e.g. the reference defaults 4.73 / 0.34, alib.cpp:17-18): the exact general-gap
- *     fp32 kernel, which performs the reference's own O(Lq*Lt*(Lq+Lt)) scan (dpmatrix.h:459-480) with
- *     the same fp32 operations in the same order.  In this mode batches return per-pair scalars,
+ *     fp32 path: every candidate of the reference's scans (dpmatrix.h:459-480) that can win is evaluated
+ *     with the same fp32 operations in the same order and the first maximum in scan order is kept
+ *     (record-list kernel for affine gaps, literal scans otherwise).  In this mode batches return per-pair scalars,
  *     aadp_batch_fetch_pair / aadp_batch_optimal recompute the requested pair, and no packed
  *     traceback is kept.  aadp_set_option("exact_float", 1) forces this class for any scoring.      */
 int aadp_set_scoring(aadp_ctx* ctx, const float* sub, int A, float gi, float ge, int align_type,
