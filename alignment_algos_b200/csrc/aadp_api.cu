@@ -1626,7 +1626,7 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   // record-list kernel (aadp_frec.cuh): affine gaps only; one warp per (pair, direction), rows and column leaders in
   // shared memory, 16-bit row/column indices
   const int rec_cap = frec_cap(maxLt);
-  const bool use_rec = c->gg_records && !(ov && ov->d_del) && maxL < 32000 && maxLt <= 1024 && frec_smem_bytes(rec_cap) <= 200 * 1024;
+  const bool use_rec = c->gg_records && !(ov && ov->d_del) && maxL < 32000 && maxLt <= 2048 && frec_smem_bytes(rec_cap) <= 200 * 1024;
   GeneralParams G{};
   G.A = c->sc.A;
   G.subf = c->subf.as<float>();
@@ -1721,13 +1721,16 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
                         : tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
   if (use_rec) {
     const size_t rsm = frec_smem_bytes(rec_cap);
-    if (tb) {
-      CK(cached_max_smem((const void*)frec_fill_kernel<1>, (size_t)(rsm)));
-      frec_fill_kernel<1><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
-    } else {
-      CK(cached_max_smem((const void*)frec_fill_kernel<0>, (size_t)(rsm)));
-      frec_fill_kernel<0><<<dim3((unsigned)n, (unsigned)nd), 32, rsm, c->stream>>>(G, rec_cap);
-    }
+    const dim3 grid((unsigned)n, (unsigned)nd);
+    const bool wide = maxLt > 1024;  // more than 32 key columns per lane
+#define AADP_FREC_LAUNCH(TB_, WIDE_)                                                      \
+    do {                                                                                  \
+      CK(cached_max_smem((const void*)frec_fill_kernel<TB_, WIDE_>, rsm));               \
+      frec_fill_kernel<TB_, WIDE_><<<grid, 32, rsm, c->stream>>>(G, rec_cap);            \
+    } while (0)
+    if (tb) { if (wide) AADP_FREC_LAUNCH(1, 1); else AADP_FREC_LAUNCH(1, 0); }
+    else { if (wide) AADP_FREC_LAUNCH(0, 1); else AADP_FREC_LAUNCH(0, 0); }
+#undef AADP_FREC_LAUNCH
   } else if (tab) {
     CK(cached_max_smem((const void*)general_fill_kernel<1, 1>, (size_t)(std::max<size_t>(smem, 1024))));
     general_fill_kernel<1, 1><<<dim3((unsigned)n, (unsigned)nd), threads, smem, c->stream>>>(G);

@@ -29,6 +29,7 @@
 // leader is not clear (4-10 % of the cells).  No block-wide barrier anywhere.
 #pragma once
 #include "aadp_general.cuh"
+#include <type_traits>
 
 #ifndef FREC_EXP_NOWALK
 #define FREC_EXP_NOWALK 0  // timing experiment only (wrong results): never follow a column's record chain
@@ -47,8 +48,10 @@ struct __align__(4) FrecDeferred { float run; short b, ri; };
 
 __device__ __forceinline__ float frec_key(float d, float ge, int k) { return __fadd_rn(d, __fmul_rn(ge, (float)k)); }
 
-template <int TBM>
+// WIDE = 1: up to 64 key columns per lane (templates of 1025..2048 residues); the record bit mask is then 64 bits wide
+template <int TBM, int WIDE>
 __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, int cap) {
+  typedef typename std::conditional<WIDE != 0, unsigned long long, unsigned>::type recmask_t;
   extern __shared__ __align__(16) unsigned char frec_smem[];
   const int item = blockIdx.x;
   const int pair = P.items ? P.items[item] : P.item0 + item;
@@ -233,28 +236,29 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
     int ec1 = __shfl_up_sync(0xffffffffu, ic1, 1);
     if (lane == 0) { ek1 = NEGK; ed1 = 0.f; ek2 = NEGK; ec1 = 0; }
     const float pre = ek1;
-    // records of this lane's columns (a bit mask: K <= 32 per lane is guaranteed by the host), their number before
+    // records of this lane's columns (a bit mask: K <= 64 per lane is guaranteed by the host), their number before
     // this lane (exclusive prefix sum), and the list itself: ONE ascending list for the row, so that a walk is a
     // plain descending index.  Only the slow path (below) reads it.
-    unsigned recmask = 0;
+    recmask_t recmask = 0;
     {
       float run = pre;
       for (int k = k0, p = p0; k <= k1; ++k, ++p) {
         const float key = frec_key(cur[p], ge, k);
-        if (key >= __fsub_rn(run, mu)) recmask |= 1u << (k - k0);
+        if (key >= __fsub_rn(run, mu)) recmask |= (recmask_t)1 << (k - k0);
         run = fmaxf(run, key);
       }
     }
-    int rbase = __popc(recmask);
+    int rbase = WIDE ? __popcll((unsigned long long)recmask) : __popc((unsigned)recmask);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int u = __shfl_up_sync(0xffffffffu, rbase, o);
       if (lane >= o) rbase += u;
     }
-    rbase -= __popc(recmask);
-    for (unsigned mm = recmask, j = 0; mm; mm &= mm - 1, ++j) {
-      const int o = __ffs(mm) - 1;
-      rl[rbase + j] = (uint32_t)(k0 + o) | ((uint32_t)(p0 + o) << 16);
+    rbase -= WIDE ? __popcll((unsigned long long)recmask) : __popc((unsigned)recmask);
+    int jrec = 0;
+    for (recmask_t mm = recmask; mm; mm &= mm - 1, ++jrec) {
+      const int o = (WIDE ? __ffsll((long long)mm) : __ffs((int)mm)) - 1;
+      rl[rbase + jrec] = (uint32_t)(k0 + o) | ((uint32_t)(p0 + o) << 16);
     }
     __syncwarp();
 
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
         const float key = frec_key(d, ge, k);
         if (key > rk1) { rk2 = rk1; rk1 = key; rd1 = d; rc1 = k; }
         else rk2 = fmaxf(rk2, key);
-        ri += (recmask >> j) & 1u;
+        ri += (int)((recmask >> j) & (recmask_t)1);
         bq = k + 2;
         // the lane that owns key column nt has no cell of its own there: it takes the first interior cell, b = 2
         if (bq > nt) bq = (k == nt && nt >= 2) ? 2 : 0;
