@@ -13,11 +13,12 @@ pin = lambda x: torch.from_numpy(x.copy()).pin_memory()
 keep = [pin(res), pin(off), pin(pq), pin(pt)]
 hb = [k.numpy() for k in keep]
 what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
-for T in (1, 2, 3):
+for T in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,2,3".split(","))]:
     ctxs, streams = [], []
+    shared = torch.cuda.Stream() if os.environ.get('SHARED_STREAM') else None
     for k in range(T):
         c = a.Context(0)
-        s = torch.cuda.Stream()
+        s = shared or torch.cuda.Stream()
         c.set_stream(s.cuda_stream)
         c.set_scoring(M, 12, 1, a.SEMI_LOCAL)
         c.fill_batch(*hb, what, 0.01)

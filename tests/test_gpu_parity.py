@@ -914,7 +914,7 @@ def test_record_and_pruned_general_gap_kernels_change_nothing(blosum):
             c.set_option("exact_float", 1)
             c.set_scoring(M, gi, ge, at)
         O = po.Oracle(M, gi, ge, at)
-        for Lq, Lt in [(2, 2), (3, 40), (61, 5), (1, 77), (97, 130), (150, 620), (333, 31), (300, 300), (40, 1500), (70, 2048)]:
+        for Lq, Lt in [(2, 2), (3, 40), (61, 5), (1, 77), (97, 130), (150, 620), (333, 31), (300, 300), (40, 1500), (70, 2048), (4, 1), (1, 1), (33, 2), (2, 65)]:
             q, t = rand_pair(rng, Lq, Lt)
             if Lq == 97:
                 t[:90] = q[:90]          # a related pair: the pruning bites hardest there
