@@ -1720,7 +1720,8 @@ static int gg_fill(aadp_ctx* c, int64_t p0, int64_t n, int dirmask, bool tb, con
   c->prof_begin(use_rec ? (tb ? "frec_fill_kernel<TB=1>" : "frec_fill_kernel<TB=0>")
                         : tab ? "general_fill_kernel<TB=1,TAB=1>" : tb ? "general_fill_kernel<TB=1>" : "general_fill_kernel<TB=0>", cu * nd);
   if (use_rec) {
-    const size_t rsm = frec_smem_bytes(rec_cap);
+    // (measurement aid: AADP_FREC_SMEM_PAD extra bytes per warp lower the resident warps per SM)
+    const size_t rsm = frec_smem_bytes(rec_cap) + (getenv("AADP_FREC_SMEM_PAD") ? (size_t)atoi(getenv("AADP_FREC_SMEM_PAD")) : 0);
     const dim3 grid((unsigned)n, (unsigned)nd);
     const bool wide = maxLt > 1024;  // more than 32 key columns per lane
 #define AADP_FREC_LAUNCH(TB_, WIDE_)                                                      \

@@ -41,7 +41,7 @@ namespace aadp {
 // template of the launch (frec_cap): lane l keeps its K columns at l*Kp .. l*Kp+K-1 with Kp = K | 1, an ODD stride, so
 // that the 32 lanes of every access fall into 32 different banks (a stride of K = 16 words was a 16-way conflict).
 __host__ __device__ inline int frec_cap(int max_nt) { return 32 * (((max_nt + 31) / 32) | 1) + 8; }
-__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 6 + 2 * 3 + 1) + 16 + 64 * 8; }
+__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 8 + 2 + 1) + 16 + 64 * 8 + 64 * 4; }
 
 // a cell waiting for the record chain of its column (see the row loop)
 struct __align__(4) FrecDeferred { float run; short b, ri; };
@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
   float* cD2 = cD1 + cap;       // D of the runner-up
   float* ckey3 = cD2 + cap;     // third-best key of the column
   uint32_t* rl = reinterpret_cast<uint32_t*>(ckey3 + cap);  // records of the previous row, ascending: column | position << 16
-  short* ck1 = reinterpret_cast<short*>(rl + cap);     // rows of leader / runner-up (0 = none)
-  short* ck2 = ck1 + cap;
-  short* clast = ck2 + cap;     // last record of the column
+  float* cK1 = reinterpret_cast<float*>(rl + cap);     // rows of leader / runner-up as floats (0 = none): they only
+  float* cK2 = cK1 + cap;                              // ever enter float arithmetic (key = D + ge*k, pen(len))
+  float* srow_s = cK2 + cap;    // 64 entries: substitution scores of the current query residue
+  short* clast = reinterpret_cast<short*>(srow_s + 64);  // last record of the column
   FrecDeferred* dq = reinterpret_cast<FrecDeferred*>(clast + cap);  // 64 entries
   uint8_t* tcode = reinterpret_cast<uint8_t*>(dq + 64);
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
   for (int b = 1 + lane; b <= nt; b += 32) {
     const int p = ph(b);
     tcode[p] = simov ? 0 : tseq[colof(b) - 1];
-    cD1[p] = 0.f; cD2[p] = 0.f; ckey3[p] = NEGK; ck1[p] = 0; ck2[p] = 0; clast[p] = 0;
+    cD1[p] = 0.f; cD2[p] = 0.f; ckey3[p] = NEGK; cK1[p] = 0.f; cK2[p] = 0.f; clast[p] = 0;
   }
   __syncwarp();
   auto simrow = [&](int a) -> const float* {
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
       const int kc = a - 1;
       const float kk = frec_key(dc, ge, kc);
       if (kk >= __fsub_rn(key1, mu)) { LK[lkbase + colof(c)] = (int)clast[pc]; clast[pc] = (short)kc; }
-      if (kk > key1) { ckey3[pc] = key2; cD2[pc] = d1; ck2[pc] = (short)kk1; cD1[pc] = dc; ck1[pc] = (short)kc; }
-      else if (kk > key2) { ckey3[pc] = key2; cD2[pc] = dc; ck2[pc] = (short)kc; }
+      if (kk > key1) { ckey3[pc] = key2; cD2[pc] = d1; cK2[pc] = (float)kk1; cD1[pc] = dc; cK1[pc] = (float)kc; }
+      else if (kk > key2) { ckey3[pc] = key2; cD2[pc] = dc; cK2[pc] = (float)kc; }
       else if (kk > key3) ckey3[pc] = kk;
     };
     // SLOW PATH: a cell whose deletion scan has two or more leaders within the noise, or whose insertion scan has three
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
         }
         if (bk && bs > os) { ob = bk; os = bs; }
       }
-      const int kk1 = (int)ck1[pc], kk2 = (int)ck2[pc];
+      const int kk1 = (int)cK1[pc], kk2 = (int)cK2[pc];
       const float d1 = cD1[pc], d2 = cD2[pc], key3 = ckey3[pc];
       const float key1 = kk1 ? frec_key(d1, ge, kk1) : NEGK, key2 = kk2 ? frec_key(d2, ge, kk2) : NEGK;
       if (a >= 3) {  // insertions (dpmatrix.h:471-480): candidate rows 1..a-2 of column b-1
@@ -367,18 +368,31 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
       nxt[0] = sv;
       rowabs = fmaxf(rowabs, fabsf(sv));
     }
-    // FAST PATH: running leader of the keys 1..k (from the exclusive prefix on), one candidate per scan class
-    float rk1 = ek1, rd1 = ed1, rk2 = ek2;
-    int rc1 = ec1;
+    // FAST PATH (rows >= 3, cells b >= 3, substitution-table similarity): running leader of the keys 1..k from the
+    // exclusive prefix on, one candidate per deletion scan, leader and runner-up of the column for the insertion scan.
+    // Row and column indices travel as floats (exact), the column entry is rewritten without branches.
+    float rk1 = ek1, rd1 = ed1, rk2 = ek2, rcf = (float)ec1;
     int ri = rbase - 1;  // index of the last record among 1..k
-    for (int j = 0; j < K; ++j) {  // the same trip count for every lane: the queue is filled with warp votes
+    const bool fast_row = a >= 3 && !simov;
+    const float af1 = (float)(a - 1), am2f = (float)(a - 2), gea1 = __fmul_rn(ge, af1);
+    const float floorv = local ? 0.f : -INFINITY;
+    if (!simov) {
+      __syncwarp();
+      for (int x = lane; x < P.A; x += 32) srow_s[x] = srow[x];
+      __syncwarp();
+    }
+    float kf = (float)k0;
+    for (int j = 0; j < K; ++j, kf += 1.0f) {  // the same trip count for every lane: the queue is filled with warp votes
       const int k = k0 + j, p = p0 + j;
       int bq = 0;
       if (k <= k1) {
         const float d = cur[p];
-        const float key = frec_key(d, ge, k);
-        if (key > rk1) { rk2 = rk1; rk1 = key; rd1 = d; rc1 = k; }
-        else rk2 = fmaxf(rk2, key);
+        const float key = __fadd_rn(d, __fmul_rn(ge, kf));
+        const bool lead = key > rk1;
+        rk2 = lead ? rk1 : fmaxf(rk2, key);
+        rd1 = lead ? d : rd1;
+        rcf = lead ? kf : rcf;
+        rk1 = lead ? key : rk1;
         ri += (int)((recmask >> j) & (recmask_t)1);
         bq = k + 2;
         // the lane that owns key column nt has no cell of its own there: it takes the first interior cell, b = 2
@@ -386,39 +400,53 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
       }
       bool defer = false;
       if (bq) {
-        // padded positions of columns b and b-1 (pad is non-zero for even K only; then b and b-1 lie at most one lane
-        // segment to the right of key column k)
-        const bool first = bq == 2;
-        const int pb = first ? 1 : (bq - 1) + pad * (lane + (j + 2 >= K ? 1 : 0));
-        const int pc = first ? 0 : (bq - 2) + pad * (lane + (j + 1 >= K ? 1 : 0));
-        const int kk1 = (int)ck1[pc], kk2 = (int)ck2[pc];
-        const float d1 = cD1[pc], d2 = cD2[pc], key3 = ckey3[pc];
-        const float key1 = kk1 ? frec_key(d1, ge, kk1) : NEGK, key2 = kk2 ? frec_key(d2, ge, kk2) : NEGK;
-        const float climit = __fsub_rn(key1, mu2);
-        const bool row_clear = first || rk2 < __fsub_rn(rk1, mu2);
-        const bool col_clear = a < 3 || FREC_EXP_NOWALK || key3 < climit;
-        if (row_clear && col_clear) {
-          const float simc = simat(srow, bq, pb);
-          const float dc = cur[pc];  // D[a-1][b-1]: the match predecessor, and the new candidate of column b-1
-          int oa = a - 1, ob = bq - 1;
-          float os = clampl(__fadd_rn(dc, simc));
-          if (!first) {  // deletions (dpmatrix.h:459-468): the one leader of row a-1 among 1..b-2
-            const float sv = clampl(__fadd_rn(__fsub_rn(rd1, gg_pen(gi, ge, bq - rc1 - 1)), simc));
-            if (sv > os) { ob = rc1; os = sv; }
-          }
-          if (a >= 3) {  // insertions (dpmatrix.h:471-480): leader and runner-up of column b-1
-            int bk = kk1;
-            float bs = clampl(__fadd_rn(__fsub_rn(d1, gg_pen(gi, ge, a - kk1 - 1)), simc));
-            if (kk2 && key2 >= climit) {
-              const float s2 = clampl(__fadd_rn(__fsub_rn(d2, gg_pen(gi, ge, a - kk2 - 1)), simc));
-              if (s2 > bs || (s2 == bs && kk2 < kk1)) { bs = s2; bk = kk2; }
+        defer = true;
+        if (fast_row && bq != 2) {
+          // padded positions of columns b and b-1 (pad is non-zero for even K only; then b and b-1 lie at most one lane
+          // segment to the right of key column k)
+          const int pb = (bq - 1) + pad * (lane + (j + 2 >= K ? 1 : 0));
+          const int pc = (bq - 2) + pad * (lane + (j + 1 >= K ? 1 : 0));
+          const float d1 = cD1[pc], k1f = cK1[pc], d2 = cD2[pc], k2f = cK2[pc], key3 = ckey3[pc];
+          const float key1 = __fadd_rn(d1, __fmul_rn(ge, k1f));  // rows >= 3: the column has a leader
+          const float key2 = k2f > 0.f ? __fadd_rn(d2, __fmul_rn(ge, k2f)) : NEGK;
+          const float climit = __fsub_rn(key1, mu2);
+          if (rk2 < __fsub_rn(rk1, mu2) && (FREC_EXP_NOWALK || key3 < climit)) {
+            defer = false;
+            const float simc = srow_s[tcode[pb]];
+            const float dc = cur[pc];  // D[a-1][b-1]: the match predecessor, and the new candidate of column b-1
+            float os = fmaxf(__fadd_rn(dc, simc), floorv);
+            // deletions (dpmatrix.h:459-468): the one leader of row a-1 among 1..b-2; len - 1 = b - 2 - column = k - column
+            const float sv = fmaxf(__fadd_rn(__fsub_rn(rd1, __fadd_rn(gi, __fmul_rn(ge, __fsub_rn(kf, rcf)))), simc), floorv);
+            const bool wdel = sv > os;
+            os = wdel ? sv : os;
+            // insertions (dpmatrix.h:471-480): leader and runner-up of column b-1; len - 1 = a - 2 - row
+            float bs = fmaxf(__fadd_rn(__fsub_rn(d1, __fadd_rn(gi, __fmul_rn(ge, __fsub_rn(am2f, k1f)))), simc), floorv);
+            float bkf = k1f;
+            if (key2 >= climit) {  // (a runner-up exists: key2 is NEGK otherwise)
+              const float s2 = fmaxf(__fadd_rn(__fsub_rn(d2, __fadd_rn(gi, __fmul_rn(ge, __fsub_rn(am2f, k2f)))), simc), floorv);
+              const bool take2 = s2 > bs || (s2 == bs && k2f < k1f);
+              bs = take2 ? s2 : bs;
+              bkf = take2 ? k2f : bkf;
             }
-            if (bs > os) { oa = bk; ob = bq - 1; os = bs; }
+            const bool wins = bs > os;
+            os = wins ? bs : os;
+            if (TBM) {
+              const int64_t o = rowbase + colof(bq);
+              PQ[o] = rowof(wins ? (int)bkf : a - 1);
+              PT[o] = colof((wins || !wdel) ? bq - 1 : (int)rcf);
+            }
+            nxt[pb] = os;
+            rowabs = fmaxf(rowabs, fabsf(os));
+            // column b-1 receives the candidate of row a-1 (used from row a+1 on)
+            const float kk = __fadd_rn(dc, gea1);
+            if (kk >= __fsub_rn(key1, mu)) { LK[lkbase + colof(bq - 1)] = (int)clast[pc]; clast[pc] = (short)(a - 1); }
+            const bool n1 = kk > key1, n2 = !n1 && kk > key2, n3 = !n1 && !n2 && kk > key3;
+            cD1[pc] = n1 ? dc : d1;
+            cK1[pc] = n1 ? af1 : k1f;
+            cD2[pc] = n1 ? d1 : (n2 ? dc : d2);
+            cK2[pc] = n1 ? k1f : (n2 ? af1 : k2f);
+            ckey3[pc] = (n1 || n2) ? key2 : (n3 ? kk : key3);
           }
-          finish(bq, pb, oa, ob, os);
-          column_update(bq - 1, pc, dc, key1, key2, key3, d1, kk1);
-        } else {
-          defer = true;
         }
       }
       const unsigned dm = __ballot_sync(0xffffffffu, defer);
