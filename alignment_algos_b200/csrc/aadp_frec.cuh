@@ -41,7 +41,7 @@ namespace aadp {
 // template of the launch (frec_cap): lane l keeps its K columns at l*Kp .. l*Kp+K-1 with Kp = K | 1, an ODD stride, so
 // that the 32 lanes of every access fall into 32 different banks (a stride of K = 16 words was a 16-way conflict).
 __host__ __device__ inline int frec_cap(int max_nt) { return 32 * (((max_nt + 31) / 32) | 1) + 8; }
-__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 8 + 2 + 1) + 16 + 64 * 8 + 64 * 4; }
+__host__ __device__ inline size_t frec_smem_bytes(int cap) { return (size_t)cap * (4 * 7 + 2 * 2 + 1) + 16 + 64 * 8 + 64 * 4; }
 
 // a cell waiting for the record chain of its column (see the row loop)
 struct __align__(4) FrecDeferred { float run; short b, ri; };
@@ -83,12 +83,12 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
   float* cD1 = rowB + cap;      // D of the column's leader (largest key, smallest row on ties)
   float* cD2 = cD1 + cap;       // D of the runner-up
   float* ckey3 = cD2 + cap;     // third-best key of the column
-  uint32_t* rl = reinterpret_cast<uint32_t*>(ckey3 + cap);  // records of the previous row, ascending: column | position << 16
-  float* cK1 = reinterpret_cast<float*>(rl + cap);     // rows of leader / runner-up as floats (0 = none): they only
+  float* cK1 = ckey3 + cap;     // rows of leader / runner-up as floats (0 = none): they only
   float* cK2 = cK1 + cap;                              // ever enter float arithmetic (key = D + ge*k, pen(len))
   float* srow_s = cK2 + cap;    // 64 entries: substitution scores of the current query residue
   short* clast = reinterpret_cast<short*>(srow_s + 64);  // last record of the column
-  FrecDeferred* dq = reinterpret_cast<FrecDeferred*>(clast + cap);  // 64 entries
+  short* rl = clast + cap;      // records (columns) of the previous row, ascending; only the slow path reads it
+  FrecDeferred* dq = reinterpret_cast<FrecDeferred*>(rl + cap);  // 64 entries
   uint8_t* tcode = reinterpret_cast<uint8_t*>(dq + 64);
 
   auto rowof = [&](int a) { return rev ? mq1 - a : q0 + a; };
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
     int jrec = 0;
     for (recmask_t mm = recmask; mm; mm &= mm - 1, ++jrec) {
       const int o = (WIDE ? __ffsll((long long)mm) : __ffs((int)mm)) - 1;
-      rl[rbase + jrec] = (uint32_t)(k0 + o) | ((uint32_t)(p0 + o) << 16);
+      rl[rbase + jrec] = (short)(k0 + o);
     }
     __syncwarp();
 
@@ -302,20 +302,19 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
         int bk = 0;
         int i = ri;
         if (i >= 0) {
-          uint32_t e = rl[i];
-          float d = cur[e >> 16];
+          int kr = (int)rl[i];
+          float d = cur[ph(kr)];
           for (;;) {
             // the next record is fetched before this one is evaluated (its key ends the walk)
-            const int kr = (int)(e & 0xffffu);
             --i;
-            uint32_t en = 0;
+            int kn = 0;
             float dn = 0.f;
-            if (i >= 0) { en = rl[i]; dn = cur[en >> 16]; }
+            if (i >= 0) { kn = (int)rl[i]; dn = cur[ph(kn)]; }
             if (frec_key(d, ge, kr) < lim) break;
             const float sv = clampl(__fadd_rn(__fsub_rn(d, gg_pen(gi, ge, bq - kr - 1)), simc));
             if (bk == 0 || sv >= bs) { bs = sv; bk = kr; }
             if (i < 0) break;
-            e = en;
+            kr = kn;
             d = dn;
           }
         }
