@@ -950,6 +950,24 @@ def test_record_and_pruned_general_gap_kernels_change_nothing(blosum):
             for key in o1:
                 if o1[key] is not None:
                     assert_matrix_equal("batch %s" % key, o1[key], o2[key])
+        if at == po.SEMI_LOCAL:
+            # the benchmark shape of the float-default line (bench.py --workload c3f): C3-shaped pairs, random and related
+            from alignment_algos_b200 import synth
+            sq, bq, bt = synth.pair_workload(1003, 384, 100, 500)
+            sq = list(sq)
+            for p in range(0, 384, 3):  # every third template becomes a mutated, shifted copy of its query
+                qv = sq[bq[p]]
+                tv = np.roll(qv.copy(), 3)
+                idx = rng.integers(0, len(tv), len(tv) // 4)
+                tv[idx] = rng.integers(0, 20, len(idx))
+                sq[bt[p]] = tv
+            r2, o2f = a.Context.pack(sq)
+            w2 = a.W_FWD | a.W_REV | a.W_MASK
+            want = cp.fill_batch(r2, o2f, bq, bt, w2, 0.01)
+            got = cr.fill_batch(r2, o2f, bq, bt, w2, 0.01)
+            for key in got:
+                if got[key] is not None:
+                    assert_matrix_equal("c3f batch %s" % key, got[key], want[key])
         for c in (cr, cp, cn):
             c.close()
 
