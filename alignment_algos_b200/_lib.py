@@ -38,6 +38,8 @@ def lib():
     L.aadp_set_scoring.argtypes = [vp, vp, C.c_int, f32, f32, C.c_int, u32]
     L.aadp_fill_pair.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, f32] + [vp] * 8
     L.aadp_fill_batch.argtypes = [vp, vp, vp, i64, vp, vp, i64, u32, f32, vp, vp, vp, vp]
+    L.aadp_fill_batch_submit.argtypes = [vp, vp, vp, i64, vp, vp, i64, u32, f32, vp, vp, vp, vp]
+    L.aadp_fill_batch_wait.argtypes = [vp]
     L.aadp_upload_batch.argtypes = [vp, vp, vp, i64, vp, vp, i64, u32]
     L.aadp_run_batch.argtypes = [vp, u32, f32, vp, vp, vp, vp]
     L.aadp_batch_resident_bytes.restype = i64
@@ -88,6 +90,6 @@ EXPORTS = [
     "aadp_batch_fetch_pair", "aadp_batch_optimal", "aadp_tb_row_bytes", "aadp_batch_tb_bytes",
     "aadp_batch_fetch_tb", "aadp_decode_cell", "aadp_upload_sequences", "aadp_cross_run", "aadp_cross_scores",
     "aadp_last_cross_cell_updates", "aadp_batch_optimal_all", "aadp_fill_subpair", "aadp_fill_pair_general",
-    "aadp_fill_subpair_batch", "aadp_fill_pair_tabulated", "aadp_fill_batch_tabulated", "aadp_batch_near_optimal", "aadp_batch_near_optimal_constrained",
+    "aadp_fill_subpair_batch", "aadp_fill_pair_tabulated", "aadp_fill_batch_tabulated", "aadp_fill_batch_submit", "aadp_fill_batch_wait", "aadp_batch_near_optimal", "aadp_batch_near_optimal_constrained",
     "aadp_batch_near_optimal_pruned", "aadp_batch_optimal_all_compact",
 ]

@@ -194,6 +194,34 @@ class Context:
                                         _ptr(pair_t), n, what, delta_ratio, _ptr(fs), _ptr(rs), _ptr(th), _ptr(cn)))
         return {"fwd_score": fs, "rev_score": rs, "threshold": th, "nearopt_count": cn}
 
+    def fill_batch_submit(self, residues, seq_off, pair_q, pair_t, what, delta_ratio=0.01, out=None):
+        """aadp_fill_batch_submit: host scheduling + everything enqueued, no final wait.  `out` may hold preallocated
+        result arrays ("fwd_score", "rev_score", "threshold", "nearopt_count"; PINNED memory keeps the device-to-host
+        copies asynchronous); inputs and outputs must stay alive and untouched until fill_batch_wait()."""
+        pair_q = np.ascontiguousarray(pair_q, np.int32)
+        pair_t = np.ascontiguousarray(pair_t, np.int32)
+        n = len(pair_q)
+        out = dict(out) if out else {}
+        want = {"fwd_score": (what & W_FWD, np.float32), "rev_score": (what & W_REV, np.float32),
+                "threshold": (what & W_MASK, np.float32), "nearopt_count": (what & W_MASK, np.int64)}
+        for k, (on, ty) in want.items():
+            if not on:
+                out[k] = None
+            elif out.get(k) is None:
+                out[k] = np.zeros(n, ty)
+        self._ck(self.L.aadp_fill_batch_submit(self.h, _ptr(residues), _ptr(seq_off), len(seq_off) - 1, _ptr(pair_q),
+                                               _ptr(pair_t), n, what, delta_ratio, _ptr(out["fwd_score"]), _ptr(out["rev_score"]),
+                                               _ptr(out["threshold"]), _ptr(out["nearopt_count"])))
+        self._pending = (residues, seq_off, pair_q, pair_t, out)  # keep the buffers alive (a refused submit leaves the old ones)
+        return out
+
+    def fill_batch_wait(self):
+        """aadp_fill_batch_wait: returns when the results of the submitted batch are in the output arrays."""
+        self._ck(self.L.aadp_fill_batch_wait(self.h))
+        out = getattr(self, "_pending", (None,) * 5)[4]
+        self._pending = None
+        return out
+
     def upload_batch(self, residues, seq_off, pair_q, pair_t, what):
         pair_q = np.ascontiguousarray(pair_q, np.int32)
         pair_t = np.ascontiguousarray(pair_t, np.int32)

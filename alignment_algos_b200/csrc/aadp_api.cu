@@ -177,6 +177,8 @@ struct aadp_ctx {
   uint8_t* pin = nullptr;
   size_t pin_cap = 0, pin_used = 0;
   int* pin_flag = nullptr;
+  bool pending = false;        // aadp_fill_batch_submit without its aadp_fill_batch_wait
+  bool flag_deferred = false;  // ... whose residue validation flag has not been looked at yet
   cudaEvent_t ev_flag = nullptr;  // recorded after the residue validation flag has been copied back
   cudaStream_t copy_stream = nullptr;  // pipelined uploads (aadp_fill_batch)
   cudaEvent_t ev_piece[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_start = nullptr;
@@ -1968,10 +1970,13 @@ int aadp_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_fwd_s
   return run_batch_impl(c, what, delta_ratio, d_fwd_score, d_rev_score, d_threshold, d_nearopt_count, false);
 }
 
-int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
-                    const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
-                    float* rev_score, float* threshold, int64_t* nearopt_count) {
+// wait = false (aadp_fill_batch_submit): everything is enqueued, the final synchronisation -- and, for batches of
+// packed pairs only, the look at the residue validation flag -- is left to aadp_fill_batch_wait.
+static int fill_batch_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                           const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
+                           float* rev_score, float* threshold, int64_t* nearopt_count, bool wait) {
   if (check_ctx(c, true)) return 1;
+  if (c->pending) return fail("a submitted batch is pending on this context: call aadp_fill_batch_wait first");
   if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
   if (!seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
   if (seq_off[0] < 0) return fail("sequence offsets must start at a non-negative offset");
@@ -2020,12 +2025,18 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     // the residue validation flag came back long ago (it was queued right after the arena kernel); the int32 and
     // wavefront kernels read the raw residues, so they are only launched on validated input
     g_marks.mark("sched");
-    CK(cudaEventSynchronize(c->ev_flag));
-    g_marks.mark("flag");
-    if (*c->pin_flag) {
-      CK(cudaStreamSynchronize(c->stream));
-      b.have_seqs = false;
-      return fail("residue code outside the substitution alphabet");
+    // the packed kernels read the device-built arenas, in which an invalid code scores as a pad column (harmless garbage
+    // that the flag voids afterwards); only the int32 / wavefront kernels index tables with raw residues
+    const bool raw_readers = !b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty();
+    c->flag_deferred = !wait && !raw_readers;
+    if (!c->flag_deferred) {
+      CK(cudaEventSynchronize(c->ev_flag));
+      g_marks.mark("flag");
+      if (*c->pin_flag) {
+        CK(cudaStreamSynchronize(c->stream));
+        b.have_seqs = false;
+        return fail("residue code outside the substitution alphabet");
+      }
     }
     if (run_batch_impl(c, what, delta_ratio, df, dr, dt, dc, true)) return 1;
     g_marks.mark("all");
@@ -2037,11 +2048,43 @@ int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off
     if (threshold && (what & AADP_W_MASK)) { CK(cudaMemcpyAsync(threshold, dt, npairs * 4, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 4; }
     if (nearopt_count && (what & AADP_W_MASK)) { CK(cudaMemcpyAsync(nearopt_count, dc, npairs * 8, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += npairs * 8; }
   }
+  if (!wait) { c->pending = true; return 0; }
   CK(cudaStreamSynchronize(c->stream));
   if (timing && pipelined)
     fprintf(stderr, "[aadp] fill_batch host timeline (ms): sequences enqueued %.2f, fwd chunk launches %.2f %.2f %.2f, all launched %.2f, done %.2f\n",
             t_seq, t_chunk[0], t_chunk[1], t_chunk[2], t_launched, ms_since());
   if (timing && pipelined) fprintf(stderr, "[aadp] marks:%s\n", g_marks.log.c_str());
+  return 0;
+}
+
+int aadp_fill_batch(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                    const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
+                    float* rev_score, float* threshold, int64_t* nearopt_count) {
+  return fill_batch_impl(c, residues, seq_off, nseq, pair_q, pair_t, npairs, what, delta_ratio, fwd_score, rev_score,
+                         threshold, nearopt_count, true);
+}
+
+int aadp_fill_batch_submit(aadp_ctx* c, const uint8_t* residues, const int64_t* seq_off, int64_t nseq, const int32_t* pair_q,
+                           const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
+                           float* rev_score, float* threshold, int64_t* nearopt_count) {
+  return fill_batch_impl(c, residues, seq_off, nseq, pair_q, pair_t, npairs, what, delta_ratio, fwd_score, rev_score,
+                         threshold, nearopt_count, false);
+}
+
+int aadp_fill_batch_wait(aadp_ctx* c) {
+  if (check_ctx(c, false)) return 1;
+  if (!c->pending) return 0;
+  c->pending = false;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->flag_deferred) {
+    c->flag_deferred = false;
+    CK(cudaEventSynchronize(c->ev_flag));
+    if (*c->pin_flag) {
+      c->b.have_seqs = false;
+      c->b.ran_what = 0;
+      return fail("residue code outside the substitution alphabet");
+    }
+  }
   return 0;
 }
 

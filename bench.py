@@ -688,6 +688,60 @@ def main():
             e2e_ms = ovl_ms
             e2e_value = total_cu * args.steps / (e2e_ms * 1e-3) / 1e9
             e2e_mode = "three contexts on three host threads, calls overlapped (each step with its own H2D and D2H)"
+    # ---- leg 2c: the same overlap WITHOUT threads: one host thread drives two contexts through aadp_fill_batch_submit /
+    # aadp_fill_batch_wait (include/aadp.h), results into pinned buffers; the host schedules batch k+1 while the GPU
+    # fills batch k.  Reported as e2e.async_*; it becomes e2e.value when it is the best of the three modes.
+    e2e_async = None
+    if args.workload != "c5" and args.steps >= 4 and not args.no_e2e_overlap:
+        T = int(os.environ.get("AADP_BENCH_ASYNC_CTX", "2"))
+        actx, astreams, aouts = [], [], []
+        for k in range(T):
+            c = a.Context(local_rank)
+            sk = torch.cuda.Stream()
+            c.set_stream(sk.cuda_stream)
+            c.set_scoring(M, GI, GE, a.SEMI_LOCAL)
+            c.fill_batch(hb["res"], hb["off"], hb["pq"], hb["pt"], what, DELTA)
+            o = {}
+            for key, ty in (("fwd_score", torch.float32), ("rev_score", torch.float32), ("threshold", torch.float32), ("nearopt_count", torch.int64)):
+                tpin = torch.zeros(n, dtype=ty).pin_memory()
+                keep.append(tpin)
+                o[key] = tpin.numpy()
+            actx.append(c)
+            astreams.append(sk)
+            aouts.append(o)
+        torch.cuda.synchronize()
+        barrier()
+        z0 = torch.cuda.Event(enable_timing=True)
+        z0.record(stream)
+        for sk in astreams:
+            sk.wait_event(z0)
+        inflight = [False] * T
+        for it in range(args.steps):
+            k = it % T
+            if inflight[k]:
+                actx[k].fill_batch_wait()
+            actx[k].fill_batch_submit(hb["res"], hb["off"], hb["pq"], hb["pt"], what, DELTA, out=aouts[k])
+            inflight[k] = True
+        for k in range(T):
+            if inflight[k]:
+                actx[k].fill_batch_wait()
+        ends = []
+        for sk in astreams:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(sk)
+            ends.append(e)
+        torch.cuda.synchronize()
+        barrier()
+        async_ms = max_over_ranks(max(z0.elapsed_time(e) for e in ends))
+        for k in range(T):
+            assert np.array_equal(aouts[k]["fwd_score"], out["fwd_score"])
+            actx[k].close()
+        e2e_async = {"value": total_cu * args.steps / (async_ms * 1e-3) / 1e9, "ms_per_step": async_ms / args.steps,
+                     "mode": "one host thread, %d contexts, aadp_fill_batch_submit / aadp_fill_batch_wait" % T}
+        if async_ms < e2e_ms:
+            e2e_ms = async_ms
+            e2e_value = e2e_async["value"]
+            e2e_mode = e2e_async["mode"] + " (each step with its own H2D and D2H)"
     sampler.stop()
     clocks = sampler.summary(w0, w1)
 
@@ -739,7 +793,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode,
                 "serial_value": total_cu * args.steps / (e2e_serial_ms * 1e-3) / 1e9,
-                "serial_ms_per_step": e2e_serial_ms / args.steps},
+                "serial_ms_per_step": e2e_serial_ms / args.steps,
+                **({"async_value": e2e_async["value"], "async_ms_per_step": e2e_async["ms_per_step"], "async_mode": e2e_async["mode"]}
+                   if e2e_async else {})},
         "gpu_launches": int(launches_step * args.steps),
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,

@@ -191,6 +191,18 @@ int aadp_fill_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_o
                     float delta_ratio, float* fwd_score, float* rev_score, float* threshold,
                     int64_t* nearopt_count);
 
+/* The same call in two halves, for a caller that wants to overlap batches WITHOUT threads: submit does the host
+ * scheduling and enqueues every copy and kernel, wait returns when the results are in the caller's buffers (and
+ * reports what submit could not know yet, e.g. a residue outside the alphabet).  With two contexts,
+ *     submit(A, batch k); submit(B, batch k+1); wait(A); submit(A, batch k+2); wait(B); ...
+ * the host schedules one batch while the GPU fills the other.  Between submit and wait only aadp_fill_batch_wait
+ * may be called on that context, and the input and output buffers must stay untouched.                              */
+int aadp_fill_batch_submit(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,
+                    const int32_t* pair_q, const int32_t* pair_t, int64_t npairs, uint32_t what,
+                    float delta_ratio, float* fwd_score, float* rev_score, float* threshold,
+                    int64_t* nearopt_count);
+int aadp_fill_batch_wait(aadp_ctx* ctx);
+
 /* Same work with inputs ALREADY RESIDENT in device memory and per-pair outputs left in device
  * memory (d_* are device pointers; may be NULL like above). Asynchronous on the context stream. */
 int aadp_upload_batch(aadp_ctx* ctx, const uint8_t* residues, const int64_t* seq_off, int64_t nseq,

@@ -1254,3 +1254,42 @@ def test_long_pair_wavefront_30000_properties(blosum):
         assert out["nearopt_count"][0] >= len(pairs) - 2
     finally:
         c.close()
+
+
+def test_fill_batch_submit_wait_equals_fill_batch(blosum):
+    # aadp_fill_batch_submit / aadp_fill_batch_wait: the same results as the blocking call, two contexts driven by one
+    # thread with batches in flight on both; an invalid residue is reported by wait (packed-only batch) or by submit
+    import alignment_algos_b200 as a
+    from alignment_algos_b200 import synth
+    _, M = blosum
+    seqs, pq, pt = synth.pair_workload(91, 40000, 60, 300)   # >= 32768 pairs: the pipelined path
+    res, off = a.Context.pack(seqs)
+    what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+    cs = [a.Context(0), a.Context(0)]
+    for c in cs:
+        c.set_scoring(M, 12, 1, po.SEMI_LOCAL)
+    want = cs[0].fill_batch(res, off, pq, pt, what, 0.01)
+    outs = [None, None]
+    for it in range(4):
+        k = it % 2
+        if outs[k] is not None:
+            got = cs[k].fill_batch_wait()
+            for key in want:
+                assert_matrix_equal("async %s" % key, got[key], want[key])
+        outs[k] = cs[k].fill_batch_submit(res, off, pq, pt, what, 0.01)
+    with pytest.raises(a.AadpError):  # a second submit before the wait
+        cs[0].fill_batch_submit(res, off, pq, pt, what, 0.01)
+    for k in range(2):
+        got = cs[k].fill_batch_wait()
+        for key in want:
+            assert_matrix_equal("async %s" % key, got[key], want[key])
+    # the resident products of a waited batch serve the usual follow-up calls
+    rc, pairs, sc = cs[1].optimal(5, a.FWD, len(seqs[pq[5]]), len(seqs[pt[5]]))
+    assert rc == 0 and sc == want["fwd_score"][5]
+    bad = res.copy()
+    bad[off[pq[7]]] = 77
+    cs[0].fill_batch_submit(bad, off, pq, pt, what, 0.01)
+    with pytest.raises(a.AadpError):
+        cs[0].fill_batch_wait()
+    for c in cs:
+        c.close()
