@@ -808,13 +808,22 @@ int reserve_direction(aadp_ctx* c, int dir, uint32_t what) {
   return 0;
 }
 
+constexpr size_t kAllChunks = (size_t)-1;
 // Packed kernel of one direction over the tasks of one chunk.
 int launch_packed_chunk(aadp_ctx* c, int dir, uint32_t what, float delta_ratio, float* d_threshold, int64_t* d_count,
                         size_t chunk) {
   Batch& b = c->b;
   const int tbm = (what & AADP_W_TB) ? 1 : 0;
-  if (chunk >= b.chunk_ntasks.size() || b.chunk_ntasks[chunk] == 0) return 0;
-  if (chunk >= 8) return fail("internal: too many task chunks");
+  // chunk == kAllChunks: ONE launch over the task lists of all chunks (they are contiguous on the device) -- every
+  // launch that is not needed for the host/GPU pipelining of aadp_fill_batch only adds a kernel tail
+  const bool all = chunk == kAllChunks;
+  if (all) {
+    if (b.chunk_ntasks.empty() || b.n_tasks == 0) return 0;
+    chunk = 7;  // its own work counter
+  } else {
+    if (chunk >= b.chunk_ntasks.size() || b.chunk_ntasks[chunk] == 0) return 0;
+    if (chunk >= 7) return fail("internal: too many task chunks");
+  }
   {
     PackedParams Q{};
     Q.sc = c->sc;
@@ -825,8 +834,8 @@ int launch_packed_chunk(aadp_ctx* c, int dir, uint32_t what, float delta_ratio, 
     Q.seq_off = c->seq_off.as<int64_t>();
     Q.pair_q = c->pair_q.as<int32_t>();
     Q.pair_t = c->pair_t.as<int32_t>();
-    Q.tasks = c->tasks.as<int32_t>() + b.chunk_first[chunk] * 64;
-    Q.n_tasks = (int)b.chunk_ntasks[chunk];
+    Q.tasks = c->tasks.as<int32_t>() + (all ? b.chunk_first[0] : b.chunk_first[chunk]) * 64;
+    Q.n_tasks = (int)(all ? b.n_tasks : b.chunk_ntasks[chunk]);
     Q.rev = dir;
     Q.counter = c->counter.as<unsigned int>() + (16 + 8 * dir + (int)chunk);
     Q.tb = tbm ? c->tb[dir].as<uint8_t>() : nullptr;
@@ -845,7 +854,7 @@ int launch_packed_chunk(aadp_ctx* c, int dir, uint32_t what, float delta_ratio, 
     Q.fin_score = c->fin_score[dir].as<int32_t>();
     Q.fin_kind = c->fin_kind[dir].as<int32_t>();
     Q.fin_k = c->fin_k[dir].as<int32_t>();
-    Q.cells_hint = b.chunk_cells[chunk];
+    Q.cells_hint = all ? b.packed_cells : b.chunk_cells[chunk];
     if (launch_packed(c, Q, tbm, fst, msk)) return 1;
   }
   return 0;
@@ -1094,7 +1103,7 @@ aadp_ctx* aadp_create(int device) {
     const int hw = (int)std::max<unsigned>(std::thread::hardware_concurrency(), 1u);
     c->host_threads = std::max(2, std::min(8, hw / ranks));
   }
-  if (const char* e = getenv("AADP_PIPELINE_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(e), 8));
+  if (const char* e = getenv("AADP_PIPELINE_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(e), 7));
   return c;
 }
 
@@ -1367,7 +1376,7 @@ static int set_pairs_impl(aadp_ctx* c, const int32_t* pair_q, const int32_t* pai
   if (upload_vec(c, c->sc_off, b.sc_off)) return 1;
   if (upload_vec(c, c->mask_off, b.mask_off)) return 1;
   // packed task list: at most one task per couple, one unpaired couple per lane width, host range and chunk
-  nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsplit, 8), npairs / 16384));
+  nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsplit, 7), npairs / 16384));
   if (c->tasks.reserve(((size_t)npairs / 2 + (size_t)33 * 8 * nsplit + 64) * 64 * sizeof(int32_t))) return 1;
   for (int k = 0; k < nsplit; ++k) {
     // the first chunk is the smallest: its kernel should start as early as possible
@@ -1874,9 +1883,7 @@ static int run_batch_impl(aadp_ctx* c, uint32_t what, float delta_ratio, float* 
   const int threads = 256;
   const int g1 = (int)std::min<int64_t>((np + threads - 1) / threads, 148 * 8);
   if (what & AADP_W_FWD) {
-    if (!fwd_packed_done)
-      for (size_t k = 0; k < b.chunk_ntasks.size(); ++k)
-        if (launch_packed_chunk(c, 0, what, delta_ratio, d_threshold, d_nearopt_count, k)) return 1;
+    if (!fwd_packed_done && launch_packed_chunk(c, 0, what, delta_ratio, d_threshold, d_nearopt_count, kAllChunks)) return 1;
     if (run_direction_int32(c, 0, what)) return 1;
     if (d_fwd_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[0].as<int32_t>(), d_fwd_score, np, c->sc.scale_log2);
@@ -1885,8 +1892,7 @@ static int run_batch_impl(aadp_ctx* c, uint32_t what, float delta_ratio, float* 
     }
   }
   if (what & AADP_W_REV) {
-    for (size_t k = 0; k < b.chunk_ntasks.size(); ++k)
-      if (launch_packed_chunk(c, 1, what, delta_ratio, d_threshold, d_nearopt_count, k)) return 1;
+    if (launch_packed_chunk(c, 1, what, delta_ratio, d_threshold, d_nearopt_count, kAllChunks)) return 1;
     if (run_direction_int32(c, 1, what)) return 1;
     if (d_rev_score) {
       scores_to_float_kernel<<<g1, threads, 0, c->stream>>>(c->fin_score[1].as<int32_t>(), d_rev_score, np, c->sc.scale_log2);
