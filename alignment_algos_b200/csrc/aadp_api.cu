@@ -2403,9 +2403,16 @@ static int optimal_all_impl(aadp_ctx* c, int direction, int64_t* ali_off, int32_
   Batch& b = c->b;
   if (direction != AADP_FWD && direction != AADP_REV) return fail("bad direction");
   const int dir = direction - 1;
-  if (c->float_mode) return fail("aadp_batch_optimal_all: exact-float mode keeps no packed traceback (use aadp_batch_optimal)");
-  if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
-  if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
+  // exact-float mode keeps no resident traceback: the forward optimal alignments (Optimal::enumerate, optimal.h:47-75) of
+  // the whole batch are produced chunk by chunk -- dense fill with predecessors (record-list kernel), then one thread per
+  // pair follows DPCell::prev_* from the final cell.  Reverse and local tracebacks go through aadp_batch_optimal.
+  const bool float_all = c->float_mode;
+  if (float_all && (dir != 0 || c->sc.local))
+    return fail("aadp_batch_optimal_all: exact-float mode traces forward, non-local alignments only (use aadp_batch_optimal)");
+  if (!float_all) {
+    if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) return fail("that direction was not run");
+    if (!(b.ran_what & AADP_W_TB)) return fail("traceback was not kept (run with AADP_W_TB)");
+  }
   if (c->sc.local && !(b.ran_what & AADP_W_SCORES)) return fail("local tracebacks need AADP_W_SCORES (find_max, optimal.h:107-124)");
   const int64_t np = b.npairs;
   std::vector<int64_t> cap((size_t)np + 1, 0);
@@ -2415,11 +2422,62 @@ static int optimal_all_impl(aadp_ctx* c, int direction, int64_t* ali_off, int32_
   }
   if (ali_off) memcpy(ali_off, cap.data(), (size_t)(np + 1) * 8);
   if (np == 0) return 0;
+  if (!compact_off && !pairs && !n_out && !status) return 0;  // a size query: the offsets are all the caller asked for
   if (!compact_off && pairs && pairs_cap < cap[(size_t)np]) return fail("aadp_batch_optimal_all: pairs buffer too small (needs 2*ali_off[npairs] ints)");
   CK(cudaStreamSynchronize(c->stream));
   if (pin_reserve(c, (size_t)(np + 1) * 8 + 4096)) return 1;
   if (upload_vec(c, c->ali_cap, cap)) return 1;
   if (c->ali_out.reserve((size_t)cap[(size_t)np] * 8) || c->ali_n.reserve((size_t)np * 4) || c->ali_status.reserve((size_t)np * 4)) return 1;
+  if (float_all) {
+    std::vector<int64_t> off;
+    std::vector<int32_t> rects;
+    c->launches = 0;
+    for (int64_t p0 = 0; p0 < np;) {
+      off.assign(1, 0);
+      int64_t p1 = p0;
+      while (p1 < np) {
+        const int qs = b.pair_q[p1], ts = b.pair_t[p1];
+        const int64_t cl = (b.seq_off[qs + 1] - b.seq_off[qs] + 2) * (b.seq_off[ts + 1] - b.seq_off[ts] + 2);
+        if (p1 > p0 && off.back() + cl > c->gg_budget_cells / 4) break;  // scores + two predecessor matrices + links
+        off.push_back(off.back() + cl);
+        ++p1;
+      }
+      const int64_t m = p1 - p0;
+      if (c->gg_fin[0].reserve(std::max<size_t>((size_t)np * 4, 16))) return 1;
+      if (gg_fill(c, p0, m, 1, true, off, c->gg_fin[0].as<float>(), nullptr)) return 1;
+      rects.resize((size_t)m * 4);
+      for (int64_t k = p0; k < p1; ++k) {
+        const int qs = b.pair_q[k], ts = b.pair_t[k];
+        rects[(size_t)(k - p0) * 4] = 0;
+        rects[(size_t)(k - p0) * 4 + 1] = 0;
+        rects[(size_t)(k - p0) * 4 + 2] = (int32_t)(b.seq_off[qs + 1] - b.seq_off[qs]) + 1;
+        rects[(size_t)(k - p0) * 4 + 3] = (int32_t)(b.seq_off[ts + 1] - b.seq_off[ts]) + 1;
+      }
+      CK(cudaStreamSynchronize(c->stream));
+      if (pin_reserve(c, (size_t)m * 16 + 4096)) return 1;
+      if (upload_vec(c, c->gg_rect, rects)) return 1;
+      SubTraceParams S{};
+      S.PQ = c->gg_pq[0].as<int32_t>();
+      S.PT = c->gg_pt[0].as<int32_t>();
+      S.D = c->gg_score[0].as<float>();
+      S.dense_off = c->gg_off.as<int64_t>();
+      S.rects = c->gg_rect.as<int4>();
+      S.cap_off = c->ali_cap.as<int64_t>();
+      S.item0 = (int)p0;
+      S.n = (int)m;
+      S.out = c->ali_out.as<int2>();
+      S.out_n = c->ali_n.as<int32_t>();
+      S.out_status = c->ali_status.as<int32_t>();
+      S.out_score = nullptr;
+      c->prof_begin("subali_trace_kernel", 0);
+      subali_trace_kernel<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(S);
+      c->prof_end();
+      CK(cudaGetLastError());
+      c->launches++;
+      CK(cudaStreamSynchronize(c->stream));  // the next chunk recycles the dense scratch and the pinned pool
+      p0 = p1;
+    }
+  }
   TraceParams T{};
   T.tb = c->tb[dir].as<uint8_t>();
   T.tb_off = c->tb_off.as<int64_t>();
@@ -2436,7 +2494,9 @@ static int optimal_all_impl(aadp_ctx* c, int direction, int64_t* ali_off, int32_
   T.out = c->ali_out.as<int2>();
   T.out_n = c->ali_n.as<int32_t>();
   T.out_status = c->ali_status.as<int32_t>();
-  if (c->sc.local) {  // Optimal[_Rev]::enumerate_local + find_max: one warp per pair
+  if (float_all) {
+    // (traced above)
+  } else if (c->sc.local) {  // Optimal[_Rev]::enumerate_local + find_max: one warp per pair
     LocalTraceParams Q{};
     Q.t = T;
     Q.sc_blob = c->scb[dir].p;
@@ -2455,7 +2515,7 @@ static int optimal_all_impl(aadp_ctx* c, int direction, int64_t* ali_off, int32_
     c->prof_end();
   }
   CK(cudaGetLastError());
-  c->launches = 1;
+  if (!float_all) c->launches = 1;
   c->d2h_bytes = 0;
   if (compact_off) {
     // compact form: only the aligned pairs that exist travel.  The lengths come back first (4 bytes per pair), the host

@@ -266,6 +266,9 @@ int aadp_batch_optimal(aadp_ctx* ctx, int64_t p, int direction, int32_t* pairs, 
  * optimal_rev.h:47-78, for AADP_REV).  Needs a batch run with AADP_W_TB.  Local alignments (align type local): one warp
  * per pair runs find_max + enumerate_local (optimal.h:76-124, optimal_rev.h:79-131) over the stored scores instead
  * (needs AADP_W_SCORES as well); status is always 0 there, as the reference never throws in that mode.
+ * Exact-float scoring (the reference defaults 4.73 / 0.34) keeps no resident traceback: there the forward, non-local
+ * alignments of the whole batch are produced chunk by chunk (dense fill with predecessors, then one walk per pair);
+ * the batch only has to be uploaded (any aadp_fill_batch / aadp_upload_batch).
  *   ali_off  host, npairs+1 (out, may be NULL): slot p is ali_off[p]..ali_off[p+1] = Lq+Lt+2 aligned pairs
  *   pairs    host, 2*ali_off[npairs] ints (may be NULL; pairs_cap = its capacity in aligned pairs): slot p holds
  *            n_out[p] (query_idx, template_idx) pairs front to back, including (0,0) and (last,last)

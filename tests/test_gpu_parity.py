@@ -1293,3 +1293,41 @@ def test_fill_batch_submit_wait_equals_fill_batch(blosum):
         cs[0].fill_batch_wait()
     for c in cs:
         c.close()
+
+
+def test_float_mode_optimal_alignments_of_a_whole_batch(blosum):
+    # aadp_batch_optimal_all[_compact] under the reference's default penalties (exact-float mode: no resident traceback):
+    # chunked dense fills with predecessors + one walk per pair; equal to the per-pair call and to the oracle's
+    # Optimal::enumerate over the literal fill
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(8)
+    seqs = [rng.integers(0, 20, int(L)).astype(np.uint8) for L in rng.integers(1, 160, 60)]
+    seqs[3] = seqs[2][:100].copy()
+    res, off = a.Context.pack(seqs)
+    pq, pt = rng.integers(0, 60, 400).astype(np.int32), rng.integers(0, 60, 400).astype(np.int32)
+    pq[0], pt[0] = 2, 3
+    for at in (po.SEMI_LOCAL, po.GLOBAL):
+        c = a.Context(0)
+        c.set_option("general_budget_mcells", 4)   # several chunks
+        c.set_scoring(M, 4.73, 0.34, at)
+        O = po.Oracle(M, 4.73, 0.34, at)
+        out = c.fill_batch(res, off, pq, pt, a.W_FWD)
+        aoff, pairs, n, st = c.optimal_all(a.FWD, len(pq))
+        coff, cpairs, cn, cst = c.optimal_all_compact(a.FWD, len(pq))
+        assert (st == 0).all() and (cst == 0).all() and np.array_equal(n, cn)
+        for p in range(len(pq)):
+            got = pairs[aoff[p]:aoff[p] + n[p]]
+            assert_matrix_equal("compact", cpairs[coff[p]:coff[p + 1]], got)
+            if p % 16 == 0:
+                q, t = seqs[pq[p]], seqs[pt[p]]
+                rc, one, sc = c.optimal(p, a.FWD, len(q), len(t))
+                assert rc == 0 and sc == out["fwd_score"][p]
+                assert_matrix_equal("per-pair call", got, one)
+                F, fq, ft = O.fill(q, t, po.FWD, True, fast=False)
+                orc, opairs, osc = O.optimal(F, fq, ft, po.FWD)
+                assert orc == 0 and osc == sc
+                assert_matrix_equal("oracle", got, opairs)
+        with pytest.raises(a.AadpError):
+            c.optimal_all(a.REV, len(pq))
+        c.close()
