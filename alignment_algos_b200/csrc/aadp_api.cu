@@ -171,6 +171,7 @@ struct aadp_ctx {
   int gg_threads_cap = 256;  // CTA size limit of the exact general-gap kernel (option "general_threads"): 512 -> 256 measured +12 %
   int ucw_user_limit = 100000, cw_user_limit = 1000000;  // ucw.h:72, cw.h:76
   int gg_prune = 1;  // pruned scans of the exact general-gap kernel (results identical either way)
+  int enum_mask_prune = 1;  // enumeration kernel: prune the deletion scans with the resident near-optimal set
   int gg_records = 1;  // record-list kernel (aadp_frec.cuh) for affine gaps in exact-float mode (results identical either way)
   double x_cells = 0;  // cell updates of the last aadp_cross_run
   // pinned host staging for metadata uploads (bump-allocated per upload)
@@ -1153,6 +1154,7 @@ int aadp_set_option(aadp_ctx* c, const char* key, int value) {
   if (!strcmp(key, "general_threads")) { c->gg_threads_cap = std::max(32, std::min(512, value / 32 * 32)); return 0; }
   if (!strcmp(key, "general_prune")) { c->gg_prune = value ? 1 : 0; return 0; }
   if (!strcmp(key, "general_records")) { c->gg_records = value ? 1 : 0; return 0; }
+  if (!strcmp(key, "enum_mask_prune")) { c->enum_mask_prune = value ? 1 : 0; return 0; }
   // alignment limits of the enumerators (ucw.h:72 hard-codes 100000, cw.h:76 1000000): beyond them the reference
   // forces optimal paths instead of branching; <= 0 restores the reference's value
   if (!strcmp(key, "ucw_user_limit")) { c->ucw_user_limit = value > 0 ? value : 100000; return 0; }
@@ -1880,6 +1882,7 @@ static int run_batch_impl(aadp_ctx* c, uint32_t what, float delta_ratio, float* 
   Batch& b = c->b;
   const int64_t np = b.npairs;
   if (!fwd_packed_done && run_prepare(c, what)) return 1;
+  if (what & AADP_W_MASK) c->last_delta = delta_ratio;  // the delta the resident near-optimal set belongs to
   const int threads = 256;
   const int g1 = (int)std::min<int64_t>((np + threads - 1) / threads, 148 * 8);
   if (what & AADP_W_FWD) {
@@ -2629,6 +2632,11 @@ static int near_optimal_impl(aadp_ctx* c, int cno, const uint8_t* flags, const i
   U.fin_score = c->fin_score[0].as<int32_t>();
   U.tb = (!c->float_mode && (b.ran_what & AADP_W_TB)) ? c->tb[0].as<uint8_t>() : nullptr;
   U.tb_off = c->tb_off.as<int64_t>();
+  // the resident near-optimal set prunes the deletion scans when it was built with the same delta_ratio (option
+  // "enum_mask_prune", default 1)
+  const bool prune = c->enum_mask_prune && !c->float_mode && (b.ran_what & AADP_W_MASK) && delta_ratio == c->last_delta;
+  U.mask = prune ? c->mask.as<uint32_t>() : nullptr;
+  U.mask_off = c->mask_off.as<int64_t>();
   U.subopt = flags ? c->ucw_flags.as<uint8_t>() : nullptr;
   U.subopt_off = flags ? c->ucw_flag_off.as<int64_t>() : nullptr;
   U.frame_plen = c->ucw_plen.as<int32_t>();

@@ -51,6 +51,8 @@ struct UcwParams {
   int st_mode_v1;             // storage of the non-packed pairs: 1 = int16, 2 = int32
   int bias16;                 // bias of the packed int16 domain
   const int32_t* fin_score;   // per pair: D[last][last].score in score units
+  const uint32_t* mask;       // near-optimal cell set of the batch (same delta_ratio), or null: prunes the deletion scans
+  const int64_t* mask_off;    // per pair (32-bit words)
   const uint8_t* tb;          // packed forward traceback blob (the optimal walks of cw.h), or null
   const int64_t* tb_off;
   // exact-float mode (one listed pair per launch): the dense fp32 forward matrix of the general-gap kernel and its
@@ -139,6 +141,8 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
   const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // ucw.h:81-83, cw.h:86-88
   if (lane == 0 && P.threshold) P.threshold[warp] = thr;
 
+  // near-optimal set of this pair as 16-bit slot words (packed layout only: reverse-flow coordinates, diagonal-major)
+  const uint16_t* mkrow = (P.mask && !P.denseF && fmt == 1) ? reinterpret_cast<const uint16_t*>(P.mask + P.mask_off[pair]) : nullptr;
   const int cap = Lq + 2;  // every step lowers the query index: at most Lq+2 aligned pairs
   int2* paths = P.paths + P.path_off[warp];
   int4* stack = P.stack + P.stack_off[warp];
@@ -204,7 +208,61 @@ __global__ void __launch_bounds__(128, 8) ucw_enum_kernel(const UcwParams P) {
       const int ndel = t0 - 2, total = 1 + ndel + (q0 - 2);
       int found = -1, cq = 0, ct = 0;
       float cg = 0.f;
-      for (int base = next; base < total && found < 0; base += 32) {
+      int scan_from = next;
+      if (mkrow && next <= ndel) {
+        // PRUNED deletion scan (packed pairs with a resident near-optimal set of the same delta): a predecessor can
+        // only pass  F[pred] + r - g > thr  if it lies in the set  F + R - sim > thr  (r - g is the score of ONE way to
+        // continue from it, R - sim of the best one; exact on the integer grid).  The set's bits of matrix row q0-1 sit
+        // in one 16-bit word per 16-column slot: lane s fetches slot s, then only the non-empty slots are tested, 16
+        // candidates at a time, in the reference's order (match first, then template positions t0-2 .. 1).
+        const int iq = q0 - 1;
+        const int a_rev = Lq + 1 - iq;                 // reverse-flow row of matrix row iq
+        const int shift = Lt + 2 - t0;                 // candidate index of reverse-flow column bb: idx = bb - shift
+        unsigned m16 = 0;
+        if (lane < L.n) {
+          const unsigned v = mkrow[((int64_t)(a_rev - 1 + lane) * L.n + lane)];  // byte (cc & 1), bit 7 - (cc >> 1)
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            const int idx = 16 * lane + cc + 1 - shift;
+            if (idx >= max(next, 1) && idx <= ndel && ((v >> (8 * (cc & 1) + 7 - (cc >> 1))) & 1u)) m16 |= 1u << cc;
+          }
+        }
+        bool first = true;
+        for (;;) {
+          const unsigned nonempty = __ballot_sync(0xffffffffu, m16 != 0);
+          const bool with_match = first && next == 0;
+          if (!nonempty && !with_match) break;
+          const int sl = nonempty ? __ffs(nonempty) - 1 : 0;
+          const unsigned ms = nonempty ? __shfl_sync(0xffffffffu, m16, sl) : 0u;
+          bool pass = false;
+          int it = 0, idx = 0;
+          float g = 0.f;
+          if (lane < 16) {
+            if ((ms >> lane) & 1u) {
+              idx = 16 * sl + lane + 1 - shift;
+              it = t0 - 1 - idx;
+              g = (P.delfree && t0 == Lt + 1) ? 0.f : pen(t0 - it - 1);
+              pass = __fsub_rn(__fadd_rn(F(iq, it), r), g) > thr;
+            }
+          } else if (lane == 31 && with_match) {  // the match candidate (idx 0) rides along in the first round
+            it = t0 - 1;
+            pass = __fadd_rn(F(iq, it), r) > thr;
+          }
+          first = false;
+          const unsigned pm = __ballot_sync(0xffffffffu, pass);
+          if (pm) {
+            const int src = (pm >> 31) ? 31 : __ffs(pm) - 1;  // the match precedes every deletion
+            found = __shfl_sync(0xffffffffu, idx, src);
+            cq = iq;
+            ct = __shfl_sync(0xffffffffu, it, src);
+            cg = __shfl_sync(0xffffffffu, g, src);
+            break;
+          }
+          if (nonempty && lane == sl) m16 = 0;
+        }
+        scan_from = ndel + 1;  // the insertion candidates follow unpruned
+      }
+      for (int base = max(next, scan_from); base < total && found < 0; base += 32) {
         const int idx = base + lane;
         bool pass = false;
         int iq = 0, it = 0;

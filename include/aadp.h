@@ -78,7 +78,8 @@ int aadp_synchronize(aadp_ctx* ctx);
  * "general_threads" (default 256): CTA size limit of that kernel.  "general_records" (default 1): the record-list
  * kernel for affine gaps in exact-float mode (identical results at a cost per cell that does not grow with the
  * reference's scans; 0 = the scan kernel).  "ucw_user_limit" / "cw_user_limit": alignment limits of the
- * enumerators (<= 0 restores the reference's 100000 / 1000000).                                          */
+ * enumerators (<= 0 restores the reference's 100000 / 1000000).  "enum_mask_prune" (default 1): the enumeration kernel
+ * tests only the deletion candidates that lie in the resident near-optimal set (same delta_ratio; identical results).                                          */
 int aadp_set_option(aadp_ctx* ctx, const char* key, int value);
 
 /* ---- scoring: replaces AASubstitutionEval(AliParams&, SubstitutionMatrix&) (aasubalib.h:14-15)

@@ -1331,3 +1331,48 @@ def test_float_mode_optimal_alignments_of_a_whole_batch(blosum):
         with pytest.raises(a.AadpError):
             c.optimal_all(a.REV, len(pq))
         c.close()
+
+
+def test_enumeration_with_and_without_mask_pruned_scans(blosum):
+    # option "enum_mask_prune" (default 1): with the near-optimal set of the same delta resident, the deletion scans of
+    # the enumeration kernel only test the cells of the set.  Every alignment, score and slot must be what the unpruned
+    # scans give (UCW and the constrained variant, wide and narrow delta, pairs with several thousand near-optimal cells),
+    # and a delta that differs from the resident set's must not be pruned with it.
+    import alignment_algos_b200 as a
+    _, M = blosum
+    rng = np.random.default_rng(21)
+    seqs, pq, pt = [], [], []
+    for k in range(160):
+        L = int(rng.integers(40, 420))
+        sq = rng.integers(0, 20, L).astype(np.uint8)
+        m = sq.copy()
+        m[::5] = rng.integers(0, 20, len(m[::5]))
+        cut = int(rng.integers(5, L - 5))
+        m = np.concatenate([m[:cut], m[cut + int(rng.integers(0, 5)):]])
+        seqs += [sq, m]
+        pq.append(2 * k)
+        pt.append(2 * k + 1)
+    pq, pt = np.array(pq, np.int32), np.array(pt, np.int32)
+    res, off = a.Context.pack(seqs)
+    ids = np.arange(len(pq), dtype=np.int64)
+    what = a.W_FWD | a.W_REV | a.W_TB | a.W_MASK
+
+    def same(x, y):
+        return all(u[0] == v[0] and u[1] == v[1] and len(u[2]) == len(v[2]) and
+                   all(s1 == s2 and np.array_equal(p1, p2) for (s1, p1), (s2, p2) in zip(u[2], v[2])) for u, v in zip(x, y))
+
+    for at in (po.SEMI_LOCAL, po.GLOBAL):
+        c = a.Context(0)
+        c.set_scoring(M, 12, 1, at)
+        for delta in (0.01, 0.05):
+            c.fill_batch(res, off, pq, pt, what, delta)
+            flags = [(rng.random(len(seqs[t]) + 2) < 0.7).astype(np.uint8) for t in pt]
+            got = {}
+            for prune in (1, 0):
+                c.set_option("enum_mask_prune", prune)
+                got[prune] = (c.near_optimal(ids, delta, 48), c.near_optimal(ids, delta, 48, subopt_flags=flags, constrained=True),
+                              c.near_optimal(ids[:40], delta * 2, 48))   # another delta than the resident set's
+            assert sum(len(g[2]) for g in got[1][0]) > 2 * len(ids)
+            for k in range(3):
+                assert same(got[1][k], got[0][k]), (at, delta, k)
+        c.close()
