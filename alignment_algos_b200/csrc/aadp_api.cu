@@ -422,6 +422,8 @@ __global__ void scores_to_float_kernel(const int32_t* fin, float* out, int64_t n
 
 int check_ctx(aadp_ctx* c, bool need_scoring) {
   if (!c) return fail("null context");
+  // between aadp_fill_batch_submit and aadp_fill_batch_wait the context belongs to the batch in flight
+  if (c->pending) return fail("a submitted batch is pending on this context: call aadp_fill_batch_wait first");
   if (need_scoring && !c->have_scoring) return fail("aadp_set_scoring has not been called");
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
@@ -1985,7 +1987,6 @@ static int fill_batch_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* 
                            const int32_t* pair_t, int64_t npairs, uint32_t what, float delta_ratio, float* fwd_score,
                            float* rev_score, float* threshold, int64_t* nearopt_count, bool wait) {
   if (check_ctx(c, true)) return 1;
-  if (c->pending) return fail("a submitted batch is pending on this context: call aadp_fill_batch_wait first");
   if (nseq < 0 || npairs < 0 || npairs > 0x7fffffff) return fail("bad batch size");
   if (!seq_off || (npairs && (!pair_q || !pair_t))) return fail("null input");
   if (seq_off[0] < 0) return fail("sequence offsets must start at a non-negative offset");
@@ -2081,9 +2082,10 @@ int aadp_fill_batch_submit(aadp_ctx* c, const uint8_t* residues, const int64_t* 
 }
 
 int aadp_fill_batch_wait(aadp_ctx* c) {
-  if (check_ctx(c, false)) return 1;
+  if (!c) return fail("null context");
   if (!c->pending) return 0;
   c->pending = false;
+  if (check_ctx(c, false)) return 1;
   CK(cudaStreamSynchronize(c->stream));
   if (c->flag_deferred) {
     c->flag_deferred = false;
