@@ -31,9 +31,6 @@
 #include "aadp_general.cuh"
 #include <type_traits>
 
-#ifndef FREC_EXP_NOWALK
-#define FREC_EXP_NOWALK 0  // timing experiment only (wrong results): never follow a column's record chain
-#endif
 namespace aadp {
 
 // Shared memory per (padded) column: two row buffers, D of the column's two leaders and the third-best key (floats),
@@ -327,7 +324,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
         const float lim = __fsub_rn(key1, mu2);
         float bs = 0.f;
         int bk = 0;
-        if (FREC_EXP_NOWALK || key3 < lim) {  // at most two candidates can win: both are at hand
+        if (key3 < lim) {  // at most two candidates can win: both are at hand
           bk = kk1;
           bs = clampl(__fadd_rn(__fsub_rn(d1, gg_pen(gi, ge, a - kk1 - 1)), simc));
           if (kk2 && key2 >= lim) {
@@ -409,7 +406,7 @@ __global__ void __launch_bounds__(32) frec_fill_kernel(const GeneralParams P, in
           const float key1 = __fadd_rn(d1, __fmul_rn(ge, k1f));  // rows >= 3: the column has a leader
           const float key2 = k2f > 0.f ? __fadd_rn(d2, __fmul_rn(ge, k2f)) : NEGK;
           const float climit = __fsub_rn(key1, mu2);
-          if (rk2 < __fsub_rn(rk1, mu2) && (FREC_EXP_NOWALK || key3 < climit)) {
+          if (rk2 < __fsub_rn(rk1, mu2) && (key3 < climit)) {
             defer = false;
             const float simc = srow_s[tcode[pb]];
             const float dc = cur[pc];  // D[a-1][b-1]: the match predecessor, and the new candidate of column b-1
