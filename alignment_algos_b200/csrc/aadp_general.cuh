@@ -371,17 +371,21 @@ __global__ void __launch_bounds__(256) general_mask_kernel(const GeneralMaskPara
   const float opt = P.fin_fwd[pair];
   const float thr = fminf(__fmul_rn(1.f - P.delta_ratio, opt), __fsub_rn(opt, 0.1f));  // cw.h:86-88
   long long cnt = 0;
-  const int64_t n = (int64_t)(Lq + 2) * sz2;
-  for (int64_t o = threadIdx.x; o < n; o += blockDim.x) {
-    const int i = (int)(o / sz2), j = (int)(o % sz2);
-    uint8_t m = 0;
-    if (i >= 1 && i <= Lq && j >= 1 && j <= Lt) {
-      float v = __fadd_rn(P.F[base + o], P.R[base + o]);
-      v = __fsub_rn(v, P.subf[(int)P.residues[qo + i - 1] * P.A + (int)P.residues[to + j - 1]]);
-      m = v > thr ? 1 : 0;
+  // row by row (no 64-bit division per cell); the border cells of a dense mask stay 0
+  if (P.mask) {
+    for (int j = threadIdx.x; j < sz2; j += blockDim.x) { P.mask[base + j] = 0; P.mask[base + (int64_t)(Lq + 1) * sz2 + j] = 0; }
+    for (int i = 1 + threadIdx.x; i <= Lq; i += blockDim.x) { P.mask[base + (int64_t)i * sz2] = 0; P.mask[base + (int64_t)i * sz2 + Lt + 1] = 0; }
+  }
+  for (int i = 1; i <= Lq; ++i) {
+    const float* subrow = P.subf + (int)P.residues[qo + i - 1] * P.A;
+    const int64_t ro = base + (int64_t)i * sz2;
+    for (int j = 1 + threadIdx.x; j <= Lt; j += blockDim.x) {
+      float v = __fadd_rn(P.F[ro + j], P.R[ro + j]);
+      v = __fsub_rn(v, subrow[(int)P.residues[to + j - 1]]);
+      const int m = v > thr ? 1 : 0;
+      if (P.mask) P.mask[ro + j] = (uint8_t)m;
+      cnt += m;
     }
-    if (P.mask) P.mask[base + o] = m;
-    cnt += m;
   }
   __shared__ long long s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
