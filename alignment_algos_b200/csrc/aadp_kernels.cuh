@@ -881,9 +881,33 @@ __global__ void __launch_bounds__(128) local_traceback_kernel(const LocalTracePa
   int best = INT_MIN;
   int64_t bidx = 0;
   const int64_t ncell = (int64_t)Lq * Lt;
-  for (int64_t i = lane; i < ncell; i += 32) {
-    const int v = score((int)(i / Lt) + 1, (int)(i % Lt) + 1);
-    if (v > best) { best = v; bidx = i; }
+  if (fmt == 1) {
+    // packed pairs: the blob is walked in STORAGE order (diagonal-major, 16-byte chunks of 8 columns: coalesced) instead of
+    // matrix order; "first maximum in ascending flow order" then needs the index in the comparison
+    const int nchunk = (Lq + L.n - 1) * 2 * L.n;
+    const int16_t* sc = (const int16_t*)Q.sc_blob + sco;
+    for (int c = lane; c < nchunk; c += 32) {
+      const int k = c % L.n, rh = c / L.n, h = rh & 1, r = rh >> 1;
+      const int a = r - k + 1;
+      if (a < 1 || a > Lq) continue;
+      const uint4 w = *reinterpret_cast<const uint4*>(sc + (int64_t)c * 8);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      const int b0 = 16 * k + 8 * h - L.sig + 1;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int b = b0 + e;
+        if (b < 1 || b > Lt) continue;
+        const int v = (int)(short)((ww[e >> 1] >> (16 * (e & 1))) & 0xffffu) - bias;
+        const int64_t idx = (int64_t)(a - 1) * Lt + (b - 1);
+        if (v > best || (v == best && idx < bidx)) { best = v; bidx = idx; }
+      }
+    }
+  } else {
+    for (int a = 1; a <= Lq; ++a)  // (row by row: a lane meets its cells in ascending order without a 64-bit division per cell)
+      for (int b = 1 + lane; b <= Lt; b += 32) {
+        const int v = score(a, b);
+        if (v > best) { best = v; bidx = (int64_t)(a - 1) * Lt + (b - 1); }
+      }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
