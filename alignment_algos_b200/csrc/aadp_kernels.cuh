@@ -661,26 +661,31 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
   // few concurrent DRAM streams (two per block), each fully sequential
   const int rows_per_blk = (Lq + gridDim.y - 1) / gridDim.y;
   const int i_lo = 1 + rows_per_blk * blockIdx.y, i_hi = min(Lq, i_lo + rows_per_blk - 1);
+  // Integer form of  (F + R) - sim > thr  (ucw.h:141-180): on the dyadic grid every term is an exact fp32 number, so the
+  // reference's float comparison equals  slack > floor(thr * 2^s)  on the integers (the packed kernels use the same form).
+  const int thr_i = (int)fminf(fmaxf(floorf(thr * (float)(1 << P.sc.scale_log2)), -2.0e9f), 2.0e9f);
+  const uint8_t* tres = P.residues + to;
   for (int i = i_lo; i <= i_hi; ++i) {
     const int qa = P.residues[qo + i - 1];
     const int8_t* subrow = P.sub8 + qa * A;
+    // row pointers: forward row i ascending, reverse row Lq-i descending (the reverse matrix is stored in flow coordinates)
+    const int16_t* f16 = (const int16_t*)P.scF + so + (int64_t)(i - 1) * scs;
+    const int16_t* r16 = (const int16_t*)P.scR + so + (int64_t)(Lq - i) * scs + (Lt - 1);
+    const int32_t* f32 = (const int32_t*)((const int16_t*)P.scF + so) + (int64_t)(i - 1) * scs;
+    const int32_t* r32 = (const int32_t*)((const int16_t*)P.scR + so) + (int64_t)(Lq - i) * scs + (Lt - 1);
+    uint32_t* mrow = mk + (int64_t)(i - 1) * mws;
     // kMaskU*32 columns per iteration: the loads of kMaskU 32-column groups are issued before any of them is used
     for (int j0 = 32 * kMaskU * warp; j0 < Lt; j0 += 32 * kMaskU * nw) {
       bool on[kMaskU];
 #pragma unroll
       for (int u = 0; u < kMaskU; ++u) {
-        const int j = j0 + 32 * u + lane + 1;
+        const int jm = j0 + 32 * u + lane;  // column index - 1
         on[u] = false;
-        if (j <= Lt) {
+        if (jm < Lt) {
           int f, r;
-          const int64_t fo = (int64_t)(i - 1) * scs + (j - 1);
-          const int64_t ro = (int64_t)(Lq - i) * scs + (Lt - j);  // reverse matrix is stored in flow coordinates
-          if (P.st_mode == 1) { f = ((const int16_t*)P.scF)[so + fo]; r = ((const int16_t*)P.scR)[so + ro]; }
-          else { f = ((const int32_t*)((const int16_t*)P.scF + so))[fo]; r = ((const int32_t*)((const int16_t*)P.scR + so))[ro]; }
-          const int sm = subrow[P.residues[to + j - 1]];
-          float v = __fadd_rn((float)f * inv, (float)r * inv);
-          v = __fsub_rn(v, (float)sm * inv);
-          on[u] = v > thr;
+          if (P.st_mode == 1) { f = f16[jm]; r = r16[-jm]; }
+          else { f = f32[jm]; r = r32[-jm]; }
+          on[u] = f + r - (int)subrow[tres[jm]] > thr_i;
         }
       }
       uint32_t mine = 0;
@@ -689,7 +694,7 @@ __global__ void __launch_bounds__(256) mask_kernel(const MaskParams P) {
         const uint32_t bits = __ballot_sync(0xffffffffu, on[u]);
         if (lane == u) mine = bits;
       }
-      if (lane < kMaskU && j0 + 32 * lane < Lt) { mk[(int64_t)(i - 1) * mws + (j0 >> 5) + lane] = mine; cnt += __popc(mine); }
+      if (lane < kMaskU && j0 + 32 * lane < Lt) { mrow[(j0 >> 5) + lane] = mine; cnt += __popc(mine); }
     }
   }
   if (P.count) {
