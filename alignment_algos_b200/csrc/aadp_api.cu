@@ -2105,7 +2105,18 @@ int64_t aadp_batch_resident_bytes(aadp_ctx* c, uint32_t which) {
   if (b.tb_off.empty() || c->float_mode) return 0;
   const int ndir = ((b.ran_what & AADP_W_FWD) ? 1 : 0) + ((b.ran_what & AADP_W_REV) ? 1 : 0);
   if (which == AADP_W_TB) return (b.ran_what & AADP_W_TB) ? b.tb_off[b.npairs] * ndir : 0;
-  if (which == AADP_W_SCORES) return (b.ran_what & (AADP_W_SCORES | AADP_W_MASK)) ? b.sc_off[b.npairs] * 2 * ndir : 0;
+  if (which == AADP_W_SCORES) {
+    // score blobs that are really kept (reserve_direction): both directions with AADP_W_SCORES; with AADP_W_MASK alone the
+    // forward one only -- the packed reverse pass fuses the near-optimal test and writes no scores -- unless int32 /
+    // wavefront pairs need the reverse matrix for their separate mask pass
+    const bool have_v1 = !b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty();
+    int blobs = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+      if (!(b.ran_what & (dir ? AADP_W_REV : AADP_W_FWD))) continue;
+      if ((b.ran_what & AADP_W_SCORES) || ((b.ran_what & AADP_W_MASK) && (dir == 0 || have_v1))) ++blobs;
+    }
+    return b.sc_off[b.npairs] * 2 * blobs;
+  }
   if (which == AADP_W_MASK) return (b.ran_what & AADP_W_MASK) ? b.mask_off[b.npairs] * 4 : 0;
   return 0;
 }
