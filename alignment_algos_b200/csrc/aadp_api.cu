@@ -2035,8 +2035,8 @@ static int fill_batch_impl(aadp_ctx* c, const uint8_t* residues, const int64_t* 
     // the residue validation flag came back long ago (it was queued right after the arena kernel); the int32 and
     // wavefront kernels read the raw residues, so they are only launched on validated input
     g_marks.mark("sched");
-    // the packed kernels read the device-built arenas, in which an invalid code scores as a pad column (harmless garbage
-    // that the flag voids afterwards); only the int32 / wavefront kernels index tables with raw residues
+    // the packed kernels read the device-built arenas, in which arena_kernel has replaced an invalid code by 0 (in-bounds
+    // garbage that the flag voids afterwards); only the int32 / wavefront kernels index tables with raw residues
     const bool raw_readers = !b.order[0].empty() || !b.order[1].empty() || !b.wave_pairs.empty();
     c->flag_deferred = !wait && !raw_readers;
     if (!c->flag_deferred) {
