@@ -1809,7 +1809,14 @@ static int gg_run_batch(aadp_ctx* c, uint32_t what, float delta_ratio, float* d_
   std::vector<int64_t> order((size_t)np);
   std::iota(order.begin(), order.end(), (int64_t)0);
   auto len_t = [&](int64_t p) { const int ts = b.pair_t[p]; return b.seq_off[ts + 1] - b.seq_off[ts]; };
-  if (c->gg_records) std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return len_t(x) > len_t(y); });
+  // (inside a shared-memory class the pairs with the most cells come first: the blocks of a launch start in this order)
+  auto len_q = [&](int64_t p) { const int qs = b.pair_q[p]; return b.seq_off[qs + 1] - b.seq_off[qs]; };
+  if (c->gg_records)
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+      const int64_t cx = (len_t(x) + 63) / 64, cy = (len_t(y) + 63) / 64;
+      if (cx != cy) return cx > cy;
+      return len_q(x) * len_t(x) > len_q(y) * len_t(y);
+    });
   std::vector<int64_t> off;
   for (int64_t p0 = 0; p0 < np;) {
     off.assign(1, 0);
