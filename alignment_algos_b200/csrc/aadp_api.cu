@@ -164,7 +164,7 @@ struct aadp_ctx {
   bool float_mode = false, force_float = false;
   float gi_f = 0.f, ge_f = 0.f;
   float last_delta = -1.f;
-  int64_t gg_budget_cells = 400000000;  // dense cells per direction and chunk of a batch
+  int64_t gg_budget_cells = 1000000000;  // dense cells per direction and chunk of a batch (8-16 B per cell and direction)
   DevBuf ali_cap, ali_out, ali_n, ali_status, gg_rect;
   DevBuf ucw_ids, ucw_path_off, ucw_stack_off, ucw_stack, ucw_paths, ucw_len, ucw_scores, ucw_n, ucw_status, ucw_thr, ucw_plen, ucw_pathbuf, ucw_flags, ucw_flag_off;
   DevBuf subf, gg_score[2], gg_pq[2], gg_pt[2], gg_mask, gg_off, gg_fin[2], gg_pm[2], gg_items, tb_del, tb_ins, tb_del_off, tb_ins_off;

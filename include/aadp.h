@@ -73,7 +73,7 @@ int aadp_synchronize(aadp_ctx* ctx);
  * cell set); 0 forces the int32 kernels.
  * "wave" / "wave_min_cells": multi-CTA wavefront for long pairs.  "host_threads": host scheduler
  * threads (0 = min(hardware, 8)).  "exact_float": see aadp_set_scoring.  "general_budget_mcells":
- * scratch budget (10^6 dense cells per direction) of one chunk of an exact-float batch.  "general_prune" (default 1):
+ * scratch budget (10^6 dense cells per direction, default 1000) of one chunk of an exact-float batch.  "general_prune" (default 1):
  * pruned candidate scans in the exact general-gap kernel (identical results; 0 = scan every candidate).
  * "general_threads" (default 256): CTA size limit of that kernel.  "general_records" (default 1): the record-list
  * kernel for affine gaps in exact-float mode (identical results at a cost per cell that does not grow with the

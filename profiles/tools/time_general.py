@@ -1,5 +1,5 @@
 """Times the exact general-gap fp32 path (reference default scoring 4.73 / 0.34) on a C3-shaped sample.
-usage: time_general.py [pairs] [general_records 0|1] [related 0|1]"""
+usage: time_general.py [pairs] [general_records 0|1] [related 0|1] [general_budget_mcells]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
@@ -22,6 +22,8 @@ if related:  # every template becomes a mutated copy of its query (25 % substitu
 res, off = a.Context.pack(seqs)
 c = a.Context(0)
 c.set_option("general_records", rec)
+if len(sys.argv) > 4:
+    c.set_option("general_budget_mcells", int(sys.argv[4]))
 c.set_scoring(M, 4.73, 0.34, a.SEMI_LOCAL)
 what = a.W_FWD | a.W_REV | a.W_MASK
 c.fill_batch(res, off, pq, pt, what, 0.01)
