@@ -171,6 +171,25 @@ def test_record_list_fill_is_the_literal_fill(golden_float, blosum):
                     cells += st[0]
                     visited += st[1] + st[2]
     assert visited < 4 * cells  # output-sensitive: a few candidates per cell, not a scan
+    # benchmark-sized pairs (C3 shape), related and repetitive: long groups of noise-tied leaders
+    for at, kind in ((po.SEMI_LOCAL, "related"), (po.GLOBAL, "related"), (po.LOCAL, "repeat"), (po.SEMI_LOCAL, "repeat")):
+        O = po.Oracle(M.astype(np.float32), 4.73, 0.34, at)
+        Lq, Lt = 330, 410
+        if kind == "repeat":
+            q = np.resize(rng.integers(0, 20, 3).astype(np.uint8), Lq)
+            t = np.resize(rng.integers(0, 20, 2).astype(np.uint8), Lt)
+        else:
+            q = rng.integers(0, 20, Lq).astype(np.uint8)
+            t = rng.integers(0, 20, Lt).astype(np.uint8)
+            t[20:320] = q[10:310]
+            idx = rng.integers(20, 320, 75)
+            t[idx] = rng.integers(0, 20, len(idx))
+        for d in (po.FWD, po.REV):
+            want = O.fill(q, t, d, True)
+            s_, pq_, pt_, _ = O.fill_rec(q, t, d, True)
+            assert_matrix_equal("rec score (large)", s_, want[0])
+            assert_matrix_equal("rec pq (large)", pq_, want[1])
+            assert_matrix_equal("rec pt (large)", pt_, want[2])
 
 
 def test_oracle_sub_rectangle_fill_matches_golden(golden_sub):
